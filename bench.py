@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py -- the CNC hot path on B200, one JSON line (contract in the task brief / DESIGN.md).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--samples N_s]
+
+Workload (BASELINE.json configs[1], restated in SURVEY 8d "Config 2"): the product field layout
+(F=8; 3D grid 12 levels res 18..514, T=2^19; 3 planes x 4 levels res 130..1026, T=2^17; MLPs
+255->160->80 and 95->160->160->3), random-init weights, +-1-worst-case tables, N_s = 262144 sample
+positions per GPU drawn inside the radius-1 ball of the +-1.5 aabb with unit view directions
+(synthetic; no datasets offline).  A step = one forward pass (sigma + rgb) of the field over the
+batch.  `value` = samples/s with inputs resident in HBM; `e2e` = the same call fed from pinned
+host memory with the rgb/sigma result read back, copies inside the timed span.
+
+`--impl reference` runs the same workload through the reference's own CUDA kernels (compiled
+unmodified into oracle/_ref) driven by the reference's python data flow (oracle/ref_pipeline.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R3 = [18, 24, 33, 44, 59, 80, 108, 148, 201, 275, 376, 514]
+R2 = [130, 258, 514, 1026]
+F = 8
+BYTES_PER_POINT_FWD = 12 + (12 * 8 + 3 * 4 * 4) * 32 + (96 + 96) * 4  # 5388 B/point, SURVEY 8(d)
+FLOP_PER_SAMPLE_FWD = 189760
+
+
+class Clocks:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md 'clocks line')."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.12)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.startswith("Active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def make_inputs(n, seed, device):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    d = torch.randn(n, 3, generator=g)
+    r = torch.rand(n, 1, generator=g) ** (1 / 3)
+    pos = d / d.norm(dim=-1, keepdim=True) * r  # uniform in the radius-1 ball (aabb +-1.5)
+    dirs = torch.randn(n, 3, generator=g)
+    dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+    return pos.float().to(device), dirs.float().to(device)
+
+
+def build_field(device, seed=0):
+    from cnc_b200.field import NGPRadianceField_mygrid_2D3D
+
+    torch.manual_seed(seed)
+    f = NGPRadianceField_mygrid_2D3D(aabb=[-1.5, -1.5, -1.5, 1.5, 1.5, 1.5], n_features_per_level=F, n_neurons=160,
+                                     resolutions_list=R3, log2_hashmap_size=19, resolutions_list_2D=R2,
+                                     log2_hashmap_size_2D=17, ste_binary=True).to(device)
+    with torch.no_grad():  # +-1 with p = 0.5 after STE: worst-case entropy / locality
+        for k in ("xyz", "xy", "xz", "yz"):
+            p = getattr(f.mlp_base, f"encoding_{k}").params
+            p.copy_(torch.where(torch.rand_like(p) < 0.5, -0.5, 0.5))
+    return f
+
+
+def cpu_baseline(n=4096):
+    """oracle port (scalar C + numpy MLP) on one host core over a bounded sample of the workload."""
+    from oracle import oracle as o
+
+    rng = np.random.default_rng(0)
+    x = rng.random((n, 3), dtype=np.float32)
+    offs3, offs2 = o.grid_layout(3, R3, 19), o.grid_layout(2, R2, 17)
+    t3 = np.where(rng.random((offs3[-1], F)) < 0.5, -1, 1).astype(np.float32)
+    t2 = [np.where(rng.random((offs2[-1], F)) < 0.5, -1, 1).astype(np.float32) for _ in range(3)]
+    W = [rng.normal(size=s).astype(np.float32) * 0.05 for s in ((255, 160), (160, 80), (95, 160), (160, 160), (160, 3))]
+    reps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < 10.0:
+        f3 = o.grid_encode_fwd(x, t3, offs3, R3, 12).transpose(1, 0, 2).reshape(n, -1)
+        fs = [o.grid_encode_fwd(np.ascontiguousarray(x[:, ax]), t, offs2, R2, 4).transpose(1, 0, 2).reshape(n, -1)
+              for ax, t in zip(([0, 1], [0, 2], [1, 2]), t2)]
+        h = np.concatenate([f3, *fs, o.freq_embed(x)], 1)
+        h = np.maximum(h @ W[0], 0) @ W[1]
+        g = np.concatenate([o.sh16(x), h[:, 1:]], 1)
+        _ = np.maximum(np.maximum(g @ W[2], 0) @ W[3], 0) @ W[4]
+        reps += 1
+    dt = time.perf_counter() - t0
+    return {"value": reps * n / dt, "unit": "samples/s", "cores": 1, "kind": "port",
+            "sample": f"{reps} x {n} samples of the same layout through oracle/ (C gather + numpy fp32 MLP)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--samples", type=int, default=262144)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    Ns = a.samples
+    field = build_field(dev, seed=0)  # replicas: identical weights on every rank
+    pos, dirs = make_inputs(Ns, seed=1000 + rank, device=dev)  # each rank its own sample shard
+    if a.impl == "reference":
+        from oracle import ref_ext
+        from oracle.ref_pipeline import RefField
+
+        if ref_ext.load("_gridencoder") is None:
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/_gridencoder.so not built"}))
+            return
+        ref = RefField([-1.5, -1.5, -1.5, 1.5, 1.5, 1.5], R3, 19, R2, 17, F, 160).to(dev)
+        ref.load_from(field)
+        model = ref
+    else:
+        model = field
+    model.eval()
+
+    from cnc_b200 import _lib
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    pin_pos, pin_dir = pos.cpu().pin_memory(), dirs.cpu().pin_memory()
+    pin_out = torch.empty(Ns, 4, dtype=torch.float32).pin_memory()
+
+    def step():
+        with torch.no_grad():
+            rgb, sigma = model(pos, dirs)
+        return rgb, sigma
+
+    def step_e2e():
+        with torch.no_grad():
+            p = pin_pos.to(dev, non_blocking=True)
+            d = pin_dir.to(dev, non_blocking=True)
+            rgb, sigma = model(p, d)
+            pin_out.copy_(torch.cat([rgb, sigma], -1), non_blocking=True)
+
+    def timed(fn, K):
+        evs = []
+        for _ in range(K):
+            flush.zero_()  # L2 flush between timed iterations (outside the event-timed span)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+        step_e2e()
+    barrier()
+    l0 = _lib.LAUNCHES
+    with Clocks(local) as clk:
+        ms = timed(step, a.steps)
+    launches = _lib.LAUNCHES - l0
+    barrier()
+    ms_e2e = timed(step_e2e, a.steps)
+    barrier()
+
+    # dominant kernel alone: the 3D grid gather (12 levels x N_s points), CUDA events on its stream
+    enc = model.encoding_xyz if a.impl == "reference" else model.mlp_base.encoding_xyz
+    xn = ((pos + 1.5) / 3.0).contiguous()
+    with torch.no_grad():
+        for _ in range(3):
+            enc(xn)
+        ms_k = timed(lambda: enc(xn), a.steps)
+    bytes_k = Ns * (12 + 12 * 8 * 32 + 96 * 4)  # 3468 B/point, 3D part of SURVEY 8(d)
+
+    t = torch.tensor([ms, ms_e2e, ms_k], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, ms_k = t.tolist()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, which = peaks()
+    ach = bytes_k / (ms_k / a.steps * 1e-3) / 1e9
+    line = {
+        "metric": "ray-samples/sec (encode+MLP)", "value": world * Ns * a.steps / (ms * 1e-3), "unit": "samples/s",
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": a.impl,
+        "config": {"workload": "configs[1]: product field F=8 (3D 12 lvl T=2^19 + 3 planes x 4 lvl T=2^17, MLP "
+                               "255-160-80 / 95-160-160-3), forward sigma+rgb over N_s samples per GPU",
+                   "samples_per_gpu": Ns, "parallelism": f"ray-sharded x{world}, replicas, no data-path collective",
+                   "l2": "flushed between timed iterations (256 MiB write outside the event-timed span)"},
+        "e2e": {"value": world * Ns * a.steps / (ms_e2e * 1e-3), "unit": "samples/s",
+                "h2d_bytes_per_step": int(pin_pos.numel() * 4 + pin_dir.numel() * 4),
+                "d2h_bytes_per_step": int(pin_out.numel() * 4)},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "roofline": {"bound": "hbm", "kernel": "grid_fwd_kernel<3,8> (3D gather, 12 levels)" if a.impl == "ours"
+                     else "kernel_grid<float,3,8> (reference)",
+                     "achieved": ach, "peak": peak, "peak_source": which, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": None, "algorithmic_bytes_per_launch": bytes_k, "ms_per_launch": ms_k / a.steps},
+    }
+    if a.impl == "reference":
+        line["cpu_baseline"] = {"value": line["value"], "unit": "samples/s", "cores": 0, "kind": "reference",
+                                "sample": "reference CUDA kernels (oracle/_ref) + torch fp32 MLP on the GPU: the "
+                                          "reference has no CPU implementation of this path"}
+        line["e2e"]["h2d_bytes_per_step"] = line["e2e"]["h2d_bytes_per_step"]
+    elif world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,91 @@
+"""ctypes loader of libcnc_b200.so -- the only door from Python into the CUDA kernels.
+
+There is no CPU fallback: if the library is missing or a call fails, a RuntimeError is
+raised (the reference raises RuntimeError from TORCH_CHECK / std::runtime_error in the same
+situations, gridencoder.cu:15-18,641,669).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcnc_b200.so")
+_lib = None
+
+_vp, _u32, _i32, _i64, _u64, _f32 = C.c_void_p, C.c_uint32, C.c_int32, C.c_int64, C.c_uint64, C.c_float
+
+# name -> argtypes (every function returns int); must list every symbol of include/cnc_b200.h
+SIGNATURES = {
+    "cnc_grid_encode_fwd": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp],
+    "cnc_grid_encode_bwd": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp],
+    "cnc_grid_encode_fwd_bits": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp],
+    "cnc_ste_binary_fwd": [_vp, _vp, _u64, _vp],
+    "cnc_ste_binary_bwd": [_vp, _vp, _vp, _u64, _vp],
+    "cnc_sign_pack": [_vp, _vp, _u64, _vp],
+    "cnc_sign_unpack": [_vp, _vp, _u64, _vp],
+    "cnc_vote_planes_fwd": [_vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _vp],
+    "cnc_vote_planes_bwd": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _vp],
+    "cnc_query_mask": [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
+    "cnc_align_pack_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _vp],
+    "cnc_align_pack_bwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
+    "cnc_segment_wsum": [_vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "cnc_cdf_from_p": [_vp, _vp, _u64, _vp],
+    "cnc_ac_encode": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "cnc_ac_decode": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "cnc_sh16": [_vp, _vp, _u64, C.c_int, _vp],
+    "cnc_freq_embed": [_vp, _vp, _u64, C.c_int, _vp],
+}
+
+
+def lib():
+    """Load (once) and return the C-ABI library.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"cnc_b200: {LIB_PATH} is missing -- run `python -m cnc_b200.build` "
+                "(there is no CPU or PyTorch fallback for the CUDA path)"
+            )
+        L = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        L.cnc_last_error.restype = C.c_char_p
+        L.cnc_version.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+LAUNCHES = 0  # successful C-ABI compute calls (each launches exactly one kernel)
+
+
+def check(rc: int) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
+    if rc != 0:
+        raise RuntimeError(f"cnc_b200 [{rc}]: {lib().cnc_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    """The current torch CUDA stream handle (the reference launches on the legacy default
+    stream, gridencoder.cu:635; we follow torch's current stream so DP ranks / side streams work)."""
+    return torch.cuda.current_stream().cuda_stream
+
+
+def need_cuda(**tensors):
+    for name, t in tensors.items():
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(f"{name} must be a CUDA tensor")
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} must be a contiguous tensor")

@@ -1,0 +1,161 @@
+// common.cuh -- shared device helpers of libcnc_b200 (sm_100a).
+//
+// The corner logic below is the single source of truth for the CNC grid semantics
+// (SURVEY Appendix A): 1-cell zero border, (res-2) scaling + 0.5 offset, optional
+// occupancy test per corner, weight renormalisation over the valid corners.  It is written
+// with explicit-rounding intrinsics (__fmul_rn / __fadd_rn / __fmaf_rn) so that the sequence
+// of fp32 roundings is fixed by this source and not by the compiler's contraction choices;
+// it reproduces the roundings of the reference kernels (gridencoder.cu:160-291, whose
+// double-literal intermediates all collapse to correctly rounded fp32 operations).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cnc_b200.h"
+
+namespace cnc {
+
+void set_error(const char *fmt, ...);
+int check_launch(const char *what);  // cudaGetLastError -> CNC_ECUDA
+
+__host__ __device__ inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// ---- index: gridencoder.cu:45-87 -----------------------------------------------------------
+template <int D>
+__device__ __forceinline__ uint32_t grid_row(const uint32_t (&c)[D], uint32_t T, uint32_t res) {
+    uint32_t stride = 1, index = 0;
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        if (stride <= T) {
+            index += c[d] * stride;
+            stride *= res;
+        }
+    }
+    if (stride > T) {
+        constexpr uint32_t P[3] = {1u, 2654435761u, 805459861u};
+        index = 0;
+#pragma unroll
+        for (int d = 0; d < D; d++) index ^= c[d] * P[d];
+    }
+    // T is a power of two for every hashed level of the shipped layouts, but dense levels
+    // (and user layouts) are not: keep the generic modulo unless it is a mask.
+    return ((T & (T - 1)) == 0) ? (index & (T - 1)) : (index % T);
+}
+
+// per-level constants, computed once per thread (cheap) ------------------------------------
+struct LevelConst {
+    uint32_t T, res, base_row;
+    float scale;     // float(res-2)
+    float scale_re;  // fl(1/(res-2))  == float(1.0/(double(float(res))-2.0)), gridencoder.cu:224
+};
+
+__device__ __forceinline__ LevelConst load_level(const int32_t *__restrict__ offsets,
+                                                 const int32_t *__restrict__ resolutions,
+                                                 uint32_t level) {
+    LevelConst lc;
+    const uint32_t o0 = (uint32_t)__ldg(offsets + level), o1 = (uint32_t)__ldg(offsets + level + 1);
+    lc.base_row = o0;
+    lc.T = o1 - o0;
+    lc.res = (uint32_t)__ldg(resolutions + level);
+    lc.scale = (float)(lc.res - 2u);
+    lc.scale_re = __frcp_rn(lc.scale);
+    return lc;
+}
+
+// "does the +-1-voxel box around grid vertex c touch an occupied cell" (gridencoder.cu:221-276)
+template <int D>
+__device__ __forceinline__ bool occ_box_any(const uint32_t (&c)[D], float scale_re, uint32_t Rb,
+                                            const uint8_t *__restrict__ vxl) {
+    int lo[D], hi[D];
+    const float fRb = (float)Rb, fRb1 = (float)(Rb - 1u);
+    const float mhalf = __fmul_rn(-0.5f, scale_re);
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        // float((double(c) - 0.5) * double(scale_re)): exact product, one rounding == fma
+        const float pn = __fmaf_rn((float)c[d], scale_re, mhalf);
+        float g1 = __fmul_rn(__fsub_rn(pn, scale_re), fRb);
+        g1 = g1 < 0.f ? 0.f : g1;
+        g1 = g1 > fRb1 ? fRb1 : g1;
+        lo[d] = (int)g1;
+        float g2 = __fmul_rn(__fadd_rn(pn, scale_re), fRb);
+        g2 = g2 < 0.f ? 0.f : g2;
+        g2 = g2 > fRb1 ? fRb1 : g2;
+        hi[d] = (int)g2;
+    }
+    if (D == 1) {
+        for (int a = lo[0]; a <= hi[0]; a++)
+            if (vxl[a]) return true;
+    } else if (D == 2) {
+        for (int a = lo[0]; a <= hi[0]; a++)
+            for (int b = lo[1]; b <= hi[1]; b++)
+                if (vxl[(size_t)a * Rb + b]) return true;
+    } else {
+        for (int a = lo[0]; a <= hi[0]; a++)
+            for (int b = lo[1]; b <= hi[1]; b++) {
+                const uint8_t *row = vxl + ((size_t)a * Rb + b) * Rb;
+                for (int cc = lo[D - 1]; cc <= hi[D - 1]; cc++)
+                    if (row[cc]) return true;
+            }
+    }
+    return false;
+}
+
+template <int D>
+struct Corners {
+    float w[1 << D];       // raw D-linear weights (not yet renormalised)
+    uint32_t row[1 << D];  // row inside the level slab
+    uint32_t valid;        // bit i set <=> corner i contributes
+    float wn_re;           // 1 / sum of valid weights
+};
+
+// returns false if the point lies outside [0,1]^D (forward writes zeros, backward skips)
+template <int D>
+__device__ __forceinline__ bool make_corners(const float (&x)[D], const LevelConst &lc, uint32_t Rb,
+                                             const uint8_t *__restrict__ vxl, Corners<D> &cs) {
+    bool oob = false;
+#pragma unroll
+    for (int d = 0; d < D; d++) oob |= (x[d] < 0.f) | (x[d] > 1.f);  // NaN -> in range, like the ref
+    if (oob) return false;
+    float f[D];
+    uint32_t g[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        const float p = __fadd_rn(__fmul_rn(x[d], lc.scale), 0.5f);  // gridencoder.cu:173
+        const float fl = floorf(p);
+        g[d] = (uint32_t)fl;
+        f[d] = __fsub_rn(p, (float)g[d]);
+    }
+    float wn = 0.f;
+    cs.valid = 0;
+#pragma unroll
+    for (int i = 0; i < (1 << D); i++) {
+        float w = 1.f;
+        uint32_t c[D];
+        bool zero = false;
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            if ((i >> d) & 1) {
+                w = __fmul_rn(w, f[d]);
+                c[d] = min(g[d] + 1u, lc.res - 1u);
+            } else {
+                w = __fmul_rn(w, __fsub_rn(1.f, f[d]));
+                c[d] = g[d];
+            }
+            zero |= (c[d] == 0u) | (c[d] == lc.res - 1u);  // gridencoder.cu:212-219
+        }
+        bool ok = !zero;
+        if (ok && vxl) ok = occ_box_any<D>(c, lc.scale_re, Rb, vxl);
+        cs.w[i] = w;
+        cs.row[i] = 0;
+        if (ok) {
+            cs.row[i] = grid_row<D>(c, lc.T, lc.res);
+            wn = __fadd_rn(wn, w);
+            cs.valid |= 1u << i;
+        }
+    }
+    if (wn == 0.f) wn = 1e-9f;  // float(0.0 + 1e-9), gridencoder.cu:288-290
+    cs.wn_re = __frcp_rn(wn);   // float(1.0 / double(wn)): correctly rounded reciprocal
+    return true;
+}
+
+}  // namespace cnc

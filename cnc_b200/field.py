@@ -1,0 +1,190 @@
+"""Host-side mirror of the reference radiance field (examples/radiance_fields/ngp.py:318-645).
+
+`NGPRadianceField_mygrid_2D3D(aabb, ..., resolutions_list, log2_hashmap_size, resolutions_list_2D,
+log2_hashmap_size_2D, n_features_per_level, n_neurons, ste_binary, ...)` with `.mlp_base`
+(`compose_3D_2D_embed`: encoding_xyz / encoding_xy / encoding_xz / encoding_yz + frequency
+embedding -> Linear-ReLU-Linear), `.mlp_head`, `query_density`, `_query_rgb`, `forward`,
+`update_embedding_params` -- same constructor arguments, attribute names (state_dict keys) and
+call semantics as the reference, so checkpoints and callers are interchangeable.
+
+What is different inside:
+  * tcnn's SphericalHarmonics(degree 4) direction encoding is `cnc_sh16` (fp16-rounded like tcnn);
+  * the 63-d frequency embedding is one kernel instead of 21 (ngp.py:598-599);
+  * the four GridEncoders read 1-bit sign tables (gridencoder.py).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Union
+
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from ._lib import check, lib, ptr, stream
+from .gridencoder import GridEncoder
+
+
+class _TruncExp(Function):
+    """ngp.py:318-334."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        x = ctx.saved_tensors[0]
+        return g * torch.exp(torch.clamp(x, max=15))
+
+
+trunc_exp = _TruncExp.apply
+
+
+def sh16(d01: torch.Tensor, fp16_round: bool = True) -> torch.Tensor:
+    """tcnn SphericalHarmonics degree-4 replacement: d01 = (dir+1)/2 in [0,1] -> [N,16] (no grad)."""
+    d = d01.detach().contiguous().float().view(-1, 3)
+    out = torch.empty(d.shape[0], 16, device=d.device, dtype=torch.float32)
+    check(lib().cnc_sh16(ptr(d), ptr(out), d.shape[0], int(fp16_round), stream()))
+    return out
+
+
+def freq_embed(x: torch.Tensor, n_freq: int = 10) -> torch.Tensor:
+    """Embedder.embed (ngp.py:598-599) for include_input=True, log-sampled 2^0..2^(n_freq-1) (no grad)."""
+    v = x.detach().contiguous().float().view(-1, 3)
+    out = torch.empty(v.shape[0], 3 + 6 * n_freq, device=v.device, dtype=torch.float32)
+    check(lib().cnc_freq_embed(ptr(v), ptr(out), v.shape[0], n_freq, stream()))
+    return out
+
+
+class DirectionEncoding(nn.Module):
+    """Stands in for `tcnn.Encoding(Composite[SphericalHarmonics degree 4])` (ngp.py:412-425)."""
+
+    n_output_dims = 16
+
+    def forward(self, d01):
+        return sh16(d01, fp16_round=True)
+
+
+def get_embedder(multires, i=0):
+    """ngp.py:602-617."""
+    if i == -1:
+        return nn.Identity(), 3
+    return (lambda x: freq_embed(x, multires)), 3 + 6 * multires
+
+
+class compose_3D_2D_embed(nn.Module):
+    """ngp.py:620-645."""
+
+    def __init__(self, encoding_xyz, encoding_xy, encoding_xz, encoding_yz, embed_fn, network, sin_encode=False):
+        super().__init__()
+        self.encoding_xyz = encoding_xyz
+        self.encoding_xy = encoding_xy
+        self.encoding_xz = encoding_xz
+        self.encoding_yz = encoding_yz
+        self.embed_fn = embed_fn
+        self.network = network
+
+    def features(self, x):
+        out_xyz = self.encoding_xyz(x)
+        out_xy = self.encoding_xy(x[..., [0, 1]].contiguous())
+        out_xz = self.encoding_xz(x[..., [0, 2]].contiguous())
+        out_yz = self.encoding_yz(x[..., [1, 2]].contiguous())
+        outs = [out_xyz, out_xy, out_xz, out_yz]
+        if self.embed_fn is not None:
+            outs.append(self.embed_fn(x))
+        return torch.cat(outs, dim=-1)
+
+    def forward(self, x):
+        return self.network(self.features(x))
+
+
+class NGPRadianceField_mygrid_2D3D(nn.Module):
+    """ngp.py:365-566."""
+
+    def __init__(self, aabb: Union[torch.Tensor, List[float]], num_dim: int = 3, use_viewdirs: bool = True,
+                 density_activation: Callable = lambda x: trunc_exp(x - 1), unbounded: bool = False,
+                 geo_feat_dim: int = 15,
+                 resolutions_list=(16, 22, 31, 42, 57, 78, 106, 146, 199, 273, 374, 512), log2_hashmap_size: int = 19,
+                 resolutions_list_2D=(64, 128, 256, 512, 1024), log2_hashmap_size_2D=17,
+                 n_features_per_level=2, n_neurons=64, ste_binary=True, ste_multistep=False, add_noise=False,
+                 Q=10) -> None:
+        super().__init__()
+        if not isinstance(aabb, torch.Tensor):
+            aabb = torch.tensor(aabb, dtype=torch.float32)
+        self.register_buffer("aabb", aabb)
+        self.num_dim = num_dim
+        self.use_viewdirs = use_viewdirs
+        self.density_activation = density_activation
+        self.unbounded = unbounded
+        if unbounded:
+            raise NotImplementedError("contract_to_unisphere (ngp.py:337-361) is not used by the CNC scripts")
+        geo_feat_dim = min(127, max(15, n_features_per_level * 10 - 1))  # ngp.py:398-400
+        self.geo_feat_dim = geo_feat_dim
+        self.resolutions_list = resolutions_list
+        self.log2_hashmap_size = log2_hashmap_size
+        self.resolutions_list_2D = resolutions_list_2D
+        self.log2_hashmap_size_2D = log2_hashmap_size_2D
+        if self.use_viewdirs:
+            self.direction_encoding = DirectionEncoding()
+
+        def enc(D, res, log2T):
+            return GridEncoder(num_dim=D, n_features=n_features_per_level, resolutions_list=res,
+                               log2_hashmap_size=log2T, ste_binary=ste_binary, ste_multistep=ste_multistep,
+                               add_noise=add_noise, Q=Q)
+
+        encoding_xyz = enc(3, resolutions_list, log2_hashmap_size)
+        encoding_xy = enc(2, resolutions_list_2D, log2_hashmap_size_2D)
+        encoding_xz = enc(2, resolutions_list_2D, log2_hashmap_size_2D)
+        encoding_yz = enc(2, resolutions_list_2D, log2_hashmap_size_2D)
+        embed_fn, input_ch = get_embedder(10, 0)
+        in_ch = (encoding_xyz.n_output_dims + encoding_xy.n_output_dims + encoding_xz.n_output_dims +
+                 encoding_yz.n_output_dims + input_ch)
+        network = nn.Sequential(nn.Linear(in_ch, n_neurons), nn.ReLU(inplace=True),
+                                nn.Linear(n_neurons, 1 + self.geo_feat_dim))
+        self.mlp_base = compose_3D_2D_embed(encoding_xyz, encoding_xy, encoding_xz, encoding_yz, embed_fn, network)
+        if self.geo_feat_dim > 0:
+            in_ch = (self.direction_encoding.n_output_dims if self.use_viewdirs else 0) + self.geo_feat_dim
+            self.mlp_head = nn.Sequential(nn.Linear(in_ch, n_neurons), nn.ReLU(inplace=True),
+                                          nn.Linear(n_neurons, n_neurons), nn.ReLU(inplace=True),
+                                          nn.Linear(n_neurons, 3))
+
+    def update_embedding_params(self, params_q_xyz_rec, params_q_xy_rec, params_q_xz_rec, params_q_yz_rec):
+        self.mlp_base.encoding_xyz.params = nn.Parameter(params_q_xyz_rec)
+        self.mlp_base.encoding_xy.params = nn.Parameter(params_q_xy_rec)
+        self.mlp_base.encoding_xz.params = nn.Parameter(params_q_xz_rec)
+        self.mlp_base.encoding_yz.params = nn.Parameter(params_q_yz_rec)
+        print('embedding_params updated!')
+
+    def _normalise(self, x):
+        aabb_min, aabb_max = torch.split(self.aabb, self.num_dim, dim=-1)
+        return (x - aabb_min) / (aabb_max - aabb_min)
+
+    def query_density(self, x, return_feat: bool = False):
+        x = self._normalise(x)
+        selector = ((x > 0.0) & (x < 1.0)).all(dim=-1)
+        x = self.mlp_base(x.view(-1, self.num_dim)).view(list(x.shape[:-1]) + [1 + self.geo_feat_dim]).to(x)
+        density_before_activation, base_mlp_out = torch.split(x, [1, self.geo_feat_dim], dim=-1)
+        density = self.density_activation(density_before_activation) * selector[..., None]
+        if return_feat:
+            return density, base_mlp_out
+        return density
+
+    def _query_rgb(self, dir, embedding, apply_act: bool = True):
+        if self.use_viewdirs:
+            dir = (dir + 1.0) / 2.0
+            d = self.direction_encoding(dir.reshape(-1, dir.shape[-1]))
+            h = torch.cat([d, embedding.reshape(-1, self.geo_feat_dim)], dim=-1)
+        else:
+            h = embedding.reshape(-1, self.geo_feat_dim)
+        rgb = self.mlp_head(h).reshape(list(embedding.shape[:-1]) + [3]).to(embedding)
+        if apply_act:
+            rgb = torch.sigmoid(rgb)
+        return rgb
+
+    def forward(self, positions: torch.Tensor, directions: torch.Tensor = None):
+        if self.use_viewdirs and (directions is not None):
+            assert positions.shape == directions.shape, f"{positions.shape} v.s. {directions.shape}"
+            density, embedding = self.query_density(positions, return_feat=True)
+            rgb = self._query_rgb(directions, embedding=embedding)
+        return rgb, density  # type: ignore

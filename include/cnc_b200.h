@@ -1,0 +1,152 @@
+/*
+ * cnc_b200.h -- C-ABI of libcnc_b200.so: the B200 (sm_100a) implementation of CNC's
+ * data-parallel hot path (hash-grid encode, field MLP, context model, range coder).
+ *
+ * This is the drop-in boundary.  Every entry point takes plain device pointers, sizes and a
+ * CUDA stream (passed as void* == cudaStream_t; NULL = legacy default stream), allocates
+ * nothing the caller can see, keeps no state between calls, and returns an int status:
+ *      0  CNC_OK
+ *     -1  CNC_EINVAL      bad argument (null pointer, size overflow)
+ *     -2  CNC_ENOTSUP     unsupported D / F combination (the reference throws
+ *                         std::runtime_error for the same cases, gridencoder.cu:641,669)
+ *     -3  CNC_ECUDA       a CUDA runtime error; cnc_last_error() has the text
+ * The Python shims in cnc_b200/ map non-zero codes to RuntimeError, like the reference's
+ * TORCH_CHECK / std::runtime_error paths (gridencoder.cu:15-18,764-783).
+ *
+ * Each prototype cites the reference interface it replaces (paths relative to the
+ * reference repo YihangChen-ee/CNC); INTEGRATION.md shows the binding a maintainer would
+ * add on the reference side.
+ */
+#ifndef CNC_B200_H
+#define CNC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNC_OK 0
+#define CNC_EINVAL (-1)
+#define CNC_ENOTSUP (-2)
+#define CNC_ECUDA (-3)
+
+typedef void *cnc_stream_t; /* cudaStream_t */
+
+int cnc_version(void);
+const char *cnc_last_error(void); /* thread-local, valid until the next failing call */
+
+/* ------------------------------------------------------------------------------------------
+ * Hash-grid encode.
+ * replaces: _gridencoder.grid_encode_forward   gridencoder/src/gridencoder.h:12-22,
+ *           gridencoder.cu:752-806 (host), :99-316 (kernel_grid)
+ *   x            [N,D] f32 in [0,1]            table [rows,F] f32
+ *   offsets      [>=L_calc+1] i32 (already sliced by the caller when min_level_id is NULL,
+ *                ngp.py:86-97)                 resolutions [>=L_calc] i32
+ *   out          [L_calc,N,F] f32 (level-major, gridencoder.cu:131)
+ *   binary_vxl   nullable, bool/u8 [Rb]^D occupancy; min_level_id nullable i32 [N]
+ * D in {1,2,3}; F in {1,2,4,8,16,32}.
+ * ---------------------------------------------------------------------------------------- */
+int cnc_grid_encode_fwd(const float *x, const float *table, const int32_t *offsets,
+                        const int32_t *resolutions, float *out, uint32_t N, uint32_t D, uint32_t F,
+                        uint32_t L_calc, uint32_t Rb, const uint8_t *binary_vxl,
+                        const int32_t *min_level_id, cnc_stream_t stream);
+
+/* replaces: _gridencoder.grid_encode_backward  gridencoder.h:24-36, gridencoder.cu:808-866,
+ *           :400-585 (kernel_grid_backward).  grad [L_calc,N,F]; grad_table [rows,F] must arrive
+ *           zeroed (ngp.py:129) and is accumulated into with float atomics. */
+int cnc_grid_encode_bwd(const float *grad, const float *x, const int32_t *offsets,
+                        const int32_t *resolutions, float *grad_table, uint32_t N, uint32_t D,
+                        uint32_t F, uint32_t L_calc, uint32_t Rb, const uint8_t *binary_vxl,
+                        const int32_t *min_level_id, cnc_stream_t stream);
+
+/* Same gather, reading a 1-bit/parameter sign table (bit ch of byte-group row = param >= 0)
+ * produced by cnc_sign_pack; the encoded features are bit-identical to cnc_grid_encode_fwd on
+ * STE_binary(params) because every table value is exactly +-1.  (ngp.py:244-245 + K1) */
+int cnc_grid_encode_fwd_bits(const float *x, const uint8_t *sign_bits, const int32_t *offsets,
+                             const int32_t *resolutions, float *out, uint32_t N, uint32_t D,
+                             uint32_t F, uint32_t L_calc, uint32_t Rb, const uint8_t *binary_vxl,
+                             const int32_t *min_level_id, cnc_stream_t stream);
+
+/* STE_binary (ngp.py:22-39 == utils_bpp_acc.py:164-181).
+ * fwd: out = (clamp(p,-1,1) >= 0) ? +1 : -1.   bwd: gin = gout * (|p| <= 1). */
+int cnc_ste_binary_fwd(const float *params, float *out, uint64_t n, cnc_stream_t stream);
+int cnc_ste_binary_bwd(const float *params, const float *gout, float *gin, uint64_t n,
+                       cnc_stream_t stream);
+/* sign bit-planes: bits[(row*F + ch) / 8] bit ((row*F+ch) % 8) = params[row,ch] >= 0.
+ * n = rows*F must be a multiple of 8 (row counts are, ngp.py:204). */
+int cnc_sign_pack(const float *params, uint8_t *bits, uint64_t n, cnc_stream_t stream);
+int cnc_sign_unpack(const uint8_t *bits, float *out, uint64_t n, cnc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dimension-wise context: 3D -> 2D vote planes.
+ * replaces: _gridencoder.cnt_np_embed / cnt_np_embed_backward   gridencoder.h:39-53,
+ *           gridencoder.cu:873-915, :972-1020
+ *   pts [N,3] i16 voxel coords at `resolution`; table = finest 3D level [T,F] f32;
+ *   out [res-2,res-2,F,2] f32 (+1 votes, -1 votes), accumulated into (caller zeroes).
+ * ---------------------------------------------------------------------------------------- */
+int cnc_vote_planes_fwd(const int16_t *pts, const float *table, float *out, uint32_t N,
+                        uint32_t resolution, uint32_t F, uint32_t hashmap_size, uint32_t axis,
+                        cnc_stream_t stream);
+int cnc_vote_planes_bwd(const int16_t *pts, const float *table, const float *out_sum,
+                        const float *grad, float *grad_table, uint32_t N, uint32_t resolution,
+                        uint32_t F, uint32_t hashmap_size, uint32_t axis, cnc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Occupancy query of voxels.
+ * replaces: pack_and_align.query_mask_3D / query_mask_3D_qlist   my_cuda_backen/aligner.cpp:37-70,
+ *           aligner_kernel.cu:4-80,161-242 (scalar resolution), :82-158,244-326 (per point)
+ *   pts [N,D] i16; binary_vxl bool [Rb]^D; mask [N] i16; overlap [N] i32;
+ *   res_per_point nullable i64 [N] (then `resolution` is ignored); D in {2,3}.
+ * ---------------------------------------------------------------------------------------- */
+int cnc_query_mask(const int16_t *pts, const uint8_t *binary_vxl, int32_t Rb, int16_t *mask,
+                   int32_t *overlap, const int64_t *res_per_point, int32_t resolution, int64_t N,
+                   int32_t D, cnc_stream_t stream);
+
+/* replaces: pack_and_align.align_and_pack_forward / _backward   aligner.cpp:4-35,
+ *           aligner_kernel.cu:413-495, :498-565.  packed [N,M,F]; feat [T,F]; cnt [N] i64;
+ *           cumsum [N+1] i64.  bwd writes every row of dfeat it owns (caller zeroes). */
+int cnc_align_pack_fwd(const float *feat, const int64_t *cnt, const int64_t *cumsum, float *packed,
+                       int64_t N, int64_t M, int64_t F, float V, cnc_stream_t stream);
+int cnc_align_pack_bwd(const float *dpacked, const int64_t *cnt, const int64_t *cumsum,
+                       float *dfeat, int64_t N, int64_t M, int64_t F, cnc_stream_t stream);
+
+/* Segment reduce that makes the padded [N,M,F] tensor unnecessary:
+ * out[i,k] = sum_j w[cumsum[i]+j] * feat[cumsum[i]+j, k]  (w nullable -> plain sum), fixed
+ * left-to-right order per segment (deterministic, GPU-count independent).
+ * replaces the pattern align_and_pack -> mul -> sum(dim=1), utils_bpp_acc.py:842-848,563-566. */
+int cnc_segment_wsum(const float *feat, const float *w, const int64_t *cumsum, float *out,
+                     int64_t N, int64_t F, cnc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Entropy coder (torchac-compatible 32-bit binary range coder).
+ * replaces: encoder()/decoder() -> torchac.encode_float_cdf / decode_float_cdf,
+ *           examples/utils_bpp_acc.py:77-110 (torchac==0.9.3, requirements.txt:32)
+ * cnc_cdf_from_p: c1 = uint16(round((1-p)*65534) + 1)  (the int16 CDF entry torchac builds).
+ * Streams are independent; stream k codes symbols [sym_off[k], sym_off[k+1]) and writes at
+ * out + out_off[k] (capacity out_off[k+1]-out_off[k]); out_len[k] receives the byte count
+ * (if it exceeds the capacity the stream is truncated and the call returns CNC_EINVAL after
+ * completion -- capacity n/8*2+64 bytes is always enough for probabilities in [1e-6,1-1e-6]).
+ * ---------------------------------------------------------------------------------------- */
+int cnc_cdf_from_p(const float *p, uint16_t *c1, uint64_t n, cnc_stream_t stream);
+int cnc_ac_encode(const uint16_t *c1, const uint8_t *sym, const int64_t *sym_off,
+                  uint8_t *out, const int64_t *out_off, int64_t *out_len, int32_t n_streams,
+                  cnc_stream_t stream);
+int cnc_ac_decode(const uint16_t *c1, const int64_t *sym_off, const uint8_t *in,
+                  const int64_t *in_off, const int64_t *in_len, uint8_t *sym, int32_t n_streams,
+                  cnc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-sample field ops.
+ * cnc_sh16 replaces tcnn.Encoding(SphericalHarmonics, degree 4) at ngp.py:412-425,541:
+ *   d01 [n,3] = (dir+1)/2 -> out [n,16] f32; fp16_round != 0 rounds through fp16 like tcnn's output.
+ * cnc_freq_embed replaces Embedder.embed (ngp.py:569-617): out [n, 3+6*n_freq].
+ * ---------------------------------------------------------------------------------------- */
+int cnc_sh16(const float *d01, float *out, uint64_t n, int fp16_round, cnc_stream_t stream);
+int cnc_freq_embed(const float *x, float *out, uint64_t n, int n_freq, cnc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNC_B200_H */
