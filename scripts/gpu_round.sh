@@ -1,0 +1,15 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, bench (both arms), ncu launch list.  Outputs under gpurun_out/.
+set -x
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt
+nproc > gpurun_out/nproc.txt
+python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err
+cat gpurun_out/bench_ours.json; tail -5 gpurun_out/bench_ours.err
+python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+cat gpurun_out/bench_ref.json; tail -5 gpurun_out/bench_ref.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+tail -3 gpurun_out/ncu_bench.log

@@ -384,10 +384,10 @@ def test_grid_encoder_module_matches_oracle(cuda, oracle):
     tab = oracle.ste_binary(enc.params.detach().cpu().numpy())
     offs, res = enc.offsets_list.cpu().numpy(), enc.resolutions_list.cpu().numpy()
     ref = oracle.grid_encode_fwd(x.view(-1, 3).cpu().numpy(), tab, offs, res, 12)  # [L,N,F]
-    np.testing.assert_array_equal(y.view(-1, 12, 8).permute(1, 0, 2).cpu().numpy(), ref)
+    np.testing.assert_array_equal(y.detach().view(-1, 12, 8).permute(1, 0, 2).cpu().numpy(), ref)
     # partial levels + gradient through STE
     y2 = enc(x.view(-1, 3), 3, 6)
-    np.testing.assert_array_equal(y2.view(-1, 3, 8).permute(1, 0, 2).cpu().numpy(), ref[3:6])
+    np.testing.assert_array_equal(y2.detach().view(-1, 3, 8).permute(1, 0, 2).cpu().numpy(), ref[3:6])
     g = torch.randn_like(y2)
     y2.backward(g)
     gref = oracle.grid_encode_bwd(g.view(-1, 3, 8).permute(1, 0, 2).contiguous().cpu().numpy(),
@@ -398,14 +398,14 @@ def test_grid_encoder_module_matches_oracle(cuda, oracle):
     # the sign table follows in-place parameter updates
     with torch.no_grad():
         enc.params.neg_()
-    np.testing.assert_array_equal(enc(x).view(-1, 12, 8).permute(1, 0, 2).cpu().numpy(), -ref)
+    np.testing.assert_array_equal(enc(x).detach().view(-1, 12, 8).permute(1, 0, 2).cpu().numpy(), -ref)
     # per-point levels
     ml = torch.randint(0, 9, (2000,), device=cuda, dtype=torch.int32)
     vx = torch.from_numpy(ball_occupancy(128)).to(cuda)
     y3 = enc.forward_diff_levels(x.view(-1, 3), ml, 3, binary_vxl=vx, PV=1001)
     ref3 = oracle.grid_encode_fwd(x.view(-1, 3).cpu().numpy(), -tab, offs, res, 3, binary_vxl=vx.cpu().numpy(),
                                   min_level_id=ml.cpu().numpy())
-    np.testing.assert_array_equal(y3.view(-1, 3, 8).permute(1, 0, 2).cpu().numpy(), ref3)
+    np.testing.assert_array_equal(y3.detach().view(-1, 3, 8).permute(1, 0, 2).cpu().numpy(), ref3)
     # forward_given_params: single 2D level, raw fp32 table (vote-fraction plane)
     enc2 = GridEncoder(num_dim=2, n_features=8, resolutions_list=R2, log2_hashmap_size=17, ste_binary=True).to(cuda)
     plane = torch.rand(130 * 130, 8, device=cuda)
@@ -414,4 +414,4 @@ def test_grid_encoder_module_matches_oracle(cuda, oracle):
     xy = torch.rand(3000, 2, device=cuda)
     y4 = enc2.forward_given_params(xy, o2, r2, plane)
     ref4 = oracle.grid_encode_fwd(xy.cpu().numpy(), plane.cpu().numpy(), [0, 130 * 130], [130], 1)[0]
-    np.testing.assert_allclose(y4.cpu().numpy(), ref4, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(y4.detach().cpu().numpy(), ref4, rtol=1e-5, atol=1e-7)
