@@ -37,6 +37,9 @@ SIGNATURES = {
     "cnc_ac_decode": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "cnc_sh16": [_vp, _vp, _u64, C.c_int, _vp],
     "cnc_freq_embed": [_vp, _vp, _u64, C.c_int, _vp],
+    "cnc_field_pack_weights": [_vp] * 12,
+    "cnc_field_fwd": [_vp] * 15 + [_u32, _vp],
+    "cnc_field_set_timeline_buffer": [_vp],
 }
 
 
@@ -56,6 +59,7 @@ def lib():
             fn.restype = C.c_int
         L.cnc_last_error.restype = C.c_char_p
         L.cnc_version.restype = C.c_int
+        L.cnc_field_blob_floats.restype = C.c_uint32
         _lib = L
     return _lib
 

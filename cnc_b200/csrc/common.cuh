@@ -120,7 +120,9 @@ __device__ __forceinline__ bool make_corners(const float (&x)[D], const LevelCon
     uint32_t g[D];
 #pragma unroll
     for (int d = 0; d < D; d++) {
-        const float p = __fadd_rn(__fmul_rn(x[d], lc.scale), 0.5f);  // gridencoder.cu:173
+        // gridencoder.cu:173 `x * float(res-2) + 0.5`: nvcc contracts the widened multiply-add of the
+        // reference into a single DFMA, i.e. one rounding of x*s + 0.5 == fmaf (see oracle/cnc_oracle.c)
+        const float p = __fmaf_rn(x[d], lc.scale, 0.5f);
         const float fl = floorf(p);
         g[d] = (uint32_t)fl;
         f[d] = __fsub_rn(p, (float)g[d]);

@@ -1,0 +1,906 @@
+// field_fused.cu -- the radiance field forward as ONE persistent kernel per batch of samples:
+//   hash-grid encode (3D 12 levels + 3 planes x 4 levels, 1-bit sign tables) + 63-d frequency
+//   embedding -> Linear(255,160)+ReLU -> Linear(160,80) -> sigma = exp(h0-1)*selector,
+//   [SH16(dir) | geo79] -> Linear(95,160)+ReLU -> Linear(160,160)+ReLU -> Linear(160,3) -> sigmoid.
+//
+// Reference behaviour restated: examples/radiance_fields/ngp.py:514-566 (query_density, _query_rgb,
+// forward), :620-645 (compose_3D_2D_embed), :569-617 (Embedder), :412-425 (tcnn SH, Appendix C of
+// SURVEY.md).  The reference runs this as 4 gather kernels + ~60 elementwise kernels + 5 cuBLAS
+// SGEMMs with a [N,255] activation round trip through HBM; here the 255-wide activation never
+// leaves the SM.
+//
+// B200 mapping
+//   * persistent grid, one CTA per SM, one tile = 128 samples = one UMMA M tile.
+//   * warps 0-3 (128 threads, thread t <-> sample row t <-> TMEM lane t): gather + interpolate the
+//     features of a 32-column K chunk, split every value into tf32 hi + lo, store both into a
+//     128B-swizzled K-major smem slot (double buffered); later the layer epilogues
+//     (tcgen05.ld -> bias/ReLU -> hi/lo split -> tcgen05.st) that turn an accumulator into the
+//     next layer's A operand *inside TMEM*.
+//   * warp 4, one elected lane: streams the pre-split, pre-swizzled weight chunks with
+//     cp.async.bulk (TMA bulk copy, mbarrier complete_tx) through a 4-stage smem ring and issues
+//     tcgen05.mma kind::tf32 (M=128, N=160/80/16, K=8).  fp32 parity comes from the 3xTF32
+//     error-compensated split  A*B ~= Ahi*Blo + Alo*Bhi + Ahi*Bhi  with fp32 accumulation in TMEM.
+//   * TMEM (512 columns) is recycled layer to layer:
+//       L1 acc [0,160) -> h1 hi in place, lo [160,320);  L2 acc [320,400);
+//       head input hi [0,96), lo [96,192);  L3 acc [192,352) -> hi in place, lo [352,512);
+//       L4 acc [0,160) -> hi in place, lo [160,320);  L5 acc [320,336).
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace cnc {
+namespace ff {
+
+constexpr int TILE_M = 128;
+constexpr int NSTAGE = 4;
+constexpr uint32_t STAGE_BYTES = 2u * 160u * 128u;  // hi + lo of a [160 x 32] fp32 chunk (or two [80 x 32] chunks)
+constexpr uint32_t A_HALF = 128u * 128u;            // one [128 x 32] fp32 chunk
+constexpr uint32_t A_SLOT_BYTES = 2u * A_HALF;
+constexpr uint32_t SMEM_B = 0;
+constexpr uint32_t SMEM_A = NSTAGE * STAGE_BYTES;            // 163840
+constexpr uint32_t SMEM_BAR = SMEM_A + 2 * A_SLOT_BYTES;     // 229376
+constexpr uint32_t SMEM_LVL = SMEM_BAR + 128;                // 16 x LevelTab (32 B)
+constexpr uint32_t SMEM_W5 = SMEM_LVL + 16 * 32;             // W5 [3][160] + b5 [3] (+pad) fp32
+constexpr uint32_t SMEM_DYN = SMEM_W5 + 484 * 4;             // 231968 <= 232448
+
+// weight stream of one tile (stage loads): L1 8 x [160x32], L2 [80x64] [80x64] [80x32], L3 3 x [160x32], L4 5 x [160x32]
+constexpr int CPT_FULL = 19, CPT_DENSITY = 11;
+constexpr uint32_t BLOB_W_FLOATS = 189440;
+constexpr uint32_t BLOB_W5 = BLOB_W_FLOATS;  // raw fp32 W5 [3][160]: the last layer runs as FFMA in the L4 epilogue
+constexpr uint32_t BIAS1 = BLOB_W5 + 480, BIAS2 = BIAS1 + 160, BIAS3 = BIAS2 + 80, BIAS4 = BIAS3 + 160,
+                   BIAS5 = BIAS4 + 160;
+constexpr uint32_t BLOB_FLOATS = BIAS5 + 16;  // 190496
+
+__host__ __device__ __forceinline__ void chunk_meta(int g, uint32_t &ofs, uint32_t &bytes) {
+    if (g < 8) { bytes = 40960; ofs = (uint32_t)g * 40960u; }                               // L1
+    else if (g < 11) { bytes = g < 10 ? 40960u : 20480u; ofs = 327680u + (uint32_t)(g - 8) * 40960u; }  // L2
+    else if (g < 14) { bytes = 40960; ofs = 430080u + (uint32_t)(g - 11) * 40960u; }        // L3
+    else { bytes = 40960; ofs = 552960u + (uint32_t)(g - 14) * 40960u; }                    // L4
+}
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: 8-row groups of 1024 B (SBO), rows of 128 B.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFFu);       // start address
+    d |= (uint64_t)1u << 16;                      // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024u >> 4) << 32;            // stride byte offset
+    d |= (uint64_t)1u << 46;                      // descriptor version (sm_100)
+    d |= (uint64_t)2u << 61;                      // SWIZZLE_128B
+    return d;
+}
+template <int N>
+__device__ __forceinline__ constexpr uint32_t idesc_tf32() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+// The async ops of the MMA warp are executed by the whole (converged) warp with the leader election inside the
+// asm block: the C++ around them stays warp-uniform straight-line code, so every operand is born in a uniform
+// register (an `if (elect)` region makes ptxas shuttle each operand through R2UR + a uniformisation loop,
+// ~100 cycles per MMA).  elect.sync picks the same leader every time, which tcgen05.commit relies on.
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xFFFFFFFF;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xFFFFFFFF;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xFFFFFFFF;\n\t"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_elect(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xFFFFFFFF;\n\t"
+                 "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+                 "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+
+// tf32 hi/lo split, 2 + 3 integer/fp ops: hi = v rounded to 10 mantissa bits (nearest, ties away: add half
+// an ulp to the magnitude, clear the low 13 bits), lo = (v - hi) rounded the same way.  v = hi + lo + O(2^-22 v).
+// (cvt.rna.tf32.f32 does the same but ptxas expands it to a ~10-instruction NaN/Inf-safe sequence.)
+__device__ __forceinline__ uint32_t rna_tf32(float v) { return (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u; }
+__device__ __forceinline__ void split_tf32(float v, uint32_t &hi, uint32_t &lo) {
+    hi = rna_tf32(v);
+    lo = __float_as_uint(__fsub_rn(v, __uint_as_float(hi)));  // |lo| <= 2^-12 |v|; the MMA truncates it to tf32 (2^-23 |v|)
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing: nn.Linear weights -> blob of pre-split, pre-swizzled K chunks + biases
+// ------------------------------------------------------------------------------------------
+struct PackArgs {
+    const float *W[5];
+    const float *b[5];
+};
+
+// head input K order: k=0 <- SH0, k=1..79 <- geo0..78, k=80..94 <- SH1..15, k=95 <- pad
+__device__ __forceinline__ int head_src_col(int k) {
+    if (k == 0) return 0;
+    if (k < 80) return 15 + k;  // geo j = k-1 sits at column 16 + j of cat[SH16, geo]
+    if (k < 95) return k - 79;  // SH 1..15
+    return -1;
+}
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(PackArgs a, float *__restrict__ blob) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= BLOB_FLOATS) return;
+    if (i >= BLOB_W_FLOATS) {
+        const uint32_t j = i - BLOB_W_FLOATS;
+        float v;
+        if (j < 480) v = a.W[4][j];  // Linear(160,3) weight, [3][160] row-major, unsplit
+        else if (j < 640) v = a.b[0][j - 480];
+        else if (j < 720) v = a.b[1][j - 640];
+        else if (j < 880) v = a.b[2][j - 720];
+        else if (j < 1040) v = a.b[3][j - 880];
+        else v = (j - 1040 < 3) ? a.b[4][j - 1040] : 0.f;
+        blob[i] = v;
+        return;
+    }
+    // which layer / chunk
+    const uint32_t byte = i * 4u;
+    int layer, kc, N;
+    uint32_t in_chunk;
+    if (byte < 327680u) { layer = 0; N = 160; kc = byte / 40960u; in_chunk = byte % 40960u; }
+    else if (byte < 430080u) { layer = 1; N = 80; kc = (byte - 327680u) / 20480u; in_chunk = (byte - 327680u) % 20480u; }
+    else if (byte < 552960u) { layer = 2; N = 160; kc = (byte - 430080u) / 40960u; in_chunk = (byte - 430080u) % 40960u; }
+    else { layer = 3; N = 160; kc = (byte - 552960u) / 40960u; in_chunk = (byte - 552960u) % 40960u; }
+    const uint32_t half_bytes = (uint32_t)N * 128u;
+    const bool is_lo = in_chunk >= half_bytes;
+    const uint32_t p = is_lo ? in_chunk - half_bytes : in_chunk;
+    const uint32_t r = (p % 1024u) / 128u, n = (p / 1024u) * 8u + r;
+    const uint32_t c16 = ((p % 128u) / 16u) ^ r;  // undo the 128B swizzle
+    const int k = kc * 32 + (int)(c16 * 4u + (p % 16u) / 4u);
+    float v = 0.f;
+    switch (layer) {
+        case 0: if (k < 255) v = a.W[0][n * 255 + k]; break;                       // Linear(255,160)
+        case 1: v = a.W[1][n * 160 + k]; break;                                    // Linear(160,80)
+        case 2: { const int c = head_src_col(k); if (c >= 0) v = a.W[2][n * 95 + c]; } break;  // Linear(95,160)
+        default: v = a.W[3][n * 160 + k]; break;                                   // Linear(160,160)
+    }
+    uint32_t hi, lo;
+    split_tf32(v, hi, lo);
+    blob[i] = __uint_as_float(is_lo ? lo : hi);
+}
+
+// ------------------------------------------------------------------------------------------
+// fused forward
+// ------------------------------------------------------------------------------------------
+struct FieldArgs {
+    const float *pos;   // [N,3] world
+    const float *dirs;  // [N,3] unit view directions (nullptr -> density only)
+    float aabb[6];
+    const uint8_t *bits3, *bits_xy, *bits_xz, *bits_yz;
+    const int32_t *offs3, *res3, *offs2, *res2;  // 12+1 / 12 and 4+1 / 4 entries
+    const float *blob;
+    float *sigma;  // [N]
+    float *rgb;    // [N,3]   (nullptr in density-only mode)
+    float *geo;    // [N,79]  nullable
+    uint32_t N;
+    unsigned long long *dbg;  // optional timeline buffer (cnc_field_set_timeline_buffer), see DESIGN.md
+};
+
+// Per-level constants, built once per CTA in shared memory (12 levels of the 3D grid, then 4 of the planes).
+struct LevelTab {
+    uint32_t base_row, res, mask, hashed;  // hashed: 1 -> row = (c0 ^ c1*P1 ^ c2*P2) & mask, 0 -> dense c0 + c1*res + c2*res^2
+    float scale, scale_re;                 // float(res-2), 1/float(res-2)
+    uint32_t res2, T;
+};
+
+__device__ __forceinline__ void make_level_tab(const int32_t *__restrict__ offs, const int32_t *__restrict__ res, int level,
+                                               int D, LevelTab &L) {
+    const LevelConst lc = load_level(offs, res, (uint32_t)level);
+    L.base_row = lc.base_row; L.res = lc.res; L.T = lc.T; L.scale = lc.scale; L.scale_re = lc.scale_re;
+    L.res2 = lc.res * lc.res;
+    // gridencoder.cu:63-87: the index is dense while the running stride stays <= T, hashed otherwise
+    uint64_t stride = 1;
+    for (int d = 0; d < D; d++) stride = stride <= lc.T ? stride * lc.res : (uint64_t)1 << 40;
+    L.hashed = stride > lc.T ? 1u : 0u;
+    L.mask = ((lc.T & (lc.T - 1u)) == 0u) ? lc.T - 1u : 0u;  // 0: T is not a power of two -> generic modulo
+}
+
+// One level of one encoder for one sample, split in two halves so that the table loads of chunk c+1 are
+// in flight while chunk c is accumulated and stored.  Float arithmetic is the one of make_corners
+// (common.cuh); the integer side factors the index into per-dimension terms, which is what makes the
+// gather cheap enough to hide behind the MMAs (the generic kernel spends ~400 instructions per level on it).
+struct Pend {
+    float ww[8];      // renormalised corner weights w_i / sum(w); 0 for corners that do not contribute (+-0 adds are exact)
+    uint32_t sb[8];   // sign bytes of the corner rows (bit k = feature k >= 0)
+};
+
+template <int D>
+__device__ __forceinline__ void gather_issue(const float (&x)[D], const uint8_t *__restrict__ bits, const LevelTab &L,
+                                             Pend &p) {
+    constexpr uint32_t P1 = 2654435761u, P2 = 805459861u;
+    bool inb = true;
+    uint32_t t[D][2];   // per-dimension index term of the low / high cell
+    float wd[D][2];     // per-dimension weight of the low / high cell
+    bool z[D][2];       // low / high cell lies on the zero border (gridencoder.cu:212-219)
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        inb = inb && !(x[d] < 0.f) && !(x[d] > 1.f);
+        const float pos = __fmaf_rn(x[d], L.scale, 0.5f);
+        const uint32_t g = (uint32_t)floorf(pos);
+        const float f = __fsub_rn(pos, (float)g);
+        const uint32_t c0 = g, c1 = min(g + 1u, L.res - 1u);
+        wd[d][0] = __fsub_rn(1.f, f);
+        wd[d][1] = f;
+        z[d][0] = (c0 == 0u) || (c0 == L.res - 1u);
+        z[d][1] = (c1 == 0u) || (c1 == L.res - 1u);
+        const uint32_t m = d == 0 ? 1u : (L.hashed ? (d == 1 ? P1 : P2) : (d == 1 ? L.res : L.res2));
+        t[d][0] = c0 * m;
+        t[d][1] = c1 * m;
+    }
+    float w[1 << D];
+    uint32_t valid = 0;
+    float wn = 0.f;
+#pragma unroll
+    for (int i = 0; i < (1 << D); i++) {
+        float wi = wd[0][i & 1];
+        bool zi = z[0][i & 1];
+        uint32_t row = t[0][i & 1];
+#pragma unroll
+        for (int d = 1; d < D; d++) {
+            wi = __fmul_rn(wi, wd[d][(i >> d) & 1]);
+            zi = zi || z[d][(i >> d) & 1];
+            row = L.hashed ? (row ^ t[d][(i >> d) & 1]) : (row + t[d][(i >> d) & 1]);
+        }
+        if (L.hashed) row = L.mask ? (row & L.mask) : (row % L.T);
+        w[i] = wi;
+        const bool on = inb && !zi;
+        if (on) {
+            wn = __fadd_rn(wn, wi);
+            valid |= 1u << i;
+        }
+        p.sb[i] = on ? (uint32_t)__ldg(bits + L.base_row + row) : 0u;
+    }
+    if (wn == 0.f) wn = 1e-9f;
+    const float wn_re = __frcp_rn(wn);
+#pragma unroll
+    for (int i = 0; i < (1 << D); i++) p.ww[i] = ((valid >> i) & 1u) ? __fmul_rn(w[i], wn_re) : 0.f;
+}
+
+template <int NC>
+__device__ __forceinline__ void gather_finish(const Pend &p, float (&f)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) f[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) f[k] = __fadd_rn(f[k], ((p.sb[i] >> k) & 1u) ? p.ww[i] : -p.ww[i]);
+    }
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// store 8 feature values (columns 8q..8q+7 of a 32-column chunk) of row r into the swizzled A slot
+__device__ __forceinline__ void store_oct(uint8_t *slot, int r, int q, const float (&f)[8]) {
+    uint8_t *rowp = slot + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        uint4 hi, lo;
+        split_tf32(f[4 * j + 0], hi.x, lo.x);
+        split_tf32(f[4 * j + 1], hi.y, lo.y);
+        split_tf32(f[4 * j + 2], hi.z, lo.z);
+        split_tf32(f[4 * j + 3], hi.w, lo.w);
+        const int phys = ((2 * q + j) ^ (r & 7)) << 4;
+        *reinterpret_cast<uint4 *>(rowp + phys) = hi;
+        *reinterpret_cast<uint4 *>(rowp + A_HALF + phys) = lo;
+    }
+}
+
+__device__ __forceinline__ void sh16_eval_h(float x, float y, float z, float (&o)[16]) {
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    o[0] = 0.28209479177387814f;
+    o[1] = -0.48860251190291987f * y;
+    o[2] = 0.48860251190291987f * z;
+    o[3] = -0.48860251190291987f * x;
+    o[4] = 1.0925484305920792f * xy;
+    o[5] = -1.0925484305920792f * yz;
+    o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+    o[7] = -1.0925484305920792f * xz;
+    o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+    o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+    o[10] = 2.8906114426405538f * xy * z;
+    o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+    o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+    o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+    o[14] = 1.4453057213202769f * z * (x2 - y2);
+    o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+#pragma unroll
+    for (int k = 0; k < 16; k++) o[k] = __half2float(__float2half_rn(o[k]));  // tcnn emits fp16
+}
+
+// timeline probe: CTA 0, its second tile; slots 0..31 = compute thread 0, 32..63 = MMA lane
+#define CNC_TL(slot) do { if (a.dbg != nullptr && blockIdx.x == 0 && it == 1) a.dbg[slot] = clock64(); } while (0)
+
+constexpr uint32_t NONE = 0xFFFFu;
+
+// 8 accumulator columns (block b8) of this thread's TMEM lane: main (+ main2) (+ small), summed in fp32 (RN)
+template <uint32_t MAIN2, uint32_t SMALL>
+__device__ __forceinline__ void acc_block(uint32_t tl, uint32_t c_main, int b8, float (&v)[8]) {
+    uint32_t m[8], m2[8], sm[8];
+    tmem_ld8(tl + c_main + 8 * b8, m);
+    if (MAIN2 != NONE) tmem_ld8(tl + MAIN2 + 8 * b8, m2);
+    if (SMALL != NONE) tmem_ld8(tl + SMALL + 8 * b8, sm);
+    tc_wait_ld();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        float x = __uint_as_float(m[k]);
+        if (MAIN2 != NONE) x = __fadd_rn(x, __uint_as_float(m2[k]));
+        if (SMALL != NONE) x = __fadd_rn(x, __uint_as_float(sm[k]));
+        v[k] = x;
+    }
+}
+
+// hidden-layer epilogue (160 columns = 20 blocks of 8, this thread's column group takes every 4th):
+// (+bias, ReLU, split) -> hi at dst_hi, lo at dst_lo
+template <uint32_t MAIN2, uint32_t SMALL>
+__device__ __forceinline__ void ep_hidden(uint32_t tl, int cg, uint32_t c_main, uint32_t dst_hi, uint32_t dst_lo,
+                                          const float *__restrict__ bias) {
+#pragma unroll 1
+    for (int b = cg; b < 20; b += 4) {
+        float v[8];
+        uint32_t hi[8], lo[8];
+        acc_block<MAIN2, SMALL>(tl, c_main, b, v);
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + 8 * b)), b1 = __ldg(reinterpret_cast<const float4 *>(bias + 8 * b) + 1);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++) split_tf32(fmaxf(__fadd_rn(v[k], bb[k]), 0.f), hi[k], lo[k]);
+        tmem_st8(tl + dst_hi + 8 * b, hi);
+        tmem_st8(tl + dst_lo + 8 * b, lo);
+    }
+    tc_wait_st();
+}
+
+constexpr int NCOMPUTE = 512;              // 16 gather/epilogue warps
+constexpr int NTHREADS = NCOMPUTE + 32;    // + the MMA / weight-stream warp
+
+template <bool DENSITY_ONLY>
+__global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5;
+    constexpr int CPT = DENSITY_ONLY ? CPT_DENSITY : CPT_FULL;
+    constexpr int MMA_WARP = NCOMPUTE / 32;
+
+    // barriers
+    const uint32_t bar0 = sbase + SMEM_BAR;
+    auto b_full = [&](uint32_t s) { return bar0 + 8u * s; };
+    auto b_empty = [&](uint32_t s) { return bar0 + 8u * (NSTAGE + s); };
+    auto a_full = [&](uint32_t s) { return bar0 + 8u * (2 * NSTAGE + s); };
+    auto a_empty = [&](uint32_t s) { return bar0 + 8u * (2 * NSTAGE + 2 + s); };
+    const uint32_t layer_done = bar0 + 8u * (2 * NSTAGE + 4);
+    const uint32_t act_ready = bar0 + 8u * (2 * NSTAGE + 5);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SMEM_BAR + 8 * (2 * NSTAGE + 6));
+    LevelTab *lvl = reinterpret_cast<LevelTab *>(smem + SMEM_LVL);
+    float *w5s = reinterpret_cast<float *>(smem + SMEM_W5);
+
+    if (threadIdx.x == 0) {
+        if (sbase & 1023u) __trap();  // the 128B-swizzled operand tiles need a 1024-byte aligned base
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(a_full(s), NCOMPUTE); mbar_init(a_empty(s), 1); }
+        mbar_init(layer_done, 1);
+        mbar_init(act_ready, NCOMPUTE);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 16) {
+        if (threadIdx.x < 12) make_level_tab(a.offs3, a.res3, threadIdx.x, 3, lvl[threadIdx.x]);
+        else make_level_tab(a.offs2, a.res2, threadIdx.x - 12, 2, lvl[threadIdx.x]);
+    }
+    for (int i = threadIdx.x; i < 484; i += NTHREADS) w5s[i] = i < 480 ? __ldg(a.blob + BLOB_W5 + i) : (i < 483 ? __ldg(a.blob + BIAS5 + (i - 480)) : 0.f);
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // This CTA owns the whole SM (227 KB of shared memory) and asks for all 512 columns, so the allocation
+    // starts at lane 0 / column 0.  Using the constant keeps every MMA operand in uniform registers.
+    if (*tmem_slot != 0u) __trap();
+    constexpr uint32_t tbase = 0u;
+
+    const uint32_t ntiles = (a.N + TILE_M - 1) / TILE_M;
+    const uint32_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == MMA_WARP) {
+        // =============================== weight stream + MMA issue ===============================
+        // The whole warp runs this control flow (all values warp-uniform -> uniform datapath); one elected
+        // lane issues the copies, MMAs and commits.
+        const uint8_t *blob = reinterpret_cast<const uint8_t *>(a.blob);
+        const uint32_t total = my_tiles * CPT;
+        uint32_t Gc = 0, Gm = 0, a_cons = 0, act_cnt = 0;
+        auto issue_copy = [&]() {
+            const uint32_t s = Gc % NSTAGE, use = Gc / NSTAGE;
+            if (use > 0) mbar_wait(b_empty(s), (use - 1) & 1u);
+            uint32_t ofs, bytes;
+            chunk_meta((int)(Gc % CPT), ofs, bytes);
+            bulk_g2s_elect(sbase + SMEM_B + s * STAGE_BYTES, blob + ofs, bytes, b_full(s));
+            Gc++;
+        };
+        // two stage loads ahead of the chunk being issued: the refill after chunk g targets the stage of
+        // chunk g-2, whose MMAs have normally retired -> issue never waits on the chunk just queued
+        for (int i = 0; i < NSTAGE - 2 && Gc < total; i++) issue_copy();
+
+        // One stage load = NATOM K-atoms (32 columns = 4 k-steps of 8) of a layer with N output columns.
+        // The two small products (Ahi*Blo, Alo*Bhi) go to their own accumulator d_small when the layer has
+        // one, so the round-toward-zero of the tensor-core accumulate acts on them at their own 2^-11 scale.
+        // bar1 / bar2: extra mbarriers (0 = none) that the completion of these MMAs arrives on.
+        auto chunk_mma = [&](auto n_tag, auto smem_tag, int natom, uint32_t a_hi, uint32_t a_lo, uint32_t d_main,
+                             bool first_main, uint32_t d_small, bool first_small, uint32_t bar1, uint32_t bar2) {
+            constexpr int N = decltype(n_tag)::value;
+            constexpr bool A_IN_SMEM = decltype(smem_tag)::value;
+            const uint32_t s = Gm % NSTAGE;
+            mbar_wait(b_full(s), (Gm / NSTAGE) & 1u);
+            tc_fence_after();
+            const uint32_t bst = sbase + SMEM_B + s * STAGE_BYTES;
+            constexpr uint32_t id = idesc_tf32<N>();
+            const bool shared_acc = (d_small == d_main);
+            for (int at = 0; at < natom; at++) {
+                const uint64_t dbh0 = smem_desc(bst + (uint32_t)at * (2u * N * 128u)),
+                               dbl0 = smem_desc(bst + (uint32_t)at * (2u * N * 128u) + (uint32_t)N * 128u);
+                const uint64_t dah0 = A_IN_SMEM ? smem_desc(a_hi) : 0ull, dal0 = A_IN_SMEM ? smem_desc(a_lo) : 0ull;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; k4++) {
+                    // +32 bytes along K inside the 128-byte swizzle row == +2 in the descriptor's address field.
+                    // Consecutive MMAs alternate accumulators (small, main, small) so that the accumulate
+                    // latency of one overlaps the next.
+                    const uint64_t dbh = dbh0 + (uint64_t)(2 * k4), dbl = dbl0 + (uint64_t)(2 * k4);
+                    const bool head = (at == 0 && k4 == 0);
+                    const uint32_t acc_s = (first_small && head) ? 0u : 1u;
+                    const uint32_t acc_m = shared_acc ? 1u : ((first_main && head) ? 0u : 1u);
+                    if (A_IN_SMEM) {
+                        const uint64_t dah = dah0 + (uint64_t)(2 * k4), dal = dal0 + (uint64_t)(2 * k4);
+                        mma_ss(tbase + d_small, dah, dbl, id, acc_s);
+                        mma_ss(tbase + d_main, dah, dbh, id, acc_m);
+                        mma_ss(tbase + d_small, dal, dbh, id, 1u);
+                    } else {
+                        const uint32_t ah = tbase + a_hi + 32u * at + 8u * k4, al = tbase + a_lo + 32u * at + 8u * k4;
+                        mma_ts(tbase + d_small, ah, dbl, id, acc_s);
+                        mma_ts(tbase + d_main, ah, dbh, id, acc_m);
+                        mma_ts(tbase + d_small, al, dbh, id, 1u);
+                    }
+                }
+            }
+            tc_commit_elect(b_empty(s));
+            if (bar1) tc_commit_elect(bar1);
+            if (bar2) tc_commit_elect(bar2);
+            Gm++;
+            if (Gc < total) issue_copy();
+        };
+        using N160 = std::integral_constant<int, 160>;
+        using N80 = std::integral_constant<int, 80>;
+        using FromSmem = std::true_type;
+        using FromTmem = std::false_type;
+
+        for (uint32_t it = 0; it < my_tiles; it++) {
+            // L1: A from smem slots; main [0,160) (even chunks) / [160,320) (odd chunks), small [320,480)
+#pragma unroll 1
+            for (int kc = 0; kc < 8; kc++) {
+                const uint32_t sl = a_cons & 1u;
+                mbar_wait(a_full(sl), (a_cons >> 1) & 1u);
+                const uint32_t ab = sbase + SMEM_A + sl * A_SLOT_BYTES;
+                if (elect_one()) CNC_TL(32 + kc);
+                chunk_mma(N160{}, FromSmem{}, 1, ab, ab + A_HALF, (kc & 1) ? 160u : 0u, kc < 2, 320u, kc == 0, a_empty(sl),
+                          kc == 7 ? layer_done : 0u);
+                a_cons++;
+            }
+            if (elect_one()) CNC_TL(40);
+            // L2: A = h1 hi [0,160) lo [160,320) -> main [320,400), small [400,480); K = 64 + 64 + 32
+            mbar_wait(act_ready, act_cnt & 1u); act_cnt++;
+            tc_fence_after();
+            if (elect_one()) CNC_TL(41);
+#pragma unroll 1
+            for (int j = 0; j < 3; j++)
+                chunk_mma(N80{}, FromTmem{}, j < 2 ? 2 : 1, 64u * j, 160u + 64u * j, 320u, j == 0, 400u, j == 0,
+                          j == 2 ? layer_done : 0u, 0u);
+            if (elect_one()) CNC_TL(42);
+            if (!DENSITY_ONLY) {
+                // L3: A = head input hi [0,96) lo [96,192) -> main [192,352), small [352,512)
+                mbar_wait(act_ready, act_cnt & 1u); act_cnt++;
+                tc_fence_after();
+                if (elect_one()) CNC_TL(43);
+#pragma unroll 1
+                for (int kc = 0; kc < 3; kc++)
+                    chunk_mma(N160{}, FromTmem{}, 1, 32u * kc, 96u + 32u * kc, 192u, kc == 0, 352u, kc == 0,
+                              kc == 2 ? layer_done : 0u, 0u);
+                // L4: A hi [192,352) lo [352,512) -> [0,160) (no room for a second accumulator)
+                mbar_wait(act_ready, act_cnt & 1u); act_cnt++;
+                tc_fence_after();
+                if (elect_one()) CNC_TL(44);
+#pragma unroll 1
+                for (int kc = 0; kc < 5; kc++)
+                    chunk_mma(N160{}, FromTmem{}, 1, 192u + 32u * kc, 352u + 32u * kc, 0u, false, 0u, kc == 0,
+                              kc == 4 ? layer_done : 0u, 0u);
+                if (elect_one()) CNC_TL(45);
+            }
+            // The next tile's first feature chunks are usually already waiting in smem, and its L1 overwrites
+            // the accumulators the last epilogue of this tile is still reading: wait until it has read them.
+            mbar_wait(act_ready, act_cnt & 1u); act_cnt++;
+            tc_fence_after();
+            if (elect_one()) CNC_TL(46);
+        }
+    } else {
+        // =============================== gather / epilogue warps ===============================
+        const int r = threadIdx.x & 127;   // row in tile == TMEM lane; (warp & 3) is the lane quarter this warp may touch
+        const int q = threadIdx.x >> 7;    // feature stage: which 8 of a chunk's 32 columns; epilogues: column group
+        const uint32_t tl = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t a_prod = 0, done_cnt = 0;
+        const float *bias = a.blob;
+        const float3 amin = make_float3(a.aabb[0], a.aabb[1], a.aabb[2]);
+        const float3 ainv = make_float3(__fsub_rn(a.aabb[3], a.aabb[0]), __fsub_rn(a.aabb[4], a.aabb[1]), __fsub_rn(a.aabb[5], a.aabb[2]));
+
+        // normalised position of this thread's row in tile `tile` (ngp.py:517-518)
+        auto load_x = [&](uint32_t tile, float (&x)[3]) {
+            const uint32_t row = tile * TILE_M + r;
+            const bool live = row < a.N;
+            const float px = live ? __ldg(a.pos + (size_t)row * 3 + 0) : __fadd_rn(amin.x, 0.5f * ainv.x);
+            const float py = live ? __ldg(a.pos + (size_t)row * 3 + 1) : __fadd_rn(amin.y, 0.5f * ainv.y);
+            const float pz = live ? __ldg(a.pos + (size_t)row * 3 + 2) : __fadd_rn(amin.z, 0.5f * ainv.z);
+            x[0] = __fdiv_rn(__fsub_rn(px, amin.x), ainv.x);
+            x[1] = __fdiv_rn(__fsub_rn(py, amin.y), ainv.y);
+            x[2] = __fdiv_rn(__fsub_rn(pz, amin.z), ainv.z);
+        };
+        // chunk c of the layer-1 input: [xyz 96 | xy 32 | xz 32 | yz 32 | x, sin/cos 63 | pad]; this thread: columns 8q..8q+7
+        auto issue = [&](int c, const float (&x)[3], Pend &p) {   // table loads of chunk c (c < 6)
+            if (c < 3) {
+                gather_issue<3>(x, a.bits3, lvl[4 * c + q], p);
+            } else {
+                const float x2[2] = {c == 5 ? x[1] : x[0], c == 3 ? x[1] : x[2]};
+                const uint8_t *bt = c == 3 ? a.bits_xy : (c == 4 ? a.bits_xz : a.bits_yz);
+                gather_issue<2>(x2, bt, lvl[12 + q], p);
+            }
+        };
+        auto publish = [&](const float (&f)[8]) {  // 8 feature values -> smem slot -> MMA warp
+            const uint32_t sl = a_prod & 1u, use = a_prod >> 1;
+            if (use > 0) mbar_wait(a_empty(sl), (use - 1) & 1u);
+            store_oct(smem + SMEM_A + sl * A_SLOT_BYTES, r, q, f);
+            fence_async_smem();
+            mbar_arrive(a_full(sl));
+            a_prod++;
+        };
+        auto finish = [&](int c, const Pend &p) {  // gathered chunk c (c < 6)
+            float f[8];
+            if (c < 3) gather_finish<8>(p, f);
+            else gather_finish<4>(p, f);
+            publish(f);
+        };
+        auto embed = [&](int c, const float (&x)[3]) {  // chunks 6, 7
+            // embed column j (0..62): j<3 -> x[j]; else g=(j-3)/3, d=(j-3)%3: even g -> sin(2^(g/2) x_d), odd -> cos
+            float f[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                const int j = (c - 6) * 32 + 8 * q + jj;
+                float v = 0.f;
+                if (j < 3) v = x[j];
+                else if (j < 63) {
+                    const int g = (j - 3) / 3, d = (j - 3) - 3 * g;
+                    const float xd = d == 0 ? x[0] : (d == 1 ? x[1] : x[2]);
+                    const float ang = __fmul_rn(xd, (float)(1 << (g >> 1)));
+                    v = (g & 1) ? cosf(ang) : sinf(ang);
+                }
+                f[jj] = v;
+            }
+            publish(f);
+        };
+
+        float x[3], xn[3];
+        Pend pa, pb;
+        int c0 = 0;  // chunks of the current tile that were already produced during the previous tile's layer chain
+        if (my_tiles > 0) {
+            load_x(blockIdx.x, x);
+            issue(0, x, pa);
+        }
+        for (uint32_t it = 0; it < my_tiles; it++) {
+            const uint32_t tile = blockIdx.x + it * gridDim.x;
+            const uint32_t row = tile * TILE_M + r;
+            const bool live = row < a.N;
+            const bool sel = (x[0] > 0.f) && (x[0] < 1.f) && (x[1] > 0.f) && (x[1] < 1.f) && (x[2] > 0.f) && (x[2] < 1.f);
+            const bool has_next = it + 1 < my_tiles;
+            if (threadIdx.x == 0) CNC_TL(0);
+            // ---- L1 feature chunks c0..7; pa holds the gather of chunk c
+#pragma unroll 1
+            for (int c = c0; c < 6; c += 2) {
+                issue(c + 1, x, pb);
+                finish(c, pa);
+                if (threadIdx.x == 0) CNC_TL(1 + c);
+                if (c + 2 < 6) issue(c + 2, x, pa);
+                finish(c + 1, pb);
+                if (threadIdx.x == 0) CNC_TL(2 + c);
+            }
+#pragma unroll 1
+            for (int c = 6; c < 8; c++) {
+                embed(c, x);
+                if (threadIdx.x == 0) CNC_TL(1 + c);
+            }
+            c0 = 0;
+            if (has_next) {
+                load_x(tile + gridDim.x, xn);
+                issue(0, xn, pa);  // in flight during the L1 tail and ep1
+            }
+            // ---- ep1: h1 = relu(acc1 + b1) -> hi in place [0,160), lo [160,320)
+            if (threadIdx.x == 0) CNC_TL(9);
+            mbar_wait(layer_done, done_cnt & 1u); done_cnt++;
+            tc_fence_after();
+            if (threadIdx.x == 0) CNC_TL(10);
+            ep_hidden<160u, 320u>(tl, q, 0u, 0u, 160u, bias + BIAS1);
+            tc_fence_before();
+            mbar_arrive(act_ready);
+            if (threadIdx.x == 0) CNC_TL(11);
+            if (has_next) {  // while L2 runs: chunk 0 of the next tile
+                issue(1, xn, pb);
+                finish(0, pa);
+            }
+            // ---- ep2: acc2 [320,400)+[400,480): col 0 -> sigma, cols 1..79 -> geo -> head input (+ SH16 block)
+            mbar_wait(layer_done, done_cnt & 1u); done_cnt++;
+            tc_fence_after();
+            if (threadIdx.x == 0) CNC_TL(12);
+#pragma unroll 1
+            for (int b = q; b < 12; b += 4) {
+                uint32_t hi[8], lo[8];
+                if (b < 10) {
+                    float v[8];
+                    acc_block<NONE, 400u>(tl, 320u, b, v);
+                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + BIAS2 + 8 * b)),
+                                 b1 = __ldg(reinterpret_cast<const float4 *>(bias + BIAS2 + 8 * b) + 1);
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        float h = __fadd_rn(v[k], bb[k]);
+                        if (k == 0 && b == 0) {
+                            // density = trunc_exp(h0 - 1) * selector   (ngp.py:528-532, :318-334)
+                            const float sg = __fmul_rn(expf(__fsub_rn(h, 1.0f)), sel ? 1.f : 0.f);
+                            if (live) a.sigma[row] = sg;
+                            h = 0.28198242f;  // SH band 0 (0.28209479 rounded to fp16) takes head-input column 0
+                        } else if (a.geo != nullptr && live) {
+                            a.geo[(size_t)row * 79 + (8 * b + k - 1)] = h;
+                        }
+                        split_tf32(h, hi[k], lo[k]);
+                    }
+                    if (!DENSITY_ONLY) {
+                        tmem_st8(tl + 0u + 8 * b, hi);
+                        tmem_st8(tl + 96u + 8 * b, lo);
+                    }
+                } else if (!DENSITY_ONLY) {
+                    // head-input columns 80..87 (b == 10) / 88..95 (b == 11): SH bands 1..8 / 9..15, pad
+                    float d3[3], sh[16];
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        const float dv = live ? __ldg(a.dirs + (size_t)row * 3 + d) : 0.f;
+                        const float d01 = __fdiv_rn(__fadd_rn(dv, 1.0f), 2.0f);  // ngp.py:540
+                        d3[d] = __fsub_rn(__fmul_rn(d01, 2.f), 1.f);             // tcnn maps back to [-1,1]
+                    }
+                    sh16_eval_h(d3[0], d3[1], d3[2], sh);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const float v = (b == 10) ? sh[1 + k] : (k < 7 ? sh[9 + k] : 0.f);
+                        split_tf32(v, hi[k], lo[k]);
+                    }
+                    tmem_st8(tl + 8u * b, hi);
+                    tmem_st8(tl + 96u + 8u * b, lo);
+                }
+            }
+            if (!DENSITY_ONLY) {
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(act_ready);
+                if (threadIdx.x == 0) CNC_TL(13);
+                // ---- ep3: [192,352)+[352,512) -> hi in place, lo over the small accumulator
+                mbar_wait(layer_done, done_cnt & 1u); done_cnt++;
+                tc_fence_after();
+                if (threadIdx.x == 0) CNC_TL(14);
+                ep_hidden<NONE, 352u>(tl, q, 192u, 192u, 352u, bias + BIAS3);
+                tc_fence_before();
+                mbar_arrive(act_ready);
+                if (threadIdx.x == 0) CNC_TL(15);
+                if (has_next) {  // while L4 (the longest of the small layers) runs: chunk 1 of the next tile
+                    issue(2, xn, pa);
+                    finish(1, pb);
+                    c0 = 2;
+                }
+                // ---- ep4 + the last layer: h4 = relu(acc4 + b4) stays in registers; Linear(160,3) is 3 x 40 FFMA per
+                // thread on its own columns (W5 broadcast from smem), the four column groups of a row meet in TMEM
+                mbar_wait(layer_done, done_cnt & 1u); done_cnt++;
+                tc_fence_after();
+                if (threadIdx.x == 0) CNC_TL(16);
+                float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll 1
+                for (int b = q; b < 20; b += 4) {
+                    float v[8];
+                    acc_block<NONE, NONE>(tl, 0u, b, v);
+                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + BIAS4 + 8 * b)),
+                                 b1 = __ldg(reinterpret_cast<const float4 *>(bias + BIAS4 + 8 * b) + 1);
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    const float4 *w0 = reinterpret_cast<const float4 *>(w5s + 8 * b), *w1 = reinterpret_cast<const float4 *>(w5s + 160 + 8 * b),
+                                 *w2 = reinterpret_cast<const float4 *>(w5s + 320 + 8 * b);
+                    const float4 wa0 = w0[0], wb0 = w0[1], wa1 = w1[0], wb1 = w1[1], wa2 = w2[0], wb2 = w2[1];
+                    const float W0[8] = {wa0.x, wa0.y, wa0.z, wa0.w, wb0.x, wb0.y, wb0.z, wb0.w};
+                    const float W1[8] = {wa1.x, wa1.y, wa1.z, wa1.w, wb1.x, wb1.y, wb1.z, wb1.w};
+                    const float W2[8] = {wa2.x, wa2.y, wa2.z, wa2.w, wb2.x, wb2.y, wb2.z, wb2.w};
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const float h = fmaxf(__fadd_rn(v[k], bb[k]), 0.f);
+                        p0 = __fmaf_rn(h, W0[k], p0);
+                        p1 = __fmaf_rn(h, W1[k], p1);
+                        p2 = __fmaf_rn(h, W2[k], p2);
+                    }
+                }
+                tmem_st4(tl + 480u + 4u * q, __float_as_uint(p0), __float_as_uint(p1), __float_as_uint(p2), 0u);
+                tc_wait_st();
+                tc_fence_before();
+                asm volatile("bar.sync 1, %0;" ::"n"(NCOMPUTE) : "memory");
+                tc_fence_after();
+                if (q == 0) {
+                    uint32_t e[16];
+                    tmem_ld16(tl + 480u, e);
+                    tc_wait_ld();
+                    if (live) {
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            float h = __fadd_rn(__uint_as_float(e[k]), __uint_as_float(e[4 + k]));
+                            h = __fadd_rn(h, __uint_as_float(e[8 + k]));
+                            h = __fadd_rn(h, __uint_as_float(e[12 + k]));
+                            h = __fadd_rn(h, w5s[480 + k]);
+                            a.rgb[(size_t)row * 3 + k] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-h)));  // torch.sigmoid
+                        }
+                    }
+                }
+            }
+            if (threadIdx.x == 0) CNC_TL(19);
+            tc_fence_before();
+            mbar_arrive(act_ready);  // this tile's accumulators are consumed: the next tile's L1 may overwrite them
+            if (has_next) {
+                if (DENSITY_ONLY) { issue(2, xn, pa); finish(1, pb); c0 = 2; }
+                x[0] = xn[0]; x[1] = xn[1]; x[2] = xn[2];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace ff
+}  // namespace cnc
+
+using namespace cnc;
+
+static unsigned long long *g_timeline = nullptr;
+
+extern "C" {
+
+/* debug facility: device buffer of 64 uint64 that CTA 0 fills with clock64() stamps of its second tile */
+int cnc_field_set_timeline_buffer(uint64_t *device_buf) { g_timeline = reinterpret_cast<unsigned long long *>(device_buf); return CNC_OK; }
+
+uint32_t cnc_field_blob_floats(void) { return ff::BLOB_FLOATS; }
+
+int cnc_field_pack_weights(const float *W1, const float *b1, const float *W2, const float *b2, const float *W3,
+                           const float *b3, const float *W4, const float *b4, const float *W5, const float *b5,
+                           float *blob, cnc_stream_t stream) {
+    if (!W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !W4 || !b4 || !W5 || !b5 || !blob) {
+        set_error("field_pack_weights: null pointer");
+        return CNC_EINVAL;
+    }
+    if (reinterpret_cast<uintptr_t>(blob) & 15u) { set_error("field_pack_weights: blob must be 16-byte aligned"); return CNC_EINVAL; }
+    ff::PackArgs a{{W1, W2, W3, W4, W5}, {b1, b2, b3, b4, b5}};
+    ff::pack_weights_kernel<<<div_up(ff::BLOB_FLOATS, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, blob);
+    return check_launch("field_pack_weights");
+}
+
+int cnc_field_fwd(const float *pos, const float *dirs, const float *aabb6_host, const uint8_t *bits_xyz,
+                  const uint8_t *bits_xy, const uint8_t *bits_xz, const uint8_t *bits_yz, const int32_t *offsets3,
+                  const int32_t *resolutions3, const int32_t *offsets2, const int32_t *resolutions2,
+                  const float *blob, float *sigma, float *rgb, float *geo, uint32_t N, cnc_stream_t stream) {
+    if (N == 0) return CNC_OK;
+    if (!pos || !aabb6_host || !bits_xyz || !bits_xy || !bits_xz || !bits_yz || !offsets3 || !resolutions3 ||
+        !offsets2 || !resolutions2 || !blob || !sigma || (dirs && !rgb)) {
+        set_error("field_fwd: null pointer");
+        return CNC_EINVAL;
+    }
+    if (reinterpret_cast<uintptr_t>(blob) & 15u) { set_error("field_fwd: blob must be 16-byte aligned"); return CNC_EINVAL; }
+    static int n_sm = 0;
+    static bool attr_set = false;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!attr_set) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e1 = cudaFuncSetAttribute(ff::field_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::SMEM_DYN);
+        cudaError_t e2 = cudaFuncSetAttribute(ff::field_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::SMEM_DYN);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            set_error("field_fwd: cannot reserve %u bytes of shared memory (%s)", ff::SMEM_DYN,
+                      cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+            return CNC_ECUDA;
+        }
+        attr_set = true;
+    }
+    ff::FieldArgs a;
+    a.pos = pos; a.dirs = dirs;
+    for (int i = 0; i < 6; i++) a.aabb[i] = aabb6_host[i];
+    a.bits3 = bits_xyz; a.bits_xy = bits_xy; a.bits_xz = bits_xz; a.bits_yz = bits_yz;
+    a.offs3 = offsets3; a.res3 = resolutions3; a.offs2 = offsets2; a.res2 = resolutions2;
+    a.blob = blob; a.sigma = sigma; a.rgb = rgb; a.geo = geo; a.N = N; a.dbg = g_timeline;
+    const uint32_t ntiles = (N + ff::TILE_M - 1) / ff::TILE_M;
+    const uint32_t grid = ntiles < (uint32_t)n_sm ? ntiles : (uint32_t)n_sm;
+    if (dirs) ff::field_fwd_kernel<false><<<grid, ff::NTHREADS, ff::SMEM_DYN, s>>>(a);
+    else ff::field_fwd_kernel<true><<<grid, ff::NTHREADS, ff::SMEM_DYN, s>>>(a);
+    return check_launch("field_fwd");
+}
+
+}  // extern "C"

@@ -16,6 +16,8 @@ from __future__ import annotations
 
 from typing import Callable, List, Union
 
+import ctypes
+
 import torch
 import torch.nn as nn
 from torch.autograd import Function
@@ -149,6 +151,57 @@ class NGPRadianceField_mygrid_2D3D(nn.Module):
                                           nn.Linear(n_neurons, n_neurons), nn.ReLU(inplace=True),
                                           nn.Linear(n_neurons, 3))
 
+    # ---- fused forward (cnc_field_fwd): encode + both MLPs in one persistent tcgen05 kernel ----------
+    def fused_available(self) -> bool:
+        """True for the product layout the fused kernel is specialised for (train_CNC_*.py:138-186)."""
+        mb = self.mlp_base
+        encs = (mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz)
+        return (self.use_viewdirs and self.geo_feat_dim == 79 and mb.embed_fn is not None
+                and all(e.ste_binary and e.n_features == 8 for e in encs)
+                and encs[0].n_levels == 12 and all(e.n_levels == 4 for e in encs[1:])
+                and mb.network[0].weight.shape == (160, 255) and mb.network[2].weight.shape == (80, 160)
+                and self.mlp_head[0].weight.shape == (160, 95) and self.mlp_head[2].weight.shape == (160, 160)
+                and self.mlp_head[4].weight.shape == (3, 160) and self.aabb.is_cuda)
+
+    def _fused_blob(self):
+        lins = (self.mlp_base.network[0], self.mlp_base.network[2], self.mlp_head[0], self.mlp_head[2], self.mlp_head[4])
+        ps = [t for l in lins for t in (l.weight, l.bias)]
+        key = tuple((t.data_ptr(), t._version) for t in ps)
+        if getattr(self, "_blob_key", None) != key:
+            blob = getattr(self, "_blob", None)
+            if blob is None or blob.device != ps[0].device:
+                blob = torch.empty(lib().cnc_field_blob_floats(), dtype=torch.float32, device=ps[0].device)
+            check(lib().cnc_field_pack_weights(*[ptr(t.detach().contiguous()) for t in ps], ptr(blob), stream()))
+            self._blob, self._blob_key = blob, key
+        return self._blob
+
+    def fused_forward(self, positions, directions=None, return_feat=False):
+        """(rgb [...,3] | None, density [...,1], geo [...,79] | None) without autograd: the whole of
+        ngp.py:514-566 in one kernel launch.  Raises RuntimeError for layouts it is not built for."""
+        if not self.fused_available():
+            raise RuntimeError("cnc_field_fwd is specialised for the CNC product layout (F=8, 12+3x4 levels, 160 neurons)")
+        mb = self.mlp_base
+        pos = positions.detach().reshape(-1, 3).contiguous().float()
+        n = pos.shape[0]
+        dirs = None if directions is None else directions.detach().reshape(-1, 3).contiguous().float()
+        if getattr(self, "_aabb_host", None) is None or self._aabb_src != (self.aabb.data_ptr(), self.aabb._version):
+            self._aabb_host = (ctypes.c_float * 6)(*self.aabb.detach().cpu().tolist())
+            self._aabb_src = (self.aabb.data_ptr(), self.aabb._version)
+        bits = [e._sign_cache.get(e.params) for e in (mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz)]
+        sigma = torch.empty(n, device=pos.device, dtype=torch.float32)
+        rgb = None if dirs is None else torch.empty(n, 3, device=pos.device, dtype=torch.float32)
+        geo = torch.empty(n, 79, device=pos.device, dtype=torch.float32) if return_feat else None
+        check(lib().cnc_field_fwd(ptr(pos), ptr(dirs), ctypes.addressof(self._aabb_host), *[ptr(b) for b in bits],
+                                  ptr(mb.encoding_xyz.offsets_list), ptr(mb.encoding_xyz.resolutions_list),
+                                  ptr(mb.encoding_xy.offsets_list), ptr(mb.encoding_xy.resolutions_list),
+                                  ptr(self._fused_blob()), ptr(sigma), ptr(rgb), ptr(geo), n, stream()))
+        shp = list(positions.shape[:-1])
+        return (None if rgb is None else rgb.view(shp + [3]), sigma.view(shp + [1]),
+                None if geo is None else geo.view(shp + [79]))
+
+    def _use_fused(self):
+        return (not torch.is_grad_enabled()) and getattr(self, "fused", True) and self.fused_available()
+
     def update_embedding_params(self, params_q_xyz_rec, params_q_xy_rec, params_q_xz_rec, params_q_yz_rec):
         self.mlp_base.encoding_xyz.params = nn.Parameter(params_q_xyz_rec)
         self.mlp_base.encoding_xy.params = nn.Parameter(params_q_xy_rec)
@@ -161,6 +214,9 @@ class NGPRadianceField_mygrid_2D3D(nn.Module):
         return (x - aabb_min) / (aabb_max - aabb_min)
 
     def query_density(self, x, return_feat: bool = False):
+        if self._use_fused():
+            _, density, geo = self.fused_forward(x, None, return_feat)
+            return (density, geo) if return_feat else density
         x = self._normalise(x)
         selector = ((x > 0.0) & (x < 1.0)).all(dim=-1)
         x = self.mlp_base(x.view(-1, self.num_dim)).view(list(x.shape[:-1]) + [1 + self.geo_feat_dim]).to(x)
@@ -185,6 +241,9 @@ class NGPRadianceField_mygrid_2D3D(nn.Module):
     def forward(self, positions: torch.Tensor, directions: torch.Tensor = None):
         if self.use_viewdirs and (directions is not None):
             assert positions.shape == directions.shape, f"{positions.shape} v.s. {directions.shape}"
+            if self._use_fused():
+                rgb, density, _ = self.fused_forward(positions, directions)
+                return rgb, density
             density, embedding = self.query_density(positions, return_feat=True)
             rgb = self._query_rgb(directions, embedding=embedding)
         return rgb, density  # type: ignore

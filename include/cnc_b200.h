@@ -146,6 +146,32 @@ int cnc_ac_decode(const uint16_t *c1, const int64_t *sym_off, const uint8_t *in,
 int cnc_sh16(const float *d01, float *out, uint64_t n, int fp16_round, cnc_stream_t stream);
 int cnc_freq_embed(const float *x, float *out, uint64_t n, int n_freq, cnc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused radiance-field forward (product layout: F=8, 3D 12 levels + 3 planes x 4 levels,
+ * n_neurons=160, geo_feat_dim=79).
+ * replaces: NGPRadianceField_mygrid_2D3D.query_density / _query_rgb / forward
+ *           examples/radiance_fields/ngp.py:514-566, compose_3D_2D_embed.forward ngp.py:629-645
+ *           (4 x _grid_encode + Embedder + torch.cat + 5 nn.Linear + trunc_exp + sigmoid).
+ * cnc_field_pack_weights: nn.Linear weights ([out,in] row-major) and biases of
+ *   mlp_base.network[0] (160x255), [2] (80x160), mlp_head[0] (160x95), [2] (160x160), [4] (3x160)
+ *   -> blob of cnc_field_blob_floats() floats (tf32 hi/lo split, 128B-swizzled K chunks).
+ * cnc_field_fwd: pos [N,3] world coords, dirs [N,3] (NULL = density only), aabb6 = 6 HOST floats
+ *   (min xyz, max xyz), bits_* = cnc_sign_pack tables of the four encoders, offsets/resolutions
+ *   of the 3D (12+1 / 12 entries) and 2D (4+1 / 4) encoders -> sigma [N], rgb [N,3],
+ *   geo [N,79] (nullable).  fp32 results via 3xTF32 tcgen05 MMA with fp32 accumulation.
+ * ---------------------------------------------------------------------------------------- */
+uint32_t cnc_field_blob_floats(void);
+/* profiling aid: 64 x uint64 device buffer that receives clock64() stamps of one tile (NULL = off) */
+int cnc_field_set_timeline_buffer(uint64_t *device_buf);
+int cnc_field_pack_weights(const float *W1, const float *b1, const float *W2, const float *b2,
+                           const float *W3, const float *b3, const float *W4, const float *b4,
+                           const float *W5, const float *b5, float *blob, cnc_stream_t stream);
+int cnc_field_fwd(const float *pos, const float *dirs, const float *aabb6_host,
+                  const uint8_t *bits_xyz, const uint8_t *bits_xy, const uint8_t *bits_xz,
+                  const uint8_t *bits_yz, const int32_t *offsets3, const int32_t *resolutions3,
+                  const int32_t *offsets2, const int32_t *resolutions2, const float *blob,
+                  float *sigma, float *rgb, float *geo, uint32_t N, cnc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

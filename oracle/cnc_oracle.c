@@ -117,8 +117,13 @@ static int corners(const float *x, uint32_t D, uint32_t T, uint32_t res, uint32_
     float pos[CNC_MAX_D];
     uint32_t g[CNC_MAX_D];
     for (uint32_t d = 0; d < D; d++) { /* gridencoder.cu:171-177 */
-        float m = x[d] * (float)(res - 2);
-        float p = (float)((double)m + 0.5);
+        /* source: `pos = inputs[d] * float(resolution - 2) + 0.5` (double literal).  nvcc (default
+         * -fmad=true) contracts fpext(fmul) + 0.5 into one DFMA on the widened operands, so the
+         * reference BINARY rounds x*s + 0.5 once, not twice (measured on B200 against oracle/_ref:
+         * with the two-rounding form 18% of the features differ in the last bits on every level
+         * whose res-2 is not a power of two; with the single rounding all of them are identical).
+         * The product of two floats is exact in double, so this is fmaf(x, s, 0.5f). */
+        float p = fmaf(x[d], (float)(res - 2), 0.5f);
         g[d] = (uint32_t)floorf(p);
         pos[d] = p - (float)g[d];
     }
