@@ -40,6 +40,7 @@ SIGNATURES = {
     "cnc_field_pack_weights": [_vp] * 12,
     "cnc_field_fwd": [_vp] * 15 + [_u32, _vp],
     "cnc_field_set_timeline_buffer": [_vp],
+    "cnc_context3d_probs": [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _i64, _vp],
 }
 
 
@@ -60,6 +61,7 @@ def lib():
         L.cnc_last_error.restype = C.c_char_p
         L.cnc_version.restype = C.c_int
         L.cnc_field_blob_floats.restype = C.c_uint32
+        L.cnc_context3d_mlp_floats.restype = C.c_uint32
         _lib = L
     return _lib
 

@@ -1,0 +1,573 @@
+"""Host-side mirror of the reference context model + codec driver (examples/utils_bpp_acc.py).
+
+`CNC_context_models(num_dim, resolutions_list, resolutions_list_2D, log2_hashmap_size,
+log2_hashmap_size_2D, n_features, sample_num, max_context_layer_num, ste_binary, ..., Pg_level,
+Pg_level_2D, Rb, step_update, skip_levels_3D, skip_levels_2D, use_dimension_wise,
+use_overlap_area_pool)` with
+
+    forward_binary_vxl_mixPg_3D2D(Encoding_xyz, Encoding_xy, Encoding_xz, Encoding_yz, binary_vxl, step=...)
+        -> (bits_per_param, MB)                                   utils_bpp_acc.py:533-706
+    encode_binary_vxl_mixPg_3D2D(..., binary_vxl, filename_prefix) -> (Pgs_dict, est_MB, coded_MB)   :709-865
+    decode_binary_vxl_mixPg_3D2D(..., *_rec tables, binary_vxl, Pgs_dict, filename_prefix)          :867-999
+
+Same constructor arguments, method names, return values and file layout (33 streams at the product
+config: `<prefix>_xy0..3.b`, `_xz*`, `_yz*`, `_3D0.b`.. `_3D<n>_<chunk>.b`), so the train scripts'
+call sites (train_CNC_nerf_synthetic.py:229-247,351-355,434-464) work unchanged.
+
+B200-native internals
+  * the chunk body of the 3D coder (mask query, compaction, 3-level masked gather, context MLP,
+    padded packing, overlap-weighted mean) is ONE kernel, `cnc_context3d_probs` (csrc/context_fused.cu);
+    `fused=False` keeps the reference's op-by-op data flow on the drop-in kernels (K6/K1/K8 + nn.Linear)
+    for parity tests;
+  * all streams of a level (all 33 at encode time) are range-coded concurrently on the GPU, one warp per
+    stream (`cnc_ac_encode/decode`), instead of one CPU thread after a D2H copy (utils_bpp_acc.py:77-110);
+  * the hash tables are read as 1-bit sign planes.
+There is no CPU path: every method raises if the tensors are not on a CUDA device.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as nnf
+from torch.autograd import Function
+
+from . import _gridencoder as _backend
+from . import pack_and_align
+from . import torchac as tac
+from ._lib import check, lib, ptr, stream
+from .gridencoder import STE_binary, STE_multistep
+
+_PRIMES = (1, 2654435761, 805459861, 3674653429, 2097192037, 1434869437, 2165219737)
+
+
+def get_grid_index(hashmap_size, resolution, pos_grid):
+    """Row index of integer grid vertices: examples/utils.py:492-511 (the python twin of
+    gridencoder.cu:45-87).  uint32 wrap-around is applied explicitly, so the result equals the CUDA
+    kernel's for any table size (the reference relies on power-of-two tables)."""
+    D = pos_grid.shape[-1]
+    hashmap_size, resolution = int(hashmap_size), int(resolution)
+    pos = pos_grid.to(torch.int64)
+    if resolution ** D <= hashmap_size:
+        idx = torch.zeros(pos.shape[:-1], dtype=torch.int64, device=pos.device)
+        stride = 1
+        for d in range(D):
+            idx += pos[..., d] * stride
+            stride *= resolution
+    else:
+        idx = torch.zeros(pos.shape[:-1], dtype=torch.int64, device=pos.device)
+        for d in range(D):
+            idx ^= (pos[..., d] * _PRIMES[d]) & 0xFFFFFFFF
+    return idx % hashmap_size
+
+
+def my_meshgrid3D(start, end, device, dtype=torch.int32):
+    """[lx, ly, lz, 3] integer lattice, x slowest (utils_bpp_acc.py:140-161)."""
+    if isinstance(start, int):
+        start, end = (start,) * 3, (end,) * 3
+    ax = [torch.arange(s, e, device=device, dtype=dtype) for s, e in zip(start, end)]
+    return torch.stack(torch.meshgrid(*ax, indexing="ij"), dim=-1)
+
+
+class _cnt_np_embed(Function):
+    """3D -> 2D vote fractions (utils_bpp_acc.py:27-75) on cnc_vote_planes_fwd/bwd."""
+
+    @staticmethod
+    def forward(ctx, inputs, embeddings, resolution, hashmap_size, axis):
+        axis = ["xy", "xz", "yz"].index(axis)
+        N, F = inputs.shape[0], embeddings.shape[-1]
+        inputs = inputs.to(torch.int16).contiguous()
+        embeddings = embeddings.contiguous()
+        scale = resolution - 2
+        pn_embed = torch.zeros(scale, scale, F, 2, device=inputs.device)
+        _backend.cnt_np_embed(inputs, embeddings, pn_embed, N, resolution, F, hashmap_size, axis)
+        pn_sum = pn_embed.sum(dim=-1, keepdim=True) + 1e-6
+        ctx.save_for_backward(inputs, embeddings, pn_sum)
+        ctx.dims = [N, resolution, F, hashmap_size, axis]
+        return pn_embed / pn_sum
+
+    @staticmethod
+    def backward(ctx, grad):
+        inputs, embeddings, pn_sum = ctx.saved_tensors
+        N, resolution, F, hashmap_size, axis = ctx.dims
+        g = torch.zeros_like(embeddings)
+        _backend.cnt_np_embed_backward(inputs, embeddings, pn_sum, grad.contiguous(), g, N, resolution, F,
+                                       hashmap_size, axis)
+        return None, g, None, None, None
+
+
+class align_and_pack(Function):
+    """ragged -> padded [N, M, F] (utils_bpp_acc.py:113-139) on cnc_align_pack_fwd/bwd."""
+
+    @staticmethod
+    def forward(ctx, voxel_features, unique_cnt, V, dim=3):
+        voxel_features = voxel_features.contiguous()
+        cs = torch.cat([torch.zeros(1, dtype=torch.int64, device=unique_cnt.device), torch.cumsum(unique_cnt, 0)])
+        N, M, F = unique_cnt.numel(), int(unique_cnt.max()) if unique_cnt.numel() else 0, voxel_features.shape[-1]
+        ctx.save_for_backward(voxel_features, unique_cnt, cs)
+        ctx.dims = [N, M, F, int(cs[-1]), dim]
+        return pack_and_align.align_and_pack_forward(voxel_features, unique_cnt, cs, N, M, F, 0.0, dim)
+
+    @staticmethod
+    def backward(ctx, dL):
+        voxel_features, unique_cnt, cs = ctx.saved_tensors
+        N, M, F, T, dim = ctx.dims
+        return pack_and_align.align_and_pack_backward(dL.contiguous(), voxel_features, unique_cnt, cs, N, M, F, T, dim), None, None, None
+
+
+class Bernoulli_entropy(nn.Module):
+    """utils_bpp_acc.py:1002-1013: bits of x in {-1,+1} under P(+1) = p (clamped to [1e-6, 1-1e-6])."""
+
+    def forward(self, x, p):
+        p = torch.clamp(p, min=1e-6, max=1 - 1e-6)
+        return -torch.log2(p) * ((1 + x) / 2.0) + -torch.log2(1 - p) * ((1 - x) / 2.0)
+
+
+def _layout(resolutions, num_dim, log2T):
+    offs, off = [], 0
+    for r in resolutions:
+        n = int(np.ceil(min(2 ** log2T, int(r) ** num_dim) / 8) * 8)
+        offs.append(off)
+        off += n
+    offs.append(off)
+    return offs
+
+
+class CNC_context_models(nn.Module):
+    def __init__(self, num_dim=3, resolutions_list=(16, 22, 31, 42, 57, 78, 106, 146, 199, 273, 374, 512),
+                 resolutions_list_2D=(128, 256, 512, 1024), log2_hashmap_size=19, log2_hashmap_size_2D=21,
+                 n_features=4, sample_num=20000, max_context_layer_num=3, ste_binary=False, ste_multistep=False,
+                 add_noise=False, Q=100, quantize_epoch=1000, Pg_level=-1, Pg_level_2D=-1, Rb=128, step_update=16,
+                 skip_levels_3D=(0, 1, 2, 3), skip_levels_2D=(0,), use_dimension_wise=True,
+                 use_overlap_area_pool=True, device="cuda", fused=True):
+        super().__init__()
+        dev = torch.device(device)
+        self.MAX_POINTS_NUM_TO_OOM = 20000000
+        self.use_overlap_area_pool, self.use_dimension_wise, self.fused = use_overlap_area_pool, use_dimension_wise, fused
+        self.num_dim, self.n_features = num_dim, n_features
+        self.res = [int(r) for r in resolutions_list]
+        self.res_2D = [int(r) for r in resolutions_list_2D]
+        self.n_levels, self.n_levels_2D = len(self.res), len(self.res_2D)
+        self.resolutions_list = torch.tensor(self.res, device=dev)
+        self.resolutions_list_2D = torch.tensor(self.res_2D, device=dev)
+        self.scales_list = (self.resolutions_list - 2).unsqueeze(-1)
+        self.scales_list_2D = (self.resolutions_list_2D - 2).unsqueeze(-1)
+        self.log2_hashmap_size, self.log2_hashmap_size_2D = log2_hashmap_size, log2_hashmap_size_2D
+        self.ste_binary, self.ste_multistep, self.add_noise, self.Q = ste_binary, ste_multistep, add_noise, Q
+        self.quantize_epoch, self.quantize_epoch_cnt = quantize_epoch, 0
+        Pg_level = self.n_levels if (Pg_level == -1 or Pg_level >= self.n_levels) else max(Pg_level, 1)
+        Pg_level_2D = self.n_levels_2D if (Pg_level_2D == -1 or Pg_level_2D >= self.n_levels_2D) else max(Pg_level_2D, 1)
+        self.Pg_level, self.Pg_level_2D = Pg_level, Pg_level_2D
+        self.skip_levels_3D, self.skip_levels_2D = tuple(skip_levels_3D), tuple(skip_levels_2D)
+        self.sample_num, self.max_context_layer_num, self.step_update = sample_num, max_context_layer_num, step_update
+
+        self.offs = _layout(self.res, num_dim, log2_hashmap_size)
+        self.offs_2D = _layout(self.res_2D, 2, log2_hashmap_size_2D)
+        self.offsets_list = torch.tensor(self.offs, dtype=torch.int64, device=dev)
+        self.offsets_list_2D = torch.tensor(self.offs_2D, dtype=torch.int64, device=dev)
+        max_params = 2 ** log2_hashmap_size
+        self.n_levels_thresh, self.resolution_thresh = self.n_levels - 1, float(self.res[-1])
+        for i in range(self.n_levels - 1):   # last dense level (utils_bpp_acc.py:288-292)
+            if self.res[i] ** num_dim <= max_params < self.res[i + 1] ** num_dim:
+                self.n_levels_thresh, self.resolution_thresh = i + 1, float(self.res[i])
+
+        # ---- inverse hash tables (utils_bpp_acc.py:294-335): for every level, the voxels grouped by table row
+        self.unique_value_list: List[torch.Tensor] = []         # rows that are hit, in bitstream symbol order
+        self.unique_count_list: List[torch.Tensor] = []         # voxels per row
+        self.unique_count_cumsum_list: List[torch.Tensor] = []  # running sum, leading 0
+        self.pos_grid_sorted_list: List[torch.Tensor] = []      # int16 [res^3, 3] voxel coords grouped by row
+        for i in range(Pg_level):
+            r = self.res[i]
+            pos_grid = my_meshgrid3D(0, r, dev).view(-1, 3)
+            indexes = get_grid_index(self.offs[i + 1] - self.offs[i], r, pos_grid)
+            indexes_sorted, order = torch.sort(indexes)
+            del indexes
+            pos_grid_sorted = pos_grid.to(torch.int16)[order]
+            del pos_grid, order
+            unique_value, unique_cnt = torch.unique_consecutive(indexes_sorted, return_counts=True)
+            del indexes_sorted
+            if r <= self.resolution_thresh:   # dense levels: random symbol order (one voxel per row)
+                shuffle_idx = torch.randperm(unique_value.nelement()).to(dev)
+                unique_value, pos_grid_sorted, unique_cnt = unique_value[shuffle_idx], pos_grid_sorted[shuffle_idx], unique_cnt[shuffle_idx]
+            self.unique_value_list.append(unique_value.to(torch.int64))
+            self.unique_count_list.append(unique_cnt.to(torch.int64))
+            self.unique_count_cumsum_list.append(torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(unique_cnt, 0)]))
+            self.pos_grid_sorted_list.append(pos_grid_sorted.contiguous())
+        self.hashparams_num_levels = torch.tensor([v.numel() for v in self.unique_value_list], device=dev)
+        snl = torch.round(self.hashparams_num_levels * (sample_num / self.hashparams_num_levels.sum())).to(torch.long)
+        self.sample_num_levels = self.hashparams_num_levels if snl[-1] > self.hashparams_num_levels[-1] else snl
+        coded = [n for n in range(self.n_levels) if n not in self.skip_levels_3D and n < Pg_level]
+        self.ttl_hashparams_num_levels = int(self.hashparams_num_levels.sum())
+        self.ttl_hashparams_num_valid_levels = int(sum(int(self.hashparams_num_levels[n]) for n in coded))
+        self.ttl_sample_num = int(self.sample_num_levels.sum())
+        self.ttl_sample_num_valid_levels = int(sum(int(self.sample_num_levels[n]) for n in coded))
+        self.utils_rand = torch.rand(Pg_level, device=dev)
+        # voxels per row as the reference computes it (int64 ** / int64 -> float32), it fixes the chunking of the streams
+        self.utils_points_per_param_levels = [((self.resolutions_list[i] ** num_dim) / self.hashparams_num_levels[i]).item()
+                                              for i in range(Pg_level)]
+        self.binary_vxl_2D_idx = torch.stack(torch.meshgrid(torch.arange(Rb, device=dev, dtype=torch.int32),
+                                                            torch.arange(Rb, device=dev, dtype=torch.int32), indexing="ij"), -1)
+
+        self.context_model_3D = nn.Sequential(nn.Linear(n_features * max_context_layer_num + 1, 32), nn.LeakyReLU(),
+                                              nn.Linear(32, 32), nn.LeakyReLU(), nn.Linear(32, n_features)).to(dev)
+        self.context_model_2D = nn.Sequential(*[
+            nn.Sequential(nn.Linear(n_features * (min(n, max_context_layer_num) + int(use_dimension_wise)) + 1, n_features))
+            for n in range(1, Pg_level_2D)]).to(dev)
+        self.entropy_model = Bernoulli_entropy()
+        self.binary_vxl_len = Rb
+        self.init_binary_vxl_coords(self.res[-1] - 2)
+        self.idx_coords2_tmp, self.batched_inputs_list = None, None
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def query_binary_vxl(self, points_n_orig, binary_vxl, n, return_overlap_area=False):
+        """utils_bpp_acc.py:404-415 (K6)."""
+        N = points_n_orig.shape[0]
+        mask = torch.zeros(N, dtype=torch.int16, device=points_n_orig.device)
+        overlap = torch.zeros(N, dtype=torch.int32, device=points_n_orig.device)
+        pack_and_align.query_mask_3D(points_n_orig.contiguous(), binary_vxl.squeeze(0).contiguous(), mask, overlap, self.res[n], N)
+        mask = mask.to(torch.bool)
+        return (mask, overlap) if return_overlap_area else mask
+
+    def query_binary_vxl_qlist(self, points_n_orig_list, binary_vxl, n_list, return_overlap_area=False):
+        """utils_bpp_acc.py:417-428 (K7)."""
+        N = points_n_orig_list.shape[0]
+        mask = torch.zeros(N, dtype=torch.int16, device=points_n_orig_list.device)
+        overlap = torch.zeros(N, dtype=torch.int32, device=points_n_orig_list.device)
+        pack_and_align.query_mask_3D_qlist(points_n_orig_list.contiguous(), binary_vxl.squeeze(0).contiguous(), mask, overlap,
+                                           self.resolutions_list[n_list].contiguous(), N)
+        mask = mask.to(torch.bool)
+        return (mask, overlap) if return_overlap_area else mask
+
+    def fetch_2D_batches(self, binary_vxl_2D, n):
+        """utils_bpp_acc.py:431-456: every plane vertex inside an occupied 2D cell (+1-vertex halo):
+        (row index in the level, normalised coordinates)."""
+        Rb = binary_vxl_2D.shape[-1]
+        scale = self.res_2D[n] - 2
+        assert scale % Rb == 0
+        T = scale // Rb
+        cells = self.binary_vxl_2D_idx.view(-1, 2)[binary_vxl_2D.reshape(-1)].to(torch.int64) * T      # [bs, 2]
+        o = torch.arange(0, T + 2, device=cells.device)
+        offsets = torch.stack(torch.meshgrid(o, o, indexing="ij"), -1).view(1, -1, 2)                  # [1, (T+2)^2, 2]
+        points_n_orig = (cells[:, None, :] + offsets).view(-1, 2)
+        indexes_2D = get_grid_index(self.offs_2D[n + 1] - self.offs_2D[n], self.res_2D[n], points_n_orig)
+        points_n = (points_n_orig.to(torch.float32) - 0.5) / float(scale)
+        return indexes_2D, points_n
+
+    def get_STE_params(self, Encoding, mode="ste_binary"):
+        assert mode in ("ste_binary", "ste_multistep", "add_noise")
+        p = Encoding.params
+        if mode == "ste_binary":
+            return STE_binary.apply(p)
+        if mode == "ste_multistep":
+            return STE_multistep.apply(p, self.Q)
+        return p + (torch.rand_like(p) - 0.5) * (1 / self.Q)
+
+    def get_BiRF_wentropy_leveln(self, params_q, n, offsets=None):
+        """utils_bpp_acc.py:472-486: level-wide +1 frequency and its zeroth-order entropy."""
+        offsets = self.offs if offsets is None else offsets
+        p = params_q[offsets[n]:offsets[n + 1]]
+        ttl = p.numel()
+        s = torch.sum(p)
+        pos, neg = (ttl + s) / 2.0, (ttl - s) / 2.0
+        Pg = pos / ttl
+        return Pg, pos * (-torch.log2(Pg)) + neg * (-torch.log2(1 - Pg)), ttl
+
+    def init_binary_vxl_coords(self, scale=512):
+        t = scale // self.binary_vxl_len
+        resolution = scale + 2
+        dev = self.resolutions_list.device
+        self.idx_coord_base = my_meshgrid3D(-1, t + 1, dev).view(1, -1, 3)
+        self.pn_frac_offsets_list = torch.tensor([0, resolution * resolution], device=dev, dtype=torch.int32)
+        self.pn_frac_resolutions_list = torch.tensor([resolution], device=dev, dtype=torch.int32)
+
+    def get_idx_coords2(self, binary_vxl, resolution=None):
+        """utils_bpp_acc.py:498-512: all finest-level voxels inside occupied occupancy cells (+halo), unique."""
+        resolution = self.res[-1] if resolution is None else resolution
+        t = (resolution - 2) // self.binary_vxl_len
+        occ = binary_vxl.squeeze(0).nonzero().to(torch.int32).contiguous()                          # [N, 3] occupied cells
+        c = (occ[:, None, :] * t + self.idx_coord_base + 1).reshape(-1, 3).to(torch.int64)
+        key = torch.unique(c[:, 0] * resolution * resolution + c[:, 1] * resolution + c[:, 2])
+        return torch.stack([key // (resolution * resolution), (key // resolution) % resolution, key % resolution], -1)
+
+    def get_pn_embed_frac(self, embeddings_3D_q, idx_coords2, resolution=None, axis="xy"):
+        """utils_bpp_acc.py:515-530: +1 vote fraction plane, zero padded to [res*res, F]."""
+        resolution = self.res[-1] if resolution is None else resolution
+        frac = _cnt_np_embed.apply(idx_coords2, embeddings_3D_q, resolution, 2 ** self.log2_hashmap_size, axis)[..., 0]
+        frac = nnf.pad(frac.permute(2, 0, 1).unsqueeze(0), pad=[1, 1, 1, 1]).squeeze(0).permute(1, 2, 0).contiguous()
+        return frac.view(-1, self.n_features)
+
+    @staticmethod
+    def _planes(binary_vxl):
+        b = binary_vxl.squeeze(0)
+        return {"xy": torch.any(b, dim=2), "xz": torch.any(b, dim=1), "yz": torch.any(b, dim=0)}
+
+    def _chunks(self, n):
+        """stream chunking of a context-coded level (utils_bpp_acc.py:798-802)."""
+        per = int(self.MAX_POINTS_NUM_TO_OOM // self.utils_points_per_param_levels[n])
+        total = int(self.hashparams_num_levels[n])
+        per = min(per, total)
+        return [(s, min(s + per, total)) for s in range(0, total, per)]
+
+    def _mlp3d_packed(self):
+        m = self.context_model_3D
+        parts = [m[0].weight.t(), m[0].bias, m[2].weight.t(), m[2].bias, m[4].weight.t(), m[4].bias]
+        return torch.cat([p.detach().contiguous().float().reshape(-1) for p in parts]).contiguous()
+
+    # ---------------------------------------------------------------------------- probabilities, 3D
+    def _probs_3D(self, Encoding_xyz, table, binary_vxl, n, lo, hi, Pg_n):
+        """P(+1) of the entries [lo, hi) of level n -> (prob [E,F] of the existing entries, mask_exist [hi-lo])."""
+        if self.fused and self.n_features == 8 and self.max_context_layer_num == 3 and n >= 3 and Encoding_xyz.ste_binary:
+            return self._probs_3D_fused(Encoding_xyz, table, binary_vxl, n, lo, hi, Pg_n)
+        return self._probs_3D_unfused(Encoding_xyz, table, binary_vxl, n, lo, hi, Pg_n)
+
+    def _probs_3D_fused(self, Encoding_xyz, table, binary_vxl, n, lo, hi, Pg_n):
+        cs = self.unique_count_cumsum_list[n]
+        seg = cs[lo:hi + 1].contiguous()
+        seg_base = int(cs[lo])
+        pts = self.pos_grid_sorted_list[n][seg_base:int(cs[hi])]
+        E = hi - lo
+        dev = pts.device
+        bits = _backend.sign_pack(table.detach().contiguous())
+        prob = torch.empty(E, 8, device=dev)
+        exist = torch.empty(E, dtype=torch.uint8, device=dev)
+        vx = binary_vxl.squeeze(0).contiguous()
+        check(lib().cnc_context3d_probs(ptr(pts), ptr(seg), E, ptr(vx), vx.shape[-1], ptr(bits),
+                                        ptr(Encoding_xyz.offsets_list), ptr(Encoding_xyz.resolutions_list), n, float(Pg_n),
+                                        ptr(self._mlp3d_packed()), ptr(prob), None, ptr(exist), seg_base, stream()))
+        ex = exist.bool()
+        return prob[ex], ex
+
+    def _probs_3D_unfused(self, Encoding_xyz, table, binary_vxl, n, lo, hi, Pg_n):
+        """the reference's op-by-op flow (utils_bpp_acc.py:803-852) on the drop-in kernels"""
+        cs = self.unique_count_cumsum_list[n]
+        points_n_orig = self.pos_grid_sorted_list[n][int(cs[lo]):int(cs[hi])]
+        points_n = (points_n_orig - 0.5) / self.scales_list[n, :]
+        mask, overlap = self.query_binary_vxl(points_n_orig, binary_vxl, n, return_overlap_area=True)
+        points_n = points_n[mask]
+        unique_cnt = self.unique_count_list[n][lo:hi]
+        mask_packed = align_and_pack.apply(mask.unsqueeze(-1).to(torch.float), unique_cnt, 0)
+        mask_cnt = torch.sum(mask_packed[:, :, 0], dim=1).to(torch.long)
+        mask_exist = mask_cnt > 0
+        mask_cnt = mask_cnt[mask_exist]
+        overlap = torch.clamp(overlap[mask], min=1)
+        ov_packed = align_and_pack.apply(overlap.unsqueeze(-1).to(torch.float), mask_cnt, 0)
+        ov_packed = ov_packed / torch.sum(ov_packed, dim=1, keepdim=True)
+        c = min(n, self.max_context_layer_num)
+        context = Encoding_xyz(points_n, n - c, n, outspace_params=table, binary_vxl=binary_vxl.squeeze(0), PV=0)
+        context = torch.cat([context, Pg_n.reshape(1, 1).expand(context.shape[0], 1)], dim=-1)
+        mean = align_and_pack.apply(self.context_model_3D(context), mask_cnt, 0.0)
+        if self.use_overlap_area_pool:
+            mean = torch.sum(mean * ov_packed, dim=1)
+        else:
+            mean = torch.sum(mean, dim=1) / mask_cnt.unsqueeze(-1)
+        return torch.clamp(mean, min=1e-6, max=1 - 1e-6), mask_exist
+
+    # ---------------------------------------------------------------------------- probabilities, 2D
+    def _probs_2D(self, Encoding_2D, table_2D, binary_vxl_2D, n, pn_embed_frac, Pg_n, batch=None, differentiable=False):
+        """plane level n >= 1 -> (mean [U,F] unclamped, rows [U] absolute).  utils_bpp_acc.py:724-746 == :895-916"""
+        if batch is None:
+            indexes_2D, points_n = self.fetch_2D_batches(binary_vxl_2D, n)
+            _, indices_2D = torch.sort(indexes_2D)
+            unique_value_2D, unique_cnt_2D = torch.unique_consecutive(indexes_2D[indices_2D], return_counts=True)
+            unique_value_2D = unique_value_2D + self.offs_2D[n]
+        else:
+            points_n, indices_2D, unique_value_2D, unique_cnt_2D = batch
+        c = min(n, self.max_context_layer_num)
+        context = Encoding_2D(points_n, n - c, n, outspace_params=table_2D, binary_vxl=binary_vxl_2D, PV=0)
+        Pg_col = Pg_n.reshape(1, 1).expand(context.shape[0], 1)
+        if self.use_dimension_wise:
+            context_pn = Encoding_2D.forward_given_params(points_n, self.pn_frac_offsets_list, self.pn_frac_resolutions_list,
+                                                          pn_embed_frac, binary_vxl_2D)
+            if not differentiable:
+                context_pn = context_pn.detach()
+            context = torch.cat([context, context_pn, Pg_col], dim=-1)
+        else:
+            context = torch.cat([context, Pg_col], dim=-1)
+        mean = torch.index_select(self.context_model_2D[n - 1](context), 0, indices_2D)
+        if differentiable:
+            mean = torch.sum(align_and_pack.apply(mean, unique_cnt_2D, 0.0, 2), dim=1)
+        else:
+            cs = torch.cat([torch.zeros(1, dtype=torch.int64, device=mean.device), torch.cumsum(unique_cnt_2D, 0)])
+            mean = pack_and_align.segment_wsum(mean.contiguous(), cs)
+        return mean / unique_cnt_2D.unsqueeze(-1), unique_value_2D, (points_n, indices_2D, unique_value_2D, unique_cnt_2D)
+
+    # ------------------------------------------------------------------------------------------ loss
+    def forward_binary_vxl_mixPg_3D2D(self, Encoding_xyz, Encoding_xy, Encoding_xz, Encoding_yz, binary_vxl=None,
+                                      verbose=False, sample_num=None, step=0):
+        """Rate term of the training loss: (bits per parameter, MB).  utils_bpp_acc.py:533-706"""
+        pq = {k: self.get_STE_params(E) for k, E in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz), ("xyz", Encoding_xyz))}
+        refresh = step % self.step_update == 0 or self.idx_coords2_tmp is None
+        if refresh:
+            self.idx_coords2_tmp = self.get_idx_coords2(binary_vxl)
+        planes = self._planes(binary_vxl)
+        if refresh:
+            self.batched_inputs_list = {}
+        ttl_bit_sum, ttl_num_sum = 0, 0
+        finest = pq["xyz"][self.offs[-2]:self.offs[-1]]
+        for axis, Enc in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz)):
+            pn = self.get_pn_embed_frac(finest, self.idx_coords2_tmp, axis=axis) if self.use_dimension_wise else None
+            for n in range(self.n_levels_2D):
+                Pg_n, bit_n, _ = self.get_BiRF_wentropy_leveln(pq[axis], n, self.offs_2D)
+                if not (n in self.skip_levels_2D or n >= self.Pg_level_2D):
+                    mean, rows, batch = self._probs_2D(Enc, None, planes[axis], n, pn, Pg_n,
+                                                       self.batched_inputs_list.get((axis, n)), differentiable=True)
+                    self.batched_inputs_list[(axis, n)] = batch
+                    bit_n = torch.sum(self.entropy_model(pq[axis][rows, :], mean))
+                ttl_bit_sum = ttl_bit_sum + bit_n
+            ttl_num_sum += pq[axis].numel()
+
+        if sample_num is not None:
+            snl = torch.round(self.hashparams_num_levels * (sample_num / self.hashparams_num_levels.sum())).to(torch.long)
+            snl = self.hashparams_num_levels if snl[-1] > self.hashparams_num_levels[-1] else snl
+            n_valid = sum(int(snl[n]) for n in range(self.n_levels) if n not in self.skip_levels_3D and n < self.Pg_level)
+        else:
+            snl, n_valid = self.sample_num_levels, self.ttl_sample_num_valid_levels
+        start = torch.round((self.hashparams_num_levels - snl) * torch.rand_like(self.utils_rand)).to(torch.long).tolist()
+        pts_l, ptsn_l, Pg_l, n_l, cnt_l, val_l = [], [], [], [], [], []
+        for n in range(self.n_levels):
+            Pg_n, bit_n, _ = self.get_BiRF_wentropy_leveln(pq["xyz"], n)
+            if n in self.skip_levels_3D or n >= self.Pg_level:
+                ttl_bit_sum = ttl_bit_sum + bit_n
+                continue
+            lo, hi = start[n], start[n] + int(snl[n])
+            cs = self.unique_count_cumsum_list[n]
+            p = self.pos_grid_sorted_list[n][int(cs[lo]):int(cs[hi])]
+            pts_l.append(p)
+            ptsn_l.append((p - 0.5) / self.scales_list[n, :])
+            Pg_l.append(Pg_n.reshape(1, 1).expand(p.shape[0], 1))
+            n_l.append(torch.full((p.shape[0],), n, dtype=torch.int64, device=p.device))
+            cnt_l.append(self.unique_count_list[n][lo:hi])
+            val_l.append(pq["xyz"][self.unique_value_list[n][lo:hi] + self.offs[n]])
+        if pts_l:
+            pts, ptsn, Pgc, nl, cnt, vals = (torch.cat(t, 0) for t in (pts_l, ptsn_l, Pg_l, n_l, cnt_l, val_l))
+            mask, overlap = self.query_binary_vxl_qlist(pts, binary_vxl, nl, return_overlap_area=True)
+            mask_packed = align_and_pack.apply(mask.unsqueeze(-1).to(torch.float), cnt, 0)
+            mask_cnt = torch.sum(mask_packed[:, :, 0], dim=1).to(torch.long)
+            mask_exist = mask_cnt > 0
+            mask_cnt, vals = mask_cnt[mask_exist], vals[mask_exist]
+            overlap = torch.clamp(overlap[mask], min=1)
+            ov_packed = align_and_pack.apply(overlap.unsqueeze(-1).to(torch.float), mask_cnt, 0)
+            ov_packed = ov_packed / torch.sum(ov_packed, dim=1, keepdim=True)
+            c = self.max_context_layer_num
+            context = Encoding_xyz.forward_diff_levels(ptsn[mask], (nl[mask] - c).to(torch.int), c, binary_vxl=binary_vxl.squeeze(0), PV=1001)
+            mean = align_and_pack.apply(self.context_model_3D(torch.cat([context, Pgc[mask]], dim=-1)), mask_cnt, 0.0)
+            mean = torch.sum(mean * ov_packed, dim=1) if self.use_overlap_area_pool else torch.sum(mean, dim=1) / mask_cnt.unsqueeze(-1)
+            bits = torch.sum(self.entropy_model(vals, mean))
+            ttl_bit_sum = ttl_bit_sum + bits / n_valid * self.ttl_hashparams_num_valid_levels
+        ttl_num_sum += pq["xyz"].numel()
+        return ttl_bit_sum / ttl_num_sum, float(ttl_bit_sum) / 8 / 1024 / 1024
+
+    # ------------------------------------------------------------------------------------------ encode
+    @torch.no_grad()
+    def encode_binary_vxl_mixPg_3D2D(self, Encoding_xyz, Encoding_xy, Encoding_xz, Encoding_yz, binary_vxl=None,
+                                     filename_prefix="b", return_streams=False):
+        """utils_bpp_acc.py:709-865.  Writes `<prefix>_<axis><n>.b`, `<prefix>_3D<n>.b`, `<prefix>_3D<n>_<chunk>.b`."""
+        pq = {k: self.get_STE_params(E) for k, E in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz), ("xyz", Encoding_xyz))}
+        Pgs_dict: Dict[str, torch.Tensor] = {}
+        names, c1s, syms = [], [], []
+        ttl_bit = torch.zeros((), device=pq["xyz"].device)
+
+        def emit(name, xs, ps):
+            names.append(name)
+            c1s.append(tac.cdf_from_p(ps))
+            syms.append(((xs + 1) // 2).to(torch.uint8).reshape(-1))
+
+        idx_coords2 = self.get_idx_coords2(binary_vxl)
+        planes = self._planes(binary_vxl)
+        finest = pq["xyz"][self.offs[-2]:self.offs[-1]]
+        for axis, Enc in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz)):
+            pn = self.get_pn_embed_frac(finest, idx_coords2, axis=axis) if self.use_dimension_wise else None
+            for n in range(self.n_levels_2D):
+                Pg_n, bit_n, _ = self.get_BiRF_wentropy_leveln(pq[axis], n, self.offs_2D)
+                Pgs_dict[axis + str(n)] = Pg_n
+                if n in self.skip_levels_2D or n >= self.Pg_level_2D:
+                    xs = pq[axis][self.offs_2D[n]:self.offs_2D[n + 1]].reshape(-1)
+                    emit(f"{filename_prefix}_{axis}{n}.b", xs, Pg_n.expand(xs.numel()))
+                else:
+                    mean, rows, _ = self._probs_2D(Enc, None, planes[axis], n, pn, Pg_n)
+                    values_q = pq[axis][rows, :]
+                    bit_n = torch.sum(self.entropy_model(values_q, mean))
+                    emit(f"{filename_prefix}_{axis}{n}.b", values_q.reshape(-1), torch.clamp(mean, 1e-6, 1 - 1e-6).reshape(-1))
+                ttl_bit += bit_n
+        for n in range(self.n_levels):
+            Pg_n, bit_n, _ = self.get_BiRF_wentropy_leveln(pq["xyz"], n)
+            Pgs_dict["3D" + str(n)] = Pg_n
+            if n in self.skip_levels_3D or n >= self.Pg_level:
+                xs = pq["xyz"][self.offs[n]:self.offs[n + 1]].reshape(-1)
+                emit(f"{filename_prefix}_3D{n}.b", xs, Pg_n.expand(xs.numel()))
+                ttl_bit += bit_n
+                continue
+            for sn, (lo, hi) in enumerate(self._chunks(n)):
+                ps, mask_exist = self._probs_3D(Encoding_xyz, pq["xyz"], binary_vxl, n, lo, hi, Pg_n)
+                values_q = pq["xyz"][self.unique_value_list[n][lo:hi] + self.offs[n]][mask_exist]
+                ttl_bit += torch.sum(self.entropy_model(values_q, ps))
+                emit(f"{filename_prefix}_3D{n}_{sn}.b", values_q.reshape(-1), ps.reshape(-1))
+        streams = tac.encode_streams(c1s, syms)      # all streams at once, one warp each
+        coded_bits = 0
+        for name, data in zip(names, streams):
+            coded_bits += len(data) * 8
+            if not return_streams:
+                d = os.path.dirname(name)
+                if d:
+                    os.makedirs(d, exist_ok=True)
+                with open(name, "wb") as f:
+                    f.write(data)
+        out = (Pgs_dict, float(ttl_bit) / 8.0 / 1024 / 1024, coded_bits / 8.0 / 1024 / 1024)
+        return out + (dict(zip(names, streams)),) if return_streams else out
+
+    # ------------------------------------------------------------------------------------------ decode
+    @torch.no_grad()
+    def decode_binary_vxl_mixPg_3D2D(self, Encoding_xyz, Encoding_xy, Encoding_xz, Encoding_yz, params_q_xyz_rec,
+                                     params_q_xy_rec, params_q_xz_rec, params_q_yz_rec, binary_vxl=None, Pgs_dict=None,
+                                     filename_prefix="b", streams=None):
+        """utils_bpp_acc.py:867-999.  3D levels in order (level n is predicted from the decoded n-3..n-1), then the
+        three planes (their dimension-wise context needs the decoded finest 3D level)."""
+        def read(name):
+            if streams is not None:
+                return streams[name]
+            with open(name, "rb") as f:
+                return f.read()
+
+        def decode(names, ps_list):
+            """one launch for the independent streams of a step -> +-1 float tensors"""
+            outs = tac.decode_streams([tac.cdf_from_p(p) for p in ps_list], [read(nm) for nm in names])
+            return [o.to(torch.float32) * 2 - 1 for o in outs]
+
+        F = self.n_features
+        for n in range(self.n_levels):
+            Pg_n = Pgs_dict["3D" + str(n)]
+            if n in self.skip_levels_3D or n >= self.Pg_level:
+                rows = self.offs[n + 1] - self.offs[n]
+                (sout,) = decode([f"{filename_prefix}_3D{n}.b"], [Pg_n.expand(rows * F)])
+                params_q_xyz_rec[self.offs[n]:self.offs[n + 1]] = sout.view(rows, F)
+                continue
+            names, ps_l, rows_l = [], [], []
+            for sn, (lo, hi) in enumerate(self._chunks(n)):   # chunks of a level are independent streams
+                ps, mask_exist = self._probs_3D(Encoding_xyz, params_q_xyz_rec, binary_vxl, n, lo, hi, Pg_n)
+                names.append(f"{filename_prefix}_3D{n}_{sn}.b")
+                ps_l.append(ps.reshape(-1))
+                rows_l.append((self.unique_value_list[n][lo:hi] + self.offs[n])[mask_exist])
+            for sout, rows in zip(decode(names, ps_l), rows_l):
+                params_q_xyz_rec[rows] = sout.view(-1, F)
+        idx_coords2 = self.get_idx_coords2(binary_vxl)
+        planes = self._planes(binary_vxl)
+        finest = params_q_xyz_rec[self.offs[-2]:self.offs[-1]]
+        recs = {"xy": params_q_xy_rec, "xz": params_q_xz_rec, "yz": params_q_yz_rec}
+        for axis, Enc in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz)):
+            rec = recs[axis]
+            pn = self.get_pn_embed_frac(finest, idx_coords2, axis=axis) if self.use_dimension_wise else None
+            for n in range(self.n_levels_2D):
+                Pg_n = Pgs_dict[axis + str(n)]
+                name = f"{filename_prefix}_{axis}{n}.b"
+                if n in self.skip_levels_2D or n >= self.Pg_level_2D:
+                    rows = self.offs_2D[n + 1] - self.offs_2D[n]
+                    (sout,) = decode([name], [Pg_n.expand(rows * F)])
+                    rec[self.offs_2D[n]:self.offs_2D[n + 1]] = sout.view(rows, F)
+                else:
+                    mean, rows, _ = self._probs_2D(Enc, rec, planes[axis], n, pn, Pg_n)
+                    (sout,) = decode([name], [torch.clamp(mean, 1e-6, 1 - 1e-6).reshape(-1)])
+                    rec[rows, :] = sout.view(-1, F)
+        return params_q_xyz_rec, params_q_xy_rec, params_q_xz_rec, params_q_yz_rec

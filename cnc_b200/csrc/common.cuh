@@ -160,4 +160,65 @@ __device__ __forceinline__ bool make_corners(const float (&x)[D], const LevelCon
     return true;
 }
 
+
+// "does the +-1-voxel box around voxel `c` (int coords at a level of resolution r) touch an occupied cell, and
+// with how much overlap": aligner_kernel.cu:161-242 (3D) / :4-80 (2D).  Returns the mask; `overlap` receives
+// int(overlap_volume * Rb^D * 1000) (truncation), the reference's overlap_area_pool entry.
+template <int D>
+__device__ __forceinline__ bool voxel_mask_overlap(const int (&c)[D], float r, int32_t Rb, const uint8_t *__restrict__ vxl,
+                                                   int32_t &overlap) {
+    const float fRb = (float)Rb, fRb1 = (float)(Rb - 1);
+    const float Rb_re = __frcp_rn(fRb);
+    const float scale_re = __frcp_rn(__fsub_rn(r, 2.0f));  // float(1.0/(double(r)-2.0)), exact sub
+    const float mhalf = __fmul_rn(-0.5f, scale_re);
+    float pn[D];
+    int lo[D], hi[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        pn[d] = __fmaf_rn((float)c[d], scale_re, mhalf);
+        float g1 = __fmul_rn(__fsub_rn(pn[d], scale_re), fRb);
+        g1 = g1 < 0.f ? 0.f : g1;
+        g1 = g1 > fRb1 ? fRb1 : g1;
+        lo[d] = (int)g1;
+        float g2 = __fmul_rn(__fadd_rn(pn[d], scale_re), fRb);
+        g2 = g2 < 0.f ? 0.f : g2;
+        g2 = g2 > fRb1 ? fRb1 : g2;
+        hi[d] = (int)g2;
+    }
+    bool m = false;
+    float area = 0.f;
+    for (int a = lo[0]; a <= hi[0]; a++) {
+        const float ra = fminf(__fmaf_rn((float)a, Rb_re, Rb_re), __fadd_rn(pn[0], scale_re));
+        const float la = fmaxf(__fmul_rn((float)a, Rb_re), __fsub_rn(pn[0], scale_re));
+        const float oa = __fsub_rn(ra, la);
+        for (int b = lo[1]; b <= hi[1]; b++) {
+            const float rb = fminf(__fmaf_rn((float)b, Rb_re, Rb_re), __fadd_rn(pn[1], scale_re));
+            const float lb = fmaxf(__fmul_rn((float)b, Rb_re), __fsub_rn(pn[1], scale_re));
+            const float ob = __fsub_rn(rb, lb);
+            if constexpr (D == 2) {
+                if (vxl[(size_t)a * Rb + b]) {
+                    m = true;
+                    area = __fmaf_rn(oa, ob, area);
+                }
+            } else {
+                const uint8_t *row = vxl + ((size_t)a * Rb + b) * Rb;
+                const float oab = __fmul_rn(oa, ob);
+                for (int cc = lo[D - 1]; cc <= hi[D - 1]; cc++) {
+                    if (row[cc]) {
+                        const float rc = fminf(__fmaf_rn((float)cc, Rb_re, Rb_re), __fadd_rn(pn[D - 1], scale_re));
+                        const float lc = fmaxf(__fmul_rn((float)cc, Rb_re), __fsub_rn(pn[D - 1], scale_re));
+                        m = true;
+                        area = __fmaf_rn(oab, __fsub_rn(rc, lc), area);
+                    }
+                }
+            }
+        }
+    }
+    area = __fmul_rn(area, fRb);
+    area = __fmul_rn(area, fRb);
+    if constexpr (D == 3) area = __fmul_rn(area, fRb);
+    overlap = (int32_t)__fmul_rn(area, 1000.0f);
+    return m;
+}
+
 }  // namespace cnc

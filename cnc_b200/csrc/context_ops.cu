@@ -24,59 +24,14 @@ query_mask_kernel(const int16_t *__restrict__ pts, const uint8_t *__restrict__ v
                   const int64_t *__restrict__ res_list, int32_t res_scalar, int64_t N) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const float fRb = (float)Rb, fRb1 = (float)(Rb - 1);
-    const float Rb_re = __frcp_rn(fRb);
     const float r = res_list ? (float)__ldg(res_list + i) : (float)res_scalar;
-    const float scale_re = __frcp_rn(__fsub_rn(r, 2.0f));  // float(1.0/(double(r)-2.0)), exact sub
-    const float mhalf = __fmul_rn(-0.5f, scale_re);
-    float pn[D];
-    int lo[D], hi[D];
+    int c[D];
 #pragma unroll
-    for (int d = 0; d < D; d++) {
-        pn[d] = __fmaf_rn((float)pts[i * D + d], scale_re, mhalf);
-        float g1 = __fmul_rn(__fsub_rn(pn[d], scale_re), fRb);
-        g1 = g1 < 0.f ? 0.f : g1;
-        g1 = g1 > fRb1 ? fRb1 : g1;
-        lo[d] = (int)g1;
-        float g2 = __fmul_rn(__fadd_rn(pn[d], scale_re), fRb);
-        g2 = g2 < 0.f ? 0.f : g2;
-        g2 = g2 > fRb1 ? fRb1 : g2;
-        hi[d] = (int)g2;
-    }
-    bool m = false;
-    float area = 0.f;
-    for (int a = lo[0]; a <= hi[0]; a++) {
-        const float ra = fminf(__fmaf_rn((float)a, Rb_re, Rb_re), __fadd_rn(pn[0], scale_re));
-        const float la = fmaxf(__fmul_rn((float)a, Rb_re), __fsub_rn(pn[0], scale_re));
-        const float oa = __fsub_rn(ra, la);
-        for (int b = lo[1]; b <= hi[1]; b++) {
-            const float rb = fminf(__fmaf_rn((float)b, Rb_re, Rb_re), __fadd_rn(pn[1], scale_re));
-            const float lb = fmaxf(__fmul_rn((float)b, Rb_re), __fsub_rn(pn[1], scale_re));
-            const float ob = __fsub_rn(rb, lb);
-            if constexpr (D == 2) {
-                if (vxl[(size_t)a * Rb + b]) {
-                    m = true;
-                    area = __fmaf_rn(oa, ob, area);
-                }
-            } else {
-                const uint8_t *row = vxl + ((size_t)a * Rb + b) * Rb;
-                const float oab = __fmul_rn(oa, ob);
-                for (int c = lo[D - 1]; c <= hi[D - 1]; c++) {
-                    if (row[c]) {
-                        const float rc = fminf(__fmaf_rn((float)c, Rb_re, Rb_re), __fadd_rn(pn[D - 1], scale_re));
-                        const float lc = fmaxf(__fmul_rn((float)c, Rb_re), __fsub_rn(pn[D - 1], scale_re));
-                        m = true;
-                        area = __fmaf_rn(oab, __fsub_rn(rc, lc), area);
-                    }
-                }
-            }
-        }
-    }
-    area = __fmul_rn(area, fRb);
-    area = __fmul_rn(area, fRb);
-    if constexpr (D == 3) area = __fmul_rn(area, fRb);
+    for (int d = 0; d < D; d++) c[d] = (int)pts[i * D + d];
+    int32_t ov;
+    const bool m = voxel_mask_overlap<D>(c, r, Rb, vxl, ov);
     mask[i] = (int16_t)m;
-    overlap[i] = (int32_t)__fmul_rn(area, 1000.0f);
+    overlap[i] = ov;
 }
 
 // ------------------------------------------------------------------------------------------

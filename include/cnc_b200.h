@@ -172,6 +172,26 @@ int cnc_field_fwd(const float *pos, const float *dirs, const float *aabb6_host,
                   const int32_t *offsets2, const int32_t *resolutions2, const float *blob,
                   float *sigma, float *rgb, float *geo, uint32_t N, cnc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Level-wise context model of the 3D grid, fused (one kernel per coded chunk).
+ * replaces the chunk body of encode_/decode_binary_vxl_mixPg_3D2D, examples/utils_bpp_acc.py:798-852
+ *   == :929-968: query_mask_3D -> compaction -> align_and_pack -> Encoding_xyz(points, n-3, n,
+ *   binary_vxl) -> context_model_3D -> align_and_pack -> overlap-weighted sum -> clamp.
+ *   pts [Nv,3] i16 voxel coords of level `level`, grouped by hash entry; seg [n_entries+1] i64 running
+ *   voxel counts with seg[0] == seg_base (a slice of unique_count_cumsum, utils_bpp_acc.py:803-808);
+ *   sign_bits = cnc_sign_pack of the whole 3D table (encoder: STE(params); decoder: the partially
+ *   reconstructed table); mlp_packed = cnc_context3d_mlp_floats() floats:
+ *   W1^T [25][32], b1 [32], W2^T [32][32], b2 [32], W3^T [32][8], b3 [8] of context_model_3D.
+ *   -> prob [n_entries,8] (clamped to [1e-6, 1-1e-6]; 0 for entries that are not coded),
+ *      mean [n_entries,8] unclamped (nullable), exist [n_entries] u8 (mask_exist, :823).
+ * ---------------------------------------------------------------------------------------- */
+uint32_t cnc_context3d_mlp_floats(void);
+int cnc_context3d_probs(const int16_t *pts, const int64_t *seg, int64_t n_entries,
+                        const uint8_t *binary_vxl, int32_t Rb, const uint8_t *sign_bits,
+                        const int32_t *offsets, const int32_t *resolutions, int32_t level, float Pg,
+                        const float *mlp_packed, float *prob, float *mean, uint8_t *exist,
+                        int64_t seg_base, cnc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
