@@ -133,6 +133,90 @@ def cpu_baseline(n=4096):
             "sample": f"{reps} x {n} samples of the same layout through oracle/ (C gather + numpy fp32 MLP)"}
 
 
+def codec_bench(dev, cpu_seconds=12.0):
+    """BASELINE metric (ii): context-model entropy encode + decode of the product hash tables (configs[2]):
+    L=12 3D levels (res 18..514, T=2^19) + 3 planes x 4 levels (T=2^17), F=8, ball occupancy, biased +-1 tables,
+    random-init context models.  MB/s = fp32 table bytes represented (161.3 MB) / wall time of the public
+    encode_/decode_binary_vxl_mixPg_3D2D call (probabilities + range coding + streams on the host).
+    CPU arm: the reference codes each stream with torchac on one CPU thread; oracle/ restates that coder in C
+    and is timed here on a bounded sample of the same (cdf, symbol) streams."""
+    from cnc_b200 import torchac as tac
+    from cnc_b200.context_models import CNC_context_models
+    from cnc_b200.gridencoder import GridEncoder
+    from oracle import oracle as o
+
+    torch.manual_seed(0)
+    t0 = time.perf_counter()
+    encs = [GridEncoder(num_dim=3, n_features=F, resolutions_list=R3, log2_hashmap_size=19, ste_binary=True).to(dev)] + \
+           [GridEncoder(num_dim=2, n_features=F, resolutions_list=R2, log2_hashmap_size=17, ste_binary=True).to(dev) for _ in range(3)]
+    with torch.no_grad():
+        for e in encs:
+            e.params.copy_(torch.where(torch.rand_like(e.params) < 0.7, 0.5, -0.5))
+    cm = CNC_context_models(num_dim=3, resolutions_list=R3, resolutions_list_2D=R2, log2_hashmap_size=19,
+                            log2_hashmap_size_2D=17, n_features=F, sample_num=150000, max_context_layer_num=3,
+                            ste_binary=True, Rb=128, skip_levels_3D=(0, 1, 2), skip_levels_2D=(0,), device=dev)
+    with torch.no_grad():
+        cm.context_model_3D[4].bias.fill_(0.6)
+        for sq in cm.context_model_2D:
+            sq[0].bias.fill_(0.6)
+    c = (torch.arange(128, device=dev) + 0.5) / 128 * 3 - 1.5
+    X, Y, Z = torch.meshgrid(c, c, c, indexing="ij")
+    vxl = (X * X + Y * Y + Z * Z <= 1.0).unsqueeze(0)   # radius-1 ball in the +-1.5 aabb (15.5 % of the cells)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+    captured = {}
+    orig = tac.encode_streams
+
+    def spy(c1s, syms):
+        captured["c1"], captured["sym"] = c1s, syms
+        return orig(c1s, syms)
+
+    tac.encode_streams = spy
+    try:
+        cm.encode_binary_vxl_mixPg_3D2D(*encs, vxl, "bench", return_streams=True)  # warm-up (+ capture the streams)
+    finally:
+        tac.encode_streams = orig
+    enc_s, dec_s = [], []
+    for _ in range(3):
+        torch.cuda.synchronize(); t = time.perf_counter()
+        Pgs, est_MB, coded_MB, streams = cm.encode_binary_vxl_mixPg_3D2D(*encs, vxl, "bench", return_streams=True)
+        torch.cuda.synchronize(); enc_s.append(time.perf_counter() - t)
+        recs = [torch.ones_like(e.params) for e in encs]
+        torch.cuda.synchronize(); t = time.perf_counter()
+        out = cm.decode_binary_vxl_mixPg_3D2D(*encs, *recs, vxl, Pgs, "bench", streams=streams)
+        torch.cuda.synchronize(); dec_s.append(time.perf_counter() - t)
+    ok = all(bool(((torch.where(e.params >= 0, 1.0, -1.0) == r) | (r == 1)).all()) for e, r in zip(encs, out))
+    n_params = sum(e.params.numel() for e in encs)
+    table_MB = n_params * 4 / 1e6
+    n_sym = sum(int(x.numel()) for x in captured["sym"])
+    # CPU coder on a bounded sample: streams in descending size until the time budget is used
+    order = sorted(range(len(captured["sym"])), key=lambda k: -captured["sym"][k].numel())
+    done_sym, t_cpu = 0, 0.0
+    for k in order:
+        c1 = captured["c1"][k].cpu().numpy().view(np.uint16)
+        sy = captured["sym"][k].cpu().numpy()
+        t = time.perf_counter()
+        data = o.ac_encode(c1, sy)
+        o.ac_decode(c1, data)
+        t_cpu += time.perf_counter() - t
+        done_sym += sy.size
+        if t_cpu > cpu_seconds:
+            break
+    cpu_sym_per_s = done_sym / t_cpu            # encode + decode of each symbol, one thread
+    enc, dec = min(enc_s), min(dec_s)
+    return {"workload": "configs[2]: product tables L=12 T=2^19 + 3x4 planes T=2^17, F=8, ball occupancy, 33 streams",
+            "table_MB_fp32": table_MB, "table_MB_1bit": n_params / 8 / 1e6, "coded_MiB": coded_MB, "estimated_MiB": est_MB,
+            "symbols": n_sym, "encode_s": enc, "decode_s": dec, "encode_MBps": table_MB / enc, "decode_MBps": table_MB / dec,
+            "encode_Msym_per_s": n_sym / enc / 1e6, "decode_Msym_per_s": n_sym / dec / 1e6, "roundtrip_ok": ok,
+            "setup_s": t_setup,
+            "cpu_baseline": {"kind": "port", "cores": 1, "unit": "MB/s",
+                             "value": table_MB / (n_sym / cpu_sym_per_s),
+                             "Msym_per_s_enc_plus_dec": cpu_sym_per_s / 1e6,
+                             "sample": f"{done_sym} of {n_sym} symbols (largest streams first) through oracle/ C range coder, "
+                                       "encode+decode, one thread; MB/s = table bytes / (coder time for all symbols, "
+                                       "encode+decode); probabilities not included (the reference computes them on the GPU)"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -141,6 +225,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=int, default=262144)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-codec", action="store_true", help="skip the entropy encode/decode measurement (metric ii)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
 
@@ -290,6 +375,10 @@ def main():
         line["e2e"]["h2d_bytes_per_step"] = line["e2e"]["h2d_bytes_per_step"]
     elif world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
+    if a.impl == "ours" and world == 1 and not a.no_codec:
+        del field, model
+        torch.cuda.empty_cache()
+        line["codec"] = codec_bench(dev)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
