@@ -537,12 +537,15 @@ class CNC_context_models(nn.Module):
             return [o.to(torch.float32) * 2 - 1 for o in outs]
 
         F = self.n_features
+        skip = [n for n in range(self.n_levels) if n in self.skip_levels_3D or n >= self.Pg_level]
+        if skip:   # zeroth-order levels do not depend on anything: one launch
+            outs = decode([f"{filename_prefix}_3D{n}.b" for n in skip],
+                          [Pgs_dict["3D" + str(n)].expand((self.offs[n + 1] - self.offs[n]) * F) for n in skip])
+            for n, sout in zip(skip, outs):
+                params_q_xyz_rec[self.offs[n]:self.offs[n + 1]] = sout.view(-1, F)
         for n in range(self.n_levels):
             Pg_n = Pgs_dict["3D" + str(n)]
-            if n in self.skip_levels_3D or n >= self.Pg_level:
-                rows = self.offs[n + 1] - self.offs[n]
-                (sout,) = decode([f"{filename_prefix}_3D{n}.b"], [Pg_n.expand(rows * F)])
-                params_q_xyz_rec[self.offs[n]:self.offs[n + 1]] = sout.view(rows, F)
+            if n in skip:
                 continue
             names, ps_l, rows_l = [], [], []
             for sn, (lo, hi) in enumerate(self._chunks(n)):   # chunks of a level are independent streams
@@ -556,18 +559,21 @@ class CNC_context_models(nn.Module):
         planes = self._planes(binary_vxl)
         finest = params_q_xyz_rec[self.offs[-2]:self.offs[-1]]
         recs = {"xy": params_q_xy_rec, "xz": params_q_xz_rec, "yz": params_q_yz_rec}
-        for axis, Enc in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz)):
-            rec = recs[axis]
-            pn = self.get_pn_embed_frac(finest, idx_coords2, axis=axis) if self.use_dimension_wise else None
-            for n in range(self.n_levels_2D):
+        axes = (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz))
+        pns = {a: (self.get_pn_embed_frac(finest, idx_coords2, axis=a) if self.use_dimension_wise else None) for a, _ in axes}
+        for n in range(self.n_levels_2D):   # the three planes are independent of each other: one launch per level
+            names, ps_l, where = [], [], []
+            for axis, Enc in axes:
                 Pg_n = Pgs_dict[axis + str(n)]
-                name = f"{filename_prefix}_{axis}{n}.b"
+                names.append(f"{filename_prefix}_{axis}{n}.b")
                 if n in self.skip_levels_2D or n >= self.Pg_level_2D:
                     rows = self.offs_2D[n + 1] - self.offs_2D[n]
-                    (sout,) = decode([name], [Pg_n.expand(rows * F)])
-                    rec[self.offs_2D[n]:self.offs_2D[n + 1]] = sout.view(rows, F)
+                    ps_l.append(Pg_n.expand(rows * F))
+                    where.append(slice(self.offs_2D[n], self.offs_2D[n + 1]))
                 else:
-                    mean, rows, _ = self._probs_2D(Enc, rec, planes[axis], n, pn, Pg_n)
-                    (sout,) = decode([name], [torch.clamp(mean, 1e-6, 1 - 1e-6).reshape(-1)])
-                    rec[rows, :] = sout.view(-1, F)
+                    mean, rows, _ = self._probs_2D(Enc, recs[axis], planes[axis], n, pns[axis], Pg_n)
+                    ps_l.append(torch.clamp(mean, 1e-6, 1 - 1e-6).reshape(-1))
+                    where.append(rows)
+            for (axis, _), sout, w in zip(axes, decode(names, ps_l), where):
+                recs[axis][w] = sout.view(-1, F)
         return params_q_xyz_rec, params_q_xy_rec, params_q_xz_rec, params_q_yz_rec

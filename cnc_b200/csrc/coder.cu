@@ -30,23 +30,51 @@ __global__ void cdf_from_p_kernel(const float *__restrict__ p, uint16_t *__restr
     }
 }
 
-constexpr int TILE = 1024;  // symbols staged per step (32 lanes x 32)
+constexpr int TILE = 2048;  // symbols staged per step
+
+// The serial part of a stream is one dependent chain per symbol:
+//   r = high-low -> t = (r*c + c) >> 16 -> select -> x = low^high -> nm = clz(x) -> ku = clz of the underflow run
+//   -> one combined shift by S = nm + ku.
+// E1/E2 (nm matching leading bits) and E3 (ku underflow positions: low = 0 1^ku.., high = 1 0^ku..) of the
+// reference's bit-at-a-time loop are resolved together: after the update span >= 2^14 always holds for
+// c1 in [1, 65535] (span > 2^30 before the symbol), so S <= 18 and a single 32-bit shift suffices; the S == 32
+// corner of degenerate CDFs (c1 == 0) is kept correct by the clamped funnel shifts.
+// Everything that is not on that chain (symbol fetch, bit packing, stores) is written so that it can issue in
+// the chain's stall slots.
+struct CoderState {
+    uint32_t low = 0u, high = 0xFFFFFFFFu;
+};
+
+// returns nm (common prefix length) and ku (underflow run); updates the state.  Precondition c in [1, 65535]
+// (what cnc_cdf_from_p / torchac's quantiser produce): then span >= 2^14 after the update, nm + ku <= 18.
+__device__ __forceinline__ void coder_step(CoderState &st, uint32_t c, uint32_t s, uint32_t &low2, uint32_t &nm, uint32_t &ku) {
+    const uint32_t r = st.high - st.low;                                   // span - 1
+    const uint32_t t = (uint32_t)(((uint64_t)r * c + c) >> 16);            // (span * c1) >> 16
+    const uint32_t nl = st.low + t;
+    low2 = s ? nl : st.low;
+    const uint32_t high2 = s ? st.high : nl - 1u;
+    nm = __clz(low2 ^ high2);
+    const uint32_t w = ~low2 | high2;                                      // 0 exactly where (low, high) = (1, 0)
+    ku = __clz(((w << nm) << 1) | 0x2000u);                                // run after the first differing bit (bounded by span >= 2^14)
+    const uint32_t S = nm + ku;
+    st.low = (low2 << S) & 0x7FFFFFFFu;
+    st.high = __funnelshift_l(0xFFFFFFFFu, high2, S) | 0x80000000u;
+}
 
 struct BitWriter {
     uint64_t acc = 0;   // bits, MSB first
     uint32_t nb = 0;    // valid bits in acc (< 32 between calls)
     uint32_t *dst;      // word cursor
     uint64_t words = 0, cap_words;
-    __device__ __forceinline__ void put(uint32_t v, uint32_t n) {  // 0 <= n <= 32
-        if (n == 0) return;
-        acc |= ((uint64_t)v << (32 - n)) << (32 - nb);
+    __device__ __forceinline__ void put(uint32_t v, uint32_t n) {  // 0 <= n <= 32, v < 2^n
+        acc |= ((uint64_t)v << (32u - n)) << (32u - nb);  // v's n bits go right after the nb valid ones
         nb += n;
-        if (nb >= 32) {
-            const uint32_t w = (uint32_t)(acc >> 32);
-            if (words < cap_words) dst[words] = __byte_perm(w, 0, 0x0123);
+        if (nb >= 32u) {
+            const uint32_t wv = (uint32_t)(acc >> 32);
+            if (words < cap_words) dst[words] = __byte_perm(wv, 0, 0x0123);
             words++;
             acc <<= 32;
-            nb -= 32;
+            nb -= 32u;
         }
     }
     __device__ __forceinline__ void put_run(uint32_t bit, uint64_t count) {
@@ -61,7 +89,7 @@ __global__ void __launch_bounds__(32)
 ac_encode_kernel(const uint16_t *__restrict__ c1, const uint8_t *__restrict__ sym,
                  const int64_t *__restrict__ sym_off, uint8_t *__restrict__ out,
                  const int64_t *__restrict__ out_off, int64_t *__restrict__ out_len) {
-    __shared__ uint32_t tile[2][TILE];
+    __shared__ __align__(16) uint32_t tile[2][TILE];
     const int k = blockIdx.x, lane = threadIdx.x;
     const int64_t s0 = sym_off[k], n = sym_off[k + 1] - s0;
     const int64_t o0 = out_off[k], cap = out_off[k + 1] - o0;
@@ -71,7 +99,7 @@ ac_encode_kernel(const uint16_t *__restrict__ c1, const uint8_t *__restrict__ sy
     BitWriter bw;
     bw.dst = reinterpret_cast<uint32_t *>(out + o0);
     bw.cap_words = (uint64_t)(cap / 4);
-    uint32_t low = 0, high = 0xFFFFFFFFu;
+    CoderState st;
     uint64_t pending = 0;
 
     auto stage = [&](int buf, int64_t base) {
@@ -88,30 +116,29 @@ ac_encode_kernel(const uint16_t *__restrict__ c1, const uint8_t *__restrict__ sy
         if (base + TILE < n) stage(buf ^ 1, base + TILE);  // next tile in flight while lane 0 codes
         if (lane == 0) {
             const int m = (int)((n - base) < TILE ? (n - base) : TILE);
-            for (int j = 0; j < m; j++) {
-                const uint32_t pk = tile[buf][j];
-                const uint32_t c = pk & 0xFFFFu, s = pk >> 16;
-                const uint32_t r = high - low;                       // span - 1
-                const uint32_t t = (uint32_t)(((uint64_t)r * c + c) >> 16);  // (span*c1) >> 16
-                if (s) low += t; else high = low + t - 1u;
-                // E1/E2: shift out the matching leading bits in one go
-                const uint32_t nm = __clz(low ^ high);
-                if (nm) {
-                    const uint32_t lead = low >> (32 - nm);          // the nm matched bits
-                    const uint32_t b0 = lead >> (nm - 1);
-                    bw.put(b0, 1);
-                    if (pending) { bw.put_run(b0 ^ 1u, pending); pending = 0; }
-                    if (nm > 1) bw.put(lead & ((1u << (nm - 1)) - 1u), nm - 1);
-                    low = (nm == 32) ? 0u : (low << nm);
-                    high = (nm == 32) ? 0xFFFFFFFFu : ((high << nm) | ((1u << nm) - 1u));
-                }
-                // E3: low = 01.., high = 10.. -> count the underflow positions
-                uint32_t ku = __clz(((~low) << 1) | (high << 1));
-                ku = ku > 31u ? 31u : ku;
-                if (ku) {
-                    pending += ku;
-                    low = (low << ku) & 0x7FFFFFFFu;
-                    high = (high << ku) | 0x80000000u | ((1u << ku) - 1u);
+            for (int j0 = 0; j0 < m; j0 += 4) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(&tile[buf][j0]);
+                const uint32_t pk[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (j0 + u < m) {
+                        uint32_t low2, nm, ku;
+                        coder_step(st, pk[u] & 0xFFFFu, pk[u] >> 16, low2, nm, ku);
+                        if (nm) {
+                            const uint32_t lead = low2 >> (32u - nm);  // the nm matched bits
+                            if (pending) {
+                                const uint32_t b0 = lead >> (nm - 1u);
+                                bw.put(b0, 1);
+                                bw.put_run(b0 ^ 1u, pending);
+                                if (nm > 1u) bw.put(lead & ((1u << (nm - 1u)) - 1u), nm - 1u);
+                            } else {
+                                bw.put(lead, nm);
+                            }
+                            pending = ku;
+                        } else {
+                            pending += ku;
+                        }
+                    }
                 }
             }
         }
@@ -120,7 +147,7 @@ ac_encode_kernel(const uint16_t *__restrict__ c1, const uint8_t *__restrict__ sy
     }
     if (lane == 0) {
         pending += 1;
-        const uint32_t b = low < 0x40000000u ? 0u : 1u;
+        const uint32_t b = st.low < 0x40000000u ? 0u : 1u;
         bw.put(b, 1);
         bw.put_run(b ^ 1u, pending);
         // flush: whole words are out; the remaining nb (<32) bits go byte by byte, zero padded
@@ -138,56 +165,34 @@ ac_encode_kernel(const uint16_t *__restrict__ c1, const uint8_t *__restrict__ sy
     }
 }
 
-struct BitReader {
-    const uint8_t *src;
-    int64_t nbytes, pos = 0;  // pos = next byte to fetch
-    uint64_t res = 0;         // upcoming bits, MSB first
-    uint32_t navail = 0;
-    __device__ __forceinline__ uint32_t fetch_word() {
-        uint32_t w = 0;
-        if (pos + 4 <= nbytes) {
-            w = __byte_perm(*reinterpret_cast<const uint32_t *>(src + pos), 0, 0x0123);
-        } else {
-            for (int b = 0; b < 4; b++) {
-                const int64_t q = pos + b;
-                w = (w << 8) | (q < nbytes ? (uint32_t)src[q] : 0u);  // zeros past the end (torchac)
-            }
-        }
-        pos += 4;
-        return w;
-    }
-    __device__ __forceinline__ void refill() {
-        if (navail <= 32) {
-            res |= (uint64_t)fetch_word() << (32 - navail);
-            navail += 32;
-        }
-    }
-    __device__ __forceinline__ uint32_t get(uint32_t n) {  // 0 <= n <= 32
-        refill();
-        const uint32_t v = n ? (uint32_t)(res >> (64 - n)) : 0u;
-        res <<= n;  // n <= 32 < 64
-        navail -= n;
-        return v;
-    }
-};
-
+// input bits: the stream's bytes are staged (big-endian words) through shared memory by the whole warp, lane 0
+// keeps a 64-bit MSB-aligned reservoir
 __global__ void __launch_bounds__(32)
 ac_decode_kernel(const uint16_t *__restrict__ c1, const int64_t *__restrict__ sym_off,
                  const uint8_t *__restrict__ in, const int64_t *__restrict__ in_off,
                  const int64_t *__restrict__ in_len, uint8_t *__restrict__ sym) {
-    __shared__ uint16_t ctile[2][TILE];
-    __shared__ uint8_t stile[TILE];
+    __shared__ __align__(16) uint16_t ctile[2][TILE];
+    __shared__ __align__(16) uint8_t stile[TILE];
+    constexpr int WT = 1024;                       // input words per staging tile
+    __shared__ uint32_t wtile[2][WT];
     const int k = blockIdx.x, lane = threadIdx.x;
     const int64_t s0 = sym_off[k], n = sym_off[k + 1] - s0;
     c1 += s0;
     sym += s0;
+    const uint8_t *src = in + in_off[k];
+    const int64_t nbytes = in_len[k];
 
-    BitReader br;
-    br.src = in + in_off[k];
-    br.nbytes = in_len[k];
-    uint32_t low = 0, high = 0xFFFFFFFFu, value = 0;
-    if (lane == 0) value = br.get(32);
-
+    auto stage_words = [&](int wb, int64_t wbase) {   // words [wbase, wbase+WT), zeros past the end (torchac)
+        for (int j = lane; j < WT; j += 32) {
+            const int64_t p = (wbase + j) * 4;
+            uint32_t w = 0;
+            if (p + 4 <= nbytes) w = __byte_perm(*reinterpret_cast<const uint32_t *>(src + p), 0, 0x0123);
+            else if (p < nbytes) {
+                for (int b = 0; b < 4; b++) w = (w << 8) | (p + b < nbytes ? (uint32_t)src[p + b] : 0u);
+            }
+            wtile[wb][j] = w;
+        }
+    };
     auto stage = [&](int buf, int64_t base) {
 #pragma unroll 8
         for (int j = lane; j < TILE; j += 32) {
@@ -195,40 +200,70 @@ ac_decode_kernel(const uint16_t *__restrict__ c1, const int64_t *__restrict__ sy
             ctile[buf][j] = (i < n) ? __ldg(c1 + i) : (uint16_t)1;
         }
     };
+    stage_words(0, 0);
+    stage_words(1, WT);
     if (n > 0) stage(0, 0);
     __syncwarp();
+
+    // reservoir
+    uint64_t res = 0;
+    uint32_t navail = 0;
+    int64_t wpos = 0;          // next word index to consume
+    int64_t staged_hi = 2 * WT; // words [0, staged_hi) have been staged
+    auto refill = [&]() {      // lane 0 only: navail < 32 -> append one word
+        const uint32_t w = wtile[(wpos / WT) & 1][wpos % WT];
+        res |= (uint64_t)w << (32u - navail);
+        navail += 32u;
+        wpos++;
+    };
+    CoderState st;
+    uint32_t value = 0;
+    if (lane == 0) {
+        refill();
+        value = (uint32_t)(res >> 32);
+        res <<= 32;
+        navail -= 32u;
+        refill();
+    }
     int buf = 0;
     for (int64_t base = 0; base < n; base += TILE) {
         if (base + TILE < n) stage(buf ^ 1, base + TILE);
         const int m = (int)((n - base) < TILE ? (n - base) : TILE);
-        if (lane == 0) {
-            for (int j = 0; j < m; j++) {
-                const uint32_t c = ctile[buf][j];
-                const uint32_t r = high - low;
-                const uint64_t lhs = (uint64_t)r * c + c;                       // c1 * span
-                const uint64_t rhs = (((uint64_t)(value - low) + 1) << 16) - 1;  // (value-low+1)*2^16 - 1
-                const uint32_t s = lhs <= rhs;                                  // c1 <= count
-                stile[j] = (uint8_t)s;
-                const uint32_t t = (uint32_t)(lhs >> 16);
-                if (s) low += t; else high = low + t - 1u;
-                const uint32_t nm = __clz(low ^ high);
-                if (nm) {
-                    const uint32_t bits = br.get(nm);
-                    low = (nm == 32) ? 0u : (low << nm);
-                    high = (nm == 32) ? 0xFFFFFFFFu : ((high << nm) | ((1u << nm) - 1u));
-                    value = (nm == 32) ? bits : ((value << nm) | bits);
-                }
-                uint32_t ku = __clz(((~low) << 1) | (high << 1));
-                ku = ku > 31u ? 31u : ku;
-                if (ku) {
-                    const uint32_t bits = br.get(ku);
-                    low = (low << ku) & 0x7FFFFFFFu;
-                    high = (high << ku) | 0x80000000u | ((1u << ku) - 1u);
-                    value = ((value << ku) ^ 0x80000000u) + bits;  // k x {value -= 2^30; shift in a bit}
+        // a tile of TILE symbols consumes at most TILE * 18 bits < WT words only if TILE*18/32 <= WT: 2048*18/32 = 1152 > 1024,
+        // so the word tiles are topped up in two halves of the symbol tile
+        for (int half = 0; half < 2; half++) {
+            const int jb = half * (TILE / 2), je = min(m, jb + TILE / 2);
+            if (lane == 0) {
+                for (int j = jb; j < je; j++) {
+                    const uint32_t c = ctile[buf][j];
+                    // symbol: largest s with cdf[s] <= count  <=>  c1 * span <= ((value - low + 1) << 16) - 1
+                    const uint32_t r = st.high - st.low;
+                    const uint64_t lhs = (uint64_t)r * c + c;
+                    const uint64_t rhs = (((uint64_t)(value - st.low) + 1ull) << 16) - 1ull;
+                    const uint32_t s = lhs <= rhs;
+                    stile[j] = (uint8_t)s;
+                    uint32_t low2, nm, ku;
+                    coder_step(st, c, s, low2, nm, ku);
+                    const uint32_t S = nm + ku;
+                    if (S) {
+                        const uint32_t bits = (uint32_t)(res >> (64u - S));
+                        res <<= S;
+                        navail -= S;
+                        value = (value << S) | bits;
+                        if (ku) value ^= 0x80000000u;   // ku x {value -= 2^30; shift in a bit}
+                        if (navail < 32u) refill();
+                    }
                 }
             }
+            __syncwarp();
+            // keep two word tiles ahead of the consumer
+            const int64_t wp = __shfl_sync(0xFFFFFFFFu, wpos, 0);
+            while (staged_hi - wp <= WT) {
+                stage_words((int)((staged_hi / WT) & 1), staged_hi);
+                staged_hi += WT;
+            }
+            __syncwarp();
         }
-        __syncwarp();
         for (int j = lane; j < m; j += 32) sym[base + j] = stile[j];
         __syncwarp();
         buf ^= 1;
