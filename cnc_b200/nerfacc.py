@@ -1,0 +1,416 @@
+"""Host-side mirror of the slice of (vendored, patched) nerfacc 0.5.3 that the CNC hot path calls.
+
+    OccGridEstimator(roi_aabb, resolution, levels)            nerfacc/estimators/occ_grid.py:19-424
+        .sampling(rays_o, rays_d, sigma_fn=..., render_step_size=..., stratified=..., ...)   :88-239
+        .update_every_n_steps(step, occ_eval_fn, occ_thre, ema_decay, warmup_steps, n)        :242-277
+        .binaries  .aabbs  .occs
+    ray_aabb_intersect, traverse_grids                        nerfacc/grid.py:20-91, :94-194
+    rendering (rgb_sigma_fn returns (rgbs, sigmas, positions): the CNC patch)    nerfacc/volrend.py:14-160
+    render_weight_from_density / _transmittance_ / _visibility_               :211-266, :314-364, :423-482
+    accumulate_along_rays, accumulate_along_rays_                               :485-575
+    pack_info, inclusive_sum, exclusive_sum, inclusive_prod, exclusive_prod     nerfacc/pack.py, scan.py
+
+Same names, arguments and return values.  The CUDA side is csrc/march_render.cu: thread-per-ray DDA
+(two passes + one scan, like grid.cu:441-507), and a fused weights + accumulation kernel that replaces
+exclusive_sum + exp + 3 x index_add_ (no atomics, fixed summation order).  No CPU path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Tuple, Union
+
+import torch
+from torch import Tensor
+
+from ._lib import check, lib, need_cuda, ptr, stream
+
+
+# ------------------------------------------------------------------------------------------ data specs
+@dataclass
+class RaySamples:
+    """nerfacc/data_specs.py RaySamples (the fields the callers read)."""
+    vals: Tensor
+    packed_info: Optional[Tensor] = None
+    ray_indices: Optional[Tensor] = None
+    is_valid: Optional[Tensor] = None
+
+
+@dataclass
+class RayIntervals:
+    """nerfacc/data_specs.py RayIntervals.  Edges are stored per sample (left, right), so
+    `vals[is_left]` / `vals[is_right]` are t_starts / t_ends like in occ_grid.py:188-189."""
+    vals: Tensor
+    packed_info: Optional[Tensor] = None
+    ray_indices: Optional[Tensor] = None
+    is_left: Optional[Tensor] = None
+    is_right: Optional[Tensor] = None
+
+
+# ------------------------------------------------------------------------------------------ pack / scans
+def pack_info(ray_indices: Tensor, n_rays: Optional[int] = None) -> Tensor:
+    """(n_rays, 2) [start, count] of every ray's chunk; ray_indices must be sorted (nerfacc/pack.py:10-49)."""
+    assert ray_indices.dim() == 1
+    if not ray_indices.is_cuda:
+        raise NotImplementedError("Only support cuda inputs.")
+    if n_rays is None:
+        n_rays = int(ray_indices.max()) + 1
+    cnt = torch.zeros(n_rays, dtype=torch.long, device=ray_indices.device)
+    cnt.index_add_(0, ray_indices, torch.ones_like(ray_indices))
+    starts = cnt.cumsum(0) - cnt
+    return torch.stack([starts, cnt], dim=-1)
+
+
+def _scan(inputs: Tensor, packed_info: Optional[Tensor], op: int, inclusive: bool, indices=None) -> Tensor:
+    if packed_info is None:
+        if indices is not None:
+            packed_info = pack_info(indices)
+        else:   # batched [n_rays, n_samples] layout
+            n, m = inputs.shape
+            packed_info = torch.stack([torch.arange(n, device=inputs.device) * m,
+                                       torch.full((n,), m, device=inputs.device)], -1)
+    x = inputs.contiguous().float()
+    need_cuda(inputs=x, packed_info=packed_info)
+    out = torch.empty_like(x)
+    pk = packed_info.contiguous().to(torch.int64)
+    check(lib().cnc_packed_scan(ptr(x), ptr(pk), pk.shape[0], ptr(out), op, int(inclusive), 0, stream()))
+    return out
+
+
+def inclusive_sum(inputs, packed_info=None, indices=None):
+    """nerfacc/scan.py:14-53"""
+    return _scan(inputs, packed_info, 0, True, indices)
+
+
+def exclusive_sum(inputs, packed_info=None, indices=None):
+    """nerfacc/scan.py:56-100"""
+    return _scan(inputs, packed_info, 0, False, indices)
+
+
+def inclusive_prod(inputs, packed_info=None, indices=None):
+    """nerfacc/scan.py:103-146"""
+    return _scan(inputs, packed_info, 1, True, indices)
+
+
+def exclusive_prod(inputs, packed_info=None, indices=None):
+    """nerfacc/scan.py:149-194"""
+    return _scan(inputs, packed_info, 1, False, indices)
+
+
+# ------------------------------------------------------------------------------------------ marching
+@torch.no_grad()
+def ray_aabb_intersect(rays_o: Tensor, rays_d: Tensor, aabbs: Tensor, near_plane: float = -float("inf"),
+                       far_plane: float = float("inf"), miss_value: float = float("inf")):
+    """(t_mins, t_maxs, hits), each [n_rays, n_aabbs].  nerfacc/grid.py:20-91"""
+    assert rays_o.ndim == 2 and rays_o.shape[-1] == 3 and rays_d.shape == rays_o.shape
+    assert aabbs.ndim == 2 and aabbs.shape[-1] == 6
+    o, d, bb = rays_o.contiguous().float(), rays_d.contiguous().float(), aabbs.contiguous().float()
+    need_cuda(rays_o=o, rays_d=d, aabbs=bb)
+    n, m = o.shape[0], bb.shape[0]
+    t_mins = torch.empty(n, m, device=o.device)
+    t_maxs = torch.empty(n, m, device=o.device)
+    hits = torch.empty(n, m, dtype=torch.uint8, device=o.device)
+    check(lib().cnc_ray_aabb_intersect(ptr(o), ptr(d), n, float(near_plane), float(far_plane), ptr(bb), m, float(miss_value),
+                                       ptr(t_mins), ptr(t_maxs), ptr(hits), stream()))
+    return t_mins, t_maxs, hits.bool()
+
+
+@torch.no_grad()
+def traverse_grids(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tensor, near_planes: Optional[Tensor] = None,
+                   far_planes: Optional[Tensor] = None, step_size: Optional[float] = 1e-3, cone_angle: Optional[float] = 0.0,
+                   traverse_steps_limit: Optional[int] = None, over_allocate: Optional[bool] = False,
+                   rays_mask: Optional[Tensor] = None, t_sorted: Optional[Tensor] = None, t_indices: Optional[Tensor] = None,
+                   hits: Optional[Tensor] = None) -> Tuple[RayIntervals, RaySamples, Tensor]:
+    """March rays through the (multi-level) occupancy grid.  nerfacc/grid.py:94-194.
+    `over_allocate` is accepted for compatibility; sizes are always exact (count pass, scan, fill pass)."""
+    o, d = rays_o.contiguous().float(), rays_d.contiguous().float()
+    need_cuda(rays_o=o, rays_d=d, binaries=binaries, aabbs=aabbs)
+    n, dev = o.shape[0], o.device
+    if near_planes is None:
+        near_planes = torch.zeros_like(o[:, 0])
+    if far_planes is None:
+        far_planes = torch.full_like(o[:, 0], float("inf"))
+    if rays_mask is None:
+        rays_mask_u8 = None
+    else:
+        rays_mask_u8 = rays_mask.contiguous().to(torch.uint8)
+    if traverse_steps_limit is None:
+        traverse_steps_limit = -1
+    if t_sorted is None or t_indices is None or hits is None:
+        t_mins, t_maxs, hits = ray_aabb_intersect(o, d, aabbs)
+        t_sorted, t_indices = torch.sort(torch.cat([t_mins, t_maxs], dim=-1), dim=-1)
+    G = aabbs.shape[0]
+    bins = binaries.contiguous()
+    bins_u8 = bins.view(torch.uint8) if bins.dtype == torch.bool else bins.to(torch.uint8)
+    hits_u8 = hits.contiguous().to(torch.uint8)
+    bb = aabbs.contiguous().float()
+    ts, ti = t_sorted.contiguous().float(), t_indices.contiguous().to(torch.int64)
+    nearp, farp = near_planes.contiguous().float(), far_planes.contiguous().float()
+    cnt = torch.empty(n, dtype=torch.int64, device=dev)
+    term = torch.empty(n, device=dev)
+    L = lib()
+
+    def run(starts, t0, t1, ri, c, tm):
+        check(L.cnc_traverse_grids(ptr(o), ptr(d), ptr(rays_mask_u8), n, G, bins.shape[-3], bins.shape[-2], bins.shape[-1],
+                                   ptr(bins_u8), ptr(bb), ptr(hits_u8), ptr(ts), ptr(ti), ptr(nearp), ptr(farp),
+                                   float(step_size), float(cone_angle), int(traverse_steps_limit), ptr(starts), ptr(c),
+                                   ptr(t0), ptr(t1), ptr(ri), ptr(tm), stream()))
+
+    run(None, None, None, None, cnt, None)
+    starts = cnt.cumsum(0) - cnt
+    total = int(cnt.sum())                       # the one host sync of the reference too (data_spec.hpp:91)
+    t0 = torch.empty(total, device=dev)
+    t1 = torch.empty(total, device=dev)
+    ri = torch.empty(total, dtype=torch.int64, device=dev)
+    if total:
+        run(starts, t0, t1, ri, None, term)
+    else:
+        term.copy_(nearp)
+    packed = torch.stack([starts, cnt], dim=-1)
+    vals = torch.stack([t0, t1], dim=-1).reshape(-1)
+    left = torch.zeros(2 * total, dtype=torch.bool, device=dev)
+    left[0::2] = True
+    intervals = RayIntervals(vals=vals, packed_info=torch.stack([starts * 2, cnt * 2], -1), ray_indices=ri.repeat_interleave(2),
+                             is_left=left, is_right=~left)
+    samples = RaySamples(vals=(t0 + t1) * 0.5, packed_info=packed, ray_indices=ri,
+                         is_valid=torch.ones(total, dtype=torch.bool, device=dev))
+    return intervals, samples, term
+
+
+# ------------------------------------------------------------------------------------------ volume rendering
+def _packed(packed_info, ray_indices, n_rays, like):
+    if packed_info is None:
+        if ray_indices is None:
+            raise ValueError("flattened samples need packed_info or ray_indices")
+        packed_info = pack_info(ray_indices, n_rays)
+    return packed_info.contiguous().to(torch.int64)
+
+
+class _RenderDensity(torch.autograd.Function):
+    """weights / transmittance / alphas from densities with the analytic backward of
+    w_i = exp(-sum_{j<i} s_j d_j) (1 - exp(-s_i d_i))  (volrend.py:211-266,314-364; scan backward scan.cu:100-110)."""
+
+    @staticmethod
+    def forward(ctx, t_starts, t_ends, sigmas, packed_info, prefix_trans):
+        t0, t1, sg = t_starts.contiguous().float(), t_ends.contiguous().float(), sigmas.contiguous().float()
+        need_cuda(t_starts=t0, t_ends=t1, sigmas=sg)
+        w, T, al = torch.empty_like(sg), torch.empty_like(sg), torch.empty_like(sg)
+        pt = None if prefix_trans is None else prefix_trans.contiguous().float()
+        check(lib().cnc_render_from_density(ptr(t0), ptr(t1), ptr(sg), None, ptr(packed_info), packed_info.shape[0], ptr(pt),
+                                            ptr(w), ptr(T), ptr(al), None, None, None, stream()))
+        ctx.save_for_backward(t0, t1, T, al, packed_info)
+        return w, T, al
+
+    @staticmethod
+    def backward(ctx, gw, gT, ga):
+        t0, t1, T, al, packed_info = ctx.saved_tensors
+        dt = t1 - t0
+        gw = torch.zeros_like(T) if gw is None else gw
+        gT = torch.zeros_like(T) if gT is None else gT
+        ga = torch.zeros_like(T) if ga is None else ga
+        # d/d(sd_k): alpha term at k, transmittance term for every later sample of the ray
+        g_alpha = (gw * T + ga) * (1 - al)
+        g_trans = (gw * al + gT) * T                      # dL/dT_i * T_i  (T_i = exp(-excl_sum))
+        out = torch.empty_like(T)
+        check(lib().cnc_packed_scan(ptr(g_trans.contiguous()), ptr(packed_info), packed_info.shape[0], ptr(out), 0, 0, 1, stream()))
+        return None, None, (g_alpha - out) * dt, None, None
+
+
+def render_weight_from_density(t_starts, t_ends, sigmas, packed_info=None, ray_indices=None, n_rays=None, prefix_trans=None):
+    """(weights, trans, alphas).  nerfacc/volrend.py:314-364"""
+    if t_starts.dim() != 1:
+        raise NotImplementedError("cnc_b200.nerfacc handles the flattened (packed) sample layout CNC uses")
+    pk = _packed(packed_info, ray_indices, n_rays, sigmas)
+    return _RenderDensity.apply(t_starts, t_ends, sigmas, pk, prefix_trans)
+
+
+def render_transmittance_from_density(t_starts, t_ends, sigmas, packed_info=None, ray_indices=None, n_rays=None, prefix_trans=None):
+    """(trans, alphas).  nerfacc/volrend.py:211-266"""
+    _, T, al = render_weight_from_density(t_starts, t_ends, sigmas, packed_info, ray_indices, n_rays, prefix_trans)
+    return T, al
+
+
+@torch.no_grad()
+def render_visibility_from_density(t_starts, t_ends, sigmas, packed_info=None, ray_indices=None, n_rays=None,
+                                   early_stop_eps: float = 1e-4, alpha_thre: float = 0.0, prefix_trans=None):
+    """nerfacc/volrend.py:423-482"""
+    T, al = render_transmittance_from_density(t_starts, t_ends, sigmas, packed_info, ray_indices, n_rays, prefix_trans)
+    vis = T >= early_stop_eps
+    if alpha_thre > 0:
+        vis = vis & (al >= alpha_thre)
+    return vis
+
+
+def accumulate_along_rays(weights, values=None, ray_indices=None, n_rays=None):
+    """sum_i w_i * v_i per ray -> [n_rays, D].  nerfacc/volrend.py:485-549"""
+    src = weights[..., None] if values is None else weights[..., None] * values
+    if ray_indices is None:
+        return src.sum(dim=-2)
+    assert n_rays is not None
+    out = torch.zeros(n_rays, src.shape[-1], device=src.device, dtype=src.dtype)
+    out.index_add_(0, ray_indices, src)
+    return out
+
+
+def accumulate_along_rays_(weights, values=None, ray_indices=None, outputs=None) -> None:
+    """in-place variant used by the test-time renderer.  nerfacc/volrend.py:552-575"""
+    src = weights[..., None] if values is None else weights[..., None] * values
+    if ray_indices is None:
+        outputs.add_(src.sum(dim=-2))
+    else:
+        outputs.index_add_(0, ray_indices, src)
+
+
+def rendering(t_starts, t_ends, ray_indices=None, n_rays=None, rgb_sigma_fn: Optional[Callable] = None,
+              rgb_alpha_fn: Optional[Callable] = None, render_bkgd=None):
+    """(colors, opacities, depths, extras).  nerfacc/volrend.py:14-160 with the CNC patch: `rgb_sigma_fn`
+    returns (rgbs, sigmas, positions) and `extras` carries sigmas / rgbs / positions (volrend.py:89,108-115)."""
+    if ray_indices is not None:
+        assert t_starts.shape == t_ends.shape == ray_indices.shape
+    if rgb_sigma_fn is None:
+        raise ValueError("cnc_b200.nerfacc.rendering needs `rgb_sigma_fn` (the path CNC uses)")
+    if t_starts.shape[0] != 0:
+        rgbs, sigmas, positions = rgb_sigma_fn(t_starts, t_ends, ray_indices)
+    else:
+        positions = None
+        rgbs = torch.empty((0, 3), device=t_starts.device)
+        sigmas = torch.empty((0,), device=t_starts.device)
+    assert rgbs.shape[-1] == 3 and sigmas.shape == t_starts.shape
+    weights, trans, alphas = render_weight_from_density(t_starts, t_ends, sigmas, ray_indices=ray_indices, n_rays=n_rays)
+    extras = {"weights": weights, "alphas": alphas, "trans": trans, "sigmas": sigmas, "rgbs": rgbs, "positions": positions}
+    colors = accumulate_along_rays(weights, values=rgbs, ray_indices=ray_indices, n_rays=n_rays)
+    opacities = accumulate_along_rays(weights, values=None, ray_indices=ray_indices, n_rays=n_rays)
+    depths = accumulate_along_rays(weights, values=(t_starts + t_ends)[..., None] / 2.0, ray_indices=ray_indices, n_rays=n_rays)
+    depths = depths / opacities.clamp_min(torch.finfo(rgbs.dtype).eps)
+    if render_bkgd is not None:
+        colors = colors + render_bkgd * (1.0 - opacities)
+    return colors, opacities, depths, extras
+
+
+@torch.no_grad()
+def render_fused(t_starts, t_ends, sigmas, rgbs, packed_info, render_bkgd=None):
+    """Inference-time tail in one kernel: (colors, opacities, depths) == rendering(...)[:3] for given sigmas / rgbs."""
+    t0, t1, sg, c = (x.contiguous().float() for x in (t_starts, t_ends, sigmas, rgbs))
+    need_cuda(t_starts=t0, sigmas=sg, rgbs=c)
+    pk = packed_info.contiguous().to(torch.int64)
+    R = pk.shape[0]
+    colors = torch.empty(R, 3, device=t0.device)
+    opac = torch.empty(R, device=t0.device)
+    depth = torch.empty(R, device=t0.device)
+    check(lib().cnc_render_from_density(ptr(t0), ptr(t1), ptr(sg), ptr(c), ptr(pk), R, None, None, None, None, ptr(colors),
+                                        ptr(opac), ptr(depth), stream()))
+    opac = opac[:, None]
+    depth = depth[:, None] / opac.clamp_min(torch.finfo(torch.float32).eps)
+    if render_bkgd is not None:
+        colors = colors + render_bkgd * (1.0 - opac)
+    return colors, opac, depth
+
+
+# ------------------------------------------------------------------------------------------ estimator
+def _enlarge_aabb(aabb, factor: float) -> Tensor:
+    center = (aabb[:3] + aabb[3:]) / 2
+    extent = (aabb[3:] - aabb[:3]) / 2
+    return torch.cat([center - extent * factor, center + extent * factor])
+
+
+class OccGridEstimator(torch.nn.Module):
+    """Occupancy-grid transmittance estimator.  nerfacc/estimators/occ_grid.py:19-424"""
+
+    DIM: int = 3
+
+    def __init__(self, roi_aabb: Union[List[int], Tensor], resolution: Union[int, List[int], Tensor] = 128, levels: int = 1, **kwargs):
+        super().__init__()
+        if "contraction_type" in kwargs:
+            raise ValueError("`contraction_type` is not supported anymore for nerfacc >= 0.4.0.")
+        if isinstance(resolution, int):
+            resolution = [resolution] * self.DIM
+        if isinstance(resolution, (list, tuple)):
+            resolution = torch.tensor(resolution, dtype=torch.int32)
+        assert isinstance(resolution, Tensor) and resolution.shape[0] == self.DIM
+        if isinstance(roi_aabb, (list, tuple)):
+            roi_aabb = torch.tensor(roi_aabb, dtype=torch.float32)
+        assert isinstance(roi_aabb, Tensor) and roi_aabb.shape[0] == self.DIM * 2
+        aabbs = torch.stack([_enlarge_aabb(roi_aabb, 2 ** i) for i in range(levels)], dim=0)
+        self.cells_per_lvl = int(resolution.prod().item())
+        self.levels = levels
+        self.register_buffer("resolution", resolution)
+        self.register_buffer("aabbs", aabbs)
+        self.register_buffer("occs", torch.zeros(self.levels * self.cells_per_lvl))
+        self.register_buffer("binaries", torch.zeros([levels] + resolution.tolist(), dtype=torch.bool))
+        coords = torch.stack(torch.meshgrid([torch.arange(int(r)) for r in resolution.tolist()], indexing="ij"), dim=-1).long()
+        self.register_buffer("grid_coords", coords.reshape(self.cells_per_lvl, self.DIM), persistent=False)
+        self.register_buffer("grid_indices", torch.arange(self.cells_per_lvl), persistent=False)
+
+    @property
+    def device(self):
+        return self.occs.device
+
+    @torch.no_grad()
+    def sampling(self, rays_o: Tensor, rays_d: Tensor, sigma_fn: Optional[Callable] = None, alpha_fn: Optional[Callable] = None,
+                 near_plane: float = 0.0, far_plane: float = 1e10, t_min: Optional[Tensor] = None, t_max: Optional[Tensor] = None,
+                 render_step_size: float = 1e-3, early_stop_eps: float = 1e-4, alpha_thre: float = 0.0, stratified: bool = False,
+                 cone_angle: float = 0.0) -> Tuple[Tensor, Tensor, Tensor]:
+        """(ray_indices, t_starts, t_ends) of the samples that survive occupancy + visibility skipping.  :88-239"""
+        near_planes = torch.full_like(rays_o[..., 0], fill_value=near_plane)
+        far_planes = torch.full_like(rays_o[..., 0], fill_value=far_plane)
+        if t_min is not None:
+            near_planes = torch.clamp(near_planes, min=t_min)
+        if t_max is not None:
+            far_planes = torch.clamp(far_planes, max=t_max)
+        if stratified:
+            near_planes += torch.rand_like(near_planes) * render_step_size
+        intervals, samples, _ = traverse_grids(rays_o, rays_d, self.binaries, self.aabbs, near_planes=near_planes,
+                                               far_planes=far_planes, step_size=render_step_size, cone_angle=cone_angle)
+        t_starts, t_ends = intervals.vals[0::2], intervals.vals[1::2]
+        ray_indices, packed_info = samples.ray_indices, samples.packed_info
+        if (alpha_thre > 0.0 or early_stop_eps > 0.0) and (sigma_fn is not None or alpha_fn is not None):
+            alpha_thre = min(alpha_thre, self.occs.mean().item())
+            if sigma_fn is None:
+                raise NotImplementedError("alpha_fn is not on the CNC path; pass sigma_fn")
+            sigmas = sigma_fn(t_starts, t_ends, ray_indices) if t_starts.shape[0] != 0 else torch.empty((0,), device=t_starts.device)
+            assert sigmas.shape == t_starts.shape, "sigmas must have shape of (N,)! Got {}".format(sigmas.shape)
+            masks = render_visibility_from_density(t_starts=t_starts, t_ends=t_ends, sigmas=sigmas, packed_info=packed_info,
+                                                   early_stop_eps=early_stop_eps, alpha_thre=alpha_thre)
+            ray_indices, t_starts, t_ends = ray_indices[masks], t_starts[masks], t_ends[masks]
+        return ray_indices, t_starts, t_ends
+
+    @torch.no_grad()
+    def update_every_n_steps(self, step: int, occ_eval_fn: Callable, occ_thre: float = 1e-2, ema_decay: float = 0.95,
+                             warmup_steps: int = 256, n: int = 16) -> None:
+        """:242-277"""
+        if not self.training:
+            raise RuntimeError("You should only call this function only during training. "
+                               "Please call _update() directly if you want to update the field during inference.")
+        if step % n == 0 and self.training:
+            self._update(step=step, occ_eval_fn=occ_eval_fn, occ_thre=occ_thre, ema_decay=ema_decay, warmup_steps=warmup_steps)
+
+    @torch.no_grad()
+    def _get_all_cells(self) -> List[Tensor]:
+        """:349-361"""
+        return [self.grid_indices[self.occs[lvl * self.cells_per_lvl + self.grid_indices] >= 0.0] for lvl in range(self.levels)]
+
+    @torch.no_grad()
+    def _sample_uniform_and_occupied_cells(self, n: int) -> List[Tensor]:
+        """:363-385"""
+        out = []
+        for lvl in range(self.levels):
+            uniform = torch.randint(self.cells_per_lvl, (n,), device=self.device)
+            uniform = uniform[self.occs[lvl * self.cells_per_lvl + uniform] >= 0.0]
+            occupied = torch.nonzero(self.binaries[lvl].flatten())[:, 0]
+            if n < len(occupied):
+                occupied = occupied[torch.randint(len(occupied), (n,), device=self.device)]
+            out.append(torch.cat([uniform, occupied], dim=0))
+        return out
+
+    @torch.no_grad()
+    def _update(self, step: int, occ_eval_fn: Callable, occ_thre: float = 0.01, ema_decay: float = 0.95, warmup_steps: int = 256) -> None:
+        """EMA update of the occupancy field and re-binarisation.  :387-424"""
+        lvl_indices = self._get_all_cells() if step < warmup_steps else self._sample_uniform_and_occupied_cells(self.cells_per_lvl // 4)
+        for lvl, indices in enumerate(lvl_indices):
+            grid_coords = self.grid_coords[indices]
+            x = (grid_coords + torch.rand_like(grid_coords, dtype=torch.float32)) / self.resolution
+            x = self.aabbs[lvl, :3] + x * (self.aabbs[lvl, 3:] - self.aabbs[lvl, :3])
+            occ = occ_eval_fn(x).squeeze(-1)
+            cell_ids = lvl * self.cells_per_lvl + indices
+            self.occs[cell_ids] = torch.maximum(self.occs[cell_ids] * ema_decay, occ)
+        thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre)
+        self.binaries = (self.occs > thre).view(self.binaries.shape)

@@ -192,6 +192,36 @@ int cnc_context3d_probs(const int16_t *pts, const int64_t *seg, int64_t n_entrie
                         const float *mlp_packed, float *prob, float *mean, uint8_t *exist,
                         int64_t seg_base, cnc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Occupancy-grid ray marching, packed scans, volume rendering (vendored nerfacc 0.5.3).
+ * replaces: nerfacc.csrc ray_aabb_intersect / traverse_grids  nerfacc/cuda/csrc/grid.cu:320-349, :68-318
+ *           (python: nerfacc/grid.py:20-91, :94-194); exclusive/inclusive_sum/prod scan.cu:9-304
+ *           (nerfacc/scan.py); render_weight_from_density + accumulate_along_rays volrend.py:314-364,485-549.
+ * cnc_traverse_grids is called twice like the reference host code (grid.cu:441-507): a count pass
+ *   (t_starts == chunk_starts == NULL, cnt filled) and, after an exclusive scan of cnt, a fill pass.
+ *   hits [n_rays,n_grids] u8, t_sorted / t_indices [n_rays, 2*n_grids] = sorted (t_min | t_max) of
+ *   cnc_ray_aabb_intersect; binaries [n_grids,rx,ry,rz] bool.  Samples come out as (t_start, t_end, ray).
+ * cnc_packed_scan: op 0 sum / 1 prod over the chunks packed_info [n_rays,2] (start, count).
+ * cnc_render_from_density: per ray, weights = exp(-exclusive_sum(sigma*dt)) * (1 - exp(-sigma*dt)) and the
+ *   accumulations sum(w*rgb), sum(w), sum(w*t_mid); every output pointer is nullable.
+ * ---------------------------------------------------------------------------------------- */
+int cnc_ray_aabb_intersect(const float *rays_o, const float *rays_d, int64_t n_rays, float near_plane,
+                           float far_plane, const float *aabbs, int32_t n_aabbs, float miss_value,
+                           float *t_mins, float *t_maxs, uint8_t *hits, cnc_stream_t stream);
+int cnc_traverse_grids(const float *rays_o, const float *rays_d, const uint8_t *rays_mask, int64_t n_rays,
+                       int32_t n_grids, int32_t rx, int32_t ry, int32_t rz, const uint8_t *binaries,
+                       const float *aabbs, const uint8_t *hits, const float *t_sorted,
+                       const int64_t *t_indices, const float *near_planes, const float *far_planes,
+                       float step_size, float cone_angle, int32_t steps_limit,
+                       const int64_t *chunk_starts, int64_t *cnt, float *t_starts, float *t_ends,
+                       int64_t *ray_indices, float *terminate_planes, cnc_stream_t stream);
+int cnc_packed_scan(const float *in, const int64_t *packed_info, int64_t n_rays, float *out, int32_t op,
+                    int32_t inclusive, int32_t reverse, cnc_stream_t stream);
+int cnc_render_from_density(const float *t_starts, const float *t_ends, const float *sigmas,
+                            const float *rgbs, const int64_t *packed_info, int64_t n_rays,
+                            const float *prefix_trans, float *weights, float *trans, float *alphas,
+                            float *colors, float *opacities, float *depths, cnc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

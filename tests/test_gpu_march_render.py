@@ -1,0 +1,158 @@
+"""GPU suite: occupancy-grid marching, packed scans and the volume-rendering tail (cnc_b200.nerfacc) against
+the CPU oracle (oracle/cnc_oracle_march.c, pinned by the nerfacc docstring KATs in tests/golden) and, where the
+reference extension is present, against the reference's own nerfacc binary.  Sample layout (counts, ray indices)
+and interval edges are compared exactly; transmittance / weights to 1e-5 (the reference's scan tree order differs)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def scene(n_rays=3000, Rb=64, seed=0, levels=1):
+    rng = np.random.default_rng(seed)
+    # camera positions on a radius-4 sphere looking roughly at the origin
+    o = rng.normal(size=(n_rays, 3))
+    o = (o / np.linalg.norm(o, axis=1, keepdims=True) * 4).astype(np.float32)
+    tgt = rng.uniform(-0.8, 0.8, (n_rays, 3))
+    d = tgt - o
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    d[0] = [0, 0, 1]; o[0] = [0.1, 0.2, -4]       # axis-aligned ray (zero direction components)
+    d[1] = [1, 0, 0]; o[1] = [9, 9, 9]            # misses everything
+    c = (np.arange(Rb) + 0.5) / Rb * 3 - 1.5
+    X, Y, Z = np.meshgrid(c, c, c, indexing="ij")
+    bins = np.stack([(X * X + Y * Y + Z * Z <= 1.0)] + [np.ones_like(X, bool)] * (levels - 1)).astype(np.uint8)
+    aabbs = np.stack([np.array([-1.5, -1.5, -1.5, 1.5, 1.5, 1.5], np.float32) * 2 ** l for l in range(levels)])
+    return o, d, bins, aabbs
+
+
+def test_ray_aabb_and_kats(cuda, oracle, golden):
+    from cnc_b200 import nerfacc as N
+
+    o, d, bins, aabbs = scene(levels=2)
+    tmin, tmax, hits = N.ray_aabb_intersect(T(o, cuda), T(d, cuda), T(aabbs, cuda))
+    rmin, rmax, rh = oracle.ray_aabb_intersect(o, d, aabbs)
+    np.testing.assert_array_equal(hits.cpu().numpy(), rh)
+    np.testing.assert_array_equal(tmin.cpu().numpy(), rmin)
+    np.testing.assert_array_equal(tmax.cpu().numpy(), rmax)
+    # nerfacc docstring known answers (pack.py:29-32, scan.py:36-39,78-81,127-130,170-173)
+    ri = T(golden["kat_ray_indices_9"], cuda)
+    pk = N.pack_info(ri, 3)
+    np.testing.assert_array_equal(pk.cpu().numpy(), golden["kat_packed_info"])
+    x = T(golden["kat_scan_in"], cuda)
+    for fn, key in ((N.inclusive_sum, "kat_inclusive_sum"), (N.exclusive_sum, "kat_exclusive_sum"),
+                    (N.inclusive_prod, "kat_inclusive_prod"), (N.exclusive_prod, "kat_exclusive_prod")):
+        np.testing.assert_array_equal(fn(x, pk).cpu().numpy(), golden[key])
+    # volrend.py:349-357 / :463-473
+    pk7 = N.pack_info(T(golden["kat_ray_indices_7"], cuda), 3)
+    w, tr, al = N.render_weight_from_density(T(golden["kat_t_starts"], cuda), T(golden["kat_t_ends"], cuda),
+                                             T(golden["kat_sigmas"], cuda), packed_info=pk7)
+    np.testing.assert_allclose(w.cpu().numpy(), golden["kat_weights_from_density"], atol=6e-3)
+    np.testing.assert_allclose(tr.cpu().numpy(), golden["kat_trans_from_density"], atol=6e-3)
+    vis = N.render_visibility_from_density(T(golden["kat_t_starts"], cuda), T(golden["kat_t_ends"], cuda),
+                                           T(golden["kat_sigmas"], cuda), packed_info=pk7, early_stop_eps=0.3, alpha_thre=0.2)
+    np.testing.assert_array_equal(vis.cpu().numpy().astype(np.uint8), golden["kat_visibility"])
+
+
+@pytest.mark.parametrize("levels,step,cone,limit", [(1, 5e-3, 0.0, None), (2, 1e-2, 0.0, None), (1, 1e-2, 4e-3, None), (1, 5e-3, 0.0, 17)])
+def test_traverse_grids_exact_vs_oracle(cuda, oracle, levels, step, cone, limit):
+    from cnc_b200 import nerfacc as N
+
+    o, d, bins, aabbs = scene(levels=levels, seed=levels)
+    rng = np.random.default_rng(3)
+    near = (rng.random(len(o)) * step).astype(np.float32)           # stratified jitter (occ_grid.py:172-173)
+    far = np.full(len(o), 1e10, np.float32)
+    mask = None if limit is None else (rng.random(len(o)) < 0.7)
+    iv, sm, term = N.traverse_grids(T(o, cuda), T(d, cuda), T(bins.astype(bool), cuda), T(aabbs, cuda), T(near, cuda), T(far, cuda),
+                                    step_size=step, cone_angle=cone, traverse_steps_limit=limit,
+                                    rays_mask=None if mask is None else T(mask, cuda))
+    t0, t1, ri, pk, rterm = oracle.traverse_grids(o, d, bins, aabbs, near, far, step, cone, 0 if limit is None else limit, mask)
+    np.testing.assert_array_equal(sm.packed_info.cpu().numpy(), pk)            # sample counts per ray: exact
+    np.testing.assert_array_equal(sm.ray_indices.cpu().numpy(), ri)
+    np.testing.assert_array_equal(iv.vals[iv.is_left].cpu().numpy(), t0)        # interval edges: exact
+    np.testing.assert_array_equal(iv.vals[iv.is_right].cpu().numpy(), t1)
+    live = np.ones(len(o), bool) if mask is None else mask
+    np.testing.assert_array_equal(term.cpu().numpy()[live], rterm[live])
+    assert pk[1, 1] == 0 and pk[:, 1].sum() > 10 * len(o)
+    if limit is not None:
+        assert pk[:, 1].max() == limit and (pk[~mask, 1] == 0).all()
+
+
+def test_render_tail_vs_oracle_and_autograd(cuda, oracle):
+    from cnc_b200 import nerfacc as N
+
+    o, d, bins, aabbs = scene(n_rays=800, seed=5)
+    t0, t1, ri, pk, _ = oracle.traverse_grids(o, d, bins, aabbs, None, None, 1e-2)
+    rng = np.random.default_rng(6)
+    sig = (rng.random(len(t0)) * 8).astype(np.float32)
+    rgb = rng.random((len(t0), 3)).astype(np.float32)
+    ref = oracle.render_from_density(t0, t1, sig, pk, rgb)
+    tt0, tt1, tsig, trgb, tri, tpk = (T(x, cuda) for x in (t0, t1, sig, rgb, ri, pk))
+    w, tr, al = N.render_weight_from_density(tt0, tt1, tsig, ray_indices=tri, n_rays=len(o))
+    np.testing.assert_allclose(w.cpu().numpy(), ref["weights"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(tr.cpu().numpy(), ref["trans"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(al.cpu().numpy(), ref["alphas"], rtol=1e-6, atol=1e-7)
+    col, op, dep = N.render_fused(tt0, tt1, tsig, trgb, tpk)
+    np.testing.assert_allclose(col.cpu().numpy(), ref["colors"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(op[:, 0].cpu().numpy(), ref["opacities"], rtol=1e-6, atol=1e-6)
+    # rendering(): patched 3-tuple callback, extras, background
+    def rgb_sigma_fn(a, b, r):
+        return trgb, tsig, torch.zeros(len(a), 3, device=cuda)
+    bk = torch.ones(3, device=cuda)
+    c2, o2, d2, ex = N.rendering(tt0, tt1, tri, n_rays=len(o), rgb_sigma_fn=rgb_sigma_fn, render_bkgd=bk)
+    cb, ob, db = N.render_fused(tt0, tt1, tsig, trgb, tpk, render_bkgd=bk)
+    torch.testing.assert_close(c2, cb, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(o2, ob, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(d2, db, rtol=1e-4, atol=1e-5)
+    assert set(ex) >= {"weights", "alphas", "trans", "sigmas", "rgbs", "positions"}
+    # autograd: analytic backward of the fused weights kernel == torch composition (double)
+    s = tsig.double().requires_grad_(True)
+    dt = (tt1 - tt0).double()
+    sd = s * dt
+    cs = torch.cumsum(sd, 0)
+    starts = tpk[:, 0][tri]
+    base = torch.where(starts > 0, cs[(starts - 1).clamp_min(0)], torch.zeros_like(cs))
+    excl = cs - sd - base
+    w_ref = torch.exp(-excl) * (1 - torch.exp(-sd))
+    g = torch.randn(len(t0), device=cuda, dtype=torch.float64)
+    (w_ref * g).sum().backward()
+    s32 = tsig.clone().requires_grad_(True)
+    w32, _, _ = N.render_weight_from_density(tt0, tt1, s32, ray_indices=tri, n_rays=len(o))
+    (w32 * g.float()).sum().backward()
+    torch.testing.assert_close(s32.grad.double(), s.grad, rtol=2e-4, atol=1e-6)
+
+
+def test_occ_grid_estimator_sampling_and_update(cuda):
+    from cnc_b200 import nerfacc as N
+
+    torch.manual_seed(0)
+    est = N.OccGridEstimator(roi_aabb=[-1.5, -1.5, -1.5, 1.5, 1.5, 1.5], resolution=64, levels=1).to(cuda)
+    assert est.binaries.shape == (1, 64, 64, 64) and est.aabbs.shape == (1, 6) and est.occs.shape == (64 ** 3,)
+
+    def density(x):   # a soft ball of radius 1
+        return (20.0 * torch.sigmoid((1.0 - x.norm(dim=-1, keepdim=True)) * 20)).float()
+
+    est.train()
+    for step in range(0, 48, 16):
+        est.update_every_n_steps(step, occ_eval_fn=lambda x: density(x) * 5e-3, occ_thre=1e-2)
+    frac = est.binaries.float().mean().item()
+    assert 0.10 < frac < 0.25       # ~ volume of the unit ball in the [-1.5,1.5]^3 box (15.5 %)
+    o, d, _, _ = scene(n_rays=2000, seed=9)
+    ro, rd = T(o, cuda), T(d, cuda)
+
+    def sigma_fn(t0, t1, ri):
+        return density(ro[ri] + rd[ri] * ((t0 + t1) / 2)[:, None]).squeeze(-1)
+
+    ri, t0, t1 = est.sampling(ro, rd, sigma_fn=sigma_fn, render_step_size=5e-3, stratified=True)
+    ri_all, t0_all, _ = est.sampling(ro, rd, render_step_size=5e-3)
+    assert 0 < ri.numel() < ri_all.numel()           # visibility filtering removed the occluded samples
+    assert (ri[1:] >= ri[:-1]).all() and torch.allclose(t1 - t0, torch.full_like(t0, 5e-3), atol=1e-6)
+    mid = ro[ri] + rd[ri] * ((t0 + t1) / 2)[:, None]
+    assert (mid.norm(dim=-1) < 1.35).all()               # samples only in cells near the (soft) ball, none in empty space
+    est.eval()
+    with pytest.raises(RuntimeError):
+        est.update_every_n_steps(0, occ_eval_fn=density)
