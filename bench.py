@@ -217,6 +217,56 @@ def codec_bench(dev, cpu_seconds=12.0):
                                        "encode+decode); probabilities not included (the reference computes them on the GPU)"}}
 
 
+def train_bench(dev, rank, world, steps, field):
+    """forward + backward + (N > 1: NCCL all-reduce of all gradients) + Adam on a synthetic ray batch per rank:
+    rays from a radius-4 sphere towards the origin, ball occupancy, random target pixels."""
+    from cnc_b200.nerfacc import OccGridEstimator
+    from cnc_b200.render import Rays
+    from cnc_b200.trainer import TrainStep
+
+    est = OccGridEstimator(roi_aabb=[-1.5, -1.5, -1.5, 1.5, 1.5, 1.5], resolution=128, levels=1).to(dev)
+    c = (torch.arange(128, device=dev) + 0.5) / 128 * 3 - 1.5
+    X, Y, Z = torch.meshgrid(c, c, c, indexing="ij")
+    est.binaries = (X * X + Y * Y + Z * Z <= 1.0).unsqueeze(0)
+    est.occs = est.binaries.reshape(-1).float()
+    g = torch.Generator(device="cpu").manual_seed(7 + rank)
+    n_rays = 1100
+    o = torch.randn(n_rays, 3, generator=g)
+    o = o / o.norm(dim=-1, keepdim=True) * 4
+    tgt = (torch.rand(n_rays, 3, generator=g) - 0.5) * 1.2
+    d = tgt - o
+    d = d / d.norm(dim=-1, keepdim=True)
+    rays = Rays(o.to(dev), d.to(dev))
+    pixels = torch.rand(n_rays, 3, generator=g).to(dev)
+    ts = TrainStep(field, est, lr=1e-4)
+    n_s = 0
+    for _ in range(3):
+        _, n_s = ts(rays, pixels, refresh_occupancy=False)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    tot = 0
+    for _ in range(steps):
+        _, n_s = ts(rays, pixels, refresh_occupancy=False)
+        tot += n_s
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1), float(tot)], dtype=torch.float64, device=dev)
+    if world > 1:
+        ms = t[:1].clone()
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        cnt = t[1:].clone()
+        torch.distributed.all_reduce(cnt, op=torch.distributed.ReduceOp.SUM)
+        t = torch.cat([ms, cnt])
+    ms, tot = t.tolist()
+    return {"what": "fwd + bwd + gradient all-reduce + Adam (differentiable path: K1/K2 kernels + fp32 nn.Linear), "
+                    "sampling through the fused density kernel", "steps": steps, "ms_per_step": ms / steps,
+            "samples_per_step_all_ranks": tot / steps, "samples_per_s": tot / (ms * 1e-3),
+            "allreduce_bytes_per_step": ts.reducer.bytes_per_step() if world > 1 else 0, "rays_per_rank": n_rays}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -226,6 +276,7 @@ def main():
     ap.add_argument("--samples", type=int, default=262144)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-codec", action="store_true", help="skip the entropy encode/decode measurement (metric ii)")
+    ap.add_argument("--train-steps", type=int, default=5, help="steps of the fwd+bwd(+all-reduce) measurement, 0 = skip")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
 
@@ -320,6 +371,9 @@ def main():
         for _ in range(3):
             field.fused_forward(pos, dirs)
         ms_k = timed(lambda: field.fused_forward(pos, dirs), a.steps)
+    train = None
+    if a.impl == "ours" and a.train_steps > 0:
+        train = train_bench(dev, rank, world, a.train_steps, field)
     t = torch.tensor([ms, ms_e2e, ms_k], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -375,6 +429,8 @@ def main():
         line["e2e"]["h2d_bytes_per_step"] = line["e2e"]["h2d_bytes_per_step"]
     elif world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
+    if train is not None:
+        line["train_step"] = train
     if a.impl == "ours" and world == 1 and not a.no_codec:
         del field, model
         torch.cuda.empty_cache()

@@ -11,8 +11,8 @@ cat gpurun_out/bench_ours.json; tail -5 gpurun_out/bench_ours.err
 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 cat gpurun_out/bench_ref.json; tail -5 gpurun_out/bench_ref.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-codec > gpurun_out/ncu_bench.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-codec --train-steps 0 > gpurun_out/ncu_bench.log 2>&1
 tail -3 gpurun_out/ncu_bench.log
 ncu --set full --clock-control none --import-source on -k regex:field_fwd_kernel -s 3 -c 1 -o gpurun_out/prof_field \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-codec > gpurun_out/ncu_full.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-codec --train-steps 0 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
