@@ -199,6 +199,64 @@ class NGPRadianceField_mygrid_2D3D(nn.Module):
         return (None if rgb is None else rgb.view(shp + [3]), sigma.view(shp + [1]),
                 None if geo is None else geo.view(shp + [79]))
 
+    @torch.no_grad()
+    def forward_host(self, positions: torch.Tensor, directions: torch.Tensor, out_rgb: torch.Tensor = None,
+                     out_sigma: torch.Tensor = None, chunk_waves: int = 4):
+        """Host-buffer entry point: positions / directions are (pinned) CPU tensors [N,3]; rgb [N,3] and density [N,1]
+        come back in (pinned) CPU tensors.  The batch is cut into chunks of `chunk_waves` full waves of the persistent
+        kernel (148 SMs x 128 samples) and pipelined over three streams -- H2D of chunk i+1, the fused kernel on chunk i
+        and D2H of chunk i-1 overlap -- so the PCIe copies hide behind the compute instead of adding to it."""
+        if not self.fused_available():
+            raise RuntimeError("forward_host needs the fused kernel (CNC product layout)")
+        dev = self.aabb.device
+        n = positions.shape[0]
+        pos_h = positions.reshape(-1, 3).float().contiguous()
+        dir_h = directions.reshape(-1, 3).float().contiguous()
+        if out_rgb is None:
+            out_rgb = torch.empty(n, 3, dtype=torch.float32).pin_memory()
+        if out_sigma is None:
+            out_sigma = torch.empty(n, 1, dtype=torch.float32).pin_memory()
+        st = getattr(self, "_host_pipe", None)
+        if st is None or st["n"] < n:
+            st = {"n": n, "pos": torch.empty(n, 3, device=dev), "dir": torch.empty(n, 3, device=dev),
+                  "rgb": torch.empty(n, 3, device=dev), "sig": torch.empty(n, device=dev),
+                  "s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev)}
+            self._host_pipe = st
+        mb = self.mlp_base
+        encs = (mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz)
+        bits = [e._sign_cache.get(e.params) for e in encs]
+        blob = self._fused_blob()
+        if getattr(self, "_aabb_host", None) is None or self._aabb_src != (self.aabb.data_ptr(), self.aabb._version):
+            self._aabb_host = (ctypes.c_float * 6)(*self.aabb.detach().cpu().tolist())
+            self._aabb_src = (self.aabb.data_ptr(), self.aabb._version)
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        step = max(1, chunk_waves) * n_sm * 128
+        cur = torch.cuda.current_stream(dev)
+        s_in, s_out = st["s_in"], st["s_out"]
+        s_in.wait_stream(cur)      # staging buffers may still be read by earlier work on the caller's stream
+        s_out.wait_stream(cur)
+        L = lib()
+        for lo in range(0, n, step):
+            hi = min(n, lo + step)
+            with torch.cuda.stream(s_in):
+                st["pos"][lo:hi].copy_(pos_h[lo:hi], non_blocking=True)
+                st["dir"][lo:hi].copy_(dir_h[lo:hi], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            cur.wait_event(ev_in)
+            check(L.cnc_field_fwd(ptr(st["pos"][lo:hi]), ptr(st["dir"][lo:hi]), ctypes.addressof(self._aabb_host),
+                                  *[ptr(b) for b in bits], ptr(mb.encoding_xyz.offsets_list), ptr(mb.encoding_xyz.resolutions_list),
+                                  ptr(mb.encoding_xy.offsets_list), ptr(mb.encoding_xy.resolutions_list), ptr(blob),
+                                  ptr(st["sig"][lo:hi]), ptr(st["rgb"][lo:hi]), None, hi - lo, cur.cuda_stream))
+            ev_k = torch.cuda.Event()
+            ev_k.record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_k)
+                out_rgb[lo:hi].copy_(st["rgb"][lo:hi], non_blocking=True)
+                out_sigma[lo:hi, 0].copy_(st["sig"][lo:hi], non_blocking=True)
+        cur.wait_stream(s_out)
+        return out_rgb, out_sigma
+
     def _use_fused(self):
         return (not torch.is_grad_enabled()) and getattr(self, "fused", True) and self.fused_available()
 

@@ -129,3 +129,19 @@ def test_fused_full_size_properties(cuda):
     rgb_d, sig_d, _ = double_reference(f, pos[sub], dirs[sub])
     assert relerr(rgb[sub], rgb_d) <= 1e-5 and relerr(sig[sub], sig_d) <= 1e-5
     assert torch.isfinite(rgb).all() and torch.isfinite(sig).all()
+
+
+def test_forward_host_pipeline_matches_device_call(cuda):
+    """host-buffer entry point (chunked, three streams) == one device call, for sizes around the chunk boundaries"""
+    f = make_field(cuda, seed=9)
+    n_sm = torch.cuda.get_device_properties(cuda).multi_processor_count
+    for n in (1000, n_sm * 128, 2 * n_sm * 128 + 77):
+        pos, dirs = inputs(n, cuda, seed=n)
+        rgb, sig, _ = f.fused_forward(pos, dirs)
+        hp, hd = pos.cpu().pin_memory(), dirs.cpu().pin_memory()
+        r1, s1 = f.forward_host(hp, hd, chunk_waves=1)
+        torch.cuda.synchronize()
+        assert torch.equal(r1, rgb.cpu()) and torch.equal(s1, sig.cpu())
+        r2, s2 = f.forward_host(hp, hd)   # buffers are reused across calls
+        torch.cuda.synchronize()
+        assert torch.equal(r2, rgb.cpu()) and torch.equal(s2, sig.cpu())
