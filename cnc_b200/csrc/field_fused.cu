@@ -27,6 +27,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -84,6 +85,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+// non-blocking test in a spin loop: for the two service warps, where the wake-up latency of a suspended
+// try_wait would sit on the critical path of every chunk
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "SPIN_%=:\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra OK_%=;\n\t"
+        "bra SPIN_%=;\n\t"
+        "OK_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -108,6 +120,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
     return d;
 }
 template <int N>
+__device__ __forceinline__ constexpr uint32_t idesc_bf16() {   // kind::f16, A/B bf16, D fp32, K = 16
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+template <int N>
 __device__ __forceinline__ constexpr uint32_t idesc_tf32() {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
@@ -125,6 +141,18 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
     asm volatile(
         "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xFFFFFFFF;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ss_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xFFFFFFFF;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xFFFFFFFF;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
         "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
@@ -166,13 +194,25 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t r0, uint32_t r
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
 
-// tf32 hi/lo split, 2 + 3 integer/fp ops: hi = v rounded to 10 mantissa bits (nearest, ties away: add half
-// an ulp to the magnitude, clear the low 13 bits), lo = (v - hi) rounded the same way.  v = hi + lo + O(2^-22 v).
-// (cvt.rna.tf32.f32 does the same but ptxas expands it to a ~10-instruction NaN/Inf-safe sequence.)
+// Error-compensated split of an fp32 operand for the tensor cores: v = hi + lo with hi = v rounded to tf32
+// (nearest, ties away: add half an ulp to the magnitude, clear the low 13 bits; cvt.rna.tf32.f32 does the same but
+// ptxas expands it to a ~10-instruction NaN/Inf-safe sequence).  A*B ~= Ahi*Bhi [one kind::tf32 MMA, K = 8]
+//   + (Ahi*Blo + Alo*Bhi) [ONE kind::f16 MMA, K = 16: the bf16 pairs (Ahi, Alo) against (Blo, Bhi)].
+// The correction terms are 2^-12 of the product, so their bf16 rounding (2^-9) costs 2^-21 relative: the same
+// order as the dropped Alo*Blo term.  One 32-bit word per element holds the pair, i.e. the "lo" buffers keep
+// their size and layout, while the MMA count per k-step drops from 3 to 2 and the two MMAs hit different
+// accumulators (a dependent accumulate costs ~130 cycles, more than the MMA itself at N <= 160).
 __device__ __forceinline__ uint32_t rna_tf32(float v) { return (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u; }
-__device__ __forceinline__ void split_tf32(float v, uint32_t &hi, uint32_t &lo) {
+__device__ __forceinline__ uint32_t pack_bf16(float lower, float upper) {   // element 2k = lower, 2k+1 = upper
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(upper), "f"(lower));
+    return d;
+}
+// A side: hi word + pair (Ahi, Alo)
+__device__ __forceinline__ void split_tf32(float v, uint32_t &hi, uint32_t &pair) {
     hi = rna_tf32(v);
-    lo = __float_as_uint(__fsub_rn(v, __uint_as_float(hi)));  // |lo| <= 2^-12 |v|; the MMA truncates it to tf32 (2^-23 |v|)
+    const float h = __uint_as_float(hi);
+    pair = pack_bf16(h, __fsub_rn(v, h));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -227,9 +267,9 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(PackArgs a, float *__
         case 2: { const int c = head_src_col(k); if (c >= 0) v = a.W[2][n * 95 + c]; } break;  // Linear(95,160)
         default: v = a.W[3][n * 160 + k]; break;                                   // Linear(160,160)
     }
-    uint32_t hi, lo;
-    split_tf32(v, hi, lo);
-    blob[i] = __uint_as_float(is_lo ? lo : hi);
+    const uint32_t hi = rna_tf32(v);
+    const float h = __uint_as_float(hi);
+    blob[i] = __uint_as_float(is_lo ? pack_bf16(__fsub_rn(v, h), h) : hi);   // B side pair (Blo, Bhi)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -427,7 +467,7 @@ __device__ __forceinline__ void ep_hidden(uint32_t tl, int cg, uint32_t c_main, 
 }
 
 constexpr int NCOMPUTE = 512;              // 16 gather/epilogue warps
-constexpr int NTHREADS = NCOMPUTE + 32;    // + the MMA / weight-stream warp
+constexpr int NTHREADS = NCOMPUTE + 64;    // + the MMA warp + the weight-stream (bulk copy) warp
 
 template <bool DENSITY_ONLY>
 __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs a) {
@@ -481,34 +521,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
         // =============================== weight stream + MMA issue ===============================
         // The whole warp runs this control flow (all values warp-uniform -> uniform datapath); one elected
         // lane issues the copies, MMAs and commits.
-        const uint8_t *blob = reinterpret_cast<const uint8_t *>(a.blob);
-        const uint32_t total = my_tiles * CPT;
-        uint32_t Gc = 0, Gm = 0, a_cons = 0, act_cnt = 0;
-        auto issue_copy = [&]() {
-            const uint32_t s = Gc % NSTAGE, use = Gc / NSTAGE;
-            if (use > 0) mbar_wait(b_empty(s), (use - 1) & 1u);
-            uint32_t ofs, bytes;
-            chunk_meta((int)(Gc % CPT), ofs, bytes);
-            bulk_g2s_elect(sbase + SMEM_B + s * STAGE_BYTES, blob + ofs, bytes, b_full(s));
-            Gc++;
-        };
-        // two stage loads ahead of the chunk being issued: the refill after chunk g targets the stage of
-        // chunk g-2, whose MMAs have normally retired -> issue never waits on the chunk just queued
-        for (int i = 0; i < NSTAGE - 2 && Gc < total; i++) issue_copy();
+        uint32_t Gm = 0, a_cons = 0, act_cnt = 0;
 
         // One stage load = NATOM K-atoms (32 columns = 4 k-steps of 8) of a layer with N output columns.
         // The two small products (Ahi*Blo, Alo*Bhi) go to their own accumulator d_small when the layer has
         // one, so the round-toward-zero of the tensor-core accumulate acts on them at their own 2^-11 scale.
         // bar1 / bar2: extra mbarriers (0 = none) that the completion of these MMAs arrives on.
         auto chunk_mma = [&](auto n_tag, auto smem_tag, int natom, uint32_t a_hi, uint32_t a_lo, uint32_t d_main,
-                             bool first_main, uint32_t d_small, bool first_small, uint32_t bar1, uint32_t bar2) {
+                             bool first_main, uint32_t d_small, bool first_small, uint32_t bar1, uint32_t bar2,
+                             uint32_t it = 0, int tl_slot = -1) {
             constexpr int N = decltype(n_tag)::value;
             constexpr bool A_IN_SMEM = decltype(smem_tag)::value;
             const uint32_t s = Gm % NSTAGE;
-            mbar_wait(b_full(s), (Gm / NSTAGE) & 1u);
+            mbar_wait_spin(b_full(s), (Gm / NSTAGE) & 1u);
             tc_fence_after();
+            if (tl_slot >= 0 && elect_one()) CNC_TL(tl_slot);
             const uint32_t bst = sbase + SMEM_B + s * STAGE_BYTES;
-            constexpr uint32_t id = idesc_tf32<N>();
+            constexpr uint32_t id = idesc_tf32<N>(), idb = idesc_bf16<N>();
             const bool shared_acc = (d_small == d_main);
             for (int at = 0; at < natom; at++) {
                 const uint64_t dbh0 = smem_desc(bst + (uint32_t)at * (2u * N * 128u)),
@@ -517,22 +546,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
 #pragma unroll
                 for (int k4 = 0; k4 < 4; k4++) {
                     // +32 bytes along K inside the 128-byte swizzle row == +2 in the descriptor's address field.
-                    // Consecutive MMAs alternate accumulators (small, main, small) so that the accumulate
-                    // latency of one overlaps the next.
+                    // The two MMAs of a k-step go to different accumulators, so their accumulate latencies overlap.
                     const uint64_t dbh = dbh0 + (uint64_t)(2 * k4), dbl = dbl0 + (uint64_t)(2 * k4);
                     const bool head = (at == 0 && k4 == 0);
                     const uint32_t acc_s = (first_small && head) ? 0u : 1u;
                     const uint32_t acc_m = shared_acc ? 1u : ((first_main && head) ? 0u : 1u);
                     if (A_IN_SMEM) {
                         const uint64_t dah = dah0 + (uint64_t)(2 * k4), dal = dal0 + (uint64_t)(2 * k4);
-                        mma_ss(tbase + d_small, dah, dbl, id, acc_s);
-                        mma_ss(tbase + d_main, dah, dbh, id, acc_m);
-                        mma_ss(tbase + d_small, dal, dbh, id, 1u);
+                        mma_ss_bf16(tbase + d_small, dal, dbl, idb, acc_s);   // Ahi*Blo + Alo*Bhi
+                        mma_ss(tbase + d_main, dah, dbh, id, acc_m);          // Ahi*Bhi
                     } else {
                         const uint32_t ah = tbase + a_hi + 32u * at + 8u * k4, al = tbase + a_lo + 32u * at + 8u * k4;
-                        mma_ts(tbase + d_small, ah, dbl, id, acc_s);
+                        mma_ts_bf16(tbase + d_small, al, dbl, idb, acc_s);
                         mma_ts(tbase + d_main, ah, dbh, id, acc_m);
-                        mma_ts(tbase + d_small, al, dbh, id, 1u);
                     }
                 }
             }
@@ -540,7 +566,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             if (bar1) tc_commit_elect(bar1);
             if (bar2) tc_commit_elect(bar2);
             Gm++;
-            if (Gc < total) issue_copy();
         };
         using N160 = std::integral_constant<int, 160>;
         using N80 = std::integral_constant<int, 80>;
@@ -548,11 +573,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
         using FromTmem = std::false_type;
 
         for (uint32_t it = 0; it < my_tiles; it++) {
-            // L1: A from smem slots; main [0,160) (even chunks) / [160,320) (odd chunks), small [320,480)
+            // L1: A from smem slots; main [0,160) (even chunks) / [160,320) (odd chunks: halves the round-toward-zero
+            // bias of the 32-step accumulation), small [320,480)
 #pragma unroll 1
             for (int kc = 0; kc < 8; kc++) {
                 const uint32_t sl = a_cons & 1u;
-                mbar_wait(a_full(sl), (a_cons >> 1) & 1u);
+                mbar_wait_spin(a_full(sl), (a_cons >> 1) & 1u);
                 const uint32_t ab = sbase + SMEM_A + sl * A_SLOT_BYTES;
                 if (elect_one()) CNC_TL(32 + kc);
                 chunk_mma(N160{}, FromSmem{}, 1, ab, ab + A_HALF, (kc & 1) ? 160u : 0u, kc < 2, 320u, kc == 0, a_empty(sl),
@@ -561,17 +587,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             }
             if (elect_one()) CNC_TL(40);
             // L2: A = h1 hi [0,160) lo [160,320) -> main [320,400), small [400,480); K = 64 + 64 + 32
-            mbar_wait(act_ready, act_cnt & 1u); act_cnt++;
+            mbar_wait_spin(act_ready, act_cnt & 1u); act_cnt++;
             tc_fence_after();
             if (elect_one()) CNC_TL(41);
 #pragma unroll 1
             for (int j = 0; j < 3; j++)
                 chunk_mma(N80{}, FromTmem{}, j < 2 ? 2 : 1, 64u * j, 160u + 64u * j, 320u, j == 0, 400u, j == 0,
-                          j == 2 ? layer_done : 0u, 0u);
+                          j == 2 ? layer_done : 0u, 0u, it, 48 + j);
             if (elect_one()) CNC_TL(42);
             if (!DENSITY_ONLY) {
                 // L3: A = head input hi [0,96) lo [96,192) -> main [192,352), small [352,512)
-                mbar_wait(act_ready, act_cnt & 1u); act_cnt++;
+                mbar_wait_spin(act_ready, act_cnt & 1u); act_cnt++;
                 tc_fence_after();
                 if (elect_one()) CNC_TL(43);
 #pragma unroll 1
@@ -579,20 +605,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                     chunk_mma(N160{}, FromTmem{}, 1, 32u * kc, 96u + 32u * kc, 192u, kc == 0, 352u, kc == 0,
                               kc == 2 ? layer_done : 0u, 0u);
                 // L4: A hi [192,352) lo [352,512) -> [0,160) (no room for a second accumulator)
-                mbar_wait(act_ready, act_cnt & 1u); act_cnt++;
+                mbar_wait_spin(act_ready, act_cnt & 1u); act_cnt++;
                 tc_fence_after();
                 if (elect_one()) CNC_TL(44);
 #pragma unroll 1
                 for (int kc = 0; kc < 5; kc++)
                     chunk_mma(N160{}, FromTmem{}, 1, 192u + 32u * kc, 352u + 32u * kc, 0u, false, 0u, kc == 0,
-                              kc == 4 ? layer_done : 0u, 0u);
+                              kc == 4 ? layer_done : 0u, 0u, it, 53 + kc);
                 if (elect_one()) CNC_TL(45);
             }
             // The next tile's first feature chunks are usually already waiting in smem, and its L1 overwrites
             // the accumulators the last epilogue of this tile is still reading: wait until it has read them.
-            mbar_wait(act_ready, act_cnt & 1u); act_cnt++;
+            mbar_wait_spin(act_ready, act_cnt & 1u); act_cnt++;
             tc_fence_after();
             if (elect_one()) CNC_TL(46);
+        }
+    } else if (warp == MMA_WARP + 1) {
+        // =============================== weight stream ===============================
+        // Keeps the 4-stage ring full: a stage is refilled as soon as the MMAs that read it have retired
+        // (tcgen05.commit -> b_empty), independently of where the MMA warp is -> up to 3 loads (120 KB) in flight.
+        const uint8_t *blob = reinterpret_cast<const uint8_t *>(a.blob);
+        const uint32_t total = my_tiles * CPT;
+        for (uint32_t G = 0; G < total; G++) {
+            const uint32_t s = G % NSTAGE, use = G / NSTAGE;
+            if (use > 0) mbar_wait_spin(b_empty(s), (use - 1) & 1u);
+            uint32_t ofs, bytes;
+            chunk_meta((int)(G % CPT), ofs, bytes);
+            if (a.dbg != nullptr && blockIdx.x == 0 && G / CPT == 1 && elect_one()) a.dbg[64 + G % CPT] = clock64();
+            bulk_g2s_elect(sbase + SMEM_B + s * STAGE_BYTES, blob + ofs, bytes, b_full(s));
+            if (a.dbg != nullptr && blockIdx.x == 0 && G / CPT == 1) {   // profiling aid: observe the arrival (serialises the loads)
+                mbar_wait_spin(b_full(s), use & 1u);
+                if (elect_one()) a.dbg[96 + G % CPT] = clock64();
+            }
         }
     } else {
         // =============================== gather / epilogue warps ===============================
@@ -692,7 +736,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                 load_x(tile + gridDim.x, xn);
                 issue(0, xn, pa);  // in flight during the L1 tail and ep1
             }
-            // ---- ep1: h1 = relu(acc1 + b1) -> hi in place [0,160), lo [160,320)
+            // ---- ep1: h1 = relu(acc1 + b1) -> hi in place [0,160), (hi, lo) bf16 pairs over the second accumulator [160,320)
             if (threadIdx.x == 0) CNC_TL(9);
             mbar_wait(layer_done, done_cnt & 1u); done_cnt++;
             tc_fence_after();
@@ -897,7 +941,8 @@ int cnc_field_fwd(const float *pos, const float *dirs, const float *aabb6_host, 
     a.offs3 = offsets3; a.res3 = resolutions3; a.offs2 = offsets2; a.res2 = resolutions2;
     a.blob = blob; a.sigma = sigma; a.rgb = rgb; a.geo = geo; a.N = N; a.dbg = g_timeline;
     const uint32_t ntiles = (N + ff::TILE_M - 1) / ff::TILE_M;
-    const uint32_t grid = ntiles < (uint32_t)n_sm ? ntiles : (uint32_t)n_sm;
+    uint32_t grid = ntiles < (uint32_t)n_sm ? ntiles : (uint32_t)n_sm;
+    if (const char *g = getenv("CNC_FIELD_GRID")) { const uint32_t v = (uint32_t)atoi(g); if (v >= 1 && v < grid) grid = v; }  // profiling aid
     if (dirs) ff::field_fwd_kernel<false><<<grid, ff::NTHREADS, ff::SMEM_DYN, s>>>(a);
     else ff::field_fwd_kernel<true><<<grid, ff::NTHREADS, ff::SMEM_DYN, s>>>(a);
     return check_launch("field_fwd");

@@ -161,7 +161,7 @@ int cnc_freq_embed(const float *x, float *out, uint64_t n, int n_freq, cnc_strea
  *   geo [N,79] (nullable).  fp32 results via 3xTF32 tcgen05 MMA with fp32 accumulation.
  * ---------------------------------------------------------------------------------------- */
 uint32_t cnc_field_blob_floats(void);
-/* profiling aid: 64 x uint64 device buffer that receives clock64() stamps of one tile (NULL = off) */
+/* profiling aid: 128 x uint64 device buffer that receives clock64() stamps of one tile (NULL = off) */
 int cnc_field_set_timeline_buffer(uint64_t *device_buf);
 int cnc_field_pack_weights(const float *W1, const float *b1, const float *W2, const float *b2,
                            const float *W3, const float *b3, const float *W4, const float *b4,
