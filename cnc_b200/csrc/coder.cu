@@ -5,16 +5,18 @@
 // tree; algorithm restated in SURVEY Appendix B and oracle/cnc_oracle.c).  The bytes produced
 // here are identical to that coder's for equal (c1, symbol) inputs.
 //
-// Range coding is sequential inside a stream (low/high carry from symbol to symbol).  The
-// B200 mapping is therefore one warp per independent stream (the product emits 33 of them):
-//   * all 32 lanes stage the stream's (c1,sym) pairs through shared memory with coalesced
-//     loads, one 1024-symbol tile ahead of the coder;
-//   * lane 0 carries (low, high, pending) and runs the dependent chain -- one 32x16-bit
-//     multiply, a select, and a renormalisation done in O(1) with clz instead of the
-//     reference's bit-at-a-time loop;
-//   * output bits are packed MSB-first in a 64-bit register and leave as 32-bit stores.
-// The decoder mirrors it and replaces torchac's 64-bit division by the equivalent comparison
-// c1*span <= ((value-low+1)<<16)-1.
+// Range coding is sequential inside a stream (the interval carries from symbol to symbol), so the
+// B200 mapping is stream-parallel (the product emits 33 independent streams) and everything that is
+// not the carried dependency is taken off the lane that runs it:
+//   * encoder: one CTA of two warps per stream.  Warp 0 stages (c1, sym) tiles with coalesced loads
+//     and its lane 0 runs the chain -- one 32x16-bit multiply, selects, ONE find-leading-one and a
+//     comparison (closed form of the reference's bit-at-a-time renormalisation loop, see below) --
+//     leaving (low, high) per symbol in shared memory.  Warp 1 converts those records into bits with
+//     warp scans (matched-prefix lengths, pending-bit counts, bit offsets), ORs them into a shared
+//     ring and stores finished words coalesced.
+//   * decoder: one warp per stream, state (low, range, value - low), torchac's 64-bit division
+//     replaced by the equivalent comparison value - low >= t, input bits from a three-word register
+//     window that is advanced with predicated moves (no branch in the loop body).
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -30,143 +32,278 @@ __global__ void cdf_from_p_kernel(const float *__restrict__ p, uint16_t *__restr
     }
 }
 
-constexpr int TILE = 2048;  // symbols staged per step
-
-// The serial part of a stream is one dependent chain per symbol:
-//   r = high-low -> t = (r*c + c) >> 16 -> select -> x = low^high -> nm = clz(x) -> ku = clz of the underflow run
-//   -> one combined shift by S = nm + ku.
-// E1/E2 (nm matching leading bits) and E3 (ku underflow positions: low = 0 1^ku.., high = 1 0^ku..) of the
-// reference's bit-at-a-time loop are resolved together: after the update span >= 2^14 always holds for
-// c1 in [1, 65535] (span > 2^30 before the symbol), so S <= 18 and a single 32-bit shift suffices; the S == 32
-// corner of degenerate CDFs (c1 == 0) is kept correct by the clamped funnel shifts.
-// Everything that is not on that chain (symbol fetch, bit packing, stores) is written so that it can issue in
-// the chain's stall slots.
-struct CoderState {
-    uint32_t low = 0u, high = 0xFFFFFFFFu;
-};
-
-// returns nm (common prefix length) and ku (underflow run); updates the state.  Precondition c in [1, 65535]
-// (what cnc_cdf_from_p / torchac's quantiser produce): then span >= 2^14 after the update, nm + ku <= 18.
-__device__ __forceinline__ void coder_step(CoderState &st, uint32_t c, uint32_t s, uint32_t &low2, uint32_t &nm, uint32_t &ku) {
-    const uint32_t r = st.high - st.low;                                   // span - 1
-    const uint32_t t = (uint32_t)(((uint64_t)r * c + c) >> 16);            // (span * c1) >> 16
-    const uint32_t nl = st.low + t;
-    low2 = s ? nl : st.low;
-    const uint32_t high2 = s ? st.high : nl - 1u;
-    nm = __clz(low2 ^ high2);
-    const uint32_t w = ~low2 | high2;                                      // 0 exactly where (low, high) = (1, 0)
-    ku = __clz(((w << nm) << 1) | 0x2000u);                                // run after the first differing bit (bounded by span >= 2^14)
-    const uint32_t S = nm + ku;
-    st.low = (low2 << S) & 0x7FFFFFFFu;
-    st.high = __funnelshift_l(0xFFFFFFFFu, high2, S) | 0x80000000u;
+// ------------------------------------------------------------------------------------------
+// The serial part of a stream is one dependent chain per symbol.  State: low and r = high - low (both 32 bit;
+// the decoder adds d = value - low).  With t = (span * c1) >> 16 = (r * c1 + c1) >> 16:
+//     s = 1: low2 = low + t, r2 = r - t          s = 0: low2 = low, r2 = t - 1            high2 = low2 + r2
+// The reference renormalises bit by bit (E1/E2: equal top bits are shifted out; E3: low = 01.., high = 10.. drops
+// the second bit).  Every one of those steps maps (low, high, value) -> (2 low, 2 high + 1, 2 value + bit) minus
+// a multiple of 2^31, and the loop stops at the largest S for which the window still fits, i.e. for which the
+// top S+1 bits of high2 and low2 differ by at most one.  Because 2^(31-c0) <= r2 < 2^(32-c0) with c0 = clz(r2),
+// that S is either c0 - 1 (always feasible) or c0, decided by one comparison:
+//     S = c0 - 1 + [ (high2 >> (31 - c0)) - (low2 >> (31 - c0)) <= 1 ]
+// and the new state is low = (low2 << S) & 0x7FFFFFFF, r = ~(~r2 << S), d = (d2 << S) | next S input bits.
+// (oracle/cnc_oracle.c runs the bit loop; tests/test_oracle_golden.py checks this closed form against it.)
+// One find-leading-one and no branch per symbol, against two and a data-dependent loop before.  c1 in
+// [1, 65535] (what the quantiser produces) keeps r2 >= 2^14 - 1, so S <= 18.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t renorm_shift(uint32_t low2, uint32_t high2, uint32_t r2) {
+    const uint32_t c0 = __clz(r2), sh = 31u - c0;
+    return c0 - 1u + (((high2 >> sh) - (low2 >> sh)) <= 1u ? 1u : 0u);
 }
 
-struct BitWriter {
-    uint64_t acc = 0;   // bits, MSB first
-    uint32_t nb = 0;    // valid bits in acc (< 32 between calls)
-    uint32_t *dst;      // word cursor
-    uint64_t words = 0, cap_words;
-    __device__ __forceinline__ void put(uint32_t v, uint32_t n) {  // 0 <= n <= 32, v < 2^n
-        acc |= ((uint64_t)v << (32u - n)) << (32u - nb);  // v's n bits go right after the nb valid ones
-        nb += n;
-        if (nb >= 32u) {
-            const uint32_t wv = (uint32_t)(acc >> 32);
-            if (words < cap_words) dst[words] = __byte_perm(wv, 0, 0x0123);
-            words++;
-            acc <<= 32;
-            nb -= 32u;
+constexpr int ET = 1024;            // symbols per tile
+constexpr int RING_WORDS = 2048;    // output ring of the bit packer (power of two)
+constexpr uint32_t SLOW_PEND = 1024;  // pending runs longer than this take the sequential emit path
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Bit packer state of one stream (held warp-uniformly by the 32 lanes of the packer warp).  Bits are MSB first;
+// finished 32-bit words leave the shared ring as coalesced big-endian stores.
+struct Packer {
+    uint32_t *ring;          // [RING_WORDS], zero outside the unflushed window
+    uint32_t *dst;           // output words
+    uint8_t *dst8;
+    uint64_t cap_bytes;
+    uint64_t gbit = 0;       // bits emitted so far
+    uint64_t flushed = 0;    // words already stored
+    uint64_t pend = 0;       // pending underflow count
+
+    // n <= 32 bits of v at absolute bit position pos (executed by the calling lane only)
+    __device__ __forceinline__ void or_bits(uint64_t pos, uint32_t v, uint32_t n) {
+        if (n == 0) return;
+        const uint32_t o = (uint32_t)pos & 31u;
+        const uint64_t V = ((uint64_t)v << (32u - n)) << (32u - o);
+        const uint32_t w = (uint32_t)(pos >> 5);
+        const uint32_t hi = (uint32_t)(V >> 32), lo = (uint32_t)V;
+        if (hi) atomicOr(&ring[w & (RING_WORDS - 1)], hi);
+        if (lo) atomicOr(&ring[(w + 1) & (RING_WORDS - 1)], lo);
+    }
+    // whole warp: store every complete word while at least `keep` of them are waiting
+    __device__ __forceinline__ void flush(int lane, uint64_t min_words) {
+        __syncwarp();
+        const uint64_t complete = gbit >> 5;
+        while (complete - flushed >= min_words && complete > flushed) {
+            const uint64_t w = flushed + (uint64_t)lane;
+            if (w < complete) {
+                const uint32_t v = ring[w & (RING_WORDS - 1)];
+                ring[w & (RING_WORDS - 1)] = 0u;
+                if (w * 4 + 4 <= cap_bytes) dst[w] = __byte_perm(v, 0, 0x0123);
+            }
+            flushed = (complete - flushed > 32) ? flushed + 32 : complete;
+        }
+        __syncwarp();
+    }
+    // whole warp, sequential semantics: `count` copies of `bit`
+    __device__ __forceinline__ void emit_run(int lane, uint32_t bit, uint64_t count) {
+        while (count > 0) {
+            const uint32_t chunk = count > 1024 ? 1024u : (uint32_t)count;
+            if (bit) {
+                const uint32_t my = (uint32_t)lane * 32u;
+                if (my < chunk) {
+                    const uint32_t n = chunk - my >= 32u ? 32u : chunk - my;
+                    or_bits(gbit + my, n == 32u ? 0xFFFFFFFFu : ((1u << n) - 1u), n);
+                }
+            }
+            gbit += chunk;
+            count -= chunk;
+            flush(lane, 32);
         }
     }
-    __device__ __forceinline__ void put_run(uint32_t bit, uint64_t count) {
-        const uint32_t fill = bit ? 0xFFFFFFFFu : 0u;
-        while (count >= 32) { put(fill, 32); count -= 32; }
-        if (count) put(fill >> (32 - (uint32_t)count), (uint32_t)count);
+    __device__ __forceinline__ void emit_bits(int lane, uint32_t v, uint32_t n) {   // n <= 32
+        if (lane == 0) or_bits(gbit, v, n);
+        gbit += n;
+    }
+    // reference bo_bit_and_pending for the nm matched bits `lead` of one symbol
+    __device__ __forceinline__ void emit_symbol_seq(int lane, uint32_t lead, uint32_t nm) {
+        const uint32_t b0 = lead >> (nm - 1u);
+        emit_bits(lane, b0, 1);
+        emit_run(lane, b0 ^ 1u, pend);
+        pend = 0;
+        emit_bits(lane, lead & ((1u << (nm - 1u)) - 1u), nm - 1u);
+        flush(lane, 32);
     }
 };
 
-// one warp (= one CTA of 32 threads) per stream
-__global__ void __launch_bounds__(32)
+// One CTA of two warps per stream.  Warp 0: all lanes stage (c1, symbol) tiles, lane 0 runs the dependent chain and
+// leaves (low2, high2) per symbol in shared memory.  Warp 1 turns those records into bits with warp scans (matched
+// prefix lengths, pending counts, bit offsets) one tile behind, so nothing but the chain is on the chain's lane.
+__global__ void __launch_bounds__(64)
 ac_encode_kernel(const uint16_t *__restrict__ c1, const uint8_t *__restrict__ sym,
                  const int64_t *__restrict__ sym_off, uint8_t *__restrict__ out,
                  const int64_t *__restrict__ out_off, int64_t *__restrict__ out_len) {
-    __shared__ __align__(16) uint32_t tile[2][TILE];
-    const int k = blockIdx.x, lane = threadIdx.x;
+    __shared__ __align__(16) uint32_t in_tile[2][ET];
+    __shared__ __align__(16) uint2 rec[2][ET];
+    __shared__ uint32_t ring[RING_WORDS];
+    __shared__ uint32_t final_low;
+    const int k = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t s0 = sym_off[k], n = sym_off[k + 1] - s0;
-    const int64_t o0 = out_off[k], cap = out_off[k + 1] - o0;
-    c1 += s0;
-    sym += s0;
+    const int64_t ntiles = (n + ET - 1) / ET;
+    constexpr int BAR_FULL = 1, BAR_EMPTY = 3;   // + buffer index
 
-    BitWriter bw;
-    bw.dst = reinterpret_cast<uint32_t *>(out + o0);
-    bw.cap_words = (uint64_t)(cap / 4);
-    CoderState st;
-    uint64_t pending = 0;
-
-    auto stage = [&](int buf, int64_t base) {
+    if (warp == 0) {
+        c1 += s0;
+        sym += s0;
+        auto stage = [&](int buf, int64_t base) {
 #pragma unroll 8
-        for (int j = lane; j < TILE; j += 32) {
-            const int64_t i = base + j;
-            tile[buf][j] = (i < n) ? ((uint32_t)__ldg(c1 + i) | ((uint32_t)__ldg(sym + i) << 16)) : 0u;
+            for (int j = lane; j < ET; j += 32) {
+                const int64_t i = base + j;
+                in_tile[buf][j] = (i < n) ? ((uint32_t)__ldg(c1 + i) | ((uint32_t)__ldg(sym + i) << 16)) : 0u;
+            }
+        };
+        if (n > 0) stage(0, 0);
+        __syncwarp();
+        uint32_t low = 0u, r = 0xFFFFFFFFu;
+        for (int64_t t = 0; t < ntiles; t++) {
+            const int buf = (int)(t & 1);
+            if (t + 1 < ntiles) stage(buf ^ 1, (t + 1) * ET);   // in flight while lane 0 codes
+            if (t >= 2) named_bar_sync(BAR_EMPTY + buf, 64);    // the packer is done with rec[buf]
+            if (lane == 0) {
+                const int m = (int)((n - t * ET) < ET ? (n - t * ET) : ET);
+                const uint32_t *src = in_tile[buf];
+                uint2 *dstrec = rec[buf];
+                auto step = [&](uint32_t pk, int j) {
+                    const uint32_t c = pk & 0xFFFFu, s = pk >> 16;
+                    const uint32_t tt = (uint32_t)(((uint64_t)r * c + c) >> 16);
+                    const uint32_t low2 = s ? low + tt : low;
+                    const uint32_t r2 = s ? r - tt : tt - 1u;
+                    const uint32_t high2 = low2 + r2;
+                    dstrec[j] = make_uint2(low2, high2);
+                    const uint32_t S = renorm_shift(low2, high2, r2);
+                    low = (low2 << S) & 0x7FFFFFFFu;
+                    r = ~(~r2 << S);
+                };
+                int j = 0;
+                uint4 q = *reinterpret_cast<const uint4 *>(src);
+                for (; j + 4 <= m; j += 4) {
+                    const uint4 cur = q;
+                    q = *reinterpret_cast<const uint4 *>(src + ((j + 4) & (ET - 1)));   // next group, off the chain
+                    step(cur.x, j);
+                    step(cur.y, j + 1);
+                    step(cur.z, j + 2);
+                    step(cur.w, j + 3);
+                }
+                for (; j < m; j++) step(src[j], j);
+                if (t == ntiles - 1) final_low = low;
+            }
+            __syncwarp();
+            __threadfence_block();
+            named_bar_arrive(BAR_FULL + buf, 64);
         }
-    };
-    if (n > 0) stage(0, 0);
+        return;
+    }
+
+    // ------------------------------------------------------------------ packer warp
+    for (int j = lane; j < RING_WORDS; j += 32) ring[j] = 0u;
+    Packer pk;
+    pk.ring = ring;
+    pk.dst8 = out + out_off[k];
+    pk.dst = reinterpret_cast<uint32_t *>(pk.dst8);
+    pk.cap_bytes = (uint64_t)(out_off[k + 1] - out_off[k]);
     __syncwarp();
-    int buf = 0;
-    for (int64_t base = 0; base < n; base += TILE) {
-        if (base + TILE < n) stage(buf ^ 1, base + TILE);  // next tile in flight while lane 0 codes
-        if (lane == 0) {
-            const int m = (int)((n - base) < TILE ? (n - base) : TILE);
-            for (int j0 = 0; j0 < m; j0 += 4) {
-                const uint4 q = *reinterpret_cast<const uint4 *>(&tile[buf][j0]);
-                const uint32_t pk[4] = {q.x, q.y, q.z, q.w};
+    for (int64_t t = 0; t < ntiles; t++) {
+        const int buf = (int)(t & 1);
+        named_bar_sync(BAR_FULL + buf, 64);
+        const int m = (int)((n - t * ET) < ET ? (n - t * ET) : ET);
+        for (int g = 0; g < m; g += 32) {
+            const int j = g + lane;
+            uint32_t nm = 0, ku = 0, lead = 0;
+            if (j < m) {
+                const uint2 lh = rec[buf][j];
+                nm = __clz(lh.x ^ lh.y);
+                ku = renorm_shift(lh.x, lh.y, lh.y - lh.x) - nm;
+                lead = nm ? lh.x >> (32u - nm) : 0u;
+            }
+            // P = inclusive sum of ku; key = (sum before this symbol) + 1 at symbols that emit
+            uint32_t P = ku;
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (j0 + u < m) {
-                        uint32_t low2, nm, ku;
-                        coder_step(st, pk[u] & 0xFFFFu, pk[u] >> 16, low2, nm, ku);
-                        if (nm) {
-                            const uint32_t lead = low2 >> (32u - nm);  // the nm matched bits
-                            if (pending) {
-                                const uint32_t b0 = lead >> (nm - 1u);
-                                bw.put(b0, 1);
-                                bw.put_run(b0 ^ 1u, pending);
-                                if (nm > 1u) bw.put(lead & ((1u << (nm - 1u)) - 1u), nm - 1u);
-                            } else {
-                                bw.put(lead, nm);
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, P, d);
+                if (lane >= d) P += v;
+            }
+            const uint32_t Pex = P - ku;
+            const uint32_t key = nm ? Pex + 1u : 0u;
+            uint32_t kmax = key;          // inclusive prefix max
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, kmax, d);
+                if (lane >= d) kmax = max(kmax, v);
+            }
+            uint32_t B = __shfl_up_sync(0xFFFFFFFFu, kmax, 1);
+            if (lane == 0) B = 0u;        // exclusive: last emitter strictly before this symbol
+            const uint64_t pend_i = B ? (uint64_t)(Pex - (B - 1u)) : pk.pend + Pex;
+            const uint32_t Ptot = __shfl_sync(0xFFFFFFFFu, P, 31), klast = __shfl_sync(0xFFFFFFFFu, kmax, 31);
+            const bool slow = __any_sync(0xFFFFFFFFu, nm && pend_i > SLOW_PEND);
+            if (!slow) {
+                const uint32_t pe = (uint32_t)pend_i;
+                const uint32_t len = nm ? nm + pe : 0u;
+                uint32_t off = len;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, off, d);
+                    if (lane >= d) off += v;
+                }
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, off, 31);
+                off -= len;
+                if (nm) {
+                    const uint64_t pos = pk.gbit + off;
+                    const uint32_t b0 = lead >> (nm - 1u), rest = lead & ((1u << (nm - 1u)) - 1u);
+                    if (len <= 32u) {
+                        const uint32_t run = b0 ? 0u : (((1u << pe) - 1u) << (nm - 1u));   // pe <= 31 here
+                        pk.or_bits(pos, (b0 << (len - 1u)) | run | rest, len);
+                    } else {
+                        pk.or_bits(pos, b0, 1);
+                        if (!b0) {
+                            uint64_t p2 = pos + 1;
+                            for (uint32_t left = pe; left > 0;) {
+                                const uint32_t cnk = left >= 32u ? 32u : left;
+                                pk.or_bits(p2, cnk == 32u ? 0xFFFFFFFFu : ((1u << cnk) - 1u), cnk);
+                                p2 += cnk;
+                                left -= cnk;
                             }
-                            pending = ku;
-                        } else {
-                            pending += ku;
                         }
+                        pk.or_bits(pos + 1 + pe, rest, nm - 1u);
                     }
+                }
+                pk.gbit += total;
+                pk.pend = klast ? (uint64_t)(Ptot - (klast - 1u)) : pk.pend + Ptot;
+                pk.flush(lane, 32);
+            } else {   // sequential semantics, symbol by symbol (astronomically rare: > SLOW_PEND pending bits)
+                for (int i = 0; i < 32; i++) {
+                    const uint32_t nmi = __shfl_sync(0xFFFFFFFFu, nm, i), kui = __shfl_sync(0xFFFFFFFFu, ku, i);
+                    const uint32_t li = __shfl_sync(0xFFFFFFFFu, lead, i);
+                    if (nmi) pk.emit_symbol_seq(lane, li, nmi);
+                    pk.pend += kui;
                 }
             }
         }
-        __syncwarp();
-        buf ^= 1;
+        if (t + 2 < ntiles) named_bar_arrive(BAR_EMPTY + buf, 64);
     }
-    if (lane == 0) {
-        pending += 1;
-        const uint32_t b = st.low < 0x40000000u ? 0u : 1u;
-        bw.put(b, 1);
-        bw.put_run(b ^ 1u, pending);
-        // flush: whole words are out; the remaining nb (<32) bits go byte by byte, zero padded
-        uint64_t bytes = bw.words * 4;
-        uint8_t *tail = out + o0;
-        uint32_t rem = bw.nb;
-        uint64_t acc = bw.acc;
-        while (rem > 0) {
-            if ((int64_t)bytes < cap) tail[bytes] = (uint8_t)(acc >> 56);
-            bytes++;
-            acc <<= 8;
-            rem = rem > 8 ? rem - 8 : 0;
+    // termination: one more pending bit, then the quarter bit and its complements (reference tail)
+    {
+        const uint32_t lowf = n > 0 ? final_low : 0u;
+        pk.pend += 1;
+        const uint32_t b = lowf < 0x40000000u ? 0u : 1u;
+        pk.emit_bits(lane, b, 1);
+        pk.emit_run(lane, b ^ 1u, pk.pend);
+        pk.flush(lane, 1);
+        // the last partial word leaves byte by byte, zero padded
+        const uint64_t bytes = (pk.gbit + 7) >> 3;
+        const uint64_t done = pk.flushed * 4;
+        if (lane == 0) {
+            const uint32_t v = ring[pk.flushed & (RING_WORDS - 1)];
+            for (uint64_t b8 = done; b8 < bytes; b8++)
+                if (b8 < pk.cap_bytes) pk.dst8[b8] = (uint8_t)(v >> (24u - 8u * (uint32_t)(b8 - done)));
+            out_len[k] = (int64_t)bytes;
         }
-        out_len[k] = (int64_t)bytes;
     }
 }
 
-// input bits: the stream's bytes are staged (big-endian words) through shared memory by the whole warp, lane 0
-// keeps a 64-bit MSB-aligned reservoir
+// Decoder: one warp per stream.  All lanes stage the CDF entries and the input words (big-endian) through shared
+// memory; lane 0 runs the chain on (low, r, d = value - low).  The input cursor is three prefetched words and a
+// bit offset, advanced with predicated moves, so the loop body has no branch and one shared load (off the chain).
+constexpr int TILE = 2048;  // symbols staged per step
 __global__ void __launch_bounds__(32)
 ac_decode_kernel(const uint16_t *__restrict__ c1, const int64_t *__restrict__ sym_off,
                  const uint8_t *__restrict__ in, const int64_t *__restrict__ in_off,
@@ -174,7 +311,7 @@ ac_decode_kernel(const uint16_t *__restrict__ c1, const int64_t *__restrict__ sy
     __shared__ __align__(16) uint16_t ctile[2][TILE];
     __shared__ __align__(16) uint8_t stile[TILE];
     constexpr int WT = 1024;                       // input words per staging tile
-    __shared__ uint32_t wtile[2][WT];
+    __shared__ uint32_t wtile[2 * WT];
     const int k = blockIdx.x, lane = threadIdx.x;
     const int64_t s0 = sym_off[k], n = sym_off[k + 1] - s0;
     c1 += s0;
@@ -182,7 +319,7 @@ ac_decode_kernel(const uint16_t *__restrict__ c1, const int64_t *__restrict__ sy
     const uint8_t *src = in + in_off[k];
     const int64_t nbytes = in_len[k];
 
-    auto stage_words = [&](int wb, int64_t wbase) {   // words [wbase, wbase+WT), zeros past the end (torchac)
+    auto stage_words = [&](int64_t wbase) {   // words [wbase, wbase+WT), zeros past the end (torchac)
         for (int j = lane; j < WT; j += 32) {
             const int64_t p = (wbase + j) * 4;
             uint32_t w = 0;
@@ -190,7 +327,7 @@ ac_decode_kernel(const uint16_t *__restrict__ c1, const int64_t *__restrict__ sy
             else if (p < nbytes) {
                 for (int b = 0; b < 4; b++) w = (w << 8) | (p + b < nbytes ? (uint32_t)src[p + b] : 0u);
             }
-            wtile[wb][j] = w;
+            wtile[(wbase + j) & (2 * WT - 1)] = w;
         }
     };
     auto stage = [&](int buf, int64_t base) {
@@ -200,66 +337,67 @@ ac_decode_kernel(const uint16_t *__restrict__ c1, const int64_t *__restrict__ sy
             ctile[buf][j] = (i < n) ? __ldg(c1 + i) : (uint16_t)1;
         }
     };
-    stage_words(0, 0);
-    stage_words(1, WT);
+    stage_words(0);
+    stage_words(WT);
     if (n > 0) stage(0, 0);
     __syncwarp();
 
-    // reservoir
-    uint64_t res = 0;
-    uint32_t navail = 0;
-    int64_t wpos = 0;          // next word index to consume
-    int64_t staged_hi = 2 * WT; // words [0, staged_hi) have been staged
-    auto refill = [&]() {      // lane 0 only: navail < 32 -> append one word
-        const uint32_t w = wtile[(wpos / WT) & 1][wpos % WT];
-        res |= (uint64_t)w << (32u - navail);
-        navail += 32u;
-        wpos++;
-    };
-    CoderState st;
-    uint32_t value = 0;
+    int64_t staged_hi = 2 * WT;   // words [0, staged_hi) have been staged
+    uint32_t low = 0u, r = 0xFFFFFFFFu, d = 0u;
+    uint32_t W0 = 0u, W1 = 0u, W2 = 0u, nb = 0u, win = 0u;
+    int64_t wi = 1;               // W0 = word[wi], W1 = word[wi+1], W2 = word[wi+2]
     if (lane == 0) {
-        refill();
-        value = (uint32_t)(res >> 32);
-        res <<= 32;
-        navail -= 32u;
-        refill();
+        d = wtile[0];
+        W0 = wtile[1]; W1 = wtile[2]; W2 = wtile[3];
+        win = W0;
     }
     int buf = 0;
     for (int64_t base = 0; base < n; base += TILE) {
         if (base + TILE < n) stage(buf ^ 1, base + TILE);
         const int m = (int)((n - base) < TILE ? (n - base) : TILE);
-        // a tile of TILE symbols consumes at most TILE * 18 bits < WT words only if TILE*18/32 <= WT: 2048*18/32 = 1152 > 1024,
-        // so the word tiles are topped up in two halves of the symbol tile
+        // a half tile consumes at most 1024 * 18 bits = 576 words < WT: the word ring is topped up in between
         for (int half = 0; half < 2; half++) {
             const int jb = half * (TILE / 2), je = min(m, jb + TILE / 2);
             if (lane == 0) {
-                for (int j = jb; j < je; j++) {
-                    const uint32_t c = ctile[buf][j];
-                    // symbol: largest s with cdf[s] <= count  <=>  c1 * span <= ((value - low + 1) << 16) - 1
-                    const uint32_t r = st.high - st.low;
-                    const uint64_t lhs = (uint64_t)r * c + c;
-                    const uint64_t rhs = (((uint64_t)(value - st.low) + 1ull) << 16) - 1ull;
-                    const uint32_t s = lhs <= rhs;
+                const uint16_t *cs = ctile[buf];
+                uint32_t wcur = (uint32_t)wi;
+                auto step = [&](uint32_t c, int j) {
+                    const uint32_t tt = (uint32_t)(((uint64_t)r * c + c) >> 16);
+                    const bool s = d >= tt;            // <=> c1 <= ((value - low + 1) * 2^16 - 1) / span
                     stile[j] = (uint8_t)s;
-                    uint32_t low2, nm, ku;
-                    coder_step(st, c, s, low2, nm, ku);
-                    const uint32_t S = nm + ku;
-                    if (S) {
-                        const uint32_t bits = (uint32_t)(res >> (64u - S));
-                        res <<= S;
-                        navail -= S;
-                        value = (value << S) | bits;
-                        if (ku) value ^= 0x80000000u;   // ku x {value -= 2^30; shift in a bit}
-                        if (navail < 32u) refill();
-                    }
+                    const uint32_t low2 = s ? low + tt : low;
+                    const uint32_t r2 = s ? r - tt : tt - 1u;
+                    const uint32_t d2 = s ? d - tt : d;
+                    const uint32_t high2 = low2 + r2;
+                    const uint32_t S = renorm_shift(low2, high2, r2);
+                    low = (low2 << S) & 0x7FFFFFFFu;
+                    r = ~(~r2 << S);
+                    d = __funnelshift_l(win, d2, S);   // (d2 << S) | top S bits of the input window
+                    nb += S;
+                    const bool cross = nb >= 32u;
+                    W0 = cross ? W1 : W0;
+                    W1 = cross ? W2 : W1;
+                    wcur += cross ? 1u : 0u;
+                    nb &= 31u;
+                    W2 = wtile[(wcur + 2u) & (2 * WT - 1)];
+                    win = __funnelshift_l(W1, W0, nb);
+                };
+                int j = jb;
+                for (; j + 4 <= je; j += 4) {
+                    const uint2 q = *reinterpret_cast<const uint2 *>(cs + j);
+                    step(q.x & 0xFFFFu, j);
+                    step(q.x >> 16, j + 1);
+                    step(q.y & 0xFFFFu, j + 2);
+                    step(q.y >> 16, j + 3);
                 }
+                for (; j < je; j++) step(cs[j], j);
+                wi += (int64_t)(wcur - (uint32_t)wi);
             }
             __syncwarp();
-            // keep two word tiles ahead of the consumer
-            const int64_t wp = __shfl_sync(0xFFFFFFFFu, wpos, 0);
+            // keep more than one word tile ahead of the consumer
+            const int64_t wp = __shfl_sync(0xFFFFFFFFu, wi, 0);
             while (staged_hi - wp <= WT) {
-                stage_words((int)((staged_hi / WT) & 1), staged_hi);
+                stage_words(staged_hi);
                 staged_hi += WT;
             }
             __syncwarp();
@@ -289,7 +427,7 @@ int cnc_ac_encode(const uint16_t *c1, const uint8_t *sym, const int64_t *sym_off
     if (n_streams <= 0) return CNC_OK;
     if (!c1 || !sym || !sym_off || !out || !out_off || !out_len) { set_error("ac_encode: null pointer"); return CNC_EINVAL; }
     if (reinterpret_cast<uintptr_t>(out) & 3u) { set_error("ac_encode: out must be 4-byte aligned"); return CNC_EINVAL; }
-    ac_encode_kernel<<<n_streams, 32, 0, static_cast<cudaStream_t>(stream)>>>(c1, sym, sym_off, out, out_off, out_len);
+    ac_encode_kernel<<<n_streams, 64, 0, static_cast<cudaStream_t>(stream)>>>(c1, sym, sym_off, out, out_off, out_len);
     return check_launch("ac_encode");
 }
 

@@ -330,6 +330,53 @@ def test_coder_extreme_probabilities_and_long_pending_runs(cuda, oracle):
     assert tac.encode_streams([T(c1.view(np.int16), cuda)], [T(sym, cuda)])[0] == want
 
 
+def _underflow_stream(n_straddle, n_tail, seed=0):
+    """(c1, sym) that keeps the interval straddling 1/2 while it narrows: every symbol adds ~15 pending (E3) bits,
+    so the run gets far beyond the packer's fast path (SLOW_PEND = 1024 in csrc/coder.cu)."""
+    low, high, pending, max_pending = 0, 2 ** 32 - 1, 0, 0
+    cs, ss = [], []
+    for i in range(n_straddle):
+        span = high - low + 1
+        if i % 2 == 0:   # s = 1: raise low to just below 1/2
+            c, s = ((2 ** 31 - 1 - low) << 16) // span, 1
+        else:            # s = 0: lower high to just above 1/2
+            c, s = -((-((2 ** 31 - low + 1) << 16)) // span), 0
+        c = min(max(c, 1), 65535)
+        t = (span * c) >> 16
+        if s:
+            low = low + t
+        else:
+            high = low + t - 1
+        while True:
+            if high < 2 ** 31 or low >= 2 ** 31:
+                low, high, pending = (low << 1) & 0xFFFFFFFF, ((high << 1) | 1) & 0xFFFFFFFF, 0
+            elif low >= 2 ** 30 and high < 3 * 2 ** 30:
+                low, high, pending = (low << 1) & 0x7FFFFFFF, ((high << 1) | 0x80000001) & 0xFFFFFFFF, pending + 1
+            else:
+                break
+        max_pending = max(max_pending, pending)
+        cs.append(c)
+        ss.append(s)
+    rng = np.random.default_rng(seed)
+    c1 = np.concatenate([np.array(cs, np.uint16), rng.integers(1, 65536, n_tail).astype(np.uint16)])
+    sym = np.concatenate([np.array(ss, np.uint8), rng.integers(0, 2, n_tail).astype(np.uint8)])
+    return c1, sym, max_pending
+
+
+@pytest.mark.parametrize("n_straddle", [40, 200, 5000])
+def test_coder_pending_runs_beyond_the_fast_path(cuda, oracle, n_straddle):
+    from cnc_b200 import torchac as tac
+
+    for n_tail in (0, 3000):
+        c1, sym, max_pending = _underflow_stream(n_straddle, n_tail, seed=n_straddle)
+        assert max_pending > 12 * n_straddle   # 40 -> below SLOW_PEND, 200 -> above, 5000 -> several 1024-bit chunks
+        want = oracle.ac_encode(c1, sym)
+        got = tac.encode_streams([T(c1.view(np.int16), cuda)], [T(sym, cuda)])[0]
+        assert got == want
+        dec = tac.decode_streams([T(c1.view(np.int16), cuda)], [want])[0]
+        np.testing.assert_array_equal(dec.cpu().numpy(), sym)
+
+
 def test_coder_roundtrip_full_size(cuda, oracle):
     """size-independent property at the product size: 33 streams, ~4e7 symbols, decode(encode(x)) == x,
     and the largest stream is byte-identical to the oracle."""

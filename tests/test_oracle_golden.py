@@ -235,3 +235,51 @@ def test_marching_oracle(oracle):
         assert mid.min() >= tin - 1e-4 and mid.max() <= tout + 1e-4
     # empty grid -> no samples
     assert oracle.traverse_grids(o, d, np.zeros_like(bins), [-1, -1, -1, 1, 1, 1], step_size=0.05)[3][:, 1].sum() == 0
+
+
+def _renorm_loop(low, high):
+    """the oracle's bit-at-a-time renormalisation (oracle/cnc_oracle.c cnc_o_ac_encode), vectorised: -> (low, high, S)"""
+    low, high = low.astype(np.uint64), high.astype(np.uint64)
+    S = np.zeros(low.shape, np.int64)
+    M = np.uint64(0xFFFFFFFF)
+    for _ in range(34):
+        e12 = (high < 0x80000000) | (low >= 0x80000000)
+        e3 = ~e12 & (low >= 0x40000000) & (high < 0xC0000000)
+        any_ = e12 | e3
+        l1 = (low << np.uint64(1)) & M
+        h1 = ((high << np.uint64(1)) | np.uint64(1)) & M
+        l3 = l1 & np.uint64(0x7FFFFFFF)
+        h3 = h1 | np.uint64(0x80000000)
+        low = np.where(e12, l1, np.where(e3, l3, low))
+        high = np.where(e12, h1, np.where(e3, h3, high))
+        S += any_
+    return low, high, S
+
+
+def test_closed_form_renormalisation_equals_reference_loop():
+    """The GPU coder replaces the E1/E2/E3 loop by S = clz(r2) - 1 + [top bits differ by <= 1] (csrc/coder.cu):
+    same shift count and same (low, high - low) afterwards, on random and on boundary-hugging intervals."""
+    rng = np.random.default_rng(5)
+    n = 400000
+    B = (rng.integers(0, 2 ** 32, n, dtype=np.uint64) >> rng.integers(0, 32, n).astype(np.uint64)) << rng.integers(0, 32, n).astype(np.uint64)
+    B = np.where(rng.random(n) < 0.4, rng.choice(np.array([2 ** 31, 2 ** 30, 3 * 2 ** 30], np.uint64), n), B & np.uint64(0xFFFFFFFF))
+    x = rng.integers(0, 2 ** 32, n, dtype=np.uint64) >> rng.integers(1, 33, n).astype(np.uint64)
+    y = rng.integers(0, 2 ** 32, n, dtype=np.uint64) >> rng.integers(1, 33, n).astype(np.uint64)
+    lo = np.maximum(B.astype(np.int64) - x.astype(np.int64), 0)
+    hi = np.minimum(B.astype(np.int64) + y.astype(np.int64), 2 ** 32 - 1)
+    lo2 = np.concatenate([lo, rng.integers(0, 2 ** 31, n)])
+    hi2 = np.concatenate([hi, rng.integers(2 ** 31, 2 ** 32, n)])
+    keep = hi2 - lo2 >= 1
+    lo2, hi2 = lo2[keep], hi2[keep]
+    r2 = hi2 - lo2
+    c0 = 32 - np.floor(np.log2(r2.astype(np.float64))).astype(np.int64) - 1
+    c0 = np.where((r2 >> (31 - c0)) == 0, c0 + 1, np.where((r2 >> (31 - c0)) > 1, c0 - 1, c0))   # exact clz
+    sh = 31 - c0
+    S = c0 - 1 + (((hi2 >> sh) - (lo2 >> sh)) <= 1)
+    low_n = ((lo2 << S) & 0x7FFFFFFF)
+    r_n = ((r2 << S) | ((1 << S) - 1)) & 0xFFFFFFFF
+    l, h, Sref = _renorm_loop(lo2, hi2)
+    np.testing.assert_array_equal(S, Sref)
+    np.testing.assert_array_equal(low_n.astype(np.uint64), l)
+    np.testing.assert_array_equal(r_n.astype(np.uint64), h - l)
+    assert (Sref >= 10).sum() > 1000 and (Sref == 0).sum() > 1000
