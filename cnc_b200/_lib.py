@@ -45,7 +45,8 @@ SIGNATURES = {
                            _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "cnc_packed_scan": [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp],
     "cnc_render_from_density": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "cnc_context3d_probs": [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _i64, _vp],
+    "cnc_context3d_probs": [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "cnc_vertex_valid_bits": [_vp, _i32, _vp, _i32, _vp, _i64, _vp, _vp],
 }
 
 

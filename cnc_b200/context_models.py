@@ -323,22 +323,60 @@ class CNC_context_models(nn.Module):
             return self._probs_3D_fused(Encoding_xyz, table, binary_vxl, n, lo, hi, Pg_n)
         return self._probs_3D_unfused(Encoding_xyz, table, binary_vxl, n, lo, hi, Pg_n)
 
+    def _vertex_bits(self, Encoding_xyz, vx):
+        """per-vertex occupancy predicate of all levels as bitmaps (cnc_vertex_valid_bits); rebuilt when the
+        occupancy grid changes"""
+        key = (vx.data_ptr(), vx._version, tuple(vx.shape))
+        if getattr(self, "_vbits_key", None) != key:
+            offs, off = [], 0
+            for r in self.res:
+                offs.append(off)
+                off += (r ** 3 + 31) // 32 * 32
+            offs.append(off)
+            bit_off = torch.tensor(offs, dtype=torch.int64, device=vx.device)
+            words = torch.empty(off // 32, dtype=torch.int32, device=vx.device)
+            check(lib().cnc_vertex_valid_bits(ptr(vx), vx.shape[-1], ptr(Encoding_xyz.resolutions_list), self.n_levels,
+                                              ptr(bit_off), off, ptr(words), stream()))
+            self._vbits, self._vbits_off, self._vbits_key = words, bit_off, key
+        return self._vbits, self._vbits_off
+
+    def _sign_bits(self, table):
+        """1-bit plane of the (partially decoded) table; repacked only when the table changed"""
+        t = table.detach()
+        key = (t.data_ptr(), t._version, t.numel())
+        if getattr(self, "_sbits_key", None) != key:
+            self._sbits, self._sbits_key = _backend.sign_pack(t.contiguous()), key
+        return self._sbits
+
     def _probs_3D_fused(self, Encoding_xyz, table, binary_vxl, n, lo, hi, Pg_n):
         cs = self.unique_count_cumsum_list[n]
         seg = cs[lo:hi + 1].contiguous()
-        seg_base = int(cs[lo])
-        pts = self.pos_grid_sorted_list[n][seg_base:int(cs[hi])]
+        seg_base, seg_end = self._cs_host(n, lo), self._cs_host(n, hi)
+        pts = self.pos_grid_sorted_list[n][seg_base:seg_end]
         E = hi - lo
         dev = pts.device
-        bits = _backend.sign_pack(table.detach().contiguous())
+        bits = self._sign_bits(table)
         prob = torch.empty(E, 8, device=dev)
         exist = torch.empty(E, dtype=torch.uint8, device=dev)
         vx = binary_vxl.squeeze(0).contiguous()
+        if vx.dtype != torch.bool and vx.dtype != torch.uint8:
+            vx = vx != 0
+        vbits, vbit_off = self._vertex_bits(Encoding_xyz, vx)
         check(lib().cnc_context3d_probs(ptr(pts), ptr(seg), E, ptr(vx), vx.shape[-1], ptr(bits),
                                         ptr(Encoding_xyz.offsets_list), ptr(Encoding_xyz.resolutions_list), n, float(Pg_n),
-                                        ptr(self._mlp3d_packed()), ptr(prob), None, ptr(exist), seg_base, stream()))
+                                        ptr(self._mlp3d_packed()), ptr(prob), None, ptr(exist), seg_base,
+                                        ptr(vbits), ptr(vbit_off), stream()))
         ex = exist.bool()
         return prob[ex], ex
+
+    def _cs_host(self, n, i):
+        """unique_count_cumsum_list[n][i] as a python int without a device sync (the tables are static)"""
+        h = getattr(self, "_cs_host_cache", None)
+        if h is None:
+            h = self._cs_host_cache = {}
+        if n not in h:
+            h[n] = self.unique_count_cumsum_list[n].cpu()
+        return int(h[n][i])
 
     def _probs_3D_unfused(self, Encoding_xyz, table, binary_vxl, n, lo, hi, Pg_n):
         """the reference's op-by-op flow (utils_bpp_acc.py:803-852) on the drop-in kernels"""
@@ -465,6 +503,7 @@ class CNC_context_models(nn.Module):
     def encode_binary_vxl_mixPg_3D2D(self, Encoding_xyz, Encoding_xy, Encoding_xz, Encoding_yz, binary_vxl=None,
                                      filename_prefix="b", return_streams=False):
         """utils_bpp_acc.py:709-865.  Writes `<prefix>_<axis><n>.b`, `<prefix>_3D<n>.b`, `<prefix>_3D<n>_<chunk>.b`."""
+        self._sbits_key = self._vbits_key = None   # per-call caches (tensor addresses are only unique while alive)
         pq = {k: self.get_STE_params(E) for k, E in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz), ("xyz", Encoding_xyz))}
         Pgs_dict: Dict[str, torch.Tensor] = {}
         names, c1s, syms = [], [], []
@@ -525,6 +564,8 @@ class CNC_context_models(nn.Module):
                                      filename_prefix="b", streams=None):
         """utils_bpp_acc.py:867-999.  3D levels in order (level n is predicted from the decoded n-3..n-1), then the
         three planes (their dimension-wise context needs the decoded finest 3D level)."""
+        self._sbits_key = self._vbits_key = None   # per-call caches (tensor addresses are only unique while alive)
+
         def read(name):
             if streams is not None:
                 return streams[name]

@@ -52,6 +52,40 @@ __device__ __forceinline__ uint32_t renorm_shift(uint32_t low2, uint32_t high2, 
     return c0 - 1u + (((high2 >> sh) - (low2 >> sh)) <= 1u ? 1u : 0u);
 }
 
+
+// ---- the chain as it is executed: renormalisation deferred into the next symbol --------------------------------
+// Carried state: R = r2, L2 = low2, H2 = high2 of the previous symbol (before its renormalisation).  With
+// f = 31 - clz(R) and diff = (H2 >> f) - (L2 >> f) in {1, 2} the shift is S = 32 - g, g = f + diff in [1, 32], and
+// everything symbol i needs from the renormalised state is a 64-bit quantity shifted right by g:
+//     t      = ((R + 1) << S) * c >> 16      = ((R + 1) * (c << 16)) >> g
+//     ~r     = ~R << S                         = (~R : 0) >> g
+//     low    = (L2 << S) & 0x7FFFFFFF          = (L2 : 0) >> g, masked
+//     d      = (D2 << S) | top S input bits    = (D2 : window) >> g
+// (clamped funnel shifts: g = 32 returns the high word).  The 32x16 multiply does not wait for the shift any more
+// -- it runs beside the find-leading-one, the longest-latency instruction of the chain -- and the dependent path
+// per symbol is FLO -> 2 shifts -> add -> funnel shift -> [compare -> select].  A warp instruction holds its
+// 16-lane pipe for two cycles whatever the number of active lanes, so the body is also kept short (~20
+// instructions for the encoder, ~32 for the decoder).
+__device__ __forceinline__ uint32_t shr64c(uint32_t hi, uint32_t lo, uint32_t g) { return __funnelshift_rc(lo, hi, g); }   // g <= 32
+// (R + 1) * c16 and floor(log2 R) as one asm block, multiply first: both only depend on R, and the multiply has to be
+// in flight while the find-leading-one (variable latency, ~19 cycles) completes -- left to the scheduler it is
+// sunk behind the first consumer of f and ends up serialised after it
+__device__ __forceinline__ void mul_and_flo(uint32_t R, uint32_t c16, uint32_t &qhi, uint32_t &qlo, uint32_t &f) {
+    asm volatile("{\n\t.reg .u64 q, a;\n\t"
+                 "mov.b64 a, {%4, %5};\n\t"
+                 "mad.wide.u32 q, %3, %4, a;\n\t"
+                 "bfind.u32 %2, %3;\n\t"
+                 "mov.b64 {%0, %1}, q;\n\t}" : "=r"(qlo), "=r"(qhi), "=r"(f) : "r"(R), "r"(c16), "r"(0u));
+}
+__device__ __forceinline__ uint32_t renorm_g(uint32_t R, uint32_t L2, uint32_t H2) {
+    const uint32_t f = 31u - __clz(R);
+    return f + (H2 >> f) - (L2 >> f);
+}
+// low after the renormalisation of the last symbol (encoder termination)
+__device__ __forceinline__ uint32_t renorm_low(uint32_t R, uint32_t L2, uint32_t H2) {
+    return (L2 << renorm_shift(L2, H2, R)) & 0x7FFFFFFFu;
+}
+
 constexpr int ET = 1024;            // symbols per tile
 constexpr int RING_WORDS = 2048;    // output ring of the bit packer (power of two)
 constexpr uint32_t SLOW_PEND = 1024;  // pending runs longer than this take the sequential emit path
@@ -154,7 +188,7 @@ ac_encode_kernel(const uint16_t *__restrict__ c1, const uint8_t *__restrict__ sy
         };
         if (n > 0) stage(0, 0);
         __syncwarp();
-        uint32_t low = 0u, r = 0xFFFFFFFFu;
+        uint32_t R = 0xFFFFFFFFu, L2 = 0u, H2 = 0xFFFFFFFFu;   // "previous symbol" of the initial state: S = 0
         for (int64_t t = 0; t < ntiles; t++) {
             const int buf = (int)(t & 1);
             if (t + 1 < ntiles) stage(buf ^ 1, (t + 1) * ET);   // in flight while lane 0 codes
@@ -164,15 +198,18 @@ ac_encode_kernel(const uint16_t *__restrict__ c1, const uint8_t *__restrict__ sy
                 const uint32_t *src = in_tile[buf];
                 uint2 *dstrec = rec[buf];
                 auto step = [&](uint32_t pk, int j) {
-                    const uint32_t c = pk & 0xFFFFu, s = pk >> 16;
-                    const uint32_t tt = (uint32_t)(((uint64_t)r * c + c) >> 16);
-                    const uint32_t low2 = s ? low + tt : low;
-                    const uint32_t r2 = s ? r - tt : tt - 1u;
-                    const uint32_t high2 = low2 + r2;
-                    dstrec[j] = make_uint2(low2, high2);
-                    const uint32_t S = renorm_shift(low2, high2, r2);
-                    low = (low2 << S) & 0x7FFFFFFFu;
-                    r = ~(~r2 << S);
+                    const uint32_t c16 = pk << 16;                  // c1 << 16 (the symbol bit sits above it)
+                    const bool s = (pk >> 16) != 0u;
+                    uint32_t qhi, qlo, f;
+                    mul_and_flo(R, c16, qhi, qlo, f);               // (R + 1) * c1 << 16, beside the FLO
+                    const uint32_t g = f + (H2 >> f) - (L2 >> f);
+                    const uint32_t t = shr64c(qhi, qlo, g);
+                    const uint32_t nr = shr64c(~R, 0u, g);
+                    const uint32_t low = shr64c(L2, 0u, g) & 0x7FFFFFFFu;
+                    R = s ? ~nr - t : t - 1u;
+                    L2 = s ? low + t : low;
+                    H2 = L2 + R;
+                    dstrec[j] = make_uint2(L2, H2);
                 };
                 int j = 0;
                 uint4 q = *reinterpret_cast<const uint4 *>(src);
@@ -185,7 +222,7 @@ ac_encode_kernel(const uint16_t *__restrict__ c1, const uint8_t *__restrict__ sy
                     step(cur.w, j + 3);
                 }
                 for (; j < m; j++) step(src[j], j);
-                if (t == ntiles - 1) final_low = low;
+                if (t == ntiles - 1) final_low = renorm_low(R, L2, H2);
             }
             __syncwarp();
             __threadfence_block();
@@ -311,7 +348,7 @@ ac_decode_kernel(const uint16_t *__restrict__ c1, const int64_t *__restrict__ sy
     __shared__ __align__(16) uint16_t ctile[2][TILE];
     __shared__ __align__(16) uint8_t stile[TILE];
     constexpr int WT = 1024;                       // input words per staging tile
-    __shared__ uint32_t wtile[2 * WT];
+    __shared__ __align__(16) uint4 wtrip[2 * WT];  // (word[i], word[i+1], word[i+2], -): one aligned load covers a cursor step
     const int k = blockIdx.x, lane = threadIdx.x;
     const int64_t s0 = sym_off[k], n = sym_off[k + 1] - s0;
     c1 += s0;
@@ -319,15 +356,22 @@ ac_decode_kernel(const uint16_t *__restrict__ c1, const int64_t *__restrict__ sy
     const uint8_t *src = in + in_off[k];
     const int64_t nbytes = in_len[k];
 
-    auto stage_words = [&](int64_t wbase) {   // words [wbase, wbase+WT), zeros past the end (torchac)
+    auto load_word = [&](int64_t widx) -> uint32_t {   // big-endian word of the stream, zeros past the end (torchac)
+        const int64_t p = widx * 4;
+        uint32_t w = 0;
+        if (p + 4 <= nbytes) w = __byte_perm(*reinterpret_cast<const uint32_t *>(src + p), 0, 0x0123);
+        else if (p < nbytes) {
+            for (int b = 0; b < 4; b++) w = (w << 8) | (p + b < nbytes ? (uint32_t)src[p + b] : 0u);
+        }
+        return w;
+    };
+    auto stage_words = [&](int64_t wbase) {   // triples [wbase, wbase+WT)
         for (int j = lane; j < WT; j += 32) {
-            const int64_t p = (wbase + j) * 4;
-            uint32_t w = 0;
-            if (p + 4 <= nbytes) w = __byte_perm(*reinterpret_cast<const uint32_t *>(src + p), 0, 0x0123);
-            else if (p < nbytes) {
-                for (int b = 0; b < 4; b++) w = (w << 8) | (p + b < nbytes ? (uint32_t)src[p + b] : 0u);
-            }
-            wtile[(wbase + j) & (2 * WT - 1)] = w;
+            const uint32_t w0 = load_word(wbase + j);
+            uint32_t w1 = __shfl_down_sync(0xFFFFFFFFu, w0, 1), w2 = __shfl_down_sync(0xFFFFFFFFu, w0, 2);
+            if (lane == 31) w1 = load_word(wbase + j + 1);
+            if (lane >= 30) w2 = load_word(wbase + j + 2);
+            wtrip[(wbase + j) & (2 * WT - 1)] = make_uint4(w0, w1, w2, 0u);
         }
     };
     auto stage = [&](int buf, int64_t base) {
@@ -342,14 +386,13 @@ ac_decode_kernel(const uint16_t *__restrict__ c1, const int64_t *__restrict__ sy
     if (n > 0) stage(0, 0);
     __syncwarp();
 
-    int64_t staged_hi = 2 * WT;   // words [0, staged_hi) have been staged
-    uint32_t low = 0u, r = 0xFFFFFFFFu, d = 0u;
-    uint32_t W0 = 0u, W1 = 0u, W2 = 0u, nb = 0u, win = 0u;
-    int64_t wi = 1;               // W0 = word[wi], W1 = word[wi+1], W2 = word[wi+2]
+    int64_t staged_hi = 2 * WT;   // triples [0, staged_hi) have been staged
+    uint32_t R = 0xFFFFFFFFu, L2 = 0u, H2 = 0xFFFFFFFFu, D2 = 0u;   // state before the (deferred) renormalisation
+    uint32_t win = 0u;            // the 32 input bits at the cursor
+    uint64_t bp = 32;             // input cursor in bits
     if (lane == 0) {
-        d = wtile[0];
-        W0 = wtile[1]; W1 = wtile[2]; W2 = wtile[3];
-        win = W0;
+        D2 = wtrip[0].x;
+        win = wtrip[0].y;
     }
     int buf = 0;
     for (int64_t base = 0; base < n; base += TILE) {
@@ -360,27 +403,28 @@ ac_decode_kernel(const uint16_t *__restrict__ c1, const int64_t *__restrict__ sy
             const int jb = half * (TILE / 2), je = min(m, jb + TILE / 2);
             if (lane == 0) {
                 const uint16_t *cs = ctile[buf];
-                uint32_t wcur = (uint32_t)wi;
+                uint32_t bpl = (uint32_t)bp;   // the low 32 bits of the cursor are enough inside a half tile
+                uint4 w = wtrip[(bpl >> 5) & (2 * WT - 1)];   // the three words at the cursor, loaded one symbol ahead
                 auto step = [&](uint32_t c, int j) {
-                    const uint32_t tt = (uint32_t)(((uint64_t)r * c + c) >> 16);
-                    const bool s = d >= tt;            // <=> c1 <= ((value - low + 1) * 2^16 - 1) / span
+                    const uint32_t c16 = c << 16;
+                    uint32_t qhi, qlo, f;
+                    mul_and_flo(R, c16, qhi, qlo, f);
+                    const uint32_t g = f + (H2 >> f) - (L2 >> f);
+                    const uint32_t t = shr64c(qhi, qlo, g);
+                    const uint32_t d = shr64c(D2, win, g);            // value - low after the shift
+                    const uint32_t nr = shr64c(~R, 0u, g);
+                    const uint32_t low = shr64c(L2, 0u, g) & 0x7FFFFFFFu;
+                    const bool s = d >= t;                            // <=> c1 <= ((value - low + 1) * 2^16 - 1) / span
+                    R = s ? ~nr - t : t - 1u;
+                    L2 = s ? low + t : low;
+                    D2 = s ? d - t : d;
+                    H2 = L2 + R;
                     stile[j] = (uint8_t)s;
-                    const uint32_t low2 = s ? low + tt : low;
-                    const uint32_t r2 = s ? r - tt : tt - 1u;
-                    const uint32_t d2 = s ? d - tt : d;
-                    const uint32_t high2 = low2 + r2;
-                    const uint32_t S = renorm_shift(low2, high2, r2);
-                    low = (low2 << S) & 0x7FFFFFFFu;
-                    r = ~(~r2 << S);
-                    d = __funnelshift_l(win, d2, S);   // (d2 << S) | top S bits of the input window
-                    nb += S;
-                    const bool cross = nb >= 32u;
-                    W0 = cross ? W1 : W0;
-                    W1 = cross ? W2 : W1;
-                    wcur += cross ? 1u : 0u;
-                    nb &= 31u;
-                    W2 = wtile[(wcur + 2u) & (2 * WT - 1)];
-                    win = __funnelshift_l(W1, W0, nb);
+                    const uint32_t bpn = bpl + 32u - g;               // the cursor advances by the shift just applied (<= 18 bits)
+                    const bool cross = ((bpn ^ bpl) & 32u) != 0u;
+                    win = __funnelshift_l(cross ? w.z : w.y, cross ? w.y : w.x, bpn);
+                    bpl = bpn;
+                    w = wtrip[(bpl >> 5) & (2 * WT - 1)];
                 };
                 int j = jb;
                 for (; j + 4 <= je; j += 4) {
@@ -391,11 +435,11 @@ ac_decode_kernel(const uint16_t *__restrict__ c1, const int64_t *__restrict__ sy
                     step(q.y >> 16, j + 3);
                 }
                 for (; j < je; j++) step(cs[j], j);
-                wi += (int64_t)(wcur - (uint32_t)wi);
+                bp += (uint64_t)(bpl - (uint32_t)bp);
             }
             __syncwarp();
             // keep more than one word tile ahead of the consumer
-            const int64_t wp = __shfl_sync(0xFFFFFFFFu, wi, 0);
+            const int64_t wp = (int64_t)(__shfl_sync(0xFFFFFFFFu, bp, 0) >> 5);
             while (staged_hi - wp <= WT) {
                 stage_words(staged_hi);
                 staged_hi += WT;

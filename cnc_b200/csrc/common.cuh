@@ -109,9 +109,9 @@ struct Corners {
 };
 
 // returns false if the point lies outside [0,1]^D (forward writes zeros, backward skips)
-template <int D>
-__device__ __forceinline__ bool make_corners(const float (&x)[D], const LevelConst &lc, uint32_t Rb,
-                                             const uint8_t *__restrict__ vxl, Corners<D> &cs) {
+// `occ(c)` decides whether grid vertex c may contribute (occupancy test of the reference, or a precomputed bitmap)
+template <int D, class OccFn>
+__device__ __forceinline__ bool make_corners_fn(const float (&x)[D], const LevelConst &lc, OccFn occ, Corners<D> &cs) {
     bool oob = false;
 #pragma unroll
     for (int d = 0; d < D; d++) oob |= (x[d] < 0.f) | (x[d] > 1.f);  // NaN -> in range, like the ref
@@ -146,7 +146,7 @@ __device__ __forceinline__ bool make_corners(const float (&x)[D], const LevelCon
             zero |= (c[d] == 0u) | (c[d] == lc.res - 1u);  // gridencoder.cu:212-219
         }
         bool ok = !zero;
-        if (ok && vxl) ok = occ_box_any<D>(c, lc.scale_re, Rb, vxl);
+        if (ok) ok = occ(c);
         cs.w[i] = w;
         cs.row[i] = 0;
         if (ok) {
@@ -158,6 +158,12 @@ __device__ __forceinline__ bool make_corners(const float (&x)[D], const LevelCon
     if (wn == 0.f) wn = 1e-9f;  // float(0.0 + 1e-9), gridencoder.cu:288-290
     cs.wn_re = __frcp_rn(wn);   // float(1.0 / double(wn)): correctly rounded reciprocal
     return true;
+}
+
+template <int D>
+__device__ __forceinline__ bool make_corners(const float (&x)[D], const LevelConst &lc, uint32_t Rb,
+                                             const uint8_t *__restrict__ vxl, Corners<D> &cs) {
+    return make_corners_fn<D>(x, lc, [&](const uint32_t (&c)[D]) { return vxl ? occ_box_any<D>(c, lc.scale_re, Rb, vxl) : true; }, cs);
 }
 
 

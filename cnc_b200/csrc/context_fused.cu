@@ -33,6 +33,8 @@ struct Args {
     const uint8_t *vxl;   // [Rb]^3 occupancy
     int32_t Rb;
     const uint8_t *bits;  // 1-bit sign table of the whole 3D encoder (cnc_sign_pack)
+    const uint32_t *vbits;     // vertex validity bitmaps of all levels (cnc_vertex_valid_bits), nullable
+    const int64_t *vbit_off;   // [L+1] bit offset of each level's bitmap (multiples of 32)
     const int32_t *offs, *res;  // level arrays of the encoder
     int32_t level;        // n >= 3; context = levels n-3, n-2, n-1
     float Pg;             // level-wide frequency of +1 (utils_bpp_acc.py:472-486)
@@ -55,8 +57,12 @@ __global__ void __launch_bounds__(256) context3d_kernel(const Args a) {
     const float res_n = (float)__ldg(a.res + a.level);
     const float scale_n = __fsub_rn(res_n, 2.0f);
     LevelConst lc[3];
+    const uint32_t *vb[3];
 #pragma unroll
-    for (int l = 0; l < 3; l++) lc[l] = load_level(a.offs, a.res, (uint32_t)(a.level - 3 + l));
+    for (int l = 0; l < 3; l++) {
+        lc[l] = load_level(a.offs, a.res, (uint32_t)(a.level - 3 + l));
+        vb[l] = a.vbits ? a.vbits + (__ldg(a.vbit_off + a.level - 3 + l) >> 5) : nullptr;
+    }
 
     for (int64_t e = warp0; e < a.Ne; e += nwarp) {
         const int64_t v0 = __ldg(a.seg + e) - a.seg_base, v1 = __ldg(a.seg + e + 1) - a.seg_base;
@@ -80,7 +86,16 @@ __global__ void __launch_bounds__(256) context3d_kernel(const Args a) {
                 float f[F];
 #pragma unroll
                 for (int k = 0; k < F; k++) f[k] = 0.f;
-                if (make_corners<3>(x, lc[l], (uint32_t)a.Rb, a.vxl, cs)) {
+                // "vertex touches the occupancy" (gridencoder.cu:221-276): read from the per-level bitmap when the
+                // caller built one (same predicate, evaluated once per vertex instead of once per use)
+                const uint32_t *vbl = vb[l];
+                const LevelConst &lcl = lc[l];
+                const bool inside = vbl
+                    ? make_corners_fn<3>(x, lcl, [&](const uint32_t (&cc)[3]) {
+                          const uint32_t v = (cc[0] * lcl.res + cc[1]) * lcl.res + cc[2];
+                          return ((__ldg(vbl + (v >> 5)) >> (v & 31u)) & 1u) != 0u; }, cs)
+                    : make_corners<3>(x, lcl, (uint32_t)a.Rb, a.vxl, cs);
+                if (inside) {
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         if ((cs.valid >> i) & 1u) {
@@ -158,6 +173,31 @@ __global__ void __launch_bounds__(256) context3d_kernel(const Args a) {
     }
 }
 
+// One bit per grid vertex of every level: does the +-1-voxel box around the vertex touch an occupied cell
+// (the per-corner test of the reference's masked gather, gridencoder.cu:221-276).  Bit v = (c0*res + c1)*res + c2
+// of level l lives at bit_off[l] + v.  A warp covers 32 consecutive vertices -> one ballot, one store.
+__global__ void __launch_bounds__(256) vertex_valid_kernel(const uint8_t *__restrict__ vxl, int32_t Rb, const int32_t *__restrict__ res_list,
+                                                           int32_t n_levels, const int64_t *__restrict__ bit_off, uint32_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t total_words = __ldg(bit_off + n_levels) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int level = 0;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total_words; w += nwarp) {
+        while (level + 1 < n_levels && (w << 5) >= __ldg(bit_off + level + 1)) level++;
+        while (level > 0 && (w << 5) < __ldg(bit_off + level)) level--;
+        const uint32_t res = (uint32_t)__ldg(res_list + level);
+        const int64_t v = (w << 5) - __ldg(bit_off + level) + lane;
+        bool ok = false;
+        if (v < (int64_t)res * res * res) {
+            const uint32_t c[3] = {(uint32_t)(v / ((int64_t)res * res)), (uint32_t)((v / res) % res), (uint32_t)(v % res)};
+            const float scale_re = __frcp_rn((float)(res - 2u));
+            ok = occ_box_any<3>(c, scale_re, (uint32_t)Rb, vxl);
+        }
+        const uint32_t word = __ballot_sync(0xFFFFFFFFu, ok);
+        if (lane == 0) out[w] = word;
+    }
+}
+
 }  // namespace cf
 }  // namespace cnc
 
@@ -167,17 +207,33 @@ extern "C" {
 
 uint32_t cnc_context3d_mlp_floats(void) { return cf::MLP_FLOATS; }
 
+int cnc_vertex_valid_bits(const uint8_t *binary_vxl, int32_t Rb, const int32_t *resolutions, int32_t n_levels,
+                           const int64_t *bit_offsets, int64_t total_bits, uint32_t *out_words, cnc_stream_t stream) {
+    if (n_levels <= 0 || total_bits <= 0) return CNC_OK;
+    if (!binary_vxl || !resolutions || !bit_offsets || !out_words || Rb <= 0 || (total_bits & 31)) {
+        set_error("vertex_valid_bits: bad argument (offsets must be multiples of 32 bits)");
+        return CNC_EINVAL;
+    }
+    const int64_t words = total_bits >> 5;
+    int64_t blocks = (words + 7) / 8;
+    if (blocks > 148 * 8 * 8) blocks = 148 * 8 * 8;
+    cf::vertex_valid_kernel<<<(uint32_t)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(binary_vxl, Rb, resolutions, n_levels,
+                                                                                          bit_offsets, out_words);
+    return check_launch("vertex_valid_bits");
+}
+
 int cnc_context3d_probs(const int16_t *pts, const int64_t *seg, int64_t n_entries, const uint8_t *binary_vxl, int32_t Rb,
                         const uint8_t *sign_bits, const int32_t *offsets, const int32_t *resolutions, int32_t level,
                         float Pg, const float *mlp_packed, float *prob, float *mean, uint8_t *exist, int64_t seg_base,
-                        cnc_stream_t stream) {
+                        const uint32_t *vertex_bits, const int64_t *vertex_bit_offsets, cnc_stream_t stream) {
     if (n_entries == 0) return CNC_OK;
     if (!pts || !seg || !binary_vxl || !sign_bits || !offsets || !resolutions || !mlp_packed || !prob || !exist || Rb <= 0) {
         set_error("context3d_probs: bad argument");
         return CNC_EINVAL;
     }
+    if ((vertex_bits == nullptr) != (vertex_bit_offsets == nullptr)) { set_error("context3d_probs: vertex_bits and vertex_bit_offsets go together"); return CNC_EINVAL; }
     if (level < 3) { set_error("context3d_probs: needs three coarser context levels (level >= 3)"); return CNC_ENOTSUP; }
-    cf::Args a{pts, seg, seg_base, binary_vxl, Rb, sign_bits, offsets, resolutions, level, Pg, mlp_packed, prob, mean, exist, n_entries};
+    cf::Args a{pts, seg, seg_base, binary_vxl, Rb, sign_bits, vertex_bits, vertex_bit_offsets, offsets, resolutions, level, Pg, mlp_packed, prob, mean, exist, n_entries};
     const int64_t warps = n_entries;
     int64_t blocks = (warps + 7) / 8;
     const int64_t cap = 148 * 8 * 4;  // persistent-ish: a few waves of 8 resident CTAs per SM, warps stride over entries

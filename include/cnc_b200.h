@@ -184,13 +184,22 @@ int cnc_field_fwd(const float *pos, const float *dirs, const float *aabb6_host,
  *   W1^T [25][32], b1 [32], W2^T [32][32], b2 [32], W3^T [32][8], b3 [8] of context_model_3D.
  *   -> prob [n_entries,8] (clamped to [1e-6, 1-1e-6]; 0 for entries that are not coded),
  *      mean [n_entries,8] unclamped (nullable), exist [n_entries] u8 (mask_exist, :823).
+ *   vertex_bits / vertex_bit_offsets (nullable, together): the per-vertex occupancy predicate of the masked
+ *   gather (gridencoder.cu:221-276) precomputed by cnc_vertex_valid_bits for all levels of the encoder: one bit
+ *   per grid vertex, bit (c0*res + c1)*res + c2 of level l at vertex_bit_offsets[l] (multiples of 32);
+ *   the occupancy does not change during an encode/decode, so the box test runs once per vertex instead of
+ *   once per (voxel, corner, context level).  Results are identical with and without it.
  * ---------------------------------------------------------------------------------------- */
 uint32_t cnc_context3d_mlp_floats(void);
+int cnc_vertex_valid_bits(const uint8_t *binary_vxl, int32_t Rb, const int32_t *resolutions,
+                          int32_t n_levels, const int64_t *bit_offsets, int64_t total_bits,
+                          uint32_t *out_words, cnc_stream_t stream);
 int cnc_context3d_probs(const int16_t *pts, const int64_t *seg, int64_t n_entries,
                         const uint8_t *binary_vxl, int32_t Rb, const uint8_t *sign_bits,
                         const int32_t *offsets, const int32_t *resolutions, int32_t level, float Pg,
                         const float *mlp_packed, float *prob, float *mean, uint8_t *exist,
-                        int64_t seg_base, cnc_stream_t stream);
+                        int64_t seg_base, const uint32_t *vertex_bits,
+                        const int64_t *vertex_bit_offsets, cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Occupancy-grid ray marching, packed scans, volume rendering (vendored nerfacc 0.5.3).
