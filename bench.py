@@ -164,18 +164,19 @@ def codec_bench(dev, cpu_seconds=12.0):
     vxl = (X * X + Y * Y + Z * Z <= 1.0).unsqueeze(0)   # radius-1 ball in the +-1.5 aabb (15.5 % of the cells)
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t0
-    captured = {}
-    orig = tac.encode_streams
+    captured = {"c1": [], "sym": []}
+    orig = tac.encode_streams_async
 
     def spy(c1s, syms):
-        captured["c1"], captured["sym"] = c1s, syms
+        captured["c1"] += list(c1s)
+        captured["sym"] += list(syms)
         return orig(c1s, syms)
 
-    tac.encode_streams = spy
+    tac.encode_streams_async = spy
     try:
         cm.encode_binary_vxl_mixPg_3D2D(*encs, vxl, "bench", return_streams=True)  # warm-up (+ capture the streams)
     finally:
-        tac.encode_streams = orig
+        tac.encode_streams_async = orig
     enc_s, dec_s = [], []
     for _ in range(3):
         torch.cuda.synchronize(); t = time.perf_counter()

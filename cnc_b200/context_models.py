@@ -506,13 +506,27 @@ class CNC_context_models(nn.Module):
         self._sbits_key = self._vbits_key = None   # per-call caches (tensor addresses are only unique while alive)
         pq = {k: self.get_STE_params(E) for k, E in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz), ("xyz", Encoding_xyz))}
         Pgs_dict: Dict[str, torch.Tensor] = {}
-        names, c1s, syms = [], [], []
+        names, c1s, syms, jobs = [], [], [], []
         ttl_bit = torch.zeros((), device=pq["xyz"].device)
+        main = torch.cuda.current_stream(pq["xyz"].device)
+        if getattr(self, "_coder_streams", None) is None:   # one per flush: the jobs must not queue behind each other
+            self._coder_streams = [torch.cuda.Stream(pq["xyz"].device) for _ in range(self.n_levels + 2)]
 
         def emit(name, xs, ps):
             names.append(name)
             c1s.append(tac.cdf_from_p(ps))
             syms.append(((xs + 1) // 2).to(torch.uint8).reshape(-1))
+
+        def flush():
+            """hand the streams collected so far to the coder on the side stream: it runs (one SM per stream)
+            while this stream goes on computing the probabilities of the next level"""
+            done = sum(len(j[0]) for j in jobs)
+            if done == len(names):
+                return
+            side = self._coder_streams[len(jobs) % len(self._coder_streams)]
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                jobs.append((names[done:], tac.encode_streams_async(c1s[done:], syms[done:])))
 
         idx_coords2 = self.get_idx_coords2(binary_vxl)
         planes = self._planes(binary_vxl)
@@ -544,7 +558,9 @@ class CNC_context_models(nn.Module):
                 values_q = pq["xyz"][self.unique_value_list[n][lo:hi] + self.offs[n]][mask_exist]
                 ttl_bit += torch.sum(self.entropy_model(values_q, ps))
                 emit(f"{filename_prefix}_3D{n}_{sn}.b", values_q.reshape(-1), ps.reshape(-1))
-        streams = tac.encode_streams(c1s, syms)      # all streams at once, one warp each
+            flush()
+        flush()
+        streams = [b for _, job in jobs for b in job.result()]
         coded_bits = 0
         for name, data in zip(names, streams):
             coded_bits += len(data) * 8

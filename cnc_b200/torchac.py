@@ -31,31 +31,58 @@ def _offsets(lengths: Sequence[int], align: int = 1):
     return off
 
 
-def encode_streams(c1_list: Sequence[torch.Tensor], sym_list: Sequence[torch.Tensor]) -> List[bytes]:
-    """Encode K independent streams (c1 int16-bit-pattern, sym uint8 in {0,1}) -> K byte strings."""
+class _EncodeJob:
+    """Streams handed to the GPU coder whose bytes have not been fetched yet (`encode_streams_async`)."""
+
+    def __init__(self, c1, sym, lens, caps, out, out_off_h, out_len, cuda_stream):
+        self.c1, self.sym, self.lens, self.caps = c1, sym, lens, caps
+        self.out, self.out_off_h, self.out_len, self.cuda_stream = out, out_off_h, out_len, cuda_stream
+
+    def result(self) -> List[bytes]:
+        """Wait for the coder and return the K byte strings."""
+        self.cuda_stream.synchronize()
+        lens_h = self.out_len.cpu().tolist()
+        if any(l > c for l, c in zip(lens_h, self.caps)):   # pathological probabilities: redo with larger buffers
+            caps = [max(c, l + 64) for l, c in zip(lens_h, self.caps)]
+            with torch.cuda.stream(self.cuda_stream):
+                job = _launch_encode(self.c1, self.sym, self.lens, caps)
+            return job.result()
+        host = self.out.cpu().numpy()
+        return [host[self.out_off_h[k]: self.out_off_h[k] + lens_h[k]].tobytes() for k in range(len(lens_h))]
+
+
+def _launch_encode(c1, sym, lens, caps) -> _EncodeJob:
+    dev = c1.device
+    K = len(lens)
+    sym_off = torch.tensor(_offsets(lens), dtype=torch.int64, device=dev)
+    out_off_h = _offsets(caps, 4)
+    out = torch.empty(out_off_h[-1], dtype=torch.uint8, device=dev)
+    out_off = torch.tensor(out_off_h, dtype=torch.int64, device=dev)
+    out_len = torch.zeros(K, dtype=torch.int64, device=dev)
+    check(lib().cnc_ac_encode(ptr(c1), ptr(sym), ptr(sym_off), ptr(out), ptr(out_off), ptr(out_len), K, stream()))
+    job = _EncodeJob(c1, sym, lens, caps, out, out_off_h, out_len, torch.cuda.current_stream(dev))
+    job._keep = (sym_off, out_off)
+    return job
+
+
+def encode_streams_async(c1_list: Sequence[torch.Tensor], sym_list: Sequence[torch.Tensor]) -> _EncodeJob:
+    """Launch the coder for K independent streams on the current CUDA stream without waiting for it;
+    `.result()` returns the byte strings.  Lets a caller code early streams while it still computes the
+    probabilities of later ones (the coder occupies one SM per stream)."""
     K = len(c1_list)
     if K == 0:
-        return []
-    dev = c1_list[0].device
+        raise ValueError("no streams")
     lens = [int(c.numel()) for c in c1_list]
-    c1 = torch.cat([c.view(-1) for c in c1_list]) if K > 1 else c1_list[0].view(-1)
-    sym = torch.cat([s.view(-1) for s in sym_list]) if K > 1 else sym_list[0].view(-1)
-    sym = sym.to(torch.uint8).contiguous()
-    c1 = c1.contiguous()
-    sym_off = torch.tensor(_offsets(lens), dtype=torch.int64, device=dev)
-    caps = [n // 8 * 2 + 64 for n in lens]
-    while True:
-        out_off_h = _offsets(caps, 4)
-        out = torch.empty(out_off_h[-1], dtype=torch.uint8, device=dev)
-        out_off = torch.tensor(out_off_h, dtype=torch.int64, device=dev)
-        out_len = torch.zeros(K, dtype=torch.int64, device=dev)
-        check(lib().cnc_ac_encode(ptr(c1), ptr(sym), ptr(sym_off), ptr(out), ptr(out_off), ptr(out_len), K, stream()))
-        lens_h = out_len.cpu().tolist()
-        if all(l <= c for l, c in zip(lens_h, caps)):
-            break
-        caps = [max(c, l + 64) for l, c in zip(lens_h, caps)]  # pathological probabilities: retry larger
-    host = out.cpu().numpy()
-    return [host[out_off_h[k]: out_off_h[k] + lens_h[k]].tobytes() for k in range(K)]
+    c1 = (torch.cat([c.view(-1) for c in c1_list]) if K > 1 else c1_list[0].view(-1)).contiguous()
+    sym = (torch.cat([x.view(-1) for x in sym_list]) if K > 1 else sym_list[0].view(-1)).to(torch.uint8).contiguous()
+    return _launch_encode(c1, sym, lens, [n // 8 * 2 + 64 for n in lens])
+
+
+def encode_streams(c1_list: Sequence[torch.Tensor], sym_list: Sequence[torch.Tensor]) -> List[bytes]:
+    """Encode K independent streams (c1 int16-bit-pattern, sym uint8 in {0,1}) -> K byte strings."""
+    if len(c1_list) == 0:
+        return []
+    return encode_streams_async(c1_list, sym_list).result()
 
 
 def decode_streams(c1_list: Sequence[torch.Tensor], streams: Sequence[bytes]) -> List[torch.Tensor]:

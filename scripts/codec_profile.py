@@ -26,7 +26,6 @@ cm.get_pn_embed_frac = timed("get_pn_embed_frac", cm.get_pn_embed_frac)
 cm._probs_2D = timed("probs_2D", cm._probs_2D)
 cm._probs_3D = timed("probs_3D", cm._probs_3D)
 cm.get_STE_params = timed("STE", cm.get_STE_params)
-tac.encode_streams = timed("encode_streams", tac.encode_streams)
 tac.decode_streams = timed("decode_streams", tac.decode_streams)
 tac.cdf_from_p = timed("cdf_from_p", tac.cdf_from_p)
 for it in range(2):

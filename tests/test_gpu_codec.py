@@ -103,20 +103,21 @@ def test_streams_equal_oracle_coder(cuda, oracle):
     cm, encs, vxl = make(cuda, **SMALL)
     from cnc_b200 import torchac as tac
 
-    captured = {}
-    orig = tac.encode_streams
+    captured = {"c1": [], "sym": []}
+    orig = tac.encode_streams_async
 
     def spy(c1s, syms):
-        out = orig(c1s, syms)
-        captured["c1"], captured["sym"], captured["out"] = c1s, syms, out
-        return out
+        captured["c1"] += list(c1s)
+        captured["sym"] += list(syms)
+        return orig(c1s, syms)
 
-    tac.encode_streams = spy
+    tac.encode_streams_async = spy
     try:
-        cm.encode_binary_vxl_mixPg_3D2D(*encs, vxl, "t", return_streams=True)
+        _, _, _, streams = cm.encode_binary_vxl_mixPg_3D2D(*encs, vxl, "t", return_streams=True)
     finally:
-        tac.encode_streams = orig
-    for c1, sym, data in zip(captured["c1"], captured["sym"], captured["out"]):
+        tac.encode_streams_async = orig
+    assert len(captured["c1"]) == len(streams) > 0
+    for c1, sym, data in zip(captured["c1"], captured["sym"], streams.values()):   # dicts keep the emission order
         want = oracle.ac_encode(c1.cpu().numpy().view(np.uint16), sym.cpu().numpy())
         assert data == want
         assert np.array_equal(oracle.ac_decode(c1.cpu().numpy().view(np.uint16), data), sym.cpu().numpy())
