@@ -84,6 +84,17 @@ def peaks():
         return 6650.0, "fallback"
 
 
+def ncu_traffic(kernel, n_samples):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` summary
+    (profiles/ncu_traffic.json, written by scripts/ncu_summary.py); None when no capture matches this launch size"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = t.get(f"{kernel}@{n_samples}")
+        return None if e is None else int(e["dram_bytes"])
+    except Exception:
+        return None
+
+
 def make_inputs(n, seed, device):
     g = torch.Generator(device="cpu").manual_seed(seed)
     d = torch.randn(n, 3, generator=g)
@@ -278,6 +289,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-codec", action="store_true", help="skip the entropy encode/decode measurement (metric ii)")
     ap.add_argument("--train-steps", type=int, default=5, help="steps of the fwd+bwd(+all-reduce) measurement, 0 = skip")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling aid: only the device-resident step is launched (e2e = null)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
 
@@ -353,19 +365,22 @@ def main():
 
     for _ in range(a.warmup):
         step()
-        step_e2e()
+        if not a.no_e2e:
+            step_e2e()
     barrier()
     l0 = _lib.LAUNCHES
     with Clocks(local) as clk:
         ms = timed(step, a.steps)
     launches = _lib.LAUNCHES - l0
     barrier()
-    ms_e2e = timed(step_e2e, a.steps)
+    ms_e2e = timed(step_e2e, a.steps) if not a.no_e2e else float("nan")
     barrier()
 
     # dominant kernel alone, CUDA events on its stream: ours = the fused field kernel (one launch = the
     # whole step); reference = its 3D grid gather kernel_grid<float,3,8> (the top non-library kernel)
-    if a.impl == "reference":
+    if a.no_e2e:
+        ms_k = ms
+    elif a.impl == "reference":
         enc = model.encoding_xyz
         xn = ((pos + 1.5) / 3.0).contiguous()
         with torch.no_grad():
@@ -376,6 +391,31 @@ def main():
         for _ in range(3):
             field.fused_forward(pos, dirs)
         ms_k = timed(lambda: field.fused_forward(pos, dirs), a.steps)
+    # forward + backward over the same sample batch (metric (i), second half: SURVEY 8d): d(sum rgb + sum sigma)
+    # w.r.t. every table and MLP parameter; ours = differentiable path, reference = its K1/K2 kernels under autograd
+    fwd_bwd = None
+    if a.train_steps > 0 and not a.no_e2e:
+        model.train()
+        params = [p for p in model.parameters() if p.requires_grad]
+
+        def fb():
+            for p in params:
+                p.grad = None
+            rgb, sigma = model(pos, dirs)
+            (rgb.sum() + sigma.sum()).backward()
+
+        for _ in range(3):
+            fb()
+        ms_fb = timed(fb, max(a.train_steps, 3))
+        t_fb = torch.tensor([ms_fb], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t_fb, op=dist.ReduceOp.MAX)
+        ms_fb = float(t_fb.item()) / max(a.train_steps, 3)
+        fwd_bwd = {"what": "forward + backward of sum(rgb) + sum(sigma) over the step's sample batch, all table and MLP gradients",
+                   "ms_per_step": ms_fb, "samples_per_s": world * Ns / (ms_fb * 1e-3)}
+        for p in params:
+            p.grad = None
+        model.eval()
     train = None
     if a.impl == "ours" and a.train_steps > 0:
         train = train_bench(dev, rank, world, a.train_steps, field)
@@ -398,12 +438,13 @@ def main():
         ach = Ns * FLOP_PER_SAMPLE_FWD / s_k / 1e12
         roof = {"bound": "tensor", "kernel": "cnc::ff::field_fwd_kernel<false> (encode + 5 FC layers, 3xTF32 tcgen05)",
                 "achieved": ach, "peak": tf_peak, "peak_source": which + " (dense bf16 cuBLAS burst)", "unit": "TFLOP/s",
-                "frac": ach / tf_peak, "traffic": None,
+                "frac": ach / tf_peak, "traffic": ncu_traffic("field_fwd_kernel", Ns),
                 "algorithmic_flops_per_launch": Ns * FLOP_PER_SAMPLE_FWD, "ms_per_launch": ms_k / a.steps,
-                "note": "algorithmic fp32 FLOPs (189760/sample); the kernel executes 2.99x that as kind::tf32 MMAs "
-                        "(3xTF32 hi/lo split, K padding; the 160->3 layer runs as FFMA) at half the bf16 rate, so "
-                        "frac 1/6 = 0.17 is the ceiling of this formulation",
-                "executed_tf32_tflops": ach * 3.0 * (256 * 160 + 160 * 80 + 96 * 160 + 160 * 160) / 94880.0,
+                "note": "algorithmic fp32 FLOPs (189760/sample). fp32 parity costs two MMAs per k-step (kind::tf32 K=8 "
+                        "for hi*hi, kind::f16 K=16 on bf16 pairs for the two correction terms), each at half the dense "
+                        "bf16 rate, plus K padding (255->256, 95->96); the 160->3 layer runs as FFMA: frac 0.25 is "
+                        "the ceiling of this formulation",
+                "executed_mma_tflops_bf16_equiv": ach * 4.0 * (256 * 160 + 160 * 80 + 96 * 160 + 160 * 160) / 94880.0,
                 "hbm_algorithmic_GBps": Ns * (12 + 4608 + 12 + 16) / s_k / 1e9, "hbm_peak_GBps": hbm_peak}
     else:
         bytes_k = Ns * (12 + 12 * 8 * 32 + 96 * 4)  # 3468 B/point, 3D part of SURVEY 8(d)
@@ -420,9 +461,9 @@ def main():
                                "255-160-80 / 95-160-160-3), forward sigma+rgb over N_s samples per GPU",
                    "samples_per_gpu": Ns, "parallelism": f"ray-sharded x{world}, replicas, no data-path collective",
                    "l2": "flushed between timed iterations (256 MiB write outside the event-timed span)"},
-        "e2e": {"value": world * Ns * a.steps / (ms_e2e * 1e-3), "unit": "samples/s",
-                "h2d_bytes_per_step": int(pin_pos.numel() * 4 + pin_dir.numel() * 4),
-                "d2h_bytes_per_step": int(pin_out.numel() * 4)},
+        "e2e": None if a.no_e2e else {"value": world * Ns * a.steps / (ms_e2e * 1e-3), "unit": "samples/s",
+                                      "h2d_bytes_per_step": int(pin_pos.numel() * 4 + pin_dir.numel() * 4),
+                                      "d2h_bytes_per_step": int(pin_out.numel() * 4)},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": roof,
@@ -431,9 +472,10 @@ def main():
         line["cpu_baseline"] = {"value": line["value"], "unit": "samples/s", "cores": 0, "kind": "reference",
                                 "sample": "reference CUDA kernels (oracle/_ref) + torch fp32 MLP on the GPU: the "
                                           "reference has no CPU implementation of this path"}
-        line["e2e"]["h2d_bytes_per_step"] = line["e2e"]["h2d_bytes_per_step"]
     elif world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
+    if fwd_bwd is not None:
+        line["fwd_bwd"] = fwd_bwd
     if train is not None:
         line["train_step"] = train
     if a.impl == "ours" and world == 1 and not a.no_codec:
