@@ -285,6 +285,11 @@ struct FieldArgs {
     float *sigma;  // [N]
     float *rgb;    // [N,3]   (nullptr in density-only mode)
     float *geo;    // [N,79]  nullable
+    // training forward (all nullable, together): what the backward pass needs, written as the values go by
+    float *sv_x0;  // [N,256] layer-1 input (192 grid features | x, sin/cos 63 | 0)
+    float *sv_h1;  // [N,160] relu(L1)
+    float *sv_h3;  // [N,160] relu(L3)
+    float *sv_h4;  // [N,160] relu(L4)
     uint32_t N;
     unsigned long long *dbg;  // optional timeline buffer (cnc_field_set_timeline_buffer), see DESIGN.md
 };
@@ -450,7 +455,7 @@ __device__ __forceinline__ void acc_block(uint32_t tl, uint32_t c_main, int b8, 
 // (+bias, ReLU, split) -> hi at dst_hi, lo at dst_lo
 template <uint32_t MAIN2, uint32_t SMALL>
 __device__ __forceinline__ void ep_hidden(uint32_t tl, int cg, uint32_t c_main, uint32_t dst_hi, uint32_t dst_lo,
-                                          const float *__restrict__ bias) {
+                                          const float *__restrict__ bias, float *__restrict__ save_row) {
 #pragma unroll 1
     for (int b = cg; b < 20; b += 4) {
         float v[8];
@@ -459,7 +464,14 @@ __device__ __forceinline__ void ep_hidden(uint32_t tl, int cg, uint32_t c_main, 
         const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + 8 * b)), b1 = __ldg(reinterpret_cast<const float4 *>(bias + 8 * b) + 1);
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int k = 0; k < 8; k++) split_tf32(fmaxf(__fadd_rn(v[k], bb[k]), 0.f), hi[k], lo[k]);
+        for (int k = 0; k < 8; k++) {
+            v[k] = fmaxf(__fadd_rn(v[k], bb[k]), 0.f);
+            split_tf32(v[k], hi[k], lo[k]);
+        }
+        if (save_row != nullptr) {
+            *reinterpret_cast<float4 *>(save_row + 8 * b) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4 *>(save_row + 8 * b + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
         tmem_st8(tl + dst_hi + 8 * b, hi);
         tmem_st8(tl + dst_lo + 8 * b, lo);
     }
@@ -669,7 +681,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                 gather_issue<2>(x2, bt, lvl[12 + q], p);
             }
         };
-        auto publish = [&](const float (&f)[8]) {  // 8 feature values -> smem slot -> MMA warp
+        auto publish = [&](int c, uint32_t prow, const float (&f)[8]) {  // 8 feature values -> smem slot -> MMA warp
+            if (a.sv_x0 != nullptr && prow < a.N) {
+                float *d = a.sv_x0 + (size_t)prow * 256 + 32 * c + 8 * q;
+                *reinterpret_cast<float4 *>(d) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4 *>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            }
             const uint32_t sl = a_prod & 1u, use = a_prod >> 1;
             if (use > 0) mbar_wait(a_empty(sl), (use - 1) & 1u);
             store_oct(smem + SMEM_A + sl * A_SLOT_BYTES, r, q, f);
@@ -677,13 +694,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             mbar_arrive(a_full(sl));
             a_prod++;
         };
-        auto finish = [&](int c, const Pend &p) {  // gathered chunk c (c < 6)
+        auto finish = [&](int c, uint32_t prow, const Pend &p) {  // gathered chunk c (c < 6) of global row prow
             float f[8];
             if (c < 3) gather_finish<8>(p, f);
             else gather_finish<4>(p, f);
-            publish(f);
+            publish(c, prow, f);
         };
-        auto embed = [&](int c, const float (&x)[3]) {  // chunks 6, 7
+        auto embed = [&](int c, uint32_t prow, const float (&x)[3]) {  // chunks 6, 7
             // embed column j (0..62): j<3 -> x[j]; else g=(j-3)/3, d=(j-3)%3: even g -> sin(2^(g/2) x_d), odd -> cos
             float f[8];
 #pragma unroll
@@ -699,7 +716,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                 }
                 f[jj] = v;
             }
-            publish(f);
+            publish(c, prow, f);
         };
 
         float x[3], xn[3];
@@ -720,15 +737,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
 #pragma unroll 1
             for (int c = c0; c < 6; c += 2) {
                 issue(c + 1, x, pb);
-                finish(c, pa);
+                finish(c, row, pa);
                 if (threadIdx.x == 0) CNC_TL(1 + c);
                 if (c + 2 < 6) issue(c + 2, x, pa);
-                finish(c + 1, pb);
+                finish(c + 1, row, pb);
                 if (threadIdx.x == 0) CNC_TL(2 + c);
             }
 #pragma unroll 1
             for (int c = 6; c < 8; c++) {
-                embed(c, x);
+                embed(c, row, x);
                 if (threadIdx.x == 0) CNC_TL(1 + c);
             }
             c0 = 0;
@@ -741,13 +758,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             mbar_wait(layer_done, done_cnt & 1u); done_cnt++;
             tc_fence_after();
             if (threadIdx.x == 0) CNC_TL(10);
-            ep_hidden<160u, 320u>(tl, q, 0u, 0u, 160u, bias + BIAS1);
+            ep_hidden<160u, 320u>(tl, q, 0u, 0u, 160u, bias + BIAS1, (a.sv_h1 != nullptr && live) ? a.sv_h1 + (size_t)row * 160 : nullptr);
             tc_fence_before();
             mbar_arrive(act_ready);
             if (threadIdx.x == 0) CNC_TL(11);
             if (has_next) {  // while L2 runs: chunk 0 of the next tile
                 issue(1, xn, pb);
-                finish(0, pa);
+                finish(0, row + gridDim.x * TILE_M, pa);
             }
             // ---- ep2: acc2 [320,400)+[400,480): col 0 -> sigma, cols 1..79 -> geo -> head input (+ SH16 block)
             mbar_wait(layer_done, done_cnt & 1u); done_cnt++;
@@ -807,13 +824,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                 mbar_wait(layer_done, done_cnt & 1u); done_cnt++;
                 tc_fence_after();
                 if (threadIdx.x == 0) CNC_TL(14);
-                ep_hidden<NONE, 352u>(tl, q, 192u, 192u, 352u, bias + BIAS3);
+                ep_hidden<NONE, 352u>(tl, q, 192u, 192u, 352u, bias + BIAS3, (a.sv_h3 != nullptr && live) ? a.sv_h3 + (size_t)row * 160 : nullptr);
                 tc_fence_before();
                 mbar_arrive(act_ready);
                 if (threadIdx.x == 0) CNC_TL(15);
                 if (has_next) {  // while L4 (the longest of the small layers) runs: chunk 1 of the next tile
                     issue(2, xn, pa);
-                    finish(1, pb);
+                    finish(1, row + gridDim.x * TILE_M, pb);
                     c0 = 2;
                 }
                 // ---- ep4 + the last layer: h4 = relu(acc4 + b4) stays in registers; Linear(160,3) is 3 x 40 FFMA per
@@ -838,9 +855,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
 #pragma unroll
                     for (int k = 0; k < 8; k++) {
                         const float h = fmaxf(__fadd_rn(v[k], bb[k]), 0.f);
+                        v[k] = h;
                         p0 = __fmaf_rn(h, W0[k], p0);
                         p1 = __fmaf_rn(h, W1[k], p1);
                         p2 = __fmaf_rn(h, W2[k], p2);
+                    }
+                    if (a.sv_h4 != nullptr && live) {
+                        float *d = a.sv_h4 + (size_t)row * 160 + 8 * b;
+                        *reinterpret_cast<float4 *>(d) = make_float4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<float4 *>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
                     }
                 }
                 tmem_st4(tl + 480u + 4u * q, __float_as_uint(p0), __float_as_uint(p1), __float_as_uint(p2), 0u);
@@ -868,7 +891,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             tc_fence_before();
             mbar_arrive(act_ready);  // this tile's accumulators are consumed: the next tile's L1 may overwrite them
             if (has_next) {
-                if (DENSITY_ONLY) { issue(2, xn, pa); finish(1, pb); c0 = 2; }
+                if (DENSITY_ONLY) { issue(2, xn, pa); finish(1, row + gridDim.x * TILE_M, pb); c0 = 2; }
                 x[0] = xn[0]; x[1] = xn[1]; x[2] = xn[2];
             }
         }
@@ -907,10 +930,11 @@ int cnc_field_pack_weights(const float *W1, const float *b1, const float *W2, co
     return check_launch("field_pack_weights");
 }
 
-int cnc_field_fwd(const float *pos, const float *dirs, const float *aabb6_host, const uint8_t *bits_xyz,
-                  const uint8_t *bits_xy, const uint8_t *bits_xz, const uint8_t *bits_yz, const int32_t *offsets3,
-                  const int32_t *resolutions3, const int32_t *offsets2, const int32_t *resolutions2,
-                  const float *blob, float *sigma, float *rgb, float *geo, uint32_t N, cnc_stream_t stream) {
+static int field_fwd_impl(const float *pos, const float *dirs, const float *aabb6_host, const uint8_t *bits_xyz,
+                          const uint8_t *bits_xy, const uint8_t *bits_xz, const uint8_t *bits_yz, const int32_t *offsets3,
+                          const int32_t *resolutions3, const int32_t *offsets2, const int32_t *resolutions2,
+                          const float *blob, float *sigma, float *rgb, float *geo, float *sv_x0, float *sv_h1, float *sv_h3,
+                          float *sv_h4, uint32_t N, cnc_stream_t stream) {
     if (N == 0) return CNC_OK;
     if (!pos || !aabb6_host || !bits_xyz || !bits_xy || !bits_xz || !bits_yz || !offsets3 || !resolutions3 ||
         !offsets2 || !resolutions2 || !blob || !sigma || (dirs && !rgb)) {
@@ -940,12 +964,33 @@ int cnc_field_fwd(const float *pos, const float *dirs, const float *aabb6_host, 
     a.bits3 = bits_xyz; a.bits_xy = bits_xy; a.bits_xz = bits_xz; a.bits_yz = bits_yz;
     a.offs3 = offsets3; a.res3 = resolutions3; a.offs2 = offsets2; a.res2 = resolutions2;
     a.blob = blob; a.sigma = sigma; a.rgb = rgb; a.geo = geo; a.N = N; a.dbg = g_timeline;
+    a.sv_x0 = sv_x0; a.sv_h1 = sv_h1; a.sv_h3 = sv_h3; a.sv_h4 = sv_h4;
     const uint32_t ntiles = (N + ff::TILE_M - 1) / ff::TILE_M;
     uint32_t grid = ntiles < (uint32_t)n_sm ? ntiles : (uint32_t)n_sm;
     if (const char *g = getenv("CNC_FIELD_GRID")) { const uint32_t v = (uint32_t)atoi(g); if (v >= 1 && v < grid) grid = v; }  // profiling aid
     if (dirs) ff::field_fwd_kernel<false><<<grid, ff::NTHREADS, ff::SMEM_DYN, s>>>(a);
     else ff::field_fwd_kernel<true><<<grid, ff::NTHREADS, ff::SMEM_DYN, s>>>(a);
     return check_launch("field_fwd");
+}
+
+int cnc_field_fwd(const float *pos, const float *dirs, const float *aabb6_host, const uint8_t *bits_xyz,
+                  const uint8_t *bits_xy, const uint8_t *bits_xz, const uint8_t *bits_yz, const int32_t *offsets3,
+                  const int32_t *resolutions3, const int32_t *offsets2, const int32_t *resolutions2,
+                  const float *blob, float *sigma, float *rgb, float *geo, uint32_t N, cnc_stream_t stream) {
+    return field_fwd_impl(pos, dirs, aabb6_host, bits_xyz, bits_xy, bits_xz, bits_yz, offsets3, resolutions3, offsets2,
+                          resolutions2, blob, sigma, rgb, geo, nullptr, nullptr, nullptr, nullptr, N, stream);
+}
+
+int cnc_field_fwd_train(const float *pos, const float *dirs, const float *aabb6_host, const uint8_t *bits_xyz,
+                        const uint8_t *bits_xy, const uint8_t *bits_xz, const uint8_t *bits_yz, const int32_t *offsets3,
+                        const int32_t *resolutions3, const int32_t *offsets2, const int32_t *resolutions2,
+                        const float *blob, float *sigma, float *rgb, float *geo, float *x0, float *h1, float *h3, float *h4,
+                        uint32_t N, cnc_stream_t stream) {
+    if (!dirs || !geo || !x0 || !h1 || !h3 || !h4) { set_error("field_fwd_train: null pointer"); return CNC_EINVAL; }
+    if ((reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(h1) | reinterpret_cast<uintptr_t>(h3) |
+         reinterpret_cast<uintptr_t>(h4)) & 15u) { set_error("field_fwd_train: activation buffers must be 16-byte aligned"); return CNC_EINVAL; }
+    return field_fwd_impl(pos, dirs, aabb6_host, bits_xyz, bits_xy, bits_xz, bits_yz, offsets3, resolutions3, offsets2,
+                          resolutions2, blob, sigma, rgb, geo, x0, h1, h3, h4, N, stream);
 }
 
 }  // extern "C"

@@ -43,6 +43,76 @@ class _TruncExp(Function):
 trunc_exp = _TruncExp.apply
 
 
+class _FusedFieldTrain(Function):
+    """Differentiable ngp.py:514-566 for the product layout: the forward is ONE launch of the fused kernel
+    (`cnc_field_fwd_train`, which also leaves x0 / h1 / geo / h3 / h4 in HBM), the backward is the chain rule written
+    out: five weight-gradient GEMMs, four input-gradient GEMMs (fp32), the K2 scatter-add of the 192 grid-feature
+    columns into the four tables (grid_encode_backward) and the STE mask.  Positions and directions get no gradient
+    (the reference never asks for one: `dy_dx` is a dead path, gridencoder.cu:400-585)."""
+
+    @staticmethod
+    def forward(ctx, field, positions, directions, p_xyz, p_xy, p_xz, p_yz, W1, b1, W2, b2, W3, b3, W4, b4, W5, b5):
+        mb = field.mlp_base
+        encs = (mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz)
+        pos = positions.detach().reshape(-1, 3).contiguous().float()
+        dirs = directions.detach().reshape(-1, 3).contiguous().float()
+        n, dev = pos.shape[0], pos.device
+        bits = [e._sign_cache.get(e.params) for e in encs]
+        sigma = torch.empty(n, device=dev)
+        rgb = torch.empty(n, 3, device=dev)
+        geo = torch.empty(n, 79, device=dev)
+        x0 = torch.empty(n, 256, device=dev)
+        h1, h3, h4 = (torch.empty(n, 160, device=dev) for _ in range(3))
+        check(lib().cnc_field_fwd_train(ptr(pos), ptr(dirs), ctypes.addressof(field._aabb_c()), *[ptr(b) for b in bits],
+                                        ptr(mb.encoding_xyz.offsets_list), ptr(mb.encoding_xyz.resolutions_list),
+                                        ptr(mb.encoding_xy.offsets_list), ptr(mb.encoding_xy.resolutions_list),
+                                        ptr(field._fused_blob()), ptr(sigma), ptr(rgb), ptr(geo), ptr(x0), ptr(h1), ptr(h3),
+                                        ptr(h4), n, stream()))
+        ctx.field = field
+        ctx.save_for_backward(pos, dirs, sigma, rgb, geo, x0, h1, h3, h4, p_xyz, p_xy, p_xz, p_yz, W1, W2, W3, W4, W5)
+        shp = list(positions.shape[:-1])
+        return rgb.view(shp + [3]), sigma.view(shp + [1])
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_sigma):
+        from . import _gridencoder as G
+
+        pos, dirs, sigma, rgb, geo, x0, h1, h3, h4, p_xyz, p_xy, p_xz, p_yz, W1, W2, W3, W4, W5 = ctx.saved_tensors
+        field = ctx.field
+        n = pos.shape[0]
+        g_rgb = g_rgb.reshape(n, 3)
+        g_sigma = g_sigma.reshape(n, 1)
+        # head: sigmoid -> Linear(160,3) -> ReLU -> Linear(160,160) -> ReLU -> Linear(95,160)
+        dz5 = g_rgb * rgb * (1.0 - rgb)
+        gW5, gb5 = dz5.t() @ h4, dz5.sum(0)
+        dz4 = (dz5 @ W5) * (h4 > 0)
+        gW4, gb4 = dz4.t() @ h3, dz4.sum(0)
+        dz3 = (dz4 @ W4) * (h3 > 0)
+        head_in = torch.cat([sh16((dirs + 1.0) / 2.0), geo], dim=-1)          # ngp.py:540-542
+        gW3, gb3 = dz3.t() @ head_in, dz3.sum(0)
+        # base: [density pre-activation | geo] = Linear(160,80)(relu(Linear(255,160)(x0)))
+        dz2 = torch.cat([g_sigma * sigma.unsqueeze(-1), dz3 @ W3[:, 16:]], dim=-1)   # d trunc_exp(h-1)*selector / dh = density
+        gW2, gb2 = dz2.t() @ h1, dz2.sum(0)
+        dz1 = (dz2 @ W2) * (h1 > 0)
+        gW1, gb1 = (dz1.t() @ x0)[:, :255], dz1.sum(0)
+        dfeat = dz1 @ W1[:, :192]                                               # only the grid columns carry on
+        # grid features -> tables: K2 scatter-add + STE mask (ngp.py:121-165, :33-39)
+        mb = field.mlp_base
+        xn = field._normalise(pos)
+        grads, col = [], 0
+        for enc, prm, dims in ((mb.encoding_xyz, p_xyz, [0, 1, 2]), (mb.encoding_xy, p_xy, [0, 1]),
+                               (mb.encoding_xz, p_xz, [0, 2]), (mb.encoding_yz, p_yz, [1, 2])):
+            L, F = enc.n_levels, enc.n_features
+            g = dfeat[:, col:col + L * F].view(n, L, F).permute(1, 0, 2).contiguous()
+            col += L * F
+            ge = torch.zeros_like(prm)
+            G.grid_encode_backward(g, xn[:, dims].contiguous(), prm, enc.offsets_list, enc.resolutions_list, ge, n,
+                                   len(dims), F, L, 0, 128, None, None, None, None)
+            grads.append(G.ste_binary_backward(prm.contiguous(), ge))
+        return (None, None, None, *grads, gW1, gb1, gW2, gb2, gW3, gb3, gW4, gb4, gW5, gb5)
+
+
+
 def sh16(d01: torch.Tensor, fp16_round: bool = True) -> torch.Tensor:
     """tcnn SphericalHarmonics degree-4 replacement: d01 = (dir+1)/2 in [0,1] -> [N,16] (no grad)."""
     d = d01.detach().contiguous().float().view(-1, 3)
@@ -257,6 +327,20 @@ class NGPRadianceField_mygrid_2D3D(nn.Module):
         cur.wait_stream(s_out)
         return out_rgb, out_sigma
 
+    def _aabb_c(self):
+        if getattr(self, "_aabb_host", None) is None or self._aabb_src != (self.aabb.data_ptr(), self.aabb._version):
+            self._aabb_host = (ctypes.c_float * 6)(*self.aabb.detach().cpu().tolist())
+            self._aabb_src = (self.aabb.data_ptr(), self.aabb._version)
+        return self._aabb_host
+
+    def fused_train_forward(self, positions, directions):
+        """(rgb, density) with autograd through `_FusedFieldTrain` (fused kernel forward, explicit backward)"""
+        mb = self.mlp_base
+        lins = (mb.network[0], mb.network[2], self.mlp_head[0], self.mlp_head[2], self.mlp_head[4])
+        return _FusedFieldTrain.apply(self, positions, directions, mb.encoding_xyz.params, mb.encoding_xy.params,
+                                      mb.encoding_xz.params, mb.encoding_yz.params,
+                                      *[t for l in lins for t in (l.weight, l.bias)])
+
     def _use_fused(self):
         return (not torch.is_grad_enabled()) and getattr(self, "fused", True) and self.fused_available()
 
@@ -302,6 +386,9 @@ class NGPRadianceField_mygrid_2D3D(nn.Module):
             if self._use_fused():
                 rgb, density, _ = self.fused_forward(positions, directions)
                 return rgb, density
+            if torch.is_grad_enabled() and getattr(self, "fused_train", True) and getattr(self, "fused", True) \
+                    and self.fused_available():
+                return self.fused_train_forward(positions, directions)
             density, embedding = self.query_density(positions, return_feat=True)
             rgb = self._query_rgb(directions, embedding=embedding)
         return rgb, density  # type: ignore
