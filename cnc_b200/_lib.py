@@ -47,6 +47,7 @@ SIGNATURES = {
     "cnc_packed_scan": [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp],
     "cnc_render_from_density": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "cnc_context3d_probs": [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "cnc_wgrad": [_vp, _u32, _u32, _vp, _u32, _u32, _vp, _u32, _u32, _vp],
     "cnc_vertex_valid_bits": [_vp, _i32, _vp, _i32, _vp, _i64, _vp, _vp],
 }
 
@@ -69,6 +70,8 @@ def lib():
         L.cnc_version.restype = C.c_int
         L.cnc_field_blob_floats.restype = C.c_uint32
         L.cnc_context3d_mlp_floats.restype = C.c_uint32
+        L.cnc_wgrad_max_partials.restype = C.c_int
+        L.cnc_wgrad_max_partials.argtypes = []
         _lib = L
     return _lib
 

@@ -1,0 +1,213 @@
+// mlp_grad.cu -- weight gradients of the field MLPs on the tensor cores, fp32-equivalent (3xTF32).
+//
+// Reference behaviour restated: the backward of the five nn.Linear layers of examples/radiance_fields/ngp.py:428-505
+// (torch autograd: dW = dY^T X, an fp32 cuBLAS GEMM whose contraction runs over the N_s samples of the batch).
+//
+//   C[i, o] = sum_s X[s, i] * Z[s, o]          X = layer input [N_s, ldx] (first Mi columns), Z = dL/d(layer output)
+//
+// Both operands live in HBM sample-major, i.e. the contraction index is the slow one: exactly the "MN-major" operand
+// form of tcgen05 (shared-memory atoms of 4 samples x 32 features, 128-byte rows swizzled in 32-byte units), so no transpose pass exists
+// anywhere.  One persistent CTA per SM walks slabs of 32 samples: eight warps stage the slab (coalesced 16-byte loads,
+// error-compensated hi/lo split, swizzled st.shared) into a two-stage ring while one warp issues
+// D += Xhi^T Zhi + Xhi^T Zlo + Xlo^T Zhi (kind::tf32, M = 128 per block of input features, N = padded output width,
+// K = 8 samples) into TMEM.  Every CTA writes its partial [Mi, No] tile; the caller sums the <= 148 partials (fixed
+// order -> deterministic gradients, unlike an atomic reduction).  The kernel is HBM-bound by design: 4 (Mi + No)
+// bytes per sample against 6 Mi No tensor FLOPs.
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace cnc {
+namespace mg {
+
+using namespace tc;
+
+constexpr int KS = 32;                 // samples per slab (4 k-steps of 8)
+constexpr int NSTAGE = 2;
+constexpr int MAX_MI = 256, MAX_NO = 160;
+constexpr uint32_t X_HALF = KS * MAX_MI * 4;     // 32 KB: hi (or lo) of a slab of X, [k-step][atom][1 KB]
+constexpr uint32_t Z_HALF = KS * MAX_NO * 4;     // 20 KB
+constexpr uint32_t STAGE_BYTES = 2 * X_HALF + 2 * Z_HALF;   // 104 KB
+constexpr uint32_t SMEM_BAR = NSTAGE * STAGE_BYTES;
+constexpr uint32_t SMEM_DYN = SMEM_BAR + 64;
+constexpr int NSTAGER = 256;           // staging threads (8 warps); warp 8 issues the MMAs
+constexpr int NTHREADS = NSTAGER + 32;
+
+struct Args {
+    const float *X;
+    const float *Z;
+    float *P;          // [gridDim.x, Mi, No] partial sums
+    uint32_t ldx, ldz, Mi, No, Ns;
+};
+
+__device__ __forceinline__ void split3(float v, uint32_t &hi, uint32_t &lo) {
+    hi = rna_tf32(v);
+    lo = __float_as_uint(__fsub_rn(v, __uint_as_float(hi)));   // the MMA reads its top 19 bits: 2^-23 |v|
+}
+
+// byte offset of the float4 m4 (= feature / 4) of sample row kr (0..7) inside a k-step tile: consecutive 1 KB blocks of
+// 32 features, each two 4-row atoms of the SW128_32B layout (tc05.cuh)
+__device__ __forceinline__ uint32_t mn_off(uint32_t kr, uint32_t m4) {
+    return (m4 >> 3) * 1024u + kr * 128u + ((((m4 >> 1) & 3u) ^ (kr & 3u)) << 5) + ((m4 & 1u) << 4);
+}
+
+template <int NO_PAD>   // 96 or 160: MMA N
+__global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const Args a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5;
+    const uint32_t natx = (a.Mi + 31u) / 32u, nblk = (a.Mi + 127u) / 128u;   // atoms along the X features; M blocks
+    const uint32_t natx_pad = nblk * 4u;
+    constexpr uint32_t natz = (NO_PAD + 31) / 32;
+    const uint32_t xstep = natx_pad * 1024u, zstep = natz * 1024u;            // bytes per k-step tile
+    auto full = [&](uint32_t s) { return sbase + SMEM_BAR + 8u * s; };
+    auto empty = [&](uint32_t s) { return sbase + SMEM_BAR + 16u + 8u * s; };
+    const uint32_t done = sbase + SMEM_BAR + 32u;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < NSTAGE; s++) { mbar_init(full(s), NSTAGER / 32); mbar_init(empty(s), 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // padding atoms / columns are never written by the staging loop: clear both stages once
+    for (uint32_t i = threadIdx.x; i < NSTAGE * STAGE_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_base_s;
+
+    const uint32_t nslab = (a.Ns + KS - 1) / KS;
+    const uint32_t my = blockIdx.x < nslab ? (nslab - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+
+    if (warp < 8) {
+        // =============================== staging ===============================
+        const uint32_t x4 = a.Mi / 4u, z4 = a.No / 4u;            // float4 per row
+        const uint32_t nx = KS * x4, nz = KS * z4;
+        for (uint32_t it = 0; it < my; it++) {
+            const uint32_t slab = blockIdx.x + it * gridDim.x, s = it % NSTAGE, use = it / NSTAGE;
+            if (use > 0) mbar_wait(empty(s), (use - 1) & 1u);
+            uint8_t *st = smem + s * STAGE_BYTES;
+            const uint32_t row0 = slab * KS;
+            for (uint32_t i = threadIdx.x; i < nx; i += NSTAGER) {
+                const uint32_t r = i / x4, c4 = i - r * x4, row = row0 + r;
+                const float4 v = row < a.Ns ? __ldg(reinterpret_cast<const float4 *>(a.X + (size_t)row * a.ldx) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                uint4 hi, lo;
+                split3(v.x, hi.x, lo.x); split3(v.y, hi.y, lo.y); split3(v.z, hi.z, lo.z); split3(v.w, hi.w, lo.w);
+                const uint32_t off = (r >> 3) * xstep + mn_off(r & 7u, c4);
+                *reinterpret_cast<uint4 *>(st + off) = hi;
+                *reinterpret_cast<uint4 *>(st + X_HALF + off) = lo;
+            }
+            for (uint32_t i = threadIdx.x; i < nz; i += NSTAGER) {
+                const uint32_t r = i / z4, c4 = i - r * z4, row = row0 + r;
+                const float4 v = row < a.Ns ? __ldg(reinterpret_cast<const float4 *>(a.Z + (size_t)row * a.ldz) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                uint4 hi, lo;
+                split3(v.x, hi.x, lo.x); split3(v.y, hi.y, lo.y); split3(v.z, hi.z, lo.z); split3(v.w, hi.w, lo.w);
+                const uint32_t off = (r >> 3) * zstep + mn_off(r & 7u, c4);
+                *reinterpret_cast<uint4 *>(st + 2 * X_HALF + off) = hi;
+                *reinterpret_cast<uint4 *>(st + 2 * X_HALF + Z_HALF + off) = lo;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(full(s));
+        }
+        // =============================== epilogue: TMEM -> partial tile ===============================
+        if (warp < 4) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+            float *P = a.P + (size_t)blockIdx.x * a.Mi * a.No;
+            for (uint32_t blk = 0; blk < nblk; blk++) {
+                const uint32_t m = blk * 128u + (uint32_t)warp * 32u + (threadIdx.x & 31u);
+                const uint32_t tl = tbase + ((uint32_t)(warp * 32) << 16) + blk * (uint32_t)NO_PAD;
+                for (uint32_t c = 0; c < (uint32_t)NO_PAD; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(tl + c, v);
+                    tc_wait_ld();
+                    if (m < a.Mi) {
+#pragma unroll
+                        for (int k = 0; k < 16; k += 4)
+                            if (c + k < a.No)
+                                *reinterpret_cast<float4 *>(P + (size_t)m * a.No + c + k) =
+                                    make_float4(my ? __uint_as_float(v[k]) : 0.f, my ? __uint_as_float(v[k + 1]) : 0.f,
+                                                my ? __uint_as_float(v[k + 2]) : 0.f, my ? __uint_as_float(v[k + 3]) : 0.f);
+                    }
+                }
+            }
+        }
+    } else {
+        // =============================== MMA issue ===============================
+        constexpr uint32_t id = idesc_tf32_mn<NO_PAD>();
+        for (uint32_t it = 0; it < my; it++) {
+            const uint32_t s = it % NSTAGE;
+            mbar_wait_spin(full(s), (it / NSTAGE) & 1u);
+            tc_fence_after();
+            const uint32_t st = sbase + s * STAGE_BYTES;
+#pragma unroll 1
+            for (uint32_t ks = 0; ks < KS / 8; ks++) {
+                const uint64_t zh = smem_desc_mn(st + 2 * X_HALF + ks * zstep, 1024u, 512u),
+                               zl = smem_desc_mn(st + 2 * X_HALF + Z_HALF + ks * zstep, 1024u, 512u);
+                for (uint32_t blk = 0; blk < nblk; blk++) {
+                    const uint64_t xh = smem_desc_mn(st + ks * xstep + blk * 4096u, 1024u, 512u),
+                                   xl = smem_desc_mn(st + X_HALF + ks * xstep + blk * 4096u, 1024u, 512u);
+                    const uint32_t d = tbase + blk * (uint32_t)NO_PAD;
+                    mma_ss(d, xh, zl, id, (it == 0 && ks == 0) ? 0u : 1u);   // the two small products first
+                    mma_ss(d, xl, zh, id, 1u);
+                    mma_ss(d, xh, zh, id, 1u);
+                }
+            }
+            tc_commit_elect(empty(s));
+        }
+        tc_commit_elect(done);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512u) : "memory");
+}
+
+}  // namespace mg
+}  // namespace cnc
+
+using namespace cnc;
+
+extern "C" {
+
+int cnc_wgrad_max_partials(void) {
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    return n_sm;
+}
+
+int cnc_wgrad(const float *X, uint32_t ldx, uint32_t Mi, const float *Z, uint32_t ldz, uint32_t No, float *partials,
+              uint32_t n_partials, uint32_t Ns, cnc_stream_t stream) {
+    if (!X || !Z || !partials) { set_error("wgrad: null pointer"); return CNC_EINVAL; }
+    if (Mi == 0 || Mi > mg::MAX_MI || (Mi & 31u) || No == 0 || No > mg::MAX_NO || (No & 15u) || (ldx & 3u) || (ldz & 3u) ||
+        ldx < Mi || ldz < No || n_partials == 0) {
+        set_error("wgrad: unsupported shape (Mi multiple of 32 <= 256, No multiple of 16 <= 160, leading dimensions multiples of 4)");
+        return CNC_ENOTSUP;
+    }
+    if ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(partials)) & 15u) {
+        set_error("wgrad: pointers must be 16-byte aligned");
+        return CNC_EINVAL;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e1 = cudaFuncSetAttribute(mg::wgrad_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg::SMEM_DYN);
+        cudaError_t e2 = cudaFuncSetAttribute(mg::wgrad_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg::SMEM_DYN);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("wgrad: cannot reserve %u bytes of shared memory", mg::SMEM_DYN); return CNC_ECUDA; }
+        attr_set = true;
+    }
+    mg::Args a{X, Z, partials, ldx, ldz, Mi, No, Ns};
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (No <= 96) mg::wgrad_kernel<96><<<n_partials, mg::NTHREADS, mg::SMEM_DYN, s>>>(a);
+    else mg::wgrad_kernel<160><<<n_partials, mg::NTHREADS, mg::SMEM_DYN, s>>>(a);
+    return check_launch("wgrad");
+}
+
+}  // extern "C"

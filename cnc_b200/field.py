@@ -43,6 +43,20 @@ class _TruncExp(Function):
 trunc_exp = _TruncExp.apply
 
 
+def wgrad(x: torch.Tensor, z: torch.Tensor, mi: int = None, no: int = None) -> torch.Tensor:
+    """x[:, :mi]^T @ z[:, :no] -> [mi, no] over the rows (samples) on the tensor cores, fp32-equivalent
+    (`cnc_wgrad`, csrc/mlp_grad.cu).  x and z are row-major fp32; mi a multiple of 32, no a multiple of 16."""
+    assert x.dim() == 2 and z.dim() == 2 and x.shape[0] == z.shape[0]
+    x, z = x.contiguous(), z.contiguous()
+    mi = x.shape[1] if mi is None else mi
+    no = z.shape[1] if no is None else no
+    ns = x.shape[0]
+    g = max(1, min(lib().cnc_wgrad_max_partials(), (ns + 31) // 32))
+    part = torch.empty(g, mi, no, device=x.device, dtype=torch.float32)
+    check(lib().cnc_wgrad(ptr(x), x.shape[1], mi, ptr(z), z.shape[1], no, ptr(part), g, ns, stream()))
+    return part.sum(0)
+
+
 class _FusedFieldTrain(Function):
     """Differentiable ngp.py:514-566 for the product layout: the forward is ONE launch of the fused kernel
     (`cnc_field_fwd_train`, which also leaves x0 / h1 / geo / h3 / h4 in HBM), the backward is the chain rule written
@@ -83,18 +97,20 @@ class _FusedFieldTrain(Function):
         g_rgb = g_rgb.reshape(n, 3)
         g_sigma = g_sigma.reshape(n, 1)
         # head: sigmoid -> Linear(160,3) -> ReLU -> Linear(160,160) -> ReLU -> Linear(95,160)
+        # (weight gradients: cnc_wgrad, contraction over the samples on the tensor cores; the 3-wide last layer and
+        #  the input gradients stay fp32 matmuls)
         dz5 = g_rgb * rgb * (1.0 - rgb)
         gW5, gb5 = dz5.t() @ h4, dz5.sum(0)
         dz4 = (dz5 @ W5) * (h4 > 0)
-        gW4, gb4 = dz4.t() @ h3, dz4.sum(0)
+        gW4, gb4 = wgrad(h3, dz4).t(), dz4.sum(0)
         dz3 = (dz4 @ W4) * (h3 > 0)
-        head_in = torch.cat([sh16((dirs + 1.0) / 2.0), geo], dim=-1)          # ngp.py:540-542
-        gW3, gb3 = dz3.t() @ head_in, dz3.sum(0)
+        head_in = torch.cat([sh16((dirs + 1.0) / 2.0), geo, geo.new_zeros(n, 1)], dim=-1)   # ngp.py:540-542 (+ pad to 96)
+        gW3, gb3 = wgrad(head_in, dz3).t()[:, :95], dz3.sum(0)
         # base: [density pre-activation | geo] = Linear(160,80)(relu(Linear(255,160)(x0)))
         dz2 = torch.cat([g_sigma * sigma.unsqueeze(-1), dz3 @ W3[:, 16:]], dim=-1)   # d trunc_exp(h-1)*selector / dh = density
-        gW2, gb2 = dz2.t() @ h1, dz2.sum(0)
+        gW2, gb2 = wgrad(h1, dz2).t(), dz2.sum(0)
         dz1 = (dz2 @ W2) * (h1 > 0)
-        gW1, gb1 = (dz1.t() @ x0)[:, :255], dz1.sum(0)
+        gW1, gb1 = wgrad(x0, dz1).t()[:, :255], dz1.sum(0)
         dfeat = dz1 @ W1[:, :192]                                               # only the grid columns carry on
         # grid features -> tables: K2 scatter-add + STE mask (ngp.py:121-165, :33-39)
         mb = field.mlp_base

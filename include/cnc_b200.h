@@ -182,6 +182,18 @@ int cnc_field_fwd_train(const float *pos, const float *dirs, const float *aabb6_
                         uint32_t N, cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Weight gradients of the field MLPs (backward of the nn.Linear layers of ngp.py:428-505; the reference leaves it to
+ * torch autograd = an fp32 cuBLAS GEMM):  C[i, o] = sum_s X[s, i] * Z[s, o],  X = layer input [Ns, ldx] (first Mi
+ * columns, Mi a multiple of 32, <= 256), Z = gradient of the layer output [Ns, ldz] (first No columns, No a multiple
+ * of 16, <= 160), fp32 row-major, 16-byte aligned.  3xTF32 tcgen05 MMAs with fp32 accumulation (fp32-equivalent).
+ * The kernel writes n_partials partial sums [n_partials, Mi, No] (one per CTA, n_partials <= cnc_wgrad_max_partials());
+ * the caller adds them up in index order, which makes the result deterministic.
+ * ---------------------------------------------------------------------------------------- */
+int cnc_wgrad_max_partials(void);
+int cnc_wgrad(const float *X, uint32_t ldx, uint32_t Mi, const float *Z, uint32_t ldz, uint32_t No,
+              float *partials, uint32_t n_partials, uint32_t Ns, cnc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Level-wise context model of the 3D grid, fused (one kernel per coded chunk).
  * replaces the chunk body of encode_/decode_binary_vxl_mixPg_3D2D, examples/utils_bpp_acc.py:798-852
  *   == :929-968: query_mask_3D -> compaction -> align_and_pack -> Encoding_xyz(points, n-3, n,

@@ -181,3 +181,24 @@ def test_fused_training_path_matches_unfused_autograd(cuda, n):
         assert float((a - b).norm()) <= 2e-3 * float(b.norm()), (k, float((a - b).norm()), float(b.norm()))
         if "encoding" in k:   # the same rows are touched
             assert float(((a != 0) ^ (b != 0)).float().mean()) < 1e-4, k
+
+
+@pytest.mark.parametrize("ns,mi,no", [(1, 32, 16), (31, 96, 160), (1000, 256, 160), (4097, 160, 80), (50000, 160, 160), (300000, 256, 160)])
+def test_wgrad_matches_fp64(cuda, ns, mi, no):
+    """cnc_wgrad (3xTF32 tcgen05, MN-major operands straight from the sample-major activations) against an fp64
+    matmul: fp32-equivalent (the error of an fp32 GEMM with this contraction length), leading dimensions honoured."""
+    from cnc_b200.field import wgrad
+
+    g = torch.Generator(device="cpu").manual_seed(ns + mi)
+    x = torch.randn(ns, mi + 32, generator=g).to(cuda) * torch.rand(1, mi + 32, generator=g).to(cuda) * 3
+    z = torch.randn(ns, no + 16, generator=g).to(cuda) * 0.1
+    x[:, 0] = 1.0      # a constant column: same-sign sums show any accumulation bias
+    z[:, 0] = 0.25
+    got = wgrad(x, z, mi, no)
+    want = x[:, :mi].double().t() @ z[:, :no].double()
+    ref32 = x[:, :mi].t() @ z[:, :no]
+    scale = (x[:, :mi].double().abs().t() @ z[:, :no].double().abs())       # sum of |terms|: the fp32 error scale
+    err = ((got.double() - want).abs() / scale).max().item()
+    err32 = ((ref32.double() - want).abs() / scale).max().item()
+    assert got.shape == (mi, no)
+    assert err <= max(4 * err32, 2e-6), (err, err32)
