@@ -436,7 +436,7 @@ def main():
     s_k = ms_k / a.steps * 1e-3
     if a.impl == "ours":
         ach = Ns * FLOP_PER_SAMPLE_FWD / s_k / 1e12
-        roof = {"bound": "tensor", "kernel": "cnc::ff::field_fwd_kernel<false> (encode + 5 FC layers, 3xTF32 tcgen05)",
+        roof = {"bound": "tensor", "kernel": "cnc::ff::field_fwd_kernel<false,false> (encode + 5 FC layers, error-compensated tf32 tcgen05)",
                 "achieved": ach, "peak": tf_peak, "peak_source": which + " (dense bf16 cuBLAS burst)", "unit": "TFLOP/s",
                 "frac": ach / tf_peak, "traffic": ncu_traffic("field_fwd_kernel", Ns),
                 "algorithmic_flops_per_launch": Ns * FLOP_PER_SAMPLE_FWD, "ms_per_launch": ms_k / a.steps,

@@ -135,7 +135,7 @@ struct FieldArgs {
     float *rgb;    // [N,3]   (nullptr in density-only mode)
     float *geo;    // [N,79]  nullable
     // training forward (all nullable, together): what the backward pass needs, written as the values go by
-    float *sv_x0;  // [N,256] layer-1 input (192 grid features | x, sin/cos 63 | 0)
+    float *sv_x0;  // [N,256] layer-1 input (192 grid features | x, sin/cos 63 | 1)
     float *sv_h1;  // [N,160] relu(L1)
     float *sv_h3;  // [N,160] relu(L3)
     float *sv_h4;  // [N,160] relu(L4)
@@ -330,7 +330,7 @@ __device__ __forceinline__ void ep_hidden(uint32_t tl, int cg, uint32_t c_main, 
 constexpr int NCOMPUTE = 512;              // 16 gather/epilogue warps
 constexpr int NTHREADS = NCOMPUTE + 64;    // + the MMA warp + the weight-stream (bulk copy) warp
 
-template <bool DENSITY_ONLY>
+template <bool DENSITY_ONLY, bool SAVE>
 __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -531,10 +531,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             }
         };
         auto publish = [&](int c, uint32_t prow, const float (&f)[8]) {  // 8 feature values -> smem slot -> MMA warp
-            if (a.sv_x0 != nullptr && prow < a.N) {
+            if (SAVE && prow < a.N) {   // column 255 (K padding, weight 0) is saved as 1: its weight-gradient row is the bias gradient
                 float *d = a.sv_x0 + (size_t)prow * 256 + 32 * c + 8 * q;
                 *reinterpret_cast<float4 *>(d) = make_float4(f[0], f[1], f[2], f[3]);
-                *reinterpret_cast<float4 *>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                *reinterpret_cast<float4 *>(d + 4) = make_float4(f[4], f[5], f[6], (c == 7 && q == 3) ? 1.0f : f[7]);
             }
             const uint32_t sl = a_prod & 1u, use = a_prod >> 1;
             if (use > 0) mbar_wait(a_empty(sl), (use - 1) & 1u);
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             mbar_wait(layer_done, done_cnt & 1u); done_cnt++;
             tc_fence_after();
             if (threadIdx.x == 0) CNC_TL(10);
-            ep_hidden<160u, 320u>(tl, q, 0u, 0u, 160u, bias + BIAS1, (a.sv_h1 != nullptr && live) ? a.sv_h1 + (size_t)row * 160 : nullptr);
+            ep_hidden<160u, 320u>(tl, q, 0u, 0u, 160u, bias + BIAS1, (SAVE && live) ? a.sv_h1 + (size_t)row * 160 : nullptr);
             tc_fence_before();
             mbar_arrive(act_ready);
             if (threadIdx.x == 0) CNC_TL(11);
@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                 mbar_wait(layer_done, done_cnt & 1u); done_cnt++;
                 tc_fence_after();
                 if (threadIdx.x == 0) CNC_TL(14);
-                ep_hidden<NONE, 352u>(tl, q, 192u, 192u, 352u, bias + BIAS3, (a.sv_h3 != nullptr && live) ? a.sv_h3 + (size_t)row * 160 : nullptr);
+                ep_hidden<NONE, 352u>(tl, q, 192u, 192u, 352u, bias + BIAS3, (SAVE && live) ? a.sv_h3 + (size_t)row * 160 : nullptr);
                 tc_fence_before();
                 mbar_arrive(act_ready);
                 if (threadIdx.x == 0) CNC_TL(15);
@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                         p1 = __fmaf_rn(h, W1[k], p1);
                         p2 = __fmaf_rn(h, W2[k], p2);
                     }
-                    if (a.sv_h4 != nullptr && live) {
+                    if (SAVE && live) {
                         float *d = a.sv_h4 + (size_t)row * 160 + 8 * b;
                         *reinterpret_cast<float4 *>(d) = make_float4(v[0], v[1], v[2], v[3]);
                         *reinterpret_cast<float4 *>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -798,8 +798,10 @@ static int field_fwd_impl(const float *pos, const float *dirs, const float *aabb
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        cudaError_t e1 = cudaFuncSetAttribute(ff::field_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::SMEM_DYN);
-        cudaError_t e2 = cudaFuncSetAttribute(ff::field_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::SMEM_DYN);
+        cudaError_t e1 = cudaFuncSetAttribute(ff::field_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::SMEM_DYN);
+        cudaError_t e2 = cudaFuncSetAttribute(ff::field_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::SMEM_DYN);
+        cudaError_t e3 = cudaFuncSetAttribute(ff::field_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::SMEM_DYN);
+        if (e1 == cudaSuccess) e1 = e3;
         if (e1 != cudaSuccess || e2 != cudaSuccess) {
             set_error("field_fwd: cannot reserve %u bytes of shared memory (%s)", ff::SMEM_DYN,
                       cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -817,8 +819,9 @@ static int field_fwd_impl(const float *pos, const float *dirs, const float *aabb
     const uint32_t ntiles = (N + ff::TILE_M - 1) / ff::TILE_M;
     uint32_t grid = ntiles < (uint32_t)n_sm ? ntiles : (uint32_t)n_sm;
     if (const char *g = getenv("CNC_FIELD_GRID")) { const uint32_t v = (uint32_t)atoi(g); if (v >= 1 && v < grid) grid = v; }  // profiling aid
-    if (dirs) ff::field_fwd_kernel<false><<<grid, ff::NTHREADS, ff::SMEM_DYN, s>>>(a);
-    else ff::field_fwd_kernel<true><<<grid, ff::NTHREADS, ff::SMEM_DYN, s>>>(a);
+    if (sv_x0) ff::field_fwd_kernel<false, true><<<grid, ff::NTHREADS, ff::SMEM_DYN, s>>>(a);
+    else if (dirs) ff::field_fwd_kernel<false, false><<<grid, ff::NTHREADS, ff::SMEM_DYN, s>>>(a);
+    else ff::field_fwd_kernel<true, false><<<grid, ff::NTHREADS, ff::SMEM_DYN, s>>>(a);
     return check_launch("field_fwd");
 }
 

@@ -52,16 +52,19 @@ __device__ __forceinline__ uint32_t mn_off(uint32_t kr, uint32_t m4) {
     return (m4 >> 3) * 1024u + kr * 128u + ((((m4 >> 1) & 3u) ^ (kr & 3u)) << 5) + ((m4 & 1u) << 4);
 }
 
-template <int NO_PAD>   // 96 or 160: MMA N
+// MI: X columns (multiple of 32), NO: Z columns (multiple of 16); ONES: row MI of the result = column sums of Z
+// (a virtual all-ones X column, synthesised in shared memory: the bias gradient for free)
+template <int MI, int NO, bool ONES>
 __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const Args a) {
+    constexpr int NO_PAD = NO <= 96 ? 96 : 160;   // MMA N
+    constexpr uint32_t MI_EFF = MI + (ONES ? 1 : 0);
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t tmem_base_s;
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5;
-    const uint32_t natx = (a.Mi + 31u) / 32u, nblk = (a.Mi + 127u) / 128u;   // atoms along the X features; M blocks
-    const uint32_t natx_pad = nblk * 4u;
-    constexpr uint32_t natz = (NO_PAD + 31) / 32;
-    const uint32_t xstep = natx_pad * 1024u, zstep = natz * 1024u;            // bytes per k-step tile
+    constexpr uint32_t nblk = (MI_EFF + 127u) / 128u;                        // M blocks of 128 input features
+    constexpr uint32_t natx_pad = nblk * 4u, natz = (NO_PAD + 31) / 32;
+    constexpr uint32_t xstep = natx_pad * 1024u, zstep = natz * 1024u;       // bytes per k-step tile
     auto full = [&](uint32_t s) { return sbase + SMEM_BAR + 8u * s; };
     auto empty = [&](uint32_t s) { return sbase + SMEM_BAR + 16u + 8u * s; };
     const uint32_t done = sbase + SMEM_BAR + 32u;
@@ -88,30 +91,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const Args a) {
 
     if (warp < 8) {
         // =============================== staging ===============================
-        const uint32_t x4 = a.Mi / 4u, z4 = a.No / 4u;            // float4 per row
-        const uint32_t nx = KS * x4, nz = KS * z4;
+        constexpr uint32_t x4 = MI / 4, z4 = NO / 4;               // float4 per row
+        constexpr uint32_t nx = KS * x4, nz = KS * z4;
+        constexpr int JX = (nx + NSTAGER - 1) / NSTAGER, JZ = (nz + NSTAGER - 1) / NSTAGER;
         for (uint32_t it = 0; it < my; it++) {
             const uint32_t slab = blockIdx.x + it * gridDim.x, s = it % NSTAGE, use = it / NSTAGE;
+            const uint32_t row0 = slab * KS;
+            // all loads of the slab first (they do not depend on the ring), then wait for the stage
+            float4 vx[JX], vz[JZ];
+#pragma unroll
+            for (int j = 0; j < JX; j++) {
+                const uint32_t i = threadIdx.x + j * NSTAGER, r = i / x4, c4 = i % x4, row = row0 + r;
+                vx[j] = (i < nx && row < a.Ns) ? __ldg(reinterpret_cast<const float4 *>(a.X + (size_t)row * a.ldx) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < JZ; j++) {
+                const uint32_t i = threadIdx.x + j * NSTAGER, r = i / z4, c4 = i % z4, row = row0 + r;
+                vz[j] = (i < nz && row < a.Ns) ? __ldg(reinterpret_cast<const float4 *>(a.Z + (size_t)row * a.ldz) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             if (use > 0) mbar_wait(empty(s), (use - 1) & 1u);
             uint8_t *st = smem + s * STAGE_BYTES;
-            const uint32_t row0 = slab * KS;
-            for (uint32_t i = threadIdx.x; i < nx; i += NSTAGER) {
-                const uint32_t r = i / x4, c4 = i - r * x4, row = row0 + r;
-                const float4 v = row < a.Ns ? __ldg(reinterpret_cast<const float4 *>(a.X + (size_t)row * a.ldx) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                uint4 hi, lo;
-                split3(v.x, hi.x, lo.x); split3(v.y, hi.y, lo.y); split3(v.z, hi.z, lo.z); split3(v.w, hi.w, lo.w);
-                const uint32_t off = (r >> 3) * xstep + mn_off(r & 7u, c4);
-                *reinterpret_cast<uint4 *>(st + off) = hi;
-                *reinterpret_cast<uint4 *>(st + X_HALF + off) = lo;
+#pragma unroll
+            for (int j = 0; j < JX; j++) {
+                const uint32_t i = threadIdx.x + j * NSTAGER, r = i / x4, c4 = i % x4;
+                if (i < nx) {
+                    uint4 hi, lo;
+                    split3(vx[j].x, hi.x, lo.x); split3(vx[j].y, hi.y, lo.y); split3(vx[j].z, hi.z, lo.z); split3(vx[j].w, hi.w, lo.w);
+                    const uint32_t off = (r >> 3) * xstep + mn_off(r & 7u, c4);
+                    *reinterpret_cast<uint4 *>(st + off) = hi;
+                    *reinterpret_cast<uint4 *>(st + X_HALF + off) = lo;
+                }
             }
-            for (uint32_t i = threadIdx.x; i < nz; i += NSTAGER) {
-                const uint32_t r = i / z4, c4 = i - r * z4, row = row0 + r;
-                const float4 v = row < a.Ns ? __ldg(reinterpret_cast<const float4 *>(a.Z + (size_t)row * a.ldz) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                uint4 hi, lo;
-                split3(v.x, hi.x, lo.x); split3(v.y, hi.y, lo.y); split3(v.z, hi.z, lo.z); split3(v.w, hi.w, lo.w);
-                const uint32_t off = (r >> 3) * zstep + mn_off(r & 7u, c4);
-                *reinterpret_cast<uint4 *>(st + 2 * X_HALF + off) = hi;
-                *reinterpret_cast<uint4 *>(st + 2 * X_HALF + Z_HALF + off) = lo;
+#pragma unroll
+            for (int j = 0; j < JZ; j++) {
+                const uint32_t i = threadIdx.x + j * NSTAGER, r = i / z4, c4 = i % z4;
+                if (i < nz) {
+                    uint4 hi, lo;
+                    split3(vz[j].x, hi.x, lo.x); split3(vz[j].y, hi.y, lo.y); split3(vz[j].z, hi.z, lo.z); split3(vz[j].w, hi.w, lo.w);
+                    const uint32_t off = (r >> 3) * zstep + mn_off(r & 7u, c4);
+                    *reinterpret_cast<uint4 *>(st + 2 * X_HALF + off) = hi;
+                    *reinterpret_cast<uint4 *>(st + 2 * X_HALF + Z_HALF + off) = lo;
+                }
+            }
+            if (ONES && threadIdx.x < KS) {   // the virtual X column MI: 1 for live samples
+                const uint32_t r = threadIdx.x;
+                const uint32_t off = (r >> 3) * xstep + mn_off(r & 7u, MI / 4);
+                *reinterpret_cast<uint32_t *>(st + off) = (row0 + r < a.Ns) ? 0x3F800000u : 0u;
             }
             fence_async_smem();
             __syncwarp();
@@ -121,7 +146,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const Args a) {
         if (warp < 4) {
             mbar_wait(done, 0);
             tc_fence_after();
-            float *P = a.P + (size_t)blockIdx.x * a.Mi * a.No;
+            float *P = a.P + (size_t)blockIdx.x * MI_EFF * NO;
             for (uint32_t blk = 0; blk < nblk; blk++) {
                 const uint32_t m = blk * 128u + (uint32_t)warp * 32u + (threadIdx.x & 31u);
                 const uint32_t tl = tbase + ((uint32_t)(warp * 32) << 16) + blk * (uint32_t)NO_PAD;
@@ -129,11 +154,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const Args a) {
                     uint32_t v[16];
                     tmem_ld16(tl + c, v);
                     tc_wait_ld();
-                    if (m < a.Mi) {
+                    if (m < MI_EFF) {
 #pragma unroll
                         for (int k = 0; k < 16; k += 4)
-                            if (c + k < a.No)
-                                *reinterpret_cast<float4 *>(P + (size_t)m * a.No + c + k) =
+                            if (c + k < (uint32_t)NO)
+                                *reinterpret_cast<float4 *>(P + (size_t)m * NO + c + k) =
                                     make_float4(my ? __uint_as_float(v[k]) : 0.f, my ? __uint_as_float(v[k + 1]) : 0.f,
                                                 my ? __uint_as_float(v[k + 2]) : 0.f, my ? __uint_as_float(v[k + 3]) : 0.f);
                     }
@@ -175,6 +200,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const Args a) {
 
 using namespace cnc;
 
+template <int MI, int NO, bool ONES>
+static int launch_wgrad(const mg::Args &a, uint32_t n_partials, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(mg::wgrad_kernel<MI, NO, ONES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg::SMEM_DYN) != cudaSuccess) {
+            set_error("wgrad: cannot reserve %u bytes of shared memory", mg::SMEM_DYN);
+            return CNC_ECUDA;
+        }
+        attr_set = true;
+    }
+    mg::wgrad_kernel<MI, NO, ONES><<<n_partials, mg::NTHREADS, mg::SMEM_DYN, s>>>(a);
+    return check_launch("wgrad");
+}
+
 extern "C" {
 
 int cnc_wgrad_max_partials(void) {
@@ -184,30 +223,27 @@ int cnc_wgrad_max_partials(void) {
     return n_sm;
 }
 
-int cnc_wgrad(const float *X, uint32_t ldx, uint32_t Mi, const float *Z, uint32_t ldz, uint32_t No, float *partials,
-              uint32_t n_partials, uint32_t Ns, cnc_stream_t stream) {
+int cnc_wgrad(const float *X, uint32_t ldx, uint32_t Mi, const float *Z, uint32_t ldz, uint32_t No, int with_ones,
+              float *partials, uint32_t n_partials, uint32_t Ns, cnc_stream_t stream) {
     if (!X || !Z || !partials) { set_error("wgrad: null pointer"); return CNC_EINVAL; }
-    if (Mi == 0 || Mi > mg::MAX_MI || (Mi & 31u) || No == 0 || No > mg::MAX_NO || (No & 15u) || (ldx & 3u) || (ldz & 3u) ||
-        ldx < Mi || ldz < No || n_partials == 0) {
-        set_error("wgrad: unsupported shape (Mi multiple of 32 <= 256, No multiple of 16 <= 160, leading dimensions multiples of 4)");
-        return CNC_ENOTSUP;
+    if ((ldx & 3u) || (ldz & 3u) || ldx < Mi || ldz < No || n_partials == 0) {
+        set_error("wgrad: leading dimensions must be multiples of 4 and cover the columns used");
+        return CNC_EINVAL;
     }
     if ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(partials)) & 15u) {
         set_error("wgrad: pointers must be 16-byte aligned");
         return CNC_EINVAL;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e1 = cudaFuncSetAttribute(mg::wgrad_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg::SMEM_DYN);
-        cudaError_t e2 = cudaFuncSetAttribute(mg::wgrad_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg::SMEM_DYN);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("wgrad: cannot reserve %u bytes of shared memory", mg::SMEM_DYN); return CNC_ECUDA; }
-        attr_set = true;
-    }
+    if (with_ones && Mi + 1 > 2 * 128) { set_error("wgrad: with_ones needs Mi < 256 (two M blocks of shared memory)"); return CNC_ENOTSUP; }
     mg::Args a{X, Z, partials, ldx, ldz, Mi, No, Ns};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (No <= 96) mg::wgrad_kernel<96><<<n_partials, mg::NTHREADS, mg::SMEM_DYN, s>>>(a);
-    else mg::wgrad_kernel<160><<<n_partials, mg::NTHREADS, mg::SMEM_DYN, s>>>(a);
-    return check_launch("wgrad");
+    const bool o = with_ones != 0;
+#define CNC_WG(MI, NO) if (Mi == MI && No == NO) return o ? launch_wgrad<MI, NO, true>(a, n_partials, s) : launch_wgrad<MI, NO, false>(a, n_partials, s);
+    if (Mi == 256 && No == 160) return launch_wgrad<256, 160, false>(a, n_partials, s);
+    CNC_WG(160, 160) CNC_WG(96, 160) CNC_WG(160, 80) CNC_WG(32, 16) CNC_WG(64, 32)
+#undef CNC_WG
+    set_error("wgrad: shape (Mi=%u, No=%u) is not instantiated: (256,160) (160,160) (96,160) (160,80) (32,16) (64,32)", Mi, No);
+    return CNC_ENOTSUP;
 }
 
 }  // extern "C"

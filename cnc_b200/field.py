@@ -43,17 +43,18 @@ class _TruncExp(Function):
 trunc_exp = _TruncExp.apply
 
 
-def wgrad(x: torch.Tensor, z: torch.Tensor, mi: int = None, no: int = None) -> torch.Tensor:
+def wgrad(x: torch.Tensor, z: torch.Tensor, mi: int = None, no: int = None, with_ones: bool = False) -> torch.Tensor:
     """x[:, :mi]^T @ z[:, :no] -> [mi, no] over the rows (samples) on the tensor cores, fp32-equivalent
-    (`cnc_wgrad`, csrc/mlp_grad.cu).  x and z are row-major fp32; mi a multiple of 32, no a multiple of 16."""
+    (`cnc_wgrad`, csrc/mlp_grad.cu).  x and z are row-major fp32.  with_ones: one more output row, the column sums
+    of z (x gets a virtual all-ones column) -- the bias gradient of a linear layer."""
     assert x.dim() == 2 and z.dim() == 2 and x.shape[0] == z.shape[0]
     x, z = x.contiguous(), z.contiguous()
     mi = x.shape[1] if mi is None else mi
     no = z.shape[1] if no is None else no
     ns = x.shape[0]
     g = max(1, min(lib().cnc_wgrad_max_partials(), (ns + 31) // 32))
-    part = torch.empty(g, mi, no, device=x.device, dtype=torch.float32)
-    check(lib().cnc_wgrad(ptr(x), x.shape[1], mi, ptr(z), z.shape[1], no, ptr(part), g, ns, stream()))
+    part = torch.empty(g, mi + int(with_ones), no, device=x.device, dtype=torch.float32)
+    check(lib().cnc_wgrad(ptr(x), x.shape[1], mi, ptr(z), z.shape[1], no, int(with_ones), ptr(part), g, ns, stream()))
     return part.sum(0)
 
 
@@ -102,15 +103,19 @@ class _FusedFieldTrain(Function):
         dz5 = g_rgb * rgb * (1.0 - rgb)
         gW5, gb5 = dz5.t() @ h4, dz5.sum(0)
         dz4 = (dz5 @ W5) * (h4 > 0)
-        gW4, gb4 = wgrad(h3, dz4).t(), dz4.sum(0)
+        g4 = wgrad(h3, dz4, with_ones=True)                     # [161, 160]: rows = input features, last row = bias grad
+        gW4, gb4 = g4[:160].t(), g4[160]
         dz3 = (dz4 @ W4) * (h3 > 0)
         head_in = torch.cat([sh16((dirs + 1.0) / 2.0), geo, geo.new_zeros(n, 1)], dim=-1)   # ngp.py:540-542 (+ pad to 96)
-        gW3, gb3 = wgrad(head_in, dz3).t()[:, :95], dz3.sum(0)
+        g3 = wgrad(head_in, dz3, with_ones=True)
+        gW3, gb3 = g3[:95].t(), g3[96]
         # base: [density pre-activation | geo] = Linear(160,80)(relu(Linear(255,160)(x0)))
         dz2 = torch.cat([g_sigma * sigma.unsqueeze(-1), dz3 @ W3[:, 16:]], dim=-1)   # d trunc_exp(h-1)*selector / dh = density
-        gW2, gb2 = wgrad(h1, dz2).t(), dz2.sum(0)
+        g2 = wgrad(h1, dz2, with_ones=True)
+        gW2, gb2 = g2[:160].t(), g2[160]
         dz1 = (dz2 @ W2) * (h1 > 0)
-        gW1, gb1 = wgrad(x0, dz1).t()[:, :255], dz1.sum(0)
+        g1 = wgrad(x0, dz1)                                     # x0 column 255 is the kernel's all-ones pad column
+        gW1, gb1 = g1[:255].t(), g1[255]
         dfeat = dz1 @ W1[:, :192]                                               # only the grid columns carry on
         # grid features -> tables: K2 scatter-add + STE mask (ngp.py:121-165, :33-39)
         mb = field.mlp_base

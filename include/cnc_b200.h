@@ -173,7 +173,7 @@ int cnc_field_fwd(const float *pos, const float *dirs, const float *aabb6_host,
                   float *sigma, float *rgb, float *geo, uint32_t N, cnc_stream_t stream);
 /* Training forward: the same kernel, additionally leaving what the backward pass of ngp.py:514-566 needs in HBM as
  * the values go by (no recomputation, no extra pass): x0 [N,256] = input of Linear(255,160) (192 grid features |
- * x, sin/cos | zero pad), h1 / h3 / h4 [N,160] = the ReLU outputs, geo [N,79]; all 16-byte aligned, all required. */
+ * x, sin/cos | a constant 1 in the pad column), h1 / h3 / h4 [N,160] = the ReLU outputs, geo [N,79]; all 16-byte aligned, all required. */
 int cnc_field_fwd_train(const float *pos, const float *dirs, const float *aabb6_host,
                         const uint8_t *bits_xyz, const uint8_t *bits_xy, const uint8_t *bits_xz,
                         const uint8_t *bits_yz, const int32_t *offsets3, const int32_t *resolutions3,
@@ -186,12 +186,15 @@ int cnc_field_fwd_train(const float *pos, const float *dirs, const float *aabb6_
  * torch autograd = an fp32 cuBLAS GEMM):  C[i, o] = sum_s X[s, i] * Z[s, o],  X = layer input [Ns, ldx] (first Mi
  * columns, Mi a multiple of 32, <= 256), Z = gradient of the layer output [Ns, ldz] (first No columns, No a multiple
  * of 16, <= 160), fp32 row-major, 16-byte aligned.  3xTF32 tcgen05 MMAs with fp32 accumulation (fp32-equivalent).
- * The kernel writes n_partials partial sums [n_partials, Mi, No] (one per CTA, n_partials <= cnc_wgrad_max_partials());
- * the caller adds them up in index order, which makes the result deterministic.
+ * with_ones != 0 appends a virtual all-ones column to X (built in shared memory, no HBM traffic): row Mi of the result
+ * is the column sum of Z, i.e. the bias gradient.  Instantiated (Mi, No): (256,160) (160,160) (96,160) (160,80) --
+ * the four GEMM-shaped layers of the field -- plus (32,16) (64,32) for tests.
+ * The kernel writes n_partials partial sums [n_partials, Mi (+1), No] (one per CTA, n_partials <=
+ * cnc_wgrad_max_partials()); the caller adds them up in index order, which makes the result deterministic.
  * ---------------------------------------------------------------------------------------- */
 int cnc_wgrad_max_partials(void);
 int cnc_wgrad(const float *X, uint32_t ldx, uint32_t Mi, const float *Z, uint32_t ldz, uint32_t No,
-              float *partials, uint32_t n_partials, uint32_t Ns, cnc_stream_t stream);
+              int with_ones, float *partials, uint32_t n_partials, uint32_t Ns, cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Level-wise context model of the 3D grid, fused (one kernel per coded chunk).

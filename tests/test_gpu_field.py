@@ -183,8 +183,9 @@ def test_fused_training_path_matches_unfused_autograd(cuda, n):
             assert float(((a != 0) ^ (b != 0)).float().mean()) < 1e-4, k
 
 
-@pytest.mark.parametrize("ns,mi,no", [(1, 32, 16), (31, 96, 160), (1000, 256, 160), (4097, 160, 80), (50000, 160, 160), (300000, 256, 160)])
-def test_wgrad_matches_fp64(cuda, ns, mi, no):
+@pytest.mark.parametrize("ns,mi,no,ones", [(1, 32, 16, False), (31, 96, 160, True), (1000, 256, 160, False), (4097, 160, 80, True),
+                                           (50000, 160, 160, True), (300000, 256, 160, False), (70, 64, 32, True)])
+def test_wgrad_matches_fp64(cuda, ns, mi, no, ones):
     """cnc_wgrad (3xTF32 tcgen05, MN-major operands straight from the sample-major activations) against an fp64
     matmul: fp32-equivalent (the error of an fp32 GEMM with this contraction length), leading dimensions honoured."""
     from cnc_b200.field import wgrad
@@ -194,7 +195,11 @@ def test_wgrad_matches_fp64(cuda, ns, mi, no):
     z = torch.randn(ns, no + 16, generator=g).to(cuda) * 0.1
     x[:, 0] = 1.0      # a constant column: same-sign sums show any accumulation bias
     z[:, 0] = 0.25
-    got = wgrad(x, z, mi, no)
+    got = wgrad(x, z, mi, no, with_ones=ones)
+    if ones:
+        np.testing.assert_allclose(got[mi].double().cpu().numpy(), z[:, :no].double().sum(0).cpu().numpy(),
+                                   rtol=0, atol=4e-6 * float(z[:, :no].abs().sum(0).max()))
+        got = got[:mi]
     want = x[:, :mi].double().t() @ z[:, :no].double()
     ref32 = x[:, :mi].t() @ z[:, :no]
     scale = (x[:, :mi].double().abs().t() @ z[:, :no].double().abs())       # sum of |terms|: the fp32 error scale
