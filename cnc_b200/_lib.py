@@ -48,6 +48,8 @@ SIGNATURES = {
     "cnc_render_from_density": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "cnc_context3d_probs": [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "cnc_wgrad": [_vp, _u32, _u32, _vp, _u32, _u32, C.c_int, _vp, _u32, _u32, _vp],
+    "cnc_dgrad_pack": [_vp, _u32, _u32, _i32, _u32, _u32, _u32, _vp, _vp],
+    "cnc_dgrad": [_vp, _u32, _u32, _vp, _u32, _vp, _u32, _vp, _u32, _u32, _vp],
     "cnc_vertex_valid_bits": [_vp, _i32, _vp, _i32, _vp, _i64, _vp, _vp],
 }
 
@@ -70,6 +72,8 @@ def lib():
         L.cnc_version.restype = C.c_int
         L.cnc_field_blob_floats.restype = C.c_uint32
         L.cnc_context3d_mlp_floats.restype = C.c_uint32
+        L.cnc_dgrad_blob_floats.restype = C.c_uint32
+        L.cnc_dgrad_blob_floats.argtypes = [_u32, _u32]
         L.cnc_wgrad_max_partials.restype = C.c_int
         L.cnc_wgrad_max_partials.argtypes = []
         _lib = L

@@ -58,6 +58,25 @@ def wgrad(x: torch.Tensor, z: torch.Tensor, mi: int = None, no: int = None, with
     return part.sum(0)
 
 
+def dgrad(z: torch.Tensor, W: torch.Tensor, n_out: int, h: torch.Tensor = None, col_off: int = 0, n_first: int = 0,
+          n_valid: int = None, rows: int = None) -> torch.Tensor:
+    """[h > 0] * (z @ W[:, col_off + n]) -> [Ns, n_out] on the tensor cores, fp32-equivalent (`cnc_dgrad`,
+    csrc/mlp_dgrad.cu): the input gradient of y = relu(...) @ W^T.  W is an nn.Linear weight [out, in]; `rows` (default
+    W.shape[0]) of it are used; output column n takes weight column n + col_off for n_first <= n < n_valid, 0 elsewhere."""
+    z, W = z.contiguous(), W.detach().contiguous()
+    ns, no_z = z.shape
+    rows = W.shape[0] if rows is None else rows
+    n_valid = n_out if n_valid is None else n_valid
+    blob = torch.empty(lib().cnc_dgrad_blob_floats(no_z, n_out), device=z.device, dtype=torch.float32)
+    check(lib().cnc_dgrad_pack(ptr(W), W.shape[1], rows, col_off, n_first, n_valid, n_out, ptr(blob), stream()))
+    out = torch.empty(ns, n_out, device=z.device, dtype=torch.float32)
+    if h is not None:
+        h = h.contiguous()
+    check(lib().cnc_dgrad(ptr(z), no_z, no_z, ptr(blob), n_out, ptr(h), 0 if h is None else h.shape[1], ptr(out), n_out, ns,
+                          stream()))
+    return out
+
+
 class _FusedFieldTrain(Function):
     """Differentiable ngp.py:514-566 for the product layout: the forward is ONE launch of the fused kernel
     (`cnc_field_fwd_train`, which also leaves x0 / h1 / geo / h3 / h4 in HBM), the backward is the chain rule written
@@ -100,23 +119,24 @@ class _FusedFieldTrain(Function):
         # head: sigmoid -> Linear(160,3) -> ReLU -> Linear(160,160) -> ReLU -> Linear(95,160)
         # (weight gradients: cnc_wgrad, contraction over the samples on the tensor cores; the 3-wide last layer and
         #  the input gradients stay fp32 matmuls)
-        dz5 = g_rgb * rgb * (1.0 - rgb)
-        gW5, gb5 = dz5.t() @ h4, dz5.sum(0)
-        dz4 = (dz5 @ W5) * (h4 > 0)
+        dz5 = torch.cat([g_rgb * rgb * (1.0 - rgb), rgb.new_zeros(n, 1)], dim=-1)         # [n, 4], column 3 = 0
+        gW5, gb5 = dz5[:, :3].t() @ h4, dz5[:, :3].sum(0)
+        dz4 = dgrad(dz5, W5, 160, h=h4)                         # (dz5 @ W5) * (h4 > 0)
         g4 = wgrad(h3, dz4, with_ones=True)                     # [161, 160]: rows = input features, last row = bias grad
         gW4, gb4 = g4[:160].t(), g4[160]
-        dz3 = (dz4 @ W4) * (h3 > 0)
+        dz3 = dgrad(dz4, W4, 160, h=h3)
         head_in = torch.cat([sh16((dirs + 1.0) / 2.0), geo, geo.new_zeros(n, 1)], dim=-1)   # ngp.py:540-542 (+ pad to 96)
         g3 = wgrad(head_in, dz3, with_ones=True)
         gW3, gb3 = g3[:95].t(), g3[96]
         # base: [density pre-activation | geo] = Linear(160,80)(relu(Linear(255,160)(x0)))
-        dz2 = torch.cat([g_sigma * sigma.unsqueeze(-1), dz3 @ W3[:, 16:]], dim=-1)   # d trunc_exp(h-1)*selector / dh = density
+        dz2 = dgrad(dz3, W3, 80, col_off=15, n_first=1)         # columns 1..79 = dz3 @ W3[:, 16:], column 0 = 0
+        dz2[:, 0] = (g_sigma * sigma.unsqueeze(-1)).squeeze(-1)  # d trunc_exp(h-1)*selector / dh = density
         g2 = wgrad(h1, dz2, with_ones=True)
         gW2, gb2 = g2[:160].t(), g2[160]
-        dz1 = (dz2 @ W2) * (h1 > 0)
+        dz1 = dgrad(dz2, W2, 160, h=h1)
         g1 = wgrad(x0, dz1)                                     # x0 column 255 is the kernel's all-ones pad column
         gW1, gb1 = g1[:255].t(), g1[255]
-        dfeat = dz1 @ W1[:, :192]                                               # only the grid columns carry on
+        dfeat = dgrad(dz1, W1, 192)                             # only the grid columns carry on
         # grid features -> tables: K2 scatter-add + STE mask (ngp.py:121-165, :33-39)
         mb = field.mlp_base
         xn = field._normalise(pos)

@@ -197,6 +197,21 @@ int cnc_wgrad(const float *X, uint32_t ldx, uint32_t Mi, const float *Z, uint32_
               int with_ones, float *partials, uint32_t n_partials, uint32_t Ns, cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Input gradients of the field MLPs with the ReLU mask fused (backward of nn.Linear + ReLU, ngp.py:428-505; the
+ * reference leaves it to torch autograd = fp32 cuBLAS GEMM + threshold_backward):
+ *   C[s, n] = [H[s, n] > 0] * sum_o Z[s, o] * W[o, n + col_off]      for n_first <= n < n_valid, 0 elsewhere (n < N)
+ * cnc_dgrad_pack turns the nn.Linear weight W [No, ldw] (row-major, [out, in]) into the streamed operand
+ * (cnc_dgrad_blob_floats(No, N) floats, once per step); cnc_dgrad runs one layer: Z [Ns, ldz] (first No columns,
+ * No <= 160, multiple of 4), H [Ns, ldh] nullable (the ReLU output that fed the layer), C [Ns, ldc] (first N columns,
+ * N in {32, 80, 160, 192}).  Error-compensated tf32 tcgen05 MMAs with fp32 accumulation (fp32-equivalent).
+ * ---------------------------------------------------------------------------------------- */
+uint32_t cnc_dgrad_blob_floats(uint32_t No, uint32_t N);
+int cnc_dgrad_pack(const float *W, uint32_t ldw, uint32_t No, int32_t col_off, uint32_t n_first,
+                   uint32_t n_valid, uint32_t N, float *blob, cnc_stream_t stream);
+int cnc_dgrad(const float *Z, uint32_t ldz, uint32_t No, const float *blob, uint32_t N, const float *H,
+              uint32_t ldh, float *C, uint32_t ldc, uint32_t Ns, cnc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Level-wise context model of the 3D grid, fused (one kernel per coded chunk).
  * replaces the chunk body of encode_/decode_binary_vxl_mixPg_3D2D, examples/utils_bpp_acc.py:798-852
  *   == :929-968: query_mask_3D -> compaction -> align_and_pack -> Encoding_xyz(points, n-3, n,

@@ -207,3 +207,25 @@ def test_wgrad_matches_fp64(cuda, ns, mi, no, ones):
     err32 = ((ref32.double() - want).abs() / scale).max().item()
     assert got.shape == (mi, no)
     assert err <= max(4 * err32, 2e-6), (err, err32)
+
+
+@pytest.mark.parametrize("ns,no,n,mask", [(1, 4, 32, False), (127, 160, 160, True), (129, 80, 160, True), (5000, 160, 80, False),
+                                          (70000, 160, 192, False), (300000, 160, 160, True)])
+def test_dgrad_matches_fp64(cuda, ns, no, n, mask):
+    """cnc_dgrad (error-compensated tf32 tcgen05, ReLU mask fused) against an fp64 matmul + mask"""
+    from cnc_b200.field import dgrad
+
+    g = torch.Generator(device="cpu").manual_seed(ns + n)
+    z = (torch.randn(ns, no, generator=g) * 0.3).to(cuda)
+    W = (torch.randn(no, n + 20, generator=g) * 0.2).to(cuda)
+    h = torch.relu(torch.randn(ns, n, generator=g)).to(cuda) if mask else None
+    got = dgrad(z, W, n, h=h, col_off=3, n_first=1)
+    want = z.double() @ W[:, 3:3 + n].double()
+    want[:, 0] = 0
+    scale = z.double().abs() @ W[:, 3:3 + n].double().abs() + 1e-30
+    ref32 = z @ W[:, 3:3 + n]
+    if mask:
+        want = want * (h > 0)
+    err = ((got.double() - want).abs() / scale).max().item()
+    err32 = (((ref32.double() * ((h > 0) if mask else 1.0)) - z.double() @ W[:, 3:3 + n].double() * ((h > 0) if mask else 1.0)).abs() / scale)[:, 1:].max().item()
+    assert err <= max(4 * err32, 2e-6), (err, err32)
