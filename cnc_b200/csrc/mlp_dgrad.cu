@@ -143,33 +143,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_kernel(const Args a) {
     } else if (warp < 8) {
         // =============================== Z staging ===============================
         const uint32_t t = threadIdx.x - 128u;        // 0..127: row of the tile
-        uint32_t g = 0;
-        for (uint32_t it = 0; it < my; it++) {
-            const uint32_t row = (blockIdx.x + it * gridDim.x) * 128u + t;
-            const bool live = row < a.Ns;
-            const float *zr = a.Z + (size_t)row * a.ldz;
-            for (uint32_t kc = 0; kc < KC; kc++, g++) {
-                const uint32_t s = g % NSTAGE, use = g / NSTAGE;
-                float4 v[8];
+        const uint32_t total = my * KC;               // chunks this CTA stages, flat over (tile, k chunk)
+        // the 8 x 16-byte loads of a chunk are issued two chunks ahead of their use: with four staging warps one chunk
+        // in flight is 16 KB per SM, a third of what the DRAM latency needs at this SM's share of the bandwidth
+        // lanes 0-7 read the eight float4 of one row, the next eight lanes the next row: a warp instruction covers four
+        // whole 128-byte lines (row-per-thread would touch 32 lines per instruction)
+        const uint32_t wq = (t >> 5) * 32u + ((uint32_t)lane >> 3), jq = (uint32_t)lane & 7u;   // first row of this lane, its float4
+        auto load = [&](uint32_t g, float4 (&v)[8]) {
+            const uint32_t it = g / KC, kc = g - it * KC;
+            const uint32_t row0 = (blockIdx.x + it * gridDim.x) * 128u + wq;
+            const uint32_t col = kc * 32u + 4u * jq;
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const uint32_t col = kc * 32u + 4u * j;
-                    v[j] = (live && col < a.No) ? __ldg(reinterpret_cast<const float4 *>(zr + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                if (use > 0) mbar_wait(empty(s), (use - 1) & 1u);
-                uint8_t *rowp = smem + s * STAGE_BYTES + (t >> 3) * 1024u + (t & 7u) * 128u;
+            for (int i = 0; i < 8; i++) {
+                const uint32_t row = row0 + 4u * i;
+                v[i] = (row < a.Ns && col < a.No) ? __ldg(reinterpret_cast<const float4 *>(a.Z + (size_t)row * a.ldz + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto process = [&](uint32_t g, const float4 (&v)[8]) {
+            const uint32_t s = g % NSTAGE, use = g / NSTAGE;
+            if (use > 0) mbar_wait(empty(s), (use - 1) & 1u);
+            uint8_t *st = smem + s * STAGE_BYTES;
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    uint4 hi, pr;
-                    split_tf32(v[j].x, hi.x, pr.x); split_tf32(v[j].y, hi.y, pr.y);
-                    split_tf32(v[j].z, hi.z, pr.z); split_tf32(v[j].w, hi.w, pr.w);
-                    const uint32_t phys = ((uint32_t)j ^ (t & 7u)) << 4;
-                    *reinterpret_cast<uint4 *>(rowp + phys) = hi;
-                    *reinterpret_cast<uint4 *>(rowp + A_HALF + phys) = pr;
-                }
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full(s));
+            for (int i = 0; i < 8; i++) {
+                const uint32_t r = wq + 4u * i;       // row inside the tile
+                uint4 hi, pr;
+                split_tf32(v[i].x, hi.x, pr.x); split_tf32(v[i].y, hi.y, pr.y);
+                split_tf32(v[i].z, hi.z, pr.z); split_tf32(v[i].w, hi.w, pr.w);
+                uint8_t *p = st + (r >> 3) * 1024u + (r & 7u) * 128u + ((jq ^ (r & 7u)) << 4);
+                *reinterpret_cast<uint4 *>(p) = hi;
+                *reinterpret_cast<uint4 *>(p + A_HALF) = pr;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full(s));
+        };
+        float4 v0[8], v1[8], v2[8];
+        if (0 < total) load(0, v0);
+        if (1 < total) load(1, v1);
+        for (uint32_t g = 0; g < total; g += 3) {
+            if (g + 2 < total) load(g + 2, v2);
+            process(g, v0);
+            if (g + 1 < total) {
+                if (g + 3 < total) load(g + 3, v0);
+                process(g + 1, v1);
+            }
+            if (g + 2 < total) {
+                if (g + 4 < total) load(g + 4, v1);
+                process(g + 2, v2);
             }
         }
     } else if (warp == 8) {
