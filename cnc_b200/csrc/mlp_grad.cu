@@ -240,9 +240,9 @@ int cnc_wgrad(const float *X, uint32_t ldx, uint32_t Mi, const float *Z, uint32_
     const bool o = with_ones != 0;
 #define CNC_WG(MI, NO) if (Mi == MI && No == NO) return o ? launch_wgrad<MI, NO, true>(a, n_partials, s) : launch_wgrad<MI, NO, false>(a, n_partials, s);
     if (Mi == 256 && No == 160) return launch_wgrad<256, 160, false>(a, n_partials, s);
-    CNC_WG(160, 160) CNC_WG(96, 160) CNC_WG(160, 80) CNC_WG(32, 16) CNC_WG(64, 32)
+    CNC_WG(160, 160) CNC_WG(96, 160) CNC_WG(160, 80) CNC_WG(160, 16) CNC_WG(32, 16) CNC_WG(64, 32)
 #undef CNC_WG
-    set_error("wgrad: shape (Mi=%u, No=%u) is not instantiated: (256,160) (160,160) (96,160) (160,80) (32,16) (64,32)", Mi, No);
+    set_error("wgrad: shape (Mi=%u, No=%u) is not instantiated: (256,160) (160,160) (96,160) (160,80) (160,16) (32,16) (64,32)", Mi, No);
     return CNC_ENOTSUP;
 }
 

@@ -119,8 +119,9 @@ class _FusedFieldTrain(Function):
         # head: sigmoid -> Linear(160,3) -> ReLU -> Linear(160,160) -> ReLU -> Linear(95,160)
         # (weight gradients: cnc_wgrad, contraction over the samples on the tensor cores; the 3-wide last layer and
         #  the input gradients stay fp32 matmuls)
-        dz5 = torch.cat([g_rgb * rgb * (1.0 - rgb), rgb.new_zeros(n, 1)], dim=-1)         # [n, 4], column 3 = 0
-        gW5, gb5 = dz5[:, :3].t() @ h4, dz5[:, :3].sum(0)
+        dz5 = torch.cat([g_rgb * rgb * (1.0 - rgb), rgb.new_zeros(n, 13)], dim=-1)        # [n, 16], columns 3.. = 0
+        g5 = wgrad(h4, dz5, with_ones=True)                     # [161, 16]
+        gW5, gb5 = g5[:160, :3].t(), g5[160, :3]
         dz4 = dgrad(dz5, W5, 160, h=h4)                         # (dz5 @ W5) * (h4 > 0)
         g4 = wgrad(h3, dz4, with_ones=True)                     # [161, 160]: rows = input features, last row = bias grad
         gW4, gb4 = g4[:160].t(), g4[160]

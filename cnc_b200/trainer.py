@@ -19,7 +19,7 @@ class TrainStep:
         self.field, self.estimator, self.cm, self.lmbda = radiance_field, estimator, context_model, lmbda
         self.render_step_size, self.target = render_step_size, target_sample_batch_size
         params = list(radiance_field.parameters()) + (list(context_model.parameters()) if context_model is not None else [])
-        self.optimizer = torch.optim.Adam(params, lr=lr, eps=1e-15)        # train...:254-266
+        self.optimizer = torch.optim.Adam(params, lr=lr, eps=1e-15, fused=params[0].is_cuda)   # train...:254-266; one fused pass over the 40 M latents
         self.reducer = GradAllReducer(params, bucket_bytes=bucket_bytes)
         self.step_id = 0
 

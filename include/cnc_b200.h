@@ -187,8 +187,8 @@ int cnc_field_fwd_train(const float *pos, const float *dirs, const float *aabb6_
  * columns, Mi a multiple of 32, <= 256), Z = gradient of the layer output [Ns, ldz] (first No columns, No a multiple
  * of 16, <= 160), fp32 row-major, 16-byte aligned.  3xTF32 tcgen05 MMAs with fp32 accumulation (fp32-equivalent).
  * with_ones != 0 appends a virtual all-ones column to X (built in shared memory, no HBM traffic): row Mi of the result
- * is the column sum of Z, i.e. the bias gradient.  Instantiated (Mi, No): (256,160) (160,160) (96,160) (160,80) --
- * the four GEMM-shaped layers of the field -- plus (32,16) (64,32) for tests.
+ * is the column sum of Z, i.e. the bias gradient.  Instantiated (Mi, No): (256,160) (160,160) (96,160) (160,80) (160,16)
+ * -- the five layers of the field -- plus (32,16) (64,32) for tests.
  * The kernel writes n_partials partial sums [n_partials, Mi (+1), No] (one per CTA, n_partials <=
  * cnc_wgrad_max_partials()); the caller adds them up in index order, which makes the result deterministic.
  * ---------------------------------------------------------------------------------------- */
