@@ -46,7 +46,7 @@ SIGNATURES = {
                            _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "cnc_packed_scan": [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp],
     "cnc_render_from_density": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "cnc_context3d_probs": [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "cnc_context3d_probs": [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp],
     "cnc_wgrad": [_vp, _u32, _u32, _vp, _u32, _u32, C.c_int, _vp, _u32, _u32, _vp],
     "cnc_dgrad_pack": [_vp, _u32, _u32, _i32, _u32, _u32, _u32, _vp, _vp],
     "cnc_dgrad": [_vp, _u32, _u32, _vp, _u32, _vp, _u32, _vp, _u32, _u32, _vp],

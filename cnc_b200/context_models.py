@@ -364,7 +364,7 @@ class CNC_context_models(nn.Module):
         vbits, vbit_off = self._vertex_bits(Encoding_xyz, vx)
         check(lib().cnc_context3d_probs(ptr(pts), ptr(seg), E, ptr(vx), vx.shape[-1], ptr(bits),
                                         ptr(Encoding_xyz.offsets_list), ptr(Encoding_xyz.resolutions_list), n, float(Pg_n),
-                                        ptr(self._mlp3d_packed()), ptr(prob), None, ptr(exist), seg_base,
+                                        ptr(self._mlp3d_packed()), ptr(prob), None, ptr(exist), seg_base, lo,
                                         ptr(vbits), ptr(vbit_off), stream()))
         ex = exist.bool()
         return prob[ex], ex

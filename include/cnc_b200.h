@@ -223,6 +223,10 @@ int cnc_dgrad(const float *Z, uint32_t ldz, uint32_t No, const float *blob, uint
  *   W1^T [25][32], b1 [32], W2^T [32][32], b2 [32], W3^T [32][8], b3 [8] of context_model_3D.
  *   -> prob [n_entries,8] (clamped to [1e-6, 1-1e-6]; 0 for entries that are not coded),
  *      mean [n_entries,8] unclamped (nullable), exist [n_entries] u8 (mask_exist, :823).
+ *   entry_base = index inside the level of the chunk's first entry (`lo` of utils_bpp_acc.py:798-802): the kernel
+ *   works in batches of 64 entries aligned to the absolute index; the summation order per entry -- and with it
+ *   every probability bit -- is a function of the voxel list and of the chunk boundaries only (never of the grid
+ *   size or the GPU count), and cuts that fall on the batch grid do not change a bit.
  *   vertex_bits / vertex_bit_offsets (nullable, together): the per-vertex occupancy predicate of the masked
  *   gather (gridencoder.cu:221-276) precomputed by cnc_vertex_valid_bits for all levels of the encoder: one bit
  *   per grid vertex, bit (c0*res + c1)*res + c2 of level l at vertex_bit_offsets[l] (multiples of 32);
@@ -237,7 +241,7 @@ int cnc_context3d_probs(const int16_t *pts, const int64_t *seg, int64_t n_entrie
                         const uint8_t *binary_vxl, int32_t Rb, const uint8_t *sign_bits,
                         const int32_t *offsets, const int32_t *resolutions, int32_t level, float Pg,
                         const float *mlp_packed, float *prob, float *mean, uint8_t *exist,
-                        int64_t seg_base, const uint32_t *vertex_bits,
+                        int64_t seg_base, int64_t entry_base, const uint32_t *vertex_bits,
                         const int64_t *vertex_bit_offsets, cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -91,12 +91,21 @@ def test_fused_context_kernel_vs_reference_flow(cuda, oracle):
         frac = (c_f != c_u).float().mean().item()
         print(f"level {n}: {ef.sum().item()} coded rows, {frac * 100:.3f}% of the int16 CDF entries differ fused vs op-by-op")
         assert frac < 0.02
-        # sub-range call == slice of the full call (chunking does not change a probability)
-        lo, hi = E // 3, 2 * E // 3
-        ps, es = cm._probs_3D_fused(encs[0], pq, vxl, n, lo, hi, Pg_n)
-        assert torch.equal(es, ef[lo:hi])
-        first = int(ef[:lo].sum())
-        assert torch.equal(ps, pf[first:first + int(es.sum())])
+        # sub-range call == slice of the full call: bit for bit when the cut falls on the kernel's batch grid (64
+        # entries, absolute), to rounding of the overlap-weighted sum otherwise (the chunking of a level is part of
+        # the stream layout and identical on both sides of the codec, utils_bpp_acc.py:798-802 == :929-933)
+        for lo, hi, exact in ((E // 3 // 64 * 64, 2 * E // 3 // 64 * 64, True), (E // 3 + 1, 2 * E // 3 + 5, False)):
+            ps, es = cm._probs_3D_fused(encs[0], pq, vxl, n, lo, hi, Pg_n)
+            assert torch.equal(es, ef[lo:hi])
+            first = int(ef[:lo].sum())
+            want = pf[first:first + int(es.sum())]
+            if exact:
+                assert torch.equal(ps, want)
+            else:
+                torch.testing.assert_close(ps, want, rtol=2e-6, atol=1e-7)
+        # and the kernel is deterministic: same call, same bits
+        p2, _ = cm._probs_3D_fused(encs[0], pq, vxl, n, 0, E, Pg_n)
+        assert torch.equal(p2, pf)
 
 
 def test_streams_equal_oracle_coder(cuda, oracle):
