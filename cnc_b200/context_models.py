@@ -528,6 +528,27 @@ class CNC_context_models(nn.Module):
             with torch.cuda.stream(side):
                 jobs.append((names[done:], tac.encode_streams_async(c1s[done:], syms[done:])))
 
+        # The coder is one serial chain per stream, so the streams with the most symbols go first: their probabilities
+        # are evaluated and their coder launched before anything else, everything shorter runs beside them.
+        def longest_stream(n):
+            if n in self.skip_levels_3D or n >= self.Pg_level:
+                return self.offs[n + 1] - self.offs[n]
+            return max(hi - lo for lo, hi in self._chunks(n))
+
+        for n in sorted(range(self.n_levels), key=lambda n: -longest_stream(n)):
+            Pg_n, bit_n, _ = self.get_BiRF_wentropy_leveln(pq["xyz"], n)
+            Pgs_dict["3D" + str(n)] = Pg_n
+            if n in self.skip_levels_3D or n >= self.Pg_level:
+                xs = pq["xyz"][self.offs[n]:self.offs[n + 1]].reshape(-1)
+                emit(f"{filename_prefix}_3D{n}.b", xs, Pg_n.expand(xs.numel()))
+                ttl_bit += bit_n
+                continue
+            for sn, (lo, hi) in enumerate(self._chunks(n)):
+                ps, mask_exist = self._probs_3D(Encoding_xyz, pq["xyz"], binary_vxl, n, lo, hi, Pg_n)
+                values_q = pq["xyz"][self.unique_value_list[n][lo:hi] + self.offs[n]][mask_exist]
+                ttl_bit += torch.sum(self.entropy_model(values_q, ps))
+                emit(f"{filename_prefix}_3D{n}_{sn}.b", values_q.reshape(-1), ps.reshape(-1))
+            flush()
         idx_coords2 = self.get_idx_coords2(binary_vxl)
         planes = self._planes(binary_vxl)
         finest = pq["xyz"][self.offs[-2]:self.offs[-1]]
@@ -545,20 +566,6 @@ class CNC_context_models(nn.Module):
                     bit_n = torch.sum(self.entropy_model(values_q, mean))
                     emit(f"{filename_prefix}_{axis}{n}.b", values_q.reshape(-1), torch.clamp(mean, 1e-6, 1 - 1e-6).reshape(-1))
                 ttl_bit += bit_n
-        for n in range(self.n_levels):
-            Pg_n, bit_n, _ = self.get_BiRF_wentropy_leveln(pq["xyz"], n)
-            Pgs_dict["3D" + str(n)] = Pg_n
-            if n in self.skip_levels_3D or n >= self.Pg_level:
-                xs = pq["xyz"][self.offs[n]:self.offs[n + 1]].reshape(-1)
-                emit(f"{filename_prefix}_3D{n}.b", xs, Pg_n.expand(xs.numel()))
-                ttl_bit += bit_n
-                continue
-            for sn, (lo, hi) in enumerate(self._chunks(n)):
-                ps, mask_exist = self._probs_3D(Encoding_xyz, pq["xyz"], binary_vxl, n, lo, hi, Pg_n)
-                values_q = pq["xyz"][self.unique_value_list[n][lo:hi] + self.offs[n]][mask_exist]
-                ttl_bit += torch.sum(self.entropy_model(values_q, ps))
-                emit(f"{filename_prefix}_3D{n}_{sn}.b", values_q.reshape(-1), ps.reshape(-1))
-            flush()
         flush()
         streams = [b for _, job in jobs for b in job.result()]
         coded_bits = 0
