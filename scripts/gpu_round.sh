@@ -16,7 +16,7 @@ tail -3 gpurun_out/ncu_bench.log
 ncu --set full --clock-control none --import-source on -k regex:field_fwd_kernel -s 3 -c 1 -f -o gpurun_out/prof_field \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-codec --train-steps 0 --no-e2e > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
-ncu --set full --clock-control none --import-source on -k regex:context3d_kernel -s 18 -c 1 -f -o gpurun_out/prof_context \
+ncu --set full --clock-control none --import-source on -k regex:context3d_kernel -s 19 -c 1 -f -o gpurun_out/prof_context \
     python scripts/codec_time.py > gpurun_out/ncu_context.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:ac_decode_kernel -s 5 -c 1 -f -o gpurun_out/prof_decode \
     python scripts/codec_time.py > gpurun_out/ncu_decode.log 2>&1

@@ -162,3 +162,21 @@ def test_codec_roundtrip_product_layout(cuda):
     n_sym = sum(8 * int(cm.hashparams_num_levels[n]) for n in range(12))
     print(f"product layout: {coded_MB:.3f} MiB coded (estimate {est_MB:.3f}) for {n_sym} 3D symbols max")
     assert abs(est_MB - coded_MB) / coded_MB < 0.02
+
+
+def test_container_roundtrip_feeds_the_decoder(cuda):
+    """encode -> one blob (streams + Pgs + occupancy bits + 13-bit context-model weights) -> unpack -> decode: the
+    decoder side needs nothing but the blob"""
+    from cnc_b200 import container as C
+
+    cm, encs, vxl = make(cuda, **SMALL)
+    Pgs, _, coded_MB, streams = cm.encode_binary_vxl_mixPg_3D2D(*encs, vxl, "c", return_streams=True)
+    blob = C.pack(streams, Pgs, vxl, {}, {"res": cm.res, "res_2D": cm.res_2D})
+    assert len(blob) < coded_MB * 1024 * 1024 + vxl.numel() / 8 + 4096
+    got = C.unpack(blob, device=cuda)
+    assert got["layout"] == {"res": cm.res, "res_2D": cm.res_2D} and torch.equal(got["binary_vxl"], vxl)
+    recs = [torch.ones_like(e.params) for e in encs]
+    out = cm.decode_binary_vxl_mixPg_3D2D(*encs, *recs, got["binary_vxl"], got["Pgs_dict"], "c", streams=got["streams"])
+    ref = cm.decode_binary_vxl_mixPg_3D2D(*encs, *[torch.ones_like(e.params) for e in encs], vxl, Pgs, "c", streams=streams)
+    for a, b in zip(out, ref):
+        assert torch.equal(a, b)
