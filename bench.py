@@ -144,19 +144,21 @@ def cpu_baseline(n=4096):
             "sample": f"{reps} x {n} samples of the same layout through oracle/ (C gather + numpy fp32 MLP)"}
 
 
-def codec_bench(dev, cpu_seconds=12.0):
+def codec_bench(dev, cpu_seconds=12.0, rank=0, world=1, dist=None):
     """BASELINE metric (ii): context-model entropy encode + decode of the product hash tables (configs[2]):
     L=12 3D levels (res 18..514, T=2^19) + 3 planes x 4 levels (T=2^17), F=8, ball occupancy, biased +-1 tables,
     random-init context models.  MB/s = fp32 table bytes represented (161.3 MB) / wall time of the public
     encode_/decode_binary_vxl_mixPg_3D2D call (probabilities + range coding + streams on the host).
     CPU arm: the reference codes each stream with torchac on one CPU thread; oracle/ restates that coder in C
-    and is timed here on a bounded sample of the same (cdf, symbol) streams."""
+    and is timed here on a bounded sample of the same (cdf, symbol) streams.
+    N > 1: the codec of one scene does not shard (a level's largest stream is one serial chain and levels decode in
+    order), so every rank codes its own scene -- replicas only; MB/s = N x table bytes / max-over-ranks time."""
     from cnc_b200 import torchac as tac
     from cnc_b200.context_models import CNC_context_models
     from cnc_b200.gridencoder import GridEncoder
     from oracle import oracle as o
 
-    torch.manual_seed(0)
+    torch.manual_seed(rank)
     t0 = time.perf_counter()
     encs = [GridEncoder(num_dim=3, n_features=F, resolutions_list=R3, log2_hashmap_size=19, ste_binary=True).to(dev)] + \
            [GridEncoder(num_dim=2, n_features=F, resolutions_list=R2, log2_hashmap_size=17, ste_binary=True).to(dev) for _ in range(3)]
@@ -189,18 +191,32 @@ def codec_bench(dev, cpu_seconds=12.0):
     finally:
         tac.encode_streams_async = orig
     enc_s, dec_s = [], []
+    def sync():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
     for _ in range(3):
-        torch.cuda.synchronize(); t = time.perf_counter()
+        sync(); t = time.perf_counter()
         Pgs, est_MB, coded_MB, streams = cm.encode_binary_vxl_mixPg_3D2D(*encs, vxl, "bench", return_streams=True)
-        torch.cuda.synchronize(); enc_s.append(time.perf_counter() - t)
+        sync(); enc_s.append(time.perf_counter() - t)   # after the barrier: the slowest rank's time
         recs = [torch.ones_like(e.params) for e in encs]
-        torch.cuda.synchronize(); t = time.perf_counter()
+        sync(); t = time.perf_counter()
         out = cm.decode_binary_vxl_mixPg_3D2D(*encs, *recs, vxl, Pgs, "bench", streams=streams)
-        torch.cuda.synchronize(); dec_s.append(time.perf_counter() - t)
+        sync(); dec_s.append(time.perf_counter() - t)
     ok = all(bool(((torch.where(e.params >= 0, 1.0, -1.0) == r) | (r == 1)).all()) for e, r in zip(encs, out))
     n_params = sum(e.params.numel() for e in encs)
     table_MB = n_params * 4 / 1e6
     n_sym = sum(int(x.numel()) for x in captured["sym"])
+    if dist is not None:
+        flag = torch.tensor([1.0 if ok else 0.0, min(enc_s), min(dec_s)], dtype=torch.float64, device=dev)
+        mn = flag.clone(); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        mx = flag.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        ok = bool(mn[0] > 0)
+        enc_s, dec_s = [float(mx[1])], [float(mx[2])]
+    if rank != 0:
+        return None
     # CPU coder on a bounded sample: streams in descending size until the time budget is used
     order = sorted(range(len(captured["sym"])), key=lambda k: -captured["sym"][k].numel())
     done_sym, t_cpu = 0, 0.0
@@ -216,10 +232,12 @@ def codec_bench(dev, cpu_seconds=12.0):
             break
     cpu_sym_per_s = done_sym / t_cpu            # encode + decode of each symbol, one thread
     enc, dec = min(enc_s), min(dec_s)
-    return {"workload": "configs[2]: product tables L=12 T=2^19 + 3x4 planes T=2^17, F=8, ball occupancy, 33 streams",
+    return {"workload": "configs[2]: product tables L=12 T=2^19 + 3x4 planes T=2^17, F=8, ball occupancy, 33 streams"
+                        + (f"; {world} scenes, one per GPU (replicas only)" if world > 1 else ""),
             "table_MB_fp32": table_MB, "table_MB_1bit": n_params / 8 / 1e6, "coded_MiB": coded_MB, "estimated_MiB": est_MB,
-            "symbols": n_sym, "encode_s": enc, "decode_s": dec, "encode_MBps": table_MB / enc, "decode_MBps": table_MB / dec,
-            "encode_Msym_per_s": n_sym / enc / 1e6, "decode_Msym_per_s": n_sym / dec / 1e6, "roundtrip_ok": ok,
+            "symbols": n_sym, "encode_s": enc, "decode_s": dec, "encode_MBps": world * table_MB / enc,
+            "decode_MBps": world * table_MB / dec, "encode_Msym_per_s": world * n_sym / enc / 1e6,
+            "decode_Msym_per_s": world * n_sym / dec / 1e6, "roundtrip_ok": ok, "scaling": "weak (replicas)" if world > 1 else "n/a",
             "setup_s": t_setup,
             "cpu_baseline": {"kind": "port", "cores": 1, "unit": "MB/s",
                              "value": table_MB / (n_sym / cpu_sym_per_s),
@@ -423,6 +441,12 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e, ms_k = t.tolist()
+    codec = None
+    if a.impl == "ours" and not a.no_codec:
+        del model
+        field = None
+        torch.cuda.empty_cache()
+        codec = codec_bench(dev, rank=rank, world=world, dist=dist)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -478,10 +502,8 @@ def main():
         line["fwd_bwd"] = fwd_bwd
     if train is not None:
         line["train_step"] = train
-    if a.impl == "ours" and world == 1 and not a.no_codec:
-        del field, model
-        torch.cuda.empty_cache()
-        line["codec"] = codec_bench(dev)
+    if codec is not None:
+        line["codec"] = codec
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
