@@ -40,6 +40,7 @@ SIGNATURES = {
     "cnc_field_pack_weights": [_vp] * 12,
     "cnc_field_fwd": [_vp] * 15 + [_u32, _vp],
     "cnc_field_fwd_train": [_vp] * 19 + [_u32, _vp],
+    "cnc_field_fwd_host": [_vp] * 14 + [_u32] + [_vp] * 4 + [_u32, _u32, _vp, _vp, _vp],
     "cnc_field_set_timeline_buffer": [_vp],
     "cnc_ray_aabb_intersect": [_vp, _vp, _i64, _f32, _f32, _vp, _i32, _f32, _vp, _vp, _vp, _vp],
     "cnc_traverse_grids": [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _i32,

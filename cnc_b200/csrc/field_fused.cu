@@ -833,6 +833,68 @@ int cnc_field_fwd(const float *pos, const float *dirs, const float *aabb6_host, 
                           resolutions2, blob, sigma, rgb, geo, nullptr, nullptr, nullptr, nullptr, N, stream);
 }
 
+/* Host-buffer entry point: the batch is cut into chunks of whole waves of the persistent kernel and pipelined over three
+ * streams (H2D of chunk i+1, kernel on chunk i, D2H of chunk i-1), all from this one call: per chunk the host issues
+ * two copies, one launch, two more copies and three event operations -- a few microseconds each -- so the chunks can be
+ * small enough that only the first upload and the last download are exposed. */
+int cnc_field_fwd_host(const float *pos_host, const float *dirs_host, const float *aabb6_host, const uint8_t *bits_xyz,
+                       const uint8_t *bits_xy, const uint8_t *bits_xz, const uint8_t *bits_yz, const int32_t *offsets3,
+                       const int32_t *resolutions3, const int32_t *offsets2, const int32_t *resolutions2, const float *blob,
+                       float *sigma_host, float *rgb_host, uint32_t N, float *d_pos, float *d_dirs, float *d_sigma,
+                       float *d_rgb, uint32_t wave_samples, uint32_t max_chunk_waves, cnc_stream_t s_compute, cnc_stream_t s_in,
+                       cnc_stream_t s_out) {
+    if (N == 0) return CNC_OK;
+    if (!pos_host || !dirs_host || !sigma_host || !rgb_host || !d_pos || !d_dirs || !d_sigma || !d_rgb || wave_samples == 0 || max_chunk_waves == 0) {
+        set_error("field_fwd_host: null pointer / zero chunk");
+        return CNC_EINVAL;
+    }
+    constexpr int NEV = 256;
+    static cudaEvent_t ev[NEV];
+    static bool ev_init = false;
+    if (!ev_init) {
+        for (int i = 0; i < NEV; i++)
+            if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { set_error("field_fwd_host: cudaEventCreate failed"); return CNC_ECUDA; }
+        ev_init = true;
+    }
+    cudaStream_t sc = static_cast<cudaStream_t>(s_compute), si = static_cast<cudaStream_t>(s_in), so = static_cast<cudaStream_t>(s_out);
+    // chunk schedule in waves: 1, 2, 4, .. max .. 4, 2, 1 -- a small first chunk starts the kernel after a short upload, a
+    // small last chunk leaves a short download exposed, the large ones in between keep the persistent kernel efficient
+    constexpr int MAXC = (NEV - 2) / 2;
+    uint32_t front[MAXC], back[MAXC];
+    int nf = 0, nb = 0;
+    uint32_t left = (N + wave_samples - 1) / wave_samples;
+    for (uint32_t sz = 1; left > 0; sz = sz * 2 < max_chunk_waves ? sz * 2 : max_chunk_waves) {
+        if (nf + nb + 2 > MAXC) { set_error("field_fwd_host: more than %d chunks", MAXC); return CNC_EINVAL; }
+        uint32_t t = sz < left ? sz : left;
+        front[nf++] = t; left -= t;
+        if (left == 0) break;
+        t = sz < left ? sz : left;
+        back[nb++] = t; left -= t;
+    }
+    const uint32_t nchunk = (uint32_t)(nf + nb);
+    int e = 0;
+    // the staging buffers may still be in use by earlier work on the caller's stream
+    cudaEventRecord(ev[e], sc); cudaStreamWaitEvent(si, ev[e], 0); cudaStreamWaitEvent(so, ev[e], 0); e++;
+    uint32_t lo = 0;
+    for (uint32_t c = 0; c < nchunk; c++) {
+        const uint32_t waves = c < (uint32_t)nf ? front[c] : back[nb - 1 - (int)(c - nf)];
+        const uint32_t want = waves * wave_samples, n = (N - lo) < want ? (N - lo) : want;
+        cudaMemcpyAsync(d_pos + (size_t)lo * 3, pos_host + (size_t)lo * 3, (size_t)n * 12, cudaMemcpyHostToDevice, si);
+        cudaMemcpyAsync(d_dirs + (size_t)lo * 3, dirs_host + (size_t)lo * 3, (size_t)n * 12, cudaMemcpyHostToDevice, si);
+        cudaEventRecord(ev[e], si); cudaStreamWaitEvent(sc, ev[e], 0); e++;
+        const int rc = field_fwd_impl(d_pos + (size_t)lo * 3, d_dirs + (size_t)lo * 3, aabb6_host, bits_xyz, bits_xy, bits_xz, bits_yz,
+                                      offsets3, resolutions3, offsets2, resolutions2, blob, d_sigma + lo, d_rgb + (size_t)lo * 3, nullptr,
+                                      nullptr, nullptr, nullptr, nullptr, n, s_compute);
+        if (rc != CNC_OK) return rc;
+        cudaEventRecord(ev[e], sc); cudaStreamWaitEvent(so, ev[e], 0); e++;
+        cudaMemcpyAsync(rgb_host + (size_t)lo * 3, d_rgb + (size_t)lo * 3, (size_t)n * 12, cudaMemcpyDeviceToHost, so);
+        cudaMemcpyAsync(sigma_host + lo, d_sigma + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, so);
+        lo += n;
+    }
+    cudaEventRecord(ev[e], so); cudaStreamWaitEvent(sc, ev[e], 0);   // the caller's stream ends after the last download
+    return check_launch("field_fwd_host");
+}
+
 int cnc_field_fwd_train(const float *pos, const float *dirs, const float *aabb6_host, const uint8_t *bits_xyz,
                         const uint8_t *bits_xy, const uint8_t *bits_xz, const uint8_t *bits_yz, const int32_t *offsets3,
                         const int32_t *resolutions3, const int32_t *offsets2, const int32_t *resolutions2,

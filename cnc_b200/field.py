@@ -313,11 +313,12 @@ class NGPRadianceField_mygrid_2D3D(nn.Module):
 
     @torch.no_grad()
     def forward_host(self, positions: torch.Tensor, directions: torch.Tensor, out_rgb: torch.Tensor = None,
-                     out_sigma: torch.Tensor = None, chunk_waves: int = 4):
+                     out_sigma: torch.Tensor = None, chunk_waves: int = 8):
         """Host-buffer entry point: positions / directions are (pinned) CPU tensors [N,3]; rgb [N,3] and density [N,1]
-        come back in (pinned) CPU tensors.  The batch is cut into chunks of `chunk_waves` full waves of the persistent
-        kernel (148 SMs x 128 samples) and pipelined over three streams -- H2D of chunk i+1, the fused kernel on chunk i
-        and D2H of chunk i-1 overlap -- so the PCIe copies hide behind the compute instead of adding to it."""
+        come back in (pinned) CPU tensors.  `cnc_field_fwd_host` cuts the batch into chunks of 1, 2, 4, .. `chunk_waves` ..
+        4, 2, 1 full waves of the persistent kernel (148 SMs x 128 samples) and pipelines them over three streams -- H2D
+        of chunk i+1, the fused kernel on chunk i and D2H of chunk i-1 overlap -- so that only a short first upload and
+        last download are exposed."""
         if not self.fused_available():
             raise RuntimeError("forward_host needs the fused kernel (CNC product layout)")
         dev = self.aabb.device
@@ -342,31 +343,17 @@ class NGPRadianceField_mygrid_2D3D(nn.Module):
             self._aabb_host = (ctypes.c_float * 6)(*self.aabb.detach().cpu().tolist())
             self._aabb_src = (self.aabb.data_ptr(), self.aabb._version)
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        step = max(1, chunk_waves) * n_sm * 128
         cur = torch.cuda.current_stream(dev)
-        s_in, s_out = st["s_in"], st["s_out"]
-        s_in.wait_stream(cur)      # staging buffers may still be read by earlier work on the caller's stream
-        s_out.wait_stream(cur)
-        L = lib()
-        for lo in range(0, n, step):
-            hi = min(n, lo + step)
-            with torch.cuda.stream(s_in):
-                st["pos"][lo:hi].copy_(pos_h[lo:hi], non_blocking=True)
-                st["dir"][lo:hi].copy_(dir_h[lo:hi], non_blocking=True)
-                ev_in = torch.cuda.Event()
-                ev_in.record(s_in)
-            cur.wait_event(ev_in)
-            check(L.cnc_field_fwd(ptr(st["pos"][lo:hi]), ptr(st["dir"][lo:hi]), ctypes.addressof(self._aabb_host),
-                                  *[ptr(b) for b in bits], ptr(mb.encoding_xyz.offsets_list), ptr(mb.encoding_xyz.resolutions_list),
-                                  ptr(mb.encoding_xy.offsets_list), ptr(mb.encoding_xy.resolutions_list), ptr(blob),
-                                  ptr(st["sig"][lo:hi]), ptr(st["rgb"][lo:hi]), None, hi - lo, cur.cuda_stream))
-            ev_k = torch.cuda.Event()
-            ev_k.record(cur)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_k)
-                out_rgb[lo:hi].copy_(st["rgb"][lo:hi], non_blocking=True)
-                out_sigma[lo:hi, 0].copy_(st["sig"][lo:hi], non_blocking=True)
-        cur.wait_stream(s_out)
+        if not (pos_h.is_pinned() and dir_h.is_pinned() and out_rgb.is_pinned() and out_sigma.is_pinned()):
+            raise RuntimeError("forward_host needs pinned host tensors (the copies are asynchronous)")
+        if not (out_rgb.is_contiguous() and out_sigma.is_contiguous()):
+            raise RuntimeError("forward_host: output tensors must be contiguous")
+        check(lib().cnc_field_fwd_host(pos_h.data_ptr(), dir_h.data_ptr(), ctypes.addressof(self._aabb_c()), *[ptr(b) for b in bits],
+                                       ptr(mb.encoding_xyz.offsets_list), ptr(mb.encoding_xyz.resolutions_list),
+                                       ptr(mb.encoding_xy.offsets_list), ptr(mb.encoding_xy.resolutions_list), ptr(blob),
+                                       out_sigma.data_ptr(), out_rgb.data_ptr(), n, ptr(st["pos"]), ptr(st["dir"]), ptr(st["sig"]),
+                                       ptr(st["rgb"]), n_sm * 128, max(1, chunk_waves), cur.cuda_stream, st["s_in"].cuda_stream,
+                                       st["s_out"].cuda_stream))
         return out_rgb, out_sigma
 
     def _aabb_c(self):

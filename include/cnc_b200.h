@@ -171,6 +171,18 @@ int cnc_field_fwd(const float *pos, const float *dirs, const float *aabb6_host,
                   const uint8_t *bits_yz, const int32_t *offsets3, const int32_t *resolutions3,
                   const int32_t *offsets2, const int32_t *resolutions2, const float *blob,
                   float *sigma, float *rgb, float *geo, uint32_t N, cnc_stream_t stream);
+/* Host-buffer forward (the call a host-side caller of the reference makes: positions and directions in, colours and
+ * densities out, all in host memory -- pinned, for the copies to be asynchronous): chunks of 1, 2, 4, .. max_chunk_waves
+ * .. 4, 2, 1 waves (wave_samples = SMs x 128 keeps whole waves of the persistent kernel) are uploaded on s_in, evaluated
+ * on s_compute and downloaded on s_out concurrently, so that only a short first upload and last download are exposed; d_pos / d_dirs / d_rgb [N,3], d_sigma [N] are device staging buffers owned by the caller.  Returns
+ * after everything is enqueued; s_compute completes after the last download. */
+int cnc_field_fwd_host(const float *pos_host, const float *dirs_host, const float *aabb6_host,
+                       const uint8_t *bits_xyz, const uint8_t *bits_xy, const uint8_t *bits_xz,
+                       const uint8_t *bits_yz, const int32_t *offsets3, const int32_t *resolutions3,
+                       const int32_t *offsets2, const int32_t *resolutions2, const float *blob,
+                       float *sigma_host, float *rgb_host, uint32_t N, float *d_pos, float *d_dirs,
+                       float *d_sigma, float *d_rgb, uint32_t wave_samples, uint32_t max_chunk_waves,
+                       cnc_stream_t s_compute, cnc_stream_t s_in, cnc_stream_t s_out);
 /* Training forward: the same kernel, additionally leaving what the backward pass of ngp.py:514-566 needs in HBM as
  * the values go by (no recomputation, no extra pass): x0 [N,256] = input of Linear(255,160) (192 grid features |
  * x, sin/cos | a constant 1 in the pad column), h1 / h3 / h4 [N,160] = the ReLU outputs, geo [N,79]; all 16-byte aligned, all required. */
