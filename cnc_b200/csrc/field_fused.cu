@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
         const uint32_t total = my_tiles * CPT;
         for (uint32_t G = 0; G < total; G++) {
             const uint32_t s = G % NSTAGE, use = G / NSTAGE;
-            if (use > 0) mbar_wait_spin(b_empty(s), (use - 1) & 1u);
+            if (use > 0) mbar_wait(b_empty(s), (use - 1) & 1u);
             uint32_t ofs, bytes;
             chunk_meta((int)(G % CPT), ofs, bytes);
             if (a.dbg != nullptr && blockIdx.x == 0 && G / CPT == 1 && elect_one()) a.dbg[64 + G % CPT] = clock64();
