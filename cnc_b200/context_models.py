@@ -99,6 +99,35 @@ class _cnt_np_embed(Function):
         return None, g, None, None, None
 
 
+class _cnt_np_embed3(Function):
+    """The three vote-fraction planes of the dimension-wise context at once (3 x `_cnt_np_embed` over
+    `get_idx_coords2`, utils_bpp_acc.py:27-75,498-530), on `cnc_vote3_fwd / cnc_vote3_bwd`: the voxel list is replaced
+    by its closed form in the occupancy grid, the atomics by per-cell / per-row ownership."""
+
+    @staticmethod
+    def forward(ctx, embeddings, vx, pts_by_row, seg, resolution, hashmap_size):
+        embeddings = embeddings.contiguous()
+        F = embeddings.shape[-1]
+        bits = _backend.sign_pack(embeddings.detach())
+        s = resolution - 2
+        outs = [torch.empty(s, s, F, 2, device=embeddings.device) for _ in range(3)]
+        check(lib().cnc_vote3_fwd(ptr(vx), vx.shape[-1], ptr(bits), resolution, F, hashmap_size, *[ptr(o) for o in outs], stream()))
+        sums = [o.sum(dim=-1, keepdim=True) + 1e-6 for o in outs]
+        ctx.save_for_backward(bits, vx, pts_by_row, seg, *sums)
+        ctx.dims = [resolution, F, hashmap_size, tuple(embeddings.shape)]
+        return tuple(o / sm for o, sm in zip(outs, sums))
+
+    @staticmethod
+    def backward(ctx, g_xy, g_xz, g_yz):
+        bits, vx, pts_by_row, seg, s_xy, s_xz, s_yz = ctx.saved_tensors
+        resolution, F, hashmap_size, shape = ctx.dims
+        g = torch.zeros(shape, device=bits.device)
+        check(lib().cnc_vote3_bwd(ptr(pts_by_row), ptr(seg), ptr(vx), vx.shape[-1], ptr(bits), resolution, F, hashmap_size,
+                                  ptr(s_xy), ptr(s_xz), ptr(s_yz), ptr(g_xy.contiguous()), ptr(g_xz.contiguous()),
+                                  ptr(g_yz.contiguous()), ptr(g), stream()))
+        return g, None, None, None, None, None
+
+
 class align_and_pack(Function):
     """ragged -> padded [N, M, F] (utils_bpp_acc.py:113-139) on cnc_align_pack_fwd/bwd."""
 
@@ -299,6 +328,35 @@ class CNC_context_models(nn.Module):
         frac = nnf.pad(frac.permute(2, 0, 1).unsqueeze(0), pad=[1, 1, 1, 1]).squeeze(0).permute(1, 2, 0).contiguous()
         return frac.view(-1, self.n_features)
 
+    def _vote3_ready(self):
+        """the fused vote path needs F == 8, the finest level's inverse hash table with every row present (row index ==
+        position) and an occupancy grid that divides the finest grid"""
+        if self.n_features != 8 or self.Pg_level != self.n_levels or (self.res[-1] - 2) % self.binary_vxl_len or self.binary_vxl_len > 128:
+            return False
+        ok = getattr(self, "_vote3_ok", None)
+        if ok is None:
+            rows = self.unique_value_list[-1]
+            T = self.offs[-1] - self.offs[-2]
+            ok = self._vote3_ok = bool(rows.numel() == T and torch.equal(rows, torch.arange(T, device=rows.device)))
+        return ok
+
+    def get_pn_embed_frac3(self, embeddings_3D_q, binary_vxl):
+        """{"xy","xz","yz"} -> +1 vote fraction plane, zero padded to [res*res, F]: what `get_idx_coords2` followed by
+        three `get_pn_embed_frac` calls compute (utils_bpp_acc.py:498-530), without the voxel list."""
+        vx = binary_vxl.squeeze(0)
+        vx = (vx if vx.dtype in (torch.bool, torch.uint8) else vx != 0).contiguous()
+        if not (self._vote3_ready() and vx.shape[-1] == self.binary_vxl_len):
+            idx = self.get_idx_coords2(binary_vxl)
+            return {a: self.get_pn_embed_frac(embeddings_3D_q, idx, axis=a) for a in ("xy", "xz", "yz")}
+        res = self.res[-1]
+        fr = _cnt_np_embed3.apply(embeddings_3D_q, vx, self.pos_grid_sorted_list[-1], self.unique_count_cumsum_list[-1], res,
+                                  self.offs[-1] - self.offs[-2])
+        out = {}
+        for a, f in zip(("xy", "xz", "yz"), fr):
+            f = nnf.pad(f[..., 0].permute(2, 0, 1).unsqueeze(0), pad=[1, 1, 1, 1]).squeeze(0).permute(1, 2, 0).contiguous()
+            out[a] = f.view(-1, self.n_features)
+        return out
+
     @staticmethod
     def _planes(binary_vxl):
         b = binary_vxl.squeeze(0)
@@ -438,15 +496,16 @@ class CNC_context_models(nn.Module):
         """Rate term of the training loss: (bits per parameter, MB).  utils_bpp_acc.py:533-706"""
         pq = {k: self.get_STE_params(E) for k, E in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz), ("xyz", Encoding_xyz))}
         refresh = step % self.step_update == 0 or self.idx_coords2_tmp is None
-        if refresh:
-            self.idx_coords2_tmp = self.get_idx_coords2(binary_vxl)
+        if refresh:   # the reference caches the voxel list for step_update steps (:541-543): keep the occupancy it stands for
+            self.idx_coords2_tmp = binary_vxl.clone()
         planes = self._planes(binary_vxl)
         if refresh:
             self.batched_inputs_list = {}
         ttl_bit_sum, ttl_num_sum = 0, 0
         finest = pq["xyz"][self.offs[-2]:self.offs[-1]]
+        pns = self.get_pn_embed_frac3(finest, self.idx_coords2_tmp) if self.use_dimension_wise else {}
         for axis, Enc in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz)):
-            pn = self.get_pn_embed_frac(finest, self.idx_coords2_tmp, axis=axis) if self.use_dimension_wise else None
+            pn = pns.get(axis)
             for n in range(self.n_levels_2D):
                 Pg_n, bit_n, _ = self.get_BiRF_wentropy_leveln(pq[axis], n, self.offs_2D)
                 if not (n in self.skip_levels_2D or n >= self.Pg_level_2D):
@@ -549,11 +608,11 @@ class CNC_context_models(nn.Module):
                 ttl_bit += torch.sum(self.entropy_model(values_q, ps))
                 emit(f"{filename_prefix}_3D{n}_{sn}.b", values_q.reshape(-1), ps.reshape(-1))
             flush()
-        idx_coords2 = self.get_idx_coords2(binary_vxl)
         planes = self._planes(binary_vxl)
         finest = pq["xyz"][self.offs[-2]:self.offs[-1]]
+        pns = self.get_pn_embed_frac3(finest, binary_vxl) if self.use_dimension_wise else {}
         for axis, Enc in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz)):
-            pn = self.get_pn_embed_frac(finest, idx_coords2, axis=axis) if self.use_dimension_wise else None
+            pn = pns.get(axis)
             for n in range(self.n_levels_2D):
                 Pg_n, bit_n, _ = self.get_BiRF_wentropy_leveln(pq[axis], n, self.offs_2D)
                 Pgs_dict[axis + str(n)] = Pg_n
@@ -619,12 +678,11 @@ class CNC_context_models(nn.Module):
                 rows_l.append((self.unique_value_list[n][lo:hi] + self.offs[n])[mask_exist])
             for sout, rows in zip(decode(names, ps_l), rows_l):
                 params_q_xyz_rec[rows] = sout.view(-1, F)
-        idx_coords2 = self.get_idx_coords2(binary_vxl)
         planes = self._planes(binary_vxl)
         finest = params_q_xyz_rec[self.offs[-2]:self.offs[-1]]
         recs = {"xy": params_q_xy_rec, "xz": params_q_xz_rec, "yz": params_q_yz_rec}
         axes = (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz))
-        pns = {a: (self.get_pn_embed_frac(finest, idx_coords2, axis=a) if self.use_dimension_wise else None) for a, _ in axes}
+        pns = self.get_pn_embed_frac3(finest, binary_vxl) if self.use_dimension_wise else {a: None for a, _ in axes}
         for n in range(self.n_levels_2D):   # the three planes are independent of each other: one launch per level
             names, ps_l, where = [], [], []
             for axis, Enc in axes:

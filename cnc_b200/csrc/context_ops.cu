@@ -128,6 +128,136 @@ vote_bwd_kernel(const int16_t *__restrict__ pts, const float *__restrict__ table
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K4 / K5 without the voxel list and without atomics (cnc_vote3_fwd / cnc_vote3_bwd).
+// The reference enumerates every finest-level voxel inside an occupied occupancy cell plus a one-voxel halo
+// (get_idx_coords2, utils_bpp_acc.py:498-512: c = occ * t + k + 1, k in [-1, t], made unique) and lets each voxel
+// atomically add to its (u, v) plane cell.  Membership of voxel c in that list is a closed form of the occupancy grid:
+// per dimension the candidate cells are o in [ceil((c - t - 1) / t), floor(c / t)] (one or two), and c is listed iff
+// one of the <= 8 candidate cells is occupied.
+//   forward:  one thread per plane cell (u, v) walks the third axis, ORs the <= 4 candidate occupancy columns into a
+//             128-bit mask once, and counts +1 / -1 votes per feature in registers -> plain stores, exact integers;
+//   backward: one warp per table row walks the row's voxels in the inverse hash table (lanes stride, coalesced),
+//             gathers d(fraction)/d(vote) of all three planes and reduces with a fixed shuffle tree -> plain stores.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void vote_cand(uint32_t c, uint32_t t, uint32_t Rb, uint32_t &o_lo, uint32_t &o_hi) {
+    o_hi = c / t;
+    o_lo = c > t + 1u ? (c - t - 2u) / t + 1u : 0u;     // ceil((c - t - 1) / t)
+    if (o_hi > Rb - 1u) o_hi = Rb - 1u;                  // (o_lo > o_hi -> no candidate)
+}
+
+__global__ void __launch_bounds__(128)
+vote3_fwd_kernel(const uint8_t *__restrict__ vxl, uint32_t Rb, const uint8_t *__restrict__ bits, uint32_t res, uint32_t T,
+                 float *__restrict__ out_xy, float *__restrict__ out_xz, float *__restrict__ out_yz) {
+    const uint32_t s = res - 2u, t = s / Rb, axis = blockIdx.z;
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x + 1u, u = blockIdx.y + 1u;   // plane cell, 1-based like the coords
+    if (v > s) return;
+    // axis 0: (u, v, w) = (x, y, z); axis 1: (x, z, y); axis 2: (y, z, x)   (gridencoder.cu:902-906)
+    const uint32_t du = axis == 2 ? 1u : 0u, dv = axis == 0 ? 1u : 2u, dw = 3u - du - dv;
+    const uint32_t stride[3] = {Rb * Rb, Rb, 1u};
+    uint32_t ulo, uhi, vlo, vhi;
+    vote_cand(u, t, Rb, ulo, uhi);
+    vote_cand(v, t, Rb, vlo, vhi);
+    uint32_t M[4] = {0u, 0u, 0u, 0u};   // occupancy along w of the candidate columns, ORed (Rb <= 128)
+    for (uint32_t ou = ulo; ou <= uhi; ou++)
+        for (uint32_t ov = vlo; ov <= vhi; ov++) {
+            const uint8_t *col = vxl + (size_t)ou * stride[du] + (size_t)ov * stride[dv];
+            for (uint32_t ow = 0; ow < Rb; ow++)
+                if (col[(size_t)ow * stride[dw]]) M[ow >> 5] |= 1u << (ow & 31u);
+        }
+    uint32_t pos[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, cnt = 0u;
+    if ((M[0] | M[1] | M[2] | M[3]) != 0u) {
+        for (uint32_t w = 1u; w <= s; w++) {
+            uint32_t wlo, whi;
+            vote_cand(w, t, Rb, wlo, whi);
+            bool member = false;
+            for (uint32_t ow = wlo; ow <= whi; ow++) member |= ((M[ow >> 5] >> (ow & 31u)) & 1u) != 0u;
+            if (!member) continue;
+            uint32_t c[3];
+            c[du] = u; c[dv] = v; c[dw] = w;
+            const uint32_t sb = __ldg(bits + grid_row<3>(c, T, res));
+#pragma unroll
+            for (int ch = 0; ch < 8; ch++) pos[ch] += (sb >> ch) & 1u;
+            cnt++;
+        }
+    }
+    float *out = axis == 0 ? out_xy : (axis == 1 ? out_xz : out_yz);
+    float4 *o = reinterpret_cast<float4 *>(out + ((size_t)(u - 1u) * s + (v - 1u)) * 16u);
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        o[q] = make_float4((float)pos[2 * q], (float)(cnt - pos[2 * q]), (float)pos[2 * q + 1], (float)(cnt - pos[2 * q + 1]));
+}
+
+struct Vote3BwdArgs {
+    const int16_t *pts;       // inverse hash table of the level: voxel coords grouped by row
+    const int64_t *seg;       // [T+1] running voxel count per row
+    const uint8_t *vxl;
+    const uint8_t *bits;      // sign bytes of the level's rows
+    const float *sum[3];      // pn_sum  [s,s,8]   per axis (xy, xz, yz)
+    const float *grad[3];     // d loss / d fraction [s,s,8,2]
+    float *grad_table;        // [T,8]
+    uint32_t Rb, res, T;
+};
+
+__global__ void __launch_bounds__(256) vote3_bwd_kernel(const Vote3BwdArgs a) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= a.T) return;
+    const uint32_t s = a.res - 2u, t = s / a.Rb;
+    const int64_t v0 = __ldg(a.seg + row), v1 = __ldg(a.seg + row + 1);
+    float accp[8], accn[8];   // sums of gv * grad over the row's voxels: +1 votes / -1 votes
+#pragma unroll
+    for (int ch = 0; ch < 8; ch++) accp[ch] = accn[ch] = 0.f;
+    for (int64_t i = v0 + lane; i < v1; i += 32) {
+        const uint32_t c[3] = {(uint32_t)(int32_t)__ldg(a.pts + i * 3), (uint32_t)(int32_t)__ldg(a.pts + i * 3 + 1), (uint32_t)(int32_t)__ldg(a.pts + i * 3 + 2)};
+        bool ok = true;
+        uint32_t lo[3], hi[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            ok = ok && c[d] != 0u && c[d] < a.res - 1u;   // gridencoder.cu:895-898
+            vote_cand(c[d], t, a.Rb, lo[d], hi[d]);
+        }
+        if (!ok) continue;
+        bool member = false;
+        for (uint32_t o0 = lo[0]; o0 <= hi[0]; o0++)
+            for (uint32_t o1 = lo[1]; o1 <= hi[1]; o1++)
+                for (uint32_t o2 = lo[2]; o2 <= hi[2]; o2++) member |= a.vxl[((size_t)o0 * a.Rb + o1) * a.Rb + o2] != 0;
+        if (!member) continue;
+#pragma unroll
+        for (int ax = 0; ax < 3; ax++) {
+            const uint32_t u = ax == 2 ? c[1] : c[0], v = ax == 0 ? c[1] : c[2];
+            const size_t cell = (size_t)(u - 1u) * s + (v - 1u);
+            const float4 *sm = reinterpret_cast<const float4 *>(a.sum[ax] + cell * 8u);
+            const float4 *gr = reinterpret_cast<const float4 *>(a.grad[ax] + cell * 16u);
+            const float4 s0 = __ldg(sm), s1 = __ldg(sm + 1);
+            const float gv[8] = {__frcp_rn(s0.x), __frcp_rn(s0.y), __frcp_rn(s0.z), __frcp_rn(s0.w),
+                                 __frcp_rn(s1.x), __frcp_rn(s1.y), __frcp_rn(s1.z), __frcp_rn(s1.w)};   // 1 / sum (:1012)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float4 g = __ldg(gr + q);      // (pos, neg) of channels 2q, 2q+1
+                accp[2 * q] = __fmaf_rn(gv[2 * q], g.x, accp[2 * q]);
+                accn[2 * q] = __fmaf_rn(gv[2 * q], g.y, accn[2 * q]);
+                accp[2 * q + 1] = __fmaf_rn(gv[2 * q + 1], g.z, accp[2 * q + 1]);
+                accn[2 * q + 1] = __fmaf_rn(gv[2 * q + 1], g.w, accn[2 * q + 1]);
+            }
+        }
+    }
+    const uint32_t sb = __ldg(a.bits + row);
+    float g[8];
+#pragma unroll
+    for (int ch = 0; ch < 8; ch++) g[ch] = ((sb >> ch) & 1u) ? accp[ch] : -accn[ch];   // d fraction / d vote, sign of the row's own value
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1)
+#pragma unroll
+        for (int ch = 0; ch < 8; ch++) g[ch] = __fadd_rn(g[ch], __shfl_xor_sync(0xFFFFFFFFu, g[ch], sh));
+    if (lane < 8) {
+        float m = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 8; ch++) if (ch == (int)lane) m = g[ch];
+        a.grad_table[(size_t)row * 8u + lane] = m;
+    }
+}
+
 static inline uint32_t gs_blocks(int64_t total) {
     const int64_t b = (total + 255) / 256;
     const int64_t cap = 148ll * 32;
@@ -195,6 +325,36 @@ int cnc_vote_planes_bwd(const int16_t *pts, const float *table, const float *out
     if (!pts || !table || !out_sum || !grad || !grad_table || axis > 2 || resolution < 3) { set_error("vote_planes_bwd: bad argument"); return CNC_EINVAL; }
     vote_bwd_kernel<<<div_up(N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(pts, table, out_sum, grad, grad_table, N, resolution, F, hashmap_size, axis);
     return check_launch("vote_planes_bwd");
+}
+
+int cnc_vote3_fwd(const uint8_t *binary_vxl, uint32_t Rb, const uint8_t *sign_bits, uint32_t resolution, uint32_t F,
+                  uint32_t hashmap_size, float *out_xy, float *out_xz, float *out_yz, cnc_stream_t stream) {
+    if (!binary_vxl || !sign_bits || !out_xy || !out_xz || !out_yz) { set_error("vote3_fwd: null pointer"); return CNC_EINVAL; }
+    if (F != 8 || Rb == 0 || Rb > 128 || resolution < 3 || (resolution - 2) % Rb != 0) {
+        set_error("vote3_fwd: needs F == 8, Rb <= 128 and (resolution - 2) a multiple of Rb");
+        return CNC_ENOTSUP;
+    }
+    const uint32_t s = resolution - 2;
+    dim3 grid(div_up(s, 128), s, 3);
+    vote3_fwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(binary_vxl, Rb, sign_bits, resolution, hashmap_size, out_xy, out_xz, out_yz);
+    return check_launch("vote3_fwd");
+}
+
+int cnc_vote3_bwd(const int16_t *pts_by_row, const int64_t *seg, const uint8_t *binary_vxl, uint32_t Rb, const uint8_t *sign_bits,
+                  uint32_t resolution, uint32_t F, uint32_t hashmap_size, const float *sum_xy, const float *sum_xz,
+                  const float *sum_yz, const float *grad_xy, const float *grad_xz, const float *grad_yz, float *grad_table,
+                  cnc_stream_t stream) {
+    if (!pts_by_row || !seg || !binary_vxl || !sign_bits || !sum_xy || !sum_xz || !sum_yz || !grad_xy || !grad_xz || !grad_yz || !grad_table) {
+        set_error("vote3_bwd: null pointer");
+        return CNC_EINVAL;
+    }
+    if (F != 8 || Rb == 0 || Rb > 128 || resolution < 3 || (resolution - 2) % Rb != 0) {
+        set_error("vote3_bwd: needs F == 8, Rb <= 128 and (resolution - 2) a multiple of Rb");
+        return CNC_ENOTSUP;
+    }
+    Vote3BwdArgs a{pts_by_row, seg, binary_vxl, sign_bits, {sum_xy, sum_xz, sum_yz}, {grad_xy, grad_xz, grad_yz}, grad_table, Rb, resolution, hashmap_size};
+    vote3_bwd_kernel<<<div_up((uint64_t)hashmap_size * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("vote3_bwd");
 }
 
 }  // extern "C"

@@ -93,6 +93,21 @@ int cnc_vote_planes_bwd(const int16_t *pts, const float *table, const float *out
                         const float *grad, float *grad_table, uint32_t N, uint32_t resolution,
                         uint32_t F, uint32_t hashmap_size, uint32_t axis, cnc_stream_t stream);
 
+/* The same vote planes for all three axes at once, from the occupancy grid instead of the enumerated voxel list and
+ * without atomics (what get_idx_coords2 + 3 x cnt_np_embed compute, utils_bpp_acc.py:498-530): a finest-level voxel c is
+ * in the reference's list iff one of the <= 8 occupancy cells o with o*t <= c <= o*t + t + 1 (t = (res-2)/Rb) is
+ * occupied.  sign_bits: cnc_sign_pack of the level's rows (vote +1 <=> value > 0.9 <=> sign bit, the table is +-1).
+ * out_* [(res-2),(res-2),8,2] are overwritten with exact integer counts.  cnc_vote3_bwd is the matching backward
+ * (gridencoder.cu:1047-1087 summed over the three planes): pts_by_row / seg = the level's inverse hash table (voxel
+ * coords grouped by table row, [T+1] running counts), grad_table [T,8] is overwritten.  F == 8, Rb <= 128. */
+int cnc_vote3_fwd(const uint8_t *binary_vxl, uint32_t Rb, const uint8_t *sign_bits, uint32_t resolution,
+                  uint32_t F, uint32_t hashmap_size, float *out_xy, float *out_xz, float *out_yz,
+                  cnc_stream_t stream);
+int cnc_vote3_bwd(const int16_t *pts_by_row, const int64_t *seg, const uint8_t *binary_vxl, uint32_t Rb,
+                  const uint8_t *sign_bits, uint32_t resolution, uint32_t F, uint32_t hashmap_size,
+                  const float *sum_xy, const float *sum_xz, const float *sum_yz, const float *grad_xy,
+                  const float *grad_xz, const float *grad_yz, float *grad_table, cnc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Occupancy query of voxels.
  * replaces: pack_and_align.query_mask_3D / query_mask_3D_qlist   my_cuda_backen/aligner.cpp:37-70,

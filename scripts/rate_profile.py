@@ -21,4 +21,4 @@ t = time.perf_counter(); step(16); torch.cuda.synchronize(); print(f"refresh ste
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for i in range(3): step(i + 33)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+print(prof.key_averages().table(sort_by=os.environ.get("SORT", "cuda_time_total"), row_limit=40, max_name_column_width=60))

@@ -180,3 +180,27 @@ def test_container_roundtrip_feeds_the_decoder(cuda):
     ref = cm.decode_binary_vxl_mixPg_3D2D(*encs, *[torch.ones_like(e.params) for e in encs], vxl, Pgs, "c", streams=streams)
     for a, b in zip(out, ref):
         assert torch.equal(a, b)
+
+
+def test_fused_vote_planes_equal_the_list_based_kernels(cuda):
+    """cnc_vote3_fwd / cnc_vote3_bwd (occupancy closed form, no voxel list, no atomics) against get_idx_coords2 +
+    3 x cnt_np_embed(_backward): vote counts are exact integers -> identical planes; the gradient w.r.t. the finest
+    level agrees to fp32 summation order."""
+    cm, encs, vxl = make(cuda, **SMALL)
+    assert cm._vote3_ready()
+    finest = cm.get_STE_params(encs[0]).detach()[cm.offs[-2]:cm.offs[-1]].clone().requires_grad_(True)
+    idx = cm.get_idx_coords2(vxl)
+    old = {a: cm.get_pn_embed_frac(finest, idx, axis=a) for a in ("xy", "xz", "yz")}
+    g = torch.Generator(device="cpu").manual_seed(4)
+    w = {a: torch.randn(old[a].shape, generator=g).to(cuda) for a in old}
+    sum(((old[a] * w[a]).sum() for a in old)).backward()
+    g_old = finest.grad.clone()
+    finest.grad = None
+    new = cm.get_pn_embed_frac3(finest, vxl)
+    for a in old:
+        assert torch.equal(new[a], old[a]), a
+    sum(((new[a] * w[a]).sum() for a in new)).backward()
+    g_new = finest.grad
+    assert torch.equal(g_new != 0, g_old != 0)
+    torch.testing.assert_close(g_new, g_old, rtol=1e-4, atol=1e-6 * float(g_old.abs().max()))
+    assert float(g_old.abs().max()) > 0
