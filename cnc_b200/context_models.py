@@ -122,9 +122,9 @@ class _cnt_np_embed3(Function):
         bits, vx, pts_by_row, seg, s_xy, s_xz, s_yz = ctx.saved_tensors
         resolution, F, hashmap_size, shape = ctx.dims
         g = torch.zeros(shape, device=bits.device)
+        gs = [(gg / sm).contiguous() for gg, sm in ((g_xy, s_xy), (g_xz, s_xz), (g_yz, s_yz))]   # 1 / sum folded in (:1012)
         check(lib().cnc_vote3_bwd(ptr(pts_by_row), ptr(seg), ptr(vx), vx.shape[-1], ptr(bits), resolution, F, hashmap_size,
-                                  ptr(s_xy), ptr(s_xz), ptr(s_yz), ptr(g_xy.contiguous()), ptr(g_xz.contiguous()),
-                                  ptr(g_yz.contiguous()), ptr(g), stream()))
+                                  ptr(gs[0]), ptr(gs[1]), ptr(gs[2]), ptr(g), stream()))
         return g, None, None, None, None, None
 
 

@@ -193,8 +193,7 @@ struct Vote3BwdArgs {
     const int64_t *seg;       // [T+1] running voxel count per row
     const uint8_t *vxl;
     const uint8_t *bits;      // sign bytes of the level's rows
-    const float *sum[3];      // pn_sum  [s,s,8]   per axis (xy, xz, yz)
-    const float *grad[3];     // d loss / d fraction [s,s,8,2]
+    const float *grad[3];     // (d loss / d fraction) / vote sum, [s,s,8,2] per axis (xy, xz, yz)
     float *grad_table;        // [T,8]
     uint32_t Rb, res, T;
 };
@@ -227,18 +226,16 @@ __global__ void __launch_bounds__(256) vote3_bwd_kernel(const Vote3BwdArgs a) {
         for (int ax = 0; ax < 3; ax++) {
             const uint32_t u = ax == 2 ? c[1] : c[0], v = ax == 0 ? c[1] : c[2];
             const size_t cell = (size_t)(u - 1u) * s + (v - 1u);
-            const float4 *sm = reinterpret_cast<const float4 *>(a.sum[ax] + cell * 8u);
+            // grad[ax] holds d loss / d fraction already divided by the cell's vote sum (1 / sum, :1012, folded by the caller:
+            // one 64-byte read per voxel and plane instead of 96)
             const float4 *gr = reinterpret_cast<const float4 *>(a.grad[ax] + cell * 16u);
-            const float4 s0 = __ldg(sm), s1 = __ldg(sm + 1);
-            const float gv[8] = {__frcp_rn(s0.x), __frcp_rn(s0.y), __frcp_rn(s0.z), __frcp_rn(s0.w),
-                                 __frcp_rn(s1.x), __frcp_rn(s1.y), __frcp_rn(s1.z), __frcp_rn(s1.w)};   // 1 / sum (:1012)
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const float4 g = __ldg(gr + q);      // (pos, neg) of channels 2q, 2q+1
-                accp[2 * q] = __fmaf_rn(gv[2 * q], g.x, accp[2 * q]);
-                accn[2 * q] = __fmaf_rn(gv[2 * q], g.y, accn[2 * q]);
-                accp[2 * q + 1] = __fmaf_rn(gv[2 * q + 1], g.z, accp[2 * q + 1]);
-                accn[2 * q + 1] = __fmaf_rn(gv[2 * q + 1], g.w, accn[2 * q + 1]);
+                accp[2 * q] = __fadd_rn(accp[2 * q], g.x);
+                accn[2 * q] = __fadd_rn(accn[2 * q], g.y);
+                accp[2 * q + 1] = __fadd_rn(accp[2 * q + 1], g.z);
+                accn[2 * q + 1] = __fadd_rn(accn[2 * q + 1], g.w);
             }
         }
     }
@@ -341,10 +338,9 @@ int cnc_vote3_fwd(const uint8_t *binary_vxl, uint32_t Rb, const uint8_t *sign_bi
 }
 
 int cnc_vote3_bwd(const int16_t *pts_by_row, const int64_t *seg, const uint8_t *binary_vxl, uint32_t Rb, const uint8_t *sign_bits,
-                  uint32_t resolution, uint32_t F, uint32_t hashmap_size, const float *sum_xy, const float *sum_xz,
-                  const float *sum_yz, const float *grad_xy, const float *grad_xz, const float *grad_yz, float *grad_table,
-                  cnc_stream_t stream) {
-    if (!pts_by_row || !seg || !binary_vxl || !sign_bits || !sum_xy || !sum_xz || !sum_yz || !grad_xy || !grad_xz || !grad_yz || !grad_table) {
+                  uint32_t resolution, uint32_t F, uint32_t hashmap_size, const float *grad_xy, const float *grad_xz,
+                  const float *grad_yz, float *grad_table, cnc_stream_t stream) {
+    if (!pts_by_row || !seg || !binary_vxl || !sign_bits || !grad_xy || !grad_xz || !grad_yz || !grad_table) {
         set_error("vote3_bwd: null pointer");
         return CNC_EINVAL;
     }
@@ -352,7 +348,7 @@ int cnc_vote3_bwd(const int16_t *pts_by_row, const int64_t *seg, const uint8_t *
         set_error("vote3_bwd: needs F == 8, Rb <= 128 and (resolution - 2) a multiple of Rb");
         return CNC_ENOTSUP;
     }
-    Vote3BwdArgs a{pts_by_row, seg, binary_vxl, sign_bits, {sum_xy, sum_xz, sum_yz}, {grad_xy, grad_xz, grad_yz}, grad_table, Rb, resolution, hashmap_size};
+    Vote3BwdArgs a{pts_by_row, seg, binary_vxl, sign_bits, {grad_xy, grad_xz, grad_yz}, grad_table, Rb, resolution, hashmap_size};
     vote3_bwd_kernel<<<div_up((uint64_t)hashmap_size * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return check_launch("vote3_bwd");
 }

@@ -99,14 +99,16 @@ int cnc_vote_planes_bwd(const int16_t *pts, const float *table, const float *out
  * occupied.  sign_bits: cnc_sign_pack of the level's rows (vote +1 <=> value > 0.9 <=> sign bit, the table is +-1).
  * out_* [(res-2),(res-2),8,2] are overwritten with exact integer counts.  cnc_vote3_bwd is the matching backward
  * (gridencoder.cu:1047-1087 summed over the three planes): pts_by_row / seg = the level's inverse hash table (voxel
- * coords grouped by table row, [T+1] running counts), grad_table [T,8] is overwritten.  F == 8, Rb <= 128. */
+ * coords grouped by table row, [T+1] running counts); grad_* [(res-2),(res-2),8,2] = d loss / d fraction already
+ * divided by the cell's vote sum (the 1/sum of :1012, folded by the caller); grad_table [T,8] is overwritten.
+ * F == 8, Rb <= 128. */
 int cnc_vote3_fwd(const uint8_t *binary_vxl, uint32_t Rb, const uint8_t *sign_bits, uint32_t resolution,
                   uint32_t F, uint32_t hashmap_size, float *out_xy, float *out_xz, float *out_yz,
                   cnc_stream_t stream);
 int cnc_vote3_bwd(const int16_t *pts_by_row, const int64_t *seg, const uint8_t *binary_vxl, uint32_t Rb,
                   const uint8_t *sign_bits, uint32_t resolution, uint32_t F, uint32_t hashmap_size,
-                  const float *sum_xy, const float *sum_xz, const float *sum_yz, const float *grad_xy,
-                  const float *grad_xz, const float *grad_yz, float *grad_table, cnc_stream_t stream);
+                  const float *grad_xy, const float *grad_xz, const float *grad_yz, float *grad_table,
+                  cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Occupancy query of voxels.
