@@ -38,17 +38,66 @@ FLOP_PER_SAMPLE_FWD = 189760
 
 
 class Clocks:
-    """nvidia-smi sampler running during the timed region (B200_PROFILING.md 'clocks line')."""
+    """SM clock and throttle-reason sampler running during the timed region (B200_PROFILING.md 'clocks line').
+    NVML is polled from a thread every ~2 ms (the timed region of the forward bench is only a few milliseconds, shorter
+    than one period of `nvidia-smi -lms`); nvidia-smi is the fallback when pynvml is missing."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.stop, self.t, self.source = index, [], None, False, None, None
+
+    def _handle(self):
+        import pynvml as N
+
+        N.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return N, N.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            return N, N.nvmlDeviceGetHandleByIndex(phys)
+
+    def sample_now(self):
+        """one synchronous sample (called between the last launch and the synchronize of the timed region: the GPU is
+        still executing the queued steps)"""
+        if getattr(self, "_nvml", None) is not None:
+            self._one(*self._nvml)
+
+    def _one(self, N, h, mx, names, reasons_fn):
+        try:
+            sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+            r = reasons_fn(h)
+            self.rows.append([str(self.index), str(sm), str(mx), "0"] + ["Active" if r & bit else "Not Active" for _, bit in names])
+        except Exception:
+            pass
+
+    def _poll(self, N, h):
+        names = (("hw_slowdown", getattr(N, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                 ("hw_thermal_slowdown", getattr(N, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                 ("sw_thermal_slowdown", getattr(N, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                 ("sw_power_cap", getattr(N, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+        reasons_fn = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        self._nvml = (N, h, mx, names, reasons_fn)
+        while not self.stop:
+            self._one(N, h, mx, names, reasons_fn)
+            time.sleep(0.002)
 
     def __enter__(self):
         try:
+            N, h = self._handle()
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll, args=(N, h), daemon=True)
+            self.t.start()
+            return self
+        except Exception:
+            pass
+        try:
+            self.source = "nvidia-smi"
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -62,9 +111,11 @@ class Clocks:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
+        self.stop = True
         if self.proc:
             time.sleep(0.12)
             self.proc.terminate()
+        if self.t:
             self.t.join(timeout=2)
 
     def summary(self):
@@ -73,7 +124,7 @@ class Clocks:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.startswith("Active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
 def peaks():
@@ -364,7 +415,7 @@ def main():
             rgb, sigma = model(p, d)
             pin_out.copy_(torch.cat([rgb, sigma], -1), non_blocking=True)
 
-    def timed(fn, K):
+    def timed(fn, K, clk=None):
         evs = []
         for _ in range(K):
             flush.zero_()  # L2 flush between timed iterations (outside the event-timed span)
@@ -373,6 +424,8 @@ def main():
             fn()
             e.record()
             evs.append((s, e))
+        if clk is not None:
+            clk.sample_now()   # the queue is still draining: a sample that is certainly under load
         torch.cuda.synchronize()
         return sum(s.elapsed_time(e) for s, e in evs)
 
@@ -388,7 +441,8 @@ def main():
     barrier()
     l0 = _lib.LAUNCHES
     with Clocks(local) as clk:
-        ms = timed(step, a.steps)
+        time.sleep(0.02)   # let the sampler thread take its first reading
+        ms = timed(step, a.steps, clk)
     launches = _lib.LAUNCHES - l0
     barrier()
     ms_e2e = timed(step_e2e, a.steps) if not a.no_e2e else float("nan")
