@@ -30,7 +30,8 @@ template <int N> struct Cfg {
     static constexpr uint32_t STAGE_BYTES = 2 * A_HALF + 2 * B_HALF;
     static constexpr uint32_t NSTAGE = N > 160 ? 2u : 3u;
     static constexpr uint32_t SMEM_BAR = NSTAGE * STAGE_BYTES;
-    static constexpr uint32_t SMEM_DYN = SMEM_BAR + 128;
+    static constexpr uint32_t SMEM_EPI = SMEM_BAR + 128;            // 4 warps x [32 rows][20 floats]: store transposition
+    static constexpr uint32_t SMEM_DYN = SMEM_EPI + 4 * 32 * 80;
 };
 constexpr int NTHREADS = 320;                            // warps 0-3 epilogue, 4-7 staging, 8 MMA, 9 weight stream
 
@@ -68,7 +69,6 @@ __global__ void __launch_bounds__(256) pack_dgrad_kernel(const float *__restrict
 template <int N>
 __global__ void __launch_bounds__(NTHREADS, 1) dgrad_kernel(const Args a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint32_t tmem_base_s;
     constexpr uint32_t B_HALF = Cfg<N>::B_HALF, STAGE_BYTES = Cfg<N>::STAGE_BYTES, NSTAGE = Cfg<N>::NSTAGE, SMEM_BAR = Cfg<N>::SMEM_BAR;
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,56 +84,78 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgrad_kernel(const Args a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SMEM_BAR + 112u), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tbase = tmem_base_s;
+    const uint32_t tbase = *reinterpret_cast<volatile uint32_t *>(smem + SMEM_BAR + 112u);   // written by tcgen05.alloc
     const uint32_t ntiles = (a.Ns + 127u) / 128u;
     const uint32_t my = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
 
     if (warp < 4) {
         // =============================== epilogue ===============================
+        // Global traffic of the epilogue is laid out so that a warp instruction touches few 128-byte lines: with one row
+        // per lane a 16-byte access per lane hits 32 different lines (measured: the mask loads and the result stores
+        // written that way cost 2/3 of the kernel).  Loads: 8 lanes per row.  Stores: through a [32][16] transposition
+        // buffer, 4 lanes per row.
         const uint32_t tl = tbase + ((uint32_t)(warp * 32) << 16);
+        float *scratch = reinterpret_cast<float *>(smem + Cfg<N>::SMEM_EPI) + warp * 32 * 20;
+        constexpr int NJ = (N + 31) / 32;
         for (uint32_t it = 0; it < my; it++) {
-            const uint32_t row = (blockIdx.x + it * gridDim.x) * 128u + (uint32_t)threadIdx.x;
-            // ReLU mask of this row as bits, fetched while the MMAs of the tile run (a global load per column block
-            // inside the loop below would put one DRAM latency on each of its N/8 iterations)
-            uint32_t mbits[(N + 31) / 32];
+            const uint32_t row0 = (blockIdx.x + it * gridDim.x) * 128u + (uint32_t)warp * 32u;   // first row of this warp
+            // ReLU mask of this lane's row (row0 + lane), fetched while the MMAs of the tile run.
+            // word j: bit 8e + m <=> column 32j + 4m + e
+            uint32_t mbits[NJ];
 #pragma unroll
-            for (int w = 0; w < (N + 31) / 32; w++) mbits[w] = 0xFFFFFFFFu;
-            if (a.H != nullptr && row < a.Ns) {
-                const float4 *hr = reinterpret_cast<const float4 *>(a.H + (size_t)row * a.ldh);
+            for (int j = 0; j < NJ; j++) mbits[j] = 0xFFFFFFFFu;
+            if (a.H != nullptr) {
 #pragma unroll
-                for (int w = 0; w < (N + 31) / 32; w++) {
-                    float4 hv[8];
+                for (int j = 0; j < NJ; j++) {
+                    float4 hv[8];   // all eight loads of the column group in flight before the first ballot consumes one
 #pragma unroll
-                    for (int j = 0; j < 8; j++) hv[j] = (32 * w + 4 * j < N) ? __ldg(hr + 8 * w + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    uint32_t m = 0;
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t r = row0 + 4u * i + ((uint32_t)lane >> 3), col = 32u * j + 4u * ((uint32_t)lane & 7u);
+                        hv[i] = (r < a.Ns && col < (uint32_t)N) ? __ldg(reinterpret_cast<const float4 *>(a.H + (size_t)r * a.ldh + col))
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
 #pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        m |= ((hv[j].x > 0.f ? 1u : 0u) | (hv[j].y > 0.f ? 2u : 0u) | (hv[j].z > 0.f ? 4u : 0u) | (hv[j].w > 0.f ? 8u : 0u)) << (4 * j);
-                    mbits[w] = m;
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t bx = __ballot_sync(0xFFFFFFFFu, hv[i].x > 0.f), by = __ballot_sync(0xFFFFFFFFu, hv[i].y > 0.f),
+                                       bz = __ballot_sync(0xFFFFFFFFu, hv[i].z > 0.f), bw = __ballot_sync(0xFFFFFFFFu, hv[i].w > 0.f);
+                        if (i == (lane >> 2)) {   // the iteration that carried this lane's row: its 8 lanes are 8 (lane & 3) ..
+                            const uint32_t sh = 8u * ((uint32_t)lane & 3u);
+                            mbits[j] = ((bx >> sh) & 0xFFu) | (((by >> sh) & 0xFFu) << 8) | (((bz >> sh) & 0xFFu) << 16) | (((bw >> sh) & 0xFFu) << 24);
+                        }
+                    }
                 }
             }
             mbar_wait(acc_full, it & 1u);
             tc_fence_after();
 #pragma unroll
-            for (uint32_t c = 0; c < (uint32_t)N; c += 8) {
-                uint32_t m[8], sm[8];
-                tmem_ld8(tl + c, m);
-                tmem_ld8(tl + (uint32_t)N + c, sm);
+            for (uint32_t c = 0; c < (uint32_t)N; c += 16) {
+                uint32_t m[16], sm[16];
+                tmem_ld16(tl + c, m);
+                tmem_ld16(tl + (uint32_t)N + c, sm);
                 tc_wait_ld();
-                if (row < a.Ns) {
-                    float v[8];
-                    const uint32_t mb = mbits[c >> 5] >> (c & 31u);
+                float v[16];
 #pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] = ((mb >> k) & 1u) ? __fadd_rn(__uint_as_float(m[k]), __uint_as_float(sm[k])) : 0.f;
-                    float *d = a.C + (size_t)row * a.ldc + c;
-                    *reinterpret_cast<float4 *>(d) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4 *>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                for (int k = 0; k < 16; k++) {
+                    const uint32_t cc = c + k;   // column; mask bit 8 (cc & 3) + ((cc & 31) >> 2) of word cc >> 5
+                    const bool on = ((mbits[cc >> 5] >> (8u * (cc & 3u) + ((cc & 31u) >> 2))) & 1u) != 0u;
+                    v[k] = on ? __fadd_rn(__uint_as_float(m[k]), __uint_as_float(sm[k])) : 0.f;
+                }
+                __syncwarp();   // the previous block has left the buffer
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    *reinterpret_cast<float4 *>(scratch + lane * 20 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t rl = 8u * i + ((uint32_t)lane >> 2), c4 = (uint32_t)lane & 3u, r = row0 + rl;
+                    const float4 o = *reinterpret_cast<const float4 *>(scratch + rl * 20 + 4 * c4);
+                    if (r < a.Ns) *reinterpret_cast<float4 *>(a.C + (size_t)r * a.ldc + c + 4u * c4) = o;
                 }
             }
             tc_fence_before();
