@@ -21,6 +21,7 @@ _vp, _u32, _i32, _i64, _u64, _f32 = C.c_void_p, C.c_uint32, C.c_int32, C.c_int64
 SIGNATURES = {
     "cnc_grid_encode_fwd": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp],
     "cnc_grid_encode_bwd": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp],
+    "cnc_grid_encode_bwd_rows": [_vp, _u32, _u32, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp],
     "cnc_grid_encode_fwd_bits": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp],
     "cnc_ste_binary_fwd": [_vp, _vp, _u64, _vp],
     "cnc_ste_binary_bwd": [_vp, _vp, _vp, _u64, _vp],

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(TPB)
 grid_bwd_kernel(const float *__restrict__ grad, const float *__restrict__ x,
                 const int32_t *__restrict__ offsets, const int32_t *__restrict__ resolutions,
                 float *__restrict__ grad_table, uint32_t N, uint32_t Rb,
-                const uint8_t *__restrict__ vxl, const int32_t *__restrict__ min_level_id) {
+                const uint8_t *__restrict__ vxl, const int32_t *__restrict__ min_level_id, uint32_t ld, uint32_t col0) {
     const uint32_t b = blockIdx.x * TPB + threadIdx.x;
     if (b >= N) return;
     const uint32_t l = blockIdx.y;
@@ -165,7 +165,9 @@ grid_bwd_kernel(const float *__restrict__ grad, const float *__restrict__ x,
 #pragma unroll
     for (int d = 0; d < D; d++) xi[d] = __ldg(x + (size_t)b * D + d);
     float g[F];
-    load_row<F, VEC>(grad + ((size_t)l * N + b) * F, g);
+    // grad is [L, N, F] (the reference's layout, ld == 0) or a column block of a row-major [N, ld] matrix (level l at
+    // columns col0 + l F .. : what a GEMM that produced the feature gradients leaves behind)
+    load_row<F, VEC>(ld ? grad + (size_t)b * ld + col0 + (size_t)l * F : grad + ((size_t)l * N + b) * F, g);
 
     Corners<D> cs;
     if (!make_corners<D>(xi, lc, Rb, vxl, cs)) return;  // gridencoder.cu:435-440
@@ -302,26 +304,26 @@ static int encode_fwd_any(bool bits, const float *x, const void *table, const in
 template <int D, int F>
 static int launch_bwd(const float *grad, const float *x, const int32_t *offsets, const int32_t *resolutions,
                       float *gt, uint32_t N, uint32_t L, uint32_t Rb, const uint8_t *vxl, const int32_t *mlid,
-                      cudaStream_t s) {
+                      cudaStream_t s, uint32_t ld = 0, uint32_t col0 = 0) {
     const dim3 grid(div_up(N, TPB), L);
-    if (aligned16(grad) && aligned16(gt))
-        grid_bwd_kernel<D, F, true><<<grid, TPB, 0, s>>>(grad, x, offsets, resolutions, gt, N, Rb, vxl, mlid);
+    if (aligned16(grad) && aligned16(gt) && (ld & 3u) == 0 && (col0 & 3u) == 0)
+        grid_bwd_kernel<D, F, true><<<grid, TPB, 0, s>>>(grad, x, offsets, resolutions, gt, N, Rb, vxl, mlid, ld, col0);
     else
-        grid_bwd_kernel<D, F, false><<<grid, TPB, 0, s>>>(grad, x, offsets, resolutions, gt, N, Rb, vxl, mlid);
+        grid_bwd_kernel<D, F, false><<<grid, TPB, 0, s>>>(grad, x, offsets, resolutions, gt, N, Rb, vxl, mlid, ld, col0);
     return check_launch("grid_encode_bwd");
 }
 
 template <int D>
 static int dispatch_bwd(uint32_t F, const float *grad, const float *x, const int32_t *offsets,
                         const int32_t *resolutions, float *gt, uint32_t N, uint32_t L, uint32_t Rb,
-                        const uint8_t *vxl, const int32_t *mlid, cudaStream_t s) {
+                        const uint8_t *vxl, const int32_t *mlid, cudaStream_t s, uint32_t ld = 0, uint32_t col0 = 0) {
     switch (F) {
-        case 1: return launch_bwd<D, 1>(grad, x, offsets, resolutions, gt, N, L, Rb, vxl, mlid, s);
-        case 2: return launch_bwd<D, 2>(grad, x, offsets, resolutions, gt, N, L, Rb, vxl, mlid, s);
-        case 4: return launch_bwd<D, 4>(grad, x, offsets, resolutions, gt, N, L, Rb, vxl, mlid, s);
-        case 8: return launch_bwd<D, 8>(grad, x, offsets, resolutions, gt, N, L, Rb, vxl, mlid, s);
-        case 16: return launch_bwd<D, 16>(grad, x, offsets, resolutions, gt, N, L, Rb, vxl, mlid, s);
-        case 32: return launch_bwd<D, 32>(grad, x, offsets, resolutions, gt, N, L, Rb, vxl, mlid, s);
+        case 1: return launch_bwd<D, 1>(grad, x, offsets, resolutions, gt, N, L, Rb, vxl, mlid, s, ld, col0);
+        case 2: return launch_bwd<D, 2>(grad, x, offsets, resolutions, gt, N, L, Rb, vxl, mlid, s, ld, col0);
+        case 4: return launch_bwd<D, 4>(grad, x, offsets, resolutions, gt, N, L, Rb, vxl, mlid, s, ld, col0);
+        case 8: return launch_bwd<D, 8>(grad, x, offsets, resolutions, gt, N, L, Rb, vxl, mlid, s, ld, col0);
+        case 16: return launch_bwd<D, 16>(grad, x, offsets, resolutions, gt, N, L, Rb, vxl, mlid, s, ld, col0);
+        case 32: return launch_bwd<D, 32>(grad, x, offsets, resolutions, gt, N, L, Rb, vxl, mlid, s, ld, col0);
         default: set_error("GridEncoding: n_features must be 1, 2, 4, 8, 16 or 32."); return CNC_ENOTSUP;
     }
 }
@@ -358,6 +360,21 @@ int cnc_grid_encode_bwd(const float *grad, const float *x, const int32_t *offset
         case 1: return dispatch_bwd<1>(F, grad, x, offsets, resolutions, grad_table, N, L_calc, Rb, binary_vxl, min_level_id, s);
         case 2: return dispatch_bwd<2>(F, grad, x, offsets, resolutions, grad_table, N, L_calc, Rb, binary_vxl, min_level_id, s);
         case 3: return dispatch_bwd<3>(F, grad, x, offsets, resolutions, grad_table, N, L_calc, Rb, binary_vxl, min_level_id, s);
+        default: set_error("GridEncoding: num_dim must be 1, 2, 3."); return CNC_ENOTSUP;
+    }
+}
+
+int cnc_grid_encode_bwd_rows(const float *grad_rows, uint32_t ld, uint32_t col0, const float *x, const int32_t *offsets,
+                             const int32_t *resolutions, float *grad_table, uint32_t N, uint32_t D, uint32_t F, uint32_t L_calc,
+                             uint32_t Rb, const uint8_t *binary_vxl, const int32_t *min_level_id, cnc_stream_t stream) {
+    if (N == 0 || L_calc == 0) return CNC_OK;
+    if (!grad_rows || !x || !offsets || !resolutions || !grad_table) { set_error("grid_encode_bwd_rows: null pointer"); return CNC_EINVAL; }
+    if (L_calc > 65535 || ld == 0 || col0 + L_calc * F > ld) { set_error("grid_encode_bwd_rows: column block outside the row"); return CNC_EINVAL; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (D) {
+        case 1: return dispatch_bwd<1>(F, grad_rows, x, offsets, resolutions, grad_table, N, L_calc, Rb, binary_vxl, min_level_id, s, ld, col0);
+        case 2: return dispatch_bwd<2>(F, grad_rows, x, offsets, resolutions, grad_table, N, L_calc, Rb, binary_vxl, min_level_id, s, ld, col0);
+        case 3: return dispatch_bwd<3>(F, grad_rows, x, offsets, resolutions, grad_table, N, L_calc, Rb, binary_vxl, min_level_id, s, ld, col0);
         default: set_error("GridEncoding: num_dim must be 1, 2, 3."); return CNC_ENOTSUP;
     }
 }

@@ -145,11 +145,10 @@ class _FusedFieldTrain(Function):
         for enc, prm, dims in ((mb.encoding_xyz, p_xyz, [0, 1, 2]), (mb.encoding_xy, p_xy, [0, 1]),
                                (mb.encoding_xz, p_xz, [0, 2]), (mb.encoding_yz, p_yz, [1, 2])):
             L, F = enc.n_levels, enc.n_features
-            g = dfeat[:, col:col + L * F].view(n, L, F).permute(1, 0, 2).contiguous()
-            col += L * F
             ge = torch.zeros_like(prm)
-            G.grid_encode_backward(g, xn[:, dims].contiguous(), prm, enc.offsets_list, enc.resolutions_list, ge, n,
-                                   len(dims), F, L, 0, 128, None, None, None, None)
+            check(lib().cnc_grid_encode_bwd_rows(ptr(dfeat), dfeat.shape[1], col, ptr(xn[:, dims].contiguous()), ptr(enc.offsets_list),
+                                                 ptr(enc.resolutions_list), ptr(ge), n, len(dims), F, L, 128, None, None, stream()))
+            col += L * F
             grads.append(G.ste_binary_backward(prm.contiguous(), ge))
         return (None, None, None, *grads, gW1, gb1, gW2, gb2, gW3, gb3, gW4, gb4, gW5, gb5)
 

@@ -60,6 +60,13 @@ int cnc_grid_encode_bwd(const float *grad, const float *x, const int32_t *offset
                         const int32_t *resolutions, float *grad_table, uint32_t N, uint32_t D,
                         uint32_t F, uint32_t L_calc, uint32_t Rb, const uint8_t *binary_vxl,
                         const int32_t *min_level_id, cnc_stream_t stream);
+/* Same scatter-add, gradient read in place from a column block of a row-major [N, ld] matrix (level l at columns
+ * col0 + l*F ..): the layout a GEMM that produced the feature gradients leaves behind; saves the permute + copy into
+ * the reference's [L, N, F] layout (ngp.py:126). */
+int cnc_grid_encode_bwd_rows(const float *grad_rows, uint32_t ld, uint32_t col0, const float *x,
+                             const int32_t *offsets, const int32_t *resolutions, float *grad_table,
+                             uint32_t N, uint32_t D, uint32_t F, uint32_t L_calc, uint32_t Rb,
+                             const uint8_t *binary_vxl, const int32_t *min_level_id, cnc_stream_t stream);
 
 /* Same gather, reading a 1-bit/parameter sign table (bit ch of byte-group row = param >= 0)
  * produced by cnc_sign_pack; the encoded features are bit-identical to cnc_grid_encode_fwd on
