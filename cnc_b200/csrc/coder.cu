@@ -77,10 +77,6 @@ __device__ __forceinline__ void mul_and_flo(uint32_t R, uint32_t c16, uint32_t &
                  "bfind.u32 %2, %3;\n\t"
                  "mov.b64 {%0, %1}, q;\n\t}" : "=r"(qlo), "=r"(qhi), "=r"(f) : "r"(R), "r"(c16), "r"(0u));
 }
-__device__ __forceinline__ uint32_t renorm_g(uint32_t R, uint32_t L2, uint32_t H2) {
-    const uint32_t f = 31u - __clz(R);
-    return f + (H2 >> f) - (L2 >> f);
-}
 // low after the renormalisation of the last symbol (encoder termination)
 __device__ __forceinline__ uint32_t renorm_low(uint32_t R, uint32_t L2, uint32_t H2) {
     return (L2 << renorm_shift(L2, H2, R)) & 0x7FFFFFFFu;
