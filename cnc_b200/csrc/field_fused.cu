@@ -24,6 +24,7 @@
 //       L1 acc [0,160) -> h1 hi in place, lo [160,320);  L2 acc [320,400);
 //       head input hi [0,96), lo [96,192);  L3 acc [192,352) -> hi in place, lo [352,512);
 //       L4 acc [0,160) -> hi in place, lo [160,320);  L5 acc [320,336).
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -135,6 +136,11 @@ struct FieldArgs {
     float *rgb;    // [N,3]   (nullptr in density-only mode)
     float *geo;    // [N,79]  nullable
     // training forward (all nullable, together): what the backward pass needs, written as the values go by
+    // single-launch host pipeline (cnc_field_fwd_host, all nullable): wave w of tiles may be read once ready[w] == epoch
+    // (written behind the H2D copy of its samples); every CTA bumps done[w] when its tile of the wave is in HBM
+    const uint32_t *ready;
+    uint32_t *done;
+    uint32_t epoch;
     float *sv_x0;  // [N,256] layer-1 input (192 grid features | x, sin/cos 63 | 1)
     float *sv_h1;  // [N,160] relu(L1)
     float *sv_h3;  // [N,160] relu(L3)
@@ -330,7 +336,7 @@ __device__ __forceinline__ void ep_hidden(uint32_t tl, int cg, uint32_t c_main, 
 constexpr int NCOMPUTE = 512;              // 16 gather/epilogue warps
 constexpr int NTHREADS = NCOMPUTE + 64;    // + the MMA warp + the weight-stream (bulk copy) warp
 
-template <bool DENSITY_ONLY, bool SAVE>
+template <bool DENSITY_ONLY, bool SAVE, bool POLL = false>
 __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -513,9 +519,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
         auto load_x = [&](uint32_t tile, float (&x)[3]) {
             const uint32_t row = tile * TILE_M + r;
             const bool live = row < a.N;
-            const float px = live ? __ldg(a.pos + (size_t)row * 3 + 0) : __fadd_rn(amin.x, 0.5f * ainv.x);
-            const float py = live ? __ldg(a.pos + (size_t)row * 3 + 1) : __fadd_rn(amin.y, 0.5f * ainv.y);
-            const float pz = live ? __ldg(a.pos + (size_t)row * 3 + 2) : __fadd_rn(amin.z, 0.5f * ainv.z);
+            if (POLL) {   // the samples of this wave are being uploaded while earlier waves are evaluated
+                const volatile uint32_t *flag = a.ready + tile / gridDim.x;
+                const long long t0 = clock64();
+                while ((int32_t)(*flag - a.epoch) < 0 && clock64() - t0 < 4000000000ll) __nanosleep(64);   // bounded: never hang the GPU
+                __threadfence();
+            }
+            // L2 loads (each value is read once; with POLL the buffer is rewritten by the copy engine between launches)
+            const float px = live ? __ldcg(a.pos + (size_t)row * 3 + 0) : __fadd_rn(amin.x, 0.5f * ainv.x);
+            const float py = live ? __ldcg(a.pos + (size_t)row * 3 + 1) : __fadd_rn(amin.y, 0.5f * ainv.y);
+            const float pz = live ? __ldcg(a.pos + (size_t)row * 3 + 2) : __fadd_rn(amin.z, 0.5f * ainv.z);
             x[0] = __fdiv_rn(__fsub_rn(px, amin.x), ainv.x);
             x[1] = __fdiv_rn(__fsub_rn(py, amin.y), ainv.y);
             x[2] = __fdiv_rn(__fsub_rn(pz, amin.z), ainv.z);
@@ -650,7 +663,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                     float d3[3], sh[16];
 #pragma unroll
                     for (int d = 0; d < 3; d++) {
-                        const float dv = live ? __ldg(a.dirs + (size_t)row * 3 + d) : 0.f;
+                        const float dv = live ? __ldcg(a.dirs + (size_t)row * 3 + d) : 0.f;
                         const float d01 = __fdiv_rn(__fadd_rn(dv, 1.0f), 2.0f);  // ngp.py:540
                         d3[d] = __fsub_rn(__fmul_rn(d01, 2.f), 1.f);             // tcnn maps back to [-1,1]
                     }
@@ -737,6 +750,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                 }
             }
             if (threadIdx.x == 0) CNC_TL(19);
+            if (POLL) {   // this tile's sigma / rgb are stored: publish for the download stream
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"n"(NCOMPUTE) : "memory");
+                if (threadIdx.x == 0) atomicAdd(a.done + it, 1u);
+            }
             tc_fence_before();
             mbar_arrive(act_ready);  // this tile's accumulators are consumed: the next tile's L1 may overwrite them
             if (has_next) {
@@ -783,7 +801,8 @@ static int field_fwd_impl(const float *pos, const float *dirs, const float *aabb
                           const uint8_t *bits_xy, const uint8_t *bits_xz, const uint8_t *bits_yz, const int32_t *offsets3,
                           const int32_t *resolutions3, const int32_t *offsets2, const int32_t *resolutions2,
                           const float *blob, float *sigma, float *rgb, float *geo, float *sv_x0, float *sv_h1, float *sv_h3,
-                          float *sv_h4, uint32_t N, cnc_stream_t stream) {
+                          float *sv_h4, uint32_t N, cnc_stream_t stream, const uint32_t *ready = nullptr, uint32_t *done = nullptr,
+                          uint32_t epoch = 0) {
     if (N == 0) return CNC_OK;
     if (!pos || !aabb6_host || !bits_xyz || !bits_xy || !bits_xz || !bits_yz || !offsets3 || !resolutions3 ||
         !offsets2 || !resolutions2 || !blob || !sigma || (dirs && !rgb)) {
@@ -802,6 +821,8 @@ static int field_fwd_impl(const float *pos, const float *dirs, const float *aabb
         cudaError_t e2 = cudaFuncSetAttribute(ff::field_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::SMEM_DYN);
         cudaError_t e3 = cudaFuncSetAttribute(ff::field_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::SMEM_DYN);
         if (e1 == cudaSuccess) e1 = e3;
+        cudaError_t e4 = cudaFuncSetAttribute(ff::field_fwd_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff::SMEM_DYN);
+        if (e1 == cudaSuccess) e1 = e4;
         if (e1 != cudaSuccess || e2 != cudaSuccess) {
             set_error("field_fwd: cannot reserve %u bytes of shared memory (%s)", ff::SMEM_DYN,
                       cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -816,10 +837,12 @@ static int field_fwd_impl(const float *pos, const float *dirs, const float *aabb
     a.offs3 = offsets3; a.res3 = resolutions3; a.offs2 = offsets2; a.res2 = resolutions2;
     a.blob = blob; a.sigma = sigma; a.rgb = rgb; a.geo = geo; a.N = N; a.dbg = g_timeline;
     a.sv_x0 = sv_x0; a.sv_h1 = sv_h1; a.sv_h3 = sv_h3; a.sv_h4 = sv_h4;
+    a.ready = ready; a.done = done; a.epoch = epoch;
     const uint32_t ntiles = (N + ff::TILE_M - 1) / ff::TILE_M;
     uint32_t grid = ntiles < (uint32_t)n_sm ? ntiles : (uint32_t)n_sm;
     if (const char *g = getenv("CNC_FIELD_GRID")) { const uint32_t v = (uint32_t)atoi(g); if (v >= 1 && v < grid) grid = v; }  // profiling aid
-    if (sv_x0) ff::field_fwd_kernel<false, true><<<grid, ff::NTHREADS, ff::SMEM_DYN, s>>>(a);
+    if (ready) ff::field_fwd_kernel<false, false, true><<<grid, ff::NTHREADS, ff::SMEM_DYN, s>>>(a);
+    else if (sv_x0) ff::field_fwd_kernel<false, true><<<grid, ff::NTHREADS, ff::SMEM_DYN, s>>>(a);
     else if (dirs) ff::field_fwd_kernel<false, false><<<grid, ff::NTHREADS, ff::SMEM_DYN, s>>>(a);
     else ff::field_fwd_kernel<true, false><<<grid, ff::NTHREADS, ff::SMEM_DYN, s>>>(a);
     return check_launch("field_fwd");
@@ -833,10 +856,12 @@ int cnc_field_fwd(const float *pos, const float *dirs, const float *aabb6_host, 
                           resolutions2, blob, sigma, rgb, geo, nullptr, nullptr, nullptr, nullptr, N, stream);
 }
 
-/* Host-buffer entry point: the batch is cut into chunks of whole waves of the persistent kernel and pipelined over three
- * streams (H2D of chunk i+1, kernel on chunk i, D2H of chunk i-1), all from this one call: per chunk the host issues
- * two copies, one launch, two more copies and three event operations -- a few microseconds each -- so the chunks can be
- * small enough that only the first upload and the last download are exposed. */
+/* Host-buffer entry point, ONE launch of the persistent kernel: the samples are uploaded in chunks of whole waves
+ * (1, 2, 4, .. max .. 4, 2, 1) on s_in, each followed by a 4-byte-per-wave "ready" stamp; the kernel, started at once on
+ * s_compute, waits for the stamp of a wave before it reads the wave's positions; CTAs count finished tiles per wave and
+ * a one-thread kernel per chunk on s_out waits for those counts before the chunk's download is queued behind it.  Only
+ * the first upload and the last download are exposed, and the kernel keeps its inter-tile overlap (six chunk launches
+ * cost 0.08 ms of ramp-up and tails at 262 144 samples). */
 int cnc_field_fwd_host(const float *pos_host, const float *dirs_host, const float *aabb6_host, const uint8_t *bits_xyz,
                        const uint8_t *bits_xy, const uint8_t *bits_xz, const uint8_t *bits_yz, const int32_t *offsets3,
                        const int32_t *resolutions3, const int32_t *offsets2, const int32_t *resolutions2, const float *blob,
@@ -848,50 +873,79 @@ int cnc_field_fwd_host(const float *pos_host, const float *dirs_host, const floa
         set_error("field_fwd_host: null pointer / zero chunk");
         return CNC_EINVAL;
     }
-    constexpr int NEV = 256;
-    static cudaEvent_t ev[NEV];
-    static bool ev_init = false;
-    if (!ev_init) {
-        for (int i = 0; i < NEV; i++)
-            if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { set_error("field_fwd_host: cudaEventCreate failed"); return CNC_ECUDA; }
-        ev_init = true;
+    constexpr uint32_t MAXW = 4096, NSLOT = 8;
+    static cudaEvent_t ev[4];
+    static uint32_t *h_stamp = nullptr, *d_ready = nullptr, *d_done = nullptr, epoch = 0;
+    static uint32_t *cum = nullptr;                       // tiles published per wave since start-up (the counters never reset)
+    typedef CUresult (*wait32_t)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    static wait32_t wait32 = nullptr;                     // cuStreamWaitValue32: a stream-side wait that needs no SM
+    static int n_sm = 0;
+    if (!h_stamp) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        bool ok = cudaMallocHost(&h_stamp, NSLOT * MAXW * 4) == cudaSuccess && cudaMalloc(&d_ready, MAXW * 4) == cudaSuccess &&
+                  cudaMalloc(&d_done, MAXW * 4) == cudaSuccess && cudaMemset(d_ready, 0, MAXW * 4) == cudaSuccess &&
+                  cudaMemset(d_done, 0, MAXW * 4) == cudaSuccess;
+        for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) == cudaSuccess;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        ok = ok && cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) == cudaSuccess && fn != nullptr;
+        wait32 = reinterpret_cast<wait32_t>(fn);
+        cum = static_cast<uint32_t *>(calloc(MAXW, 4));
+        ok = ok && cum != nullptr;
+        if (!ok) { h_stamp = nullptr; set_error("field_fwd_host: cannot allocate the pipeline state"); return CNC_ECUDA; }
     }
+    if (wave_samples != (uint32_t)n_sm * ff::TILE_M) { set_error("field_fwd_host: wave_samples must be SMs x 128 = %d", n_sm * ff::TILE_M); return CNC_EINVAL; }
+    const uint32_t ntiles = (N + ff::TILE_M - 1) / ff::TILE_M, grid = ntiles < (uint32_t)n_sm ? ntiles : (uint32_t)n_sm;
+    const uint32_t nwaves = (ntiles + grid - 1) / grid;
+    if (nwaves > MAXW) { set_error("field_fwd_host: more than %u waves", MAXW); return CNC_EINVAL; }
     cudaStream_t sc = static_cast<cudaStream_t>(s_compute), si = static_cast<cudaStream_t>(s_in), so = static_cast<cudaStream_t>(s_out);
-    // chunk schedule in waves: 1, 2, 4, .. max .. 4, 2, 1 -- a small first chunk starts the kernel after a short upload, a
-    // small last chunk leaves a short download exposed, the large ones in between keep the persistent kernel efficient
-    constexpr int MAXC = (NEV - 2) / 2;
-    uint32_t front[MAXC], back[MAXC];
+    epoch++;
+    uint32_t *stamp = h_stamp + (epoch % NSLOT) * MAXW;   // a slot per call: earlier calls may still be copying from theirs
+    for (uint32_t w = 0; w < nwaves; w++) stamp[w] = epoch;
+    // chunk schedule in waves: 1, 2, 4, .. max .. 4, 2, 1
+    uint32_t front[64], back[64];
     int nf = 0, nb = 0;
-    uint32_t left = (N + wave_samples - 1) / wave_samples;
-    for (uint32_t sz = 1; left > 0; sz = sz * 2 < max_chunk_waves ? sz * 2 : max_chunk_waves) {
-        if (nf + nb + 2 > MAXC) { set_error("field_fwd_host: more than %d chunks", MAXC); return CNC_EINVAL; }
+    uint32_t left = nwaves;
+    for (uint32_t sz = 1; left > 0 && nf < 63 && nb < 63; sz = sz * 2 < max_chunk_waves ? sz * 2 : max_chunk_waves) {
         uint32_t t = sz < left ? sz : left;
         front[nf++] = t; left -= t;
         if (left == 0) break;
         t = sz < left ? sz : left;
         back[nb++] = t; left -= t;
     }
-    const uint32_t nchunk = (uint32_t)(nf + nb);
-    int e = 0;
-    // the staging buffers may still be in use by earlier work on the caller's stream
-    cudaEventRecord(ev[e], sc); cudaStreamWaitEvent(si, ev[e], 0); cudaStreamWaitEvent(so, ev[e], 0); e++;
-    uint32_t lo = 0;
-    for (uint32_t c = 0; c < nchunk; c++) {
-        const uint32_t waves = c < (uint32_t)nf ? front[c] : back[nb - 1 - (int)(c - nf)];
-        const uint32_t want = waves * wave_samples, n = (N - lo) < want ? (N - lo) : want;
-        cudaMemcpyAsync(d_pos + (size_t)lo * 3, pos_host + (size_t)lo * 3, (size_t)n * 12, cudaMemcpyHostToDevice, si);
-        cudaMemcpyAsync(d_dirs + (size_t)lo * 3, dirs_host + (size_t)lo * 3, (size_t)n * 12, cudaMemcpyHostToDevice, si);
-        cudaEventRecord(ev[e], si); cudaStreamWaitEvent(sc, ev[e], 0); e++;
-        const int rc = field_fwd_impl(d_pos + (size_t)lo * 3, d_dirs + (size_t)lo * 3, aabb6_host, bits_xyz, bits_xy, bits_xz, bits_yz,
-                                      offsets3, resolutions3, offsets2, resolutions2, blob, d_sigma + lo, d_rgb + (size_t)lo * 3, nullptr,
-                                      nullptr, nullptr, nullptr, nullptr, n, s_compute);
-        if (rc != CNC_OK) return rc;
-        cudaEventRecord(ev[e], sc); cudaStreamWaitEvent(so, ev[e], 0); e++;
-        cudaMemcpyAsync(rgb_host + (size_t)lo * 3, d_rgb + (size_t)lo * 3, (size_t)n * 12, cudaMemcpyDeviceToHost, so);
-        cudaMemcpyAsync(sigma_host + lo, d_sigma + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, so);
-        lo += n;
+    if (left > 0) front[nf - 1] += left;   // (only for tiny max_chunk_waves on huge batches)
+    // the staging buffers and the stamps may still be in use by earlier work on the caller's stream
+    cudaEventRecord(ev[0], sc); cudaStreamWaitEvent(si, ev[0], 0); cudaStreamWaitEvent(so, ev[0], 0);
+    const int rc = field_fwd_impl(d_pos, d_dirs, aabb6_host, bits_xyz, bits_xy, bits_xz, bits_yz, offsets3, resolutions3, offsets2,
+                                  resolutions2, blob, d_sigma, d_rgb, nullptr, nullptr, nullptr, nullptr, nullptr, N, s_compute, d_ready,
+                                  d_done, epoch);
+    if (rc != CNC_OK) return rc;
+    const uint32_t last_ctas = ntiles - (nwaves - 1) * grid;
+    uint32_t w0 = 0;
+    for (int c = 0; c < nf + nb; c++) {
+        const uint32_t waves = c < nf ? front[c] : back[nb - 1 - (c - nf)], w1 = w0 + waves;
+        const size_t lo = (size_t)w0 * grid * ff::TILE_M;
+        size_t hi = (size_t)w1 * grid * ff::TILE_M;
+        if (hi > N) hi = N;
+        const size_t n = hi - lo;
+        cudaMemcpyAsync(d_pos + lo * 3, pos_host + lo * 3, n * 12, cudaMemcpyHostToDevice, si);
+        cudaMemcpyAsync(d_dirs + lo * 3, dirs_host + lo * 3, n * 12, cudaMemcpyHostToDevice, si);
+        cudaMemcpyAsync(d_ready + w0, stamp + w0, (size_t)waves * 4, cudaMemcpyHostToDevice, si);   // behind the data, same stream
+        for (uint32_t w = w0; w < w1; w++) {   // the download waits (on the stream, no kernel) for every tile of the chunk
+            cum[w] += w == nwaves - 1 ? last_ctas : grid;
+            if (wait32((CUstream)so, (CUdeviceptr)(uintptr_t)(d_done + w), cum[w], CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) {
+                set_error("field_fwd_host: cuStreamWaitValue32 failed");
+                return CNC_ECUDA;
+            }
+        }
+        cudaMemcpyAsync(rgb_host + lo * 3, d_rgb + lo * 3, n * 12, cudaMemcpyDeviceToHost, so);
+        cudaMemcpyAsync(sigma_host + lo, d_sigma + lo, n * 4, cudaMemcpyDeviceToHost, so);
+        w0 = w1;
     }
-    cudaEventRecord(ev[e], so); cudaStreamWaitEvent(sc, ev[e], 0);   // the caller's stream ends after the last download
+    cudaEventRecord(ev[1], so); cudaStreamWaitEvent(sc, ev[1], 0);   // the caller's stream ends after the last download
+    cudaEventRecord(ev[2], si); cudaStreamWaitEvent(sc, ev[2], 0);
     return check_launch("field_fwd_host");
 }
 

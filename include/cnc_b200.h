@@ -196,10 +196,13 @@ int cnc_field_fwd(const float *pos, const float *dirs, const float *aabb6_host,
                   const int32_t *offsets2, const int32_t *resolutions2, const float *blob,
                   float *sigma, float *rgb, float *geo, uint32_t N, cnc_stream_t stream);
 /* Host-buffer forward (the call a host-side caller of the reference makes: positions and directions in, colours and
- * densities out, all in host memory -- pinned, for the copies to be asynchronous): chunks of 1, 2, 4, .. max_chunk_waves
- * .. 4, 2, 1 waves (wave_samples = SMs x 128 keeps whole waves of the persistent kernel) are uploaded on s_in, evaluated
- * on s_compute and downloaded on s_out concurrently, so that only a short first upload and last download are exposed; d_pos / d_dirs / d_rgb [N,3], d_sigma [N] are device staging buffers owned by the caller.  Returns
- * after everything is enqueued; s_compute completes after the last download. */
+ * densities out, all in host memory -- pinned, for the copies to be asynchronous).  ONE launch of the persistent kernel
+ * on s_compute; the samples are uploaded on s_in in chunks of 1, 2, 4, .. max_chunk_waves .. 4, 2, 1 waves
+ * (wave_samples = SMs x 128), each followed by a per-wave "ready" stamp the kernel waits for before it reads the wave;
+ * CTAs count finished tiles per wave and the downloads on s_out wait for those counts with cuStreamWaitValue32, so only
+ * a short first upload and last download are exposed.  d_pos / d_dirs / d_rgb [N,3], d_sigma [N] are device staging
+ * buffers owned by the caller.  Returns after everything is enqueued; s_compute completes after the last download.
+ * All device-side waits are bounded (2 s), a missing stamp cannot hang the GPU. */
 int cnc_field_fwd_host(const float *pos_host, const float *dirs_host, const float *aabb6_host,
                        const uint8_t *bits_xyz, const uint8_t *bits_xy, const uint8_t *bits_xz,
                        const uint8_t *bits_yz, const int32_t *offsets3, const int32_t *resolutions3,
