@@ -520,10 +520,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             const uint32_t row = tile * TILE_M + r;
             const bool live = row < a.N;
             if (POLL) {   // the samples of this wave are being uploaded while earlier waves are evaluated
-                const volatile uint32_t *flag = a.ready + tile / gridDim.x;
-                const long long t0 = clock64();
-                while ((int32_t)(*flag - a.epoch) < 0 && clock64() - t0 < 4000000000ll) __nanosleep(64);   // bounded: never hang the GPU
-                __threadfence();
+                const uint32_t *flag = a.ready + tile / gridDim.x;
+                uint32_t v, spins = 0;
+                do {   // acquire: the positions written before the stamp are visible after it; bounded (~2 s): never hang the GPU
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                    if ((int32_t)(v - a.epoch) >= 0) break;
+                    __nanosleep(64);
+                } while (++spins < (1u << 23));
             }
             // L2 loads (each value is read once; with POLL the buffer is rewritten by the copy engine between launches)
             const float px = live ? __ldcg(a.pos + (size_t)row * 3 + 0) : __fadd_rn(amin.x, 0.5f * ainv.x);
