@@ -342,10 +342,33 @@ def train_bench(dev, rank, world, steps, field):
         torch.distributed.all_reduce(cnt, op=torch.distributed.ReduceOp.SUM)
         t = torch.cat([ms, cnt])
     ms, tot = t.tolist()
-    return {"what": "fwd + bwd + gradient all-reduce + Adam (differentiable path: K1/K2 kernels + fp32 nn.Linear), "
-                    "sampling through the fused density kernel", "steps": steps, "ms_per_step": ms / steps,
-            "samples_per_step_all_ranks": tot / steps, "samples_per_s": tot / (ms * 1e-3),
-            "allreduce_bytes_per_step": ts.reducer.bytes_per_step() if world > 1 else 0, "rays_per_rank": n_rays}
+    out = {"what": "occupancy march + visibility pass (fused density kernel) + fused forward (cnc_field_fwd_train) + volume "
+                   "rendering + MSE + backward (cnc_dgrad / cnc_wgrad / K2) + gradient all-reduce + fused Adam",
+           "steps": steps, "ms_per_step": ms / steps,
+           "samples_per_step_all_ranks": tot / steps, "samples_per_s": tot / (ms * 1e-3),
+           "allreduce_bytes_per_step": ts.reducer.bytes_per_step() if world > 1 else 0, "rays_per_rank": n_rays}
+    if world == 1:
+        # the same step with the rate term of the CNC loss (lambda > 0: context model on 150 000 sampled entries + planes)
+        from cnc_b200.context_models import CNC_context_models
+
+        cm = CNC_context_models(num_dim=3, resolutions_list=R3, resolutions_list_2D=R2, log2_hashmap_size=19, log2_hashmap_size_2D=17,
+                                n_features=F, sample_num=150000, max_context_layer_num=3, ste_binary=True, Rb=128,
+                                skip_levels_3D=(0, 1, 2), skip_levels_2D=(0,), device=dev)
+        ts2 = TrainStep(field, est, context_model=cm, lmbda=1e-3, lr=1e-4)
+        for _ in range(2):
+            ts2(rays, pixels, refresh_occupancy=False)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            ts2(rays, pixels, refresh_occupancy=False)
+        e1.record()
+        torch.cuda.synchronize()
+        out["with_rate_term"] = {"what": "same step + lambda * bits-per-parameter (forward_binary_vxl_mixPg_3D2D, 150 000 sampled "
+                                         "entries, dimension-wise context) and its backward", "lambda": 1e-3,
+                                 "ms_per_step": e0.elapsed_time(e1) / steps}
+        del cm, ts2
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():
