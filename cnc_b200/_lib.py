@@ -35,6 +35,8 @@ SIGNATURES = {
     "cnc_align_pack_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _vp],
     "cnc_align_pack_bwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],
     "cnc_segment_wsum": [_vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "cnc_segment_wsum_idx": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
+    "cnc_segment_wsum_idx_bwd": [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "cnc_cdf_from_p": [_vp, _vp, _u64, _vp],
     "cnc_ac_encode": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "cnc_ac_decode": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],

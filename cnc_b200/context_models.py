@@ -147,6 +147,30 @@ class align_and_pack(Function):
         return pack_and_align.align_and_pack_backward(dL.contiguous(), voxel_features, unique_cnt, cs, N, M, F, T, dim), None, None, None
 
 
+class segment_sum(Function):
+    """out[i] = sum_j w[j] * feat[idx[j]] over the rows j of segment i (cumsum [N+1]; w, idx optional), differentiable in
+    `feat`: replaces index_select -> align_and_pack -> (* weights) -> sum(dim=1) and its padded [N, M, F] temporaries
+    (utils_bpp_acc.py:563-566,741-745) by one kernel each way (cnc_segment_wsum_idx / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, feat, cumsum, weights=None, idx=None):
+        feat = feat.contiguous()
+        N, F = cumsum.numel() - 1, feat.shape[1]
+        out = torch.empty(N, F, device=feat.device, dtype=torch.float32)
+        check(lib().cnc_segment_wsum_idx(ptr(feat), ptr(idx), ptr(weights), ptr(cumsum), ptr(out), N, F, stream()))
+        ctx.save_for_backward(cumsum, weights, idx)
+        ctx.rows = feat.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        cumsum, weights, idx = ctx.saved_tensors
+        N, F = cumsum.numel() - 1, g.shape[1]
+        gf = torch.zeros(ctx.rows, F, device=g.device, dtype=torch.float32)
+        check(lib().cnc_segment_wsum_idx_bwd(ptr(g.contiguous()), ptr(idx), ptr(weights), ptr(cumsum), ptr(gf), N, F, stream()))
+        return gf, None, None, None
+
+
 class Bernoulli_entropy(nn.Module):
     """utils_bpp_acc.py:1002-1013: bits of x in {-1,+1} under P(+1) = p (clamped to [1e-6, 1-1e-6])."""
 
@@ -482,12 +506,9 @@ class CNC_context_models(nn.Module):
             context = torch.cat([context, context_pn, Pg_col], dim=-1)
         else:
             context = torch.cat([context, Pg_col], dim=-1)
-        mean = torch.index_select(self.context_model_2D[n - 1](context), 0, indices_2D)
-        if differentiable:
-            mean = torch.sum(align_and_pack.apply(mean, unique_cnt_2D, 0.0, 2), dim=1)
-        else:
-            cs = torch.cat([torch.zeros(1, dtype=torch.int64, device=mean.device), torch.cumsum(unique_cnt_2D, 0)])
-            mean = pack_and_align.segment_wsum(mean.contiguous(), cs)
+        # index_select by the sort permutation + per-row sum (utils_bpp_acc.py:741-745) as one segment reduction
+        cs = torch.cat([torch.zeros(1, dtype=torch.int64, device=points_n.device), torch.cumsum(unique_cnt_2D, 0)])
+        mean = segment_sum.apply(self.context_model_2D[n - 1](context), cs, None, indices_2D.contiguous())
         return mean / unique_cnt_2D.unsqueeze(-1), unique_value_2D, (points_n, indices_2D, unique_value_2D, unique_cnt_2D)
 
     # ------------------------------------------------------------------------------------------ loss
@@ -541,17 +562,23 @@ class CNC_context_models(nn.Module):
         if pts_l:
             pts, ptsn, Pgc, nl, cnt, vals = (torch.cat(t, 0) for t in (pts_l, ptsn_l, Pg_l, n_l, cnt_l, val_l))
             mask, overlap = self.query_binary_vxl_qlist(pts, binary_vxl, nl, return_overlap_area=True)
-            mask_packed = align_and_pack.apply(mask.unsqueeze(-1).to(torch.float), cnt, 0)
-            mask_cnt = torch.sum(mask_packed[:, :, 0], dim=1).to(torch.long)
+            # voxels per entry that touch the occupancy, overlap weights normalised per entry, weighted mean of the MLP
+            # outputs (utils_bpp_acc.py:553-566): segment reductions over the ragged lists instead of padded [E, M, F] tensors
+            zero = torch.zeros(1, dtype=torch.int64, device=pts.device)
+            cs_all = torch.cat([zero, torch.cumsum(cnt, 0)])
+            mask_cnt = pack_and_align.segment_wsum(mask.to(torch.float).unsqueeze(-1), cs_all).squeeze(-1).to(torch.long)
             mask_exist = mask_cnt > 0
             mask_cnt, vals = mask_cnt[mask_exist], vals[mask_exist]
-            overlap = torch.clamp(overlap[mask], min=1)
-            ov_packed = align_and_pack.apply(overlap.unsqueeze(-1).to(torch.float), mask_cnt, 0)
-            ov_packed = ov_packed / torch.sum(ov_packed, dim=1, keepdim=True)
+            cs = torch.cat([zero, torch.cumsum(mask_cnt, 0)])
+            if self.use_overlap_area_pool:
+                ov = torch.clamp(overlap[mask], min=1).to(torch.float)
+                ov_sum = pack_and_align.segment_wsum(ov.unsqueeze(-1), cs).squeeze(-1)
+                w = ov / torch.repeat_interleave(ov_sum, mask_cnt)
+            else:
+                w = torch.repeat_interleave(1.0 / mask_cnt.to(torch.float), mask_cnt)
             c = self.max_context_layer_num
             context = Encoding_xyz.forward_diff_levels(ptsn[mask], (nl[mask] - c).to(torch.int), c, binary_vxl=binary_vxl.squeeze(0), PV=1001)
-            mean = align_and_pack.apply(self.context_model_3D(torch.cat([context, Pgc[mask]], dim=-1)), mask_cnt, 0.0)
-            mean = torch.sum(mean * ov_packed, dim=1) if self.use_overlap_area_pool else torch.sum(mean, dim=1) / mask_cnt.unsqueeze(-1)
+            mean = segment_sum.apply(self.context_model_3D(torch.cat([context, Pgc[mask]], dim=-1)), cs, w.contiguous(), None)
             bits = torch.sum(self.entropy_model(vals, mean))
             ttl_bit_sum = ttl_bit_sum + bits / n_valid * self.ttl_hashparams_num_valid_levels
         ttl_num_sum += pq["xyz"].numel()

@@ -78,6 +78,35 @@ segment_wsum_kernel(const float *__restrict__ feat, const float *__restrict__ w,
     out[t] = acc;
 }
 
+// out[i,k] = sum_j w[j] * feat[row(j), k], row(j) = idx ? idx[j] : j, j ascending over [cumsum[i], cumsum[i+1]):
+// the segment reduction of the context models with the gather that precedes it (index_select by the sort permutation,
+// utils_bpp_acc.py:741) folded in, and its backward (idx is a permutation: every feat row is written at most once).
+__global__ void __launch_bounds__(256)
+segment_wsum_idx_kernel(const float *__restrict__ feat, const int64_t *__restrict__ idx, const float *__restrict__ w,
+                        const int64_t *__restrict__ cumsum, float *__restrict__ out, int64_t N, int64_t F) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * F) return;
+    const int64_t i = t / F, k = t % F;
+    const int64_t s = __ldg(cumsum + i), e = __ldg(cumsum + i + 1);
+    float acc = 0.f;
+    for (int64_t j = s; j < e; j++) {
+        const float v = __ldg(feat + (idx ? __ldg(idx + j) : j) * F + k);
+        acc = __fadd_rn(acc, w ? __fmul_rn(v, __ldg(w + j)) : v);
+    }
+    out[t] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+segment_wsum_idx_bwd_kernel(const float *__restrict__ gout, const int64_t *__restrict__ idx, const float *__restrict__ w,
+                            const int64_t *__restrict__ cumsum, float *__restrict__ gfeat, int64_t N, int64_t F) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * F) return;
+    const int64_t i = t / F, k = t % F;
+    const int64_t s = __ldg(cumsum + i), e = __ldg(cumsum + i + 1);
+    const float g = __ldg(gout + t);
+    for (int64_t j = s; j < e; j++) gfeat[(idx ? __ldg(idx + j) : j) * F + k] = w ? __fmul_rn(g, __ldg(w + j)) : g;
+}
+
 // ------------------------------------------------------------------------------------------
 // K4 / K5: vote planes (cnt_np_embed).  Counts are small exact integers in fp32, so the
 // order of the atomic adds does not change the result.
@@ -351,6 +380,22 @@ int cnc_vote3_bwd(const int16_t *pts_by_row, const int64_t *seg, const uint8_t *
     Vote3BwdArgs a{pts_by_row, seg, binary_vxl, sign_bits, {grad_xy, grad_xz, grad_yz}, grad_table, Rb, resolution, hashmap_size};
     vote3_bwd_kernel<<<div_up((uint64_t)hashmap_size * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return check_launch("vote3_bwd");
+}
+
+int cnc_segment_wsum_idx(const float *feat, const int64_t *idx, const float *w, const int64_t *cumsum, float *out, int64_t N,
+                         int64_t F, cnc_stream_t stream) {
+    if (N * F == 0) return CNC_OK;
+    if (!feat || !cumsum || !out) { set_error("segment_wsum_idx: null pointer"); return CNC_EINVAL; }
+    segment_wsum_idx_kernel<<<div_up((uint64_t)(N * F), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(feat, idx, w, cumsum, out, N, F);
+    return check_launch("segment_wsum_idx");
+}
+
+int cnc_segment_wsum_idx_bwd(const float *grad_out, const int64_t *idx, const float *w, const int64_t *cumsum, float *grad_feat,
+                             int64_t N, int64_t F, cnc_stream_t stream) {
+    if (N * F == 0) return CNC_OK;
+    if (!grad_out || !cumsum || !grad_feat) { set_error("segment_wsum_idx_bwd: null pointer"); return CNC_EINVAL; }
+    segment_wsum_idx_bwd_kernel<<<div_up((uint64_t)(N * F), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(grad_out, idx, w, cumsum, grad_feat, N, F);
+    return check_launch("segment_wsum_idx_bwd");
 }
 
 }  // extern "C"

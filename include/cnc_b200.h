@@ -142,6 +142,14 @@ int cnc_align_pack_bwd(const float *dpacked, const int64_t *cnt, const int64_t *
  * replaces the pattern align_and_pack -> mul -> sum(dim=1), utils_bpp_acc.py:842-848,563-566. */
 int cnc_segment_wsum(const float *feat, const float *w, const int64_t *cumsum, float *out,
                      int64_t N, int64_t F, cnc_stream_t stream);
+/* The same reduction with the preceding row gather folded in (out[i] = sum_j w[j] * feat[idx[j]], idx nullable) and its
+ * backward w.r.t. feat (grad_feat[idx[j]] = w[j] * grad_out[i]; idx must be a permutation, rows outside every segment
+ * are left untouched): the differentiable form used by the rate term (utils_bpp_acc.py:563-566,741-745). */
+int cnc_segment_wsum_idx(const float *feat, const int64_t *idx, const float *w, const int64_t *cumsum,
+                         float *out, int64_t N, int64_t F, cnc_stream_t stream);
+int cnc_segment_wsum_idx_bwd(const float *grad_out, const int64_t *idx, const float *w,
+                             const int64_t *cumsum, float *grad_feat, int64_t N, int64_t F,
+                             cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Entropy coder (torchac-compatible 32-bit binary range coder).

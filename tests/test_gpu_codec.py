@@ -204,3 +204,31 @@ def test_fused_vote_planes_equal_the_list_based_kernels(cuda):
     assert torch.equal(g_new != 0, g_old != 0)
     torch.testing.assert_close(g_new, g_old, rtol=1e-4, atol=1e-6 * float(g_old.abs().max()))
     assert float(g_old.abs().max()) > 0
+
+
+def test_segment_sum_matches_padded_flow(cuda):
+    """segment_sum (cnc_segment_wsum_idx / _bwd) == index_select -> align_and_pack -> * weights -> sum(dim=1) of the
+    reference's rate term (utils_bpp_acc.py:563-566,741-745), values and gradients"""
+    from cnc_b200.context_models import align_and_pack, segment_sum
+
+    g = torch.Generator(device="cpu").manual_seed(3)
+    cnt = torch.randint(0, 7, (500,), generator=g).to(cuda)
+    cnt[::50] = 0
+    M = int(cnt.sum())
+    cs = torch.cat([torch.zeros(1, dtype=torch.int64, device=cuda), torch.cumsum(cnt, 0)])
+    perm = torch.randperm(M + 13, generator=g)[:M].to(cuda)          # rows of feat that are used, in segment order
+    w = torch.rand(M, generator=g).to(cuda)
+    for use_idx, use_w in ((True, True), (True, False), (False, True)):
+        feat = torch.randn(M + 13, 8, generator=g).to(cuda).requires_grad_(True)
+        gout = torch.randn(500, 8, generator=g).to(cuda)
+        got = segment_sum.apply(feat, cs, w if use_w else None, perm if use_idx else None)
+        got.backward(gout)
+        g_got = feat.grad.clone()
+        feat.grad = None
+        rows = torch.index_select(feat, 0, perm) if use_idx else feat[:M]
+        if use_w:
+            rows = rows * w[:, None]
+        want = torch.sum(align_and_pack.apply(rows, cnt, 0.0, 2), dim=1)
+        want.backward(gout)
+        torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(g_got, feat.grad, rtol=1e-6, atol=1e-7)
