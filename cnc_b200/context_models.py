@@ -171,6 +171,24 @@ class segment_sum(Function):
         return gf, None, None, None
 
 
+class _LevelSums(Function):
+    """sum of all entries of every level of a table [rows, F] -> [L]; the backward hands one full-size gradient tensor
+    to autograd instead of one zero-padded tensor per level slice (what slicing under autograd does)."""
+
+    @staticmethod
+    def forward(ctx, params_q, offsets):
+        ctx.offsets, ctx.shape = tuple(int(o) for o in offsets), tuple(params_q.shape)
+        return torch.stack([params_q[o0:o1].sum() for o0, o1 in zip(ctx.offsets[:-1], ctx.offsets[1:])])
+
+    @staticmethod
+    def backward(ctx, g):
+        offs = ctx.offsets
+        reps = torch.tensor([o1 - o0 for o0, o1 in zip(offs[:-1], offs[1:])], device=g.device)
+        gr = torch.zeros(ctx.shape[0], device=g.device, dtype=g.dtype)
+        gr[offs[0]:offs[-1]] = torch.repeat_interleave(g, reps)
+        return gr.unsqueeze(-1).expand(ctx.shape).contiguous(), None
+
+
 class Bernoulli_entropy(nn.Module):
     """utils_bpp_acc.py:1002-1013: bits of x in {-1,+1} under P(+1) = p (clamped to [1e-6, 1-1e-6])."""
 
@@ -327,6 +345,17 @@ class CNC_context_models(nn.Module):
         pos, neg = (ttl + s) / 2.0, (ttl - s) / 2.0
         Pg = pos / ttl
         return Pg, pos * (-torch.log2(Pg)) + neg * (-torch.log2(1 - Pg)), ttl
+
+    def level_entropies(self, params_q, offsets=None):
+        """get_BiRF_wentropy_leveln for every level at once (same arithmetic, utils_bpp_acc.py:472-486): ([Pg_n], [bit_n])"""
+        offsets = self.offs if offsets is None else offsets
+        F = params_q.shape[-1]
+        ttl = torch.tensor([(o1 - o0) * F for o0, o1 in zip(offsets[:-1], offsets[1:])], device=params_q.device, dtype=torch.float32)
+        s = _LevelSums.apply(params_q, offsets)
+        pos, neg = (ttl + s) / 2.0, (ttl - s) / 2.0
+        Pg = pos / ttl
+        bits = pos * (-torch.log2(Pg)) + neg * (-torch.log2(1 - Pg))
+        return list(Pg.unbind(0)), list(bits.unbind(0))
 
     def init_binary_vxl_coords(self, scale=512):
         t = scale // self.binary_vxl_len
@@ -527,14 +556,20 @@ class CNC_context_models(nn.Module):
         pns = self.get_pn_embed_frac3(finest, self.idx_coords2_tmp) if self.use_dimension_wise else {}
         for axis, Enc in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz)):
             pn = pns.get(axis)
+            Pgs_2D, bits_2D = self.level_entropies(pq[axis], self.offs_2D)
+            means, rows_l = [], []
             for n in range(self.n_levels_2D):
-                Pg_n, bit_n, _ = self.get_BiRF_wentropy_leveln(pq[axis], n, self.offs_2D)
+                Pg_n, bit_n = Pgs_2D[n], bits_2D[n]
                 if not (n in self.skip_levels_2D or n >= self.Pg_level_2D):
                     mean, rows, batch = self._probs_2D(Enc, None, planes[axis], n, pn, Pg_n,
                                                        self.batched_inputs_list.get((axis, n)), differentiable=True)
                     self.batched_inputs_list[(axis, n)] = batch
-                    bit_n = torch.sum(self.entropy_model(pq[axis][rows, :], mean))
-                ttl_bit_sum = ttl_bit_sum + bit_n
+                    means.append(mean)
+                    rows_l.append(rows)
+                else:
+                    ttl_bit_sum = ttl_bit_sum + bit_n
+            if means:   # one gather of the coded rows of the plane (one index backward instead of one per level)
+                ttl_bit_sum = ttl_bit_sum + torch.sum(self.entropy_model(pq[axis][torch.cat(rows_l), :], torch.cat(means, 0)))
             ttl_num_sum += pq[axis].numel()
 
         if sample_num is not None:
@@ -545,22 +580,24 @@ class CNC_context_models(nn.Module):
             snl, n_valid = self.sample_num_levels, self.ttl_sample_num_valid_levels
         start = torch.round((self.hashparams_num_levels - snl) * torch.rand_like(self.utils_rand)).to(torch.long).tolist()
         pts_l, ptsn_l, Pg_l, n_l, cnt_l, val_l = [], [], [], [], [], []
+        Pgs_3D, bits_3D = self.level_entropies(pq["xyz"])
+        snl_h = snl.tolist()
         for n in range(self.n_levels):
-            Pg_n, bit_n, _ = self.get_BiRF_wentropy_leveln(pq["xyz"], n)
+            Pg_n, bit_n = Pgs_3D[n], bits_3D[n]
             if n in self.skip_levels_3D or n >= self.Pg_level:
                 ttl_bit_sum = ttl_bit_sum + bit_n
                 continue
-            lo, hi = start[n], start[n] + int(snl[n])
-            cs = self.unique_count_cumsum_list[n]
-            p = self.pos_grid_sorted_list[n][int(cs[lo]):int(cs[hi])]
+            lo, hi = start[n], start[n] + int(snl_h[n])
+            p = self.pos_grid_sorted_list[n][self._cs_host(n, lo):self._cs_host(n, hi)]
             pts_l.append(p)
             ptsn_l.append((p - 0.5) / self.scales_list[n, :])
             Pg_l.append(Pg_n.reshape(1, 1).expand(p.shape[0], 1))
             n_l.append(torch.full((p.shape[0],), n, dtype=torch.int64, device=p.device))
             cnt_l.append(self.unique_count_list[n][lo:hi])
-            val_l.append(pq["xyz"][self.unique_value_list[n][lo:hi] + self.offs[n]])
+            val_l.append(self.unique_value_list[n][lo:hi] + self.offs[n])
         if pts_l:
-            pts, ptsn, Pgc, nl, cnt, vals = (torch.cat(t, 0) for t in (pts_l, ptsn_l, Pg_l, n_l, cnt_l, val_l))
+            pts, ptsn, Pgc, nl, cnt, rows3 = (torch.cat(t, 0) for t in (pts_l, ptsn_l, Pg_l, n_l, cnt_l, val_l))
+            vals = pq["xyz"][rows3]   # one gather of the sampled entries (one index backward instead of one per level)
             mask, overlap = self.query_binary_vxl_qlist(pts, binary_vxl, nl, return_overlap_area=True)
             # voxels per entry that touch the occupancy, overlap weights normalised per entry, weighted mean of the MLP
             # outputs (utils_bpp_acc.py:553-566): segment reductions over the ragged lists instead of padded [E, M, F] tensors
