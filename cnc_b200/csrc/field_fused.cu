@@ -37,13 +37,20 @@
 namespace cnc {
 namespace ff {
 
-constexpr int NSTAGE = 4;
+#ifndef CNC_FF_NSTAGE
+#define CNC_FF_NSTAGE 2
+#endif
+#ifndef CNC_FF_NA
+#define CNC_FF_NA 2
+#endif
+constexpr int NSTAGE = CNC_FF_NSTAGE;   // weight ring depth
+constexpr int NA = CNC_FF_NA;           // layer-1 operand slots (feature chunks in flight between gather warps and MMA warp)
 constexpr uint32_t STAGE_BYTES = 2u * 160u * 128u;  // hi + lo of a [160 x 32] fp32 chunk (or two [80 x 32] chunks)
 constexpr uint32_t A_HALF = 128u * 128u;            // one [128 x 32] fp32 chunk
 constexpr uint32_t A_SLOT_BYTES = 2u * A_HALF;
 constexpr uint32_t SMEM_B = 0;
 constexpr uint32_t SMEM_A = NSTAGE * STAGE_BYTES;            // 163840
-constexpr uint32_t SMEM_BAR = SMEM_A + 2 * A_SLOT_BYTES;     // 229376
+constexpr uint32_t SMEM_BAR = SMEM_A + NA * A_SLOT_BYTES;
 constexpr uint32_t SMEM_LVL = SMEM_BAR + 128;                // 16 x LevelTab (32 B)
 constexpr uint32_t SMEM_W5 = SMEM_LVL + 16 * 32;             // W5 [3][160] + b5 [3] (+pad) fp32
 constexpr uint32_t SMEM_DYN = SMEM_W5 + 484 * 4;             // 231968 <= 232448
@@ -310,7 +317,7 @@ __device__ __forceinline__ void acc_block(uint32_t tl, uint32_t c_main, int b8, 
 // (+bias, ReLU, split) -> hi at dst_hi, lo at dst_lo
 template <uint32_t MAIN2, uint32_t SMALL>
 __device__ __forceinline__ void ep_hidden(uint32_t tl, int cg, uint32_t c_main, uint32_t dst_hi, uint32_t dst_lo,
-                                          const float *__restrict__ bias, float *__restrict__ save_row) {
+                                          const float *__restrict__ bias, float *__restrict__ save_row, uint32_t part_bar = 0u) {
 #pragma unroll 1
     for (int b = cg; b < 20; b += 4) {
         float v[8];
@@ -329,6 +336,11 @@ __device__ __forceinline__ void ep_hidden(uint32_t tl, int cg, uint32_t c_main, 
         }
         tmem_st8(tl + dst_hi + 8 * b, hi);
         tmem_st8(tl + dst_lo + 8 * b, lo);
+        if (part_bar != 0u && b < 16) {   // this 32-column group is complete once all four column groups have stored
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(part_bar + 8u * (uint32_t)(b >> 2));
+        }
     }
     tc_wait_st();
 }
@@ -349,19 +361,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
     auto b_full = [&](uint32_t s) { return bar0 + 8u * s; };
     auto b_empty = [&](uint32_t s) { return bar0 + 8u * (NSTAGE + s); };
     auto a_full = [&](uint32_t s) { return bar0 + 8u * (2 * NSTAGE + s); };
-    auto a_empty = [&](uint32_t s) { return bar0 + 8u * (2 * NSTAGE + 2 + s); };
-    const uint32_t layer_done = bar0 + 8u * (2 * NSTAGE + 4);
-    const uint32_t act_ready = bar0 + 8u * (2 * NSTAGE + 5);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SMEM_BAR + 8 * (2 * NSTAGE + 6));
+    auto a_empty = [&](uint32_t s) { return bar0 + 8u * (2 * NSTAGE + NA + s); };
+    const uint32_t layer_done = bar0 + 8u * (2 * NSTAGE + 2 * NA);
+    const uint32_t act_ready = bar0 + 8u * (2 * NSTAGE + 2 * NA + 1);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SMEM_BAR + 8 * (2 * NSTAGE + 2 * NA + 2));
+    // act_part(i): columns [32 i, 32 i + 32) of h3 are in TMEM (ep3 -> L4 wavefront), one completion per tile each
+    auto act_part = [&](uint32_t i) { return bar0 + 8u * (2 * NSTAGE + 2 * NA + 3 + i); };
+    static_assert(2 * NSTAGE + 2 * NA + 7 <= 16, "barrier block is 128 bytes");
     LevelTab *lvl = reinterpret_cast<LevelTab *>(smem + SMEM_LVL);
     float *w5s = reinterpret_cast<float *>(smem + SMEM_W5);
 
     if (threadIdx.x == 0) {
         if (sbase & 1023u) __trap();  // the 128B-swizzled operand tiles need a 1024-byte aligned base
         for (int s = 0; s < NSTAGE; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(a_full(s), NCOMPUTE); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < NA; s++) { mbar_init(a_full(s), NCOMPUTE); mbar_init(a_empty(s), 1); }
         mbar_init(layer_done, 1);
         mbar_init(act_ready, NCOMPUTE);
+        for (int i = 0; i < 4; i++) mbar_init(act_part(i), NCOMPUTE);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 16) {
@@ -422,6 +438,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                         const uint64_t dah = dah0 + (uint64_t)(2 * k4), dal = dal0 + (uint64_t)(2 * k4);
                         mma_ss_bf16(tbase + d_small, dal, dbl, idb, acc_s);   // Ahi*Blo + Alo*Bhi
                         mma_ss(tbase + d_main, dah, dbh, id, acc_m);          // Ahi*Bhi
+#ifdef CNC_FF_SPLIT_L4
+                    } else if (N == 160 && shared_acc) {
+                        // one accumulator for both products: two independent column halves instead of one dependent chain
+                        constexpr uint32_t idh = idesc_tf32<80>(), idbh = idesc_bf16<80>();
+                        constexpr uint64_t half = (80u * 128u) >> 4;
+                        const uint32_t ah = tbase + a_hi + 32u * at + 8u * k4, al = tbase + a_lo + 32u * at + 8u * k4;
+                        mma_ts_bf16(tbase + d_small, al, dbl, idbh, acc_s);
+                        mma_ts_bf16(tbase + d_small + 80u, al, dbl + half, idbh, acc_s);
+                        mma_ts(tbase + d_main, ah, dbh, idh, 1u);
+                        mma_ts(tbase + d_main + 80u, ah, dbh + half, idh, 1u);
+#endif
                     } else {
                         const uint32_t ah = tbase + a_hi + 32u * at + 8u * k4, al = tbase + a_lo + 32u * at + 8u * k4;
                         mma_ts_bf16(tbase + d_small, al, dbl, idb, acc_s);
@@ -444,8 +471,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             // bias of the 32-step accumulation), small [320,480)
 #pragma unroll 1
             for (int kc = 0; kc < 8; kc++) {
-                const uint32_t sl = a_cons & 1u;
-                mbar_wait_spin(a_full(sl), (a_cons >> 1) & 1u);
+                const uint32_t sl = a_cons % NA;
+                mbar_wait_spin(a_full(sl), (a_cons / NA) & 1u);
                 const uint32_t ab = sbase + SMEM_A + sl * A_SLOT_BYTES;
                 if (elect_one()) CNC_TL(32 + kc);
                 chunk_mma(N160{}, FromSmem{}, 1, ab, ab + A_HALF, (kc & 1) ? 160u : 0u, kc < 2, 320u, kc == 0, a_empty(sl),
@@ -471,14 +498,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                 for (int kc = 0; kc < 3; kc++)
                     chunk_mma(N160{}, FromTmem{}, 1, 32u * kc, 96u + 32u * kc, 192u, kc == 0, 352u, kc == 0,
                               kc == 2 ? layer_done : 0u, 0u);
-                // L4: A hi [192,352) lo [352,512) -> [0,160) (no room for a second accumulator)
-                mbar_wait_spin(act_ready, act_cnt & 1u); act_cnt++;
-                tc_fence_after();
-                if (elect_one()) CNC_TL(44);
+                // L4: A hi [192,352) lo [352,512) -> [0,160) (no room for a second accumulator).  Wavefront behind ep3:
+                // K chunk kc needs only columns [32 kc, 32 kc + 32) of h3, and [0,160) is dead once L3 has completed.
 #pragma unroll 1
-                for (int kc = 0; kc < 5; kc++)
+                for (int kc = 0; kc < 5; kc++) {
+                    if (kc < 4) mbar_wait_spin(act_part(kc), it & 1u);
+                    else { mbar_wait_spin(act_ready, act_cnt & 1u); act_cnt++; }
+                    tc_fence_after();
+                    if (kc == 0 && elect_one()) CNC_TL(44);
                     chunk_mma(N160{}, FromTmem{}, 1, 192u + 32u * kc, 352u + 32u * kc, 0u, false, 0u, kc == 0,
                               kc == 4 ? layer_done : 0u, 0u, it, 53 + kc);
+                }
                 if (elect_one()) CNC_TL(45);
             }
             // The next tile's first feature chunks are usually already waiting in smem, and its L1 overwrites
@@ -552,7 +582,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                 *reinterpret_cast<float4 *>(d) = make_float4(f[0], f[1], f[2], f[3]);
                 *reinterpret_cast<float4 *>(d + 4) = make_float4(f[4], f[5], f[6], (c == 7 && q == 3) ? 1.0f : f[7]);
             }
-            const uint32_t sl = a_prod & 1u, use = a_prod >> 1;
+            const uint32_t sl = a_prod % NA, use = a_prod / NA;
             if (use > 0) mbar_wait(a_empty(sl), (use - 1) & 1u);
             store_oct(smem + SMEM_A + sl * A_SLOT_BYTES, r, q, f);
             fence_async_smem();
@@ -585,8 +615,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
         };
 
         float x[3], xn[3];
-        Pend pa, pb;
+        Pend pa, pb;   // gathers in flight: even chunks use pa, odd chunks pb
         int c0 = 0;  // chunks of the current tile that were already produced during the previous tile's layer chain
+        // chunks of the NEXT tile produced while this tile's L2 / L4 (density-only: the tile's tail) run on the tensor
+        // pipe.  All NA operand slots are free by then (L1 is complete), and no more than NA chunks may be produced
+        // before this tile's last epilogue has arrived on act_ready (the MMA warp frees slots only after that).
+        constexpr int PRE2 = NA >= 4 ? 2 : 1, PRE4 = NA >= 3 ? 2 : 1;
+        static_assert(PRE2 + PRE4 <= NA, "pre-gathered chunks must fit the operand slots");
+        auto pre = [&](auto ctag, uint32_t prow) {   // finish chunk c of the next tile (gather already in flight), start c + 1
+            constexpr int c = decltype(ctag)::value;
+            if (c + 1 < 6) issue(c + 1, xn, (c & 1) ? pa : pb);
+            finish(c, prow, (c & 1) ? pb : pa);
+        };
+        using C0 = std::integral_constant<int, 0>;
+        using C1 = std::integral_constant<int, 1>;
+        using CA = std::integral_constant<int, PRE2>;
+        using CB = std::integral_constant<int, PRE2 + 1>;
         if (my_tiles > 0) {
             load_x(blockIdx.x, x);
             issue(0, x, pa);
@@ -599,6 +643,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             const bool has_next = it + 1 < my_tiles;
             if (threadIdx.x == 0) CNC_TL(0);
             // ---- L1 feature chunks c0..7; pa holds the gather of chunk c
+            if (c0 & 1) {   // pb holds chunk c0
+                if (c0 + 1 < 6) issue(c0 + 1, x, pa);
+                finish(c0, row, pb);
+                c0++;
+            }
 #pragma unroll 1
             for (int c = c0; c < 6; c += 2) {
                 issue(c + 1, x, pb);
@@ -627,9 +676,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             tc_fence_before();
             mbar_arrive(act_ready);
             if (threadIdx.x == 0) CNC_TL(11);
-            if (has_next) {  // while L2 runs: chunk 0 of the next tile
-                issue(1, xn, pb);
-                finish(0, row + gridDim.x * TILE_M, pa);
+            float dv[3] = {0.f, 0.f, 0.f};   // view direction of the row (column groups 2, 3 build the SH block in ep2)
+            if (!DENSITY_ONLY && q >= 2 && live) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) dv[d] = __ldcg(a.dirs + (size_t)row * 3 + d);
+            }
+            if (has_next) {  // while L2 runs: the first chunk(s) of the next tile
+                pre(C0{}, row + gridDim.x * TILE_M);
+                if (PRE2 >= 2) pre(C1{}, row + gridDim.x * TILE_M);
             }
             // ---- ep2: acc2 [320,400)+[400,480): col 0 -> sigma, cols 1..79 -> geo -> head input (+ SH16 block)
             mbar_wait(layer_done, done_cnt & 1u); done_cnt++;
@@ -666,8 +720,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                     float d3[3], sh[16];
 #pragma unroll
                     for (int d = 0; d < 3; d++) {
-                        const float dv = live ? __ldcg(a.dirs + (size_t)row * 3 + d) : 0.f;
-                        const float d01 = __fdiv_rn(__fadd_rn(dv, 1.0f), 2.0f);  // ngp.py:540
+                        const float d01 = __fdiv_rn(__fadd_rn(dv[d], 1.0f), 2.0f);  // ngp.py:540
                         d3[d] = __fsub_rn(__fmul_rn(d01, 2.f), 1.f);             // tcnn maps back to [-1,1]
                     }
                     sh16_eval_h(d3[0], d3[1], d3[2], sh);
@@ -689,14 +742,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                 mbar_wait(layer_done, done_cnt & 1u); done_cnt++;
                 tc_fence_after();
                 if (threadIdx.x == 0) CNC_TL(14);
-                ep_hidden<NONE, 352u>(tl, q, 192u, 192u, 352u, bias + BIAS3, (SAVE && live) ? a.sv_h3 + (size_t)row * 160 : nullptr);
+                ep_hidden<NONE, 352u>(tl, q, 192u, 192u, 352u, bias + BIAS3, (SAVE && live) ? a.sv_h3 + (size_t)row * 160 : nullptr,
+                                      act_part(0));
                 tc_fence_before();
                 mbar_arrive(act_ready);
                 if (threadIdx.x == 0) CNC_TL(15);
-                if (has_next) {  // while L4 (the longest of the small layers) runs: chunk 1 of the next tile
-                    issue(2, xn, pa);
-                    finish(1, row + gridDim.x * TILE_M, pb);
-                    c0 = 2;
+                if (has_next) {  // while L4 (the longest of the small layers) runs: the next chunk(s) of the next tile
+                    pre(CA{}, row + gridDim.x * TILE_M);
+                    if (PRE4 >= 2) pre(CB{}, row + gridDim.x * TILE_M);
+                    c0 = PRE2 + PRE4;
                 }
                 // ---- ep4 + the last layer: h4 = relu(acc4 + b4) stays in registers; Linear(160,3) is 3 x 40 FFMA per
                 // thread on its own columns (W5 broadcast from smem), the four column groups of a row meet in TMEM
@@ -761,7 +815,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             tc_fence_before();
             mbar_arrive(act_ready);  // this tile's accumulators are consumed: the next tile's L1 may overwrite them
             if (has_next) {
-                if (DENSITY_ONLY) { issue(2, xn, pa); finish(1, row + gridDim.x * TILE_M, pb); c0 = 2; }
+                if (DENSITY_ONLY) { pre(CA{}, row + gridDim.x * TILE_M); c0 = PRE2 + 1; }
                 x[0] = xn[0]; x[1] = xn[1]; x[2] = xn[2];
             }
         }
