@@ -51,7 +51,7 @@ constexpr uint32_t A_SLOT_BYTES = 2u * A_HALF;
 constexpr uint32_t SMEM_B = 0;
 constexpr uint32_t SMEM_A = NSTAGE * STAGE_BYTES;            // 163840
 constexpr uint32_t SMEM_BAR = SMEM_A + NA * A_SLOT_BYTES;
-constexpr uint32_t SMEM_LVL = SMEM_BAR + 128;                // 16 x LevelTab (32 B)
+constexpr uint32_t SMEM_LVL = SMEM_BAR + 256;                // 16 x LevelTab (32 B)
 constexpr uint32_t SMEM_W5 = SMEM_LVL + 16 * 32;             // W5 [3][160] + b5 [3] (+pad) fp32
 constexpr uint32_t SMEM_DYN = SMEM_W5 + 484 * 4;             // 231968 <= 232448
 
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SMEM_BAR + 8 * (2 * NSTAGE + 2 * NA + 2));
     // act_part(i): columns [32 i, 32 i + 32) of h3 are in TMEM (ep3 -> L4 wavefront), one completion per tile each
     auto act_part = [&](uint32_t i) { return bar0 + 8u * (2 * NSTAGE + 2 * NA + 3 + i); };
-    static_assert(2 * NSTAGE + 2 * NA + 7 <= 16, "barrier block is 128 bytes");
+    static_assert(2 * NSTAGE + 2 * NA + 7 <= 32, "barrier block is 256 bytes");
     LevelTab *lvl = reinterpret_cast<LevelTab *>(smem + SMEM_LVL);
     float *w5s = reinterpret_cast<float *>(smem + SMEM_W5);
 
@@ -426,6 +426,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                 const uint64_t dbh0 = smem_desc(bst + (uint32_t)at * (2u * N * 128u)),
                                dbl0 = smem_desc(bst + (uint32_t)at * (2u * N * 128u) + (uint32_t)N * 128u);
                 const uint64_t dah0 = A_IN_SMEM ? smem_desc(a_hi) : 0ull, dal0 = A_IN_SMEM ? smem_desc(a_lo) : 0ull;
+#ifdef CNC_FF_L4_GROUP
+                if (!A_IN_SMEM && shared_acc) {   // one accumulator for both products: group the MMAs of a chunk by kind
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; k4++)
+                        mma_ts_bf16(tbase + d_small, tbase + a_lo + 32u * at + 8u * k4, dbl0 + (uint64_t)(2 * k4), idb,
+                                    (first_small && at == 0 && k4 == 0) ? 0u : 1u);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; k4++)
+                        mma_ts(tbase + d_main, tbase + a_hi + 32u * at + 8u * k4, dbh0 + (uint64_t)(2 * k4), id, 1u);
+                    continue;
+                }
+#endif
 #pragma unroll
                 for (int k4 = 0; k4 < 4; k4++) {
                     // +32 bytes along K inside the 128-byte swizzle row == +2 in the descriptor's address field.
@@ -530,10 +542,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             chunk_meta((int)(G % CPT), ofs, bytes);
             if (a.dbg != nullptr && blockIdx.x == 0 && G / CPT == 1 && elect_one()) a.dbg[64 + G % CPT] = clock64();
             bulk_g2s_elect(sbase + SMEM_B + s * STAGE_BYTES, blob + ofs, bytes, b_full(s));
-            if (a.dbg != nullptr && blockIdx.x == 0 && G / CPT == 1) {   // profiling aid: observe the arrival (serialises the loads)
-                mbar_wait_spin(b_full(s), use & 1u);
-                if (elect_one()) a.dbg[96 + G % CPT] = clock64();
-            }
         }
     } else {
         // =============================== gather / epilogue warps ===============================
@@ -546,7 +554,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
         const float3 ainv = make_float3(__fsub_rn(a.aabb[3], a.aabb[0]), __fsub_rn(a.aabb[4], a.aabb[1]), __fsub_rn(a.aabb[5], a.aabb[2]));
 
         // normalised position of this thread's row in tile `tile` (ngp.py:517-518)
-        auto load_x = [&](uint32_t tile, float (&x)[3]) {
+        auto load_pos = [&](uint32_t tile, float (&p)[3]) {
             const uint32_t row = tile * TILE_M + r;
             const bool live = row < a.N;
             if (POLL) {   // the samples of this wave are being uploaded while earlier waves are evaluated
@@ -559,12 +567,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                 } while (++spins < (1u << 23));
             }
             // L2 loads (each value is read once; with POLL the buffer is rewritten by the copy engine between launches)
-            const float px = live ? __ldcg(a.pos + (size_t)row * 3 + 0) : __fadd_rn(amin.x, 0.5f * ainv.x);
-            const float py = live ? __ldcg(a.pos + (size_t)row * 3 + 1) : __fadd_rn(amin.y, 0.5f * ainv.y);
-            const float pz = live ? __ldcg(a.pos + (size_t)row * 3 + 2) : __fadd_rn(amin.z, 0.5f * ainv.z);
-            x[0] = __fdiv_rn(__fsub_rn(px, amin.x), ainv.x);
-            x[1] = __fdiv_rn(__fsub_rn(py, amin.y), ainv.y);
-            x[2] = __fdiv_rn(__fsub_rn(pz, amin.z), ainv.z);
+            p[0] = live ? __ldcg(a.pos + (size_t)row * 3 + 0) : __fadd_rn(amin.x, 0.5f * ainv.x);
+            p[1] = live ? __ldcg(a.pos + (size_t)row * 3 + 1) : __fadd_rn(amin.y, 0.5f * ainv.y);
+            p[2] = live ? __ldcg(a.pos + (size_t)row * 3 + 2) : __fadd_rn(amin.z, 0.5f * ainv.z);
+        };
+        auto normalise = [&](const float (&p)[3], float (&x)[3]) {
+            x[0] = __fdiv_rn(__fsub_rn(p[0], amin.x), ainv.x);
+            x[1] = __fdiv_rn(__fsub_rn(p[1], amin.y), ainv.y);
+            x[2] = __fdiv_rn(__fsub_rn(p[2], amin.z), ainv.z);
+        };
+        auto load_x = [&](uint32_t tile, float (&x)[3]) {
+            float p[3];
+            load_pos(tile, p);
+            normalise(p, x);
         };
         // chunk c of the layer-1 input: [xyz 96 | xy 32 | xz 32 | yz 32 | x, sin/cos 63 | pad]; this thread: columns 8q..8q+7
         auto issue = [&](int c, const float (&x)[3], Pend &p) {   // table loads of chunk c (c < 6)
@@ -657,6 +672,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                 finish(c + 1, row, pb);
                 if (threadIdx.x == 0) CNC_TL(2 + c);
             }
+            if (has_next) load_pos(tile + gridDim.x, xn);   // raw positions of the next tile: in flight behind the sin/cos chunks
 #pragma unroll 1
             for (int c = 6; c < 8; c++) {
                 embed(c, row, x);
@@ -664,7 +680,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             }
             c0 = 0;
             if (has_next) {
-                load_x(tile + gridDim.x, xn);
+                normalise(xn, xn);
                 issue(0, xn, pa);  // in flight during the L1 tail and ep1
             }
             // ---- ep1: h1 = relu(acc1 + b1) -> hi in place [0,160), (hi, lo) bf16 pairs over the second accumulator [160,320)
