@@ -171,6 +171,21 @@ class segment_sum(Function):
         return gf, None, None, None
 
 
+_LEVEL_CONST = {}
+
+
+def _level_const(offsets, F, device):
+    """(level index of every table row [rows] int64, entries per level [L] fp32), cached: building them per call costs a
+    host->device copy (a sync) each"""
+    key = (tuple(int(o) for o in offsets), int(F), str(device))
+    if key not in _LEVEL_CONST:
+        offs = key[0]
+        sizes = torch.tensor([o1 - o0 for o0, o1 in zip(offs[:-1], offs[1:])])
+        level = torch.repeat_interleave(torch.arange(len(sizes)), sizes)
+        _LEVEL_CONST[key] = (level.to(device), (sizes * F).to(torch.float32).to(device))
+    return _LEVEL_CONST[key]
+
+
 class _LevelSums(Function):
     """sum of all entries of every level of a table [rows, F] -> [L]; the backward hands one full-size gradient tensor
     to autograd instead of one zero-padded tensor per level slice (what slicing under autograd does)."""
@@ -183,9 +198,12 @@ class _LevelSums(Function):
     @staticmethod
     def backward(ctx, g):
         offs = ctx.offsets
-        reps = torch.tensor([o1 - o0 for o0, o1 in zip(offs[:-1], offs[1:])], device=g.device)
-        gr = torch.zeros(ctx.shape[0], device=g.device, dtype=g.dtype)
-        gr[offs[0]:offs[-1]] = torch.repeat_interleave(g, reps)
+        level, _ = _level_const(offs, ctx.shape[1], g.device)
+        if offs[0] == 0 and offs[-1] == ctx.shape[0]:
+            gr = g[level]
+        else:
+            gr = torch.zeros(ctx.shape[0], device=g.device, dtype=g.dtype)
+            gr[offs[0]:offs[-1]] = g[level]
         return gr.unsqueeze(-1).expand(ctx.shape).contiguous(), None
 
 
@@ -350,7 +368,7 @@ class CNC_context_models(nn.Module):
         """get_BiRF_wentropy_leveln for every level at once (same arithmetic, utils_bpp_acc.py:472-486): ([Pg_n], [bit_n])"""
         offsets = self.offs if offsets is None else offsets
         F = params_q.shape[-1]
-        ttl = torch.tensor([(o1 - o0) * F for o0, o1 in zip(offsets[:-1], offsets[1:])], device=params_q.device, dtype=torch.float32)
+        _, ttl = _level_const(offsets, F, params_q.device)
         s = _LevelSums.apply(params_q, offsets)
         pos, neg = (ttl + s) / 2.0, (ttl - s) / 2.0
         Pg = pos / ttl
@@ -578,10 +596,10 @@ class CNC_context_models(nn.Module):
             n_valid = sum(int(snl[n]) for n in range(self.n_levels) if n not in self.skip_levels_3D and n < self.Pg_level)
         else:
             snl, n_valid = self.sample_num_levels, self.ttl_sample_num_valid_levels
-        start = torch.round((self.hashparams_num_levels - snl) * torch.rand_like(self.utils_rand)).to(torch.long).tolist()
+        start = torch.round((self.hashparams_num_levels - snl) * torch.rand_like(self.utils_rand)).to(torch.long)
+        start, snl_h = torch.stack([start, snl.to(torch.long)]).tolist()   # one device->host read for both
         pts_l, ptsn_l, Pg_l, n_l, cnt_l, val_l = [], [], [], [], [], []
         Pgs_3D, bits_3D = self.level_entropies(pq["xyz"])
-        snl_h = snl.tolist()
         for n in range(self.n_levels):
             Pg_n, bit_n = Pgs_3D[n], bits_3D[n]
             if n in self.skip_levels_3D or n >= self.Pg_level:
@@ -604,22 +622,24 @@ class CNC_context_models(nn.Module):
             zero = torch.zeros(1, dtype=torch.int64, device=pts.device)
             cs_all = torch.cat([zero, torch.cumsum(cnt, 0)])
             mask_cnt = pack_and_align.segment_wsum(mask.to(torch.float).unsqueeze(-1), cs_all).squeeze(-1).to(torch.long)
-            mask_exist = mask_cnt > 0
-            mask_cnt, vals = mask_cnt[mask_exist], vals[mask_exist]
+            # boolean masks -> index lists once each (every `x[bool_mask]` is a nonzero() plus a host sync of its own)
+            ex_i = (mask_cnt > 0).nonzero().squeeze(1)
+            m_i = mask.nonzero().squeeze(1)
+            mask_cnt, vals = mask_cnt[ex_i], vals[ex_i]
             cs = torch.cat([zero, torch.cumsum(mask_cnt, 0)])
             if self.use_overlap_area_pool:
-                ov = torch.clamp(overlap[mask], min=1).to(torch.float)
+                ov = torch.clamp(overlap[m_i], min=1).to(torch.float)
                 ov_sum = pack_and_align.segment_wsum(ov.unsqueeze(-1), cs).squeeze(-1)
-                w = ov / torch.repeat_interleave(ov_sum, mask_cnt)
+                w = ov / torch.repeat_interleave(ov_sum, mask_cnt, output_size=m_i.numel())
             else:
-                w = torch.repeat_interleave(1.0 / mask_cnt.to(torch.float), mask_cnt)
+                w = torch.repeat_interleave(1.0 / mask_cnt.to(torch.float), mask_cnt, output_size=m_i.numel())
             c = self.max_context_layer_num
-            context = Encoding_xyz.forward_diff_levels(ptsn[mask], (nl[mask] - c).to(torch.int), c, binary_vxl=binary_vxl.squeeze(0), PV=1001)
-            mean = segment_sum.apply(self.context_model_3D(torch.cat([context, Pgc[mask]], dim=-1)), cs, w.contiguous(), None)
+            context = Encoding_xyz.forward_diff_levels(ptsn[m_i], (nl[m_i] - c).to(torch.int), c, binary_vxl=binary_vxl.squeeze(0), PV=1001)
+            mean = segment_sum.apply(self.context_model_3D(torch.cat([context, Pgc[m_i]], dim=-1)), cs, w.contiguous(), None)
             bits = torch.sum(self.entropy_model(vals, mean))
             ttl_bit_sum = ttl_bit_sum + bits / n_valid * self.ttl_hashparams_num_valid_levels
         ttl_num_sum += pq["xyz"].numel()
-        return ttl_bit_sum / ttl_num_sum, float(ttl_bit_sum) / 8 / 1024 / 1024
+        return ttl_bit_sum / ttl_num_sum, float(ttl_bit_sum.detach()) / 8 / 1024 / 1024
 
     # ------------------------------------------------------------------------------------------ encode
     @torch.no_grad()
