@@ -426,18 +426,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                 const uint64_t dbh0 = smem_desc(bst + (uint32_t)at * (2u * N * 128u)),
                                dbl0 = smem_desc(bst + (uint32_t)at * (2u * N * 128u) + (uint32_t)N * 128u);
                 const uint64_t dah0 = A_IN_SMEM ? smem_desc(a_hi) : 0ull, dal0 = A_IN_SMEM ? smem_desc(a_lo) : 0ull;
-#ifdef CNC_FF_L4_GROUP
-                if (!A_IN_SMEM && shared_acc) {   // one accumulator for both products: group the MMAs of a chunk by kind
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; k4++)
-                        mma_ts_bf16(tbase + d_small, tbase + a_lo + 32u * at + 8u * k4, dbl0 + (uint64_t)(2 * k4), idb,
-                                    (first_small && at == 0 && k4 == 0) ? 0u : 1u);
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; k4++)
-                        mma_ts(tbase + d_main, tbase + a_hi + 32u * at + 8u * k4, dbh0 + (uint64_t)(2 * k4), id, 1u);
-                    continue;
-                }
-#endif
 #pragma unroll
                 for (int k4 = 0; k4 < 4; k4++) {
                     // +32 bytes along K inside the 128-byte swizzle row == +2 in the descriptor's address field.
@@ -450,17 +438,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                         const uint64_t dah = dah0 + (uint64_t)(2 * k4), dal = dal0 + (uint64_t)(2 * k4);
                         mma_ss_bf16(tbase + d_small, dal, dbl, idb, acc_s);   // Ahi*Blo + Alo*Bhi
                         mma_ss(tbase + d_main, dah, dbh, id, acc_m);          // Ahi*Bhi
-#ifdef CNC_FF_SPLIT_L4
-                    } else if (N == 160 && shared_acc) {
-                        // one accumulator for both products: two independent column halves instead of one dependent chain
-                        constexpr uint32_t idh = idesc_tf32<80>(), idbh = idesc_bf16<80>();
-                        constexpr uint64_t half = (80u * 128u) >> 4;
-                        const uint32_t ah = tbase + a_hi + 32u * at + 8u * k4, al = tbase + a_lo + 32u * at + 8u * k4;
-                        mma_ts_bf16(tbase + d_small, al, dbl, idbh, acc_s);
-                        mma_ts_bf16(tbase + d_small + 80u, al, dbl + half, idbh, acc_s);
-                        mma_ts(tbase + d_main, ah, dbh, idh, 1u);
-                        mma_ts(tbase + d_main + 80u, ah, dbh + half, idh, 1u);
-#endif
                     } else {
                         const uint32_t ah = tbase + a_hi + 32u * at + 8u * k4, al = tbase + a_lo + 32u * at + 8u * k4;
                         mma_ts_bf16(tbase + d_small, al, dbl, idb, acc_s);
@@ -611,20 +588,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             publish(c, prow, f);
         };
         auto embed = [&](int c, uint32_t prow, const float (&x)[3]) {  // chunks 6, 7
-            // embed column j (0..62): j<3 -> x[j]; else g=(j-3)/3, d=(j-3)%3: even g -> sin(2^(g/2) x_d), odd -> cos
+            // embed column j (0..62): j<3 -> x[j]; else g=(j-3)/3, d=(j-3)%3: even g -> sin(2^(g/2) x_d), odd -> cos.
+            // The cosine of an angle sits three columns after its sine: where both fall into this thread's octet one
+            // sincosf (one range reduction) serves both.
             float f[8];
+            bool done[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) { f[jj] = 0.f; done[jj] = false; }
 #pragma unroll
             for (int jj = 0; jj < 8; jj++) {
                 const int j = (c - 6) * 32 + 8 * q + jj;
-                float v = 0.f;
-                if (j < 3) v = x[j];
-                else if (j < 63) {
+                if (j < 3) f[jj] = x[j];
+                else if (j < 63 && !done[jj]) {
                     const int g = (j - 3) / 3, d = (j - 3) - 3 * g;
                     const float xd = d == 0 ? x[0] : (d == 1 ? x[1] : x[2]);
                     const float ang = __fmul_rn(xd, (float)(1 << (g >> 1)));
-                    v = (g & 1) ? cosf(ang) : sinf(ang);
+                    if (g & 1) f[jj] = cosf(ang);
+                    else if (jj + 3 < 8) {
+                        float sv, cv;
+                        sincosf(ang, &sv, &cv);
+                        f[jj] = sv;
+                        f[jj + 3 < 8 ? jj + 3 : 7] = cv;
+                        done[jj + 3 < 8 ? jj + 3 : 7] = true;
+                    } else f[jj] = sinf(ang);
                 }
-                f[jj] = v;
             }
             publish(c, prow, f);
         };
