@@ -1,4 +1,6 @@
-"""Host-side mirror of the render glue: examples/utils.py:83-216 `render_image_with_occgrid`.
+"""Host-side mirror of the render glue: examples/utils.py:83-216 `render_image_with_occgrid` and
+examples/utils.py:316-489 `render_image_with_occgrid_test` (first version: the reference's wavefront
+loop on the fused kernels).
 
 Same signature and return values; `Rays` is the reference's namedtuple (origins, viewdirs).  During training the
 whole batch is one chunk, at test time `test_chunk_size` rays per chunk (utils.py:169-174).  The closures go through
@@ -12,7 +14,8 @@ from typing import Optional
 
 import torch
 
-from .nerfacc import OccGridEstimator, render_fused, rendering
+from .nerfacc import (OccGridEstimator, accumulate_along_rays_, ray_aabb_intersect, render_fused, render_weight_from_density,
+                      rendering, traverse_grids)
 
 Rays = collections.namedtuple("Rays", ("origins", "viewdirs"))
 
@@ -65,3 +68,74 @@ def render_image_with_occgrid(radiance_field: torch.nn.Module, estimator: OccGri
     out = (colors.view((*rays_shape[:-1], -1)), opacities.view((*rays_shape[:-1], -1)), depths.view((*rays_shape[:-1], -1)),
            sum(n_samples))
     return out + (extras,) if return_extra else out
+
+
+@torch.no_grad()
+def render_image_with_occgrid_test(max_samples: int, radiance_field: torch.nn.Module, estimator: OccGridEstimator, rays: Rays,
+                                   near_plane: float = 0.0, far_plane: float = 1e10, render_step_size: float = 1e-3,
+                                   render_bkgd: Optional[torch.Tensor] = None, cone_angle: float = 0.0, alpha_thre: float = 0.0,
+                                   early_stop_eps: float = 1e-4, timestamps=None):
+    """Test-time renderer, examples/utils.py:316-489: all rays of the image advance together, a few samples per ray and
+    round (more as rays die), a ray leaves the wavefront once its opacity exceeds 1 - early_stop_eps or it reaches the far
+    plane.  -> (rgb, opacity, depth, total_samples).  Every round is march (`cnc_traverse_grids` with a step limit, the
+    ray mask and the previous termination planes) -> fused field forward -> `cnc_render_from_density` with the rays'
+    running transmittance as prefix -> index_add of colour / opacity / depth."""
+    if timestamps is not None:
+        raise NotImplementedError("timestamps belong to the dynamic-scene fields, which the CNC scripts do not use")
+    rays_shape = rays.origins.shape
+    if len(rays_shape) == 3:
+        num_rays = rays_shape[0] * rays_shape[1]
+        rays = namedtuple_map(lambda r: r.reshape([num_rays] + list(r.shape[2:])), rays)
+    else:
+        num_rays = rays_shape[0]
+    device = rays.origins.device
+    opacity = torch.zeros(num_rays, 1, device=device)
+    depth = torch.zeros(num_rays, 1, device=device)
+    rgb = torch.zeros(num_rays, 3, device=device)
+    ray_mask = torch.ones(num_rays, device=device, dtype=torch.bool)
+    min_samples = 1 if cone_angle == 0 else 4   # 1 for synthetic scenes, 4 for real scenes
+    iter_samples = total_samples = 0
+    rays_o, rays_d = rays.origins.contiguous(), rays.viewdirs.contiguous()
+    near_planes = torch.full_like(rays_o[..., 0], fill_value=near_plane)
+    far_planes = torch.full_like(rays_o[..., 0], fill_value=far_plane)
+    t_mins, t_maxs, hits = ray_aabb_intersect(rays_o, rays_d, estimator.aabbs)
+    n_grids = estimator.binaries.size(0)
+    if n_grids > 1:
+        t_sorted, t_indices = torch.sort(torch.cat([t_mins, t_maxs], -1), -1)
+    else:
+        t_sorted = torch.cat([t_mins, t_maxs], -1)
+        t_indices = torch.arange(0, n_grids * 2, device=device, dtype=torch.int64).expand(num_rays, n_grids * 2)
+    opc_thre = 1 - early_stop_eps
+    while iter_samples < max_samples:
+        n_alive = int(ray_mask.sum())
+        if n_alive == 0:
+            break
+        n_samples = max(min(num_rays // n_alive, 64), min_samples)   # the number of samples to add on each ray
+        iter_samples += n_samples
+        intervals, samples, termination_planes = traverse_grids(
+            rays_o, rays_d, estimator.binaries, estimator.aabbs, near_planes, far_planes, render_step_size, cone_angle,
+            n_samples, True, ray_mask, t_sorted, t_indices, hits)
+        t_starts, t_ends = intervals.vals[intervals.is_left], intervals.vals[intervals.is_right]
+        ray_indices = samples.ray_indices[samples.is_valid]
+        packed_info = samples.packed_info
+        if ray_indices.numel():
+            t_dirs = rays_d[ray_indices]
+            positions = rays_o[ray_indices] + t_dirs * (t_starts[:, None] + t_ends[:, None]) / 2.0
+            rgbs, sigmas = radiance_field(positions, t_dirs)
+            weights, _, alphas = render_weight_from_density(t_starts, t_ends, sigmas.squeeze(-1), ray_indices=ray_indices,
+                                                            n_rays=num_rays, prefix_trans=1 - opacity[ray_indices].squeeze(-1))
+            if alpha_thre > 0:
+                vis = alphas >= alpha_thre
+                ray_indices, rgbs, weights, t_starts, t_ends = ray_indices[vis], rgbs[vis], weights[vis], t_starts[vis], t_ends[vis]
+            accumulate_along_rays_(weights, values=rgbs, ray_indices=ray_indices, outputs=rgb)
+            accumulate_along_rays_(weights, values=None, ray_indices=ray_indices, outputs=opacity)
+            accumulate_along_rays_(weights, values=(t_starts + t_ends)[..., None] / 2.0, ray_indices=ray_indices, outputs=depth)
+        near_planes = torch.where(ray_mask, termination_planes, near_planes)   # dead rays keep their last plane
+        # early stopping, and rays that have reached the far plane (fewer samples than asked for) leave the wavefront
+        ray_mask = torch.logical_and(opacity.view(-1) <= opc_thre, packed_info[:, 1] == n_samples)
+        total_samples += int(ray_indices.shape[0])
+    if render_bkgd is not None:
+        rgb = rgb + render_bkgd * (1.0 - opacity)
+    depth = depth / opacity.clamp_min(torch.finfo(rgb.dtype).eps)
+    return (rgb.view((*rays_shape[:-1], -1)), opacity.view((*rays_shape[:-1], -1)), depth.view((*rays_shape[:-1], -1)),
+            total_samples)

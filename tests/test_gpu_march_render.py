@@ -156,3 +156,76 @@ def test_occ_grid_estimator_sampling_and_update(cuda):
     est.eval()
     with pytest.raises(RuntimeError):
         est.update_every_n_steps(0, occ_eval_fn=density)
+
+
+class _BallField(torch.nn.Module):
+    """analytic radiance field: a soft ball of radius 1, colour from position and direction"""
+
+    def query_density(self, x):
+        return (20.0 * torch.sigmoid((1.0 - x.norm(dim=-1, keepdim=True)) * 20)).float()
+
+    def forward(self, x, d):
+        return torch.sigmoid(3.0 * x + d), self.query_density(x)
+
+
+def _ball_estimator(cuda, res=64):
+    from cnc_b200 import nerfacc as N
+
+    est = N.OccGridEstimator(roi_aabb=[-1.5, -1.5, -1.5, 1.5, 1.5, 1.5], resolution=res, levels=1).to(cuda)
+    c = (torch.arange(res, device=cuda) + 0.5) / res * 3 - 1.5
+    X, Y, Z = torch.meshgrid(c, c, c, indexing="ij")
+    est.binaries.copy_(((X * X + Y * Y + Z * Z) <= 1.2 ** 2).unsqueeze(0))
+    return est.eval()
+
+
+def test_test_time_renderer_matches_the_full_march(cuda):
+    """examples/utils.py:316-489 against :83-216 on the same rays: without early stopping the wavefront visits exactly
+    the samples of the one-shot march (the step-limited march resumes on the same t lattice); with it the image moves by
+    less than early_stop_eps and fewer samples are evaluated."""
+    from cnc_b200.render import Rays, render_image_with_occgrid, render_image_with_occgrid_test
+
+    est, field = _ball_estimator(cuda), _BallField().to(cuda).eval()
+    o, d, _, _ = scene(n_rays=1200, seed=4)
+    rays = Rays(origins=T(o, cuda), viewdirs=T(d, cuda))
+    bkgd = torch.ones(3, device=cuda)
+    kw = dict(render_step_size=5e-3, render_bkgd=bkgd)
+    with torch.no_grad():
+        rgb_f, opa_f, dep_f, n_f = render_image_with_occgrid(field, est, rays, test_chunk_size=500, **kw)
+    rgb_w, opa_w, dep_w, n_w = render_image_with_occgrid_test(4096, field, est, rays, early_stop_eps=0.0, **kw)
+    assert n_w >= n_f > 0       # the one-shot path drops samples behind T < 1e-4 (visibility pass), the wavefront keeps them
+    torch.testing.assert_close(rgb_w, rgb_f, rtol=0, atol=2e-4)
+    torch.testing.assert_close(opa_w, opa_f, rtol=0, atol=2e-4)
+    hit = opa_f.view(-1) > 0.5
+    torch.testing.assert_close(dep_w[hit], dep_f[hit], rtol=0, atol=2e-3)
+    rgb_e, opa_e, dep_e, n_e = render_image_with_occgrid_test(4096, field, est, rays, early_stop_eps=1e-4, **kw)
+    assert 0 < n_e < n_w
+    torch.testing.assert_close(rgb_e, rgb_w, rtol=0, atol=3e-4)
+    assert rgb_e.shape == (1200, 3) and opa_e.shape == (1200, 1) and dep_e.shape == (1200, 1)
+    assert (opa_e[1] == 0).all() and torch.equal(rgb_e[1], bkgd)          # the ray that misses the box shows the background
+    # image-shaped rays and a sample budget that ends the loop early
+    img = Rays(origins=rays.origins[:1000].view(25, 40, 3), viewdirs=rays.viewdirs[:1000].view(25, 40, 3))
+    rgb_i, opa_i, _, n_i = render_image_with_occgrid_test(8, field, est, img, early_stop_eps=1e-4, **kw)
+    assert rgb_i.shape == (25, 40, 3) and opa_i.shape == (25, 40, 1) and 0 < n_i <= 8 * 1000
+
+
+def test_test_time_renderer_on_the_fused_field(cuda):
+    """the product field behind the wavefront renderer: same image as the chunked one-shot renderer"""
+    from test_gpu_field import make_field
+    from cnc_b200.render import Rays, render_image_with_occgrid, render_image_with_occgrid_test
+
+    f = make_field(cuda).eval()
+    est = _ball_estimator(cuda, res=128)
+    o, d, _, _ = scene(n_rays=800, seed=5)
+    rays = Rays(origins=T(o, cuda), viewdirs=T(d, cuda))
+    kw = dict(render_step_size=5e-3, render_bkgd=torch.zeros(3, device=cuda))
+    with torch.no_grad():
+        rgb_f, opa_f, _, n_f = render_image_with_occgrid(f, est, rays, test_chunk_size=8192, **kw)
+    rgb_w, opa_w, _, n_w = render_image_with_occgrid_test(4096, f, est, rays, early_stop_eps=1e-4, **kw)
+    assert n_w > 0 and n_f > 0
+    # A resumed march recomputes the cell boundaries from its new start, so a sample whose midpoint sits within an ulp of
+    # a boundary can fall on the other side (the reference's algorithm has the same property); with this field's small
+    # alphas (~2e-3 per sample) one such sample moves a ray by ~1e-3.  Everything else agrees to the early-stop epsilon.
+    for w, f_ in ((rgb_w, rgb_f), (opa_w, opa_f)):
+        diff = (w - f_).abs().amax(dim=-1)
+        assert diff.max().item() < 4e-3
+        assert torch.quantile(diff, 0.98).item() < 3e-4
