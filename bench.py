@@ -368,6 +368,30 @@ def train_bench(dev, rank, world, steps, field):
                                  "ms_per_step": e0.elapsed_time(e1) / steps}
         del cm, ts2
         torch.cuda.empty_cache()
+        # test-time renderer: one 256 x 256 view of the same scene through render_image_with_occgrid_test
+        from cnc_b200.render import render_image_with_occgrid_test
+
+        H = W = 256
+        v, u = torch.meshgrid(torch.linspace(-0.3, 0.3, H, device=dev), torch.linspace(-0.3, 0.3, W, device=dev), indexing="ij")
+        dirs = torch.stack([u, v, torch.ones_like(u)], -1)
+        dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+        img = Rays(torch.tensor([0.0, 0.0, -4.0], device=dev).expand(H, W, 3).contiguous(), dirs.contiguous())
+        was_training = field.training
+        field.eval()
+        kw = dict(render_step_size=5e-3, render_bkgd=torch.ones(3, device=dev))
+        render_image_with_occgrid_test(1024, field, est, img, **kw)
+        torch.cuda.synchronize()
+        e0.record()
+        _, opa, _, n_tot = render_image_with_occgrid_test(1024, field, est, img, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        field.train(was_training)
+        ms_img = e0.elapsed_time(e1)
+        out["test_render"] = {"what": "render_image_with_occgrid_test: wavefront rounds of march + fused forward + compositing, "
+                                      "early stop at 1 - 1e-4, untrained field (low density: most rays run to the far side)",
+                              "rays": H * W, "samples": int(n_tot), "ms_per_image": ms_img,
+                              "rays_per_s": H * W / (ms_img * 1e-3), "samples_per_s": n_tot / (ms_img * 1e-3),
+                              "mean_opacity": float(opa.mean())}
     return out
 
 

@@ -44,6 +44,10 @@ class RayIntervals:
     ray_indices: Optional[Tensor] = None
     is_left: Optional[Tensor] = None
     is_right: Optional[Tensor] = None
+    # not in nerfacc: the same edges as two flat arrays, so that callers inside this package need no boolean-mask
+    # indexing (a nonzero() and a host sync each) to get them back
+    t_starts: Optional[Tensor] = None
+    t_ends: Optional[Tensor] = None
 
 
 # ------------------------------------------------------------------------------------------ pack / scans
@@ -170,7 +174,7 @@ def traverse_grids(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tens
     left = torch.zeros(2 * total, dtype=torch.bool, device=dev)
     left[0::2] = True
     intervals = RayIntervals(vals=vals, packed_info=torch.stack([starts * 2, cnt * 2], -1), ray_indices=ri.repeat_interleave(2),
-                             is_left=left, is_right=~left)
+                             is_left=left, is_right=~left, t_starts=t0, t_ends=t1)
     samples = RaySamples(vals=(t0 + t1) * 0.5, packed_info=packed, ray_indices=ri,
                          is_valid=torch.ones(total, dtype=torch.bool, device=dev))
     return intervals, samples, term

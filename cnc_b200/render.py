@@ -115,8 +115,8 @@ def render_image_with_occgrid_test(max_samples: int, radiance_field: torch.nn.Mo
         intervals, samples, termination_planes = traverse_grids(
             rays_o, rays_d, estimator.binaries, estimator.aabbs, near_planes, far_planes, render_step_size, cone_angle,
             n_samples, True, ray_mask, t_sorted, t_indices, hits)
-        t_starts, t_ends = intervals.vals[intervals.is_left], intervals.vals[intervals.is_right]
-        ray_indices = samples.ray_indices[samples.is_valid]
+        t_starts, t_ends = intervals.t_starts, intervals.t_ends   # == vals[is_left], vals[is_right] (utils.py:431-432)
+        ray_indices = samples.ray_indices                         # every returned sample is valid (exact-size march)
         packed_info = samples.packed_info
         if ray_indices.numel():
             t_dirs = rays_d[ray_indices]
