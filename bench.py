@@ -392,6 +392,17 @@ def train_bench(dev, rank, world, steps, field):
                               "rays": H * W, "samples": int(n_tot), "ms_per_image": ms_img,
                               "rays_per_s": H * W / (ms_img * 1e-3), "samples_per_s": n_tot / (ms_img * 1e-3),
                               "mean_opacity": float(opa.mean())}
+        field.eval()
+        render_image_with_occgrid_test(1024, field, est, img, samples_per_round=32, **kw)
+        torch.cuda.synchronize()
+        e0.record()
+        _, _, _, n_k = render_image_with_occgrid_test(1024, field, est, img, samples_per_round=32, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        field.train(was_training)
+        out["test_render"]["fixed_rounds_of_32"] = {"what": "same view, samples_per_round=32 (fewer, larger rounds; same image within "
+                                                           "early_stop_eps)", "samples": int(n_k), "ms_per_image": e0.elapsed_time(e1),
+                                                   "rays_per_s": H * W / (e0.elapsed_time(e1) * 1e-3)}
     return out
 
 

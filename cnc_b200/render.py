@@ -74,12 +74,18 @@ def render_image_with_occgrid(radiance_field: torch.nn.Module, estimator: OccGri
 def render_image_with_occgrid_test(max_samples: int, radiance_field: torch.nn.Module, estimator: OccGridEstimator, rays: Rays,
                                    near_plane: float = 0.0, far_plane: float = 1e10, render_step_size: float = 1e-3,
                                    render_bkgd: Optional[torch.Tensor] = None, cone_angle: float = 0.0, alpha_thre: float = 0.0,
-                                   early_stop_eps: float = 1e-4, timestamps=None):
+                                   early_stop_eps: float = 1e-4, timestamps=None, samples_per_round: Optional[int] = None):
     """Test-time renderer, examples/utils.py:316-489: all rays of the image advance together, a few samples per ray and
     round (more as rays die), a ray leaves the wavefront once its opacity exceeds 1 - early_stop_eps or it reaches the far
     plane.  -> (rgb, opacity, depth, total_samples).  Every round is march (`cnc_traverse_grids` with a step limit, the
     ray mask and the previous termination planes) -> fused field forward -> `cnc_render_from_density` with the rays'
-    running transmittance as prefix -> index_add of colour / opacity / depth."""
+    running transmittance as prefix -> index_add of colour / opacity / depth.
+
+    `samples_per_round` (not in the reference): a fixed number of samples per live ray and round instead of the reference's
+    `max(min(num_rays // n_alive, 64), min_samples)`.  The reference's schedule starts at ONE sample per ray and round, i.e.
+    hundreds of rounds of a few launches and two host syncs each; a round is cheap on this hardware only when it is large.
+    The image is the same within `early_stop_eps` (a ray is retired at the end of the round in which it crosses the
+    threshold, so it may take up to samples_per_round - 1 samples more); `total_samples` grows accordingly."""
     if timestamps is not None:
         raise NotImplementedError("timestamps belong to the dynamic-scene fields, which the CNC scripts do not use")
     rays_shape = rays.origins.shape
@@ -110,7 +116,10 @@ def render_image_with_occgrid_test(max_samples: int, radiance_field: torch.nn.Mo
         n_alive = int(ray_mask.sum())
         if n_alive == 0:
             break
-        n_samples = max(min(num_rays // n_alive, 64), min_samples)   # the number of samples to add on each ray
+        if samples_per_round is None:
+            n_samples = max(min(num_rays // n_alive, 64), min_samples)   # the number of samples to add on each ray
+        else:
+            n_samples = max(int(samples_per_round), min_samples)
         iter_samples += n_samples
         intervals, samples, termination_planes = traverse_grids(
             rays_o, rays_d, estimator.binaries, estimator.aabbs, near_planes, far_planes, render_step_size, cone_angle,

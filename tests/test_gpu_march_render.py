@@ -202,6 +202,11 @@ def test_test_time_renderer_matches_the_full_march(cuda):
     torch.testing.assert_close(rgb_e, rgb_w, rtol=0, atol=3e-4)
     assert rgb_e.shape == (1200, 3) and opa_e.shape == (1200, 1) and dep_e.shape == (1200, 1)
     assert (opa_e[1] == 0).all() and torch.equal(rgb_e[1], bkgd)          # the ray that misses the box shows the background
+    # fixed round size: same image within the early-stop epsilon, at most (round - 1) samples more per retired ray
+    rgb_k, opa_k, dep_k, n_k = render_image_with_occgrid_test(4096, field, est, rays, early_stop_eps=1e-4, samples_per_round=32, **kw)
+    assert n_e <= n_k <= n_e + 31 * 1200
+    torch.testing.assert_close(rgb_k, rgb_e, rtol=0, atol=3e-4)
+    torch.testing.assert_close(opa_k, opa_e, rtol=0, atol=3e-4)
     # image-shaped rays and a sample budget that ends the loop early
     img = Rays(origins=rays.origins[:1000].view(25, 40, 3), viewdirs=rays.viewdirs[:1000].view(25, 40, 3))
     rgb_i, opa_i, _, n_i = render_image_with_occgrid_test(8, field, est, img, early_stop_eps=1e-4, **kw)
