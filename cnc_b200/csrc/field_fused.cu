@@ -942,26 +942,27 @@ int cnc_field_fwd_host(const float *pos_host, const float *dirs_host, const floa
         set_error("field_fwd_host: null pointer / zero chunk");
         return CNC_EINVAL;
     }
-    constexpr uint32_t MAXW = 4096, NSLOT = 8;
+    constexpr uint32_t MAXW = 4096, NSLOT = 8, NPIPE = 4;
     static cudaEvent_t ev[4];
     static uint32_t *h_stamp = nullptr, *d_ready = nullptr, *d_done = nullptr, epoch = 0;
     static uint32_t *cum = nullptr;                       // tiles published per wave since start-up (the counters never reset)
     typedef CUresult (*wait32_t)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
     static wait32_t wait32 = nullptr;                     // cuStreamWaitValue32: a stream-side wait that needs no SM
     static int n_sm = 0;
+    static const float *pipe_key[NPIPE] = {nullptr, nullptr, nullptr, nullptr};   // staging buffer -> its own flags / counters
     if (!h_stamp) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        bool ok = cudaMallocHost(&h_stamp, NSLOT * MAXW * 4) == cudaSuccess && cudaMalloc(&d_ready, MAXW * 4) == cudaSuccess &&
-                  cudaMalloc(&d_done, MAXW * 4) == cudaSuccess && cudaMemset(d_ready, 0, MAXW * 4) == cudaSuccess &&
-                  cudaMemset(d_done, 0, MAXW * 4) == cudaSuccess;
+        bool ok = cudaMallocHost(&h_stamp, NSLOT * MAXW * 4) == cudaSuccess && cudaMalloc(&d_ready, NPIPE * MAXW * 4) == cudaSuccess &&
+                  cudaMalloc(&d_done, NPIPE * MAXW * 4) == cudaSuccess && cudaMemset(d_ready, 0, NPIPE * MAXW * 4) == cudaSuccess &&
+                  cudaMemset(d_done, 0, NPIPE * MAXW * 4) == cudaSuccess;
         for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) == cudaSuccess;
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult q;
         ok = ok && cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) == cudaSuccess && fn != nullptr;
         wait32 = reinterpret_cast<wait32_t>(fn);
-        cum = static_cast<uint32_t *>(calloc(MAXW, 4));
+        cum = static_cast<uint32_t *>(calloc(NPIPE * MAXW, 4));
         ok = ok && cum != nullptr;
         if (!ok) { h_stamp = nullptr; set_error("field_fwd_host: cannot allocate the pipeline state"); return CNC_ECUDA; }
     }
@@ -970,6 +971,13 @@ int cnc_field_fwd_host(const float *pos_host, const float *dirs_host, const floa
     const uint32_t nwaves = (ntiles + grid - 1) / grid;
     if (nwaves > MAXW) { set_error("field_fwd_host: more than %u waves", MAXW); return CNC_EINVAL; }
     cudaStream_t sc = static_cast<cudaStream_t>(s_compute), si = static_cast<cudaStream_t>(s_in), so = static_cast<cudaStream_t>(s_out);
+    // Calls on different staging buffers issued from different streams overlap (the upload of one runs beside the kernel of
+    // the other): each staging buffer gets its own ready flags and tile counters.
+    uint32_t pipe = 0;
+    while (pipe < NPIPE && pipe_key[pipe] != d_pos && pipe_key[pipe] != nullptr) pipe++;
+    if (pipe == NPIPE) { pipe = 0; cudaDeviceSynchronize(); for (uint32_t i = 1; i < NPIPE; i++) pipe_key[i] = nullptr; }   // table full: start over
+    pipe_key[pipe] = d_pos;
+    uint32_t *const ready_p = d_ready + pipe * MAXW, *const done_p = d_done + pipe * MAXW, *const cum_p = cum + pipe * MAXW;
     epoch++;
     uint32_t *stamp = h_stamp + (epoch % NSLOT) * MAXW;   // a slot per call: earlier calls may still be copying from theirs
     for (uint32_t w = 0; w < nwaves; w++) stamp[w] = epoch;
@@ -988,8 +996,8 @@ int cnc_field_fwd_host(const float *pos_host, const float *dirs_host, const floa
     // the staging buffers and the stamps may still be in use by earlier work on the caller's stream
     cudaEventRecord(ev[0], sc); cudaStreamWaitEvent(si, ev[0], 0); cudaStreamWaitEvent(so, ev[0], 0);
     const int rc = field_fwd_impl(d_pos, d_dirs, aabb6_host, bits_xyz, bits_xy, bits_xz, bits_yz, offsets3, resolutions3, offsets2,
-                                  resolutions2, blob, d_sigma, d_rgb, nullptr, nullptr, nullptr, nullptr, nullptr, N, s_compute, d_ready,
-                                  d_done, epoch);
+                                  resolutions2, blob, d_sigma, d_rgb, nullptr, nullptr, nullptr, nullptr, nullptr, N, s_compute, ready_p,
+                                  done_p, epoch);
     if (rc != CNC_OK) return rc;
     const uint32_t last_ctas = ntiles - (nwaves - 1) * grid;
     uint32_t w0 = 0;
@@ -1001,10 +1009,10 @@ int cnc_field_fwd_host(const float *pos_host, const float *dirs_host, const floa
         const size_t n = hi - lo;
         cudaMemcpyAsync(d_pos + lo * 3, pos_host + lo * 3, n * 12, cudaMemcpyHostToDevice, si);
         cudaMemcpyAsync(d_dirs + lo * 3, dirs_host + lo * 3, n * 12, cudaMemcpyHostToDevice, si);
-        cudaMemcpyAsync(d_ready + w0, stamp + w0, (size_t)waves * 4, cudaMemcpyHostToDevice, si);   // behind the data, same stream
+        cudaMemcpyAsync(ready_p + w0, stamp + w0, (size_t)waves * 4, cudaMemcpyHostToDevice, si);   // behind the data, same stream
         for (uint32_t w = w0; w < w1; w++) {   // the download waits (on the stream, no kernel) for every tile of the chunk
-            cum[w] += w == nwaves - 1 ? last_ctas : grid;
-            if (wait32((CUstream)so, (CUdeviceptr)(uintptr_t)(d_done + w), cum[w], CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) {
+            cum_p[w] += w == nwaves - 1 ? last_ctas : grid;
+            if (wait32((CUstream)so, (CUdeviceptr)(uintptr_t)(done_p + w), cum_p[w], CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) {
                 set_error("field_fwd_host: cuStreamWaitValue32 failed");
                 return CNC_ECUDA;
             }

@@ -312,12 +312,14 @@ class NGPRadianceField_mygrid_2D3D(nn.Module):
 
     @torch.no_grad()
     def forward_host(self, positions: torch.Tensor, directions: torch.Tensor, out_rgb: torch.Tensor = None,
-                     out_sigma: torch.Tensor = None, chunk_waves: int = 8):
+                     out_sigma: torch.Tensor = None, chunk_waves: int = 8, slot: int = 0):
         """Host-buffer entry point: positions / directions are (pinned) CPU tensors [N,3]; rgb [N,3] and density [N,1]
         come back in (pinned) CPU tensors.  `cnc_field_fwd_host` cuts the batch into chunks of 1, 2, 4, .. `chunk_waves` ..
         4, 2, 1 full waves of the persistent kernel (148 SMs x 128 samples) and pipelines them over three streams -- H2D
         of chunk i+1, the fused kernel on chunk i and D2H of chunk i-1 overlap -- so that only a short first upload and
-        last download are exposed."""
+        last download are exposed.  Those two are hidden as well when independent batches are issued alternately with
+        `slot=0` / `slot=1` (own device staging each) from two CUDA streams: the first upload of one batch then runs beside
+        the kernel of the other, the last download beside the next kernel."""
         if not self.fused_available():
             raise RuntimeError("forward_host needs the fused kernel (CNC product layout)")
         dev = self.aabb.device
@@ -328,12 +330,13 @@ class NGPRadianceField_mygrid_2D3D(nn.Module):
             out_rgb = torch.empty(n, 3, dtype=torch.float32).pin_memory()
         if out_sigma is None:
             out_sigma = torch.empty(n, 1, dtype=torch.float32).pin_memory()
-        st = getattr(self, "_host_pipe", None)
+        pipes = getattr(self, "_host_pipe", None)
+        if pipes is None:
+            pipes = self._host_pipe = {"s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev)}
+        st = pipes.get(slot)
         if st is None or st["n"] < n:
-            st = {"n": n, "pos": torch.empty(n, 3, device=dev), "dir": torch.empty(n, 3, device=dev),
-                  "rgb": torch.empty(n, 3, device=dev), "sig": torch.empty(n, device=dev),
-                  "s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev)}
-            self._host_pipe = st
+            st = pipes[slot] = {"n": n, "pos": torch.empty(n, 3, device=dev), "dir": torch.empty(n, 3, device=dev),
+                                "rgb": torch.empty(n, 3, device=dev), "sig": torch.empty(n, device=dev)}
         mb = self.mlp_base
         encs = (mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz)
         bits = [e._sign_cache.get(e.params) for e in encs]
@@ -351,8 +354,8 @@ class NGPRadianceField_mygrid_2D3D(nn.Module):
                                        ptr(mb.encoding_xyz.offsets_list), ptr(mb.encoding_xyz.resolutions_list),
                                        ptr(mb.encoding_xy.offsets_list), ptr(mb.encoding_xy.resolutions_list), ptr(blob),
                                        out_sigma.data_ptr(), out_rgb.data_ptr(), n, ptr(st["pos"]), ptr(st["dir"]), ptr(st["sig"]),
-                                       ptr(st["rgb"]), n_sm * 128, max(1, chunk_waves), cur.cuda_stream, st["s_in"].cuda_stream,
-                                       st["s_out"].cuda_stream))
+                                       ptr(st["rgb"]), n_sm * 128, max(1, chunk_waves), cur.cuda_stream, pipes["s_in"].cuda_stream,
+                                       pipes["s_out"].cuda_stream))
         return out_rgb, out_sigma
 
     def _aabb_c(self):

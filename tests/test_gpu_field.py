@@ -147,6 +147,33 @@ def test_forward_host_pipeline_matches_device_call(cuda):
         assert torch.equal(r2, rgb.cpu()) and torch.equal(s2, sig.cpu())
 
 
+def test_forward_host_two_slots_on_two_streams(cuda):
+    """independent batches issued alternately with slot 0 / 1 from two streams overlap (upload of one beside the kernel of
+    the other) and still return exactly the device results, call after call"""
+    f = make_field(cuda, seed=11)
+    n_sm = torch.cuda.get_device_properties(cuda).multi_processor_count
+    n = 5 * n_sm * 128 + 333
+    batches = []
+    for k in range(2):
+        pos, dirs = inputs(n, cuda, seed=50 + k)
+        rgb, sig, _ = f.fused_forward(pos, dirs)
+        batches.append((pos.cpu().pin_memory(), dirs.cpu().pin_memory(), rgb.cpu(), sig.cpu(),
+                        torch.empty(n, 3).pin_memory(), torch.empty(n, 1).pin_memory()))
+    streams = [torch.cuda.Stream(cuda), torch.cuda.Stream(cuda)]
+    torch.cuda.synchronize()
+    for rep in range(6):
+        k = rep & 1
+        hp, hd, _, _, o_rgb, o_sig = batches[k]
+        o_rgb.zero_(); o_sig.zero_()
+        with torch.cuda.stream(streams[k]):
+            f.forward_host(hp, hd, o_rgb, o_sig, slot=k)
+        if rep >= 1:   # the previous batch (other stream, other slot) is checked while this one is in flight
+            j = 1 - k
+            streams[j].synchronize()
+            assert torch.equal(batches[j][4], batches[j][2]) and torch.equal(batches[j][5], batches[j][3])
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("n", [1000, 20000])
 def test_fused_training_path_matches_unfused_autograd(cuda, n):
     """`_FusedFieldTrain` (fused-kernel forward + explicit backward) against torch autograd through the op-by-op
