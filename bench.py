@@ -521,11 +521,9 @@ def main():
             s.record()
             for st in side:
                 st.wait_stream(cur)
-            t_h = time.perf_counter()
             for k in range(K):
                 with torch.cuda.stream(side[k & 1]):
                     field.forward_host(*pins[k & 1], slot=k & 1)
-            print("enqueue ms/call", (time.perf_counter() - t_h) / K * 1e3, [t.is_pinned() for p_ in pins for t in p_], file=sys.stderr)
             for st in side:
                 cur.wait_stream(st)
             e.record()
@@ -533,9 +531,7 @@ def main():
             return s.elapsed_time(e)
 
         stream_of_batches(4)
-        spans = [stream_of_batches(a.steps) for _ in range(3)]
-        print("two-slot spans (ms):", spans, file=sys.stderr)
-        ms_stream = spans[0]
+        ms_stream = sorted(stream_of_batches(a.steps) for _ in range(3))[1]   # median of three spans of a.steps batches
         barrier()
 
     # dominant kernel alone, CUDA events on its stream: ours = the fused field kernel (one launch = the
@@ -634,7 +630,7 @@ def main():
                                       "d2h_bytes_per_step": int(pin_out.numel() * 4),
                                       **({"two_slot_stream": {"value": world * Ns * a.steps / (ms_stream * 1e-3), "unit": "samples/s",
                                                               "what": "same call, independent batches alternating between two staging "
-                                                                      "slots / two CUDA streams, one timed span over all batches, "
+                                                                      "slots / two CUDA streams, one timed span over all batches (median of 3), "
                                                                       "no flush between them"}}
                                          if ms_stream == ms_stream else {})},
         "gpu_launches": int(launches),
