@@ -7,10 +7,11 @@ from conftest import R2, R3
 from test_gpu_codec import make
 dev = torch.device("cuda:0")
 cm, encs, vxl = make(dev, res3=R3, log2T=19, res2=R2, log2T2=17, Rb=128, seed=1)
+SN = int(os.environ.get("SAMPLE_NUM", "0"))   # the training scripts use 150000 (make(): 4000)
 params = [e.params for e in encs] + list(cm.parameters())
 def step(i):
     for p in params: p.grad = None
-    bpp, mb = cm.forward_binary_vxl_mixPg_3D2D(*encs, vxl, step=i)
+    bpp, mb = cm.forward_binary_vxl_mixPg_3D2D(*encs, vxl, step=i, sample_num=SN or None)
     bpp.backward()
     return bpp
 for i in range(3): step(i + 1)
