@@ -210,7 +210,10 @@ int cnc_field_fwd(const float *pos, const float *dirs, const float *aabb6_host,
  * CTAs count finished tiles per wave and the downloads on s_out wait for those counts with cuStreamWaitValue32, so only
  * a short first upload and last download are exposed.  d_pos / d_dirs / d_rgb [N,3], d_sigma [N] are device staging
  * buffers owned by the caller.  Returns after everything is enqueued; s_compute completes after the last download.
- * All device-side waits are bounded (2 s), a missing stamp cannot hang the GPU. */
+ * All device-side waits are bounded (2 s), a missing stamp cannot hang the GPU.
+ * Ready flags and tile counters are kept per staging buffer (keyed by d_pos, up to 4): calls that use different staging
+ * buffers and different s_compute streams (same s_in / s_out) overlap -- the first upload of one call runs beside the
+ * kernel of the other -- which is how a stream of independent batches reaches the device-resident rate. */
 int cnc_field_fwd_host(const float *pos_host, const float *dirs_host, const float *aabb6_host,
                        const uint8_t *bits_xyz, const uint8_t *bits_xy, const uint8_t *bits_xz,
                        const uint8_t *bits_yz, const int32_t *offsets3, const int32_t *resolutions3,
