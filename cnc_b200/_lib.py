@@ -57,6 +57,8 @@ SIGNATURES = {
     "cnc_dgrad_pack": [_vp, _u32, _u32, _i32, _u32, _u32, _u32, _vp, _vp],
     "cnc_dgrad": [_vp, _u32, _u32, _vp, _u32, _vp, _u32, _vp, _u32, _u32, _vp],
     "cnc_vertex_valid_bits": [_vp, _i32, _vp, _i32, _vp, _i64, _vp, _vp],
+    "cnc_ctx_mlp_fwd": [_vp, _vp, _vp, _i64, _vp],
+    "cnc_ctx_mlp_bwd": [_vp, _vp, _vp, _vp, _vp, _u32, _i64, _vp],
 }
 
 
@@ -82,6 +84,10 @@ def lib():
         L.cnc_dgrad_blob_floats.argtypes = [_u32, _u32]
         L.cnc_wgrad_max_partials.restype = C.c_int
         L.cnc_wgrad_max_partials.argtypes = []
+        L.cnc_ctx_mlp_floats.restype = C.c_uint32
+        L.cnc_ctx_mlp_floats.argtypes = []
+        L.cnc_ctx_mlp_max_partials.restype = C.c_int
+        L.cnc_ctx_mlp_max_partials.argtypes = []
         _lib = L
     return _lib
 

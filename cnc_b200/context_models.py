@@ -171,6 +171,36 @@ class segment_sum(Function):
         return gf, None, None, None
 
 
+class _CtxMLP3(Function):
+    """context_model_3D (Linear(25,32) LeakyReLU Linear(32,32) LeakyReLU Linear(32,8)) over [voxels, 25] as one forward and
+    one backward kernel (`cnc_ctx_mlp_fwd / _bwd`, csrc/context_mlp.cu): the hidden activations are recomputed in the
+    backward instead of being written to and read from HBM, the weight gradients are per-CTA partials added in index order."""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2, W3, b3):
+        x = x.contiguous().float()
+        packed = torch.cat([t.detach().float().reshape(-1) for t in (W1.t(), b1, W2.t(), b2, W3.t(), b3)]).contiguous()
+        y = torch.empty(x.shape[0], W3.shape[0], device=x.device, dtype=torch.float32)
+        check(lib().cnc_ctx_mlp_fwd(ptr(x), ptr(packed), ptr(y), x.shape[0], stream()))
+        ctx.save_for_backward(x, packed)
+        ctx.dims = (W1.shape[1], W1.shape[0], W3.shape[0])
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, packed = ctx.saved_tensors
+        nin, nh, no = ctx.dims
+        M = x.shape[0]
+        gx = torch.empty_like(x)
+        G = max(1, min(lib().cnc_ctx_mlp_max_partials(), (M + 255) // 256))
+        parts = torch.empty(G, packed.numel(), device=x.device, dtype=torch.float32)
+        check(lib().cnc_ctx_mlp_bwd(ptr(x), ptr(packed), ptr(gy.contiguous().float()), ptr(gx), ptr(parts), G, M, stream()))
+        g = parts.sum(0)
+        o = [0, nin * nh, nin * nh + nh, nin * nh + nh + nh * nh, nin * nh + 2 * nh + nh * nh, nin * nh + 2 * nh + nh * nh + nh * no]
+        return (gx, g[o[0]:o[1]].view(nin, nh).t(), g[o[1]:o[2]], g[o[2]:o[3]].view(nh, nh).t(), g[o[3]:o[4]],
+                g[o[4]:o[5]].view(nh, no).t(), g[o[5]:o[5] + no])
+
+
 _LEVEL_CONST = {}
 
 
@@ -635,7 +665,13 @@ class CNC_context_models(nn.Module):
                 w = torch.repeat_interleave(1.0 / mask_cnt.to(torch.float), mask_cnt, output_size=m_i.numel())
             c = self.max_context_layer_num
             context = Encoding_xyz.forward_diff_levels(ptsn[m_i], (nl[m_i] - c).to(torch.int), c, binary_vxl=binary_vxl.squeeze(0), PV=1001)
-            mean = segment_sum.apply(self.context_model_3D(torch.cat([context, Pgc[m_i]], dim=-1)), cs, w.contiguous(), None)
+            ctx_in = torch.cat([context, Pgc[m_i]], dim=-1)
+            if getattr(self, "fused_mlp_train", True) and ctx_in.shape[1] == 25 and self.n_features == 8:   # the product layout
+                m3 = self.context_model_3D
+                mlp_out = _CtxMLP3.apply(ctx_in, m3[0].weight, m3[0].bias, m3[2].weight, m3[2].bias, m3[4].weight, m3[4].bias)
+            else:
+                mlp_out = self.context_model_3D(ctx_in)
+            mean = segment_sum.apply(mlp_out, cs, w.contiguous(), None)
             bits = torch.sum(self.entropy_model(vals, mean))
             ttl_bit_sum = ttl_bit_sum + bits / n_valid * self.ttl_hashparams_num_valid_levels
         ttl_num_sum += pq["xyz"].numel()

@@ -294,6 +294,19 @@ int cnc_context3d_probs(const int16_t *pts, const int64_t *seg, int64_t n_entrie
                         int64_t seg_base, int64_t entry_base, const uint32_t *vertex_bits,
                         const int64_t *vertex_bit_offsets, cnc_stream_t stream);
 
+/* context_model_3D (Linear(25,32) LeakyReLU Linear(32,32) LeakyReLU Linear(32,8), utils_bpp_acc.py:247-251) for the rate
+ * term of the training loss (utils_bpp_acc.py:533-706), where the reference runs it under autograd (six cuBLAS GEMMs +
+ * elementwise passes over [voxels, 32] activations).  One forward and one backward kernel, thread = voxel:
+ *   cnc_ctx_mlp_fwd: X [M,25] row-major, mlp_packed (layout of cnc_context3d_probs, cnc_ctx_mlp_floats() floats) -> Y [M,8]
+ *   cnc_ctx_mlp_bwd: recomputes the hidden activations, gY [M,8] -> gX [M,25] and n_partials partial gradient vectors
+ *                    [n_partials, cnc_ctx_mlp_floats()] in the packed layout (every CTA writes one; the caller adds them
+ *                    in index order: deterministic).  n_partials <= cnc_ctx_mlp_max_partials() is a sensible grid. */
+uint32_t cnc_ctx_mlp_floats(void);
+int cnc_ctx_mlp_max_partials(void);
+int cnc_ctx_mlp_fwd(const float *X, const float *mlp_packed, float *Y, int64_t M, cnc_stream_t stream);
+int cnc_ctx_mlp_bwd(const float *X, const float *mlp_packed, const float *gY, float *gX, float *partials,
+                    uint32_t n_partials, int64_t M, cnc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Occupancy-grid ray marching, packed scans, volume rendering (vendored nerfacc 0.5.3).
  * replaces: nerfacc.csrc ray_aabb_intersect / traverse_grids  nerfacc/cuda/csrc/grid.cu:320-349, :68-318

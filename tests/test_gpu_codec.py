@@ -232,3 +232,51 @@ def test_segment_sum_matches_padded_flow(cuda):
         want.backward(gout)
         torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
         torch.testing.assert_close(g_got, feat.grad, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("M", [1, 255, 256, 257, 40013])
+def test_fused_context_mlp_matches_fp64_autograd(cuda, M):
+    """cnc_ctx_mlp_fwd / _bwd (context_model_3D as one forward and one backward kernel) against fp64 autograd of the same
+    nn.Sequential: outputs, input gradient and all weight / bias gradients to fp32 rounding (torch's fp32 path shown for scale)"""
+    from cnc_b200.context_models import _CtxMLP3
+
+    torch.manual_seed(M)
+    def mk():
+        return torch.nn.Sequential(torch.nn.Linear(25, 32), torch.nn.LeakyReLU(), torch.nn.Linear(32, 32), torch.nn.LeakyReLU(),
+                                   torch.nn.Linear(32, 8)).to(cuda)
+    net, net64 = mk(), mk().double()
+    net64.load_state_dict({k: v.double() for k, v in net.state_dict().items()})
+    x = torch.randn(M, 25, device=cuda, requires_grad=True)
+    gy = torch.randn(M, 8, device=cuda)
+    ps = [net[0].weight, net[0].bias, net[2].weight, net[2].bias, net[4].weight, net[4].bias]
+    ps64 = [net64[0].weight, net64[0].bias, net64[2].weight, net64[2].bias, net64[4].weight, net64[4].bias]
+    y = _CtxMLP3.apply(x, *ps)
+    got = torch.autograd.grad(y, [x] + ps, gy)
+    x64 = x.detach().double().requires_grad_(True)
+    y64 = net64(x64)
+    want = torch.autograd.grad(y64, [x64] + ps64, gy.double())
+    rel = lambda a, b: ((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+    assert y.shape == (M, 8) and all(a.shape == b.shape for a, b in zip(got, want))
+    assert rel(y, y64) < 5e-6
+    for a, b in zip(got, want):
+        assert rel(a, b) < 5e-6
+
+
+def test_rate_term_same_with_and_without_the_fused_context_mlp(cuda):
+    """forward_binary_vxl_mixPg_3D2D: the fused context MLP changes neither the loss nor the gradients (fp32 noise)"""
+    cm, encs, vxl = make(cuda, **SMALL)
+    params = [e.params for e in encs] + list(cm.parameters())
+    out = {}
+    for fused in (False, True):
+        cm.fused_mlp_train = fused
+        torch.manual_seed(3)
+        for p in params:
+            p.grad = None
+        bpp, _ = cm.forward_binary_vxl_mixPg_3D2D(*encs, vxl, step=1)
+        bpp.backward()
+        out[fused] = (bpp.detach().clone(), [None if p.grad is None else p.grad.clone() for p in params])
+    torch.testing.assert_close(out[True][0], out[False][0], rtol=1e-5, atol=0)
+    for a, b in zip(out[True][1], out[False][1]):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert ((a - b).norm() / b.norm().clamp_min(1e-30)).item() < 1e-4
