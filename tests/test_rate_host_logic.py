@@ -1,0 +1,58 @@
+"""CPU suite: the host-side pieces of the rate term that replace per-level autograd slicing (cnc_b200/context_models.py:
+`_LevelSums`, `level_entropies`) against the per-level function that mirrors utils_bpp_acc.py:472-486, values and gradients."""
+import types
+
+import torch
+
+from cnc_b200.context_models import CNC_context_models, _LevelSums, _level_const
+
+
+def _stub(offs):
+    return types.SimpleNamespace(offs=offs)
+
+
+def test_level_sums_forward_and_backward_match_slicing():
+    torch.manual_seed(0)
+    offs = [0, 5, 12, 13, 40]
+    p = torch.randn(40, 8, dtype=torch.float64, requires_grad=True)
+    s = _LevelSums.apply(p, offs)
+    want = torch.stack([p[a:b].sum() for a, b in zip(offs[:-1], offs[1:])])
+    torch.testing.assert_close(s, want)
+    g = torch.randn(4, dtype=torch.float64)
+    (ga,) = torch.autograd.grad(s, p, g)
+    (gb,) = torch.autograd.grad(want, p, g)
+    torch.testing.assert_close(ga, gb)
+    assert torch.autograd.gradcheck(lambda t: _LevelSums.apply(t, offs), (p,))
+    # a table whose levels do not start at row 0 / end at the last row
+    offs2 = [3, 10, 30]
+    (gc,) = torch.autograd.grad(_LevelSums.apply(p, offs2), p, torch.tensor([2.0, -1.0], dtype=torch.float64))
+    assert (gc[:3] == 0).all() and (gc[30:] == 0).all() and (gc[3:10] == 2).all() and (gc[10:30] == -1).all()
+
+
+def test_level_constants_are_cached_per_layout():
+    a = _level_const([0, 4, 9], 8, torch.device("cpu"))
+    b = _level_const([0, 4, 9], 8, torch.device("cpu"))
+    assert a[0] is b[0] and a[1] is b[1]
+    assert a[0].tolist() == [0] * 4 + [1] * 5 and a[1].tolist() == [32.0, 40.0]
+    c = _level_const([0, 4, 9], 2, torch.device("cpu"))
+    assert c[1].tolist() == [8.0, 10.0]
+
+
+def test_level_entropies_equal_the_per_level_function():
+    """same Pg and bits as get_BiRF_wentropy_leveln level by level, same gradient of their sum w.r.t. the table"""
+    torch.manual_seed(1)
+    offs = [0, 64, 200, 1000]
+    table = torch.where(torch.rand(1000, 8) < 0.7, 1.0, -1.0).requires_grad_(True)
+    me = _stub(offs)
+    Pgs, bits = CNC_context_models.level_entropies(me, table)
+    tot_a = sum(bits)
+    tot_b = 0
+    for n in range(3):
+        Pg_n, bit_n, ttl = CNC_context_models.get_BiRF_wentropy_leveln(me, table, n)
+        assert ttl == (offs[n + 1] - offs[n]) * 8
+        torch.testing.assert_close(Pgs[n], Pg_n, rtol=1e-6, atol=0)
+        torch.testing.assert_close(bits[n], bit_n, rtol=1e-5, atol=0)
+        tot_b = tot_b + bit_n
+    (ga,) = torch.autograd.grad(tot_a, table)
+    (gb,) = torch.autograd.grad(tot_b, table)
+    torch.testing.assert_close(ga, gb, rtol=1e-5, atol=1e-7)
