@@ -181,7 +181,8 @@ class _CtxMLP3(Function):
         x = x.contiguous().float()
         packed = torch.cat([t.detach().float().reshape(-1) for t in (W1.t(), b1, W2.t(), b2, W3.t(), b3)]).contiguous()
         y = torch.empty(x.shape[0], W3.shape[0], device=x.device, dtype=torch.float32)
-        check(lib().cnc_ctx_mlp_fwd(ptr(x), ptr(packed), ptr(y), x.shape[0], stream()))
+        if x.shape[0]:   # (no voxel of the sampled entries touches the occupancy: nothing to evaluate)
+            check(lib().cnc_ctx_mlp_fwd(ptr(x), ptr(packed), ptr(y), x.shape[0], stream()))
         ctx.save_for_backward(x, packed)
         ctx.dims = (W1.shape[1], W1.shape[0], W3.shape[0])
         return y
@@ -192,6 +193,9 @@ class _CtxMLP3(Function):
         nin, nh, no = ctx.dims
         M = x.shape[0]
         gx = torch.empty_like(x)
+        if M == 0:
+            z = lambda *shape: torch.zeros(*shape, device=x.device, dtype=torch.float32)
+            return gx, z(nh, nin), z(nh), z(nh, nh), z(nh), z(no, nh), z(no)
         G = max(1, min(lib().cnc_ctx_mlp_max_partials(), (M + 255) // 256))
         parts = torch.empty(G, packed.numel(), device=x.device, dtype=torch.float32)
         check(lib().cnc_ctx_mlp_bwd(ptr(x), ptr(packed), ptr(gy.contiguous().float()), ptr(gx), ptr(parts), G, M, stream()))

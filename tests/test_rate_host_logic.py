@@ -4,7 +4,7 @@ import types
 
 import torch
 
-from cnc_b200.context_models import CNC_context_models, _LevelSums, _level_const
+from cnc_b200.context_models import CNC_context_models, _CtxMLP3, _LevelSums, _level_const
 
 
 def _stub(offs):
@@ -56,3 +56,16 @@ def test_level_entropies_equal_the_per_level_function():
     (ga,) = torch.autograd.grad(tot_a, table)
     (gb,) = torch.autograd.grad(tot_b, table)
     torch.testing.assert_close(ga, gb, rtol=1e-5, atol=1e-7)
+
+
+def test_fused_context_mlp_with_no_voxels():
+    """no voxel of the sampled entries touches the occupancy: empty output, zero weight gradients, no kernel call"""
+    net = torch.nn.Sequential(torch.nn.Linear(25, 32), torch.nn.LeakyReLU(), torch.nn.Linear(32, 32), torch.nn.LeakyReLU(), torch.nn.Linear(32, 8))
+    ps = [net[0].weight, net[0].bias, net[2].weight, net[2].bias, net[4].weight, net[4].bias]
+    x = torch.zeros(0, 25, requires_grad=True)
+    y = _CtxMLP3.apply(x, *ps)
+    assert y.shape == (0, 8)
+    grads = torch.autograd.grad(y.sum(), [x] + ps)
+    assert grads[0].shape == (0, 25)
+    for g, p_ in zip(grads[1:], ps):
+        assert g.shape == p_.shape and not g.any()
