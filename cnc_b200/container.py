@@ -64,11 +64,32 @@ def _unpack_uint(data: bytes, n: int, digits: int) -> np.ndarray:
     return (bits << np.arange(digits, dtype=np.uint64)[None, :]).sum(1)
 
 
+def quantize_state(state: Dict[str, torch.Tensor], digits: int = 13) -> Dict[str, tuple]:
+    """{name: (integer levels [shape] int64, min fp32, interval fp32)}: the `digits`-bit grid of quantize_params, kept as
+    integers so that what `pack` stores is exactly what the encoder side used (re-quantising a dequantised tensor does not
+    reproduce it: the interval is derived from max - min, which shrinks)"""
+    out = {}
+    for name, t in state.items():
+        t32 = t.detach().float().cpu()
+        min_v, max_v = torch.min(t32), torch.max(t32)
+        interval = (max_v - min_v) / (2 ** digits - 1) + 1e-6
+        out[name] = (((t32 - min_v) // interval).to(torch.int64), min_v.clone(), interval.clone())
+    return out
+
+
+def dequantize_state(qstate: Dict[str, tuple], device="cpu") -> Dict[str, torch.Tensor]:
+    """the tensors a decoder gets back from `unpack` for this quantised state, bit for bit (same fp32 arithmetic on the CPU).
+    An encoder must run the context models with THESE weights (train_CNC_nerf_synthetic.py:513-520 only accounts for the
+    13 bits; a stand-alone decoder actually has nothing else)."""
+    return {k: (q.to(torch.float32) * i.to(torch.float32) + m.to(torch.float32)).to(device) for k, (q, m, i) in qstate.items()}
+
+
 def pack(streams: Dict[str, bytes], Pgs_dict: Dict[str, torch.Tensor], binary_vxl: torch.Tensor,
          mlp_state: Optional[Dict[str, torch.Tensor]] = None, layout: Optional[dict] = None, digits: int = 13) -> bytes:
     """-> one self-contained blob.  `streams` as returned by encode_binary_vxl_mixPg_3D2D(..., return_streams=True);
-    `mlp_state`: every non-table tensor the decoder side needs (field MLPs, context models); `layout`: free-form json
-    (resolutions, hash sizes, ...) echoed back by `unpack`."""
+    `mlp_state`: every non-table tensor the decoder side needs (field MLPs, context models), as tensors (quantised here)
+    or as the triples of `quantize_state` (stored as they are); `layout`: free-form json (resolutions, hash sizes, the
+    symbol-order seed: `CNC_context_models.layout()`) echoed back by `unpack`."""
     sections, index = [], {"layout": layout or {}, "digits": digits, "streams": [], "pgs": [], "tensors": []}
 
     def add(b: bytes) -> int:
@@ -82,13 +103,13 @@ def pack(streams: Dict[str, bytes], Pgs_dict: Dict[str, torch.Tensor], binary_vx
     vx = binary_vxl.detach().cpu().numpy().astype(bool)
     index["occupancy_shape"] = list(vx.shape)
     add(np.packbits(vx.reshape(-1), bitorder="little").tobytes())
-    for name, t in (mlp_state or {}).items():
-        t32 = t.detach().float().cpu()
-        min_v, max_v = torch.min(t32), torch.max(t32)
-        interval = (max_v - min_v) / (2 ** digits - 1) + 1e-6
-        q = ((t32 - min_v) // interval).numpy()
-        index["tensors"].append({"name": name, "shape": list(t32.shape), "bytes": add(
-            struct.pack("<ff", float(min_v), float(interval)) + _pack_uint(q, digits))})
+    mlp_state = mlp_state or {}
+    raw = {k: v for k, v in mlp_state.items() if isinstance(v, torch.Tensor)}
+    qstate = {**quantize_state(raw, digits), **{k: v for k, v in mlp_state.items() if not isinstance(v, torch.Tensor)}}
+    for name in mlp_state:
+        q, min_v, interval = qstate[name]
+        index["tensors"].append({"name": name, "shape": list(q.shape), "bytes": add(
+            struct.pack("<ff", float(min_v), float(interval)) + _pack_uint(q.numpy(), digits))})
     for name, data in streams.items():
         index["streams"].append({"name": name, "bytes": add(bytes(data))})
     head = json.dumps(index, separators=(",", ":")).encode()

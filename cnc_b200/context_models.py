@@ -249,6 +249,22 @@ class Bernoulli_entropy(nn.Module):
         return -torch.log2(p) * ((1 + x) / 2.0) + -torch.log2(1 - p) * ((1 - x) / 2.0)
 
 
+def _z85(b: bytes) -> str:
+    """generator state -> text for the json header (zlib: the mt19937 state array is 5 KB, mostly incompressible, but
+    the tail of torch's state blob is zeros)"""
+    import base64
+    import zlib
+
+    return base64.b85encode(zlib.compress(b, 9)).decode()
+
+
+def _unz85(s: str) -> bytes:
+    import base64
+    import zlib
+
+    return zlib.decompress(base64.b85decode(s.encode()))
+
+
 def _layout(resolutions, num_dim, log2T):
     offs, off = [], 0
     for r in resolutions:
@@ -265,7 +281,13 @@ class CNC_context_models(nn.Module):
                  n_features=4, sample_num=20000, max_context_layer_num=3, ste_binary=False, ste_multistep=False,
                  add_noise=False, Q=100, quantize_epoch=1000, Pg_level=-1, Pg_level_2D=-1, Rb=128, step_update=16,
                  skip_levels_3D=(0, 1, 2, 3), skip_levels_2D=(0,), use_dimension_wise=True,
-                 use_overlap_area_pool=True, device="cuda", fused=True):
+                 use_overlap_area_pool=True, device="cuda", fused=True, shuffle_seed=None):
+        """`shuffle_seed`: the symbol order of the dense context-coded levels is a random permutation
+        (utils_bpp_acc.py:311-315) that encoder and decoder must share.  None = the reference's behaviour: drawn from
+        torch's global CPU generator (same `torch.manual_seed` => same order as the reference's constructor); an int =
+        drawn from a private generator seeded with it.  Either way `self.shuffle_seed` ends up holding what a decoder
+        in another process needs to rebuild the same tables (an int, or the CPU generator state as bytes); the container
+        stores it (container.pack(..., layout=cm.layout()))."""
         super().__init__()
         dev = torch.device(device)
         self.MAX_POINTS_NUM_TO_OOM = 20000000
@@ -302,23 +324,25 @@ class CNC_context_models(nn.Module):
         self.unique_count_list: List[torch.Tensor] = []         # voxels per row
         self.unique_count_cumsum_list: List[torch.Tensor] = []  # running sum, leading 0
         self.pos_grid_sorted_list: List[torch.Tensor] = []      # int16 [res^3, 3] voxel coords grouped by row
-        for i in range(Pg_level):
+        if shuffle_seed is None:          # the reference: global CPU generator; remember where it stood
+            gen, self.shuffle_seed = None, torch.get_rng_state().numpy().tobytes()
+        elif isinstance(shuffle_seed, (bytes, bytearray)):   # a recorded generator state
+            gen = torch.Generator()
+            gen.set_state(torch.frombuffer(bytearray(shuffle_seed), dtype=torch.uint8).clone())
+            self.shuffle_seed = bytes(shuffle_seed)
+        else:
+            gen, self.shuffle_seed = torch.Generator().manual_seed(int(shuffle_seed)), int(shuffle_seed)
+        # finest level first, like the reference (utils_bpp_acc.py:301): the order fixes which randperm a level gets
+        for i in reversed(range(Pg_level)):
             r = self.res[i]
-            pos_grid = my_meshgrid3D(0, r, dev).view(-1, 3)
-            indexes = get_grid_index(self.offs[i + 1] - self.offs[i], r, pos_grid)
-            indexes_sorted, order = torch.sort(indexes)
-            del indexes
-            pos_grid_sorted = pos_grid.to(torch.int16)[order]
-            del pos_grid, order
-            unique_value, unique_cnt = torch.unique_consecutive(indexes_sorted, return_counts=True)
-            del indexes_sorted
-            if r <= self.resolution_thresh:   # dense levels: random symbol order (one voxel per row)
-                shuffle_idx = torch.randperm(unique_value.nelement()).to(dev)
-                unique_value, pos_grid_sorted, unique_cnt = unique_value[shuffle_idx], pos_grid_sorted[shuffle_idx], unique_cnt[shuffle_idx]
-            self.unique_value_list.append(unique_value.to(torch.int64))
-            self.unique_count_list.append(unique_cnt.to(torch.int64))
-            self.unique_count_cumsum_list.append(torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(unique_cnt, 0)]))
-            self.pos_grid_sorted_list.append(pos_grid_sorted.contiguous())
+            rows, cnt, pts = self._inverse_table(i, dev)
+            if r <= self.resolution_thresh:   # dense levels: random symbol order (one voxel per row), CPU generator
+                shuffle_idx = torch.randperm(rows.nelement(), generator=gen).to(dev)
+                rows, pts, cnt = rows[shuffle_idx], pts[shuffle_idx], cnt[shuffle_idx]
+            self.unique_value_list.insert(0, rows.to(torch.int64))
+            self.unique_count_list.insert(0, cnt.to(torch.int64))
+            self.unique_count_cumsum_list.insert(0, torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(cnt, 0)]))
+            self.pos_grid_sorted_list.insert(0, pts.contiguous())
         self.hashparams_num_levels = torch.tensor([v.numel() for v in self.unique_value_list], device=dev)
         snl = torch.round(self.hashparams_num_levels * (sample_num / self.hashparams_num_levels.sum())).to(torch.long)
         self.sample_num_levels = self.hashparams_num_levels if snl[-1] > self.hashparams_num_levels[-1] else snl
@@ -327,7 +351,7 @@ class CNC_context_models(nn.Module):
         self.ttl_hashparams_num_valid_levels = int(sum(int(self.hashparams_num_levels[n]) for n in coded))
         self.ttl_sample_num = int(self.sample_num_levels.sum())
         self.ttl_sample_num_valid_levels = int(sum(int(self.sample_num_levels[n]) for n in coded))
-        self.utils_rand = torch.rand(Pg_level, device=dev)
+        self.utils_rand = torch.rand(Pg_level).to(dev)   # CPU generator, like the reference (utils_bpp_acc.py:367)
         # voxels per row as the reference computes it (int64 ** / int64 -> float32), it fixes the chunking of the streams
         self.utils_points_per_param_levels = [((self.resolutions_list[i] ** num_dim) / self.hashparams_num_levels[i]).item()
                                               for i in range(Pg_level)]
@@ -343,6 +367,38 @@ class CNC_context_models(nn.Module):
         self.binary_vxl_len = Rb
         self.init_binary_vxl_coords(self.res[-1] - 2)
         self.idx_coords2_tmp, self.batched_inputs_list = None, None
+
+    def _inverse_table(self, i, dev):
+        """level i -> (rows that are hit [E] ascending, voxels per row [E], int16 voxel coordinates grouped by row
+        [res^3, 3]; within a row in lattice order x-major): utils_bpp_acc.py:303-309"""
+        r = self.res[i]
+        pos_grid = my_meshgrid3D(0, r, dev).view(-1, 3)
+        indexes = get_grid_index(self.offs[i + 1] - self.offs[i], r, pos_grid)
+        indexes_sorted, order = torch.sort(indexes, stable=True)
+        del indexes
+        pts = pos_grid.to(torch.int16)[order]
+        del pos_grid, order
+        rows, cnt = torch.unique_consecutive(indexes_sorted, return_counts=True)
+        return rows, cnt, pts
+
+    def layout(self) -> dict:
+        """what a decoder in another process needs to rebuild this object (json-able; goes into the container header)"""
+        seed = self.shuffle_seed
+        return {"num_dim": self.num_dim, "resolutions_list": self.res, "resolutions_list_2D": self.res_2D,
+                "log2_hashmap_size": self.log2_hashmap_size, "log2_hashmap_size_2D": self.log2_hashmap_size_2D,
+                "n_features": self.n_features, "max_context_layer_num": self.max_context_layer_num,
+                "Pg_level": self.Pg_level, "Pg_level_2D": self.Pg_level_2D, "Rb": self.binary_vxl_len,
+                "skip_levels_3D": list(self.skip_levels_3D), "skip_levels_2D": list(self.skip_levels_2D),
+                "use_dimension_wise": self.use_dimension_wise, "use_overlap_area_pool": self.use_overlap_area_pool,
+                "shuffle_seed": seed if isinstance(seed, int) else {"cpu_rng_state_hex": _z85(seed)}}
+
+    @classmethod
+    def from_layout(cls, layout: dict, device="cuda", **kw):
+        lay = dict(layout)
+        seed = lay.pop("shuffle_seed")
+        if isinstance(seed, dict):
+            seed = _unz85(seed["cpu_rng_state_hex"])
+        return cls(ste_binary=True, device=device, shuffle_seed=seed, **lay, **kw)
 
     # ------------------------------------------------------------------------------------------ helpers
     def query_binary_vxl(self, points_n_orig, binary_vxl, n, return_overlap_area=False):

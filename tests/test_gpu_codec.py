@@ -165,21 +165,47 @@ def test_codec_roundtrip_product_layout(cuda):
 
 
 def test_container_roundtrip_feeds_the_decoder(cuda):
-    """encode -> one blob (streams + Pgs + occupancy bits + 13-bit context-model weights) -> unpack -> decode: the
-    decoder side needs nothing but the blob"""
+    """encode -> one blob (streams + Pgs + occupancy bits + 13-bit context-model weights + layout incl. the symbol-order
+    seed) -> a decoder built from NOTHING but the blob (fresh CNC_context_models, fresh GridEncoders, a global generator
+    in another state: ADVICE r1) -> the coded tables"""
     from cnc_b200 import container as C
+    from cnc_b200.context_models import CNC_context_models
+    from cnc_b200.gridencoder import GridEncoder
 
-    cm, encs, vxl = make(cuda, **SMALL)
+    cm, encs, vxl = make(cuda, **SMALL, skip3=(0,))             # level 1 is dense AND context-coded: shuffled symbol order
+    assert cm.res[1] <= cm.resolution_thresh
+    qs = C.quantize_state(cm.state_dict(), digits=13)
+    cm.load_state_dict(C.dequantize_state(qs, device=cuda))      # the encoder runs with the weights the decoder will have
     Pgs, _, coded_MB, streams = cm.encode_binary_vxl_mixPg_3D2D(*encs, vxl, "c", return_streams=True)
-    blob = C.pack(streams, Pgs, vxl, {}, {"res": cm.res, "res_2D": cm.res_2D})
-    assert len(blob) < coded_MB * 1024 * 1024 + vxl.numel() / 8 + 4096
+    blob = C.pack(streams, Pgs, vxl, qs, cm.layout())
+    assert len(blob) < coded_MB * 1024 * 1024 + vxl.numel() / 8 + 16384
+    q = [torch.where(e.params >= 0, 1.0, -1.0) for e in encs]
+    offs, skip = cm.offs, cm.skip_levels_3D
+    del cm, encs
+    torch.manual_seed(987654)
+    torch.rand(11)
     got = C.unpack(blob, device=cuda)
-    assert got["layout"] == {"res": cm.res, "res_2D": cm.res_2D} and torch.equal(got["binary_vxl"], vxl)
-    recs = [torch.ones_like(e.params) for e in encs]
-    out = cm.decode_binary_vxl_mixPg_3D2D(*encs, *recs, got["binary_vxl"], got["Pgs_dict"], "c", streams=got["streams"])
-    ref = cm.decode_binary_vxl_mixPg_3D2D(*encs, *[torch.ones_like(e.params) for e in encs], vxl, Pgs, "c", streams=streams)
-    for a, b in zip(out, ref):
-        assert torch.equal(a, b)
+    lay = got["layout"]
+    cm2 = CNC_context_models.from_layout(lay, device=cuda)
+    cm2.load_state_dict(got["mlp_state"])
+    encs2 = [GridEncoder(num_dim=3, n_features=8, resolutions_list=lay["resolutions_list"], log2_hashmap_size=lay["log2_hashmap_size"],
+                         ste_binary=True).to(cuda)] + \
+            [GridEncoder(num_dim=2, n_features=8, resolutions_list=lay["resolutions_list_2D"], log2_hashmap_size=lay["log2_hashmap_size_2D"],
+                         ste_binary=True).to(cuda) for _ in range(3)]
+    recs = [torch.ones_like(e.params) for e in encs2]
+    out = cm2.decode_binary_vxl_mixPg_3D2D(*encs2, *recs, got["binary_vxl"], got["Pgs_dict"], "c", streams=got["streams"])
+    n_coded = 0
+    for k in range(4):
+        differs = (q[k] != out[k]).any(-1)
+        assert (out[k][differs] == 1).all()                       # rows that were never coded stay +1, everything else is back
+        n_coded += int((~differs).sum())
+    for n in skip:
+        assert torch.equal(q[0][offs[n]:offs[n + 1]], out[0][offs[n]:offs[n + 1]])
+    # the dense context-coded level: a wrong permutation would scatter its symbols to the wrong rows
+    n = 1
+    lvl_q, lvl_o = q[0][offs[n]:offs[n + 1]], out[0][offs[n]:offs[n + 1]]
+    coded = ~(lvl_q != lvl_o).any(-1)
+    assert float(coded.float().mean()) > 0.3 and float((lvl_q[coded] == -1).float().mean()) > 0.2
 
 
 def test_fused_vote_planes_equal_the_list_based_kernels(cuda):
