@@ -11,8 +11,12 @@ positions per GPU drawn inside the radius-1 ball of the +-1.5 aabb with unit vie
 batch.  `value` = samples/s with inputs resident in HBM; `e2e` = the same call fed from pinned
 host memory with the rgb/sigma result read back, copies inside the timed span.
 
-`--impl reference` runs the same workload through the reference's own CUDA kernels (compiled
-unmodified into oracle/_ref) driven by the reference's python data flow (oracle/ref_pipeline.py).
+`--impl reference` runs the same workloads through the UNMODIFIED reference: its own classes
+(NGPRadianceField_mygrid_2D3D, OccGridEstimator, render_image_with_occgrid[_test], CNC_context_models; byte-compiled
+from /root/reference into oracle/_ref/py) on its own CUDA kernels (compiled unmodified into oracle/_ref/*.so), see
+oracle/ref_py.py.  Third-party pieces absent offline stand in as oracle restatements: torchac (the oracle C coder, one
+CPU thread like torchac) and tinycudann's SH encoding.  Only the step loop of the training script
+(train_CNC_nerf_synthetic.py:302-366) is restated here, because the script is not importable.
 """
 from __future__ import annotations
 
@@ -156,18 +160,91 @@ def make_inputs(n, seed, device):
     return pos.float().to(device), dirs.float().to(device)
 
 
-def build_field(device, seed=0):
-    from cnc_b200.field import NGPRadianceField_mygrid_2D3D
+class Arm:
+    """what a leg of the bench needs, from this package (`ours`) or from the unmodified reference (`reference`)"""
 
-    torch.manual_seed(seed)
-    f = NGPRadianceField_mygrid_2D3D(aabb=[-1.5, -1.5, -1.5, 1.5, 1.5, 1.5], n_features_per_level=F, n_neurons=160,
-                                     resolutions_list=R3, log2_hashmap_size=19, resolutions_list_2D=R2,
-                                     log2_hashmap_size_2D=17, ste_binary=True).to(device)
-    with torch.no_grad():  # +-1 with p = 0.5 after STE: worst-case entropy / locality
-        for k in ("xyz", "xy", "xz", "yz"):
-            p = getattr(f.mlp_base, f"encoding_{k}").params
-            p.copy_(torch.where(torch.rand_like(p) < 0.5, -0.5, 0.5))
-    return f
+    def __init__(self, impl, dev):
+        self.impl, self.dev = impl, dev
+        if impl == "ours":
+            from cnc_b200 import nerfacc, render
+            from cnc_b200.context_models import CNC_context_models
+            from cnc_b200.field import NGPRadianceField_mygrid_2D3D
+            from cnc_b200.gridencoder import GridEncoder
+
+            self.Field, self.GridEncoder, self.CM = NGPRadianceField_mygrid_2D3D, GridEncoder, CNC_context_models
+            self.Estimator, self.Rays = nerfacc.OccGridEstimator, render.Rays
+            self.render_train, self.render_test = render.render_image_with_occgrid, render.render_image_with_occgrid_test
+            self.cm_kw = dict(Rb=128, device=dev)
+        else:
+            from oracle import ref_py
+
+            r = ref_py.load()
+            import datasets.utils as du   # the reference's (resolved by oracle/ref_py)
+
+            self.Field, self.GridEncoder, self.CM = r.ngp.NGPRadianceField_mygrid_2D3D, r.ngp.GridEncoder, r.bpp.CNC_context_models
+            self.Estimator, self.Rays = r.nerfacc.OccGridEstimator, du.Rays
+            self.render_train, self.render_test = r.utils.render_image_with_occgrid, r.utils.render_image_with_occgrid_test
+            self.cm_kw = {}
+
+    def field(self, seed=0):
+        torch.manual_seed(seed)
+        f = self.Field(aabb=[-1.5, -1.5, -1.5, 1.5, 1.5, 1.5], n_features_per_level=F, n_neurons=160, resolutions_list=R3,
+                       log2_hashmap_size=19, resolutions_list_2D=R2, log2_hashmap_size_2D=17, ste_binary=True).to(self.dev)
+        g = torch.Generator(device="cpu").manual_seed(seed + 1)
+        with torch.no_grad():  # +-1 with p = 0.5 after STE: worst-case entropy / locality; identical in both arms
+            for k in ("xyz", "xy", "xz", "yz"):
+                p = getattr(f.mlp_base, f"encoding_{k}").params
+                p.copy_(torch.where(torch.rand(p.shape, generator=g) < 0.5, -0.5, 0.5).to(self.dev))
+        return f
+
+    def context_model(self):
+        cm = self.CM(num_dim=3, resolutions_list=R3, resolutions_list_2D=R2, log2_hashmap_size=19, log2_hashmap_size_2D=17,
+                     n_features=F, sample_num=150000, max_context_layer_num=3, ste_binary=True, skip_levels_3D=(0, 1, 2),
+                     skip_levels_2D=(0,), **self.cm_kw)
+        return cm.to(self.dev)
+
+    def estimator(self):
+        est = self.Estimator(roi_aabb=[-1.5, -1.5, -1.5, 1.5, 1.5, 1.5], resolution=128, levels=1).to(self.dev)
+        c = (torch.arange(128, device=self.dev) + 0.5) / 128 * 3 - 1.5
+        X, Y, Z = torch.meshgrid(c, c, c, indexing="ij")
+        est.binaries = (X * X + Y * Y + Z * Z <= 1.0).unsqueeze(0)   # radius-1 ball in the +-1.5 aabb (15.5 % of the cells)
+        est.occs = est.binaries.reshape(-1).float()
+        return est
+
+
+class RefTrainStep:
+    """train_CNC_nerf_synthetic.py:302-366 around the reference's own objects: render_image_with_occgrid -> MSE
+    (+ lmbda * bits per parameter) -> GradScaler-scaled backward -> Adam (field) and Adam (context models), as the script
+    does it (two optimizers, torch's stock Adam, `scaler.scale(loss).backward()` without unscaling, :362-364)."""
+
+    def __init__(self, arm, field, est, cm=None, lmbda=0.0, lr=1e-4):
+        self.arm, self.field, self.est, self.cm, self.lmbda = arm, field, est, cm, lmbda
+        self.opt = torch.optim.Adam([{"params": field.parameters()}], lr=lr, eps=1e-15, weight_decay=2e-6)
+        self.opt2 = None if cm is None else torch.optim.Adam([{"params": cm.parameters()}], lr=lr, eps=1e-15)
+        self.step_id = 0
+
+    def __call__(self, rays, pixels, refresh_occupancy=False):
+        self.field.train()
+        self.est.train()
+        if refresh_occupancy:
+            self.est.update_every_n_steps(step=self.step_id, occ_thre=1e-2,
+                                          occ_eval_fn=lambda x: self.field.query_density(x) * 5e-3)
+        rgb, acc, depth, n = self.arm.render_train(self.field, self.est, rays, render_step_size=5e-3,
+                                                   render_bkgd=torch.ones(3, device=pixels.device))
+        loss = torch.nn.functional.mse_loss(rgb, pixels)
+        if self.cm is not None and self.lmbda > 0:
+            mb = self.field.mlp_base
+            bpp, _ = self.cm.forward_binary_vxl_mixPg_3D2D(mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz,
+                                                           self.est.binaries, step=self.step_id)
+            loss = loss + self.lmbda * bpp
+            self.opt2.zero_grad()
+        self.opt.zero_grad()
+        (loss * 1024.0).backward()
+        self.opt.step()
+        if self.opt2 is not None:
+            self.opt2.step()
+        self.step_id += 1
+        return loss.detach(), n
 
 
 def cpu_baseline(n=4096):
@@ -195,71 +272,108 @@ def cpu_baseline(n=4096):
             "sample": f"{reps} x {n} samples of the same layout through oracle/ (C gather + numpy fp32 MLP)"}
 
 
-def codec_bench(dev, cpu_seconds=12.0, rank=0, world=1, dist=None):
+def codec_bench(arm, cpu_seconds=12.0, rank=0, world=1, dist=None):
     """BASELINE metric (ii): context-model entropy encode + decode of the product hash tables (configs[2]):
     L=12 3D levels (res 18..514, T=2^19) + 3 planes x 4 levels (T=2^17), F=8, ball occupancy, biased +-1 tables,
     random-init context models.  MB/s = fp32 table bytes represented (161.3 MB) / wall time of the public
-    encode_/decode_binary_vxl_mixPg_3D2D call (probabilities + range coding + streams on the host).
-    CPU arm: the reference codes each stream with torchac on one CPU thread; oracle/ restates that coder in C
-    and is timed here on a bounded sample of the same (cdf, symbol) streams.
+    encode_/decode_binary_vxl_mixPg_3D2D call (probabilities + range coding + streams on the host / in files).
+    Reference arm: the reference's own CNC_context_models on its own kernels, coding each stream with the torchac
+    stand-in (oracle C coder) on one CPU thread after a D2H copy, exactly the structure of utils_bpp_acc.py:77-110.
+    CPU baseline (ours arm): the bare coder over the same (cdf, symbol) streams on one thread and on all host cores.
     N > 1: the codec of one scene does not shard (a level's largest stream is one serial chain and levels decode in
     order), so every rank codes its own scene -- replicas only; MB/s = N x table bytes / max-over-ranks time."""
-    from cnc_b200 import torchac as tac
-    from cnc_b200.context_models import CNC_context_models
-    from cnc_b200.gridencoder import GridEncoder
-    from oracle import oracle as o
+    import tempfile
 
-    torch.manual_seed(rank)
+    dev, ours = arm.dev, arm.impl == "ours"
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
     t0 = time.perf_counter()
-    encs = [GridEncoder(num_dim=3, n_features=F, resolutions_list=R3, log2_hashmap_size=19, ste_binary=True).to(dev)] + \
-           [GridEncoder(num_dim=2, n_features=F, resolutions_list=R2, log2_hashmap_size=17, ste_binary=True).to(dev) for _ in range(3)]
+    encs = [arm.GridEncoder(num_dim=3, n_features=F, resolutions_list=R3, log2_hashmap_size=19, ste_binary=True).to(dev)] + \
+           [arm.GridEncoder(num_dim=2, n_features=F, resolutions_list=R2, log2_hashmap_size=17, ste_binary=True).to(dev) for _ in range(3)]
     with torch.no_grad():
         for e in encs:
-            e.params.copy_(torch.where(torch.rand_like(e.params) < 0.7, 0.5, -0.5))
-    cm = CNC_context_models(num_dim=3, resolutions_list=R3, resolutions_list_2D=R2, log2_hashmap_size=19,
-                            log2_hashmap_size_2D=17, n_features=F, sample_num=150000, max_context_layer_num=3,
-                            ste_binary=True, Rb=128, skip_levels_3D=(0, 1, 2), skip_levels_2D=(0,), device=dev)
+            e.params.copy_(torch.where(torch.rand(e.params.shape, generator=g) < 0.7, 0.5, -0.5).to(dev))
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    torch.manual_seed(rank)
+    cm = arm.context_model()
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t1
     with torch.no_grad():
         cm.context_model_3D[4].bias.fill_(0.6)
         for sq in cm.context_model_2D:
             sq[0].bias.fill_(0.6)
-    c = (torch.arange(128, device=dev) + 0.5) / 128 * 3 - 1.5
-    X, Y, Z = torch.meshgrid(c, c, c, indexing="ij")
-    vxl = (X * X + Y * Y + Z * Z <= 1.0).unsqueeze(0)   # radius-1 ball in the +-1.5 aabb (15.5 % of the cells)
-    torch.cuda.synchronize()
-    t_setup = time.perf_counter() - t0
+    vxl = arm.estimator().binaries
+    tmp = tempfile.mkdtemp(prefix="cnc_bench_")
+    prefix = os.path.join(tmp, "bench")
     captured = {"c1": [], "sym": []}
-    orig = tac.encode_streams_async
+    ctx_ms = []          # (launch ms, voxels, entries) of every cnc_context3d_probs launch of the timed encodes
+    if ours:
+        from cnc_b200 import torchac as tac
 
-    def spy(c1s, syms):
-        captured["c1"] += list(c1s)
-        captured["sym"] += list(syms)
-        return orig(c1s, syms)
+        orig, orig_fused = tac.encode_streams_async, cm._probs_3D_fused
 
-    tac.encode_streams_async = spy
-    try:
-        cm.encode_binary_vxl_mixPg_3D2D(*encs, vxl, "bench", return_streams=True)  # warm-up (+ capture the streams)
-    finally:
-        tac.encode_streams_async = orig
-    enc_s, dec_s = [], []
+        def spy(c1s, syms):
+            captured["c1"] += list(c1s)
+            captured["sym"] += list(syms)
+            return orig(c1s, syms)
+
+        def timed_fused(Enc, table, bvx, n, lo, hi, Pg_n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = orig_fused(Enc, table, bvx, n, lo, hi, Pg_n)
+            e1.record()
+            ctx_ms.append((e0, e1, cm._cs_host(n, hi) - cm._cs_host(n, lo), hi - lo))
+            return out
+
+        tac.encode_streams_async = spy
+        try:
+            cm.encode_binary_vxl_mixPg_3D2D(*encs, vxl, prefix, return_streams=True)  # warm-up (+ capture the streams)
+        finally:
+            tac.encode_streams_async = orig
+
+    def encode():
+        with torch.no_grad():
+            if ours:
+                return cm.encode_binary_vxl_mixPg_3D2D(*encs, vxl, prefix, return_streams=True)
+            return cm.encode_binary_vxl_mixPg_3D2D(*encs, vxl, prefix) + (None,)
+
+    def decode(Pgs, streams):
+        recs = [torch.ones_like(e.params) for e in encs]
+        with torch.no_grad():
+            if ours:
+                return cm.decode_binary_vxl_mixPg_3D2D(*encs, *recs, vxl, Pgs, prefix, streams=streams)
+            return cm.decode_binary_vxl_mixPg_3D2D(*encs, *recs, vxl, Pgs, prefix)
+
     def sync():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(3):
+    if not ours:
+        encode()   # warm-up
+    enc_s, dec_s = [], []
+    for it in range(3 if ours else 2):
+        if ours and it == 2:
+            cm._probs_3D_fused = timed_fused    # the per-launch events go into the last repetition only
         sync(); t = time.perf_counter()
-        Pgs, est_MB, coded_MB, streams = cm.encode_binary_vxl_mixPg_3D2D(*encs, vxl, "bench", return_streams=True)
+        Pgs, est_MB, coded_MB, streams = encode()
         sync(); enc_s.append(time.perf_counter() - t)   # after the barrier: the slowest rank's time
-        recs = [torch.ones_like(e.params) for e in encs]
+        if ours:
+            cm._probs_3D_fused = orig_fused
         sync(); t = time.perf_counter()
-        out = cm.decode_binary_vxl_mixPg_3D2D(*encs, *recs, vxl, Pgs, "bench", streams=streams)
+        out = decode(Pgs, streams)
         sync(); dec_s.append(time.perf_counter() - t)
     ok = all(bool(((torch.where(e.params >= 0, 1.0, -1.0) == r) | (r == 1)).all()) for e, r in zip(encs, out))
     n_params = sum(e.params.numel() for e in encs)
     table_MB = n_params * 4 / 1e6
-    n_sym = sum(int(x.numel()) for x in captured["sym"])
+    if ours:
+        n_sym = sum(int(x.numel()) for x in captured["sym"])
+    else:   # 8 symbols per coded byte-stream row: count from the tables (every coded row is restored, the others stay +1)
+        n_sym = None
+    import shutil
+
+    shutil.rmtree(tmp, ignore_errors=True)
     if dist is not None:
         flag = torch.tensor([1.0 if ok else 0.0, min(enc_s), min(dec_s)], dtype=torch.float64, device=dev)
         mn = flag.clone(); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
@@ -268,12 +382,39 @@ def codec_bench(dev, cpu_seconds=12.0, rank=0, world=1, dist=None):
         enc_s, dec_s = [float(mx[1])], [float(mx[2])]
     if rank != 0:
         return None
+    enc, dec = min(enc_s), min(dec_s)
+    res = {"workload": "configs[2]: product tables L=12 T=2^19 + 3x4 planes T=2^17, F=8, ball occupancy, 33 streams"
+                       + (f"; {world} scenes, one per GPU (replicas only)" if world > 1 else ""),
+           "table_MB_fp32": table_MB, "table_MB_1bit": n_params / 8 / 1e6, "coded_MiB": coded_MB, "estimated_MiB": est_MB,
+           "encode_s": enc, "decode_s": dec, "encode_MBps": world * table_MB / enc, "decode_MBps": world * table_MB / dec,
+           "roundtrip_ok": ok, "scaling": "weak (replicas)" if world > 1 else "n/a", "setup_s": t_setup,
+           "setup_what": "CNC_context_models.__init__: inverse hash tables of all levels (utils_bpp_acc.py:294-335)"}
+    if not ours:
+        res["coder"] = "torchac stand-in: oracle C range coder, one CPU thread, after a D2H copy (utils_bpp_acc.py:77-110)"
+        return res
+    from oracle import oracle as o
+
+    res.update({"symbols": n_sym, "encode_Msym_per_s": world * n_sym / enc / 1e6, "decode_Msym_per_s": world * n_sym / dec / 1e6})
+    # dominant kernel of the encode: cnc_context3d_probs (one launch per coded chunk), timed live with CUDA events
+    if ctx_ms:
+        hbm_peak, which = peaks()
+        ms_l = [e0.elapsed_time(e1) for e0, e1, _, _ in ctx_ms]
+        vox, ent = sum(v for _, _, v, _ in ctx_ms), sum(e for _, _, _, e in ctx_ms)
+        # algorithmic bytes (codec): per voxel 6 B of int16 coordinates + the masked 3-level context gather
+        # 3 x 8 corners x F x 4 B; per entry 8 B of run offsets + F x 4 B of probabilities + 1 B exists flag
+        bytes_alg = vox * (6 + 3 * 8 * F * 4) + ent * (8 + 4 * F + 1)
+        ach = bytes_alg / (sum(ms_l) * 1e-3) / 1e9
+        res["roofline"] = {"bound": "hbm", "kernel": "cnc::context3d_kernel (mask + 3-level masked gather + 25-32-32-8 MLP + overlap-weighted mean)",
+                           "achieved": ach, "peak": hbm_peak, "peak_source": which, "unit": "GB/s", "frac": ach / hbm_peak,
+                           "traffic": ncu_traffic("context3d_kernel", "encode"), "launches": len(ms_l),
+                           "ms_all_launches": sum(ms_l), "voxels": vox, "entries": ent, "algorithmic_bytes": bytes_alg,
+                           "note": "the context tables are read as 1-bit planes from L2, so DRAM traffic << algorithmic bytes; the "
+                                   "kernel is FFMA-issue bound (2080 FMA per voxel), see profiles/"}
     # CPU coder on a bounded sample: streams in descending size until the time budget is used
     order = sorted(range(len(captured["sym"])), key=lambda k: -captured["sym"][k].numel())
+    host = [(captured["c1"][k].cpu().numpy().view(np.uint16), captured["sym"][k].cpu().numpy()) for k in order]
     done_sym, t_cpu = 0, 0.0
-    for k in order:
-        c1 = captured["c1"][k].cpu().numpy().view(np.uint16)
-        sy = captured["sym"][k].cpu().numpy()
+    for c1, sy in host:
         t = time.perf_counter()
         data = o.ac_encode(c1, sy)
         o.ac_decode(c1, data)
@@ -282,34 +423,37 @@ def codec_bench(dev, cpu_seconds=12.0, rank=0, world=1, dist=None):
         if t_cpu > cpu_seconds:
             break
     cpu_sym_per_s = done_sym / t_cpu            # encode + decode of each symbol, one thread
-    enc, dec = min(enc_s), min(dec_s)
-    return {"workload": "configs[2]: product tables L=12 T=2^19 + 3x4 planes T=2^17, F=8, ball occupancy, 33 streams"
-                        + (f"; {world} scenes, one per GPU (replicas only)" if world > 1 else ""),
-            "table_MB_fp32": table_MB, "table_MB_1bit": n_params / 8 / 1e6, "coded_MiB": coded_MB, "estimated_MiB": est_MB,
-            "symbols": n_sym, "encode_s": enc, "decode_s": dec, "encode_MBps": world * table_MB / enc,
-            "decode_MBps": world * table_MB / dec, "encode_Msym_per_s": world * n_sym / enc / 1e6,
-            "decode_Msym_per_s": world * n_sym / dec / 1e6, "roundtrip_ok": ok, "scaling": "weak (replicas)" if world > 1 else "n/a",
-            "setup_s": t_setup,
-            "cpu_baseline": {"kind": "port", "cores": 1, "unit": "MB/s",
-                             "value": table_MB / (n_sym / cpu_sym_per_s),
-                             "Msym_per_s_enc_plus_dec": cpu_sym_per_s / 1e6,
-                             "sample": f"{done_sym} of {n_sym} symbols (largest streams first) through oracle/ C range coder, "
-                                       "encode+decode, one thread; MB/s = table bytes / (coder time for all symbols, "
-                                       "encode+decode); probabilities not included (the reference computes them on the GPU)"}}
+    # all host cores: the 33 streams dealt to a thread pool, largest first (ctypes releases the GIL inside the C coder)
+    from concurrent.futures import ThreadPoolExecutor
+
+    cores = os.cpu_count() or 1
+
+    def one(cs):
+        d = o.ac_encode(cs[0], cs[1])
+        o.ac_decode(cs[0], d)
+        return cs[1].size
+
+    t = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        done_all = sum(ex.map(one, host))
+    t_all = time.perf_counter() - t
+    res["cpu_baseline"] = {"kind": "port", "cores": 1, "unit": "MB/s", "value": table_MB / (n_sym / cpu_sym_per_s),
+                           "Msym_per_s_enc_plus_dec": cpu_sym_per_s / 1e6,
+                           "sample": f"{done_sym} of {n_sym} symbols (largest streams first) through oracle/ C range coder, "
+                                     "encode+decode, one thread; MB/s = table bytes / (coder time for all symbols, "
+                                     "encode+decode); probabilities not included (the reference computes them on the GPU)",
+                           "all_cores": {"cores": cores, "value": table_MB / t_all, "unit": "MB/s", "seconds": t_all,
+                                         "sample": f"all {len(host)} streams ({done_all} symbols), encode+decode, one thread-pool task per "
+                                                   f"stream over {cores} threads: bounded below by the longest stream's serial chain"}}
+    return res
 
 
-def train_bench(dev, rank, world, steps, field):
-    """forward + backward + (N > 1: NCCL all-reduce of all gradients) + Adam on a synthetic ray batch per rank:
-    rays from a radius-4 sphere towards the origin, ball occupancy, random target pixels."""
-    from cnc_b200.nerfacc import OccGridEstimator
-    from cnc_b200.render import Rays
-    from cnc_b200.trainer import TrainStep
-
-    est = OccGridEstimator(roi_aabb=[-1.5, -1.5, -1.5, 1.5, 1.5, 1.5], resolution=128, levels=1).to(dev)
-    c = (torch.arange(128, device=dev) + 0.5) / 128 * 3 - 1.5
-    X, Y, Z = torch.meshgrid(c, c, c, indexing="ij")
-    est.binaries = (X * X + Y * Y + Z * Z <= 1.0).unsqueeze(0)
-    est.occs = est.binaries.reshape(-1).float()
+def train_bench(arm, rank, world, steps, field):
+    """forward + backward + (N > 1: NCCL exchange of the gradients) + Adam on a synthetic ray batch per rank:
+    rays from a radius-4 sphere towards the origin, ball occupancy, random target pixels.
+    Reference arm: the same step around the reference's own objects (RefTrainStep), single GPU."""
+    dev, ours = arm.dev, arm.impl == "ours"
+    est = arm.estimator()
     g = torch.Generator(device="cpu").manual_seed(7 + rank)
     n_rays = 1100
     o = torch.randn(n_rays, 3, generator=g)
@@ -317,12 +461,20 @@ def train_bench(dev, rank, world, steps, field):
     tgt = (torch.rand(n_rays, 3, generator=g) - 0.5) * 1.2
     d = tgt - o
     d = d / d.norm(dim=-1, keepdim=True)
-    rays = Rays(o.to(dev), d.to(dev))
+    rays = arm.Rays(o.to(dev), d.to(dev))
     pixels = torch.rand(n_rays, 3, generator=g).to(dev)
-    ts = TrainStep(field, est, lr=1e-4)
+    bk = torch.ones(3, device=dev)
+    if ours:
+        from cnc_b200.trainer import TrainStep
+
+        ts = TrainStep(field, est, lr=1e-4)
+        call = lambda t: t(rays, pixels, render_bkgd=bk, refresh_occupancy=False)
+    else:
+        ts = RefTrainStep(arm, field, est, lr=1e-4)
+        call = lambda t: t(rays, pixels, refresh_occupancy=False)
     n_s = 0
     for _ in range(3):
-        _, n_s = ts(rays, pixels, refresh_occupancy=False)
+        _, n_s = call(ts)
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
@@ -330,8 +482,8 @@ def train_bench(dev, rank, world, steps, field):
     e0.record()
     tot = 0
     for _ in range(steps):
-        _, n_s = ts(rays, pixels, refresh_occupancy=False)
-        tot += n_s
+        _, n_s = call(ts)
+        tot += int(n_s)
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1), float(tot)], dtype=torch.float64, device=dev)
@@ -342,67 +494,85 @@ def train_bench(dev, rank, world, steps, field):
         torch.distributed.all_reduce(cnt, op=torch.distributed.ReduceOp.SUM)
         t = torch.cat([ms, cnt])
     ms, tot = t.tolist()
-    out = {"what": "occupancy march + visibility pass (fused density kernel) + fused forward (cnc_field_fwd_train) + volume "
-                   "rendering + MSE + backward (cnc_dgrad / cnc_wgrad / K2) + gradient all-reduce + fused Adam",
-           "steps": steps, "ms_per_step": ms / steps,
+    out = {"what": ("occupancy march + visibility pass (fused density kernel) + fused forward (cnc_field_fwd_train) + volume "
+                    "rendering + MSE + backward (cnc_dgrad / cnc_wgrad / K2) + gradient exchange + fused Adam") if ours else
+                   ("reference: estimator.sampling (traverse_grids 2 passes + query_density) + rendering(radiance_field) + MSE + "
+                    "autograd backward + torch Adam (train_CNC_nerf_synthetic.py:302-366)"),
+           "steps": steps, "ms_per_step": ms / steps, "scaling": "weak",
            "samples_per_step_all_ranks": tot / steps, "samples_per_s": tot / (ms * 1e-3),
-           "allreduce_bytes_per_step": ts.reducer.bytes_per_step() if world > 1 else 0, "rays_per_rank": n_rays}
+           "comm_bytes_per_step": ts.comm_bytes_per_step() if (ours and world > 1) else 0, "rays_per_rank": n_rays}
+    if ours and world > 1:
+        out["comm"] = ts.comm_description()
     if world == 1:
         # the same step with the rate term of the CNC loss (lambda > 0: context model on 150 000 sampled entries + planes)
-        from cnc_b200.context_models import CNC_context_models
-
-        cm = CNC_context_models(num_dim=3, resolutions_list=R3, resolutions_list_2D=R2, log2_hashmap_size=19, log2_hashmap_size_2D=17,
-                                n_features=F, sample_num=150000, max_context_layer_num=3, ste_binary=True, Rb=128,
-                                skip_levels_3D=(0, 1, 2), skip_levels_2D=(0,), device=dev)
-        ts2 = TrainStep(field, est, context_model=cm, lmbda=1e-3, lr=1e-4)
+        cm = arm.context_model()
+        if ours:
+            ts2 = TrainStep(field, est, context_model=cm, lmbda=1e-3, lr=1e-4)
+        else:
+            ts2 = RefTrainStep(arm, field, est, cm=cm, lmbda=1e-3, lr=1e-4)
         for _ in range(2):
-            ts2(rays, pixels, refresh_occupancy=False)
+            call(ts2)
         torch.cuda.synchronize()
         e0.record()
         for _ in range(steps):
-            ts2(rays, pixels, refresh_occupancy=False)
+            call(ts2)
         e1.record()
         torch.cuda.synchronize()
         out["with_rate_term"] = {"what": "same step + lambda * bits-per-parameter (forward_binary_vxl_mixPg_3D2D, 150 000 sampled "
                                          "entries, dimension-wise context) and its backward", "lambda": 1e-3,
                                  "ms_per_step": e0.elapsed_time(e1) / steps}
+        # the rate term alone (forward + backward), the part of the step utils_bpp_acc.py:533-706 owns
+        mb = field.mlp_base
+        encs = (mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz)
+
+        def rate_only(k):
+            bpp, _ = cm.forward_binary_vxl_mixPg_3D2D(*encs, est.binaries, step=k)
+            bpp.backward()
+            for p in list(field.parameters()) + list(cm.parameters()):
+                p.grad = None
+
+        rate_only(1)
+        torch.cuda.synchronize()
+        e0.record()
+        for k in range(steps):
+            rate_only(1 + k)
+        e1.record()
+        torch.cuda.synchronize()
+        out["with_rate_term"]["rate_term_alone_ms"] = e0.elapsed_time(e1) / steps
         del cm, ts2
         torch.cuda.empty_cache()
         # test-time renderer: one 256 x 256 view of the same scene through render_image_with_occgrid_test
-        from cnc_b200.render import render_image_with_occgrid_test
-
         H = W = 256
         v, u = torch.meshgrid(torch.linspace(-0.3, 0.3, H, device=dev), torch.linspace(-0.3, 0.3, W, device=dev), indexing="ij")
         dirs = torch.stack([u, v, torch.ones_like(u)], -1)
         dirs = dirs / dirs.norm(dim=-1, keepdim=True)
-        img = Rays(torch.tensor([0.0, 0.0, -4.0], device=dev).expand(H, W, 3).contiguous(), dirs.contiguous())
+        img = arm.Rays(torch.tensor([0.0, 0.0, -4.0], device=dev).expand(H, W, 3).contiguous(), dirs.contiguous())
         was_training = field.training
         field.eval()
-        kw = dict(render_step_size=5e-3, render_bkgd=torch.ones(3, device=dev))
-        render_image_with_occgrid_test(1024, field, est, img, **kw)
+        kw = dict(render_step_size=5e-3, render_bkgd=bk)
+        arm.render_test(1024, field, est, img, **kw)
         torch.cuda.synchronize()
         e0.record()
-        _, opa, _, n_tot = render_image_with_occgrid_test(1024, field, est, img, **kw)
+        _, opa, _, n_tot = arm.render_test(1024, field, est, img, **kw)
         e1.record()
         torch.cuda.synchronize()
-        field.train(was_training)
         ms_img = e0.elapsed_time(e1)
-        out["test_render"] = {"what": "render_image_with_occgrid_test: wavefront rounds of march + fused forward + compositing, "
+        out["test_render"] = {"what": "render_image_with_occgrid_test (examples/utils.py:316-489), the reference's round schedule, "
                                       "early stop at 1 - 1e-4, untrained field (low density: most rays run to the far side)",
                               "rays": H * W, "samples": int(n_tot), "ms_per_image": ms_img,
                               "rays_per_s": H * W / (ms_img * 1e-3), "samples_per_s": n_tot / (ms_img * 1e-3),
                               "mean_opacity": float(opa.mean())}
-        field.eval()
-        render_image_with_occgrid_test(1024, field, est, img, samples_per_round=32, **kw)
-        torch.cuda.synchronize()
-        e0.record()
-        _, _, _, n_k = render_image_with_occgrid_test(1024, field, est, img, samples_per_round=32, **kw)
-        e1.record()
-        torch.cuda.synchronize()
+        if ours:
+            arm.render_test(1024, field, est, img, samples_per_round=32, **kw)
+            torch.cuda.synchronize()
+            e0.record()
+            _, _, _, n_k = arm.render_test(1024, field, est, img, samples_per_round=32, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            out["test_render"]["fixed_rounds_of_32"] = {"what": "same view, samples_per_round=32 (fewer, larger rounds; same image within "
+                                                               "early_stop_eps)", "samples": int(n_k), "ms_per_image": e0.elapsed_time(e1),
+                                                       "rays_per_s": H * W / (e0.elapsed_time(e1) * 1e-3)}
         field.train(was_training)
-        out["test_render"]["fixed_rounds_of_32"] = {"what": "same view, samples_per_round=32 (fewer, larger rounds; same image within "
-                                                           "early_stop_eps)", "samples": int(n_k), "ms_per_image": e0.elapsed_time(e1),
-                                                   "rays_per_s": H * W / (e0.elapsed_time(e1) * 1e-3)}
     return out
 
 
@@ -434,21 +604,17 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     Ns = a.samples
-    field = build_field(dev, seed=0)  # replicas: identical weights on every rank
-    pos, dirs = make_inputs(Ns, seed=1000 + rank, device=dev)  # each rank its own sample shard
     if a.impl == "reference":
-        from oracle import ref_ext
-        from oracle.ref_pipeline import RefField
+        from oracle import ref_py
 
-        if ref_ext.load("_gridencoder") is None:
+        if not ref_py.available():
             if rank == 0:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/_gridencoder.so not built"}))
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference binaries + bytecode) not built"}))
             return
-        ref = RefField([-1.5, -1.5, -1.5, 1.5, 1.5, 1.5], R3, 19, R2, 17, F, 160).to(dev)
-        ref.load_from(field)
-        model = ref
-    else:
-        model = field
+    arm = Arm(a.impl, dev)
+    field = arm.field(seed=0)  # replicas: identical weights on every rank
+    pos, dirs = make_inputs(Ns, seed=1000 + rank, device=dev)  # each rank its own sample shard
+    model = field
     model.eval()
 
     from cnc_b200 import _lib
@@ -539,7 +705,7 @@ def main():
     if a.no_e2e:
         ms_k = ms
     elif a.impl == "reference":
-        enc = model.encoding_xyz
+        enc = model.mlp_base.encoding_xyz
         xn = ((pos + 1.5) / 3.0).contiguous()
         with torch.no_grad():
             for _ in range(3):
@@ -575,18 +741,18 @@ def main():
             p.grad = None
         model.eval()
     train = None
-    if a.impl == "ours" and a.train_steps > 0:
-        train = train_bench(dev, rank, world, a.train_steps, field)
+    if a.train_steps > 0 and not a.no_e2e and (a.impl == "ours" or world == 1):
+        train = train_bench(arm, rank, world, a.train_steps, field)
     t = torch.tensor([ms, ms_e2e, ms_k, ms_stream], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e, ms_k, ms_stream = t.tolist()
     codec = None
-    if a.impl == "ours" and not a.no_codec:
+    if not a.no_codec and not a.no_e2e and (a.impl == "ours" or world == 1):
         del model
         field = None
         torch.cuda.empty_cache()
-        codec = codec_bench(dev, rank=rank, world=world, dist=dist)
+        codec = codec_bench(arm, rank=rank, world=world, dist=dist)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -639,8 +805,9 @@ def main():
     }
     if a.impl == "reference":
         line["cpu_baseline"] = {"value": line["value"], "unit": "samples/s", "cores": 0, "kind": "reference",
-                                "sample": "reference CUDA kernels (oracle/_ref) + torch fp32 MLP on the GPU: the "
-                                          "reference has no CPU implementation of this path"}
+                                "sample": "the unmodified reference classes (oracle/_ref/py) on the reference CUDA kernels "
+                                          "(oracle/_ref/*.so) + torch fp32 MLP on the GPU: the reference has no CPU "
+                                          "implementation of this path; its CPU piece is the entropy coder (codec.coder)"}
     elif world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     if fwd_bwd is not None:

@@ -3,6 +3,12 @@ occupancy grid, each rank its own ray shard, ONE exchange per step -- a bucketed
 (dominated by the 161 MB hash-table gradient at the product layout) -- plus an 8-byte all-reduce of the sample
 count that drives the adaptive ray budget (train_CNC_nerf_synthetic.py:340-344).  The reference has no distributed
 code; this is the B200 equivalent described in SURVEY 8(e).  Works on NCCL (GPU) and gloo (CPU tests).
+
+`ShardedTableAdam` is the exchange of the latent tables: the rows of every table are split over the ranks, the gradient is
+REDUCE-SCATTERED (each rank receives the average of its rows only: half the traffic of an all-reduce), Adam runs on the
+owned rows (1/N of the 40 M latents, one pass that also emits the rows' two STE bit planes), and what comes back is an
+ALL-GATHER of the bit planes -- 2 bits per latent, 10 MB instead of 161 MB -- because the field reads a latent only through
+sign(p) (forward) and [|p| <= 1] (backward).  Rows a rank does not own hold a stand-in with the same two bits.
 """
 from __future__ import annotations
 
@@ -74,19 +80,123 @@ class GradAllReducer:
                 if flat is None:
                     ps[0].grad = ps[0].grad.contiguous()
                     flat = ps[0].grad.view(-1)
-                pending.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat, None))
+                pending.append((dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True), flat, None))
             else:
                 flat = torch.cat([p.grad.reshape(-1) for p in ps])
-                pending.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat, ps))
+                pending.append((dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True), flat, ps))
         for work, flat, ps in pending:
             work.wait()
-            flat.div_(world)
             if ps is not None:
                 off = 0
                 for p in ps:
                     n = p.numel()
                     p.grad.copy_(flat[off:off + n].view_as(p.grad))
                     off += n
+
+
+class ShardedTableAdam:
+    """Adam over the latent hash tables of `encoders` (GridEncoder modules, F = 8 product tables), rows split over the
+    ranks of `group`.  One `step()` per training iteration, after `backward()`:
+
+        reduce-scatter(AVG) of every table gradient        -> this rank's rows          [161 MB in, 161/N MB out]
+        Adam + bit-plane refresh on the owned rows          (train_ops.adam_planes, one pass)
+        all-gather of the sign and window planes            [2 x 5 MB]
+        stand-in latents for the rows owned elsewhere       (train_ops.surrogate_fill, one write pass)
+
+    A table of n elements is cut at multiples of 32*world elements (whole words of the bit planes per rank); the < 32*world
+    elements behind the last cut are replicated: their gradient is all-reduced and every rank updates them identically.
+    The sign plane is handed to the encoder's sign cache, so the forward of the next step starts without a repack pass.
+    world == 1 is the same code without the collectives.  `sync_params()` all-gathers the true fp32 rows (checkpoints)."""
+
+    def __init__(self, encoders, lr: float = 6e-3, betas=(0.9, 0.999), eps: float = 1e-15, weight_decay: float = 0.0, group=None):
+        from .train_ops import planes_pack
+
+        self.encoders = list(encoders)
+        self.lr, self.betas, self.eps, self.weight_decay, self.group = lr, betas, eps, weight_decay, group
+        on = dist.is_initialized()
+        self.world = dist.get_world_size(group) if on else 1
+        self.rank = dist.get_rank(group) if on else 0
+        self.step_id = 0
+        self.tables = []
+        for enc in self.encoders:
+            p = enc.params
+            n = p.numel()
+            if n % 32:
+                raise ValueError("ShardedTableAdam needs tables with numel % 32 == 0 (rows are multiples of 8: any F >= 4)")
+            gran = 32 * self.world
+            n_main = n // gran * gran
+            S = n_main // self.world
+            lo, hi = self.rank * S, (self.rank + 1) * S
+            t = {"p": p, "n": n, "n_main": n_main, "S": S, "lo": lo, "hi": hi,
+                 "m": torch.zeros(S, device=p.device), "v": torch.zeros(S, device=p.device),
+                 "tm": torch.zeros(n - n_main, device=p.device), "tv": torch.zeros(n - n_main, device=p.device)}
+            t["sign"], t["mask"] = planes_pack(p.detach().contiguous().view(-1))
+            self.tables.append(t)
+
+    def comm_bytes_per_step(self) -> int:
+        """bytes this rank hands to the collectives per step (reduce-scatter input + its share of the all-gathers)"""
+        if self.world == 1:
+            return 0
+        return sum(4 * t["n_main"] + 4 * (t["n"] - t["n_main"]) + 2 * t["S"] // 8 for t in self.tables)
+
+    @torch.no_grad()
+    def step(self) -> None:
+        from .train_ops import adam_planes, surrogate_fill
+
+        self.step_id += 1
+        W, pend = self.world, []
+        for t in self.tables:
+            p = t["p"]
+            g = p.grad if p.grad is not None else torch.zeros_like(p)
+            g = g.contiguous().view(-1)
+            if W > 1:
+                gs = torch.empty(t["S"], device=g.device)
+                w1 = dist.reduce_scatter_tensor(gs, g[:t["n_main"]], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+                gt = g[t["n_main"]:].clone()
+                w2 = dist.all_reduce(gt, op=dist.ReduceOp.AVG, group=self.group, async_op=True) if gt.numel() else None
+                pend.append((gs, gt, w1, w2, g))   # (g is kept alive until the collective has read it)
+            else:
+                pend.append((g[:t["n_main"]], g[t["n_main"]:], None, None, g))
+        gathers = []
+        for t, (gs, gt, w1, w2, _) in zip(self.tables, pend):
+            if w1 is not None:
+                w1.wait()
+            if w2 is not None:
+                w2.wait()
+            flat = t["p"].detach().view(-1)
+            lo, hi, nm = t["lo"], t["hi"], t["n_main"]
+            kw = dict(step=self.step_id, lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
+            adam_planes(flat[lo:hi], gs, t["m"], t["v"], sign=t["sign"][lo // 8:hi // 8], mask=t["mask"][lo // 8:hi // 8], **kw)
+            if t["n"] > nm:
+                adam_planes(flat[nm:], gt, t["tm"], t["tv"], sign=t["sign"][nm // 8:], mask=t["mask"][nm // 8:], **kw)
+            if W > 1:
+                for plane in (t["sign"], t["mask"]):
+                    mine = plane[lo // 8:hi // 8].clone()
+                    gathers.append(dist.all_gather_into_tensor(plane[:nm // 8], mine, group=self.group, async_op=True))
+        for w in gathers:
+            w.wait()
+        for t, enc in zip(self.tables, self.encoders):
+            p = t["p"]
+            if W > 1:
+                tail = p.detach().view(-1)[t["n_main"]:].clone()
+                surrogate_fill(p.detach().view(-1), t["sign"], t["mask"], t["lo"], t["hi"])
+                p.detach().view(-1)[t["n_main"]:] = tail
+            torch.autograd.graph.increment_version(p)         # the kernels wrote through raw pointers
+            cache = getattr(enc, "_sign_cache", None)
+            if cache is not None and p.is_cuda:               # the next forward gathers from this plane: no repack pass
+                cache.bits, cache.key = t["sign"], (p.data_ptr(), p._version, tuple(p.shape))
+
+    @torch.no_grad()
+    def sync_params(self) -> None:
+        """make `.params` the true fp32 latents on every rank (before a checkpoint; not needed for training or encoding,
+        which read signs only)"""
+        if self.world == 1:
+            return
+        for t in self.tables:
+            flat = t["p"].detach().view(-1)
+            mine = flat[t["lo"]:t["hi"]].clone()
+            dist.all_gather_into_tensor(flat[:t["n_main"]], mine, group=self.group)
+            torch.autograd.graph.increment_version(t["p"])
 
 
 def allreduce_scalar(value: float, device, op=None, group=None) -> float:

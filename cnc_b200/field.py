@@ -131,7 +131,8 @@ class _FusedFieldTrain(Function):
         gW3, gb3 = g3[:95].t(), g3[96]
         # base: [density pre-activation | geo] = Linear(160,80)(relu(Linear(255,160)(x0)))
         dz2 = dgrad(dz3, W3, 80, col_off=15, n_first=1)         # columns 1..79 = dz3 @ W3[:, 16:], column 0 = 0
-        dz2[:, 0] = (g_sigma * sigma.unsqueeze(-1)).squeeze(-1)  # d trunc_exp(h-1)*selector / dh = density
+        # d trunc_exp(h-1)*selector / dh = exp(min(h-1, 15)) * selector (ngp.py:328-334) = density, capped at e^15
+        dz2[:, 0] = (g_sigma * torch.clamp(sigma, max=3269017.3724721107).unsqueeze(-1)).squeeze(-1)
         g2 = wgrad(h1, dz2, with_ones=True)
         gW2, gb2 = g2[:160].t(), g2[160]
         dz1 = dgrad(dz2, W2, 160, h=h1)
@@ -335,6 +336,10 @@ class NGPRadianceField_mygrid_2D3D(nn.Module):
             pipes = self._host_pipe = {"s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev)}
         st = pipes.get(slot)
         if st is None or st["n"] < n:
+            if st is not None:   # an earlier asynchronous call on this slot may still be reading / writing its staging buffers
+                torch.cuda.current_stream(dev).synchronize()
+                pipes["s_in"].synchronize()
+                pipes["s_out"].synchronize()
             st = pipes[slot] = {"n": n, "pos": torch.empty(n, 3, device=dev), "dir": torch.empty(n, 3, device=dev),
                                 "rgb": torch.empty(n, 3, device=dev), "sig": torch.empty(n, device=dev)}
         mb = self.mlp_base

@@ -197,7 +197,12 @@ class GridEncoder(nn.Module):
 
     def reset_parameters(self):
         std = 1e-4
-        self.params.data.uniform_(-std, std)
+        with torch.no_grad():   # (an in-place op on the parameter itself: bumps the version the sign cache is keyed on)
+            self.params.uniform_(-std, std)
+
+    def invalidate(self):
+        """forget the cached sign planes (after writing to `params` through `.data` or a raw pointer)"""
+        self._sign_cache.key = self._sign_cache_out.key = None
 
     def __repr__(self):
         return (f"GridEncoder: num_dim={self.num_dim} n_levels={self.n_levels} n_features={self.n_features} "
@@ -208,8 +213,12 @@ class GridEncoder(nn.Module):
     def _encode(self, inputs, outspace_params, min_level_id, n_levels_calc, test_phase, binary_vxl, PV):
         params = self.params if outspace_params is None else outspace_params
         if self.ste_binary:
-            cache = self._sign_cache if outspace_params is None else self._sign_cache_out
-            bits = cache.get(params)
+            if outspace_params is None:
+                bits = self._sign_cache.get(params)
+            else:
+                # a caller-provided table (decode: the partially reconstructed one; a fresh STE output per call): address and
+                # version do not identify it -- the allocator hands the same block to the next temporary -- so no caching
+                bits = _backend.sign_pack(params.detach().contiguous(), None)
             return _grid_encode_ste.apply(inputs, params, bits, self.offsets_list, self.resolutions_list,
                                           min_level_id, n_levels_calc, binary_vxl)
         if self.add_noise and not test_phase:

@@ -1,41 +1,85 @@
 """One training iteration of the CNC scripts as a reusable object (train_CNC_nerf_synthetic.py:302-366):
 occupancy refresh -> occupancy/visibility sampling -> differentiable render -> photometric loss (+ lambda * rate)
--> backward -> [data parallel: bucketed gradient all-reduce] -> Adam.  It is the caller of the hot path, kept small:
-no datasets, schedulers or logging."""
+-> backward -> [data parallel: gradient exchange] -> Adam.  It is the caller of the hot path, kept small: no datasets,
+schedulers or logging (`lr` is an attribute: a scheduler sets it between steps).
+
+Optimiser layout (train_CNC_nerf_synthetic.py:254-266): Adam(lr, eps=1e-15, weight_decay) over the field, Adam(lr,
+eps=1e-15) over the context models.  Here the four latent tables (99.7 % of the parameters) go through
+`dp.ShardedTableAdam` -- one fused pass that also refreshes the 1-bit planes the next forward reads; under data parallelism
+a reduce-scatter in, two bit planes out -- and everything else (MLPs, context models, < 1 MB) through a bucketed
+all-reduce and torch's fused Adam.
+
+Data parallelism: every rank renders its own ray shard.  The decision to skip a step (the reference `continue`s when a
+batch produced no sample, :337-338) is taken by all ranks together, and the occupancy grid is refreshed on rank 0's random
+numbers only (broadcast), so replicas never diverge.
+"""
 from __future__ import annotations
 
 from typing import Optional
 
 import torch
+import torch.distributed as dist
 import torch.nn.functional as F
 
-from .dp import GradAllReducer, allreduce_scalar
+from .dp import GradAllReducer, ShardedTableAdam, allreduce_scalar, broadcast_module_buffers
 from .render import Rays, render_image_with_occgrid
 
 
 class TrainStep:
     def __init__(self, radiance_field, estimator, context_model=None, lmbda: float = 0.0, lr: float = 6e-3,
-                 render_step_size: float = 5e-3, target_sample_batch_size: int = 1 << 18, bucket_bytes: int = 32 << 20):
+                 render_step_size: float = 5e-3, target_sample_batch_size: int = 1 << 18, bucket_bytes: int = 32 << 20,
+                 weight_decay: float = 2e-6, occ_refresh_every: int = 16):
         self.field, self.estimator, self.cm, self.lmbda = radiance_field, estimator, context_model, lmbda
-        self.render_step_size, self.target = render_step_size, target_sample_batch_size
-        params = list(radiance_field.parameters()) + (list(context_model.parameters()) if context_model is not None else [])
-        self.optimizer = torch.optim.Adam(params, lr=lr, eps=1e-15, fused=params[0].is_cuda)   # train...:254-266; one fused pass over the 40 M latents
-        self.reducer = GradAllReducer(params, bucket_bytes=bucket_bytes)
+        self.render_step_size, self.target, self.occ_every = render_step_size, target_sample_batch_size, occ_refresh_every
+        self.lr = lr
+        mb = radiance_field.mlp_base
+        encs = [mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz]
+        self.sharded = all(e.params.numel() % 32 == 0 and e.ste_binary for e in encs)
+        table_ids = {id(e.params) for e in encs} if self.sharded else set()
+        field_rest = [p for p in radiance_field.parameters() if id(p) not in table_ids and p.requires_grad]
+        ctx = [p for p in context_model.parameters() if p.requires_grad] if context_model is not None else []
+        self.table_opt = ShardedTableAdam(encs, lr=lr, eps=1e-15, weight_decay=weight_decay) if self.sharded else None
+        groups = [{"params": field_rest, "weight_decay": weight_decay}]
+        if ctx:
+            groups.append({"params": ctx, "weight_decay": 0.0})
+        self.optimizer = torch.optim.Adam(groups, lr=lr, eps=1e-15, fused=field_rest[0].is_cuda)
+        self.reducer = GradAllReducer(field_rest + ctx, bucket_bytes=bucket_bytes)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.step_id = 0
+
+    # ---- what the exchange moves (for the bench line / DESIGN.md)
+    def comm_bytes_per_step(self) -> int:
+        return (self.table_opt.comm_bytes_per_step() if self.table_opt is not None else 0) + \
+            (self.reducer.bytes_per_step() if self.world > 1 else 0)
+
+    def comm_description(self) -> str:
+        if self.world == 1:
+            return "single process: no exchange"
+        if self.table_opt is None:
+            return "bucketed all-reduce of every gradient"
+        return ("latent tables: reduce-scatter(avg) of the gradient by rows, Adam on the owned 1/N, all-gather of the sign and "
+                "STE-window bit planes; MLP / context-model gradients: one bucketed all-reduce; sample count: 8-byte all-reduce")
+
+    def _everyone_has_samples(self, n_samples: int, device) -> bool:
+        if self.world == 1:
+            return n_samples > 0
+        return allreduce_scalar(float(n_samples), device, op=dist.ReduceOp.MIN) > 0
 
     def __call__(self, rays: Rays, pixels: torch.Tensor, render_bkgd: Optional[torch.Tensor] = None, refresh_occupancy: bool = True):
         """returns (loss value tensor, number of rendered samples on this rank)"""
         self.field.train()
         self.estimator.train()
         if refresh_occupancy:   # train...:314-321
-            self.estimator.update_every_n_steps(step=self.step_id, occ_thre=1e-2,
+            self.estimator.update_every_n_steps(step=self.step_id, occ_thre=1e-2, n=self.occ_every,
                                                 occ_eval_fn=lambda x: self.field.query_density(x) * self.render_step_size)
+            if self.world > 1 and self.step_id % self.occ_every == 0:
+                # each rank drew its own random cell samples: rank 0's grid is everybody's grid
+                broadcast_module_buffers(self.estimator, ["occs", "binaries"], src=0)
         rgb, acc, depth, n_samples = render_image_with_occgrid(self.field, self.estimator, rays, render_step_size=self.render_step_size,
                                                                render_bkgd=render_bkgd)
-        if n_samples == 0:      # train...:337-338
+        if not self._everyone_has_samples(n_samples, pixels.device):   # train...:337-338, decided by all ranks together
             self.step_id += 1
-            self.reducer.reduce()
-            return torch.zeros((), device=pixels.device), 0
+            return torch.zeros((), device=pixels.device), n_samples
         loss = F.mse_loss(rgb, pixels)   # train...:346
         if self.cm is not None and self.lmbda > 0:
             mb = self.field.mlp_base
@@ -43,8 +87,16 @@ class TrainStep:
                                                            self.estimator.binaries, step=self.step_id)
             loss = loss + self.lmbda * bpp
         self.optimizer.zero_grad(set_to_none=True)
+        if self.table_opt is not None:
+            for t in self.table_opt.tables:
+                t["p"].grad = None
         loss.backward()
-        self.reducer.reduce()            # the one exchange of the data-parallel step
+        for g in self.optimizer.param_groups:
+            g["lr"] = self.lr
+        if self.table_opt is not None:
+            self.table_opt.lr = self.lr
+            self.table_opt.step()        # tables: reduce-scatter -> Adam on the owned rows -> bit planes all-gather
+        self.reducer.reduce()            # MLPs + context models: one small bucketed all-reduce
         self.optimizer.step()
         self.step_id += 1
         return loss.detach(), n_samples
@@ -52,5 +104,10 @@ class TrainStep:
     def adapt_num_rays(self, num_rays: int, n_samples_local: int, device) -> int:
         """train...:340-344 with the global sample count (all ranks take the same decision)"""
         total = allreduce_scalar(float(n_samples_local), device)
-        world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
-        return int(num_rays * (self.target * world / max(total, 1.0)))
+        return int(num_rays * (self.target * self.world / max(total, 1.0)))
+
+    def sync_params(self) -> None:
+        """true fp32 latents on every rank (a data-parallel rank otherwise keeps stand-ins with the right sign and STE
+        window for the rows it does not own)"""
+        if self.table_opt is not None:
+            self.table_opt.sync_params()

@@ -87,6 +87,25 @@ int cnc_sign_pack(const float *params, uint8_t *bits, uint64_t n, cnc_stream_t s
 int cnc_sign_unpack(const uint8_t *bits, float *out, uint64_t n, cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training step over the latent tables (caller side: the optimizer step of train_CNC_nerf_synthetic.py:254-266,
+ * :362-364 and, under data parallelism, the exchange SURVEY 8(e) adds; the reference has neither kernel).
+ * A replica needs from a table row only sign(p) (STE forward, ngp.py:26-31) and [|p| <= 1] (STE backward, ngp.py:33-39):
+ *   cnc_ste_planes_pack : params [n] -> sign plane (cnc_sign_pack layout) and window plane (bit = -1 <= p <= 1), n % 32 == 0;
+ *                         mask_bits may be NULL.
+ *   cnc_surrogate_fill  : params[i] = +-0.5 (window bit set) / +-1.5 (clear), sign from the sign plane, for every i
+ *                         outside [keep_lo, keep_hi); n, keep_lo, keep_hi multiples of 32.
+ *   cnc_adam_planes     : torch.optim.Adam (L2 weight decay, fp32 state, bias correction with `step` >= 1) over
+ *                         params/grad/exp_avg/exp_avg_sq [n], emitting the two planes of the updated values in the same
+ *                         pass (sign_bits / mask_bits nullable); grad is divided by grad_scale first (GradScaler, :211,362).
+ * ---------------------------------------------------------------------------------------- */
+int cnc_ste_planes_pack(const float *params, uint8_t *sign_bits, uint8_t *mask_bits, uint64_t n, cnc_stream_t stream);
+int cnc_surrogate_fill(float *params, const uint8_t *sign_bits, const uint8_t *mask_bits, uint64_t n, uint64_t keep_lo,
+                       uint64_t keep_hi, cnc_stream_t stream);
+int cnc_adam_planes(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, uint8_t *sign_bits, uint8_t *mask_bits,
+                    uint64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                    cnc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Dimension-wise context: 3D -> 2D vote planes.
  * replaces: _gridencoder.cnt_np_embed / cnt_np_embed_backward   gridencoder.h:39-53,
  *           gridencoder.cu:873-915, :972-1020

@@ -21,7 +21,7 @@ is not run.
 
 The reference's hot-path *Python* (ngp.py, utils_bpp_acc.py, utils.py, the vendored nerfacc package)
 is built the same way: `build_py()` byte-compiles every file of PY_MODULES from where it lies into
-`oracle/_ref/py/<module path>.pyc` (CPython 3.12 bytecode -- a binary like the `.so` files, git-ignored,
+`oracle/_ref/py/<module path>.pyc.bin` (CPython 3.12 bytecode -- a binary like the `.so` files, git-ignored,
 no source text in the repo).  `oracle/ref_py.py` imports those `.pyc` files on the GPU box with the
 third-party modules the reference needs (torchac, tinycudann) shimmed by the oracle, so the UNMODIFIED
 reference classes (CNC_context_models, NGPRadianceField_mygrid_2D3D, OccGridEstimator, rendering, ...)
@@ -89,7 +89,7 @@ PY_OUT = os.path.join(OUT, "py")
 
 
 def pyc_path(module: str) -> str:
-    return os.path.join(PY_OUT, module + ".pyc")
+    return os.path.join(PY_OUT, module + ".pyc.bin")
 
 
 def build_py(force: bool = False) -> None:

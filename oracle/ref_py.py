@@ -3,7 +3,7 @@
 TEST INFRASTRUCTURE ONLY: used by tests/ and by `bench.py --impl reference`; never imported by `cnc_b200/`.
 
 `oracle/build_ref.py:build_py()` byte-compiles the reference's hot-path modules from where they lie under
-/root/reference into `oracle/_ref/py/*.pyc` (binary build outputs, git-ignored, shipped to the GPU box next to the
+/root/reference into `oracle/_ref/py/*.pyc.bin` (binary build outputs, git-ignored, shipped to the GPU box next to the
 reference `.so` files).  `load()` installs an import hook that resolves exactly the module names the reference's own
 `import` statements use:
 
@@ -39,13 +39,13 @@ _installed = False
 
 def available() -> bool:
     need = ("utils", "utils_bpp_acc", "radiance_fields.ngp", "nerfacc", "nerfacc.estimators.occ_grid")
-    return all(os.path.exists(os.path.join(PY_DIR, m + ".pyc")) for m in need) and all(
+    return all(os.path.exists(os.path.join(PY_DIR, m + ".pyc.bin")) for m in need) and all(
         os.path.exists(ref_ext.path(n)) for n in ("_gridencoder", "pack_and_align", "nerfacc_csrc"))
 
 
 class _Finder(importlib.abc.MetaPathFinder):
     def find_spec(self, name, path=None, target=None):
-        pyc = os.path.join(PY_DIR, name + ".pyc")
+        pyc = os.path.join(PY_DIR, name + ".pyc.bin")
         is_pkg = name in _PACKAGES
         if os.path.exists(pyc):
             loader = importlib.machinery.SourcelessFileLoader(name, pyc)

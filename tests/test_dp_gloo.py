@@ -96,3 +96,120 @@ def test_shard_range_partitions():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+class _Enc(torch.nn.Module):
+    """the two attributes ShardedTableAdam reads from a GridEncoder"""
+
+    def __init__(self, rows, F=8):
+        super().__init__()
+        self.params = torch.nn.Parameter(torch.empty(rows, F))
+        self.ste_binary = True
+
+
+def _sharded_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cnc_b200.dp import ShardedTableAdam
+    from cnc_b200.trainer import TrainStep
+
+    g = torch.Generator().manual_seed(5)
+    encs = [_Enc(1000), _Enc(136)]                      # 8000 and 1088 latents: cut at 64-element multiples, tails of 0 / 0 .. 63
+    with torch.no_grad():
+        for e in encs:
+            e.params.copy_(torch.randn(e.params.shape, generator=g) * 0.9)     # some outside the STE window |p| <= 1
+    opt = ShardedTableAdam(encs, lr=0.05, eps=1e-15, weight_decay=1e-3)
+    grads = []
+    for step in range(3):
+        gs = [torch.randn(e.params.shape, generator=torch.Generator().manual_seed(100 * step + 10 * k + rank)) for k, e in enumerate(encs)]
+        for e, gg in zip(encs, gs):
+            e.params.grad = gg.clone()
+        opt.step()
+        grads.append(gs)
+    before_sync = [e.params.detach().clone() for e in encs]
+    spans = [(t["lo"], t["hi"], t["n_main"]) for t in opt.tables]
+    planes = [(t["sign"].clone(), t["mask"].clone()) for t in opt.tables]
+    opt.sync_params()
+    # the skip decision of TrainStep: one empty rank -> nobody steps
+    ts = TrainStep.__new__(TrainStep)
+    ts.world = world
+    votes = (ts._everyone_has_samples(0 if rank == 1 else 7, "cpu"), ts._everyone_has_samples(3 + rank, "cpu"))
+    q.put((rank, before_sync, [e.params.detach().clone() for e in encs], spans, planes, votes, opt.comm_bytes_per_step()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_table_adam_world2():
+    """reduce-scatter + Adam on the owned rows + bit-plane all-gather == plain Adam on the rank-averaged gradient: the
+    owned rows hold the true latents, the others a stand-in with the same sign and STE window; sync_params restores all"""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process reference
+    g = torch.Generator().manual_seed(5)
+    ref = [torch.nn.Parameter(torch.randn(1000, 8, generator=g) * 0.9), torch.nn.Parameter(torch.randn(136, 8, generator=g) * 0.9)]
+    opt = torch.optim.Adam(ref, lr=0.05, eps=1e-15, weight_decay=1e-3)
+    for step in range(3):
+        for k, p in enumerate(ref):
+            gs = [torch.randn(p.shape, generator=torch.Generator().manual_seed(100 * step + 10 * k + r)) for r in range(world)]
+            p.grad = sum(gs) / world
+        opt.step()
+    from cnc_b200.train_ops import planes_pack
+
+    for rank, before, after, spans, planes, votes, comm in out:
+        for k, p in enumerate(ref):
+            lo, hi, n_main = spans[k]
+            assert lo % 32 == 0 and hi % 32 == 0 and (hi - lo) * world == n_main and p.numel() - n_main < 32 * world
+            want = p.detach().view(-1)
+            got = before[k].view(-1)
+            torch.testing.assert_close(got[lo:hi], want[lo:hi], rtol=1e-5, atol=1e-6)          # owned rows: the true latents
+            torch.testing.assert_close(got[n_main:], want[n_main:], rtol=1e-5, atol=1e-6)      # replicated tail
+            other = torch.ones_like(want, dtype=torch.bool)
+            other[lo:hi] = False
+            other[n_main:] = False
+            assert other.any()
+            assert torch.equal(got[other] >= 0, want[other] >= 0)                              # stand-ins: same sign ...
+            assert torch.equal(got[other].abs() <= 1, want[other].abs() <= 1)                  # ... same STE window
+            assert set(got[other].abs().unique().tolist()) <= {0.5, 1.5}
+            s, m = planes_pack(want.contiguous())
+            assert torch.equal(planes[k][0], s) and torch.equal(planes[k][1], m)               # planes of the whole table
+            torch.testing.assert_close(after[k].view(-1), want, rtol=1e-5, atol=1e-6)          # after sync_params: everything
+        assert votes == (False, True)
+        assert comm == sum(4 * p.numel() + 2 * (spans[k][1] - spans[k][0]) // 8 for k, p in enumerate(ref))
+    assert torch.equal(out[0][2][0], out[1][2][0])
+
+
+def test_train_ops_cpu_reference_paths():
+    """planes / stand-ins / Adam of cnc_b200.train_ops on CPU tensors (the arithmetic the gloo tests run on)"""
+    from cnc_b200.train_ops import adam_planes, planes_pack, surrogate_fill
+
+    g = torch.Generator().manual_seed(0)
+    p = torch.randn(256, generator=g) * 1.2
+    p[:4] = torch.tensor([0.0, -0.0, 1.0, -1.0])
+    s, m = planes_pack(p.clone())
+    bits = lambda b: ((b.view(-1, 1).to(torch.int32) >> torch.arange(8, dtype=torch.int32)) & 1).bool().view(-1)
+    assert torch.equal(bits(s), p >= 0) and torch.equal(bits(m), p.abs() <= 1)
+    q = p.clone()
+    surrogate_fill(q, s, m, 64, 128)
+    assert torch.equal(q[64:128], p[64:128])
+    rest = torch.cat([q[:64], q[128:]])
+    ref = torch.cat([p[:64], p[128:]])
+    assert torch.equal(rest >= 0, ref >= 0) and torch.equal(rest.abs() <= 1, ref.abs() <= 1)
+    a = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([a], lr=0.01, eps=1e-15, weight_decay=2e-6)
+    b, m1, v2 = p.clone(), torch.zeros(256), torch.zeros(256)
+    for step in range(1, 4):
+        gr = torch.randn(256, generator=g)
+        a.grad = gr.clone()
+        opt.step()
+        adam_planes(b, gr * 1024.0, m1, v2, step=step, lr=0.01, eps=1e-15, weight_decay=2e-6, grad_scale=1024.0, sign=s, mask=m)
+    torch.testing.assert_close(b, a.detach(), rtol=1e-5, atol=1e-7)
+    assert torch.equal(bits(s), b >= 0)

@@ -172,8 +172,9 @@ def test_container_roundtrip_feeds_the_decoder(cuda):
     from cnc_b200.context_models import CNC_context_models
     from cnc_b200.gridencoder import GridEncoder
 
-    cm, encs, vxl = make(cuda, **SMALL, skip3=(0,))             # level 1 is dense AND context-coded: shuffled symbol order
-    assert cm.res[1] <= cm.resolution_thresh
+    # level 3 is dense AND context-coded: its symbol order is the random permutation
+    cm, encs, vxl = make(cuda, res3=[6, 8, 10, 12, 18, 34], log2T=12, res2=[18, 34, 66], log2T2=10, Rb=16)
+    assert cm.res[3] <= cm.resolution_thresh and 3 not in cm.skip_levels_3D
     qs = C.quantize_state(cm.state_dict(), digits=13)
     cm.load_state_dict(C.dequantize_state(qs, device=cuda))      # the encoder runs with the weights the decoder will have
     Pgs, _, coded_MB, streams = cm.encode_binary_vxl_mixPg_3D2D(*encs, vxl, "c", return_streams=True)
@@ -202,7 +203,7 @@ def test_container_roundtrip_feeds_the_decoder(cuda):
     for n in skip:
         assert torch.equal(q[0][offs[n]:offs[n + 1]], out[0][offs[n]:offs[n + 1]])
     # the dense context-coded level: a wrong permutation would scatter its symbols to the wrong rows
-    n = 1
+    n = 3
     lvl_q, lvl_o = q[0][offs[n]:offs[n + 1]], out[0][offs[n]:offs[n + 1]]
     coded = ~(lvl_q != lvl_o).any(-1)
     assert float(coded.float().mean()) > 0.3 and float((lvl_q[coded] == -1).float().mean()) > 0.2

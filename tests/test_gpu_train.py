@@ -1,0 +1,120 @@
+"""GPU suite: the training-step driver (cnc_b200.trainer.TrainStep) and the table passes under it
+(csrc/train_ops.cu through cnc_b200.train_ops).
+
+  * planes / stand-in latents / fused Adam kernels against the torch arithmetic of the same module (bit planes exact,
+    Adam to fp32 rounding against torch.optim.Adam), at the product table size and at sizes that are not multiples of
+    the kernels' 1024-element chunks;
+  * TrainStep on the product field: the photometric loss of a fixed ray batch falls over 50 steps, the sign planes the
+    next forward reads are the signs of the updated latents, and lambda > 0 (rate term) steps run and stay finite.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import R2, R3
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [32, 992, 1024, 4003896 * 8, 345616 * 8 // 2 + 32])
+def test_table_passes_vs_torch(cuda, n):
+    from cnc_b200.train_ops import adam_planes, planes_pack, surrogate_fill
+
+    g = torch.Generator().manual_seed(n % 1000)
+    small = n <= 1 << 20
+    p = (torch.randn(n, generator=g) * 0.9) if small else (torch.randn(n, device=cuda) * 0.9).cpu()
+    p[:4] = torch.tensor([0.0, -0.0, 1.0, -1.0])
+    pc = p.to(cuda)
+    s_c, m_c = planes_pack(pc)
+    s_h, m_h = planes_pack(p.clone())
+    assert torch.equal(s_c.cpu(), s_h) and torch.equal(m_c.cpu(), m_h)
+    lo, hi = (n // 3) // 32 * 32, (2 * n // 3) // 32 * 32
+    q_c, q_h = pc.clone(), p.clone()
+    surrogate_fill(q_c, s_c, m_c, lo, hi)
+    surrogate_fill(q_h, s_h, m_h, lo, hi)
+    assert torch.equal(q_c.cpu(), q_h)
+    assert torch.equal(q_c[lo:hi], pc[lo:hi])
+    # Adam: three steps against torch.optim.Adam (fused) on the same gradients, with a loss scale to divide out
+    a = torch.nn.Parameter(pc.clone())
+    opt = torch.optim.Adam([a], lr=6e-3, eps=1e-15, weight_decay=2e-6, fused=True)
+    b, m1, v2 = pc.clone(), torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    sign, mask = torch.empty(n // 8, dtype=torch.uint8, device=cuda), torch.empty(n // 8, dtype=torch.uint8, device=cuda)
+    for step in range(1, 4):
+        gr = torch.randn(n, device=cuda) * (10.0 ** float(np.random.default_rng(step).integers(-6, 1)))
+        gr[::7] = 0                                               # untouched table rows: zero gradient
+        a.grad = gr.clone()
+        opt.step()
+        adam_planes(b, gr * 1024.0, m1, v2, step=step, lr=6e-3, eps=1e-15, weight_decay=2e-6, grad_scale=1024.0, sign=sign, mask=mask)
+        torch.testing.assert_close(b, a.detach(), rtol=2e-5, atol=1e-7)
+    s2, m2 = planes_pack(b)
+    assert torch.equal(sign, s2) and torch.equal(mask, m2)       # the planes the kernel emitted are those of what it wrote
+
+
+def _scene(dev, n_rays=600, seed=0):
+    from cnc_b200.field import NGPRadianceField_mygrid_2D3D
+    from cnc_b200.nerfacc import OccGridEstimator
+    from cnc_b200.render import Rays
+
+    torch.manual_seed(seed)
+    field = NGPRadianceField_mygrid_2D3D(aabb=[-1.5] * 3 + [1.5] * 3, n_features_per_level=8, n_neurons=160, resolutions_list=R3,
+                                         log2_hashmap_size=19, resolutions_list_2D=R2, log2_hashmap_size_2D=17, ste_binary=True).to(dev)
+    est = OccGridEstimator(roi_aabb=[-1.5] * 3 + [1.5] * 3, resolution=128, levels=1).to(dev)
+    c = (torch.arange(128, device=dev) + 0.5) / 128 * 3 - 1.5
+    X, Y, Z = torch.meshgrid(c, c, c, indexing="ij")
+    est.binaries = (X * X + Y * Y + Z * Z <= 0.6 ** 2).unsqueeze(0)
+    est.occs = est.binaries.reshape(-1).float()
+    g = torch.Generator().manual_seed(seed + 1)
+    o = torch.randn(n_rays, 3, generator=g)
+    o = o / o.norm(dim=-1, keepdim=True) * 4
+    d = (torch.rand(n_rays, 3, generator=g) - 0.5) * 0.8 - o
+    d = d / d.norm(dim=-1, keepdim=True)
+    pixels = torch.rand(n_rays, 3, generator=g) * 0.5
+    return field, est, Rays(o.to(dev), d.to(dev)), pixels.to(dev)
+
+
+def test_train_step_loss_falls_and_planes_follow(cuda):
+    from cnc_b200 import _gridencoder as G
+    from cnc_b200.trainer import TrainStep
+
+    field, est, rays, pixels = _scene(cuda)
+    ts = TrainStep(field, est, lr=6e-3)
+    assert ts.sharded and ts.comm_bytes_per_step() == 0
+    bk = torch.zeros(3, device=cuda)
+    losses = []
+    p0 = field.mlp_base.encoding_xyz.params.detach().clone()
+    for _ in range(50):
+        loss, n = ts(rays, pixels, render_bkgd=bk, refresh_occupancy=False)
+        assert n > 0
+        losses.append(float(loss))
+    assert all(np.isfinite(losses))
+    assert np.mean(losses[-5:]) < 0.5 * np.mean(losses[:5]), (losses[:5], losses[-5:])
+    mb = field.mlp_base
+    for enc in (mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz):
+        cached = enc._sign_cache.get(enc.params)              # what the next forward will gather from
+        assert torch.equal(cached, G.sign_pack(enc.params.detach().contiguous()))
+    moved = (mb.encoding_xyz.params.detach() != p0).any(-1).float().mean()
+    assert 0.001 < float(moved) <= 1.0                         # rows the rays touched (plus weight decay on all rows)
+    # inference through the fused kernel sees the trained tables (same planes) -> the rendered colours match the loss
+    field.eval()
+    with torch.no_grad():
+        from cnc_b200.render import render_image_with_occgrid
+
+        rgb, _, _, _ = render_image_with_occgrid(field, est, rays, render_step_size=5e-3, render_bkgd=bk)
+    assert float(torch.nn.functional.mse_loss(rgb, pixels)) < 1.5 * np.mean(losses[-5:]) + 1e-3
+
+
+def test_train_step_with_rate_term(cuda):
+    from cnc_b200.context_models import CNC_context_models
+    from cnc_b200.trainer import TrainStep
+
+    field, est, rays, pixels = _scene(cuda, seed=3)
+    cm = CNC_context_models(num_dim=3, resolutions_list=R3, resolutions_list_2D=R2, log2_hashmap_size=19, log2_hashmap_size_2D=17,
+                            n_features=8, sample_num=20000, max_context_layer_num=3, ste_binary=True, Rb=128,
+                            skip_levels_3D=(0, 1, 2), skip_levels_2D=(0,), device=cuda)
+    ts = TrainStep(field, est, context_model=cm, lmbda=1e-3, lr=1e-3)
+    w0 = cm.context_model_3D[0].weight.detach().clone()
+    for _ in range(3):
+        loss, n = ts(rays, pixels, refresh_occupancy=False)
+        assert torch.isfinite(loss) and n > 0
+    assert not torch.equal(cm.context_model_3D[0].weight.detach(), w0)      # the context model trains with the field
+    assert all(torch.isfinite(p).all() for p in field.parameters())

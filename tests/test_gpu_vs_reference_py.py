@@ -96,11 +96,31 @@ def test_fused_field_forward_vs_reference_field(cuda, ref, scale):
 
 def test_field_gradients_vs_reference_autograd(cuda, ref):
     """the fused training path (cnc_field_fwd_train + cnc_dgrad + cnc_wgrad + K2 + STE mask) against torch autograd over
-    the reference field on the reference kernels: every parameter's gradient"""
+    the reference field on the reference kernels: every parameter's gradient to 1e-4 of its maximum.
+
+    The gradient of a ReLU network is discontinuous where a hidden pre-activation crosses zero: two correct fp32
+    implementations round h differently and take different sides of max(h, 0) on a few of the 3.1e7 pre-activations of a
+    batch -- the forward outputs do not notice (h ~ 0 either way), the gradient of that sample jumps.  Samples with a
+    pre-activation within 1e-4 of a kink (measured on the REFERENCE's forward) therefore get zero loss weight; everything
+    else must agree."""
     ours, theirs = _fields(ref, cuda)
-    pos, dirs = _samples(cuda, 65536, seed=2)
+    n = 65536
+    pos, dirs = _samples(cuda, n, seed=2)
     g = torch.Generator().manual_seed(3)
-    w_rgb, w_sig = torch.randn(65536, 3, generator=g).to(cuda), torch.randn(65536, 1, generator=g).to(cuda)
+    w_rgb, w_sig = torch.randn(n, 3, generator=g).to(cuda), torch.randn(n, 1, generator=g).to(cuda)
+    pre, hooks = [], []
+    for lin in (theirs.mlp_base.network[0], theirs.mlp_head[0], theirs.mlp_head[2]):
+        hooks.append(lin.register_forward_hook(lambda m, i, out: pre.append(out.detach().clone())))   # (ReLU is in place)
+    with torch.no_grad():
+        theirs(pos, dirs)
+    for h in hooks:
+        h.remove()
+    near_kink = torch.zeros(n, dtype=torch.bool, device=cuda)
+    for h in pre:
+        near_kink |= (h.abs() < 1e-4 * h.abs().max()).any(-1)
+    keep = (~near_kink).float().unsqueeze(-1)
+    assert 0.5 < float(keep.mean()) < 1.0, float(keep.mean())
+    w_rgb, w_sig = w_rgb * keep, w_sig * keep
     ours.train()
     theirs.train()
     rgb_r, sig_r = theirs(pos, dirs)
@@ -109,12 +129,17 @@ def test_field_gradients_vs_reference_autograd(cuda, ref):
     assert rgb_o.grad_fn is not None and "FusedFieldTrain" in type(rgb_o.grad_fn).__name__
     ((rgb_o * w_rgb).sum() + (sig_o * w_sig).sum()).backward()
     gr = dict(theirs.named_parameters())
+    stats = {}
     for name, p in ours.named_parameters():
         a, b = p.grad, gr[name].grad
         assert a is not None and b is not None, name
         if "params" in name:   # tables: the same rows touched, the same STE mask (a sum may cancel to exactly 0 on one side only)
             assert float(((a == 0) != (b == 0)).float().mean()) < 1e-6, name
-        assert rel(a, b) <= 1e-4, (name, rel(a, b))
+        stats[name] = rel(a, b)
+        assert float(b.abs().max()) > 0
+    print(f"{float(keep.mean()) * 100:.1f} % of the samples away from a ReLU kink; gradient deviation vs reference autograd, "
+          f"relative to each parameter's maximum: " + ", ".join(f"{k} {v:.1e}" for k, v in stats.items()))
+    assert max(stats.values()) <= 1e-4, stats
 
 
 # ================================================================================================ codec
@@ -404,7 +429,8 @@ def test_marching_vs_reference_nerfacc(cuda, ref, levels, step, cone):
     assert torch.equal(sm_r.vals, sm_o.vals)
     assert torch.equal(iv_r.vals[iv_r.is_left], iv_o.vals[iv_o.is_left])
     assert torch.equal(iv_r.vals[iv_r.is_right], iv_o.vals[iv_o.is_right])
-    assert torch.equal(term_r, term_o)
+    got = sm_o.packed_info[:, 1] > 0     # (the reference's second pass skips empty rays: their plane is uninitialised memory, grid.cu:102-105)
+    assert torch.equal(term_r[got], term_o[got])
     assert int(sm_o.packed_info[:, 1].sum()) > 10 * o.shape[0]
     # the test renderer's call (examples/utils.py:402-428)
     tm, tx, hits = RN.grid.ray_aabb_intersect(o, d, aabbs)
@@ -459,6 +485,9 @@ def test_scans_and_weights_vs_reference_nerfacc(cuda, ref):
         torch.testing.assert_close(T_o, T_r, rtol=1e-5, atol=1e-7)
         torch.testing.assert_close(a_o, a_r, rtol=1e-5, atol=1e-7)
     gw = torch.randn(ri.numel(), generator=g).to(cuda)
+    # (without a prefix: with one the reference multiplies the saved transmittance in place and its own backward raises)
+    w_o, _, _ = N.render_weight_from_density(t0, t1, sig_o, ray_indices=ri, n_rays=o.shape[0])
+    w_r, _, _ = RN.volrend.render_weight_from_density(t0, t1, sig_r, ray_indices=ri, n_rays=o.shape[0])
     (w_o * gw).sum().backward()
     (w_r * gw).sum().backward()
     assert rel(sig_o.grad, sig_r.grad) <= 1e-5
@@ -495,8 +524,19 @@ def test_occupancy_estimator_update_and_sampling_vs_reference(cuda, ref):
         est_r.update_every_n_steps(step=step, occ_eval_fn=fn, occ_thre=1e-2)
         torch.manual_seed(40 + step)
         est_o.update_every_n_steps(step=step, occ_eval_fn=fn, occ_thre=1e-2)
-        assert torch.equal(est_o.occs, est_r.occs), step
-        assert torch.equal(est_o.binaries, est_r.binaries), step
+        if step < 256:   # warm-up: every cell once -> deterministic
+            assert torch.equal(est_o.occs, est_r.occs), step
+            assert torch.equal(est_o.binaries, est_r.binaries), step
+        else:
+            # sampled refresh: `occs[ids] = maximum(occs[ids] * decay, occ)` with repeated ids (randint draws with
+            # replacement, occupied cells are appended) -- which duplicate's value lands is unspecified in torch, i.e. the
+            # reference is not reproducible against itself here.  Same draws, so: cells without a duplicate are identical.
+            same = est_o.occs == est_r.occs
+            assert float(same.float().mean()) > 0.75, float(same.float().mean())
+            torch.testing.assert_close(est_o.occs, est_r.occs, rtol=0.5, atol=2e-3)
+            assert float((est_o.binaries != est_r.binaries).float().mean()) < 2e-3
+            est_o.occs.copy_(est_r.occs)
+            est_o.binaries = est_r.binaries.clone()
     assert 0.001 < float(est_o.binaries.float().mean()) < 0.5
     o, d = (t.to(cuda) for t in _rays(4096, seed=7))
     sigma_fn = lambda t0, t1, ri: field.query_density(o[ri] + d[ri] * (t0 + t1)[:, None] / 2.0).squeeze(-1)
