@@ -197,10 +197,10 @@ class Arm:
                 p.copy_(torch.where(torch.rand(p.shape, generator=g) < 0.5, -0.5, 0.5).to(self.dev))
         return f
 
-    def context_model(self):
+    def context_model(self, **kw):
         cm = self.CM(num_dim=3, resolutions_list=R3, resolutions_list_2D=R2, log2_hashmap_size=19, log2_hashmap_size_2D=17,
                      n_features=F, sample_num=150000, max_context_layer_num=3, ste_binary=True, skip_levels_3D=(0, 1, 2),
-                     skip_levels_2D=(0,), **self.cm_kw)
+                     skip_levels_2D=(0,), **self.cm_kw, **kw)
         return cm.to(self.dev)
 
     def estimator(self):
@@ -394,7 +394,37 @@ def codec_bench(arm, cpu_seconds=12.0, rank=0, world=1, dist=None):
         return res
     from oracle import oracle as o
 
-    res.update({"symbols": n_sym, "encode_Msym_per_s": world * n_sym / enc / 1e6, "decode_Msym_per_s": world * n_sym / dec / 1e6})
+    res.update({"symbols": n_sym, "encode_Msym_per_s": world * n_sym / enc / 1e6, "decode_Msym_per_s": world * n_sym / dec / 1e6,
+                "table_state_MB": cm.table_bytes() / 1e6})
+    # the same codec from occupancy-pruned tables (histogram pass at construction, vertex lists per occupancy grid)
+    if world == 1:
+        state = cm.state_dict()
+        del cm
+        torch.cuda.empty_cache()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        torch.manual_seed(rank)
+        cm = arm.context_model(tables="pruned")
+        torch.cuda.synchronize()
+        t_setup_p = time.perf_counter() - t
+        cm.load_state_dict(state)
+        t = time.perf_counter()
+        Pgs, _, coded_p, streams = encode()          # first call: builds the pruned vertex lists of the nine coded levels
+        torch.cuda.synchronize()
+        t_first = time.perf_counter() - t
+        es, ds = [], []
+        for _ in range(2):
+            sync(); t = time.perf_counter()
+            Pgs, _, coded_p, streams = encode()      # (encode() drops the per-call cache: the lists are rebuilt every time)
+            sync(); es.append(time.perf_counter() - t)
+            sync(); t = time.perf_counter()
+            out = decode(Pgs, streams)
+            sync(); ds.append(time.perf_counter() - t)
+        okp = all(bool(((torch.where(e.params >= 0, 1.0, -1.0) == r) | (r == 1)).all()) for e, r in zip(encs, out))
+        res["pruned_tables"] = {"what": "tables='pruned': row statistics from one histogram pass per level at construction; vertex lists "
+                                        "built per occupancy grid for the vertices that pass the occupancy test (csrc/table_build.cu)",
+                                "setup_s": t_setup_p, "first_encode_s": t_first, "encode_s": min(es), "decode_s": min(ds),
+                                "table_state_MB": cm.table_bytes() / 1e6, "coded_MiB": coded_p, "roundtrip_ok": okp}
     # dominant kernel of the encode: cnc_context3d_probs (one launch per coded chunk), timed live with CUDA events
     if ctx_ms:
         hbm_peak, which = peaks()

@@ -27,6 +27,9 @@ SIGNATURES = {
     "cnc_ste_binary_bwd": [_vp, _vp, _vp, _u64, _vp],
     "cnc_sign_pack": [_vp, _vp, _u64, _vp],
     "cnc_sign_unpack": [_vp, _vp, _u64, _vp],
+    "cnc_level_row_hist": [_u32, _u32, _vp, _vp],
+    "cnc_level_pruned_keys": [_u32, _u32, _vp, _i32, _vp, _vp, _vp, _vp],
+    "cnc_keys_to_points": [_vp, _u64, _u32, _vp, _vp, _vp],
     "cnc_ste_planes_pack": [_vp, _vp, _vp, _u64, _vp],
     "cnc_surrogate_fill": [_vp, _vp, _vp, _u64, _u64, _u64, _vp],
     "cnc_adam_planes": [_vp, _vp, _vp, _vp, _vp, _vp, _u64, _f32, _f32, _f32, _f32, _f32, _i64, _f32, _vp],

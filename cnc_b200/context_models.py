@@ -281,14 +281,26 @@ class CNC_context_models(nn.Module):
                  n_features=4, sample_num=20000, max_context_layer_num=3, ste_binary=False, ste_multistep=False,
                  add_noise=False, Q=100, quantize_epoch=1000, Pg_level=-1, Pg_level_2D=-1, Rb=128, step_update=16,
                  skip_levels_3D=(0, 1, 2, 3), skip_levels_2D=(0,), use_dimension_wise=True,
-                 use_overlap_area_pool=True, device="cuda", fused=True, shuffle_seed=None):
+                 use_overlap_area_pool=True, device="cuda", fused=True, shuffle_seed=None, tables="full"):
         """`shuffle_seed`: the symbol order of the dense context-coded levels is a random permutation
         (utils_bpp_acc.py:311-315) that encoder and decoder must share.  None = the reference's behaviour: drawn from
         torch's global CPU generator (same `torch.manual_seed` => same order as the reference's constructor); an int =
         drawn from a private generator seeded with it.  Either way `self.shuffle_seed` ends up holding what a decoder
         in another process needs to rebuild the same tables (an int, or the CPU generator state as bytes); the container
-        stores it (container.pack(..., layout=cm.layout()))."""
+        stores it (container.pack(..., layout=cm.layout())).
+
+        `tables`: "full" = the reference's inverse hash tables (every lattice vertex of every level grouped by table row,
+        utils_bpp_acc.py:294-335: 1.34 GB at the product layout, `pos_grid_sorted_list`).  "pruned" (CUDA, codec only) = only
+        the row statistics are computed at construction (one histogram pass per level, csrc/table_build.cu); the vertex
+        lists are built per occupancy grid at encode / decode time for the vertices that pass the occupancy test -- what
+        `mask` / `mask_exist` keep anyway (:811-833).  Same entry numbering, symbol order and chunking; the probabilities of
+        an entry are summed over the same vertices in the same order, grouped differently into the kernel's batches, so
+        the two modes agree to fp32 rounding, not bit for bit: the mode is part of `layout()` and must match on both
+        sides of the codec.  The training loss needs the full lists and builds them on first use."""
         super().__init__()
+        if tables not in ("full", "pruned"):
+            raise ValueError("tables must be 'full' or 'pruned'")
+        self.tables = tables
         dev = torch.device(device)
         self.MAX_POINTS_NUM_TO_OOM = 20000000
         self.use_overlap_area_pool, self.use_dimension_wise, self.fused = use_overlap_area_pool, use_dimension_wise, fused
@@ -333,16 +345,28 @@ class CNC_context_models(nn.Module):
         else:
             gen, self.shuffle_seed = torch.Generator().manual_seed(int(shuffle_seed)), int(shuffle_seed)
         # finest level first, like the reference (utils_bpp_acc.py:301): the order fixes which randperm a level gets
+        self.entry_of_row_list: List[torch.Tensor] = []         # pruned mode: table row -> entry index (int32), None = identity
         for i in reversed(range(Pg_level)):
             r = self.res[i]
-            rows, cnt, pts = self._inverse_table(i, dev)
+            if tables == "full":
+                rows, cnt, pts = self._inverse_table(i, dev)
+            else:
+                rows, cnt, pts = self._row_statistics(i, dev)
             if r <= self.resolution_thresh:   # dense levels: random symbol order (one voxel per row), CPU generator
                 shuffle_idx = torch.randperm(rows.nelement(), generator=gen).to(dev)
-                rows, pts, cnt = rows[shuffle_idx], pts[shuffle_idx], cnt[shuffle_idx]
+                rows, cnt = rows[shuffle_idx], cnt[shuffle_idx]
+                if pts is not None:
+                    pts = pts[shuffle_idx]
+            entry_of_row = None
+            T_i = self.offs[i + 1] - self.offs[i]
+            if tables == "pruned" and not (rows.numel() == T_i and r > self.resolution_thresh):
+                entry_of_row = torch.full((T_i,), -1, dtype=torch.int32, device=dev)
+                entry_of_row[rows] = torch.arange(rows.numel(), dtype=torch.int32, device=dev)
+            self.entry_of_row_list.insert(0, entry_of_row)
             self.unique_value_list.insert(0, rows.to(torch.int64))
             self.unique_count_list.insert(0, cnt.to(torch.int64))
             self.unique_count_cumsum_list.insert(0, torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(cnt, 0)]))
-            self.pos_grid_sorted_list.insert(0, pts.contiguous())
+            self.pos_grid_sorted_list.insert(0, None if pts is None else pts.contiguous())
         self.hashparams_num_levels = torch.tensor([v.numel() for v in self.unique_value_list], device=dev)
         snl = torch.round(self.hashparams_num_levels * (sample_num / self.hashparams_num_levels.sum())).to(torch.long)
         self.sample_num_levels = self.hashparams_num_levels if snl[-1] > self.hashparams_num_levels[-1] else snl
@@ -381,6 +405,67 @@ class CNC_context_models(nn.Module):
         rows, cnt = torch.unique_consecutive(indexes_sorted, return_counts=True)
         return rows, cnt, pts
 
+    def _row_statistics(self, i, dev):
+        """level i -> (rows that are hit ascending, vertices per row, None): what `_inverse_table` returns minus the vertex
+        list, from one histogram pass (cnc_level_row_hist) instead of a sort of res^3 keys"""
+        if dev.type != "cuda":
+            raise RuntimeError("tables='pruned' builds its tables with CUDA kernels: a CUDA device is required")
+        T = self.offs[i + 1] - self.offs[i]
+        cnt = torch.zeros(T, dtype=torch.int32, device=dev)
+        check(lib().cnc_level_row_hist(self.res[i], T, ptr(cnt), stream()))
+        rows = cnt.nonzero().squeeze(1)
+        return rows, cnt[rows].to(torch.int64), None
+
+    def _ensure_full_tables(self):
+        """the vertex lists of every level (training loss, op-by-op paths): built on first use in pruned mode"""
+        if all(p is not None for p in self.pos_grid_sorted_list):
+            return
+        dev = self.resolutions_list.device
+        for i in range(self.Pg_level):
+            if self.pos_grid_sorted_list[i] is None:
+                rows, _, pts = self._inverse_table(i, dev)
+                if self.res[i] <= self.resolution_thresh:    # dense: entry j is row unique_value_list[j] (one vertex each)
+                    pts = pts[self.unique_value_list[i]]
+                self.pos_grid_sorted_list[i] = pts.contiguous()
+
+    def _pruned_level(self, n, vx):
+        """vertex list of level n restricted to the vertices that pass the occupancy test of `vx` [Rb,Rb,Rb] (cached per
+        grid): (pts int16 [M,3] grouped by entry, ent int64 [Ee] entry indices that exist ascending, seg int64 [Ee+1]
+        running vertex counts, ent / seg also as numpy on the host)"""
+        key = (vx.data_ptr(), vx._version, tuple(vx.shape))
+        cache = getattr(self, "_pruned_cache", None)
+        if cache is None or cache[0] != key:
+            cache = self._pruned_cache = (key, {})
+        if n not in cache[1]:
+            dev = vx.device
+            r, T = self.res[n], self.offs[n + 1] - self.offs[n]
+            eor = self.entry_of_row_list[n]
+            counter = torch.zeros(1, dtype=torch.int64, device=dev)
+            args = (r, T, ptr(vx), vx.shape[-1], ptr(eor))
+            check(lib().cnc_level_pruned_keys(*args, None, ptr(counter), stream()))
+            M = int(counter.item())
+            keys = torch.empty(M, dtype=torch.int64, device=dev)
+            counter.zero_()
+            check(lib().cnc_level_pruned_keys(*args, ptr(keys), ptr(counter), stream()))
+            keys, _ = torch.sort(keys)
+            pts = torch.empty(M, 3, dtype=torch.int16, device=dev)
+            entry = torch.empty(M, dtype=torch.int32, device=dev)
+            check(lib().cnc_keys_to_points(ptr(keys), M, r, ptr(pts), ptr(entry), stream()))
+            del keys
+            ent, cnt = torch.unique_consecutive(entry, return_counts=True)
+            seg = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(cnt, 0)])
+            cache[1][n] = (pts, ent.to(torch.int64), seg, ent.cpu().numpy(), seg.cpu().numpy())
+        return cache[1][n]
+
+    def table_bytes(self) -> int:
+        """device bytes held by the inverse hash tables right now (vertex lists + per-entry arrays + pruned caches)"""
+        ts = [t for lst in (self.unique_value_list, self.unique_count_list, self.unique_count_cumsum_list, self.pos_grid_sorted_list,
+                            self.entry_of_row_list) for t in lst if t is not None]
+        cache = getattr(self, "_pruned_cache", None)
+        if cache is not None:
+            ts += [t for v in cache[1].values() for t in v[:3]]
+        return sum(t.numel() * t.element_size() for t in ts)
+
     def layout(self) -> dict:
         """what a decoder in another process needs to rebuild this object (json-able; goes into the container header)"""
         seed = self.shuffle_seed
@@ -390,7 +475,7 @@ class CNC_context_models(nn.Module):
                 "Pg_level": self.Pg_level, "Pg_level_2D": self.Pg_level_2D, "Rb": self.binary_vxl_len,
                 "skip_levels_3D": list(self.skip_levels_3D), "skip_levels_2D": list(self.skip_levels_2D),
                 "use_dimension_wise": self.use_dimension_wise, "use_overlap_area_pool": self.use_overlap_area_pool,
-                "shuffle_seed": seed if isinstance(seed, int) else {"cpu_rng_state_hex": _z85(seed)}}
+                "tables": self.tables, "shuffle_seed": seed if isinstance(seed, int) else {"cpu_rng_state_hex": _z85(seed)}}
 
     @classmethod
     def from_layout(cls, layout: dict, device="cuda", **kw):
@@ -539,8 +624,34 @@ class CNC_context_models(nn.Module):
     def _probs_3D(self, Encoding_xyz, table, binary_vxl, n, lo, hi, Pg_n):
         """P(+1) of the entries [lo, hi) of level n -> (prob [E,F] of the existing entries, mask_exist [hi-lo])."""
         if self.fused and self.n_features == 8 and self.max_context_layer_num == 3 and n >= 3 and Encoding_xyz.ste_binary:
+            if self.tables == "pruned":
+                return self._probs_3D_pruned(Encoding_xyz, table, binary_vxl, n, lo, hi, Pg_n)
             return self._probs_3D_fused(Encoding_xyz, table, binary_vxl, n, lo, hi, Pg_n)
+        self._ensure_full_tables()
         return self._probs_3D_unfused(Encoding_xyz, table, binary_vxl, n, lo, hi, Pg_n)
+
+    def _probs_3D_pruned(self, Encoding_xyz, table, binary_vxl, n, lo, hi, Pg_n):
+        """`_probs_3D_fused` on the occupancy-pruned vertex list: only the entries of [lo, hi) that exist are handed to the
+        kernel, each with exactly the vertices the reference keeps after its mask (utils_bpp_acc.py:811-833)"""
+        vx = binary_vxl.squeeze(0).contiguous()
+        if vx.dtype != torch.bool and vx.dtype != torch.uint8:
+            vx = vx != 0
+        pts, ent, seg, ent_h, seg_h = self._pruned_level(n, vx)
+        a, b = int(np.searchsorted(ent_h, lo)), int(np.searchsorted(ent_h, hi))
+        E, dev = b - a, pts.device
+        exist = torch.zeros(hi - lo, dtype=torch.bool, device=dev)
+        prob = torch.empty(E, 8, device=dev)
+        if E == 0:
+            return prob, exist
+        exist[ent[a:b] - lo] = True
+        seg_base = int(seg_h[a])
+        ex = torch.empty(E, dtype=torch.uint8, device=dev)
+        vbits, vbit_off = self._vertex_bits(Encoding_xyz, vx)
+        check(lib().cnc_context3d_probs(ptr(pts[seg_base:int(seg_h[b])]), ptr(seg[a:b + 1].contiguous()), E, ptr(vx), vx.shape[-1],
+                                        ptr(self._sign_bits(table)), ptr(Encoding_xyz.offsets_list), ptr(Encoding_xyz.resolutions_list),
+                                        n, float(Pg_n), ptr(self._mlp3d_packed()), ptr(prob), None, ptr(ex), seg_base, a,
+                                        ptr(vbits), ptr(vbit_off), stream()))
+        return prob, exist
 
     def _vertex_bits(self, Encoding_xyz, vx):
         """per-vertex occupancy predicate of all levels as bitmaps (cnc_vertex_valid_bits); rebuilt when the
@@ -652,6 +763,7 @@ class CNC_context_models(nn.Module):
     def forward_binary_vxl_mixPg_3D2D(self, Encoding_xyz, Encoding_xy, Encoding_xz, Encoding_yz, binary_vxl=None,
                                       verbose=False, sample_num=None, step=0):
         """Rate term of the training loss: (bits per parameter, MB).  utils_bpp_acc.py:533-706"""
+        self._ensure_full_tables()
         pq = {k: self.get_STE_params(E) for k, E in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz), ("xyz", Encoding_xyz))}
         refresh = step % self.step_update == 0 or self.idx_coords2_tmp is None
         if refresh:   # the reference caches the voxel list for step_update steps (:541-543): keep the occupancy it stands for
@@ -742,7 +854,7 @@ class CNC_context_models(nn.Module):
     def encode_binary_vxl_mixPg_3D2D(self, Encoding_xyz, Encoding_xy, Encoding_xz, Encoding_yz, binary_vxl=None,
                                      filename_prefix="b", return_streams=False):
         """utils_bpp_acc.py:709-865.  Writes `<prefix>_<axis><n>.b`, `<prefix>_3D<n>.b`, `<prefix>_3D<n>_<chunk>.b`."""
-        self._sbits_key = self._vbits_key = None   # per-call caches (tensor addresses are only unique while alive)
+        self._sbits_key = self._vbits_key = self._pruned_cache = None   # per-call caches (tensor addresses are only unique while alive)
         pq = {k: self.get_STE_params(E) for k, E in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz), ("xyz", Encoding_xyz))}
         Pgs_dict: Dict[str, torch.Tensor] = {}
         names, c1s, syms, jobs = [], [], [], []
@@ -827,6 +939,8 @@ class CNC_context_models(nn.Module):
         """utils_bpp_acc.py:867-999.  3D levels in order (level n is predicted from the decoded n-3..n-1), then the
         three planes (their dimension-wise context needs the decoded finest 3D level)."""
         self._sbits_key = self._vbits_key = None   # per-call caches (tensor addresses are only unique while alive)
+        if getattr(self, "_pruned_cache", None) is not None and self._pruned_cache[0][0] != binary_vxl.squeeze(0).data_ptr():
+            self._pruned_cache = None
 
         def read(name):
             if streams is not None:

@@ -87,6 +87,26 @@ int cnc_sign_pack(const float *params, uint8_t *bits, uint64_t n, cnc_stream_t s
 int cnc_sign_unpack(const uint8_t *bits, float *out, uint64_t n, cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Inverse hash tables of the context model, pruned by the occupancy grid.
+ * replaces: CNC_context_models.__init__ table construction, examples/utils_bpp_acc.py:294-335 (meshgrid of every level ->
+ *           get_grid_index -> torch.sort of up to 135.8 M keys -> unique), followed at every encode/decode by
+ *           query_mask_3D + boolean compaction of the same lists (:811-833).
+ *   cnc_level_row_hist    : counts [hashmap_size] u32 += number of lattice vertices of the level hashing to each row
+ *                           (caller zeroes).  Which rows are hit fixes entry numbering / chunking (:337-352, :798-802).
+ *   cnc_level_pruned_keys : every vertex whose +-1-cell box touches an occupied cell (the K6 test, aligner_kernel.cu:
+ *                           161-242) -> key (entry << 28) | ((x*res + y)*res + z), entry = entry_of_row[row] (NULL:
+ *                           entry = row), appended at *counter (u64, caller zeroes).  keys == NULL: count only.
+ *                           Sorting the keys gives the reference's order (entries ascending, lattice order inside).
+ *   cnc_keys_to_points    : sorted keys -> pts [n,3] i16, entry [n] i32.
+ * resolution^3 < 2^28.  binary_vxl [Rb,Rb,Rb] u8.
+ * ---------------------------------------------------------------------------------------- */
+int cnc_level_row_hist(uint32_t resolution, uint32_t hashmap_size, uint32_t *counts, cnc_stream_t stream);
+int cnc_level_pruned_keys(uint32_t resolution, uint32_t hashmap_size, const uint8_t *binary_vxl, int32_t Rb,
+                          const int32_t *entry_of_row, uint64_t *keys, uint64_t *counter, cnc_stream_t stream);
+int cnc_keys_to_points(const uint64_t *keys, uint64_t n, uint32_t resolution, int16_t *pts, int32_t *entry,
+                       cnc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Training step over the latent tables (caller side: the optimizer step of train_CNC_nerf_synthetic.py:254-266,
  * :362-364 and, under data parallelism, the exchange SURVEY 8(e) adds; the reference has neither kernel).
  * A replica needs from a table row only sign(p) (STE forward, ngp.py:26-31) and [|p| <= 1] (STE backward, ngp.py:33-39):

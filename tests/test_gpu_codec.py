@@ -21,7 +21,7 @@ def ball(Rb, radius=0.8):
     return torch.from_numpy(X * X + Y * Y + Z * Z <= radius * radius)
 
 
-def make(dev, res3, log2T, res2, log2T2, Rb, skip3=(0, 1, 2), seed=0, fused=True, smooth=True):
+def make(dev, res3, log2T, res2, log2T2, Rb, skip3=(0, 1, 2), seed=0, fused=True, smooth=True, tables="full"):
     from cnc_b200.context_models import CNC_context_models
     from cnc_b200.gridencoder import GridEncoder
 
@@ -34,7 +34,7 @@ def make(dev, res3, log2T, res2, log2T2, Rb, skip3=(0, 1, 2), seed=0, fused=True
             e.params.copy_(torch.where(torch.rand_like(e.params) < 0.7, 0.5, -0.5))
     cm = CNC_context_models(num_dim=3, resolutions_list=res3, resolutions_list_2D=res2, log2_hashmap_size=log2T,
                             log2_hashmap_size_2D=log2T2, n_features=8, sample_num=4000, max_context_layer_num=3,
-                            ste_binary=True, Rb=Rb, skip_levels_3D=skip3, skip_levels_2D=(0,), device=dev, fused=fused)
+                            ste_binary=True, Rb=Rb, skip_levels_3D=skip3, skip_levels_2D=(0,), device=dev, fused=fused, tables=tables)
     with torch.no_grad():   # context models that give non-trivial, valid probabilities
         for m in list(cm.context_model_3D) + [l for s in cm.context_model_2D for l in s]:
             if isinstance(m, torch.nn.Linear):
@@ -307,3 +307,95 @@ def test_rate_term_same_with_and_without_the_fused_context_mlp(cuda):
         assert (a is None) == (b is None)
         if a is not None:
             assert ((a - b).norm() / b.norm().clamp_min(1e-30)).item() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ SURVEY 8f.4
+DENSE3 = dict(res3=[6, 8, 10, 12, 18, 34], log2T=12, res2=[18, 34, 66], log2T2=10, Rb=16)   # level 3 dense + context-coded
+
+
+@pytest.mark.parametrize("cfg", [SMALL, DENSE3, dict(res3=R3, log2T=19, res2=R2, log2T2=17, Rb=128)], ids=["small", "dense3", "product"])
+def test_pruned_tables_are_the_masked_full_tables(cuda, cfg):
+    """tables='pruned' (histogram pass + occupancy-pruned key sort, csrc/table_build.cu) against the reference construction
+    (meshgrid -> hash -> sort -> unique, utils_bpp_acc.py:294-335) followed by the reference's mask (K6, :811-833):
+    identical entry numbering, per-entry vertex lists in the same order, identical existing-entry set -- all integers."""
+    cm_f, _, vxl = make(cuda, **cfg, seed=3, tables="full")
+    cm_p, _, _ = make(cuda, **cfg, seed=3, tables="pruned")
+    assert all(p is None for p in cm_p.pos_grid_sorted_list)
+    for n in range(cm_f.n_levels):
+        assert torch.equal(cm_f.unique_value_list[n], cm_p.unique_value_list[n]), n       # incl. the dense levels' shuffle
+        assert torch.equal(cm_f.unique_count_list[n], cm_p.unique_count_list[n]), n
+        assert torch.equal(cm_f.unique_count_cumsum_list[n], cm_p.unique_count_cumsum_list[n]), n
+    assert torch.equal(cm_f.hashparams_num_levels, cm_p.hashparams_num_levels)
+    assert cm_f.utils_points_per_param_levels == cm_p.utils_points_per_param_levels
+    vx = vxl.squeeze(0).contiguous()
+    total_f = total_p = 0
+    for n in range(3, cm_f.n_levels):
+        pts_f = cm_f.pos_grid_sorted_list[n]
+        mask = cm_f.query_binary_vxl(pts_f, vxl, n)
+        E = cm_f.unique_value_list[n].numel()
+        entry_f = torch.repeat_interleave(torch.arange(E, device=cuda), cm_f.unique_count_list[n])[mask]
+        pts_p, ent, seg, ent_h, seg_h = cm_p._pruned_level(n, vx)
+        assert torch.equal(pts_p, pts_f[mask]), n
+        e_want, c_want = torch.unique_consecutive(entry_f, return_counts=True)
+        assert torch.equal(ent, e_want) and torch.equal(seg[1:] - seg[:-1], c_want), n
+        assert np.array_equal(ent_h, ent.cpu().numpy()) and int(seg_h[-1]) == pts_p.shape[0]
+        total_f += pts_f.numel() * 2
+        total_p += pts_p.numel() * 2
+    print(f"vertex lists of the coded levels: full {total_f / 1e6:.1f} MB, pruned {total_p / 1e6:.1f} MB; "
+          f"all table state: full {cm_f.table_bytes() / 1e6:.1f} MB, pruned {cm_p.table_bytes() / 1e6:.1f} MB")
+    assert total_p < 0.6 * total_f
+    # the training loss still works from a pruned object: it builds the full lists on first use, identical to the reference's
+    cm_p._ensure_full_tables()
+    for n in range(cm_f.n_levels):
+        assert torch.equal(cm_f.pos_grid_sorted_list[n], cm_p.pos_grid_sorted_list[n]), n
+
+
+@pytest.mark.parametrize("cfg", [SMALL, DENSE3], ids=["small", "dense3"])
+def test_codec_pruned_mode_roundtrip_and_vs_full(cuda, cfg):
+    """encode / decode with pruned tables: round trip restores every coded row; against full-table mode the same files
+    carry the same symbols in the same order, the int16 CDFs are at most one step apart (same vertices, same order per
+    entry, different batching inside the kernel), and a decoder rebuilt from `layout()` is in pruned mode too."""
+    from cnc_b200 import torchac as tac
+    from cnc_b200.context_models import CNC_context_models
+
+    def encode(cm, encs, vxl):
+        cap, orig = {"c1": [], "sym": []}, tac.encode_streams_async
+
+        def spy(c1s, syms):
+            cap["c1"] += list(c1s)
+            cap["sym"] += list(syms)
+            return orig(c1s, syms)
+
+        tac.encode_streams_async = spy
+        try:
+            Pgs, est, coded, streams = cm.encode_binary_vxl_mixPg_3D2D(*encs, vxl, "p", return_streams=True)
+        finally:
+            tac.encode_streams_async = orig
+        return Pgs, streams, {k: (c, s_) for k, c, s_ in zip(streams, cap["c1"], cap["sym"])}, coded
+
+    cm_f, encs, vxl = make(cuda, **cfg, seed=5, tables="full")
+    cm_p, _, _ = make(cuda, **cfg, seed=5, tables="pruned")
+    cm_p.load_state_dict(cm_f.state_dict())
+    Pgs_f, st_f, cap_f, coded_f = encode(cm_f, encs, vxl)
+    Pgs_p, st_p, cap_p, coded_p = encode(cm_p, encs, vxl)
+    assert list(st_f) == list(st_p)
+    n_diff = n_tot = 0
+    for k in st_f:
+        assert torch.equal(cap_f[k][1], cap_p[k][1]), k                       # symbols: same rows, same order
+        d = (cap_f[k][0].to(torch.int32) - cap_p[k][0].to(torch.int32)).abs()
+        assert int(d.max()) <= 1, k
+        n_diff, n_tot = n_diff + int((d != 0).sum()), n_tot + d.numel()
+    print(f"pruned vs full tables: {n_diff} of {n_tot} int16 CDF entries differ; coded {coded_p * 1024:.2f} vs {coded_f * 1024:.2f} KiB")
+    assert n_diff < 0.01 * n_tot
+    lay = cm_p.layout()
+    assert lay["tables"] == "pruned"
+    cm_d = CNC_context_models.from_layout(lay, device=cuda)
+    assert cm_d.tables == "pruned"
+    cm_d.load_state_dict(cm_p.state_dict())
+    out = cm_d.decode_binary_vxl_mixPg_3D2D(*encs, *[torch.ones_like(e.params) for e in encs], vxl, Pgs_p, "p", streams=st_p)
+    ref = cm_f.decode_binary_vxl_mixPg_3D2D(*encs, *[torch.ones_like(e.params) for e in encs], vxl, Pgs_f, "p", streams=st_f)
+    for a, b, e in zip(out, ref, encs):
+        assert torch.equal(a, b)                                             # both modes reconstruct the same tables
+        q = torch.where(e.params >= 0, 1.0, -1.0)
+        assert ((a == q) | (a == 1)).all()
+    assert all(p is None for p in cm_d.pos_grid_sorted_list)                 # the decoder never built a full vertex list

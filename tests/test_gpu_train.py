@@ -68,8 +68,23 @@ def _scene(dev, n_rays=600, seed=0):
     o = o / o.norm(dim=-1, keepdim=True) * 4
     d = (torch.rand(n_rays, 3, generator=g) - 0.5) * 0.8 - o
     d = d / d.norm(dim=-1, keepdim=True)
-    pixels = torch.rand(n_rays, 3, generator=g) * 0.5
-    return field, est, Rays(o.to(dev), d.to(dev)), pixels.to(dev)
+    rays = Rays(o.to(dev), d.to(dev))
+
+    class Teacher(torch.nn.Module):
+        """a closed-form scene: the target pixels are its rendering through the same occupancy grid"""
+
+        def query_density(self, x):
+            return 30.0 * torch.exp(-8.0 * (x * x).sum(-1, keepdim=True))
+
+        def forward(self, x, dd):
+            return torch.sigmoid(4.0 * x), self.query_density(x)
+
+    from cnc_b200.render import render_image_with_occgrid
+
+    teacher = Teacher().to(dev).eval()
+    with torch.no_grad():
+        pixels = render_image_with_occgrid(teacher, est, rays, render_step_size=5e-3, render_bkgd=torch.zeros(3, device=dev))[0]
+    return field, est, rays, pixels
 
 
 def test_train_step_loss_falls_and_planes_follow(cuda):
@@ -77,17 +92,19 @@ def test_train_step_loss_falls_and_planes_follow(cuda):
     from cnc_b200.trainer import TrainStep
 
     field, est, rays, pixels = _scene(cuda)
-    ts = TrainStep(field, est, lr=6e-3)
+    ts = TrainStep(field, est, lr=2e-3)
     assert ts.sharded and ts.comm_bytes_per_step() == 0
     bk = torch.zeros(3, device=cuda)
     losses = []
     p0 = field.mlp_base.encoding_xyz.params.detach().clone()
-    for _ in range(50):
+    for _ in range(60):
         loss, n = ts(rays, pixels, render_bkgd=bk, refresh_occupancy=False)
         assert n > 0
         losses.append(float(loss))
     assert all(np.isfinite(losses))
-    assert np.mean(losses[-5:]) < 0.5 * np.mean(losses[:5]), (losses[:5], losses[-5:])
+    print("loss, first and last five of 60 steps:", [round(l, 5) for l in losses[:5]], [round(l, 5) for l in losses[-5:]])
+    assert losses[-1] < 0.5 * losses[0], (losses[:5], losses[-5:])
+    assert losses[-1] < 0.9 * float((pixels ** 2).mean()), "no better than a transparent field"
     mb = field.mlp_base
     for enc in (mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz):
         cached = enc._sign_cache.get(enc.params)              # what the next forward will gather from
