@@ -184,7 +184,7 @@ class ShardedTableAdam:
             torch.autograd.graph.increment_version(p)         # the kernels wrote through raw pointers
             cache = getattr(enc, "_sign_cache", None)
             if cache is not None and p.is_cuda:               # the next forward gathers from this plane: no repack pass
-                cache.bits, cache.key = t["sign"], (p.data_ptr(), p._version, tuple(p.shape))
+                cache.publish(p, t["sign"])
 
     @torch.no_grad()
     def sync_params(self) -> None:

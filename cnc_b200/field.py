@@ -91,7 +91,7 @@ class _FusedFieldTrain(Function):
         pos = positions.detach().reshape(-1, 3).contiguous().float()
         dirs = directions.detach().reshape(-1, 3).contiguous().float()
         n, dev = pos.shape[0], pos.device
-        bits = [e._sign_cache.get(e.params) for e in encs]
+        bits = [e.sign_bits() for e in encs]
         sigma = torch.empty(n, device=dev)
         rgb = torch.empty(n, 3, device=dev)
         geo = torch.empty(n, 79, device=dev)
@@ -278,8 +278,10 @@ class NGPRadianceField_mygrid_2D3D(nn.Module):
     def _fused_blob(self):
         lins = (self.mlp_base.network[0], self.mlp_base.network[2], self.mlp_head[0], self.mlp_head[2], self.mlp_head[4])
         ps = [t for l in lins for t in (l.weight, l.bias)]
+        # (address, version) identifies the weights only outside training: fused optimizers update them without bumping the
+        # version counter, so a training-mode forward always re-packs (762 KB, one small kernel)
         key = tuple((t.data_ptr(), t._version) for t in ps)
-        if getattr(self, "_blob_key", None) != key:
+        if self.training or getattr(self, "_blob_key", None) != key:
             blob = getattr(self, "_blob", None)
             if blob is None or blob.device != ps[0].device:
                 blob = torch.empty(lib().cnc_field_blob_floats(), dtype=torch.float32, device=ps[0].device)
@@ -299,7 +301,7 @@ class NGPRadianceField_mygrid_2D3D(nn.Module):
         if getattr(self, "_aabb_host", None) is None or self._aabb_src != (self.aabb.data_ptr(), self.aabb._version):
             self._aabb_host = (ctypes.c_float * 6)(*self.aabb.detach().cpu().tolist())
             self._aabb_src = (self.aabb.data_ptr(), self.aabb._version)
-        bits = [e._sign_cache.get(e.params) for e in (mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz)]
+        bits = [e.sign_bits() for e in (mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz)]
         sigma = torch.empty(n, device=pos.device, dtype=torch.float32)
         rgb = None if dirs is None else torch.empty(n, 3, device=pos.device, dtype=torch.float32)
         geo = torch.empty(n, 79, device=pos.device, dtype=torch.float32) if return_feat else None
@@ -344,7 +346,7 @@ class NGPRadianceField_mygrid_2D3D(nn.Module):
                                 "rgb": torch.empty(n, 3, device=dev), "sig": torch.empty(n, device=dev)}
         mb = self.mlp_base
         encs = (mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz)
-        bits = [e._sign_cache.get(e.params) for e in encs]
+        bits = [e.sign_bits() for e in encs]
         blob = self._fused_blob()
         if getattr(self, "_aabb_host", None) is None or self._aabb_src != (self.aabb.data_ptr(), self.aabb._version):
             self._aabb_host = (ctypes.c_float * 6)(*self.aabb.detach().cpu().tolist())
@@ -376,6 +378,18 @@ class NGPRadianceField_mygrid_2D3D(nn.Module):
         return _FusedFieldTrain.apply(self, positions, directions, mb.encoding_xyz.params, mb.encoding_xy.params,
                                       mb.encoding_xz.params, mb.encoding_yz.params,
                                       *[t for l in lins for t in (l.weight, l.bias)])
+
+    def train(self, mode: bool = True):
+        if mode != self.training:
+            self._blob_key = None            # the last optimizer step may not have bumped the version counters
+        return super().train(mode)
+
+    def invalidate_caches(self):
+        """forget the packed MLP weights and the sign planes (after updating parameters behind autograd's back)"""
+        self._blob_key = None
+        mb = self.mlp_base
+        for e in (mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz):
+            e.invalidate()
 
     def _use_fused(self):
         return (not torch.is_grad_enabled()) and getattr(self, "fused", True) and self.fused_available()

@@ -108,17 +108,28 @@ grid_encode = _grid_encode.apply
 
 
 class _SignCache:
-    """1-bit sign table of a parameter tensor, re-packed only when the tensor changed."""
+    """1-bit sign table of a parameter tensor.
+
+    The tensor's (address, version, shape) is only trusted as "unchanged" outside training: fused optimizers
+    (torch.optim.Adam(fused=True), our own table Adam) write the parameters WITHOUT bumping the autograd version counter,
+    so during training the plane is re-packed on every forward (one read pass of the table) -- unless an optimizer that
+    keeps the plane up to date itself has `publish`ed it (dp.ShardedTableAdam writes the sign plane in the same pass as the
+    update)."""
 
     def __init__(self):
         self.key = None
         self.bits = None
+        self.published = False
 
-    def get(self, params: torch.Tensor) -> torch.Tensor:
+    def publish(self, params: torch.Tensor, bits: torch.Tensor) -> None:
+        """`bits` is, and will be kept, the sign plane of `params` by whoever updates `params` in place"""
+        self.bits, self.key, self.published = bits, (params.data_ptr(), params._version, tuple(params.shape)), True
+
+    def get(self, params: torch.Tensor, trust_version: bool = True) -> torch.Tensor:
         key = (params.data_ptr(), params._version, tuple(params.shape))
-        if key != self.key:
+        if key != self.key or not (trust_version or self.published):
             self.bits = _backend.sign_pack(params.detach().contiguous(), None)
-            self.key = key
+            self.key, self.published = key, False
         return self.bits
 
 
@@ -201,8 +212,18 @@ class GridEncoder(nn.Module):
             self.params.uniform_(-std, std)
 
     def invalidate(self):
-        """forget the cached sign planes (after writing to `params` through `.data` or a raw pointer)"""
+        """forget the cached sign planes (after writing to `params` through `.data`, a raw pointer or a fused optimizer)"""
         self._sign_cache.key = self._sign_cache_out.key = None
+        self._sign_cache.published = False
+
+    def train(self, mode: bool = True):
+        if mode != self.training and not self._sign_cache.published:
+            self._sign_cache.key = None      # the last optimizer step may not have bumped the version (see _SignCache)
+        return super().train(mode)
+
+    def sign_bits(self) -> torch.Tensor:
+        """the 1-bit plane of `params` the forward gathers from"""
+        return self._sign_cache.get(self.params, trust_version=not self.training)
 
     def __repr__(self):
         return (f"GridEncoder: num_dim={self.num_dim} n_levels={self.n_levels} n_features={self.n_features} "
@@ -214,7 +235,7 @@ class GridEncoder(nn.Module):
         params = self.params if outspace_params is None else outspace_params
         if self.ste_binary:
             if outspace_params is None:
-                bits = self._sign_cache.get(params)
+                bits = self.sign_bits()
             else:
                 # a caller-provided table (decode: the partially reconstructed one; a fresh STE output per call): address and
                 # version do not identify it -- the allocator hands the same block to the next temporary -- so no caching

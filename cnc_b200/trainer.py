@@ -28,13 +28,13 @@ from .render import Rays, render_image_with_occgrid
 class TrainStep:
     def __init__(self, radiance_field, estimator, context_model=None, lmbda: float = 0.0, lr: float = 6e-3,
                  render_step_size: float = 5e-3, target_sample_batch_size: int = 1 << 18, bucket_bytes: int = 32 << 20,
-                 weight_decay: float = 2e-6, occ_refresh_every: int = 16):
+                 weight_decay: float = 2e-6, occ_refresh_every: int = 16, shard_tables: bool = True):
         self.field, self.estimator, self.cm, self.lmbda = radiance_field, estimator, context_model, lmbda
         self.render_step_size, self.target, self.occ_every = render_step_size, target_sample_batch_size, occ_refresh_every
         self.lr = lr
         mb = radiance_field.mlp_base
         encs = [mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz]
-        self.sharded = all(e.params.numel() % 32 == 0 and e.ste_binary for e in encs)
+        self.sharded = shard_tables and all(e.params.numel() % 32 == 0 and e.ste_binary for e in encs)
         table_ids = {id(e.params) for e in encs} if self.sharded else set()
         field_rest = [p for p in radiance_field.parameters() if id(p) not in table_ids and p.requires_grad]
         ctx = [p for p in context_model.parameters() if p.requires_grad] if context_model is not None else []

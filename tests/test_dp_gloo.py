@@ -45,8 +45,8 @@ def _worker(rank, world, port, q):
     buf.register_buffer("binaries", torch.full((4,), rank == 0))
     buf.register_buffer("occs", torch.full((4,), float(rank + 1)))
     broadcast_module_buffers(buf, ["binaries", "occs"], src=0)
-    q.put((rank, [p.grad.clone() if p.grad is not None else None for p in params], n, mine.origins.shape[0],
-           buf.binaries.clone(), buf.occs.clone(), [list(b) for b in red.buckets]))
+    q.put((rank, [p.grad.numpy().copy() if p.grad is not None else None for p in params], n, mine.origins.shape[0],
+           buf.binaries.numpy().copy(), buf.occs.numpy().copy(), [list(b) for b in red.buckets]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -62,7 +62,9 @@ def test_bucketed_grad_allreduce_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    T = lambda l: [None if t is None else torch.from_numpy(t) for t in l]
     (r0, g0, n0, c0, b0, o0, buckets), (r1, g1, n1, c1, b1, o1, _) = out
+    g0, g1, b0, b1, o1 = T(g0), T(g1), torch.from_numpy(b0), torch.from_numpy(b1), torch.from_numpy(o1)
     assert c0 + c1 == 11 and abs(c0 - c1) <= 1 and n0 == n1 == 11.0
     # single-process reference: mean over ranks of the per-rank gradients
     from cnc_b200.dp import shard_range
@@ -135,7 +137,9 @@ def _sharded_worker(rank, world, port, q):
     ts = TrainStep.__new__(TrainStep)
     ts.world = world
     votes = (ts._everyone_has_samples(0 if rank == 1 else 7, "cpu"), ts._everyone_has_samples(3 + rank, "cpu"))
-    q.put((rank, before_sync, [e.params.detach().clone() for e in encs], spans, planes, votes, opt.comm_bytes_per_step()))
+    np_ = lambda t: t.detach().numpy().copy()      # by value: the parent may read the queue after this process is gone
+    q.put((rank, [np_(t) for t in before_sync], [np_(e.params) for e in encs], spans, [(np_(a), np_(b)) for a, b in planes], votes,
+           opt.comm_bytes_per_step()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -165,6 +169,8 @@ def test_sharded_table_adam_world2():
     from cnc_b200.train_ops import planes_pack
 
     for rank, before, after, spans, planes, votes, comm in out:
+        before, after = [torch.from_numpy(t) for t in before], [torch.from_numpy(t) for t in after]
+        planes = [(torch.from_numpy(a), torch.from_numpy(b)) for a, b in planes]
         for k, p in enumerate(ref):
             lo, hi, n_main = spans[k]
             assert lo % 32 == 0 and hi % 32 == 0 and (hi - lo) * world == n_main and p.numel() - n_main < 32 * world
@@ -184,7 +190,7 @@ def test_sharded_table_adam_world2():
             torch.testing.assert_close(after[k].view(-1), want, rtol=1e-5, atol=1e-6)          # after sync_params: everything
         assert votes == (False, True)
         assert comm == sum(4 * p.numel() + 2 * (spans[k][1] - spans[k][0]) // 8 for k, p in enumerate(ref))
-    assert torch.equal(out[0][2][0], out[1][2][0])
+    assert (out[0][2][0] == out[1][2][0]).all()
 
 
 def test_train_ops_cpu_reference_paths():

@@ -103,11 +103,12 @@ def test_train_step_loss_falls_and_planes_follow(cuda):
         losses.append(float(loss))
     assert all(np.isfinite(losses))
     print("loss, first and last five of 60 steps:", [round(l, 5) for l in losses[:5]], [round(l, 5) for l in losses[-5:]])
-    assert losses[-1] < 0.5 * losses[0], (losses[:5], losses[-5:])
+    # (the reference's own step on its own kernels goes 0.148 -> 0.001 on this scene in 60 steps: scripts/train_compare.py)
+    assert np.mean(losses[-5:]) < 0.05 * losses[0], (losses[:5], losses[-5:])
     assert losses[-1] < 0.9 * float((pixels ** 2).mean()), "no better than a transparent field"
     mb = field.mlp_base
     for enc in (mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz):
-        cached = enc._sign_cache.get(enc.params)              # what the next forward will gather from
+        cached = enc.sign_bits()                              # what the next forward will gather from
         assert torch.equal(cached, G.sign_pack(enc.params.detach().contiguous()))
     moved = (mb.encoding_xyz.params.detach() != p0).any(-1).float().mean()
     assert 0.001 < float(moved) <= 1.0                         # rows the rays touched (plus weight decay on all rows)
@@ -118,6 +119,32 @@ def test_train_step_loss_falls_and_planes_follow(cuda):
 
         rgb, _, _, _ = render_image_with_occgrid(field, est, rays, render_step_size=5e-3, render_bkgd=bk)
     assert float(torch.nn.functional.mse_loss(rgb, pixels)) < 1.5 * np.mean(losses[-5:]) + 1e-3
+
+
+def test_caches_follow_fused_optimizers(cuda):
+    """torch.optim.Adam(fused=True) (and any kernel writing through raw pointers) updates parameters without bumping the
+    autograd version counter: the packed MLP blob and the sign planes must not be trusted by version during training,
+    and a train() -> eval() switch must drop them (round-1 bug: every forward after the first saw step-0 weights)."""
+    from cnc_b200.render import render_image_with_occgrid
+
+    field, est, rays, pixels = _scene(cuda, seed=5)
+    bk = torch.zeros(3, device=cuda)
+    opt = torch.optim.Adam(field.parameters(), lr=5e-3, eps=1e-15, fused=True)
+
+    def render():
+        return render_image_with_occgrid(field, est, rays, render_step_size=5e-3, render_bkgd=bk)[0]
+
+    for _ in range(3):
+        field.train()
+        opt.zero_grad(set_to_none=True)
+        torch.nn.functional.mse_loss(render(), pixels).backward()
+        opt.step()
+        field.eval()
+        with torch.no_grad():
+            got = render()                                   # through the caches
+            field.invalidate_caches()
+            want = render()                                  # everything re-packed from the parameters
+        assert torch.equal(got, want)
 
 
 def test_train_step_with_rate_term(cuda):
