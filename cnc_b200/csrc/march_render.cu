@@ -5,10 +5,10 @@
 // include/utils_scan.cuh + scan.cu (segmented inclusive/exclusive sum/prod), nerfacc/volrend.py:211-266,
 // :314-364, :485-549 (transmittance / weights / accumulate_along_rays).  SURVEY Appendix E.
 //
-// B200 notes: these are per-ray sequential walks over a 2 MiB occupancy grid (L2 resident) and a few floats
-// per sample -- latency-bound integer/float work, one thread per ray.  Where the reference launches
-// exclusive_sum + exp + mul + 3 x index_add_ (plus pack_info) for the rendering tail, `cnc_render_from_density`
-// does it in one pass per ray with no atomics and a fixed (sequential) summation order.
+// B200 notes: the march of a ray is a sequential walk over a 2 MiB occupancy grid (L2 resident) -- latency-bound, one
+// ray per warp for training-size batches (see traverse_kernel).  The scans and the rendering tail are one warp per ray,
+// 32 samples per pass with shuffle scans: where the reference launches exclusive_sum + exp + mul + 3 x index_add_ (plus
+// pack_info), `cnc_render_from_density` does it in one pass per ray with no atomics and a fixed summation tree.
 // Multiply-adds that nvcc contracts in the reference build are written as explicit __fmaf_rn (this library is
 // compiled with --fmad=false), matching oracle/cnc_oracle_march.c.
 #include <cuda_runtime.h>
@@ -82,9 +82,19 @@ struct MarchArgs {
     float *terminate;             // nullable: where the march of the ray stopped
 };
 
-// one thread per ray: grid.cu:68-318 with the interval edges folded into (t_start, t_end) per sample
+// grid.cu:68-318 with the interval edges folded into (t_start, t_end) per sample.  The walk of a ray is one sequential
+// chain (t += dt in fp32, DDA boundaries tdist += delta: both defined by their rounding sequence) with nested
+// data-dependent loops.  RAY_PER_WARP: lane 0 of every warp walks one ray and the other lanes retire at once -- with
+// 32 rays per warp the warp executes the UNION of 32 different loop nests (measured: 292 us for 1100 rays, ten times one
+// ray's chain); a training batch has a few thousand rays, far fewer than the machine has warp slots.  Large batches
+// (test-time wavefronts of 10^5..10^6 rays with a step limit) keep one thread per ray.
+template <bool RAY_PER_WARP>
 __global__ void __launch_bounds__(128) traverse_kernel(const MarchArgs a) {
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (RAY_PER_WARP) {
+        if (threadIdx.x & 31) return;
+        tid >>= 5;
+    }
     if (tid >= a.n_rays) return;
     if (a.rays_mask && !a.rays_mask[tid]) {
         if (a.cnt) a.cnt[tid] = 0;
@@ -190,59 +200,95 @@ __global__ void __launch_bounds__(128) traverse_kernel(const MarchArgs a) {
     if (a.cnt) a.cnt[tid] = n_samples;
 }
 
-// op: 0 sum, 1 prod; sequential per ray (deterministic; the reference's smem tree differs in the last bits)
+__device__ __forceinline__ float warp_incl_scan(float v, int op, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (uint32_t)d) v = op ? __fmul_rn(o, v) : __fadd_rn(o, v);
+    }
+    return v;
+}
+
+// op: 0 sum, 1 prod.  One warp per ray: 32 consecutive samples per pass (coalesced), a shuffle scan inside the pass and a
+// running carry between passes -- a fixed summation tree per ray (deterministic; the reference's smem tree, 32 elements per
+// tile as well, differs in the last bits: utils_scan.cuh:153-245).
 __global__ void __launch_bounds__(128)
 packed_scan_kernel(const float *__restrict__ in, const int64_t *__restrict__ packed, int64_t n_rays, float *__restrict__ out,
                    int op, int inclusive, int reverse) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
     if (r >= n_rays) return;
     const int64_t s = packed[r * 2], c = packed[r * 2 + 1];
-    float acc = op ? 1.0f : 0.0f;
-    for (int64_t j = 0; j < c; j++) {
+    float carry = op ? 1.0f : 0.0f;
+    for (int64_t j0 = 0; j0 < c; j0 += 32) {
+        const int64_t j = j0 + lane;
+        const bool ok = j < c;
         const int64_t i = reverse ? s + c - 1 - j : s + j;
-        const float v = in[i];
-        if (inclusive) {
-            acc = op ? __fmul_rn(acc, v) : __fadd_rn(acc, v);
-            out[i] = acc;
-        } else {
-            out[i] = acc;
-            acc = op ? __fmul_rn(acc, v) : __fadd_rn(acc, v);
-        }
+        const float v = ok ? in[i] : (op ? 1.0f : 0.0f);
+        float inc = warp_incl_scan(v, op, lane);
+        inc = op ? __fmul_rn(carry, inc) : __fadd_rn(carry, inc);
+        float exc = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) exc = carry;
+        if (ok) out[i] = inclusive ? inc : exc;
+        carry = __shfl_sync(0xffffffffu, inc, 31);
     }
 }
 
-// volrend.py:211-266 + :314-364 + :485-549 in one pass per ray
+// volrend.py:211-266 + :314-364 + :485-549 in one pass per ray, one warp per ray (32 samples per pass)
 __global__ void __launch_bounds__(128)
 render_density_kernel(const float *__restrict__ t0, const float *__restrict__ t1, const float *__restrict__ sigma,
                       const float *__restrict__ rgb, const int64_t *__restrict__ packed, int64_t n_rays,
                       const float *__restrict__ prefix_trans, float *__restrict__ weights, float *__restrict__ trans,
                       float *__restrict__ alphas, float *__restrict__ colors, float *__restrict__ opac,
                       float *__restrict__ depth) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
     if (r >= n_rays) return;
     const int64_t s = packed[r * 2], c = packed[r * 2 + 1];
-    float acc = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, op = 0.f, dp = 0.f;
-    for (int64_t i = s; i < s + c; i++) {
-        const float sd = __fmul_rn(sigma[i], __fsub_rn(t1[i], t0[i]));
-        const float al = __fsub_rn(1.0f, expf(-sd));
-        float T = expf(-acc);
-        if (prefix_trans) T = __fmul_rn(T, prefix_trans[i]);
-        const float w = __fmul_rn(T, al);
-        acc = __fadd_rn(acc, sd);
-        if (weights) weights[i] = w;
-        if (trans) trans[i] = T;
-        if (alphas) alphas[i] = al;
-        if (rgb) {
-            cr = __fadd_rn(cr, __fmul_rn(w, rgb[i * 3 + 0]));   // accumulate_along_rays: src = weights * values, then add
-            cg = __fadd_rn(cg, __fmul_rn(w, rgb[i * 3 + 1]));
-            cb = __fadd_rn(cb, __fmul_rn(w, rgb[i * 3 + 2]));
+    float carry = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, op = 0.f, dp = 0.f;
+    for (int64_t j0 = 0; j0 < c; j0 += 32) {
+        const int64_t i = s + j0 + lane;
+        const bool ok = j0 + lane < c;
+        float a0 = 0.f, a1 = 0.f, sd = 0.f;
+        if (ok) {
+            a0 = t0[i];
+            a1 = t1[i];
+            sd = __fmul_rn(sigma[i], __fsub_rn(a1, a0));
         }
-        op = __fadd_rn(op, w);
-        dp = __fadd_rn(dp, __fmul_rn(w, __fmul_rn(__fadd_rn(t0[i], t1[i]), 0.5f)));
+        const float inc = __fadd_rn(carry, warp_incl_scan(sd, 0, lane));
+        float acc = __shfl_up_sync(0xffffffffu, inc, 1);     // exclusive sum of sigma * delta along the ray
+        if (lane == 0) acc = carry;
+        carry = __shfl_sync(0xffffffffu, inc, 31);
+        if (ok) {
+            const float al = __fsub_rn(1.0f, expf(-sd));
+            float T = expf(-acc);
+            if (prefix_trans) T = __fmul_rn(T, prefix_trans[i]);
+            const float w = __fmul_rn(T, al);
+            if (weights) weights[i] = w;
+            if (trans) trans[i] = T;
+            if (alphas) alphas[i] = al;
+            if (rgb) {
+                cr = __fadd_rn(cr, __fmul_rn(w, rgb[i * 3 + 0]));   // accumulate_along_rays: src = weights * values, then add
+                cg = __fadd_rn(cg, __fmul_rn(w, rgb[i * 3 + 1]));
+                cb = __fadd_rn(cb, __fmul_rn(w, rgb[i * 3 + 2]));
+            }
+            op = __fadd_rn(op, w);
+            dp = __fadd_rn(dp, __fmul_rn(w, __fmul_rn(__fadd_rn(a0, a1), 0.5f)));
+        }
     }
-    if (colors) { colors[r * 3 + 0] = cr; colors[r * 3 + 1] = cg; colors[r * 3 + 2] = cb; }
-    if (opac) opac[r] = op;
-    if (depth) depth[r] = dp;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        cr = __fadd_rn(cr, __shfl_xor_sync(0xffffffffu, cr, d));
+        cg = __fadd_rn(cg, __shfl_xor_sync(0xffffffffu, cg, d));
+        cb = __fadd_rn(cb, __shfl_xor_sync(0xffffffffu, cb, d));
+        op = __fadd_rn(op, __shfl_xor_sync(0xffffffffu, op, d));
+        dp = __fadd_rn(dp, __shfl_xor_sync(0xffffffffu, dp, d));
+    }
+    if (lane == 0) {
+        if (colors) { colors[r * 3 + 0] = cr; colors[r * 3 + 1] = cg; colors[r * 3 + 2] = cb; }
+        if (opac) opac[r] = op;
+        if (depth) depth[r] = dp;
+    }
 }
 
 }  // namespace mr
@@ -279,7 +325,10 @@ int cnc_traverse_grids(const float *rays_o, const float *rays_d, const uint8_t *
     mr::MarchArgs a{rays_o, rays_d, rays_mask, n_rays, n_grids, rx, ry, rz, binaries, aabbs, hits, t_sorted, t_indices,
                     near_planes, far_planes, step_size, cone_angle, steps_limit, chunk_starts, cnt, t_starts, t_ends,
                     ray_indices, terminate_planes};
-    mr::traverse_kernel<<<div_up((uint64_t)n_rays, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    if (n_rays <= 148 * 64 * 2)   // at most two waves of one-ray warps
+        mr::traverse_kernel<true><<<div_up((uint64_t)n_rays * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    else
+        mr::traverse_kernel<false><<<div_up((uint64_t)n_rays, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return check_launch("traverse_grids");
 }
 
@@ -287,7 +336,7 @@ int cnc_packed_scan(const float *in, const int64_t *packed_info, int64_t n_rays,
                     int32_t reverse, cnc_stream_t stream) {
     if (n_rays == 0) return CNC_OK;
     if (!in || !packed_info || !out) { set_error("packed_scan: null pointer"); return CNC_EINVAL; }
-    mr::packed_scan_kernel<<<div_up((uint64_t)n_rays, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(in, packed_info, n_rays, out, op, inclusive, reverse);
+    mr::packed_scan_kernel<<<div_up((uint64_t)n_rays * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(in, packed_info, n_rays, out, op, inclusive, reverse);
     return check_launch("packed_scan");
 }
 
@@ -297,7 +346,7 @@ int cnc_render_from_density(const float *t_starts, const float *t_ends, const fl
                             cnc_stream_t stream) {
     if (n_rays == 0) return CNC_OK;
     if (!t_starts || !t_ends || !sigmas || !packed_info) { set_error("render_from_density: null pointer"); return CNC_EINVAL; }
-    mr::render_density_kernel<<<div_up((uint64_t)n_rays, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    mr::render_density_kernel<<<div_up((uint64_t)n_rays * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
         t_starts, t_ends, sigmas, rgbs, packed_info, n_rays, prefix_trans, weights, trans, alphas, colors, opacities, depths);
     return check_launch("render_from_density");
 }

@@ -35,19 +35,76 @@ class RaySamples:
     is_valid: Optional[Tensor] = None
 
 
-@dataclass
 class RayIntervals:
-    """nerfacc/data_specs.py RayIntervals.  Edges are stored per sample (left, right), so
-    `vals[is_left]` / `vals[is_right]` are t_starts / t_ends like in occ_grid.py:188-189."""
-    vals: Tensor
-    packed_info: Optional[Tensor] = None
-    ray_indices: Optional[Tensor] = None
-    is_left: Optional[Tensor] = None
-    is_right: Optional[Tensor] = None
-    # not in nerfacc: the same edges as two flat arrays, so that callers inside this package need no boolean-mask
-    # indexing (a nonzero() and a host sync each) to get them back
-    t_starts: Optional[Tensor] = None
-    t_ends: Optional[Tensor] = None
+    """nerfacc/data_specs.py RayIntervals.  Edges are stored per sample (left, right), so `vals[is_left]` / `vals[is_right]`
+    are t_starts / t_ends like in occ_grid.py:188-189.  The march produces the two edge arrays directly (`t_starts`,
+    `t_ends`, not in nerfacc); the interleaved reference layout (`vals`, `is_left`, `is_right`, `ray_indices`,
+    `packed_info`) is materialised on first access, so callers inside this package pay for none of it."""
+
+    def __init__(self, vals=None, packed_info=None, ray_indices=None, is_left=None, is_right=None, t_starts=None, t_ends=None,
+                 sample_packed_info=None, sample_ray_indices=None):
+        self._vals, self._packed_info, self._ray_indices, self._is_left, self._is_right = vals, packed_info, ray_indices, is_left, is_right
+        self.t_starts, self.t_ends = t_starts, t_ends
+        self._spk, self._sri = sample_packed_info, sample_ray_indices
+
+    @property
+    def vals(self):
+        if self._vals is None and self.t_starts is not None:
+            self._vals = torch.stack([self.t_starts, self.t_ends], dim=-1).reshape(-1)
+        return self._vals
+
+    @property
+    def is_left(self):
+        if self._is_left is None and self.t_starts is not None:
+            self._is_left = torch.zeros(2 * self.t_starts.numel(), dtype=torch.bool, device=self.t_starts.device)
+            self._is_left[0::2] = True
+        return self._is_left
+
+    @property
+    def is_right(self):
+        if self._is_right is None and self.t_starts is not None:
+            self._is_right = ~self.is_left
+        return self._is_right
+
+    @property
+    def ray_indices(self):
+        if self._ray_indices is None and self._sri is not None:
+            self._ray_indices = self._sri.repeat_interleave(2)
+        return self._ray_indices
+
+    @property
+    def packed_info(self):
+        if self._packed_info is None and self._spk is not None:
+            self._packed_info = self._spk * 2
+        return self._packed_info
+
+
+class _LazySamples(RaySamples):
+    """RaySamples of an exact-size march: `vals` (the sample midpoints) and `is_valid` (all true) on first access"""
+
+    def __init__(self, t0, t1, packed_info, ray_indices):
+        self._t0, self._t1, self._v, self._ok = t0, t1, None, None
+        self.packed_info, self.ray_indices = packed_info, ray_indices
+
+    @property
+    def vals(self):
+        if self._v is None:
+            self._v = (self._t0 + self._t1) * 0.5
+        return self._v
+
+    @vals.setter
+    def vals(self, v):
+        self._v = v
+
+    @property
+    def is_valid(self):
+        if self._ok is None:
+            self._ok = torch.ones(self._t0.numel(), dtype=torch.bool, device=self._t0.device)
+        return self._ok
+
+    @is_valid.setter
+    def is_valid(self, v):
+        self._ok = v
 
 
 # ------------------------------------------------------------------------------------------ pack / scans
@@ -170,13 +227,8 @@ def traverse_grids(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tens
     else:
         term.copy_(nearp)
     packed = torch.stack([starts, cnt], dim=-1)
-    vals = torch.stack([t0, t1], dim=-1).reshape(-1)
-    left = torch.zeros(2 * total, dtype=torch.bool, device=dev)
-    left[0::2] = True
-    intervals = RayIntervals(vals=vals, packed_info=torch.stack([starts * 2, cnt * 2], -1), ray_indices=ri.repeat_interleave(2),
-                             is_left=left, is_right=~left, t_starts=t0, t_ends=t1)
-    samples = RaySamples(vals=(t0 + t1) * 0.5, packed_info=packed, ray_indices=ri,
-                         is_valid=torch.ones(total, dtype=torch.bool, device=dev))
+    intervals = RayIntervals(t_starts=t0, t_ends=t1, sample_packed_info=packed, sample_ray_indices=ri)
+    samples = _LazySamples(t0, t1, packed, ri)
     return intervals, samples, term
 
 
@@ -364,7 +416,7 @@ class OccGridEstimator(torch.nn.Module):
             near_planes += torch.rand_like(near_planes) * render_step_size
         intervals, samples, _ = traverse_grids(rays_o, rays_d, self.binaries, self.aabbs, near_planes=near_planes,
                                                far_planes=far_planes, step_size=render_step_size, cone_angle=cone_angle)
-        t_starts, t_ends = intervals.vals[0::2], intervals.vals[1::2]
+        t_starts, t_ends = intervals.t_starts, intervals.t_ends      # == vals[is_left], vals[is_right] (occ_grid.py:188-189)
         ray_indices, packed_info = samples.ray_indices, samples.packed_info
         if (alpha_thre > 0.0 or early_stop_eps > 0.0) and (sigma_fn is not None or alpha_fn is not None):
             alpha_thre = min(alpha_thre, self.occs.mean().item())

@@ -93,12 +93,14 @@ def test_render_tail_vs_oracle_and_autograd(cuda, oracle):
     ref = oracle.render_from_density(t0, t1, sig, pk, rgb)
     tt0, tt1, tsig, trgb, tri, tpk = (T(x, cuda) for x in (t0, t1, sig, rgb, ri, pk))
     w, tr, al = N.render_weight_from_density(tt0, tt1, tsig, ray_indices=tri, n_rays=len(o))
-    np.testing.assert_allclose(w.cpu().numpy(), ref["weights"], rtol=1e-6, atol=1e-7)
-    np.testing.assert_allclose(tr.cpu().numpy(), ref["trans"], rtol=1e-6, atol=1e-7)
-    np.testing.assert_allclose(al.cpu().numpy(), ref["alphas"], rtol=1e-6, atol=1e-7)
+    # (the oracle sums a ray sequentially, the kernel in a fixed 32-wide shuffle tree, the reference in its own smem tree:
+    #  1e-5, the contract for fp32 results)
+    np.testing.assert_allclose(w.cpu().numpy(), ref["weights"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(tr.cpu().numpy(), ref["trans"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(al.cpu().numpy(), ref["alphas"], rtol=1e-5, atol=1e-7)
     col, op, dep = N.render_fused(tt0, tt1, tsig, trgb, tpk)
-    np.testing.assert_allclose(col.cpu().numpy(), ref["colors"], rtol=1e-6, atol=1e-6)
-    np.testing.assert_allclose(op[:, 0].cpu().numpy(), ref["opacities"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(col.cpu().numpy(), ref["colors"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(op[:, 0].cpu().numpy(), ref["opacities"], rtol=1e-5, atol=1e-6)
     # rendering(): patched 3-tuple callback, extras, background
     def rgb_sigma_fn(a, b, r):
         return trgb, tsig, torch.zeros(len(a), 3, device=cuda)

@@ -134,6 +134,7 @@ def test_caches_follow_fused_optimizers(cuda):
     def render():
         return render_image_with_occgrid(field, est, rays, render_step_size=5e-3, render_bkgd=bk)[0]
 
+    first = None
     for _ in range(3):
         field.train()
         opt.zero_grad(set_to_none=True)
@@ -144,7 +145,9 @@ def test_caches_follow_fused_optimizers(cuda):
             got = render()                                   # through the caches
             field.invalidate_caches()
             want = render()                                  # everything re-packed from the parameters
-        assert torch.equal(got, want)
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)   # (index_add_ accumulation order is not fixed)
+        assert float((got - first).abs().max()) > 1e-3 if first is not None else True
+        first = got if first is None else first
 
 
 def test_train_step_with_rate_term(cuda):

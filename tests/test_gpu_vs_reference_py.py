@@ -142,6 +142,48 @@ def test_field_gradients_vs_reference_autograd(cuda, ref):
     assert max(stats.values()) <= 1e-4, stats
 
 
+def test_train_step_loss_curve_vs_reference_step(cuda, ref):
+    """TrainStep (fused forward/backward, table Adam with plane refresh, fused Adam for the MLPs) against the training
+    script's step (train_CNC_nerf_synthetic.py:302-366) around the reference's own field, estimator, renderer and torch Adam
+    on the same closed-form scene, same seed, same initial weights: the losses of the first steps agree to 1 %, later ones
+    statistically (Adam's early steps are sign-like: rounding-level gradient differences flip individual updates)."""
+    from test_gpu_train import _scene
+
+    from cnc_b200.trainer import TrainStep
+
+    field, est, rays, pixels = _scene(cuda)
+    theirs = ref.ngp.NGPRadianceField_mygrid_2D3D(aabb=AABB, n_features_per_level=8, n_neurons=160, resolutions_list=R3,
+                                                  log2_hashmap_size=19, resolutions_list_2D=R2, log2_hashmap_size_2D=17, ste_binary=True).to(cuda)
+    theirs.load_state_dict(field.state_dict(), strict=False)
+    est_r = ref.nerfacc.OccGridEstimator(roi_aabb=AABB, resolution=128, levels=1).to(cuda)
+    est_r.binaries, est_r.occs = est.binaries.clone(), est.occs.clone()
+    import datasets.utils as du
+
+    rays_r = du.Rays(origins=rays.origins, viewdirs=rays.viewdirs)
+    bk = torch.zeros(3, device=cuda)
+    lr, steps = 2e-3, 40
+    ts = TrainStep(field, est, lr=lr, weight_decay=2e-6)
+    opt = torch.optim.Adam(theirs.parameters(), lr=lr, eps=1e-15, weight_decay=2e-6)
+    ours, want = [], []
+    theirs.train(); est_r.train()
+    for k in range(steps):
+        torch.manual_seed(100 + k)                      # the stratified jitter of the sampler (occ_grid.py:172-173)
+        ours.append(float(ts(rays, pixels, render_bkgd=bk, refresh_occupancy=False)[0]))
+        torch.manual_seed(100 + k)
+        rgb, _, _, n = ref.utils.render_image_with_occgrid(theirs, est_r, rays_r, render_step_size=5e-3, render_bkgd=bk)
+        loss = torch.nn.functional.mse_loss(rgb, pixels)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        want.append(float(loss))
+    print("loss ours     ", [round(x, 5) for x in ours[:8]], "...", [round(x, 5) for x in ours[-3:]])
+    print("loss reference", [round(x, 5) for x in want[:8]], "...", [round(x, 5) for x in want[-3:]])
+    for k in range(6):
+        assert abs(ours[k] - want[k]) <= 0.01 * want[k], (k, ours[k], want[k])
+    assert ours[-1] < 0.1 * ours[0] and want[-1] < 0.1 * want[0]
+    assert 0.5 < np.mean(ours[-5:]) / np.mean(want[-5:]) < 2.0
+
+
 # ================================================================================================ codec
 SMALL = dict(res3=[18, 33, 59, 108, 201, 514], log2T=17, res2=[130, 258, 514], log2T2=14, skip3=(0, 1, 2), radius=0.45)
 PRODUCT = dict(res3=R3, log2T=19, res2=R2, log2T2=17, skip3=(0, 1, 2), radius=0.5)
