@@ -593,6 +593,14 @@ def train_bench(arm, rank, world, steps, field):
                               "rays_per_s": H * W / (ms_img * 1e-3), "samples_per_s": n_tot / (ms_img * 1e-3),
                               "mean_opacity": float(opa.mean())}
         if ours:
+            arm.render_test(1024, field, est, img, device_loop=False, **kw)
+            torch.cuda.synchronize()
+            e0.record()
+            arm.render_test(1024, field, est, img, device_loop=False, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            out["test_render"]["host_loop_ms_per_image"] = e0.elapsed_time(e1)
+            out["test_render"]["what"] += "; sync-free device loop (wf_* kernels + cnc_field_fwd_n), host_loop_ms = the python loop on the same kernels"
             arm.render_test(1024, field, est, img, samples_per_round=32, **kw)
             torch.cuda.synchronize()
             e0.record()

@@ -153,6 +153,7 @@ struct FieldArgs {
     float *sv_h3;  // [N,160] relu(L3)
     float *sv_h4;  // [N,160] relu(L4)
     uint32_t N;
+    const uint32_t *n_dev;    // nullable: the sample count lives in device memory (<= N; wavefront renderer, no host sync)
     unsigned long long *dbg;  // optional timeline buffer (cnc_field_set_timeline_buffer), see DESIGN.md
 };
 
@@ -397,7 +398,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
     if (*tmem_slot != 0u) __trap();
     constexpr uint32_t tbase = 0u;
 
-    const uint32_t ntiles = (a.N + TILE_M - 1) / TILE_M;
+    const uint32_t Nrt = a.n_dev ? min(__ldg(a.n_dev), a.N) : a.N;
+    const uint32_t ntiles = (Nrt + TILE_M - 1) / TILE_M;
     const uint32_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (warp == MMA_WARP) {
@@ -533,7 +535,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
         // normalised position of this thread's row in tile `tile` (ngp.py:517-518)
         auto load_pos = [&](uint32_t tile, float (&p)[3]) {
             const uint32_t row = tile * TILE_M + r;
-            const bool live = row < a.N;
+            const bool live = row < Nrt;
             if (POLL) {   // the samples of this wave are being uploaded while earlier waves are evaluated
                 const uint32_t *flag = a.ready + tile / gridDim.x;
                 uint32_t v, spins = 0;
@@ -569,7 +571,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             }
         };
         auto publish = [&](int c, uint32_t prow, const float (&f)[8]) {  // 8 feature values -> smem slot -> MMA warp
-            if (SAVE && prow < a.N) {   // column 255 (K padding, weight 0) is saved as 1: its weight-gradient row is the bias gradient
+            if (SAVE && prow < Nrt) {   // column 255 (K padding, weight 0) is saved as 1: its weight-gradient row is the bias gradient
                 float *d = a.sv_x0 + (size_t)prow * 256 + 32 * c + 8 * q;
                 *reinterpret_cast<float4 *>(d) = make_float4(f[0], f[1], f[2], f[3]);
                 *reinterpret_cast<float4 *>(d + 4) = make_float4(f[4], f[5], f[6], (c == 7 && q == 3) ? 1.0f : f[7]);
@@ -640,7 +642,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
         for (uint32_t it = 0; it < my_tiles; it++) {
             const uint32_t tile = blockIdx.x + it * gridDim.x;
             const uint32_t row = tile * TILE_M + r;
-            const bool live = row < a.N;
+            const bool live = row < Nrt;
             const bool sel = (x[0] > 0.f) && (x[0] < 1.f) && (x[1] > 0.f) && (x[1] < 1.f) && (x[2] > 0.f) && (x[2] < 1.f);
             const bool has_next = it + 1 < my_tiles;
             if (threadIdx.x == 0) CNC_TL(0);
@@ -862,7 +864,7 @@ static int field_fwd_impl(const float *pos, const float *dirs, const float *aabb
                           const int32_t *resolutions3, const int32_t *offsets2, const int32_t *resolutions2,
                           const float *blob, float *sigma, float *rgb, float *geo, float *sv_x0, float *sv_h1, float *sv_h3,
                           float *sv_h4, uint32_t N, cnc_stream_t stream, const uint32_t *ready = nullptr, uint32_t *done = nullptr,
-                          uint32_t epoch = 0) {
+                          uint32_t epoch = 0, const uint32_t *n_dev = nullptr) {
     if (N == 0) return CNC_OK;
     if (!pos || !aabb6_host || !bits_xyz || !bits_xy || !bits_xz || !bits_yz || !offsets3 || !resolutions3 ||
         !offsets2 || !resolutions2 || !blob || !sigma || (dirs && !rgb)) {
@@ -906,7 +908,7 @@ static int field_fwd_impl(const float *pos, const float *dirs, const float *aabb
     a.offs3 = offsets3; a.res3 = resolutions3; a.offs2 = offsets2; a.res2 = resolutions2;
     a.blob = blob; a.sigma = sigma; a.rgb = rgb; a.geo = geo; a.N = N; a.dbg = g_timeline;
     a.sv_x0 = sv_x0; a.sv_h1 = sv_h1; a.sv_h3 = sv_h3; a.sv_h4 = sv_h4;
-    a.ready = ready; a.done = done; a.epoch = epoch;
+    a.ready = ready; a.done = done; a.epoch = epoch; a.n_dev = n_dev;
     const uint32_t ntiles = (N + ff::TILE_M - 1) / ff::TILE_M;
     uint32_t grid = ntiles < (uint32_t)n_sm ? ntiles : (uint32_t)n_sm;
     if (const char *g = getenv("CNC_FIELD_GRID")) { const uint32_t v = (uint32_t)atoi(g); if (v >= 1 && v < grid) grid = v; }  // profiling aid
@@ -923,6 +925,18 @@ int cnc_field_fwd(const float *pos, const float *dirs, const float *aabb6_host, 
                   const float *blob, float *sigma, float *rgb, float *geo, uint32_t N, cnc_stream_t stream) {
     return field_fwd_impl(pos, dirs, aabb6_host, bits_xyz, bits_xy, bits_xz, bits_yz, offsets3, resolutions3, offsets2,
                           resolutions2, blob, sigma, rgb, geo, nullptr, nullptr, nullptr, nullptr, N, stream);
+}
+
+/* The same forward with the sample count read from device memory at kernel start (*n_dev, clamped to n_max): the caller
+ * of a wavefront loop whose per-round sample count is produced on the device launches it without knowing the count. */
+int cnc_field_fwd_n(const float *pos, const float *dirs, const float *aabb6_host, const uint8_t *bits_xyz,
+                    const uint8_t *bits_xy, const uint8_t *bits_xz, const uint8_t *bits_yz, const int32_t *offsets3,
+                    const int32_t *resolutions3, const int32_t *offsets2, const int32_t *resolutions2,
+                    const float *blob, float *sigma, float *rgb, const uint32_t *n_dev, uint32_t n_max, cnc_stream_t stream) {
+    if (!n_dev) { set_error("field_fwd_n: null count pointer"); return CNC_EINVAL; }
+    return field_fwd_impl(pos, dirs, aabb6_host, bits_xyz, bits_xy, bits_xz, bits_yz, offsets3, resolutions3, offsets2,
+                          resolutions2, blob, sigma, rgb, nullptr, nullptr, nullptr, nullptr, nullptr, n_max, stream, nullptr,
+                          nullptr, 0, n_dev);
 }
 
 /* Host-buffer entry point, ONE launch of the persistent kernel: the samples are uploaded in chunks of whole waves

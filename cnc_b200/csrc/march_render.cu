@@ -82,32 +82,16 @@ struct MarchArgs {
     float *terminate;             // nullable: where the march of the ray stopped
 };
 
-// grid.cu:68-318 with the interval edges folded into (t_start, t_end) per sample.  The walk of a ray is one sequential
-// chain (t += dt in fp32, DDA boundaries tdist += delta: both defined by their rounding sequence) with nested
-// data-dependent loops.  RAY_PER_WARP: lane 0 of every warp walks one ray and the other lanes retire at once -- with
-// 32 rays per warp the warp executes the UNION of 32 different loop nests (measured: 292 us for 1100 rays, ten times one
-// ray's chain); a training batch has a few thousand rays, far fewer than the machine has warp slots.  Large batches
-// (test-time wavefronts of 10^5..10^6 rays with a step limit) keep one thread per ray.
-template <bool RAY_PER_WARP>
-__global__ void __launch_bounds__(128) traverse_kernel(const MarchArgs a) {
-    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (RAY_PER_WARP) {
-        if (threadIdx.x & 31) return;
-        tid >>= 5;
-    }
-    if (tid >= a.n_rays) return;
-    if (a.rays_mask && !a.rays_mask[tid]) {
-        if (a.cnt) a.cnt[tid] = 0;
-        return;
-    }
+// The walk of one ray: grid.cu:68-318 with the interval edges folded into (t_start, t_end) per sample.  `emit(j, t0, t1)`
+// receives sample j; returns the number of samples and leaves the stopping point of the march in t_end.
+template <class Emit>
+__device__ __forceinline__ int64_t march_ray(const MarchArgs &a, int64_t tid, float near, float far, int32_t steps_limit, Emit emit,
+                                             float &t_end) {
     const float eps = 1e-6f;
-    const bool fill = a.t_starts != nullptr;
     const float o[3] = {a.rays_o[tid * 3], a.rays_o[tid * 3 + 1], a.rays_o[tid * 3 + 2]};
     const float d[3] = {a.rays_d[tid * 3], a.rays_d[tid * 3 + 1], a.rays_d[tid * 3 + 2]};
     const float inv[3] = {__fdiv_rn(1.0f, d[0]), __fdiv_rn(1.0f, d[1]), __fdiv_rn(1.0f, d[2])};
-    const float near = a.near_planes[tid], far = a.far_planes[tid];
     int64_t n_samples = 0;
-    const int64_t start = a.chunk_starts ? a.chunk_starts[tid] : 0;
     float t_last = near;
     bool continuous = false;
     const int64_t bh = tid * a.n_grids, bt = tid * a.n_grids * 2;
@@ -152,7 +136,7 @@ __global__ void __launch_bounds__(128) traverse_kernel(const MarchArgs a) {
             delta[k] = (d[k] == 0.0f) ? this_tmax : __fmul_rn(__fmul_rn(vox, inv[k]), sf);
             over[k] = fin + step[k];
         }
-        while (a.steps_limit <= 0 || n_samples < a.steps_limit) {
+        while (steps_limit <= 0 || n_samples < steps_limit) {
             const float t_trav = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), this_tmax);
             const int64_t cell = (int64_t)cur[0] * a.ry * a.rz + (int64_t)cur[1] * a.rz + cur[2] + level * (int64_t)a.rx * a.ry * a.rz;
             if (!a.binaries[cell]) {
@@ -163,7 +147,7 @@ __global__ void __launch_bounds__(128) traverse_kernel(const MarchArgs a) {
                 }
                 continuous = false;
             } else {
-                while (a.steps_limit <= 0 || n_samples < a.steps_limit) {
+                while (steps_limit <= 0 || n_samples < steps_limit) {
                     float t_next;
                     if (a.step_size <= 0.0f) t_next = t_trav;
                     else {
@@ -171,11 +155,7 @@ __global__ void __launch_bounds__(128) traverse_kernel(const MarchArgs a) {
                         if (__fmaf_rn(dt, 0.5f, t_last) >= t_trav) break;
                         t_next = __fadd_rn(t_last, dt);
                     }
-                    if (fill) {
-                        a.t_starts[start + n_samples] = t_last;
-                        a.t_ends[start + n_samples] = t_next;
-                        a.ray_idx[start + n_samples] = tid;
-                    }
+                    emit(n_samples, t_last, t_next);
                     n_samples++;
                     continuous = true;
                     t_last = t_next;
@@ -196,6 +176,38 @@ __global__ void __launch_bounds__(128) traverse_kernel(const MarchArgs a) {
             if (done) break;
         }
     }
+    t_end = t_last;
+    return n_samples;
+}
+
+// RAY_PER_WARP: lane 0 of every warp walks one ray and the other lanes retire at once -- the walk is one sequential chain
+// (t += dt in fp32, DDA boundaries tdist += delta: both defined by their rounding sequence) with nested data-dependent
+// loops, and with 32 rays per warp the warp executes the UNION of 32 different loop nests (measured: 292 us for 1100
+// rays, ten times one ray's chain); a training batch has a few thousand rays, far fewer than the machine has warp slots.
+// Large batches (test-time wavefronts of 10^5..10^6 rays with a step limit) keep one thread per ray.
+template <bool RAY_PER_WARP>
+__global__ void __launch_bounds__(128) traverse_kernel(const MarchArgs a) {
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (RAY_PER_WARP) {
+        if (threadIdx.x & 31) return;
+        tid >>= 5;
+    }
+    if (tid >= a.n_rays) return;
+    if (a.rays_mask && !a.rays_mask[tid]) {
+        if (a.cnt) a.cnt[tid] = 0;
+        return;
+    }
+    const bool fill = a.t_starts != nullptr;
+    const int64_t start = a.chunk_starts ? a.chunk_starts[tid] : 0;
+    float t_last;
+    const int64_t n_samples = march_ray(a, tid, a.near_planes[tid], a.far_planes[tid], a.steps_limit,
+                                        [&](int64_t j, float t0, float t1) {
+                                            if (fill) {
+                                                a.t_starts[start + j] = t0;
+                                                a.t_ends[start + j] = t1;
+                                                a.ray_idx[start + j] = tid;
+                                            }
+                                        }, t_last);
     if (a.terminate) a.terminate[tid] = t_last;
     if (a.cnt) a.cnt[tid] = n_samples;
 }
@@ -291,6 +303,156 @@ render_density_kernel(const float *__restrict__ t0, const float *__restrict__ t1
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Test-time wavefront renderer without host round trips (examples/utils.py:395-479).  One round = wf_begin -> wf_march ->
+// field forward (cnc_field_fwd_n, sample count read from `st`) -> wf_composite; everything the reference's python loop
+// decides on the host per round (number of live rays -> samples per ray of the round, the stop conditions) lives in `st`.
+// st[0] live rays of this round   st[1] samples per ray of this round   st[2] iter_samples   st[3] done
+// st[4] samples marched this round (atomic cursor)   st[5] live rays after this round   st[6] rounds   st[8..9] total samples (u64)
+// ------------------------------------------------------------------------------------------
+__global__ void wf_begin_kernel(uint32_t *__restrict__ st, uint32_t n_rays, uint32_t min_samples, uint32_t max_samples) {
+    st[4] = 0;
+    if (st[3]) return;
+    const uint32_t alive = st[5];
+    if (alive == 0 || st[2] >= max_samples) {   // utils.py:395-399
+        st[3] = 1;
+        return;
+    }
+    uint32_t n = n_rays / alive;
+    n = n < 64u ? n : 64u;
+    n = n > min_samples ? n : min_samples;       // utils.py:402
+    st[0] = alive;
+    st[1] = n;
+    st[2] += n;
+    st[5] = 0;
+    st[6] += 1;
+}
+
+struct WaveArgs {
+    MarchArgs m;               // rays, grids, precomputed intersections; near_planes = the running planes (updated in place)
+    uint32_t *st;
+    uint8_t *ray_mask;         // [n_rays] live flags (updated by wf_composite)
+    float *near_planes;        // [n_rays]
+    uint32_t capacity;         // sample slots of the round buffers
+    // per-ray outputs of the march
+    uint32_t *ray_base, *ray_cnt;
+    float *ray_term;
+    // per-sample outputs of the march = inputs of the field kernel and of the compositing
+    float *t0, *t1, *pos, *dir;
+};
+
+// one thread per ray: count the samples of the round, reserve their slots (warp-aggregated atomic), march again writing
+// them.  The walk itself is march_ray, i.e. the sample placement of traverse_grids bit for bit.
+__global__ void __launch_bounds__(128) wf_march_kernel(const WaveArgs w) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (w.st[3]) return;
+    const int32_t limit = (int32_t)w.st[1];
+    const bool live = tid < w.m.n_rays && w.ray_mask[tid];
+    float near = 0.f, far = 0.f, t_end = 0.f;
+    uint32_t cnt = 0;
+    if (live) {
+        near = w.near_planes[tid];
+        far = w.m.far_planes[tid];
+        cnt = (uint32_t)march_ray(w.m, tid, near, far, limit, [](int64_t, float, float) {}, t_end);
+    }
+    // slots: exclusive prefix inside the warp + one atomic per warp
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += o;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total) base = atomicAdd(w.st + 4, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+    if (!live) return;
+    w.ray_base[tid] = base;
+    w.ray_cnt[tid] = cnt;
+    w.ray_term[tid] = t_end;
+    if (cnt == 0 || base + cnt > w.capacity) return;   // (capacity is sized for the schedule: n_live * n <= n_rays * min_samples)
+    const float o[3] = {w.m.rays_o[tid * 3], w.m.rays_o[tid * 3 + 1], w.m.rays_o[tid * 3 + 2]};
+    const float d[3] = {w.m.rays_d[tid * 3], w.m.rays_d[tid * 3 + 1], w.m.rays_d[tid * 3 + 2]};
+    float dummy;
+    march_ray(w.m, tid, near, far, limit, [&](int64_t j, float ta, float tb) {
+        const uint32_t k = base + (uint32_t)j;
+        w.t0[k] = ta;
+        w.t1[k] = tb;
+        // positions = origins + dirs * (t_starts + t_ends) / 2 (utils.py:350-352): add, multiply by the direction, divide, add
+        const float ts = __fadd_rn(ta, tb);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            w.pos[k * 3 + c] = __fadd_rn(o[c], __fdiv_rn(__fmul_rn(d[c], ts), 2.0f));
+            w.dir[k * 3 + c] = d[c];
+        }
+    }, dummy);
+}
+
+struct CompArgs {
+    uint32_t *st;
+    uint8_t *ray_mask;
+    float *near_planes;
+    const uint32_t *ray_base, *ray_cnt;
+    const float *ray_term, *t0, *t1, *sigma, *rgbs;
+    float *rgb, *opacity, *depth;   // [n_rays,3], [n_rays], [n_rays] accumulators
+    int64_t n_rays;
+    uint32_t capacity;
+    float alpha_thre, opc_thre;
+};
+
+// one thread per ray: weights of the round's samples with the ray's running transmittance as prefix
+// (render_weight_from_density(prefix_trans=1-opacity), utils.py:436-443), accumulation into the image buffers
+// (accumulate_along_rays_ x3, :454-471), new near plane, new live flag (:473-478)
+__global__ void __launch_bounds__(128) wf_composite_kernel(const CompArgs a) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.st[3]) return;
+    const bool live = tid < a.n_rays && a.ray_mask[tid];
+    bool stay = false;
+    uint32_t cnt = 0, n_vis = 0;
+    if (live) {
+        cnt = a.ray_cnt[tid];
+        const uint32_t base = a.ray_base[tid];
+        const float op0 = a.opacity[tid];
+        const float prefix = __fsub_rn(1.0f, op0);
+        float acc = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, op = 0.f, dp = 0.f;
+        if (base + cnt <= a.capacity) {
+            for (uint32_t j = 0; j < cnt; j++) {
+                const uint32_t i = base + j;
+                const float ta = a.t0[i], tb = a.t1[i];
+                const float sd = __fmul_rn(a.sigma[i], __fsub_rn(tb, ta));
+                const float al = __fsub_rn(1.0f, expf(-sd));
+                const float w = __fmul_rn(__fmul_rn(expf(-acc), prefix), al);
+                acc = __fadd_rn(acc, sd);
+                if (a.alpha_thre > 0.f && !(al >= a.alpha_thre)) continue;   // vis_mask (utils.py:444-452)
+                n_vis++;
+                cr = __fadd_rn(cr, __fmul_rn(w, a.rgbs[i * 3 + 0]));
+                cg = __fadd_rn(cg, __fmul_rn(w, a.rgbs[i * 3 + 1]));
+                cb = __fadd_rn(cb, __fmul_rn(w, a.rgbs[i * 3 + 2]));
+                op = __fadd_rn(op, w);
+                dp = __fadd_rn(dp, __fmul_rn(w, __fdiv_rn(__fadd_rn(ta, tb), 2.0f)));
+            }
+        }
+        a.rgb[tid * 3 + 0] = __fadd_rn(a.rgb[tid * 3 + 0], cr);
+        a.rgb[tid * 3 + 1] = __fadd_rn(a.rgb[tid * 3 + 1], cg);
+        a.rgb[tid * 3 + 2] = __fadd_rn(a.rgb[tid * 3 + 2], cb);
+        const float op1 = __fadd_rn(op0, op);
+        a.opacity[tid] = op1;
+        a.depth[tid] = __fadd_rn(a.depth[tid], dp);
+        a.near_planes[tid] = a.ray_term[tid];
+        stay = (op1 <= a.opc_thre) && (cnt == a.st[1]);
+        a.ray_mask[tid] = stay ? 1 : 0;
+    }
+    const uint32_t n_stay = __popc(__ballot_sync(0xffffffffu, stay));
+    uint32_t c = n_vis;                      // total_samples counts what is accumulated (utils.py:479)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31u) == 0) {
+        if (n_stay) atomicAdd(a.st + 5, n_stay);
+        if (c) atomicAdd(reinterpret_cast<unsigned long long *>(a.st + 8), (unsigned long long)c);
+    }
+}
+
 }  // namespace mr
 }  // namespace cnc
 
@@ -330,6 +492,48 @@ int cnc_traverse_grids(const float *rays_o, const float *rays_d, const uint8_t *
     else
         mr::traverse_kernel<false><<<div_up((uint64_t)n_rays, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return check_launch("traverse_grids");
+}
+
+int cnc_wavefront_begin(uint32_t *state, uint32_t n_rays, uint32_t min_samples, uint32_t max_samples, cnc_stream_t stream) {
+    if (!state || n_rays == 0) { set_error("wavefront_begin: bad argument"); return CNC_EINVAL; }
+    mr::wf_begin_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(state, n_rays, min_samples < 1 ? 1 : min_samples, max_samples);
+    return check_launch("wavefront_begin");
+}
+
+int cnc_wavefront_march(const float *rays_o, const float *rays_d, int64_t n_rays, int32_t n_grids, int32_t rx, int32_t ry, int32_t rz,
+                        const uint8_t *binaries, const float *aabbs, const uint8_t *hits, const float *t_sorted,
+                        const int64_t *t_indices, const float *far_planes, float step_size, float cone_angle, uint32_t *state,
+                        uint8_t *ray_mask, float *near_planes, uint32_t capacity, uint32_t *ray_base, uint32_t *ray_cnt,
+                        float *ray_term, float *t0, float *t1, float *pos, float *dirs, cnc_stream_t stream) {
+    if (n_rays == 0) return CNC_OK;
+    if (!rays_o || !rays_d || !binaries || !aabbs || !hits || !t_sorted || !t_indices || !far_planes || !state || !ray_mask ||
+        !near_planes || !ray_base || !ray_cnt || !ray_term || !t0 || !t1 || !pos || !dirs) {
+        set_error("wavefront_march: null pointer");
+        return CNC_EINVAL;
+    }
+    mr::WaveArgs w;
+    w.m = mr::MarchArgs{rays_o, rays_d, nullptr, n_rays, n_grids, rx, ry, rz, binaries, aabbs, hits, t_sorted, t_indices,
+                        near_planes, far_planes, step_size, cone_angle, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    w.st = state; w.ray_mask = ray_mask; w.near_planes = near_planes; w.capacity = capacity;
+    w.ray_base = ray_base; w.ray_cnt = ray_cnt; w.ray_term = ray_term; w.t0 = t0; w.t1 = t1; w.pos = pos; w.dir = dirs;
+    mr::wf_march_kernel<<<div_up((uint64_t)n_rays, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(w);
+    return check_launch("wavefront_march");
+}
+
+int cnc_wavefront_composite(uint32_t *state, uint8_t *ray_mask, float *near_planes, const uint32_t *ray_base, const uint32_t *ray_cnt,
+                            const float *ray_term, const float *t0, const float *t1, const float *sigma, const float *rgbs,
+                            float *rgb, float *opacity, float *depth, int64_t n_rays, uint32_t capacity, float alpha_thre,
+                            float opc_thre, cnc_stream_t stream) {
+    if (n_rays == 0) return CNC_OK;
+    if (!state || !ray_mask || !near_planes || !ray_base || !ray_cnt || !ray_term || !t0 || !t1 || !sigma || !rgbs || !rgb ||
+        !opacity || !depth) {
+        set_error("wavefront_composite: null pointer");
+        return CNC_EINVAL;
+    }
+    mr::CompArgs a{state, ray_mask, near_planes, ray_base, ray_cnt, ray_term, t0, t1, sigma, rgbs, rgb, opacity, depth, n_rays,
+                   capacity, alpha_thre, opc_thre};
+    mr::wf_composite_kernel<<<div_up((uint64_t)n_rays, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("wavefront_composite");
 }
 
 int cnc_packed_scan(const float *in, const int64_t *packed_info, int64_t n_rays, float *out, int32_t op, int32_t inclusive,

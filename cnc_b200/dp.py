@@ -139,52 +139,86 @@ class ShardedTableAdam:
             return 0
         return sum(4 * t["n_main"] + 4 * (t["n"] - t["n_main"]) + 2 * t["S"] // 8 for t in self.tables)
 
-    @torch.no_grad()
-    def step(self) -> None:
-        from .train_ops import adam_planes, surrogate_fill
+    def _batched(self):
+        """context that turns the collectives issued inside it into ONE NCCL group launch (gloo: issued one by one)"""
+        import contextlib
 
-        self.step_id += 1
-        W, pend = self.world, []
+        if self.world > 1 and dist.get_backend(self.group) == "nccl":
+            return dist._coalescing_manager(group=self.group, async_ops=True)
+        return contextlib.nullcontext()
+
+    @torch.no_grad()
+    def exchange(self):
+        """launch the gradient exchange (asynchronous): reduce-scatter of every table's rows, one small all-reduce of the
+        replicated tails.  Returns what `apply` needs."""
+        W, works, parts = self.world, [], []
+        tails = []
         for t in self.tables:
             p = t["p"]
-            g = p.grad if p.grad is not None else torch.zeros_like(p)
-            g = g.contiguous().view(-1)
-            if W > 1:
-                gs = torch.empty(t["S"], device=g.device)
-                w1 = dist.reduce_scatter_tensor(gs, g[:t["n_main"]], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
-                gt = g[t["n_main"]:].clone()
-                w2 = dist.all_reduce(gt, op=dist.ReduceOp.AVG, group=self.group, async_op=True) if gt.numel() else None
-                pend.append((gs, gt, w1, w2, g))   # (g is kept alive until the collective has read it)
-            else:
-                pend.append((g[:t["n_main"]], g[t["n_main"]:], None, None, g))
-        gathers = []
-        for t, (gs, gt, w1, w2, _) in zip(self.tables, pend):
-            if w1 is not None:
-                w1.wait()
-            if w2 is not None:
-                w2.wait()
+            g = (p.grad if p.grad is not None else torch.zeros_like(p)).contiguous().view(-1)
+            gs = torch.empty(t["S"], device=g.device) if W > 1 else g[:t["n_main"]]
+            parts.append((g, gs))
+            tails.append(g[t["n_main"]:])
+        tail = torch.cat(tails) if sum(x.numel() for x in tails) else None
+        if W > 1:
+            with self._batched() as cm:
+                for t, (g, gs) in zip(self.tables, parts):
+                    w = dist.reduce_scatter_tensor(gs, g[:t["n_main"]], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+                    if cm is None:
+                        works.append(w)
+            if cm is not None:
+                works.append(cm)
+            if tail is not None:
+                works.append(dist.all_reduce(tail, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        return works, parts, tail
+
+    @torch.no_grad()
+    def apply(self, exchanged) -> None:
+        """Adam on the owned rows (+ the replicated tails), bit planes to everybody, stand-ins for the rows owned elsewhere"""
+        from .train_ops import adam_planes, surrogate_fill
+
+        works, parts, tail = exchanged
+        for w in works:
+            w.wait()
+        self.step_id += 1
+        W, off = self.world, 0
+        kw = dict(step=self.step_id, lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
+        sends = []
+        for t, (g, gs) in zip(self.tables, parts):
             flat = t["p"].detach().view(-1)
             lo, hi, nm = t["lo"], t["hi"], t["n_main"]
-            kw = dict(step=self.step_id, lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
             adam_planes(flat[lo:hi], gs, t["m"], t["v"], sign=t["sign"][lo // 8:hi // 8], mask=t["mask"][lo // 8:hi // 8], **kw)
             if t["n"] > nm:
-                adam_planes(flat[nm:], gt, t["tm"], t["tv"], sign=t["sign"][nm // 8:], mask=t["mask"][nm // 8:], **kw)
+                gt = tail[off:off + t["n"] - nm]
+                off += t["n"] - nm
+                adam_planes(flat[nm:], gt.contiguous(), t["tm"], t["tv"], sign=t["sign"][nm // 8:], mask=t["mask"][nm // 8:], **kw)
             if W > 1:
                 for plane in (t["sign"], t["mask"]):
-                    mine = plane[lo // 8:hi // 8].clone()
-                    gathers.append(dist.all_gather_into_tensor(plane[:nm // 8], mine, group=self.group, async_op=True))
-        for w in gathers:
-            w.wait()
+                    sends.append((plane[:nm // 8], plane[lo // 8:hi // 8].clone()))
+        if W > 1:
+            works = []
+            with self._batched() as cm:
+                for out, mine in sends:
+                    w = dist.all_gather_into_tensor(out, mine, group=self.group, async_op=True)
+                    if cm is None:
+                        works.append(w)
+            if cm is not None:
+                works.append(cm)
+            for w in works:
+                w.wait()
         for t, enc in zip(self.tables, self.encoders):
             p = t["p"]
             if W > 1:
-                tail = p.detach().view(-1)[t["n_main"]:].clone()
+                keep = p.detach().view(-1)[t["n_main"]:].clone()
                 surrogate_fill(p.detach().view(-1), t["sign"], t["mask"], t["lo"], t["hi"])
-                p.detach().view(-1)[t["n_main"]:] = tail
+                p.detach().view(-1)[t["n_main"]:] = keep
             torch.autograd.graph.increment_version(p)         # the kernels wrote through raw pointers
             cache = getattr(enc, "_sign_cache", None)
             if cache is not None and p.is_cuda:               # the next forward gathers from this plane: no repack pass
                 cache.publish(p, t["sign"])
+
+    def step(self) -> None:
+        self.apply(self.exchange())
 
     @torch.no_grad()
     def sync_params(self) -> None:

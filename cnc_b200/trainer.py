@@ -65,6 +65,30 @@ class TrainStep:
             return n_samples > 0
         return allreduce_scalar(float(n_samples), device, op=dist.ReduceOp.MIN) > 0
 
+    def _vote_async(self, n_samples: int, device):
+        """start the all-ranks minimum of the sample count; `_vote_result` reads it later without stalling the launch
+        queue: the result is copied to pinned memory on a side stream, and only that copy's event is waited for"""
+        if self.world == 1 or device.type != "cuda":
+            return n_samples
+        if getattr(self, "_vote_stream", None) is None:
+            self._vote_stream = torch.cuda.Stream(device)
+            self._vote_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        flag = torch.tensor([n_samples], dtype=torch.int64).pin_memory().to(device, non_blocking=True)
+        self._vote_stream.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(self._vote_stream):
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            self._vote_host.copy_(flag, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._vote_stream)
+        flag.record_stream(self._vote_stream)
+        return ev
+
+    def _vote_result(self, vote) -> bool:
+        if isinstance(vote, int):
+            return vote > 0
+        vote.synchronize()
+        return int(self._vote_host[0]) > 0
+
     def __call__(self, rays: Rays, pixels: torch.Tensor, render_bkgd: Optional[torch.Tensor] = None, refresh_occupancy: bool = True):
         """returns (loss value tensor, number of rendered samples on this rank)"""
         self.field.train()
@@ -77,7 +101,11 @@ class TrainStep:
                 broadcast_module_buffers(self.estimator, ["occs", "binaries"], src=0)
         rgb, acc, depth, n_samples = render_image_with_occgrid(self.field, self.estimator, rays, render_step_size=self.render_step_size,
                                                                render_bkgd=render_bkgd)
-        if not self._everyone_has_samples(n_samples, pixels.device):   # train...:337-338, decided by all ranks together
+        # train...:337-338: a batch without samples skips the step.  Under data parallelism all ranks decide together; the
+        # vote travels while this rank goes on (a rank without samples contributes zero gradients to the collectives, which
+        # every rank issues in the same order either way) and is read just before the update is applied.
+        vote = self._vote_async(n_samples, pixels.device)
+        if self.world == 1 and n_samples == 0:
             self.step_id += 1
             return torch.zeros((), device=pixels.device), n_samples
         loss = F.mse_loss(rgb, pixels)   # train...:346
@@ -90,14 +118,22 @@ class TrainStep:
         if self.table_opt is not None:
             for t in self.table_opt.tables:
                 t["p"].grad = None
-        loss.backward()
+        if loss.requires_grad:           # (a data-parallel rank whose batch produced no sample still joins the collectives)
+            loss.backward()
         for g in self.optimizer.param_groups:
             g["lr"] = self.lr
+        exchanged = None
         if self.table_opt is not None:
             self.table_opt.lr = self.lr
-            self.table_opt.step()        # tables: reduce-scatter -> Adam on the owned rows -> bit planes all-gather
-        self.reducer.reduce()            # MLPs + context models: one small bucketed all-reduce
-        self.optimizer.step()
+            exchanged = self.table_opt.exchange()   # tables: reduce-scatter of the rows (asynchronous)
+        self.reducer.reduce()                       # MLPs + context models: one small bucketed all-reduce
+        if self._vote_result(vote):
+            if exchanged is not None:
+                self.table_opt.apply(exchanged)     # Adam on the owned rows -> bit planes all-gather -> stand-ins
+            self.optimizer.step()
+        elif exchanged is not None:
+            for w in exchanged[0]:
+                w.wait()
         self.step_id += 1
         return loss.detach(), n_samples
 

@@ -87,6 +87,33 @@ int cnc_sign_pack(const float *params, uint8_t *bits, uint64_t n, cnc_stream_t s
 int cnc_sign_unpack(const uint8_t *bits, float *out, uint64_t n, cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Test-time wavefront renderer without host round trips.
+ * replaces: the python loop of render_image_with_occgrid_test, examples/utils.py:395-479 (per round: ray_mask.sum().item(),
+ *           traverse_grids(over_allocate), boolean compactions, rgb_sigma_fn, render_weight_from_density, 3 x
+ *           accumulate_along_rays_, ray-mask update).
+ * `state` = 16 x u32 in device memory: [0] live rays of the round, [1] samples per ray of the round, [2] iter_samples,
+ * [3] done, [4] samples of the round (the count cnc_field_fwd_n reads), [5] live rays after the round (initialise to
+ * n_rays), [6] rounds, [8..9] total accumulated samples (u64).  One round = cnc_wavefront_begin -> cnc_wavefront_march
+ * (sample placement == traverse_grids, bit for bit; writes t0/t1/pos/dirs of the round's samples into `capacity` slots)
+ * -> cnc_field_fwd_n(pos, dirs, ..., n_dev = state + 4, n_max = capacity) -> cnc_wavefront_composite.  After `done` every
+ * kernel returns at once, so a caller may queue rounds in batches and look at state[3] between batches.
+ * ---------------------------------------------------------------------------------------- */
+int cnc_wavefront_begin(uint32_t *state, uint32_t n_rays, uint32_t min_samples, uint32_t max_samples, cnc_stream_t stream);
+int cnc_wavefront_march(const float *rays_o, const float *rays_d, int64_t n_rays, int32_t n_grids, int32_t rx, int32_t ry, int32_t rz,
+                        const uint8_t *binaries, const float *aabbs, const uint8_t *hits, const float *t_sorted,
+                        const int64_t *t_indices, const float *far_planes, float step_size, float cone_angle, uint32_t *state,
+                        uint8_t *ray_mask, float *near_planes, uint32_t capacity, uint32_t *ray_base, uint32_t *ray_cnt,
+                        float *ray_term, float *t0, float *t1, float *pos, float *dirs, cnc_stream_t stream);
+int cnc_wavefront_composite(uint32_t *state, uint8_t *ray_mask, float *near_planes, const uint32_t *ray_base, const uint32_t *ray_cnt,
+                            const float *ray_term, const float *t0, const float *t1, const float *sigma, const float *rgbs,
+                            float *rgb, float *opacity, float *depth, int64_t n_rays, uint32_t capacity, float alpha_thre,
+                            float opc_thre, cnc_stream_t stream);
+int cnc_field_fwd_n(const float *pos, const float *dirs, const float *aabb6_host, const uint8_t *bits_xyz,
+                    const uint8_t *bits_xy, const uint8_t *bits_xz, const uint8_t *bits_yz, const int32_t *offsets3,
+                    const int32_t *resolutions3, const int32_t *offsets2, const int32_t *resolutions2,
+                    const float *blob, float *sigma, float *rgb, const uint32_t *n_dev, uint32_t n_max, cnc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Inverse hash tables of the context model, pruned by the occupancy grid.
  * replaces: CNC_context_models.__init__ table construction, examples/utils_bpp_acc.py:294-335 (meshgrid of every level ->
  *           get_grid_index -> torch.sort of up to 135.8 M keys -> unique), followed at every encode/decode by

@@ -9,14 +9,16 @@ from cnc_b200.nerfacc import OccGridEstimator
 from cnc_b200.render import Rays
 from cnc_b200.trainer import TrainStep
 
-dev = torch.device("cuda:0")
-field = bench.build_field(dev)
-est = OccGridEstimator(roi_aabb=[-1.5] * 3 + [1.5] * 3, resolution=128, levels=1).to(dev)
-c = (torch.arange(128, device=dev) + 0.5) / 128 * 3 - 1.5
-X, Y, Z = torch.meshgrid(c, c, c, indexing="ij")
-est.binaries = (X * X + Y * Y + Z * Z <= 1.0).unsqueeze(0)
-est.occs = est.binaries.reshape(-1).float()
-g = torch.Generator(device="cpu").manual_seed(7)
+# (works under torchrun too: every rank trains its own ray shard, rank 0 prints)
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    torch.distributed.init_process_group("nccl", device_id=dev)
+arm = bench.Arm("ours", dev)
+field = arm.field(seed=0)
+est = arm.estimator()
+g = torch.Generator(device="cpu").manual_seed(7 + rank)
 n_rays = int(sys.argv[1]) if len(sys.argv) > 1 else 1100
 o = torch.randn(n_rays, 3, generator=g); o = o / o.norm(dim=-1, keepdim=True) * 4
 tgt = (torch.rand(n_rays, 3, generator=g) - 0.5) * 1.2
@@ -31,9 +33,14 @@ t = time.perf_counter()
 for _ in range(5):
     ts(rays, pixels, refresh_occupancy=False)
 torch.cuda.synchronize()
-print(f"samples {n_s}; wall {1e3 * (time.perf_counter() - t) / 5:.2f} ms/step")
+if rank == 0:
+    print(f"samples {n_s}; wall {1e3 * (time.perf_counter() - t) / 5:.2f} ms/step; world {world}")
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3):
         ts(rays, pixels, refresh_occupancy=False)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+if rank == 0:
+    print(prof.key_averages().table(sort_by=os.environ.get("SORT", "self_cuda_time_total"), row_limit=45, max_name_column_width=70))
+    print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=15, max_name_column_width=70))
+if world > 1:
+    torch.distributed.destroy_process_group()

@@ -236,3 +236,32 @@ def test_test_time_renderer_on_the_fused_field(cuda):
         diff = (w - f_).abs().amax(dim=-1)
         assert diff.max().item() < 4e-3
         assert torch.quantile(diff, 0.98).item() < 3e-4
+
+
+@pytest.mark.parametrize("cone,step,alpha_thre", [(0.0, 5e-3, 0.0), (4e-3, 1e-2, 0.0), (0.0, 5e-3, 1e-3)])
+def test_device_loop_equals_the_host_loop(cuda, cone, step, alpha_thre):
+    """the sync-free wavefront renderer (`device_loop=True`: wf_begin / wf_march / cnc_field_fwd_n / wf_composite queued in
+    batches) against the python loop of examples/utils.py:395-479 on the same kernels: the same rounds take the same
+    samples (total_samples equal), images to 1e-5; image-shaped rays, a dense trained-like field (weights scaled up so
+    that rays saturate and the early stop and the growing round size are exercised), a sample budget that cuts the loop."""
+    from test_gpu_field import make_field
+    from cnc_b200.render import Rays, render_image_with_occgrid_test
+
+    f = make_field(cuda).eval()
+    with torch.no_grad():
+        f.mlp_base.network[2].bias[0] += 4.0          # densities of e^3: opaque after a few dozen samples
+    f.invalidate_caches()
+    est = _ball_estimator(cuda, res=128)
+    o, d, _, _ = scene(n_rays=48 * 40, seed=6)
+    rays = Rays(origins=T(o, cuda).view(48, 40, 3), viewdirs=T(d, cuda).view(48, 40, 3))
+    kw = dict(render_step_size=step, render_bkgd=torch.ones(3, device=cuda), cone_angle=cone, alpha_thre=alpha_thre)
+    for budget in (1024, 24):
+        a = render_image_with_occgrid_test(budget, f, est, rays, device_loop=False, **kw)
+        b = render_image_with_occgrid_test(budget, f, est, rays, device_loop=True, rounds_per_check=7, **kw)
+        c = render_image_with_occgrid_test(budget, f, est, rays, **kw)                 # default: the device loop
+        assert a[3] == b[3] == c[3] > 0, (a[3], b[3], c[3])
+        for x, y, z in zip(a[:3], b[:3], c[:3]):
+            assert x.shape == y.shape
+            torch.testing.assert_close(y, x, rtol=1e-5, atol=2e-6)
+            assert torch.equal(y, z)
+    assert float(a[1].mean()) > 0.3 and float((a[1] > 1 - 1e-4).float().mean()) > 0.05   # rays did saturate
