@@ -148,26 +148,48 @@ class ShardedTableAdam:
         return contextlib.nullcontext()
 
     @torch.no_grad()
+    def contribute(self, k: int, grad: torch.Tensor) -> bool:
+        """hand over the COMPLETE gradient of table k as soon as it exists (called from inside backward): its
+        reduce-scatter starts at once and overlaps whatever backward still has to do.  Only valid when nothing else
+        contributes to that table's gradient in this step (no rate term); returns True = consumed (leave `.grad` empty)."""
+        if self.world == 1:
+            return False
+        t = self.tables[k]
+        g = grad.contiguous().view(-1)
+        gs = torch.empty(t["S"], device=g.device)
+        w = dist.reduce_scatter_tensor(gs, g[:t["n_main"]], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        self._early = getattr(self, "_early", {})
+        self._early[k] = (g, gs, w)
+        return True
+
+    @torch.no_grad()
     def exchange(self):
-        """launch the gradient exchange (asynchronous): reduce-scatter of every table's rows, one small all-reduce of the
-        replicated tails.  Returns what `apply` needs."""
+        """launch the gradient exchange (asynchronous): reduce-scatter of every table's rows (those not handed over early
+        by `contribute`), one small all-reduce of the replicated tails.  Returns what `apply` needs."""
         W, works, parts = self.world, [], []
-        tails = []
-        for t in self.tables:
-            p = t["p"]
-            g = (p.grad if p.grad is not None else torch.zeros_like(p)).contiguous().view(-1)
-            gs = torch.empty(t["S"], device=g.device) if W > 1 else g[:t["n_main"]]
+        tails, late = [], []
+        early, self._early = getattr(self, "_early", {}), {}
+        for k, t in enumerate(self.tables):
+            if k in early:
+                g, gs, w = early[k]
+                works.append(w)
+            else:
+                p = t["p"]
+                g = (p.grad if p.grad is not None else torch.zeros_like(p)).contiguous().view(-1)
+                gs = torch.empty(t["S"], device=g.device) if W > 1 else g[:t["n_main"]]
+                late.append((t, g, gs))
             parts.append((g, gs))
             tails.append(g[t["n_main"]:])
         tail = torch.cat(tails) if sum(x.numel() for x in tails) else None
         if W > 1:
-            with self._batched() as cm:
-                for t, (g, gs) in zip(self.tables, parts):
-                    w = dist.reduce_scatter_tensor(gs, g[:t["n_main"]], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
-                    if cm is None:
-                        works.append(w)
-            if cm is not None:
-                works.append(cm)
+            if late:
+                with self._batched() as cm:
+                    for t, g, gs in late:
+                        w = dist.reduce_scatter_tensor(gs, g[:t["n_main"]], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+                        if cm is None:
+                            works.append(w)
+                if cm is not None:
+                    works.append(cm)
             if tail is not None:
                 works.append(dist.all_reduce(tail, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
         return works, parts, tail

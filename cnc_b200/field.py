@@ -119,38 +119,44 @@ class _FusedFieldTrain(Function):
         # head: sigmoid -> Linear(160,3) -> ReLU -> Linear(160,160) -> ReLU -> Linear(95,160)
         # (weight gradients: cnc_wgrad, contraction over the samples on the tensor cores; the 3-wide last layer and
         #  the input gradients stay fp32 matmuls)
+        # Order: the chain of input gradients first (each needs only the previous one), then the table gradients, then the
+        # five weight gradients -- so that under data parallelism the exchange of the table gradients (99.7 % of the bytes)
+        # can start while the weight-gradient GEMMs still run (`field._table_grad_sink`, set by trainer.TrainStep).
         dz5 = torch.cat([g_rgb * rgb * (1.0 - rgb), rgb.new_zeros(n, 13)], dim=-1)        # [n, 16], columns 3.. = 0
-        g5 = wgrad(h4, dz5, with_ones=True)                     # [161, 16]
-        gW5, gb5 = g5[:160, :3].t(), g5[160, :3]
         dz4 = dgrad(dz5, W5, 160, h=h4)                         # (dz5 @ W5) * (h4 > 0)
-        g4 = wgrad(h3, dz4, with_ones=True)                     # [161, 160]: rows = input features, last row = bias grad
-        gW4, gb4 = g4[:160].t(), g4[160]
         dz3 = dgrad(dz4, W4, 160, h=h3)
-        head_in = torch.cat([sh16((dirs + 1.0) / 2.0), geo, geo.new_zeros(n, 1)], dim=-1)   # ngp.py:540-542 (+ pad to 96)
-        g3 = wgrad(head_in, dz3, with_ones=True)
-        gW3, gb3 = g3[:95].t(), g3[96]
         # base: [density pre-activation | geo] = Linear(160,80)(relu(Linear(255,160)(x0)))
         dz2 = dgrad(dz3, W3, 80, col_off=15, n_first=1)         # columns 1..79 = dz3 @ W3[:, 16:], column 0 = 0
         # d trunc_exp(h-1)*selector / dh = exp(min(h-1, 15)) * selector (ngp.py:328-334) = density, capped at e^15
         dz2[:, 0] = (g_sigma * torch.clamp(sigma, max=3269017.3724721107).unsqueeze(-1)).squeeze(-1)
-        g2 = wgrad(h1, dz2, with_ones=True)
-        gW2, gb2 = g2[:160].t(), g2[160]
         dz1 = dgrad(dz2, W2, 160, h=h1)
-        g1 = wgrad(x0, dz1)                                     # x0 column 255 is the kernel's all-ones pad column
-        gW1, gb1 = g1[:255].t(), g1[255]
         dfeat = dgrad(dz1, W1, 192)                             # only the grid columns carry on
         # grid features -> tables: K2 scatter-add + STE mask (ngp.py:121-165, :33-39)
         mb = field.mlp_base
         xn = field._normalise(pos)
+        sink = getattr(field, "_table_grad_sink", None)
         grads, col = [], 0
-        for enc, prm, dims in ((mb.encoding_xyz, p_xyz, [0, 1, 2]), (mb.encoding_xy, p_xy, [0, 1]),
-                               (mb.encoding_xz, p_xz, [0, 2]), (mb.encoding_yz, p_yz, [1, 2])):
+        for k, (enc, prm, dims) in enumerate(((mb.encoding_xyz, p_xyz, [0, 1, 2]), (mb.encoding_xy, p_xy, [0, 1]),
+                                              (mb.encoding_xz, p_xz, [0, 2]), (mb.encoding_yz, p_yz, [1, 2]))):
             L, F = enc.n_levels, enc.n_features
             ge = torch.zeros_like(prm)
             check(lib().cnc_grid_encode_bwd_rows(ptr(dfeat), dfeat.shape[1], col, ptr(xn[:, dims].contiguous()), ptr(enc.offsets_list),
                                                  ptr(enc.resolutions_list), ptr(ge), n, len(dims), F, L, 128, None, None, stream()))
             col += L * F
-            grads.append(G.ste_binary_backward(prm.contiguous(), ge))
+            g = G.ste_binary_backward(prm.contiguous(), ge)
+            grads.append(None if (sink is not None and sink(k, g)) else g)   # consumed: the exchange is already under way
+        # weight gradients: cnc_wgrad, contraction over the samples on the tensor cores
+        g5 = wgrad(h4, dz5, with_ones=True)                     # [161, 16]
+        gW5, gb5 = g5[:160, :3].t(), g5[160, :3]
+        g4 = wgrad(h3, dz4, with_ones=True)                     # [161, 160]: rows = input features, last row = bias grad
+        gW4, gb4 = g4[:160].t(), g4[160]
+        head_in = torch.cat([sh16((dirs + 1.0) / 2.0), geo, geo.new_zeros(n, 1)], dim=-1)   # ngp.py:540-542 (+ pad to 96)
+        g3 = wgrad(head_in, dz3, with_ones=True)
+        gW3, gb3 = g3[:95].t(), g3[96]
+        g2 = wgrad(h1, dz2, with_ones=True)
+        gW2, gb2 = g2[:160].t(), g2[160]
+        g1 = wgrad(x0, dz1)                                     # x0 column 255 is the kernel's all-ones pad column
+        gW1, gb1 = g1[:255].t(), g1[255]
         return (None, None, None, *grads, gW1, gb1, gW2, gb2, gW3, gb3, gW4, gb4, gW5, gb5)
 
 

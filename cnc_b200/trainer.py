@@ -118,8 +118,12 @@ class TrainStep:
         if self.table_opt is not None:
             for t in self.table_opt.tables:
                 t["p"].grad = None
+        # without a rate term the render path is the only source of table gradients: their exchange starts inside backward
+        early = self.table_opt is not None and self.world > 1 and not (self.cm is not None and self.lmbda > 0)
+        self.field._table_grad_sink = self.table_opt.contribute if early else None
         if loss.requires_grad:           # (a data-parallel rank whose batch produced no sample still joins the collectives)
             loss.backward()
+        self.field._table_grad_sink = None
         for g in self.optimizer.param_groups:
             g["lr"] = self.lr
         exchanged = None
