@@ -27,6 +27,8 @@ SIGNATURES = {
     "cnc_ste_binary_bwd": [_vp, _vp, _vp, _u64, _vp],
     "cnc_sign_pack": [_vp, _vp, _u64, _vp],
     "cnc_sign_unpack": [_vp, _vp, _u64, _vp],
+    "cnc_ctx3d_gather_fwd": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "cnc_ctx3d_gather_bwd": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "cnc_wavefront_begin": [_vp, _u32, _u32, _u32, _vp],
     "cnc_wavefront_march": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _u32,
                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -205,6 +205,37 @@ class _CtxMLP3(Function):
                 g[o[4]:o[5]].view(nh, no).t(), g[o[5]:o[5] + no])
 
 
+class _Ctx3DGather(Function):
+    """[voxels, 25] input of context_model_3D for the training loss: the three coarser levels' features interpolated at each
+    voxel (masked gather, per-point start level) | Pg of the voxel's level -- `forward_diff_levels(..., PV=1001)` + `cat` of
+    utils_bpp_acc.py:685-686 in one kernel each way (csrc/context_train.cu).  Gradients: to the latent table (K2 scatter-add
+    + STE window) and to the level frequencies."""
+
+    @staticmethod
+    def forward(ctx, params, Pg_levels, pts, level, enc, vbits, vbit_off):
+        M = pts.shape[0]
+        x = torch.empty(M, 25, device=pts.device, dtype=torch.float32)
+        bits = enc.sign_bits() if params is enc.params else _backend.sign_pack(params.detach().contiguous())
+        pg = Pg_levels.detach().contiguous().float()
+        check(lib().cnc_ctx3d_gather_fwd(ptr(pts), ptr(level), M, ptr(bits), ptr(enc.offsets_list), ptr(enc.resolutions_list),
+                                         ptr(vbits), ptr(vbit_off), ptr(pg), ptr(x), stream()))
+        ctx.save_for_backward(params, pts, level, vbits, vbit_off)
+        ctx.enc, ctx.L = enc, Pg_levels.numel()
+        return x
+
+    @staticmethod
+    def backward(ctx, gx):
+        params, pts, level, vbits, vbit_off = ctx.saved_tensors
+        enc = ctx.enc
+        gx = gx.contiguous()
+        ge = torch.zeros_like(params)
+        check(lib().cnc_ctx3d_gather_bwd(ptr(pts), ptr(level), pts.shape[0], ptr(enc.offsets_list), ptr(enc.resolutions_list),
+                                         ptr(vbits), ptr(vbit_off), ptr(gx), ptr(ge), stream()))
+        g_params = _backend.ste_binary_backward(params.contiguous(), ge)
+        g_pg = torch.zeros(ctx.L, device=gx.device, dtype=gx.dtype).index_add_(0, level, gx[:, 24])
+        return g_params, g_pg, None, None, None, None, None
+
+
 _LEVEL_CONST = {}
 
 
@@ -435,7 +466,7 @@ class CNC_context_models(nn.Module):
         key = (vx.data_ptr(), vx._version, tuple(vx.shape))
         cache = getattr(self, "_pruned_cache", None)
         if cache is None or cache[0] != key:
-            cache = self._pruned_cache = (key, {})
+            cache = self._pruned_cache = (key, {}, vx)   # (vx kept alive: see _vertex_bits)
         if n not in cache[1]:
             dev = vx.device
             r, T = self.res[n], self.offs[n + 1] - self.offs[n]
@@ -668,6 +699,7 @@ class CNC_context_models(nn.Module):
             check(lib().cnc_vertex_valid_bits(ptr(vx), vx.shape[-1], ptr(Encoding_xyz.resolutions_list), self.n_levels,
                                               ptr(bit_off), off, ptr(words), stream()))
             self._vbits, self._vbits_off, self._vbits_key = words, bit_off, key
+            self._vbits_keep = vx   # (a live reference: the storage cannot be recycled for another grid while the key is trusted)
         return self._vbits, self._vbits_off
 
     def _sign_bits(self, table):
@@ -675,7 +707,7 @@ class CNC_context_models(nn.Module):
         t = table.detach()
         key = (t.data_ptr(), t._version, t.numel())
         if getattr(self, "_sbits_key", None) != key:
-            self._sbits, self._sbits_key = _backend.sign_pack(t.contiguous()), key
+            self._sbits, self._sbits_key, self._sbits_keep = _backend.sign_pack(t.contiguous()), key, t
         return self._sbits
 
     def _probs_3D_fused(self, Encoding_xyz, table, binary_vxl, n, lo, hi, Pg_n):
@@ -800,6 +832,8 @@ class CNC_context_models(nn.Module):
             snl, n_valid = self.sample_num_levels, self.ttl_sample_num_valid_levels
         start = torch.round((self.hashparams_num_levels - snl) * torch.rand_like(self.utils_rand)).to(torch.long)
         start, snl_h = torch.stack([start, snl.to(torch.long)]).tolist()   # one device->host read for both
+        fast = (self.n_features == 8 and self.max_context_layer_num == 3 and Encoding_xyz.ste_binary
+                and getattr(self, "fused_gather_train", True) and min([n for n in range(self.n_levels) if n not in self.skip_levels_3D] + [99]) >= 3)
         pts_l, ptsn_l, Pg_l, n_l, cnt_l, val_l = [], [], [], [], [], []
         Pgs_3D, bits_3D = self.level_entropies(pq["xyz"])
         for n in range(self.n_levels):
@@ -810,13 +844,14 @@ class CNC_context_models(nn.Module):
             lo, hi = start[n], start[n] + int(snl_h[n])
             p = self.pos_grid_sorted_list[n][self._cs_host(n, lo):self._cs_host(n, hi)]
             pts_l.append(p)
-            ptsn_l.append((p - 0.5) / self.scales_list[n, :])
-            Pg_l.append(Pg_n.reshape(1, 1).expand(p.shape[0], 1))
+            if not fast:
+                ptsn_l.append((p - 0.5) / self.scales_list[n, :])
+                Pg_l.append(Pg_n.reshape(1, 1).expand(p.shape[0], 1))
             n_l.append(torch.full((p.shape[0],), n, dtype=torch.int64, device=p.device))
             cnt_l.append(self.unique_count_list[n][lo:hi])
             val_l.append(self.unique_value_list[n][lo:hi] + self.offs[n])
         if pts_l:
-            pts, ptsn, Pgc, nl, cnt, rows3 = (torch.cat(t, 0) for t in (pts_l, ptsn_l, Pg_l, n_l, cnt_l, val_l))
+            pts, nl, cnt, rows3 = (torch.cat(t, 0) for t in (pts_l, n_l, cnt_l, val_l))
             vals = pq["xyz"][rows3]   # one gather of the sampled entries (one index backward instead of one per level)
             mask, overlap = self.query_binary_vxl_qlist(pts, binary_vxl, nl, return_overlap_area=True)
             # voxels per entry that touch the occupancy, overlap weights normalised per entry, weighted mean of the MLP
@@ -836,8 +871,16 @@ class CNC_context_models(nn.Module):
             else:
                 w = torch.repeat_interleave(1.0 / mask_cnt.to(torch.float), mask_cnt, output_size=m_i.numel())
             c = self.max_context_layer_num
-            context = Encoding_xyz.forward_diff_levels(ptsn[m_i], (nl[m_i] - c).to(torch.int), c, binary_vxl=binary_vxl.squeeze(0), PV=1001)
-            ctx_in = torch.cat([context, Pgc[m_i]], dim=-1)
+            if fast:   # masked 3-level gather + Pg column straight into the [M, 25] MLP input (csrc/context_train.cu)
+                vx = binary_vxl.squeeze(0)
+                vx = (vx if vx.dtype in (torch.bool, torch.uint8) else vx != 0).contiguous()
+                vbits, vbit_off = self._vertex_bits(Encoding_xyz, vx)
+                ctx_in = _Ctx3DGather.apply(Encoding_xyz.params, torch.stack(Pgs_3D), pts[m_i].contiguous(), nl[m_i].contiguous(),
+                                            Encoding_xyz, vbits, vbit_off)
+            else:
+                ptsn, Pgc = torch.cat(ptsn_l, 0), torch.cat(Pg_l, 0)
+                context = Encoding_xyz.forward_diff_levels(ptsn[m_i], (nl[m_i] - c).to(torch.int), c, binary_vxl=binary_vxl.squeeze(0), PV=1001)
+                ctx_in = torch.cat([context, Pgc[m_i]], dim=-1)
             if getattr(self, "fused_mlp_train", True) and ctx_in.shape[1] == 25 and self.n_features == 8:   # the product layout
                 m3 = self.context_model_3D
                 mlp_out = _CtxMLP3.apply(ctx_in, m3[0].weight, m3[0].bias, m3[2].weight, m3[2].bias, m3[4].weight, m3[4].bias)

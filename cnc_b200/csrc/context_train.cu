@@ -1,0 +1,140 @@
+// context_train.cu -- the 3D context gather of the rate term, forward and backward (training loss,
+// examples/utils_bpp_acc.py:644-687).
+//
+// Reference flow per step: the voxels of ~150 000 sampled hash entries that touch the occupancy (5.7 M at the product
+// layout) are normalised, pushed through GridEncoder.forward_diff_levels (K1 with a per-point start level and the per-corner
+// occupancy test, gridencoder.cu:221-276: a box of up to 17^3 occupancy cells per corner), permuted, concatenated with the
+// level frequency Pg into the [M, 25] input of context_model_3D; the backward runs K2 with the same per-corner boxes.
+//
+// Here one kernel each way works straight from the int16 voxel coordinates:
+//   * the per-corner occupancy test is one bit of the per-vertex bitmaps (cnc_vertex_valid_bits, rebuilt only when the
+//     occupancy grid changes, every 16 steps) instead of a box scan -- the same predicate, evaluated once per vertex;
+//   * features come from the 1-bit sign planes (L2 resident) and land directly in the [M, 25] layout, Pg column included:
+//     no [3, M, 8] intermediate, no permute, no cat;
+//   * the backward reads the [M, 25] input gradient in place and scatter-adds with red.global.add.v4.f32.
+// Thread = (voxel, context level); the arithmetic is make_corners_fn of common.cuh, i.e. K1's, so the features are
+// bit-identical to the reference flow on +-1 tables.
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace cnc {
+namespace ct {
+
+struct Args {
+    const int16_t *pts;        // [M,3] voxel coordinates at their own level
+    const int64_t *level;      // [M]   level n of every voxel (>= 3)
+    const uint8_t *sign_bits;  // sign plane of the whole 3D table
+    const int32_t *offsets, *resolutions;
+    const uint32_t *vbits;     // per-vertex validity bitmaps
+    const int64_t *vbit_off;   // [L+1]
+    const float *Pg;           // [L] level frequencies (column 24)
+    float *x;                  // fwd out [M,25]
+    const float *gx;           // bwd in  [M,25]
+    float *grad_table;         // bwd out [rows,8], accumulated into
+    int64_t M;
+};
+
+__device__ __forceinline__ bool corners_of(const Args &a, int64_t v, uint32_t l, LevelConst &lc, Corners<3> &cs) {
+    const uint32_t n = (uint32_t)__ldg(a.level + v);
+    const uint32_t lev = n - 3u + l;
+    lc = load_level(a.offsets, a.resolutions, lev);
+    // normalised coordinate of the voxel at ITS level: (c - 0.5) / (res_n - 2)   (utils_bpp_acc.py:647)
+    const float sc = (float)((uint32_t)__ldg(a.resolutions + n) - 2u);
+    float xi[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) xi[d] = __fdiv_rn(__fsub_rn((float)a.pts[v * 3 + d], 0.5f), sc);
+    const uint32_t *vb = a.vbits + (__ldg(a.vbit_off + lev) >> 5);
+    const uint32_t res = lc.res;
+    return make_corners_fn<3>(xi, lc, [&](const uint32_t (&c)[3]) {
+        const uint32_t bit = (c[0] * res + c[1]) * res + c[2];
+        return ((__ldg(vb + (bit >> 5)) >> (bit & 31u)) & 1u) != 0u;
+    }, cs);
+}
+
+__global__ void __launch_bounds__(256) ctx3d_gather_fwd_kernel(const Args a) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.M) return;
+    const uint32_t l = blockIdx.y;
+    LevelConst lc;
+    Corners<3> cs;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = 0.f;
+    if (corners_of(a, v, l, lc, cs)) {
+        uint32_t sb[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) sb[i] = ((cs.valid >> i) & 1u) ? (uint32_t)__ldg(a.sign_bits + (uint64_t)lc.base_row + cs.row[i]) : 0u;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if ((cs.valid >> i) & 1u) {
+                const float ww = __fmul_rn(cs.w[i], cs.wn_re);
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[k] = __fadd_rn(acc[k], ((sb[i] >> k) & 1u) ? ww : -ww);
+            }
+        }
+    }
+    float *o = a.x + v * 25 + l * 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++) o[k] = acc[k];
+    if (l == 0) a.x[v * 25 + 24] = __ldg(a.Pg + __ldg(a.level + v));
+}
+
+__global__ void __launch_bounds__(256) ctx3d_gather_bwd_kernel(const Args a) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.M) return;
+    const uint32_t l = blockIdx.y;
+    LevelConst lc;
+    Corners<3> cs;
+    if (!corners_of(a, v, l, lc, cs)) return;
+    float g[8];
+    const float *gi = a.gx + v * 25 + l * 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++) g[k] = __ldg(gi + k);
+    float *gt = a.grad_table + (size_t)lc.base_row * 8;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if ((cs.valid >> i) & 1u) {
+            const float ww = __fmul_rn(cs.w[i], cs.wn_re);
+            float4 *p = reinterpret_cast<float4 *>(gt + (size_t)cs.row[i] * 8);
+            atomicAdd(p, make_float4(__fmul_rn(ww, g[0]), __fmul_rn(ww, g[1]), __fmul_rn(ww, g[2]), __fmul_rn(ww, g[3])));
+            atomicAdd(p + 1, make_float4(__fmul_rn(ww, g[4]), __fmul_rn(ww, g[5]), __fmul_rn(ww, g[6]), __fmul_rn(ww, g[7])));
+        }
+    }
+}
+
+}  // namespace ct
+}  // namespace cnc
+
+using namespace cnc;
+
+extern "C" {
+
+int cnc_ctx3d_gather_fwd(const int16_t *pts, const int64_t *level, int64_t M, const uint8_t *sign_bits, const int32_t *offsets,
+                         const int32_t *resolutions, const uint32_t *vertex_bits, const int64_t *vertex_bit_offsets, const float *Pg,
+                         float *x, cnc_stream_t stream) {
+    if (M == 0) return CNC_OK;
+    if (!pts || !level || !sign_bits || !offsets || !resolutions || !vertex_bits || !vertex_bit_offsets || !Pg || !x) {
+        set_error("ctx3d_gather_fwd: null pointer");
+        return CNC_EINVAL;
+    }
+    ct::Args a{pts, level, sign_bits, offsets, resolutions, vertex_bits, vertex_bit_offsets, Pg, x, nullptr, nullptr, M};
+    ct::ctx3d_gather_fwd_kernel<<<dim3(div_up((uint64_t)M, 256), 3), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("ctx3d_gather_fwd");
+}
+
+int cnc_ctx3d_gather_bwd(const int16_t *pts, const int64_t *level, int64_t M, const int32_t *offsets, const int32_t *resolutions,
+                         const uint32_t *vertex_bits, const int64_t *vertex_bit_offsets, const float *gx, float *grad_table,
+                         cnc_stream_t stream) {
+    if (M == 0) return CNC_OK;
+    if (!pts || !level || !offsets || !resolutions || !vertex_bits || !vertex_bit_offsets || !gx || !grad_table) {
+        set_error("ctx3d_gather_bwd: null pointer");
+        return CNC_EINVAL;
+    }
+    if (reinterpret_cast<uintptr_t>(grad_table) & 15u) { set_error("ctx3d_gather_bwd: grad_table must be 16-byte aligned"); return CNC_EINVAL; }
+    ct::Args a{pts, level, nullptr, offsets, resolutions, vertex_bits, vertex_bit_offsets, nullptr, nullptr, gx, grad_table, M};
+    ct::ctx3d_gather_bwd_kernel<<<dim3(div_up((uint64_t)M, 256), 3), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("ctx3d_gather_bwd");
+}
+
+}  // extern "C"

@@ -136,12 +136,14 @@ class _FusedFieldTrain(Function):
         xn = field._normalise(pos)
         sink = getattr(field, "_table_grad_sink", None)
         grads, col = [], 0
-        for k, (enc, prm, dims) in enumerate(((mb.encoding_xyz, p_xyz, [0, 1, 2]), (mb.encoding_xy, p_xy, [0, 1]),
-                                              (mb.encoding_xz, p_xz, [0, 2]), (mb.encoding_yz, p_yz, [1, 2]))):
+        # (coordinate pairs as strided slices: indexing with a python list builds an index tensor on the host and copies it
+        #  over -- a stream synchronisation per call, four per backward)
+        for k, (enc, prm, xs) in enumerate(((mb.encoding_xyz, p_xyz, xn), (mb.encoding_xy, p_xy, xn[:, 0:2]),
+                                            (mb.encoding_xz, p_xz, xn[:, 0::2]), (mb.encoding_yz, p_yz, xn[:, 1:3]))):
             L, F = enc.n_levels, enc.n_features
             ge = torch.zeros_like(prm)
-            check(lib().cnc_grid_encode_bwd_rows(ptr(dfeat), dfeat.shape[1], col, ptr(xn[:, dims].contiguous()), ptr(enc.offsets_list),
-                                                 ptr(enc.resolutions_list), ptr(ge), n, len(dims), F, L, 128, None, None, stream()))
+            check(lib().cnc_grid_encode_bwd_rows(ptr(dfeat), dfeat.shape[1], col, ptr(xs.contiguous()), ptr(enc.offsets_list),
+                                                 ptr(enc.resolutions_list), ptr(ge), n, xs.shape[1], F, L, 128, None, None, stream()))
             col += L * F
             g = G.ste_binary_backward(prm.contiguous(), ge)
             grads.append(None if (sink is not None and sink(k, g)) else g)   # consumed: the exchange is already under way
@@ -207,9 +209,9 @@ class compose_3D_2D_embed(nn.Module):
 
     def features(self, x):
         out_xyz = self.encoding_xyz(x)
-        out_xy = self.encoding_xy(x[..., [0, 1]].contiguous())
-        out_xz = self.encoding_xz(x[..., [0, 2]].contiguous())
-        out_yz = self.encoding_yz(x[..., [1, 2]].contiguous())
+        out_xy = self.encoding_xy(x[..., 0:2].contiguous())
+        out_xz = self.encoding_xz(x[..., 0::2].contiguous())
+        out_yz = self.encoding_yz(x[..., 1:3].contiguous())
         outs = [out_xyz, out_xy, out_xz, out_yz]
         if self.embed_fn is not None:
             outs.append(self.embed_fn(x))

@@ -419,14 +419,16 @@ class OccGridEstimator(torch.nn.Module):
         t_starts, t_ends = intervals.t_starts, intervals.t_ends      # == vals[is_left], vals[is_right] (occ_grid.py:188-189)
         ray_indices, packed_info = samples.ray_indices, samples.packed_info
         if (alpha_thre > 0.0 or early_stop_eps > 0.0) and (sigma_fn is not None or alpha_fn is not None):
-            alpha_thre = min(alpha_thre, self.occs.mean().item())
+            if alpha_thre > 0.0:   # (min(alpha_thre <= 0, mean) cannot make the test below true: no device read needed)
+                alpha_thre = min(alpha_thre, self.occs.mean().item())
             if sigma_fn is None:
                 raise NotImplementedError("alpha_fn is not on the CNC path; pass sigma_fn")
             sigmas = sigma_fn(t_starts, t_ends, ray_indices) if t_starts.shape[0] != 0 else torch.empty((0,), device=t_starts.device)
             assert sigmas.shape == t_starts.shape, "sigmas must have shape of (N,)! Got {}".format(sigmas.shape)
             masks = render_visibility_from_density(t_starts=t_starts, t_ends=t_ends, sigmas=sigmas, packed_info=packed_info,
                                                    early_stop_eps=early_stop_eps, alpha_thre=alpha_thre)
-            ray_indices, t_starts, t_ends = ray_indices[masks], t_starts[masks], t_ends[masks]
+            keep = masks.nonzero().squeeze(1)      # one compaction (and one host sync) instead of one per indexed tensor
+            ray_indices, t_starts, t_ends = ray_indices[keep], t_starts[keep], t_ends[keep]
         return ray_indices, t_starts, t_ends
 
     @torch.no_grad()

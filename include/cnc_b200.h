@@ -87,6 +87,22 @@ int cnc_sign_pack(const float *params, uint8_t *bits, uint64_t n, cnc_stream_t s
 int cnc_sign_unpack(const uint8_t *bits, float *out, uint64_t n, cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * 3D context gather of the rate term (training loss), forward and backward.
+ * replaces: Encoding_xyz.forward_diff_levels(points, n_list - 3, 3, binary_vxl, PV=1001) + torch.cat([context, Pg]) and its
+ *           autograd backward, examples/utils_bpp_acc.py:644-687 (K1 / K2 with per-point start level, gridencoder.cu:118-126).
+ *   pts [M,3] i16 voxel coordinates at their own level `level[i]` (>= 3), sign_bits = cnc_sign_pack of the 3D table,
+ *   vertex_bits / vertex_bit_offsets from cnc_vertex_valid_bits (the per-corner occupancy predicate as one bit per vertex),
+ *   Pg [L] level frequencies.  fwd: x [M,25] = 3 x 8 interpolated context features of levels n-3..n-1 | Pg[n].
+ *   bwd: grad_table [rows,8] += scatter of gx[:, 0:24] (caller zeroes; d/dPg is the column sum of gx[:,24] per level).
+ * ---------------------------------------------------------------------------------------- */
+int cnc_ctx3d_gather_fwd(const int16_t *pts, const int64_t *level, int64_t M, const uint8_t *sign_bits, const int32_t *offsets,
+                         const int32_t *resolutions, const uint32_t *vertex_bits, const int64_t *vertex_bit_offsets,
+                         const float *Pg, float *x, cnc_stream_t stream);
+int cnc_ctx3d_gather_bwd(const int16_t *pts, const int64_t *level, int64_t M, const int32_t *offsets, const int32_t *resolutions,
+                         const uint32_t *vertex_bits, const int64_t *vertex_bit_offsets, const float *gx, float *grad_table,
+                         cnc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Test-time wavefront renderer without host round trips.
  * replaces: the python loop of render_image_with_occgrid_test, examples/utils.py:395-479 (per round: ray_mask.sum().item(),
  *           traverse_grids(over_allocate), boolean compactions, rgb_sigma_fn, render_weight_from_density, 3 x

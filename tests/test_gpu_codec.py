@@ -399,3 +399,23 @@ def test_codec_pruned_mode_roundtrip_and_vs_full(cuda, cfg):
         q = torch.where(e.params >= 0, 1.0, -1.0)
         assert ((a == q) | (a == 1)).all()
     assert all(p is None for p in cm_d.pos_grid_sorted_list)                 # the decoder never built a full vertex list
+
+
+def test_fused_context_gather_equals_forward_diff_levels(cuda):
+    """rate term: `_Ctx3DGather` (bitmap-masked 3-level gather + Pg column, csrc/context_train.cu) against
+    GridEncoder.forward_diff_levels + cat on the drop-in K1/K2 (per-corner occupancy boxes): identical features on the
+    +-1 table -> identical loss; table / Pg / MLP gradients to fp32 atomics order."""
+    cm, encs, vxl = make(cuda, res3=R3, log2T=19, res2=R2, log2T2=17, Rb=128, seed=2)
+    out = {}
+    for fast in (True, False):
+        cm.fused_gather_train = fast
+        for p in [e.params for e in encs] + list(cm.parameters()):
+            p.grad = None
+        torch.manual_seed(9)
+        bpp, _ = cm.forward_binary_vxl_mixPg_3D2D(*encs, vxl, step=0, sample_num=20000)
+        bpp.backward()
+        out[fast] = (float(bpp), [e.params.grad.clone() for e in encs], [p.grad.clone() for p in cm.parameters()])
+    assert abs(out[True][0] - out[False][0]) <= 1e-6 * abs(out[False][0]), (out[True][0], out[False][0])
+    for a, b in zip(out[True][1] + out[True][2], out[False][1] + out[False][2]):
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-12
+    assert float(out[True][1][0].abs().max()) > 0
