@@ -28,14 +28,14 @@ SIGNATURES = {
     "cnc_sign_pack": [_vp, _vp, _u64, _vp],
     "cnc_sign_unpack": [_vp, _vp, _u64, _vp],
     "cnc_ctx3d_gather_fwd": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "cnc_ctx3d_gather_bwd": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "cnc_ctx3d_gather_bwd": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "cnc_wavefront_begin": [_vp, _u32, _u32, _u32, _vp],
     "cnc_wavefront_march": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _u32,
                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "cnc_wavefront_composite": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _u32, _f32, _f32, _vp],
     "cnc_field_fwd_n": [_vp] * 14 + [_vp, _u32, _vp],
     "cnc_level_row_hist": [_u32, _u32, _vp, _vp],
-    "cnc_level_pruned_keys": [_u32, _u32, _vp, _i32, _vp, _vp, _vp, _vp],
+    "cnc_level_pruned_keys": [_u32, _u32, _vp, _i32, _vp, _vp, _vp, _i32, _vp],
     "cnc_keys_to_points": [_vp, _u64, _u32, _vp, _vp, _vp],
     "cnc_ste_planes_pack": [_vp, _vp, _vp, _u64, _vp],
     "cnc_surrogate_fill": [_vp, _vp, _vp, _u64, _u64, _u64, _vp],

@@ -227,4 +227,28 @@ __device__ __forceinline__ bool voxel_mask_overlap(const int (&c)[D], float r, i
     return m;
 }
 
+// Candidate occupancy cells of finest-level coordinate c in the reference's vote list (get_idx_coords2,
+// utils_bpp_acc.py:498-512: c = occ * t + k + 1, k in [-1, t]): o in [ceil((c - t - 1) / t), floor(c / t)].
+__device__ __forceinline__ void vote_cand(uint32_t c, uint32_t t, uint32_t Rb, uint32_t &o_lo, uint32_t &o_hi) {
+    o_hi = c / t;
+    o_lo = c > t + 1u ? (c - t - 2u) / t + 1u : 0u;     // ceil((c - t - 1) / t)
+    if (o_hi > Rb - 1u) o_hi = Rb - 1u;                  // (o_lo > o_hi -> no candidate)
+}
+
+// is finest-level vertex c in that list (and inside the border the vote kernels skip, gridencoder.cu:895-898)?
+__device__ __forceinline__ bool vote_member(const uint32_t (&c)[3], uint32_t res, uint32_t Rb, const uint8_t *__restrict__ vxl) {
+    const uint32_t t = (res - 2u) / Rb;
+    uint32_t lo[3], hi[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        if (c[d] == 0u || c[d] >= res - 1u) return false;
+        vote_cand(c[d], t, Rb, lo[d], hi[d]);
+    }
+    for (uint32_t o0 = lo[0]; o0 <= hi[0]; o0++)
+        for (uint32_t o1 = lo[1]; o1 <= hi[1]; o1++)
+            for (uint32_t o2 = lo[2]; o2 <= hi[2]; o2++)
+                if (vxl[((size_t)o0 * Rb + o1) * Rb + o2]) return true;
+    return false;
+}
+
 }  // namespace cnc

@@ -169,11 +169,7 @@ vote_bwd_kernel(const int16_t *__restrict__ pts, const float *__restrict__ table
 //   backward: one warp per table row walks the row's voxels in the inverse hash table (lanes stride, coalesced),
 //             gathers d(fraction)/d(vote) of all three planes and reduces with a fixed shuffle tree -> plain stores.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void vote_cand(uint32_t c, uint32_t t, uint32_t Rb, uint32_t &o_lo, uint32_t &o_hi) {
-    o_hi = c / t;
-    o_lo = c > t + 1u ? (c - t - 2u) / t + 1u : 0u;     // ceil((c - t - 1) / t)
-    if (o_hi > Rb - 1u) o_hi = Rb - 1u;                  // (o_lo > o_hi -> no candidate)
-}
+// (vote_cand: common.cuh)
 
 __global__ void __launch_bounds__(128)
 vote3_fwd_kernel(const uint8_t *__restrict__ vxl, uint32_t Rb, const uint8_t *__restrict__ bits, uint32_t res, uint32_t T,

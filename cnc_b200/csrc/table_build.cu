@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) level_row_hist_kernel(uint32_t res, uint3
 
 __global__ void __launch_bounds__(256)
 level_pruned_keys_kernel(uint32_t res, uint32_t T, const uint8_t *__restrict__ vxl, int32_t Rb, const int32_t *__restrict__ entry_of_row,
-                         unsigned long long *__restrict__ keys, unsigned long long *__restrict__ counter, uint64_t n) {
+                         unsigned long long *__restrict__ keys, unsigned long long *__restrict__ counter, uint64_t n, int mode) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
     // (the loop bound is rounded up to whole warps so that the ballot below is executed by all 32 lanes)
@@ -51,7 +51,7 @@ level_pruned_keys_kernel(uint32_t res, uint32_t T, const uint8_t *__restrict__ v
             const uint32_t cu[3] = {xy / res, xy % res, z};
             const int ci[3] = {(int)cu[0], (int)cu[1], (int)cu[2]};
             int32_t ov;
-            pass = voxel_mask_overlap<3>(ci, (float)res, Rb, vxl, ov);
+            pass = mode == 0 ? voxel_mask_overlap<3>(ci, (float)res, Rb, vxl, ov) : vote_member(cu, res, (uint32_t)Rb, vxl);
             if (pass) row = grid_row<3>(cu, T, res);
         }
         const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
@@ -100,13 +100,14 @@ int cnc_level_row_hist(uint32_t resolution, uint32_t hashmap_size, uint32_t *cou
 }
 
 int cnc_level_pruned_keys(uint32_t resolution, uint32_t hashmap_size, const uint8_t *binary_vxl, int32_t Rb, const int32_t *entry_of_row,
-                          uint64_t *keys, uint64_t *counter, cnc_stream_t stream) {
-    if (!binary_vxl || !counter || resolution < 3 || hashmap_size == 0 || Rb < 1) { set_error("level_pruned_keys: bad argument"); return CNC_EINVAL; }
+                          uint64_t *keys, uint64_t *counter, int32_t mode, cnc_stream_t stream) {
+    if (!binary_vxl || !counter || resolution < 3 || hashmap_size == 0 || Rb < 1 || mode < 0 || mode > 1) { set_error("level_pruned_keys: bad argument"); return CNC_EINVAL; }
+    if (mode == 1 && ((resolution - 2) % (uint32_t)Rb)) { set_error("level_pruned_keys: vote membership needs (resolution - 2) % Rb == 0"); return CNC_EINVAL; }
     const uint64_t n = (uint64_t)resolution * resolution * resolution;
     if (n >= (1ull << 28)) { set_error("level_pruned_keys: resolution^3 must stay below 2^28"); return CNC_EINVAL; }
     level_pruned_keys_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         resolution, hashmap_size, binary_vxl, Rb, entry_of_row, reinterpret_cast<unsigned long long *>(keys),
-        reinterpret_cast<unsigned long long *>(counter), n);
+        reinterpret_cast<unsigned long long *>(counter), n, mode);
     return check_launch("level_pruned_keys");
 }
 

@@ -93,14 +93,14 @@ int cnc_sign_unpack(const uint8_t *bits, float *out, uint64_t n, cnc_stream_t st
  *   pts [M,3] i16 voxel coordinates at their own level `level[i]` (>= 3), sign_bits = cnc_sign_pack of the 3D table,
  *   vertex_bits / vertex_bit_offsets from cnc_vertex_valid_bits (the per-corner occupancy predicate as one bit per vertex),
  *   Pg [L] level frequencies.  fwd: x [M,25] = 3 x 8 interpolated context features of levels n-3..n-1 | Pg[n].
- *   bwd: grad_table [rows,8] += scatter of gx[:, 0:24] (caller zeroes; d/dPg is the column sum of gx[:,24] per level).
+ *   bwd: grad_table [rows,8] += scatter of gx[:, 0:24], grad_pg [L] += gx[:,24] summed per level (caller zeroes both).
  * ---------------------------------------------------------------------------------------- */
 int cnc_ctx3d_gather_fwd(const int16_t *pts, const int64_t *level, int64_t M, const uint8_t *sign_bits, const int32_t *offsets,
                          const int32_t *resolutions, const uint32_t *vertex_bits, const int64_t *vertex_bit_offsets,
                          const float *Pg, float *x, cnc_stream_t stream);
 int cnc_ctx3d_gather_bwd(const int16_t *pts, const int64_t *level, int64_t M, const int32_t *offsets, const int32_t *resolutions,
                          const uint32_t *vertex_bits, const int64_t *vertex_bit_offsets, const float *gx, float *grad_table,
-                         cnc_stream_t stream);
+                         float *grad_pg, cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Test-time wavefront renderer without host round trips.
@@ -140,12 +140,14 @@ int cnc_field_fwd_n(const float *pos, const float *dirs, const float *aabb6_host
  *                           161-242) -> key (entry << 28) | ((x*res + y)*res + z), entry = entry_of_row[row] (NULL:
  *                           entry = row), appended at *counter (u64, caller zeroes).  keys == NULL: count only.
  *                           Sorting the keys gives the reference's order (entries ascending, lattice order inside).
+ *                           mode 1: the predicate is membership in the vote list of the dimension-wise context instead
+ *                           (get_idx_coords2, utils_bpp_acc.py:498-512, minus the border the vote kernels skip).
  *   cnc_keys_to_points    : sorted keys -> pts [n,3] i16, entry [n] i32.
  * resolution^3 < 2^28.  binary_vxl [Rb,Rb,Rb] u8.
  * ---------------------------------------------------------------------------------------- */
 int cnc_level_row_hist(uint32_t resolution, uint32_t hashmap_size, uint32_t *counts, cnc_stream_t stream);
 int cnc_level_pruned_keys(uint32_t resolution, uint32_t hashmap_size, const uint8_t *binary_vxl, int32_t Rb,
-                          const int32_t *entry_of_row, uint64_t *keys, uint64_t *counter, cnc_stream_t stream);
+                          const int32_t *entry_of_row, uint64_t *keys, uint64_t *counter, int32_t mode, cnc_stream_t stream);
 int cnc_keys_to_points(const uint64_t *keys, uint64_t n, uint32_t resolution, int16_t *pts, int32_t *entry,
                        cnc_stream_t stream);
 
