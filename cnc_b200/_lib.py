@@ -27,6 +27,8 @@ SIGNATURES = {
     "cnc_ste_binary_bwd": [_vp, _vp, _vp, _u64, _vp],
     "cnc_sign_pack": [_vp, _vp, _u64, _vp],
     "cnc_sign_unpack": [_vp, _vp, _u64, _vp],
+    "cnc_lin8_fwd": [_vp, _vp, _vp, _vp, _i64, _i32, _vp],
+    "cnc_lin8_bwd": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "cnc_ctx3d_gather_fwd": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "cnc_ctx3d_gather_bwd": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "cnc_wavefront_begin": [_vp, _u32, _u32, _u32, _vp],
@@ -101,6 +103,8 @@ def lib():
         L.cnc_ctx_mlp_floats.argtypes = []
         L.cnc_ctx_mlp_max_partials.restype = C.c_int
         L.cnc_ctx_mlp_max_partials.argtypes = []
+        L.cnc_lin8_rows_per_block.restype = C.c_int
+        L.cnc_lin8_rows_per_block.argtypes = []
         _lib = L
     return _lib
 

@@ -205,6 +205,40 @@ class _CtxMLP3(Function):
                 g[o[4]:o[5]].view(nh, no).t(), g[o[5]:o[5] + no])
 
 
+class _Lin8(Function):
+    """nn.Linear(K, 8) over [N, K] rows, K in {9, 17, 25, 33}: the plane context models (utils_bpp_acc.py:386-393) as one
+    pass each way (csrc/context_lin8.cu) instead of cuBLAS' tall-skinny SIMT GEMMs"""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        x = x.contiguous().float()
+        Wc, bc = W.detach().contiguous().float(), b.detach().contiguous().float()
+        y = torch.empty(x.shape[0], 8, device=x.device, dtype=torch.float32)
+        check(lib().cnc_lin8_fwd(ptr(x), ptr(Wc), ptr(bc), ptr(y), x.shape[0], x.shape[1], stream()))
+        ctx.save_for_backward(x, Wc)
+        ctx.need_gx = x.requires_grad or True
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, Wc = ctx.saved_tensors
+        N, K = x.shape
+        if N == 0:
+            return torch.zeros_like(x), torch.zeros(8, K, device=x.device), torch.zeros(8, device=x.device)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        nb = (N + lib().cnc_lin8_rows_per_block() - 1) // lib().cnc_lin8_rows_per_block()
+        parts = torch.empty(nb, 8 * K + 8, device=x.device, dtype=torch.float32)
+        check(lib().cnc_lin8_bwd(ptr(x), ptr(Wc), ptr(gy.contiguous().float()), ptr(gx), ptr(parts), N, K, stream()))
+        g = parts.sum(0)
+        return gx, g[:8 * K].view(8, K), g[8 * K:]
+
+
+def _linear8(lin: nn.Linear, x: torch.Tensor) -> torch.Tensor:
+    if x.is_cuda and lin.out_features == 8 and lin.in_features in (9, 17, 25, 33) and x.shape[0] > 0:
+        return _Lin8.apply(x, lin.weight, lin.bias)
+    return lin(x)
+
+
 class _Ctx3DGather(Function):
     """[voxels, 25] input of context_model_3D for the training loss: the three coarser levels' features interpolated at each
     voxel (masked gather, per-point start level) | Pg of the voxel's level -- `forward_diff_levels(..., PV=1001)` + `cat` of
@@ -816,7 +850,7 @@ class CNC_context_models(nn.Module):
             context = torch.cat([context, Pg_col], dim=-1)
         # index_select by the sort permutation + per-row sum (utils_bpp_acc.py:741-745) as one segment reduction
         cs = torch.cat([torch.zeros(1, dtype=torch.int64, device=points_n.device), torch.cumsum(unique_cnt_2D, 0)])
-        mean = segment_sum.apply(self.context_model_2D[n - 1](context), cs, None, indices_2D.contiguous())
+        mean = segment_sum.apply(_linear8(self.context_model_2D[n - 1][0], context), cs, None, indices_2D.contiguous())
         return mean / unique_cnt_2D.unsqueeze(-1), unique_value_2D, (points_n, indices_2D, unique_value_2D, unique_cnt_2D)
 
     # ------------------------------------------------------------------------------------------ loss

@@ -87,6 +87,17 @@ int cnc_sign_pack(const float *params, uint8_t *bits, uint64_t n, cnc_stream_t s
 int cnc_sign_unpack(const uint8_t *bits, float *out, uint64_t n, cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Plane context models: y [N,8] = x [N,K] W^T [8,K] + b, K = 8 * context levels + 1 in {9, 17, 25, 33}.
+ * replaces: context_model_2D[n-1] (nn.Linear -> cuBLAS sgemm) and its autograd backward, utils_bpp_acc.py:386-393, :558-561.
+ *   bwd: gx [N,K] (nullable) = gy W; parts [ceil(N / cnc_lin8_rows_per_block()), 8K + 8] = per-block partials of
+ *   (dW [8,K] row-major | db [8]); the caller sums them over the blocks in index order.
+ * ---------------------------------------------------------------------------------------- */
+int cnc_lin8_rows_per_block(void);
+int cnc_lin8_fwd(const float *x, const float *W, const float *b, float *y, int64_t N, int32_t K, cnc_stream_t stream);
+int cnc_lin8_bwd(const float *x, const float *W, const float *gy, float *gx, float *parts, int64_t N, int32_t K,
+                 cnc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * 3D context gather of the rate term (training loss), forward and backward.
  * replaces: Encoding_xyz.forward_diff_levels(points, n_list - 3, 3, binary_vxl, PV=1001) + torch.cat([context, Pg]) and its
  *           autograd backward, examples/utils_bpp_acc.py:644-687 (K1 / K2 with per-point start level, gridencoder.cu:118-126).

@@ -419,3 +419,25 @@ def test_fused_context_gather_equals_forward_diff_levels(cuda):
     for a, b in zip(out[True][1] + out[True][2], out[False][1] + out[False][2]):
         assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-12
     assert float(out[True][1][0].abs().max()) > 0
+
+
+@pytest.mark.parametrize("K,N", [(17, 1000), (25, 70001), (33, 256), (33, 300000), (9, 5)])
+def test_lin8_kernels_vs_torch(cuda, K, N):
+    """cnc_lin8_fwd / _bwd (plane context models, csrc/context_lin8.cu) against nn.Linear + autograd in fp64"""
+    from cnc_b200.context_models import _linear8
+
+    torch.manual_seed(K + N)
+    lin = torch.nn.Linear(K, 8).to(cuda)
+    x = torch.randn(N, K, device=cuda, requires_grad=True)
+    gy = torch.randn(N, 8, device=cuda)
+    y = _linear8(lin, x)
+    assert "Lin8" in type(y.grad_fn).__name__
+    y.backward(gy)
+    got = (y.detach(), x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+    lin64 = torch.nn.Linear(K, 8).to(cuda).double()
+    lin64.load_state_dict({k: v.double() for k, v in lin.state_dict().items()})
+    x64 = x.detach().double().requires_grad_(True)
+    y64 = lin64(x64)
+    y64.backward(gy.double())
+    for a, b in zip(got, (y64.detach(), x64.grad, lin64.weight.grad, lin64.bias.grad)):
+        assert float((a.double() - b).abs().max()) <= 2e-6 * float(b.abs().max()) * max(1.0, (N / 1e4) ** 0.5)
