@@ -850,7 +850,9 @@ class CNC_context_models(nn.Module):
             context = torch.cat([context, Pg_col], dim=-1)
         # index_select by the sort permutation + per-row sum (utils_bpp_acc.py:741-745) as one segment reduction
         cs = torch.cat([torch.zeros(1, dtype=torch.int64, device=points_n.device), torch.cumsum(unique_cnt_2D, 0)])
-        mean = segment_sum.apply(_linear8(self.context_model_2D[n - 1][0], context), cs, None, indices_2D.contiguous())
+        lin = self.context_model_2D[n - 1][0]
+        mean = segment_sum.apply(_linear8(lin, context) if getattr(self, "fused_lin8", True) else lin(context), cs, None,
+                                 indices_2D.contiguous())
         return mean / unique_cnt_2D.unsqueeze(-1), unique_value_2D, (points_n, indices_2D, unique_value_2D, unique_cnt_2D)
 
     # ------------------------------------------------------------------------------------------ loss

@@ -210,10 +210,14 @@ def _codec_pair(ref, dev, res3, log2T, res2, log2T2, skip3, radius, seed=0, samp
     cm_r = ref.bpp.CNC_context_models(**kw).cuda()
     torch.manual_seed(seed + 100)
     cm_o = CNC_context_models(**kw, Rb=128, device=dev)
-    with torch.no_grad():   # context models that give non-trivial, valid probabilities; identical on both sides
+    with torch.no_grad():
+        # context models that give non-trivial, valid probabilities, identical on both sides -- and well inside (0, 1):
+        # d bits / d p = -1 / (p ln 2), so an entry whose predicted probability sits within 1e-5 of the clamp at 1e-6 turns a
+        # rounding-level difference of p (3e-7: cuBLAS vs any other summation order) into a 30 % difference of its gradient,
+        # and those entries carry the largest gradients of all.  Weights scaled so that p stays in 0.6 +- 0.3.
         for m in list(cm_o.context_model_3D) + [l for s in cm_o.context_model_2D for l in s]:
             if isinstance(m, torch.nn.Linear):
-                m.weight.mul_(0.5)
+                m.weight.mul_(0.25)
         cm_o.context_model_3D[4].bias.fill_(0.6)
         for s in cm_o.context_model_2D:
             s[0].bias.fill_(0.6)
@@ -321,11 +325,11 @@ def _check_encode(ref, pair_o, pair_r, vxl, tmp_path, label):
             n_ident += 1
         else:
             p_o = None
-            d = (c1_r.to(torch.int32) != c1.to(torch.int32))
+            d = ((c1_r.to(torch.int32) & 0xFFFF) != (c1.to(torch.int32) & 0xFFFF))
             n_diff += int(d.sum())
             n_tot += d.numel()
             # probabilities to 1e-5: compare on the 16-bit grid the coder sees (1 step = 1.5e-5) -> at most one step apart
-            assert int((c1_r.to(torch.int32) - c1.to(torch.int32)).abs().max()) <= 1, name
+            assert int(((c1_r.to(torch.int32) & 0xFFFF) - (c1.to(torch.int32) & 0xFFFF)).abs().max()) <= 1   # (the uint16 entries travel as int16), name
             assert abs(len(bytes_r) - len(bytes_o)) <= max(8, 1e-4 * len(bytes_r)), name
         assert len(bytes_o) > 0
     assert abs(est_r - est_o) <= 1e-5 * est_r and abs(coded_r - coded_o) <= 1e-4 * coded_r
