@@ -186,7 +186,7 @@ class Arm:
             self.render_train, self.render_test = r.utils.render_image_with_occgrid, r.utils.render_image_with_occgrid_test
             self.cm_kw = {}
 
-    def field(self, seed=0):
+    def field(self, seed=0, F=F):
         torch.manual_seed(seed)
         f = self.Field(aabb=[-1.5, -1.5, -1.5, 1.5, 1.5, 1.5], n_features_per_level=F, n_neurons=160, resolutions_list=R3,
                        log2_hashmap_size=19, resolutions_list_2D=R2, log2_hashmap_size_2D=17, ste_binary=True).to(self.dev)
@@ -778,6 +778,27 @@ def main():
         for p in params:
             p.grad = None
         model.eval()
+    # secondary sizes / layouts (N_s = 150 000 as well; --n_features 2 of the training scripts: the fused kernel is
+    # specialised for F = 8 / 160 neurons, other layouts run K1 on the sign planes + cuBLAS nn.Linear)
+    other = None
+    if world == 1 and not a.no_e2e:
+        model.eval()
+        p15, d15 = pos[:150000].contiguous(), dirs[:150000].contiguous()
+        with torch.no_grad():
+            for _ in range(3):
+                model(p15, d15)
+            ms15 = timed(lambda: model(p15, d15), a.steps) / a.steps
+        f2 = arm.field(seed=0, F=2).eval()
+        with torch.no_grad():
+            for _ in range(3):
+                f2(pos, dirs)
+            ms_f2 = timed(lambda: f2(pos, dirs), a.steps) / a.steps
+        other = {"samples_150000": {"ms_per_step": ms15, "samples_per_s": 150000 / (ms15 * 1e-3)},
+                 "n_features_2": {"what": "same 12 + 3 x 4 level layout with F = 2 (MLP 87-160-20 / 35-160-160-3), 262 144 samples"
+                                          + ("; NOT the fused kernel: GridEncoder on sign planes (K1) + torch nn.Linear" if a.impl == "ours" else ""),
+                                  "ms_per_step": ms_f2, "samples_per_s": Ns / (ms_f2 * 1e-3)}}
+        del f2
+        torch.cuda.empty_cache()
     train = None
     if a.train_steps > 0 and not a.no_e2e and (a.impl == "ours" or world == 1):
         train = train_bench(arm, rank, world, a.train_steps, field)
@@ -848,6 +869,8 @@ def main():
                                           "implementation of this path; its CPU piece is the entropy coder (codec.coder)"}
     elif world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
+    if other is not None:
+        line["other_workloads"] = other
     if fwd_bwd is not None:
         line["fwd_bwd"] = fwd_bwd
     if train is not None:
