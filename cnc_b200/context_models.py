@@ -424,7 +424,7 @@ class CNC_context_models(nn.Module):
                     pts = pts[shuffle_idx]
             entry_of_row = None
             T_i = self.offs[i + 1] - self.offs[i]
-            if tables == "pruned" and not (rows.numel() == T_i and r > self.resolution_thresh):
+            if not (rows.numel() == T_i and r > self.resolution_thresh) and dev.type == "cuda":
                 entry_of_row = torch.full((T_i,), -1, dtype=torch.int32, device=dev)
                 entry_of_row[rows] = torch.arange(rows.numel(), dtype=torch.int32, device=dev)
             self.entry_of_row_list.insert(0, entry_of_row)
@@ -522,13 +522,30 @@ class CNC_context_models(nn.Module):
             cache[1][n] = (pts, ent.to(torch.int64), seg, ent.cpu().numpy(), seg.cpu().numpy())
         return cache[1][n]
 
+    def _pruned_weights(self, n, vx, binary_vxl):
+        """per-vertex weights of the overlap-weighted mean over an entry's vertices (utils_bpp_acc.py:672-682), for the
+        pruned list of level n: clamp(overlap, 1) / sum over the entry, or 1 / count.  Cached with the list."""
+        pts, ent, seg, _, _ = self._pruned_level(n, vx)
+        cache = self._pruned_cache[1]
+        if ("w", n) not in cache:
+            cnt = seg[1:] - seg[:-1]
+            if self.use_overlap_area_pool:
+                _, overlap = self.query_binary_vxl(pts, binary_vxl, n, return_overlap_area=True)
+                ov = torch.clamp(overlap, min=1).to(torch.float)
+                ov_sum = pack_and_align.segment_wsum(ov.unsqueeze(-1), seg).squeeze(-1)
+                w = ov / torch.repeat_interleave(ov_sum, cnt, output_size=pts.shape[0])
+            else:
+                w = torch.repeat_interleave(1.0 / cnt.to(torch.float), cnt, output_size=pts.shape[0])
+            cache[("w", n)] = (w.contiguous(), torch.full((pts.shape[0],), n, dtype=torch.int64, device=pts.device))
+        return cache[("w", n)]
+
     def table_bytes(self) -> int:
         """device bytes held by the inverse hash tables right now (vertex lists + per-entry arrays + pruned caches)"""
         ts = [t for lst in (self.unique_value_list, self.unique_count_list, self.unique_count_cumsum_list, self.pos_grid_sorted_list,
                             self.entry_of_row_list) for t in lst if t is not None]
         cache = getattr(self, "_pruned_cache", None)
         if cache is not None:
-            ts += [t for v in cache[1].values() for t in v[:3]]
+            ts += [t for v in cache[1].values() for t in v[:3] if isinstance(t, torch.Tensor)]
         return sum(t.numel() * t.element_size() for t in ts)
 
     def layout(self) -> dict:
@@ -859,7 +876,6 @@ class CNC_context_models(nn.Module):
     def forward_binary_vxl_mixPg_3D2D(self, Encoding_xyz, Encoding_xy, Encoding_xz, Encoding_yz, binary_vxl=None,
                                       verbose=False, sample_num=None, step=0):
         """Rate term of the training loss: (bits per parameter, MB).  utils_bpp_acc.py:533-706"""
-        self._ensure_full_tables()
         pq = {k: self.get_STE_params(E) for k, E in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz), ("xyz", Encoding_xyz))}
         refresh = step % self.step_update == 0 or self.idx_coords2_tmp is None
         if refresh:   # the reference caches the voxel list for step_update steps (:541-543): keep the occupancy it stands for
@@ -898,8 +914,47 @@ class CNC_context_models(nn.Module):
         start, snl_h = torch.stack([start, snl.to(torch.long)]).tolist()   # one device->host read for both
         fast = (self.n_features == 8 and self.max_context_layer_num == 3 and Encoding_xyz.ste_binary
                 and getattr(self, "fused_gather_train", True) and min([n for n in range(self.n_levels) if n not in self.skip_levels_3D] + [99]) >= 3)
-        pts_l, ptsn_l, Pg_l, n_l, cnt_l, val_l = [], [], [], [], [], []
         Pgs_3D, bits_3D = self.level_entropies(pq["xyz"])
+        if fast and pq["xyz"].is_cuda and getattr(self, "cached_selection_train", True):
+            # The vertices of the sampled entries that touch the occupancy, and their pooling weights, depend on the occupancy
+            # grid only: they are the pruned vertex lists of section 3.7 (built once per grid, i.e. every `step_update` steps in
+            # the training loop) -- a window of entries is a SLICE of them.  The reference (and the path below) enumerates,
+            # masks (K7) and compacts ~8.6 M candidate vertices every step to arrive at the same lists.
+            vx = binary_vxl.squeeze(0)
+            vx = (vx if vx.dtype in (torch.bool, torch.uint8) else vx != 0).contiguous()
+            pts_l, w_l, n_l, cnt_l, val_l = [], [], [], [], []
+            for n in range(self.n_levels):
+                if n in self.skip_levels_3D or n >= self.Pg_level:
+                    ttl_bit_sum = ttl_bit_sum + bits_3D[n]
+                    continue
+                lo, hi = start[n], start[n] + int(snl_h[n])
+                pts_n, ent, seg, ent_h, seg_h = self._pruned_level(n, vx)
+                w_n, lev_n = self._pruned_weights(n, vx, binary_vxl)
+                a_, b_ = int(np.searchsorted(ent_h, lo)), int(np.searchsorted(ent_h, hi))
+                v0, v1 = int(seg_h[a_]), int(seg_h[b_])
+                pts_l.append(pts_n[v0:v1])
+                w_l.append(w_n[v0:v1])
+                n_l.append(lev_n[v0:v1])
+                cnt_l.append(seg[a_ + 1:b_ + 1] - seg[a_:b_])
+                val_l.append(self.unique_value_list[n][ent[a_:b_]] + self.offs[n])
+            if pts_l and sum(p.shape[0] for p in pts_l):
+                pts, w, nl, cnt, rows3 = (torch.cat(t, 0) for t in (pts_l, w_l, n_l, cnt_l, val_l))
+                vals = pq["xyz"][rows3]
+                cs = torch.cat([torch.zeros(1, dtype=torch.int64, device=pts.device), torch.cumsum(cnt, 0)])
+                vbits, vbit_off = self._vertex_bits(Encoding_xyz, vx)
+                ctx_in = _Ctx3DGather.apply(Encoding_xyz.params, torch.stack(Pgs_3D), pts, nl, Encoding_xyz, vbits, vbit_off)
+                m3 = self.context_model_3D
+                if getattr(self, "fused_mlp_train", True):
+                    mlp_out = _CtxMLP3.apply(ctx_in, m3[0].weight, m3[0].bias, m3[2].weight, m3[2].bias, m3[4].weight, m3[4].bias)
+                else:
+                    mlp_out = m3(ctx_in)
+                mean = segment_sum.apply(mlp_out, cs, w, None)
+                bits = torch.sum(self.entropy_model(vals, mean))
+                ttl_bit_sum = ttl_bit_sum + bits / n_valid * self.ttl_hashparams_num_valid_levels
+            ttl_num_sum += pq["xyz"].numel()
+            return ttl_bit_sum / ttl_num_sum, float(ttl_bit_sum.detach()) / 8 / 1024 / 1024
+        self._ensure_full_tables()
+        pts_l, ptsn_l, Pg_l, n_l, cnt_l, val_l = [], [], [], [], [], []
         for n in range(self.n_levels):
             Pg_n, bit_n = Pgs_3D[n], bits_3D[n]
             if n in self.skip_levels_3D or n >= self.Pg_level:
