@@ -436,7 +436,7 @@ def codec_bench(arm, cpu_seconds=12.0, rank=0, world=1, dist=None):
         ach = bytes_alg / (sum(ms_l) * 1e-3) / 1e9
         res["roofline"] = {"bound": "hbm", "kernel": "cnc::context3d_kernel (mask + 3-level masked gather + 25-32-32-8 MLP + overlap-weighted mean)",
                            "achieved": ach, "peak": hbm_peak, "peak_source": which, "unit": "GB/s", "frac": ach / hbm_peak,
-                           "traffic": ncu_traffic("context3d_kernel", "encode"), "launches": len(ms_l),
+                           "traffic": ncu_traffic("context3d_kernel", 524288), "traffic_what": "one launch (a 524 288-entry chunk, profiles/r01_v11_ncu_context3d.txt)", "launches": len(ms_l),
                            "ms_all_launches": sum(ms_l), "voxels": vox, "entries": ent, "algorithmic_bytes": bytes_alg,
                            "note": "the context tables are read as 1-bit planes from L2, so DRAM traffic << algorithmic bytes; the "
                                    "kernel is FFMA-issue bound (2080 FMA per voxel), see profiles/"}

@@ -31,6 +31,8 @@ SIGNATURES = {
     "cnc_lin8_bwd": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "cnc_ctx3d_gather_fwd": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "cnc_ctx3d_gather_bwd": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "cnc_ctx2d_gather_fwd": [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp],
+    "cnc_ctx2d_gather_bwd": [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "cnc_wavefront_begin": [_vp, _u32, _u32, _u32, _vp],
     "cnc_wavefront_march": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _u32,
                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -270,6 +270,39 @@ class _Ctx3DGather(Function):
         return g_params, g_pg, None, None, None, None, None
 
 
+class _Ctx2DGather(Function):
+    """[vertices, 8c (+8) + 1] input of a plane context model: c coarser plane levels | vote fraction plane | Pg, and its
+    backward (csrc/context_train.cu).  `params` = the plane's latent table when it is the encoder's own (gradient: K2 + STE
+    window), else a caller-provided +-1 table (decode: no gradient)."""
+
+    @staticmethod
+    def forward(ctx, params, frac, Pg_n, pts, enc, n, c, vxl2, res_frac, own):
+        N = pts.shape[0]
+        K = 8 * c + (8 if frac is not None else 0) + 1
+        x = torch.empty(N, K, device=pts.device, dtype=torch.float32)
+        bits = enc.sign_bits() if own else _backend.sign_pack(params.detach().contiguous())
+        fr = None if frac is None else frac.detach().contiguous().float()
+        pg = Pg_n.detach().reshape(1).contiguous().float()
+        check(lib().cnc_ctx2d_gather_fwd(ptr(pts), N, ptr(bits), ptr(enc.offsets_list), ptr(enc.resolutions_list), n, c, ptr(vxl2),
+                                         vxl2.shape[-1], ptr(fr), res_frac, ptr(pg), ptr(x), stream()))
+        ctx.save_for_backward(params, pts, vxl2)
+        ctx.enc, ctx.dims, ctx.frac_shape = enc, (n, c, K, res_frac), None if frac is None else tuple(frac.shape)
+        return x
+
+    @staticmethod
+    def backward(ctx, gx):
+        params, pts, vxl2 = ctx.saved_tensors
+        enc, (n, c, K, res_frac) = ctx.enc, ctx.dims
+        gx = gx.contiguous()
+        ge = torch.zeros_like(params)
+        gf = None if ctx.frac_shape is None else torch.zeros(ctx.frac_shape, device=gx.device, dtype=torch.float32)
+        gpg = torch.zeros(1, device=gx.device, dtype=torch.float32)
+        check(lib().cnc_ctx2d_gather_bwd(ptr(pts), pts.shape[0], ptr(enc.offsets_list), ptr(enc.resolutions_list), n, c, ptr(vxl2),
+                                         vxl2.shape[-1], res_frac, ptr(gx), ptr(ge), ptr(gf), ptr(gpg), stream()))
+        g_params = _backend.ste_binary_backward(params.contiguous(), ge) if ctx.needs_input_grad[0] else None
+        return g_params, gf, gpg.reshape(()), None, None, None, None, None, None, None
+
+
 _LEVEL_CONST = {}
 
 
@@ -639,6 +672,7 @@ class CNC_context_models(nn.Module):
         self.idx_coord_base = my_meshgrid3D(-1, t + 1, dev).view(1, -1, 3)
         self.pn_frac_offsets_list = torch.tensor([0, resolution * resolution], device=dev, dtype=torch.int32)
         self.pn_frac_resolutions_list = torch.tensor([resolution], device=dev, dtype=torch.int32)
+        self.pn_frac_resolutions_list_host = resolution
 
     def get_idx_coords2(self, binary_vxl, resolution=None):
         """utils_bpp_acc.py:498-512: all finest-level voxels inside occupied occupancy cells (+halo), unique."""
@@ -855,16 +889,26 @@ class CNC_context_models(nn.Module):
         else:
             points_n, indices_2D, unique_value_2D, unique_cnt_2D = batch
         c = min(n, self.max_context_layer_num)
-        context = Encoding_2D(points_n, n - c, n, outspace_params=table_2D, binary_vxl=binary_vxl_2D, PV=0)
-        Pg_col = Pg_n.reshape(1, 1).expand(context.shape[0], 1)
-        if self.use_dimension_wise:
-            context_pn = Encoding_2D.forward_given_params(points_n, self.pn_frac_offsets_list, self.pn_frac_resolutions_list,
-                                                          pn_embed_frac, binary_vxl_2D)
-            if not differentiable:
-                context_pn = context_pn.detach()
-            context = torch.cat([context, context_pn, Pg_col], dim=-1)
+        if (self.n_features == 8 and Encoding_2D.ste_binary and points_n.is_cuda and getattr(self, "fused_gather2d", True)):
+            # one kernel: c plane levels | vote fraction plane | Pg  ->  [N, K]   (csrc/context_train.cu)
+            vx2 = (binary_vxl_2D if binary_vxl_2D.dtype in (torch.bool, torch.uint8) else binary_vxl_2D != 0).contiguous()
+            own = table_2D is None
+            frac = pn_embed_frac if self.use_dimension_wise else None
+            if frac is not None and not differentiable:
+                frac = frac.detach()
+            context = _Ctx2DGather.apply(Encoding_2D.params if own else table_2D, frac, Pg_n, points_n.contiguous().float(),
+                                         Encoding_2D, n, c, vx2, int(self.pn_frac_resolutions_list_host), own)
         else:
-            context = torch.cat([context, Pg_col], dim=-1)
+            context = Encoding_2D(points_n, n - c, n, outspace_params=table_2D, binary_vxl=binary_vxl_2D, PV=0)
+            Pg_col = Pg_n.reshape(1, 1).expand(context.shape[0], 1)
+            if self.use_dimension_wise:
+                context_pn = Encoding_2D.forward_given_params(points_n, self.pn_frac_offsets_list, self.pn_frac_resolutions_list,
+                                                              pn_embed_frac, binary_vxl_2D)
+                if not differentiable:
+                    context_pn = context_pn.detach()
+                context = torch.cat([context, context_pn, Pg_col], dim=-1)
+            else:
+                context = torch.cat([context, Pg_col], dim=-1)
         # index_select by the sort permutation + per-row sum (utils_bpp_acc.py:741-745) as one segment reduction
         cs = torch.cat([torch.zeros(1, dtype=torch.int64, device=points_n.device), torch.cumsum(unique_cnt_2D, 0)])
         lin = self.context_model_2D[n - 1][0]

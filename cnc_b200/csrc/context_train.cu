@@ -119,6 +119,113 @@ __global__ void __launch_bounds__(256) ctx3d_gather_bwd_kernel(const Args a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Plane context of the rate term / codec (utils_bpp_acc.py:551-558, :731-738): for every plane vertex of the occupied
+// region, the c coarser levels of the plane encoder (masked bilinear gather, K1 with D = 2) | the +1 vote fraction plane of the
+// dimension-wise context sampled at the vertex (Encoding_2D.forward_given_params: K1 over a float table, one dense level)
+// | Pg  ->  [N, 8c + 8 + 1] in one kernel, and the matching backward (K2 into the plane table, K2 into the fraction plane,
+// column sum for Pg).  Replaces two K1 launches, a permute-reshape each, expand and cat (108 MB per call at level 3) and, in
+// the backward, two zero-fills, two K2 launches and the slicing of the [N, K] gradient.  Arithmetic = make_corners<2>.
+// ------------------------------------------------------------------------------------------
+struct Args2 {
+    const float *pts;          // [N,2] normalised vertex coordinates
+    const uint8_t *sign_bits;  // sign plane of the whole plane table
+    const int32_t *offsets, *resolutions;
+    const uint8_t *vxl2;       // [Rb,Rb] occupancy of the plane
+    const float *frac;         // [res_f^2, 8] vote fraction plane (nullable: no dimension-wise context)
+    const float *Pg;           // 1 float
+    float *x;                  // fwd out [N,K]
+    const float *gx;           // bwd in  [N,K]
+    float *grad_table;         // bwd out [rows,8]   (accumulated into)
+    float *grad_frac;          // bwd out [res_f^2,8] (accumulated into; nullable)
+    float *g_pg;               // bwd out 1 float (accumulated into)
+    int64_t N;
+    int32_t level, c, K, Rb, res_f;
+};
+
+__device__ __forceinline__ bool corners2_of(const Args2 &a, int64_t v, int slot, LevelConst &lc, Corners<2> &cs) {
+    if (slot < a.c) {
+        lc = load_level(a.offsets, a.resolutions, (uint32_t)(a.level - a.c + slot));
+    } else {   // the fraction plane: one dense level of res_f^2 rows
+        lc.base_row = 0;
+        lc.res = (uint32_t)a.res_f;
+        lc.T = lc.res * lc.res;
+        lc.scale = (float)(lc.res - 2u);
+        lc.scale_re = __frcp_rn(lc.scale);
+    }
+    const float xi[2] = {__ldg(a.pts + v * 2), __ldg(a.pts + v * 2 + 1)};
+    return make_corners<2>(xi, lc, (uint32_t)a.Rb, a.vxl2, cs);
+}
+
+__global__ void __launch_bounds__(256) ctx2d_gather_fwd_kernel(const Args2 a) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.N) return;
+    const int slot = blockIdx.y;
+    LevelConst lc;
+    Corners<2> cs;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = 0.f;
+    if (corners2_of(a, v, slot, lc, cs)) {
+        if (slot < a.c) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if ((cs.valid >> i) & 1u) {
+                    const uint32_t sb = __ldg(a.sign_bits + (uint64_t)lc.base_row + cs.row[i]);
+                    const float ww = __fmul_rn(cs.w[i], cs.wn_re);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) acc[k] = __fadd_rn(acc[k], ((sb >> k) & 1u) ? ww : -ww);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if ((cs.valid >> i) & 1u) {
+                    const float4 *r = reinterpret_cast<const float4 *>(a.frac + (size_t)cs.row[i] * 8);
+                    const float4 r0 = __ldg(r), r1 = __ldg(r + 1);
+                    const float t[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                    const float ww = __fmul_rn(cs.w[i], cs.wn_re);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) acc[k] = __fmaf_rn(ww, t[k], acc[k]);   // gridencoder.cu:301
+                }
+            }
+        }
+    }
+    float *o = a.x + v * a.K + slot * 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++) o[k] = acc[k];
+    if (slot == 0) a.x[v * a.K + a.K - 1] = __ldg(a.Pg);
+}
+
+__global__ void __launch_bounds__(256) ctx2d_gather_bwd_kernel(const Args2 a) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot = blockIdx.y;
+    if (slot == 0) {
+        float g = v < a.N ? __ldg(a.gx + v * a.K + a.K - 1) : 0.f;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) g = __fadd_rn(g, __shfl_xor_sync(0xffffffffu, g, d));
+        if ((threadIdx.x & 31) == 0) atomicAdd(a.g_pg, g);
+    }
+    if (v >= a.N) return;
+    LevelConst lc;
+    Corners<2> cs;
+    if (!corners2_of(a, v, slot, lc, cs)) return;
+    float g[8];
+    const float *gi = a.gx + v * a.K + slot * 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++) g[k] = __ldg(gi + k);
+    float *gt = slot < a.c ? a.grad_table + (size_t)lc.base_row * 8 : a.grad_frac;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if ((cs.valid >> i) & 1u) {
+            const float ww = __fmul_rn(cs.w[i], cs.wn_re);
+            float4 *p = reinterpret_cast<float4 *>(gt + (size_t)cs.row[i] * 8);
+            atomicAdd(p, make_float4(__fmul_rn(ww, g[0]), __fmul_rn(ww, g[1]), __fmul_rn(ww, g[2]), __fmul_rn(ww, g[3])));
+            atomicAdd(p + 1, make_float4(__fmul_rn(ww, g[4]), __fmul_rn(ww, g[5]), __fmul_rn(ww, g[6]), __fmul_rn(ww, g[7])));
+        }
+    }
+}
+
 }  // namespace ct
 }  // namespace cnc
 
@@ -151,6 +258,43 @@ int cnc_ctx3d_gather_bwd(const int16_t *pts, const int64_t *level, int64_t M, co
     ct::Args a{pts, level, nullptr, offsets, resolutions, vertex_bits, vertex_bit_offsets, nullptr, nullptr, gx, grad_table, grad_pg, M};
     ct::ctx3d_gather_bwd_kernel<<<dim3(div_up((uint64_t)M, 256), 3), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return check_launch("ctx3d_gather_bwd");
+}
+
+int cnc_ctx2d_gather_fwd(const float *pts, int64_t N, const uint8_t *sign_bits, const int32_t *offsets, const int32_t *resolutions,
+                         int32_t level, int32_t n_ctx_levels, const uint8_t *binary_vxl_2D, int32_t Rb, const float *frac, int32_t res_frac,
+                         const float *Pg, float *x, cnc_stream_t stream) {
+    if (N == 0) return CNC_OK;
+    if (!pts || !sign_bits || !offsets || !resolutions || !binary_vxl_2D || !Pg || !x || n_ctx_levels < 0 || n_ctx_levels > level || Rb < 1 ||
+        (frac && res_frac < 3)) {
+        set_error("ctx2d_gather_fwd: bad argument");
+        return CNC_EINVAL;
+    }
+    const int slots = n_ctx_levels + (frac ? 1 : 0);
+    if (slots == 0) { set_error("ctx2d_gather_fwd: nothing to gather"); return CNC_EINVAL; }
+    if (frac && (reinterpret_cast<uintptr_t>(frac) & 15u)) { set_error("ctx2d_gather_fwd: frac must be 16-byte aligned"); return CNC_EINVAL; }
+    ct::Args2 a{pts, sign_bits, offsets, resolutions, binary_vxl_2D, frac, Pg, x, nullptr, nullptr, nullptr, nullptr, N, level, n_ctx_levels,
+                8 * slots + 1, Rb, res_frac};
+    ct::ctx2d_gather_fwd_kernel<<<dim3(div_up((uint64_t)N, 256), slots), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("ctx2d_gather_fwd");
+}
+
+int cnc_ctx2d_gather_bwd(const float *pts, int64_t N, const int32_t *offsets, const int32_t *resolutions, int32_t level,
+                         int32_t n_ctx_levels, const uint8_t *binary_vxl_2D, int32_t Rb, int32_t res_frac, const float *gx, float *grad_table,
+                         float *grad_frac, float *grad_pg, cnc_stream_t stream) {
+    if (N == 0) return CNC_OK;
+    if (!pts || !offsets || !resolutions || !binary_vxl_2D || !gx || !grad_table || !grad_pg || n_ctx_levels < 0 || n_ctx_levels > level || Rb < 1) {
+        set_error("ctx2d_gather_bwd: bad argument");
+        return CNC_EINVAL;
+    }
+    const int slots = n_ctx_levels + (grad_frac ? 1 : 0);
+    if ((reinterpret_cast<uintptr_t>(grad_table) & 15u) || (grad_frac && (reinterpret_cast<uintptr_t>(grad_frac) & 15u))) {
+        set_error("ctx2d_gather_bwd: gradient buffers must be 16-byte aligned");
+        return CNC_EINVAL;
+    }
+    ct::Args2 a{pts, nullptr, offsets, resolutions, binary_vxl_2D, nullptr, nullptr, nullptr, gx, grad_table, grad_frac, grad_pg, N, level,
+                n_ctx_levels, 8 * slots + 1, Rb, res_frac};
+    ct::ctx2d_gather_bwd_kernel<<<dim3(div_up((uint64_t)N, 256), slots), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("ctx2d_gather_bwd");
 }
 
 }  // extern "C"

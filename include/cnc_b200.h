@@ -113,6 +113,19 @@ int cnc_ctx3d_gather_bwd(const int16_t *pts, const int64_t *level, int64_t M, co
                          const uint32_t *vertex_bits, const int64_t *vertex_bit_offsets, const float *gx, float *grad_table,
                          float *grad_pg, cnc_stream_t stream);
 
+/* Plane context (utils_bpp_acc.py:551-558, :731-738) in one kernel each way:
+ * replaces: Encoding_2D(points, n - c, n, binary_vxl_2D) + Encoding_2D.forward_given_params(points, ..., pn_embed_frac,
+ *           binary_vxl_2D) + expand + torch.cat, and their autograd backward (2 x K1 / K2 with D = 2, ngp.py:228-315).
+ *   pts [N,2] normalised plane vertices; sign_bits / offsets / resolutions of the plane encoder; level n, n_ctx_levels c (levels
+ *   n-c..n-1); binary_vxl_2D [Rb,Rb]; frac [res_frac^2, 8] f32 (nullable: no dimension-wise context), Pg 1 float (device).
+ *   fwd: x [N, 8c (+8) + 1].  bwd: grad_table [rows,8] +=, grad_frac [res_frac^2,8] += (nullable), grad_pg [1] += (caller zeroes). */
+int cnc_ctx2d_gather_fwd(const float *pts, int64_t N, const uint8_t *sign_bits, const int32_t *offsets, const int32_t *resolutions,
+                         int32_t level, int32_t n_ctx_levels, const uint8_t *binary_vxl_2D, int32_t Rb, const float *frac,
+                         int32_t res_frac, const float *Pg, float *x, cnc_stream_t stream);
+int cnc_ctx2d_gather_bwd(const float *pts, int64_t N, const int32_t *offsets, const int32_t *resolutions, int32_t level,
+                         int32_t n_ctx_levels, const uint8_t *binary_vxl_2D, int32_t Rb, int32_t res_frac, const float *gx,
+                         float *grad_table, float *grad_frac, float *grad_pg, cnc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Test-time wavefront renderer without host round trips.
  * replaces: the python loop of render_image_with_occgrid_test, examples/utils.py:395-479 (per round: ray_mask.sum().item(),

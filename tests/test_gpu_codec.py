@@ -441,3 +441,29 @@ def test_lin8_kernels_vs_torch(cuda, K, N):
     y64.backward(gy.double())
     for a, b in zip(got, (y64.detach(), x64.grad, lin64.weight.grad, lin64.bias.grad)):
         assert float((a.double() - b).abs().max()) <= 2e-6 * float(b.abs().max()) * max(1.0, (N / 1e4) ** 0.5)
+
+
+def test_fused_plane_gather_equals_the_two_k1_flow(cuda):
+    """`_Ctx2DGather` (c plane levels | vote fraction plane | Pg in one kernel, csrc/context_train.cu) against
+    Encoding_2D(...) + forward_given_params(...) + cat on the drop-in K1/K2: same loss, gradients of the plane tables, of the
+    finest 3D level (through the vote planes) and of the context models to fp32 atomics order; same coded streams."""
+    cm, encs, vxl = make(cuda, res3=R3, log2T=19, res2=R2, log2T2=17, Rb=128, seed=4)
+    with torch.no_grad():   # keep the plane probabilities away from the clamp (see the A/B suite)
+        for s_ in cm.context_model_2D:
+            s_[0].weight.mul_(0.5)
+    out, streams = {}, {}
+    for fast in (True, False):
+        cm.fused_gather2d = fast
+        for p in [e.params for e in encs] + list(cm.parameters()):
+            p.grad = None
+        torch.manual_seed(9)
+        bpp, _ = cm.forward_binary_vxl_mixPg_3D2D(*encs, vxl, step=0, sample_num=20000)
+        bpp.backward()
+        out[fast] = (float(bpp), [e.params.grad.clone() for e in encs], [p.grad.clone() for p in cm.parameters()])
+        streams[fast] = cm.encode_binary_vxl_mixPg_3D2D(*encs, vxl, "g", return_streams=True)[3]
+    assert abs(out[True][0] - out[False][0]) <= 1e-6 * abs(out[False][0]), (out[True][0], out[False][0])
+    for a, b in zip(out[True][1] + out[True][2], out[False][1] + out[False][2]):
+        assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-12
+    assert all(float(g.abs().max()) > 0 for g in out[True][1])
+    assert list(streams[True]) == list(streams[False])
+    assert all(streams[True][k] == streams[False][k] for k in streams[True])    # identical features -> identical bytes
