@@ -9,21 +9,26 @@
 // SGEMMs with a [N,255] activation round trip through HBM; here the 255-wide activation never
 // leaves the SM.
 //
-// B200 mapping
-//   * persistent grid, one CTA per SM, one tile = 128 samples = one UMMA M tile.
-//   * warps 0-3 (128 threads, thread t <-> sample row t <-> TMEM lane t): gather + interpolate the
-//     features of a 32-column K chunk, split every value into tf32 hi + lo, store both into a
-//     128B-swizzled K-major smem slot (double buffered); later the layer epilogues
-//     (tcgen05.ld -> bias/ReLU -> hi/lo split -> tcgen05.st) that turn an accumulator into the
-//     next layer's A operand *inside TMEM*.
-//   * warp 4, one elected lane: streams the pre-split, pre-swizzled weight chunks with
-//     cp.async.bulk (TMA bulk copy, mbarrier complete_tx) through a 4-stage smem ring and issues
-//     tcgen05.mma kind::tf32 (M=128, N=160/80/16, K=8).  fp32 parity comes from the 3xTF32
-//     error-compensated split  A*B ~= Ahi*Blo + Alo*Bhi + Ahi*Bhi  with fp32 accumulation in TMEM.
-//   * TMEM (512 columns) is recycled layer to layer:
-//       L1 acc [0,160) -> h1 hi in place, lo [160,320);  L2 acc [320,400);
-//       head input hi [0,96), lo [96,192);  L3 acc [192,352) -> hi in place, lo [352,512);
-//       L4 acc [0,160) -> hi in place, lo [160,320);  L5 acc [320,336).
+// B200 mapping (as built; DESIGN.md 3.1 has the measurements behind each choice)
+//   * persistent grid, one CTA per SM (576 threads), one tile = 128 samples = one UMMA M tile.
+//   * warps 0-15, the gather / epilogue warps: thread (r, q) = sample row r (= TMEM lane) x octet q of a 32-column K chunk.
+//     Per chunk it gathers one level of one encoder (8 features from 1-bit sign planes; the corner bytes are loaded one
+//     chunk ahead), splits every value into a tf32 hi word and a bf16 (hi, lo) pair word and stores both into a
+//     128B-swizzled, double-buffered smem operand slot; chunks 6-7 are the 63 sin/cos columns.  The same warps run the
+//     layer epilogues (tcgen05.ld -> bias / ReLU -> split -> tcgen05.st) that turn an accumulator into the next layer's A
+//     operand *inside TMEM*, and pre-gather chunks 0-1 of the CTA's next tile while layers 2 and 4 run.
+//   * warp 16, the MMA warp (warp-uniform control flow, one elected lane issues): per k-step ONE kind::tf32 MMA
+//     (Ahi*Bhi, K = 8) and ONE kind::f16 MMA on the bf16 pairs (Ahi*Blo + Alo*Bhi, K = 16) into different TMEM
+//     accumulators -- fp32 parity from two half-rate MMAs instead of three.  Layer 1 reads A from smem, layers 2-4 from TMEM.
+//   * warp 17, the weight-stream warp: pre-split, pre-swizzled weight chunks by cp.async.bulk (mbarrier complete_tx)
+//     through a 2-stage smem ring (147 KB of shared memory in total, requested explicitly so that ~90 KB of the SM's
+//     array stay L1 for the byte gathers).
+//   * TMEM (all 512 columns) is recycled layer to layer: L1 main [0,160) / [160,320) (even / odd chunks), small [320,480);
+//     h1 hi in place [0,160), pairs [160,320); L2 acc [320,400) + [400,480); head input hi [0,96), pairs [96,192);
+//     L3 acc [192,352) + [352,512) -> h3 in place; L4 acc [0,160) (ep3 -> L4 wavefront per 32-column group);
+//     Linear(160,3) runs as FFMA in the last epilogue.
+//   * variants: DENSITY_ONLY (sigma pass of the sampler), SAVE (training forward: x0 / h1 / h3 / h4 / geo to HBM), POLL
+//     (host-buffer pipeline, cnc_field_fwd_host); the sample count may live in device memory (cnc_field_fwd_n).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>

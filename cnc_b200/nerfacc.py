@@ -271,6 +271,40 @@ class _RenderDensity(torch.autograd.Function):
         return None, None, (g_alpha - out) * dt, None, None
 
 
+class _RenderAll(torch.autograd.Function):
+    """weights / transmittance / alphas AND the three per-ray accumulations (colour, opacity, weighted depth) of
+    `rendering` (volrend.py:14-160) in one warp-per-ray pass -- no `index_add_` atomics, a fixed summation tree -- with the
+    analytic backward: d/dw_i = gC_r . c_i + gO_r + gD_r m_i, d/dc_i = w_i gC_r, then the backward of `_RenderDensity`."""
+
+    @staticmethod
+    def forward(ctx, t_starts, t_ends, sigmas, rgbs, packed_info, ray_indices):
+        t0, t1, sg, c = (x.contiguous().float() for x in (t_starts, t_ends, sigmas, rgbs))
+        need_cuda(t_starts=t0, t_ends=t1, sigmas=sg, rgbs=c)
+        R = packed_info.shape[0]
+        w, T, al = torch.empty_like(sg), torch.empty_like(sg), torch.empty_like(sg)
+        colors = torch.empty(R, 3, device=sg.device)
+        opac, depth = torch.empty(R, device=sg.device), torch.empty(R, device=sg.device)
+        check(lib().cnc_render_from_density(ptr(t0), ptr(t1), ptr(sg), ptr(c), ptr(packed_info), R, None, ptr(w), ptr(T), ptr(al),
+                                            ptr(colors), ptr(opac), ptr(depth), stream()))
+        ctx.save_for_backward(t0, t1, T, al, w, c, packed_info, ray_indices)
+        ctx.mark_non_differentiable(T, al)
+        return w, T, al, colors, opac, depth
+
+    @staticmethod
+    def backward(ctx, gw, gT, ga, gC, gO, gD):
+        t0, t1, T, al, w, c, packed_info, ri = ctx.saved_tensors
+        mid = (t0 + t1) * 0.5
+        gw_tot = (gC[ri] * c).sum(-1) + gO[ri] + gD[ri] * mid
+        if gw is not None:
+            gw_tot = gw_tot + gw
+        g_rgb = w.unsqueeze(-1) * gC[ri]
+        g_alpha = (gw_tot * T) * (1 - al)
+        g_trans = (gw_tot * al) * T
+        out = torch.empty_like(T)
+        check(lib().cnc_packed_scan(ptr(g_trans.contiguous()), ptr(packed_info), packed_info.shape[0], ptr(out), 0, 0, 1, stream()))
+        return None, None, (g_alpha - out) * (t1 - t0), g_rgb, None, None
+
+
 def render_weight_from_density(t_starts, t_ends, sigmas, packed_info=None, ray_indices=None, n_rays=None, prefix_trans=None):
     """(weights, trans, alphas).  nerfacc/volrend.py:314-364"""
     if t_starts.dim() != 1:
@@ -331,11 +365,17 @@ def rendering(t_starts, t_ends, ray_indices=None, n_rays=None, rgb_sigma_fn: Opt
         rgbs = torch.empty((0, 3), device=t_starts.device)
         sigmas = torch.empty((0,), device=t_starts.device)
     assert rgbs.shape[-1] == 3 and sigmas.shape == t_starts.shape
-    weights, trans, alphas = render_weight_from_density(t_starts, t_ends, sigmas, ray_indices=ray_indices, n_rays=n_rays)
-    extras = {"weights": weights, "alphas": alphas, "trans": trans, "sigmas": sigmas, "rgbs": rgbs, "positions": positions}
-    colors = accumulate_along_rays(weights, values=rgbs, ray_indices=ray_indices, n_rays=n_rays)
-    opacities = accumulate_along_rays(weights, values=None, ray_indices=ray_indices, n_rays=n_rays)
-    depths = accumulate_along_rays(weights, values=(t_starts + t_ends)[..., None] / 2.0, ray_indices=ray_indices, n_rays=n_rays)
+    if t_starts.dim() == 1 and ray_indices is not None and t_starts.is_cuda and t_starts.shape[0] != 0:
+        pk = _packed(None, ray_indices, n_rays, sigmas)
+        weights, trans, alphas, colors, opac, dsum = _RenderAll.apply(t_starts, t_ends, sigmas, rgbs, pk, ray_indices)
+        extras = {"weights": weights, "alphas": alphas, "trans": trans, "sigmas": sigmas, "rgbs": rgbs, "positions": positions}
+        opacities, depths = opac.unsqueeze(-1), dsum.unsqueeze(-1)
+    else:
+        weights, trans, alphas = render_weight_from_density(t_starts, t_ends, sigmas, ray_indices=ray_indices, n_rays=n_rays)
+        extras = {"weights": weights, "alphas": alphas, "trans": trans, "sigmas": sigmas, "rgbs": rgbs, "positions": positions}
+        colors = accumulate_along_rays(weights, values=rgbs, ray_indices=ray_indices, n_rays=n_rays)
+        opacities = accumulate_along_rays(weights, values=None, ray_indices=ray_indices, n_rays=n_rays)
+        depths = accumulate_along_rays(weights, values=(t_starts + t_ends)[..., None] / 2.0, ray_indices=ray_indices, n_rays=n_rays)
     depths = depths / opacities.clamp_min(torch.finfo(rgbs.dtype).eps)
     if render_bkgd is not None:
         colors = colors + render_bkgd * (1.0 - opacities)
