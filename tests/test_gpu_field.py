@@ -256,3 +256,29 @@ def test_dgrad_matches_fp64(cuda, ns, no, n, mask):
     err = ((got.double() - want).abs() / scale).max().item()
     err32 = (((ref32.double() * ((h > 0) if mask else 1.0)) - z.double() @ W[:, 3:3 + n].double() * ((h > 0) if mask else 1.0)).abs() / scale)[:, 1:].max().item()
     assert err <= max(4 * err32, 2e-6), (err, err32)
+
+
+def test_fused_training_density_gradient_is_capped_like_trunc_exp(cuda):
+    """trunc_exp's backward uses exp(min(h - 1, 15)) (ngp.py:328-334); the fused backward takes the density
+    itself as d density / d h, which must be capped at e^15 the same way once the pre-activation exceeds 16."""
+    f = make_field(cuda, seed=4)
+    f.train()
+    with torch.no_grad():
+        f.mlp_base.network[2].bias[0] = 19.0      # h - 1 ~ 18 > 15 for every sample
+    f.invalidate_caches()
+    pos, dirs = inputs(512, cuda, seed=6)
+    grads = {}
+    for mode in (True, False):
+        f.fused_train = mode
+        for p in f.parameters():
+            p.grad = None
+        rgb, sigma = f(pos, dirs)
+        assert float(sigma.max()) > 3.3e6          # beyond e^15
+        (sigma * 1e-7).sum().backward()
+        grads[mode] = f.mlp_base.network[2].weight.grad[0].clone(), f.mlp_base.network[2].bias.grad[0].clone()
+    (wa, ba), (wb, bb) = grads[True], grads[False]
+    assert torch.isfinite(wa).all() and float(bb) > 0
+    assert abs(float(ba) - float(bb)) <= 1e-4 * float(bb)
+    assert float((wa - wb).abs().max()) <= 1e-4 * float(wb.abs().max())
+    # with the uncapped derivative the bias gradient would be the sum of the densities themselves: ~e^18 / e^15 = 20x larger
+    assert float(ba) < 0.2 * float((sigma.detach() * 1e-7).sum())
