@@ -145,9 +145,6 @@ class _grid_encode_ste(Function):
         n_features = params.shape[1]
         outputs = torch.empty(n_levels_calc, N, n_features, device=inputs.device, dtype=torch.float32)
         offs, ress, mlid = _levels(offsets_list, resolutions_list, min_level_id, n_levels_calc)
-        if isinstance(min_level_id, int):
-            # the bit table is indexed by absolute row: keep absolute offsets, slice only the start
-            pass
         _backend.grid_encode_forward_bits(inputs, bits, offs.contiguous(), ress.contiguous(), outputs, N, num_dim,
                                           n_features, n_levels_calc, Rb, binary_vxl, mlid)
         outputs = outputs.permute(1, 0, 2).reshape(N, n_levels_calc * n_features)
