@@ -259,6 +259,15 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// one 256-bit global store (STG.E.256, sm_100): a full 32-byte sector per thread and instruction.  The training forward writes
+// 3.3 KB per sample row by row (thread = row), i.e. every warp store touches 32 different lines; as pairs of 16-byte stores
+// that was 7.5e7 half-sector requests per 380 k samples and the store path, not HBM, bounded the kernel (1.4 TB/s).
+__device__ __forceinline__ void st_global_v8(float *p, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
 // store 8 feature values (columns 8q..8q+7 of a 32-column chunk) of row r into the swizzled A slot
 __device__ __forceinline__ void store_oct(uint8_t *slot, int r, int q, const float (&f)[8]) {
     uint8_t *rowp = slot + (r >> 3) * 1024 + (r & 7) * 128;
@@ -336,10 +345,7 @@ __device__ __forceinline__ void ep_hidden(uint32_t tl, int cg, uint32_t c_main, 
             v[k] = fmaxf(__fadd_rn(v[k], bb[k]), 0.f);
             split_tf32(v[k], hi[k], lo[k]);
         }
-        if (save_row != nullptr) {
-            *reinterpret_cast<float4 *>(save_row + 8 * b) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4 *>(save_row + 8 * b + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        }
+        if (save_row != nullptr) st_global_v8(save_row + 8 * b, v);
         tmem_st8(tl + dst_hi + 8 * b, hi);
         tmem_st8(tl + dst_lo + 8 * b, lo);
         if (part_bar != 0u && b < 16) {   // this 32-column group is complete once all four column groups have stored
@@ -578,8 +584,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
         auto publish = [&](int c, uint32_t prow, const float (&f)[8]) {  // 8 feature values -> smem slot -> MMA warp
             if (SAVE && prow < Nrt) {   // column 255 (K padding, weight 0) is saved as 1: its weight-gradient row is the bias gradient
                 float *d = a.sv_x0 + (size_t)prow * 256 + 32 * c + 8 * q;
-                *reinterpret_cast<float4 *>(d) = make_float4(f[0], f[1], f[2], f[3]);
-                *reinterpret_cast<float4 *>(d + 4) = make_float4(f[4], f[5], f[6], (c == 7 && q == 3) ? 1.0f : f[7]);
+                const float fs[8] = {f[0], f[1], f[2], f[3], f[4], f[5], f[6], (c == 7 && q == 3) ? 1.0f : f[7]};
+                st_global_v8(d, fs);
             }
             const uint32_t sl = a_prod % NA, use = a_prod / NA;
             if (use > 0) mbar_wait(a_empty(sl), (use - 1) & 1u);
@@ -703,7 +709,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
             for (int b = q; b < 12; b += 4) {
                 uint32_t hi[8], lo[8];
                 if (b < 10) {
-                    float v[8];
+                    float v[8], hs[8];
                     acc_block<NONE, 400u>(tl, 320u, b, v);
                     const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + BIAS2 + 8 * b)),
                                  b1 = __ldg(reinterpret_cast<const float4 *>(bias + BIAS2 + 8 * b) + 1);
@@ -716,11 +722,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                             const float sg = __fmul_rn(expf(__fsub_rn(h, 1.0f)), sel ? 1.f : 0.f);
                             if (live) a.sigma[row] = sg;
                             h = 0.28198242f;  // SH band 0 (0.28209479 rounded to fp16) takes head-input column 0
-                        } else if (a.geo != nullptr && live) {
+                        } else if (!SAVE && a.geo != nullptr && live) {
                             a.geo[(size_t)row * 79 + (8 * b + k - 1)] = h;
                         }
+                        hs[k] = h;
                         split_tf32(h, hi[k], lo[k]);
                     }
+                    // training forward: geo goes out as rows of 80 (column 0 = the slot of the density pre-activation, not
+                    // used by the consumer), one 32-byte store per block instead of 79 scalar stores per sample
+                    if (SAVE && a.geo != nullptr && live) st_global_v8(a.geo + (size_t)row * 80 + 8 * b, hs);
                     if (!DENSITY_ONLY) {
                         tmem_st8(tl + 0u + 8 * b, hi);
                         tmem_st8(tl + 96u + 8 * b, lo);
@@ -789,11 +799,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                         p1 = __fmaf_rn(h, W1[k], p1);
                         p2 = __fmaf_rn(h, W2[k], p2);
                     }
-                    if (SAVE && live) {
-                        float *d = a.sv_h4 + (size_t)row * 160 + 8 * b;
-                        *reinterpret_cast<float4 *>(d) = make_float4(v[0], v[1], v[2], v[3]);
-                        *reinterpret_cast<float4 *>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                    }
+                    if (SAVE && live) st_global_v8(a.sv_h4 + (size_t)row * 160 + 8 * b, v);
                 }
                 tmem_st4(tl + 480u + 4u * q, __float_as_uint(p0), __float_as_uint(p1), __float_as_uint(p2), 0u);
                 tc_wait_st();
@@ -1052,7 +1058,10 @@ int cnc_field_fwd_train(const float *pos, const float *dirs, const float *aabb6_
                         uint32_t N, cnc_stream_t stream) {
     if (!dirs || !geo || !x0 || !h1 || !h3 || !h4) { set_error("field_fwd_train: null pointer"); return CNC_EINVAL; }
     if ((reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(h1) | reinterpret_cast<uintptr_t>(h3) |
-         reinterpret_cast<uintptr_t>(h4)) & 15u) { set_error("field_fwd_train: activation buffers must be 16-byte aligned"); return CNC_EINVAL; }
+         reinterpret_cast<uintptr_t>(h4) | reinterpret_cast<uintptr_t>(geo)) & 31u) {
+        set_error("field_fwd_train: activation buffers must be 32-byte aligned (rows leave as 256-bit stores); geo is [N,80]");
+        return CNC_EINVAL;
+    }
     return field_fwd_impl(pos, dirs, aabb6_host, bits_xyz, bits_xy, bits_xz, bits_yz, offsets3, resolutions3, offsets2,
                           resolutions2, blob, sigma, rgb, geo, x0, h1, h3, h4, N, stream);
 }

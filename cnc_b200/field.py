@@ -94,7 +94,7 @@ class _FusedFieldTrain(Function):
         bits = [e.sign_bits() for e in encs]
         sigma = torch.empty(n, device=dev)
         rgb = torch.empty(n, 3, device=dev)
-        geo = torch.empty(n, 79, device=dev)
+        geo = torch.empty(n, 80, device=dev)      # columns 1..79 (column 0 is scratch: rows leave the kernel as 256-bit stores)
         x0 = torch.empty(n, 256, device=dev)
         h1, h3, h4 = (torch.empty(n, 160, device=dev) for _ in range(3))
         check(lib().cnc_field_fwd_train(ptr(pos), ptr(dirs), ctypes.addressof(field._aabb_c()), *[ptr(b) for b in bits],
@@ -152,7 +152,7 @@ class _FusedFieldTrain(Function):
         gW5, gb5 = g5[:160, :3].t(), g5[160, :3]
         g4 = wgrad(h3, dz4, with_ones=True)                     # [161, 160]: rows = input features, last row = bias grad
         gW4, gb4 = g4[:160].t(), g4[160]
-        head_in = torch.cat([sh16((dirs + 1.0) / 2.0), geo, geo.new_zeros(n, 1)], dim=-1)   # ngp.py:540-542 (+ pad to 96)
+        head_in = torch.cat([sh16((dirs + 1.0) / 2.0), geo[:, 1:], geo.new_zeros(n, 1)], dim=-1)   # ngp.py:540-542 (+ pad to 96)
         g3 = wgrad(head_in, dz3, with_ones=True)
         gW3, gb3 = g3[:95].t(), g3[96]
         g2 = wgrad(h1, dz2, with_ones=True)
