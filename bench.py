@@ -592,6 +592,22 @@ def train_bench(arm, rank, world, steps, field):
                               "rays": H * W, "samples": int(n_tot), "ms_per_image": ms_img,
                               "rays_per_s": H * W / (ms_img * 1e-3), "samples_per_s": n_tot / (ms_img * 1e-3),
                               "mean_opacity": float(opa.mean())}
+        # the evaluation size of the training scripts: one 800 x 800 view (640 000 rays), same camera
+        H8 = W8 = 800
+        v8, u8 = torch.meshgrid(torch.linspace(-0.3, 0.3, H8, device=dev), torch.linspace(-0.3, 0.3, W8, device=dev), indexing="ij")
+        d8 = torch.stack([u8, v8, torch.ones_like(u8)], -1)
+        d8 = d8 / d8.norm(dim=-1, keepdim=True)
+        img8 = arm.Rays(torch.tensor([0.0, 0.0, -4.0], device=dev).expand(H8, W8, 3).contiguous(), d8.contiguous())
+        if ours:
+            arm.render_test(1024, field, est, img8, **kw)   # warm-up (the reference arm is timed cold: one view is 5 s)
+        torch.cuda.synchronize()
+        e0.record()
+        _, _, _, n8 = arm.render_test(1024, field, est, img8, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        out["test_render"]["view_800x800"] = {"rays": H8 * W8, "samples": int(n8), "ms_per_image": e0.elapsed_time(e1),
+                                              "samples_per_s": n8 / (e0.elapsed_time(e1) * 1e-3)}
+        del img8, d8, u8, v8
         if ours:
             arm.render_test(1024, field, est, img, device_loop=False, **kw)
             torch.cuda.synchronize()

@@ -43,7 +43,7 @@ SIGNATURES = {
     "cnc_keys_to_points": [_vp, _u64, _u32, _vp, _vp, _vp],
     "cnc_ste_planes_pack": [_vp, _vp, _vp, _u64, _vp],
     "cnc_surrogate_fill": [_vp, _vp, _vp, _u64, _u64, _u64, _vp],
-    "cnc_adam_planes": [_vp, _vp, _vp, _vp, _vp, _vp, _u64, _f32, _f32, _f32, _f32, _f32, _i64, _f32, _vp],
+    "cnc_adam_planes": [_vp, _vp, _vp, _vp, _vp, _vp, _u64, _f32, _f32, _f32, _f32, _f32, _i64, _f32, _i32, _vp],
     "cnc_vote_planes_fwd": [_vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _vp],
     "cnc_vote_planes_bwd": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _vp],
     "cnc_vote3_fwd": [_vp, _u32, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp],

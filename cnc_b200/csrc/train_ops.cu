@@ -92,7 +92,7 @@ __global__ void surrogate_fill_kernel(float *__restrict__ p, const uint32_t *__r
 // sum-instead-of-mean reductions) and is divided out first.
 __global__ void adam_planes_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m1, float *__restrict__ v2,
                                    uint32_t *__restrict__ sign, uint32_t *__restrict__ mask, uint64_t n_words, float lr, float b1,
-                                   float b2, float eps, float wd, float bc1, float bc2_sqrt, float inv_scale) {
+                                   float b2, float eps, float wd, float bc1, float bc2_sqrt, float inv_scale, int ste_window) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t n_chunks = (n_words + 31) / 32;
@@ -113,6 +113,7 @@ __global__ void adam_planes_kernel(float *__restrict__ p, const float *__restric
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     float gr = __fmul_rn(ga[j], inv_scale);
+                    if (ste_window && !(pa[j] >= -1.f && pa[j] <= 1.f)) gr = 0.f;   // STE_binary backward (ngp.py:33-39), folded in
                     gr = __fmaf_rn(wd, pa[j], gr);
                     ma[j] = __fmaf_rn(1.f - b1, __fsub_rn(gr, ma[j]), ma[j]);
                     va[j] = __fmaf_rn(b2, va[j], __fmul_rn(__fmul_rn(1.f - b2, gr), gr));
@@ -171,7 +172,7 @@ int cnc_surrogate_fill(float *params, const uint8_t *sign_bits, const uint8_t *m
 
 int cnc_adam_planes(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, uint8_t *sign_bits, uint8_t *mask_bits,
                     uint64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
-                    cnc_stream_t stream) {
+                    int32_t ste_window, cnc_stream_t stream) {
     if (n == 0) return CNC_OK;
     if (!params || !grad || !exp_avg || !exp_avg_sq) { set_error("adam_planes: null pointer"); return CNC_EINVAL; }
     if (n % 32 || step < 1 || grad_scale == 0.f) { set_error("adam_planes: n must be a multiple of 32, step >= 1, grad_scale != 0"); return CNC_EINVAL; }
@@ -182,7 +183,7 @@ int cnc_adam_planes(float *params, const float *grad, float *exp_avg, float *exp
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     adam_planes_kernel<<<stream_blocks(n / 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         params, grad, exp_avg, exp_avg_sq, reinterpret_cast<uint32_t *>(sign_bits), reinterpret_cast<uint32_t *>(mask_bits), n / 32, lr,
-        beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), 1.f / grad_scale);
+        beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), 1.f / grad_scale, ste_window);
     return check_launch("adam_planes");
 }
 

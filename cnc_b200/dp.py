@@ -108,11 +108,13 @@ class ShardedTableAdam:
     The sign plane is handed to the encoder's sign cache, so the forward of the next step starts without a repack pass.
     world == 1 is the same code without the collectives.  `sync_params()` all-gathers the true fp32 rows (checkpoints)."""
 
-    def __init__(self, encoders, lr: float = 6e-3, betas=(0.9, 0.999), eps: float = 1e-15, weight_decay: float = 0.0, group=None):
+    def __init__(self, encoders, lr: float = 6e-3, betas=(0.9, 0.999), eps: float = 1e-15, weight_decay: float = 0.0, group=None,
+                 ste_window: bool = False):
         from .train_ops import planes_pack
 
         self.encoders = list(encoders)
         self.lr, self.betas, self.eps, self.weight_decay, self.group = lr, betas, eps, weight_decay, group
+        self.ste_window = ste_window    # the table gradients arrive without the STE window mask: apply it in the Adam pass
         on = dist.is_initialized()
         self.world = dist.get_world_size(group) if on else 1
         self.rank = dist.get_rank(group) if on else 0
@@ -204,7 +206,8 @@ class ShardedTableAdam:
             w.wait()
         self.step_id += 1
         W, off = self.world, 0
-        kw = dict(step=self.step_id, lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay)
+        kw = dict(step=self.step_id, lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay,
+                  ste_window=self.ste_window)
         sends = []
         for t, (g, gs) in zip(self.tables, parts):
             flat = t["p"].detach().view(-1)

@@ -145,7 +145,8 @@ class _FusedFieldTrain(Function):
             check(lib().cnc_grid_encode_bwd_rows(ptr(dfeat), dfeat.shape[1], col, ptr(xs.contiguous()), ptr(enc.offsets_list),
                                                  ptr(enc.resolutions_list), ptr(ge), n, xs.shape[1], F, L, 128, None, None, stream()))
             col += L * F
-            g = G.ste_binary_backward(prm.contiguous(), ge)
+            # STE window |p| <= 1 (ngp.py:33-39) -- unless the table optimizer applies it in its own pass (TrainStep)
+            g = ge if getattr(field, "_defer_ste", False) else G.ste_binary_backward(prm.contiguous(), ge)
             grads.append(None if (sink is not None and sink(k, g)) else g)   # consumed: the exchange is already under way
         # weight gradients: cnc_wgrad, contraction over the samples on the tensor cores
         g5 = wgrad(h4, dz5, with_ones=True)                     # [161, 16]

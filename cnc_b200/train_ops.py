@@ -57,17 +57,21 @@ def surrogate_fill(p: torch.Tensor, sign: torch.Tensor, mask: torch.Tensor, keep
 
 
 def adam_planes(p, g, exp_avg, exp_avg_sq, step: int, lr: float, betas=(0.9, 0.999), eps: float = 1e-15, weight_decay: float = 0.0,
-                grad_scale: float = 1.0, sign: torch.Tensor = None, mask: torch.Tensor = None) -> None:
+                grad_scale: float = 1.0, sign: torch.Tensor = None, mask: torch.Tensor = None, ste_window: bool = False) -> None:
     """one torch.optim.Adam step over the flat fp32 tensors (numel % 32 == 0), in place; `sign` / `mask` (uint8
-    [numel/8], optional) receive the planes of the updated values in the same pass"""
+    [numel/8], optional) receive the planes of the updated values in the same pass; `ste_window`: drop the gradient of latents
+    outside [-1, 1] first (STE_binary backward folded in)"""
     n = p.numel()
     assert n % 32 == 0 and all(t.is_contiguous() and t.numel() == n for t in (p, g, exp_avg, exp_avg_sq))
     if p.is_cuda:
         check(lib().cnc_adam_planes(ptr(p), ptr(g), ptr(exp_avg), ptr(exp_avg_sq), ptr(sign), ptr(mask), n, lr, betas[0], betas[1],
-                                    eps, weight_decay, step, grad_scale, stream()))
+                                    eps, weight_decay, step, grad_scale, int(ste_window), stream()))
         return
     with torch.no_grad():
-        gr = g / grad_scale + weight_decay * p
+        gr = g / grad_scale
+        if ste_window:
+            gr = gr * ((p >= -1) & (p <= 1))
+        gr = gr + weight_decay * p
         exp_avg.lerp_(gr, 1 - betas[0])
         exp_avg_sq.mul_(betas[1]).addcmul_(gr, gr, value=1 - betas[1])
         bc1, bc2 = 1 - betas[0] ** step, 1 - betas[1] ** step

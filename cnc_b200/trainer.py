@@ -38,7 +38,9 @@ class TrainStep:
         table_ids = {id(e.params) for e in encs} if self.sharded else set()
         field_rest = [p for p in radiance_field.parameters() if id(p) not in table_ids and p.requires_grad]
         ctx = [p for p in context_model.parameters() if p.requires_grad] if context_model is not None else []
-        self.table_opt = ShardedTableAdam(encs, lr=lr, eps=1e-15, weight_decay=weight_decay) if self.sharded else None
+        # the STE window of the render path's table gradient is applied inside the table optimizer's pass (idempotent for the
+        # contributions of the rate term, which arrive already masked): four full-table elementwise kernels less per step
+        self.table_opt = ShardedTableAdam(encs, lr=lr, eps=1e-15, weight_decay=weight_decay, ste_window=True) if self.sharded else None
         groups = [{"params": field_rest, "weight_decay": weight_decay}]
         if ctx:
             groups.append({"params": ctx, "weight_decay": 0.0})
@@ -121,9 +123,11 @@ class TrainStep:
         # without a rate term the render path is the only source of table gradients: their exchange starts inside backward
         early = self.table_opt is not None and self.world > 1 and not (self.cm is not None and self.lmbda > 0)
         self.field._table_grad_sink = self.table_opt.contribute if early else None
+        self.field._defer_ste = self.table_opt is not None
         if loss.requires_grad:           # (a data-parallel rank whose batch produced no sample still joins the collectives)
             loss.backward()
         self.field._table_grad_sink = None
+        self.field._defer_ste = False
         for g in self.optimizer.param_groups:
             g["lr"] = self.lr
         exchanged = None

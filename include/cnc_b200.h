@@ -185,14 +185,16 @@ int cnc_keys_to_points(const uint64_t *keys, uint64_t n, uint32_t resolution, in
  *                         outside [keep_lo, keep_hi); n, keep_lo, keep_hi multiples of 32.
  *   cnc_adam_planes     : torch.optim.Adam (L2 weight decay, fp32 state, bias correction with `step` >= 1) over
  *                         params/grad/exp_avg/exp_avg_sq [n], emitting the two planes of the updated values in the same
- *                         pass (sign_bits / mask_bits nullable); grad is divided by grad_scale first (GradScaler, :211,362).
+ *                         pass (sign_bits / mask_bits nullable); grad is divided by grad_scale first (GradScaler, :211,362);
+ *                         ste_window != 0: the gradient of a latent outside [-1, 1] is dropped first (the STE_binary
+ *                         backward, ngp.py:33-39, for callers that hand over the unmasked table gradient).
  * ---------------------------------------------------------------------------------------- */
 int cnc_ste_planes_pack(const float *params, uint8_t *sign_bits, uint8_t *mask_bits, uint64_t n, cnc_stream_t stream);
 int cnc_surrogate_fill(float *params, const uint8_t *sign_bits, const uint8_t *mask_bits, uint64_t n, uint64_t keep_lo,
                        uint64_t keep_hi, cnc_stream_t stream);
 int cnc_adam_planes(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, uint8_t *sign_bits, uint8_t *mask_bits,
                     uint64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
-                    cnc_stream_t stream);
+                    int32_t ste_window, cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dimension-wise context: 3D -> 2D vote planes.

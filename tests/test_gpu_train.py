@@ -48,6 +48,16 @@ def test_table_passes_vs_torch(cuda, n):
         torch.testing.assert_close(b, a.detach(), rtol=2e-5, atol=1e-7)
     s2, m2 = planes_pack(b)
     assert torch.equal(sign, s2) and torch.equal(mask, m2)       # the planes the kernel emitted are those of what it wrote
+    # STE window folded into the pass: the gradient of latents outside [-1, 1] is dropped (weight decay still acts on them)
+    with torch.no_grad():
+        a[: n // 2] *= 1.5
+        b[: n // 2] *= 1.5
+    gr = torch.randn(n, device=cuda)
+    a.grad = gr * ((a.detach() >= -1) & (a.detach() <= 1))
+    opt.step()
+    adam_planes(b, gr, m1, v2, step=4, lr=6e-3, eps=1e-15, weight_decay=2e-6, ste_window=True)
+    torch.testing.assert_close(b, a.detach(), rtol=2e-5, atol=1e-7)
+    assert float(((a.detach().abs() > 1)).float().mean()) > 0.05
 
 
 def _scene(dev, n_rays=600, seed=0):
