@@ -497,7 +497,7 @@ def train_bench(arm, rank, world, steps, field):
     if ours:
         from cnc_b200.trainer import TrainStep
 
-        ts = TrainStep(field, est, lr=1e-4)
+        ts = TrainStep(field, est, lr=1e-4, exchange=os.environ.get("CNC_EXCHANGE", "auto"))
         call = lambda t: t(rays, pixels, render_bkgd=bk, refresh_occupancy=False)
     else:
         ts = RefTrainStep(arm, field, est, lr=1e-4)
@@ -533,11 +533,13 @@ def train_bench(arm, rank, world, steps, field):
            "comm_bytes_per_step": ts.comm_bytes_per_step() if (ours and world > 1) else 0, "rays_per_rank": n_rays}
     if ours and world > 1:
         out["comm"] = ts.comm_description()
+        if ts.table_opt is not None and ts.table_opt.peer is not None:
+            out["nvlink_bytes_per_step"] = ts.table_opt.link_bytes_per_step()
     if world == 1:
         # the same step with the rate term of the CNC loss (lambda > 0: context model on 150 000 sampled entries + planes)
         cm = arm.context_model()
         if ours:
-            ts2 = TrainStep(field, est, context_model=cm, lmbda=1e-3, lr=1e-4)
+            ts2 = TrainStep(field, est, context_model=cm, lmbda=1e-3, lr=1e-4, exchange=os.environ.get("CNC_EXCHANGE", "auto"))
         else:
             ts2 = RefTrainStep(arm, field, est, cm=cm, lmbda=1e-3, lr=1e-4)
         for _ in range(2):

@@ -76,6 +76,14 @@ SIGNATURES = {
     "cnc_vertex_valid_bits": [_vp, _i32, _vp, _i32, _vp, _i64, _vp, _vp],
     "cnc_ctx_mlp_fwd": [_vp, _vp, _vp, _i64, _vp],
     "cnc_ctx_mlp_bwd": [_vp, _vp, _vp, _vp, _vp, _u32, _i64, _vp],
+    "cnc_peer_alloc": [_u64, _vp],
+    "cnc_peer_free": [_vp],
+    "cnc_peer_export": [_vp, _vp],
+    "cnc_peer_import": [_vp, _vp],
+    "cnc_peer_unmap": [_vp],
+    "cnc_peer_barrier": [_vp, _i32, _i32, _i32, _u32, _u32, _vp],
+    "cnc_peer_reduce": [_vp, _i32, _i64, _i64, _f32, _vp, _i32, _vp],
+    "cnc_peer_push": [_vp, _i32, _i32, _vp, _vp, _i32, _vp],
 }
 
 
@@ -107,6 +115,9 @@ def lib():
         L.cnc_ctx_mlp_max_partials.argtypes = []
         L.cnc_lin8_rows_per_block.restype = C.c_int
         L.cnc_lin8_rows_per_block.argtypes = []
+        for name in ("cnc_peer_handle_bytes", "cnc_peer_pad_bytes"):
+            getattr(L, name).restype = C.c_int
+            getattr(L, name).argtypes = []
         _lib = L
     return _lib
 

@@ -94,6 +94,16 @@ class GradAllReducer:
                     off += n
 
 
+class _EventWork:
+    """a CUDA event with the `.wait()` of a torch.distributed work handle: the current stream waits for it"""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
 class ShardedTableAdam:
     """Adam over the latent hash tables of `encoders` (GridEncoder modules, F = 8 product tables), rows split over the
     ranks of `group`.  One `step()` per training iteration, after `backward()`:
@@ -103,13 +113,19 @@ class ShardedTableAdam:
         all-gather of the sign and window planes            [2 x 5 MB]
         stand-in latents for the rows owned elsewhere       (train_ops.surrogate_fill, one write pass)
 
+    `exchange` picks who moves the bytes.  "nccl": the two collectives above.  "peer" (what "auto" takes when all ranks sit
+    on one NVLink box): the gradients are written into buffers every rank maps (peer.PeerMemory); after a device-side
+    barrier each rank LOADS its rows straight from all N buffers and averages them (`cnc_peer_reduce`: every byte crosses
+    NVLink once, no ring, no NCCL kernel holding SMs), and after Adam STORES its plane words into every peer's planes
+    (`cnc_peer_push`) -- the same result up to the order of the N-term sum, which here is the rank order.
+
     A table of n elements is cut at multiples of 32*world elements (whole words of the bit planes per rank); the < 32*world
     elements behind the last cut are replicated: their gradient is all-reduced and every rank updates them identically.
     The sign plane is handed to the encoder's sign cache, so the forward of the next step starts without a repack pass.
     world == 1 is the same code without the collectives.  `sync_params()` all-gathers the true fp32 rows (checkpoints)."""
 
     def __init__(self, encoders, lr: float = 6e-3, betas=(0.9, 0.999), eps: float = 1e-15, weight_decay: float = 0.0, group=None,
-                 ste_window: bool = False):
+                 ste_window: bool = False, exchange: str = "auto", peer_control_group=None):
         from .train_ops import planes_pack
 
         self.encoders = list(encoders)
@@ -134,12 +150,88 @@ class ShardedTableAdam:
                  "tm": torch.zeros(n - n_main, device=p.device), "tv": torch.zeros(n - n_main, device=p.device)}
             t["sign"], t["mask"] = planes_pack(p.detach().contiguous().view(-1))
             self.tables.append(t)
+        if exchange not in ("auto", "nccl", "peer"):
+            raise ValueError("exchange must be 'auto', 'nccl' or 'peer'")
+        self.peer = None
+        cuda = all(t["p"].is_cuda for t in self.tables)
+        if self.world > 1 and cuda and exchange != "nccl":
+            from . import peer as P
+
+            if exchange == "peer" or P.peer_capable(group):
+                self._setup_peer(P, peer_control_group)
+        elif exchange == "peer" and self.world > 1:
+            raise RuntimeError("exchange='peer' needs CUDA tables")
+
+    # ---- peer-memory exchange (csrc/peer.cu) -------------------------------------------------------------------------
+    def _setup_peer(self, P, control_group) -> None:
+        dev = self.tables[0]["p"].device
+        sig = P.PeerSignals(group=self.group, device=dev, control_group=control_group)
+        # gradient arena: two copies of every table (a step writes one while a slow peer may still read the other)
+        g_off, off = [], 0
+        for t in self.tables:
+            g_off.append(off)
+            off += (4 * t["n"] + 255) // 256 * 256
+        g_bytes = off
+        gmem = P.PeerMemory(2 * g_bytes, group=self.group, device=dev, control_group=control_group)
+        # plane arena: sign and window plane of every table
+        p_off, off = [], 0
+        for t in self.tables:
+            nb = (t["n"] // 8 + 255) // 256 * 256
+            p_off.append((off, off + nb))
+            off += 2 * nb
+        pmem = P.PeerMemory(off, group=self.group, device=dev, control_group=control_group)
+        for k, t in enumerate(self.tables):
+            for name, o in zip(("sign", "mask"), p_off[k]):
+                plane = pmem.tensor(o, t["n"] // 8, torch.uint8)
+                plane.copy_(t[name])
+                t[name] = plane
+            t["gbuf"] = [gmem.tensor(par * g_bytes + g_off[k], t["n"]).view_as(t["p"]) for par in (0, 1)]
+            t["gsrc"] = [gmem.pointer_array(par * g_bytes + g_off[k]) for par in (0, 1)]
+            t["gs"] = torch.empty(t["S"], device=dev)
+            t["gt"] = torch.empty(t["n"] - t["n_main"], device=dev)
+            t["push"] = [(o // 4 + t["lo"] // 32, t["S"] // 32) for o in p_off[k]]
+        self.peer = {"P": P, "sig": sig, "gmem": gmem, "pmem": pmem, "stream": torch.cuda.Stream(dev), "parity": 0}
+        torch.cuda.synchronize(dev)
+        sig.barrier(15)                    # nobody starts reading before everybody's arenas hold their initial contents
+        torch.cuda.synchronize(dev)
+
+    def grad_buffer(self, k: int):
+        """where this step's gradient of table k should be accumulated (peer exchange: the buffer the other ranks read;
+        otherwise None = allocate as usual).  The caller zeroes it."""
+        return None if self.peer is None else self.tables[k]["gbuf"][self.peer["parity"]]
+
+    def _peer_reduce(self, k: int, grad: torch.Tensor):
+        """table k's gradient of this step is complete in `grad`: meet the other ranks, average the owned rows"""
+        pr, t = self.peer, self.tables[k]
+        P, par = pr["P"], pr["parity"]
+        buf = t["gbuf"][par]
+        if grad is None:
+            buf.zero_()
+        elif grad.data_ptr() != buf.data_ptr():
+            buf.copy_(grad.view_as(buf))
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(pr["stream"]):
+            pr["stream"].wait_event(ready)
+            pr["sig"].barrier(k)
+            P.reduce_rows(t["gsrc"][par], self.world, t["lo"], t["S"], 1.0 / self.world, t["gs"])
+            if t["n"] > t["n_main"]:
+                P.reduce_rows(t["gsrc"][par], self.world, t["n_main"], t["n"] - t["n_main"], 1.0 / self.world, t["gt"])
+            done = torch.cuda.Event()
+            done.record()
+        return buf.view(-1), t["gs"], t["gt"], _EventWork(done)
 
     def comm_bytes_per_step(self) -> int:
         """bytes this rank hands to the collectives per step (reduce-scatter input + its share of the all-gathers)"""
         if self.world == 1:
             return 0
         return sum(4 * t["n_main"] + 4 * (t["n"] - t["n_main"]) + 2 * t["S"] // 8 for t in self.tables)
+
+    def link_bytes_per_step(self) -> int:
+        """bytes that cross this rank's NVLink port per step in the peer exchange: rows loaded from the N - 1 peers plus the
+        plane words stored into them"""
+        W = self.world
+        return sum((W - 1) * 4 * (t["S"] + t["n"] - t["n_main"]) + (W - 1) * 2 * t["S"] // 8 for t in self.tables) if W > 1 else 0
 
     def _batched(self):
         """context that turns the collectives issued inside it into ONE NCCL group launch (gloo: issued one by one)"""
@@ -157,11 +249,14 @@ class ShardedTableAdam:
         if self.world == 1:
             return False
         t = self.tables[k]
+        self._early = getattr(self, "_early", {})
+        if self.peer is not None:
+            self._early[k] = self._peer_reduce(k, grad)
+            return True
         g = grad.contiguous().view(-1)
         gs = torch.empty(t["S"], device=g.device)
         w = dist.reduce_scatter_tensor(gs, g[:t["n_main"]], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
-        self._early = getattr(self, "_early", {})
-        self._early[k] = (g, gs, w)
+        self._early[k] = (g, gs, None, w)
         return True
 
     @torch.no_grad()
@@ -169,18 +264,25 @@ class ShardedTableAdam:
         """launch the gradient exchange (asynchronous): reduce-scatter of every table's rows (those not handed over early
         by `contribute`), one small all-reduce of the replicated tails.  Returns what `apply` needs."""
         W, works, parts = self.world, [], []
-        tails, late = [], []
         early, self._early = getattr(self, "_early", {}), {}
+        if self.peer is not None:
+            for k, t in enumerate(self.tables):
+                g, gs, gt, w = early[k] if k in early else self._peer_reduce(k, t["p"].grad)
+                works.append(w)
+                parts.append((g, gs, gt))
+            self.peer["parity"] ^= 1
+            return works, parts
+        tails, late = [], []
         for k, t in enumerate(self.tables):
             if k in early:
-                g, gs, w = early[k]
+                g, gs, _, w = early[k]
                 works.append(w)
             else:
                 p = t["p"]
                 g = (p.grad if p.grad is not None else torch.zeros_like(p)).contiguous().view(-1)
                 gs = torch.empty(t["S"], device=g.device) if W > 1 else g[:t["n_main"]]
                 late.append((t, g, gs))
-            parts.append((g, gs))
+            parts.append([g, gs, None])
             tails.append(g[t["n_main"]:])
         tail = torch.cat(tails) if sum(x.numel() for x in tails) else None
         if W > 1:
@@ -194,33 +296,40 @@ class ShardedTableAdam:
                     works.append(cm)
             if tail is not None:
                 works.append(dist.all_reduce(tail, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
-        return works, parts, tail
+        off = 0
+        for part, t in zip(parts, self.tables):     # every table's replicated tail as a view of the reduced buffer
+            nt = t["n"] - t["n_main"]
+            part[2] = tail[off:off + nt] if nt else None
+            off += nt
+        return works, parts
 
     @torch.no_grad()
     def apply(self, exchanged) -> None:
         """Adam on the owned rows (+ the replicated tails), bit planes to everybody, stand-ins for the rows owned elsewhere"""
         from .train_ops import adam_planes, surrogate_fill
 
-        works, parts, tail = exchanged
+        works, parts = exchanged[0], exchanged[1]
         for w in works:
             w.wait()
         self.step_id += 1
-        W, off = self.world, 0
+        W = self.world
         kw = dict(step=self.step_id, lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay,
                   ste_window=self.ste_window)
         sends = []
-        for t, (g, gs) in zip(self.tables, parts):
+        for t, (g, gs, gt) in zip(self.tables, parts):
             flat = t["p"].detach().view(-1)
             lo, hi, nm = t["lo"], t["hi"], t["n_main"]
             adam_planes(flat[lo:hi], gs, t["m"], t["v"], sign=t["sign"][lo // 8:hi // 8], mask=t["mask"][lo // 8:hi // 8], **kw)
             if t["n"] > nm:
-                gt = tail[off:off + t["n"] - nm]
-                off += t["n"] - nm
                 adam_planes(flat[nm:], gt.contiguous(), t["tm"], t["tv"], sign=t["sign"][nm // 8:], mask=t["mask"][nm // 8:], **kw)
-            if W > 1:
+            if W > 1 and self.peer is None:
                 for plane in (t["sign"], t["mask"]):
                     sends.append((plane[:nm // 8], plane[lo // 8:hi // 8].clone()))
-        if W > 1:
+        if self.peer is not None:
+            pr = self.peer
+            pr["P"].push_words(pr["pmem"], [seg for t in self.tables for seg in t["push"]])
+            pr["sig"].barrier(8)               # everybody's words have arrived here, and mine everywhere
+        elif W > 1:
             works = []
             with self._batched() as cm:
                 for out, mine in sends:

@@ -135,13 +135,15 @@ class _FusedFieldTrain(Function):
         mb = field.mlp_base
         xn = field._normalise(pos)
         sink = getattr(field, "_table_grad_sink", None)
+        buffer_of = getattr(field, "_table_grad_buffer", None)
         grads, col = [], 0
         # (coordinate pairs as strided slices: indexing with a python list builds an index tensor on the host and copies it
         #  over -- a stream synchronisation per call, four per backward)
         for k, (enc, prm, xs) in enumerate(((mb.encoding_xyz, p_xyz, xn), (mb.encoding_xy, p_xy, xn[:, 0:2]),
                                             (mb.encoding_xz, p_xz, xn[:, 0::2]), (mb.encoding_yz, p_yz, xn[:, 1:3]))):
             L, F = enc.n_levels, enc.n_features
-            ge = torch.zeros_like(prm)
+            ge = buffer_of(k) if buffer_of is not None else None    # (data parallel: a buffer the other ranks can read)
+            ge = torch.zeros_like(prm) if ge is None else ge.zero_()
             check(lib().cnc_grid_encode_bwd_rows(ptr(dfeat), dfeat.shape[1], col, ptr(xs.contiguous()), ptr(enc.offsets_list),
                                                  ptr(enc.resolutions_list), ptr(ge), n, xs.shape[1], F, L, 128, None, None, stream()))
             col += L * F

@@ -28,7 +28,7 @@ from .render import Rays, render_image_with_occgrid
 class TrainStep:
     def __init__(self, radiance_field, estimator, context_model=None, lmbda: float = 0.0, lr: float = 6e-3,
                  render_step_size: float = 5e-3, target_sample_batch_size: int = 1 << 18, bucket_bytes: int = 32 << 20,
-                 weight_decay: float = 2e-6, occ_refresh_every: int = 16, shard_tables: bool = True):
+                 weight_decay: float = 2e-6, occ_refresh_every: int = 16, shard_tables: bool = True, exchange: str = "auto"):
         self.field, self.estimator, self.cm, self.lmbda = radiance_field, estimator, context_model, lmbda
         self.render_step_size, self.target, self.occ_every = render_step_size, target_sample_batch_size, occ_refresh_every
         self.lr = lr
@@ -40,7 +40,8 @@ class TrainStep:
         ctx = [p for p in context_model.parameters() if p.requires_grad] if context_model is not None else []
         # the STE window of the render path's table gradient is applied inside the table optimizer's pass (idempotent for the
         # contributions of the rate term, which arrive already masked): four full-table elementwise kernels less per step
-        self.table_opt = ShardedTableAdam(encs, lr=lr, eps=1e-15, weight_decay=weight_decay, ste_window=True) if self.sharded else None
+        self.table_opt = ShardedTableAdam(encs, lr=lr, eps=1e-15, weight_decay=weight_decay, ste_window=True,
+                                          exchange=exchange) if self.sharded else None
         groups = [{"params": field_rest, "weight_decay": weight_decay}]
         if ctx:
             groups.append({"params": ctx, "weight_decay": 0.0})
@@ -59,6 +60,11 @@ class TrainStep:
             return "single process: no exchange"
         if self.table_opt is None:
             return "bucketed all-reduce of every gradient"
+        if self.table_opt.peer is not None:
+            return ("latent tables over NVLink peer memory: device-side barrier, every rank loads and averages its 1/N of the rows "
+                    "from all N gradient buffers (cnc_peer_reduce), Adam on them, stores its words of the sign and STE-window bit "
+                    "planes into every peer (cnc_peer_push); MLP / context-model gradients: one bucketed NCCL all-reduce; sample "
+                    "count: 8-byte NCCL all-reduce")
         return ("latent tables: reduce-scatter(avg) of the gradient by rows, Adam on the owned 1/N, all-gather of the sign and "
                 "STE-window bit planes; MLP / context-model gradients: one bucketed all-reduce; sample count: 8-byte all-reduce")
 
@@ -124,9 +130,12 @@ class TrainStep:
         early = self.table_opt is not None and self.world > 1 and not (self.cm is not None and self.lmbda > 0)
         self.field._table_grad_sink = self.table_opt.contribute if early else None
         self.field._defer_ste = self.table_opt is not None
+        # (peer exchange: K2 accumulates straight into the buffer the other ranks will read)
+        self.field._table_grad_buffer = self.table_opt.grad_buffer if early else None
         if loss.requires_grad:           # (a data-parallel rank whose batch produced no sample still joins the collectives)
             loss.backward()
         self.field._table_grad_sink = None
+        self.field._table_grad_buffer = None
         self.field._defer_ste = False
         for g in self.optimizer.param_groups:
             g["lr"] = self.lr

@@ -197,6 +197,36 @@ int cnc_adam_planes(float *params, const float *grad, float *exp_avg, float *exp
                     int32_t ste_window, cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Gradient exchange of the data-parallel step over NVLink peer memory (csrc/peer.cu; SURVEY 8(e): the reference has no
+ * distributed code).  Buffers live in plain device allocations that every rank of the box maps (CUDA IPC); the 64-byte
+ * handles travel through the caller's control plane (torch.distributed).
+ *   cnc_peer_alloc / _free      : zero-filled device allocation that can be exported
+ *   cnc_peer_export / _import   : cudaIpcGetMemHandle / cudaIpcOpenMemHandle (`handle`: cnc_peer_handle_bytes() bytes);
+ *                                 _unmap closes an imported mapping
+ *   cnc_peer_barrier            : all ranks meet: rank r stores `epoch` into word [slot][r] of every rank's signal pad
+ *                                 (pads[k] = rank k's pad as mapped here, cnc_peer_pad_bytes() bytes, zero at start) and waits
+ *                                 until its own pad holds >= epoch from everybody; epochs of a slot must increase.  A wait
+ *                                 longer than timeout_ms traps the kernel (the next CUDA call reports it).
+ *   cnc_peer_reduce             : out[i] = scale * sum_{k < world} srcs[k][lo + i], i < count, summed in rank order (lo,
+ *                                 count multiples of 4); `blocks` caps the grid (0 = one CTA per SM)
+ *   cnc_peer_push               : words [off, off + words) of rank `rank`'s arena are stored at the same offsets of every
+ *                                 other rank's arena (arenas[k] as mapped here; uint32 words; at most 8 segments)
+ * ---------------------------------------------------------------------------------------- */
+int cnc_peer_alloc(uint64_t bytes, void **out);
+int cnc_peer_free(void *p);
+int cnc_peer_handle_bytes(void);
+int cnc_peer_pad_bytes(void);
+int cnc_peer_export(void *p, uint8_t *handle);
+int cnc_peer_import(const uint8_t *handle, void **out);
+int cnc_peer_unmap(void *p);
+int cnc_peer_barrier(void *const *pads, int32_t rank, int32_t world, int32_t slot, uint32_t epoch, uint32_t timeout_ms,
+                     cnc_stream_t stream);
+int cnc_peer_reduce(const void *const *srcs, int32_t world, int64_t lo, int64_t count, float scale, float *out, int32_t blocks,
+                    cnc_stream_t stream);
+int cnc_peer_push(void *const *arenas, int32_t rank, int32_t world, const int64_t *seg_off_words, const int64_t *seg_words,
+                  int32_t n_seg, cnc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Dimension-wise context: 3D -> 2D vote planes.
  * replaces: _gridencoder.cnt_np_embed / cnt_np_embed_backward   gridencoder.h:39-53,
  *           gridencoder.cu:873-915, :972-1020

@@ -24,7 +24,9 @@ o = torch.randn(n_rays, 3, generator=g); o = o / o.norm(dim=-1, keepdim=True) * 
 tgt = (torch.rand(n_rays, 3, generator=g) - 0.5) * 1.2
 d = tgt - o; d = d / d.norm(dim=-1, keepdim=True)
 rays = Rays(o.to(dev), d.to(dev)); pixels = torch.rand(n_rays, 3, generator=g).to(dev)
-ts = TrainStep(field, est, lr=1e-4)
+ts = TrainStep(field, est, lr=1e-4, exchange=os.environ.get("CNC_EXCHANGE", "auto"))
+if rank == 0:
+    print("exchange:", ts.comm_description())
 for _ in range(3):
     _, n_s = ts(rays, pixels, refresh_occupancy=False)
 torch.cuda.synchronize()
@@ -35,10 +37,16 @@ for _ in range(5):
 torch.cuda.synchronize()
 if rank == 0:
     print(f"samples {n_s}; wall {1e3 * (time.perf_counter() - t) / 5:.2f} ms/step; world {world}")
+if os.environ.get("PROFILE", "1") == "0":
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    sys.exit(0)
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3):
         ts(rays, pixels, refresh_occupancy=False)
     torch.cuda.synchronize()
+if rank == 0 and os.environ.get("TRACE"):
+    prof.export_chrome_trace(os.environ["TRACE"])
 if rank == 0:
     print(prof.key_averages().table(sort_by=os.environ.get("SORT", "self_cuda_time_total"), row_limit=45, max_name_column_width=70))
     print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=15, max_name_column_width=70))
