@@ -84,7 +84,13 @@ struct MarchArgs {
 
 // The walk of one ray: grid.cu:68-318 with the interval edges folded into (t_start, t_end) per sample.  `emit(j, t0, t1)`
 // receives sample j; returns the number of samples and leaves the stopping point of the march in t_end.
-template <class Emit>
+//
+// WARP = true: the whole warp walks ONE ray, every lane holding the same state.  The DDA (which cells, where the ray leaves
+// them) does not depend on the sampling state, so the warp first runs the DDA 32 cells ahead on a copy, lane j keeps cell j
+// and ALL 32 occupancy bytes are loaded at once (one memory latency per 32 cells instead of one per cell: the walk is a
+// latency chain, 390 cycles per cell when measured one load at a time); a ballot hands every lane the 32 bits, and the walk
+// proper replays the same cells with the same arithmetic in the same order -- sample placement stays bit for bit.
+template <bool WARP = false, class Emit>
 __device__ __forceinline__ int64_t march_ray(const MarchArgs &a, int64_t tid, float near, float far, int32_t steps_limit, Emit emit,
                                              float &t_end) {
     const float eps = 1e-6f;
@@ -136,10 +142,47 @@ __device__ __forceinline__ int64_t march_ray(const MarchArgs &a, int64_t tid, fl
             delta[k] = (d[k] == 0.0f) ? this_tmax : __fmul_rn(__fmul_rn(vox, inv[k]), sf);
             over[k] = fin + step[k];
         }
+        uint32_t occ_bits = 0;   // WARP: occupancy of the next cells of the DDA, bit 0 = the current one
+        int occ_left = 0;
+        const uint32_t lane = WARP ? (threadIdx.x & 31u) : 0u;
         while (steps_limit <= 0 || n_samples < steps_limit) {
             const float t_trav = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), this_tmax);
             const int64_t cell = (int64_t)cur[0] * a.ry * a.rz + (int64_t)cur[1] * a.rz + cur[2] + level * (int64_t)a.rx * a.ry * a.rz;
-            if (!a.binaries[cell]) {
+            bool occupied;
+            if (WARP) {
+                if (occ_left == 0) {
+                    // run the DDA ahead on a copy: lane j keeps the j-th cell from here
+                    float td[3] = {tdist[0], tdist[1], tdist[2]};
+                    int cu[3] = {cur[0], cur[1], cur[2]};
+                    int64_t mine = cell;
+                    int n_ahead = 0;
+                    for (int j = 0; j < 32; j++) {
+                        const int64_t cj = (int64_t)cu[0] * a.ry * a.rz + (int64_t)cu[1] * a.rz + cu[2] + level * (int64_t)a.rx * a.ry * a.rz;
+                        if (lane == (uint32_t)j) mine = cj;
+                        n_ahead = j + 1;
+                        const int axj = ((td[0] < td[1]) && (td[0] < td[2])) ? 0 : ((td[1] < td[2]) ? 1 : 2);
+                        bool fin = false;
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            if (k == axj) {
+                                cu[k] += step[k];
+                                td[k] = __fadd_rn(td[k], delta[k]);
+                                fin = cu[k] == over[k];
+                            }
+                        }
+                        if (fin) break;
+                    }
+                    const bool o = lane < (uint32_t)n_ahead && a.binaries[mine] != 0;
+                    occ_bits = __ballot_sync(0xffffffffu, o);
+                    occ_left = n_ahead;
+                }
+                occupied = occ_bits & 1u;
+                occ_bits >>= 1;
+                occ_left--;
+            } else {
+                occupied = a.binaries[cell] != 0;
+            }
+            if (!occupied) {
                 if (a.step_size <= 0.0f) t_last = t_trav;
                 else {
                     const float dt = calc_dt(t_last, a.cone_angle, a.step_size, 1e10f);
@@ -188,26 +231,49 @@ __device__ __forceinline__ int64_t march_ray(const MarchArgs &a, int64_t tid, fl
 template <bool RAY_PER_WARP>
 __global__ void __launch_bounds__(128) traverse_kernel(const MarchArgs a) {
     int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (RAY_PER_WARP) {
-        if (threadIdx.x & 31) return;
-        tid >>= 5;
-    }
+    const uint32_t lane = threadIdx.x & 31u;
+    if (RAY_PER_WARP) tid >>= 5;
     if (tid >= a.n_rays) return;
     if (a.rays_mask && !a.rays_mask[tid]) {
-        if (a.cnt) a.cnt[tid] = 0;
+        if (a.cnt && (!RAY_PER_WARP || lane == 0)) a.cnt[tid] = 0;
         return;
     }
     const bool fill = a.t_starts != nullptr;
     const int64_t start = a.chunk_starts ? a.chunk_starts[tid] : 0;
     float t_last;
-    const int64_t n_samples = march_ray(a, tid, a.near_planes[tid], a.far_planes[tid], a.steps_limit,
-                                        [&](int64_t j, float t0, float t1) {
-                                            if (fill) {
-                                                a.t_starts[start + j] = t0;
-                                                a.t_ends[start + j] = t1;
-                                                a.ray_idx[start + j] = tid;
+    int64_t n_samples;
+    if (RAY_PER_WARP) {
+        // every lane sees every sample; lane (j % 32) keeps sample j, and 32 of them leave as one coalesced store
+        float k0 = 0.f, k1 = 0.f;
+        n_samples = march_ray<true>(a, tid, a.near_planes[tid], a.far_planes[tid], a.steps_limit,
+                                    [&](int64_t j, float t0, float t1) {
+                                        if (fill) {
+                                            if ((uint32_t)(j & 31) == lane) { k0 = t0; k1 = t1; }
+                                            if ((j & 31) == 31) {
+                                                const int64_t at = start + j - 31 + lane;
+                                                a.t_starts[at] = k0;
+                                                a.t_ends[at] = k1;
+                                                a.ray_idx[at] = tid;
                                             }
-                                        }, t_last);
+                                        }
+                                    }, t_last);
+        if (fill && lane < (uint32_t)(n_samples & 31)) {
+            const int64_t at = start + (n_samples & ~(int64_t)31) + lane;
+            a.t_starts[at] = k0;
+            a.t_ends[at] = k1;
+            a.ray_idx[at] = tid;
+        }
+        if (lane) return;
+    } else {
+        n_samples = march_ray(a, tid, a.near_planes[tid], a.far_planes[tid], a.steps_limit,
+                              [&](int64_t j, float t0, float t1) {
+                                  if (fill) {
+                                      a.t_starts[start + j] = t0;
+                                      a.t_ends[start + j] = t1;
+                                      a.ray_idx[start + j] = tid;
+                                  }
+                              }, t_last);
+    }
     if (a.terminate) a.terminate[tid] = t_last;
     if (a.cnt) a.cnt[tid] = n_samples;
 }
@@ -244,6 +310,91 @@ packed_scan_kernel(const float *__restrict__ in, const int64_t *__restrict__ pac
         if (ok) out[i] = inclusive ? inc : exc;
         carry = __shfl_sync(0xffffffffu, inc, 31);
     }
+}
+
+// Backward of render_density_kernel (+ the three accumulations) in one pass per ray, walking the ray from its far end:
+//   gw_i  = gC_r . c_i + gO_r + gD_r * mid_i (+ the gradient that arrives at the weights themselves)
+//   gc_i  = w_i * gC_r
+//   gs_i  = (gw_i * T_i * (1 - a_i) - sum_{j > i} gw_j * a_j * T_j) * (t1_i - t0_i)
+// (w = T a, T_i = exp(-sum_{j<i} s_j d_j), a_i = 1 - exp(-s_i d_i): d w_j / d s_i = -w_j d_i for j > i, T_i (1 - a_i) d_i for j = i).
+__global__ void __launch_bounds__(128)
+render_bwd_kernel(const float *__restrict__ t0, const float *__restrict__ t1, const float *__restrict__ trans,
+                  const float *__restrict__ alphas, const float *__restrict__ weights, const float *__restrict__ rgb,
+                  const int64_t *__restrict__ packed, int64_t n_rays, const float *__restrict__ g_colors,
+                  const float *__restrict__ g_opac, const float *__restrict__ g_depth, const float *__restrict__ g_weights,
+                  float *__restrict__ g_sigma, float *__restrict__ g_rgb) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (r >= n_rays) return;
+    const int64_t s = packed[r * 2], c = packed[r * 2 + 1];
+    const float gr = g_colors ? g_colors[r * 3] : 0.f, gg = g_colors ? g_colors[r * 3 + 1] : 0.f, gb = g_colors ? g_colors[r * 3 + 2] : 0.f;
+    const float go = g_opac ? g_opac[r] : 0.f, gd = g_depth ? g_depth[r] : 0.f;
+    float carry = 0.f;
+    for (int64_t j0 = 0; j0 < c; j0 += 32) {
+        const int64_t j = j0 + lane;
+        const bool ok = j < c;
+        const int64_t i = s + c - 1 - j;
+        float a0 = 0.f, a1 = 0.f, T = 0.f, al = 0.f, gw = 0.f;
+        if (ok) {
+            a0 = t0[i];
+            a1 = t1[i];
+            T = trans[i];
+            al = alphas[i];
+            const float mid = __fmul_rn(__fadd_rn(a0, a1), 0.5f);
+            const float cr = rgb[i * 3], cg = rgb[i * 3 + 1], cb = rgb[i * 3 + 2];
+            gw = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(gr, cr), __fmul_rn(gg, cg)), __fmul_rn(gb, cb)), go), __fmul_rn(gd, mid));
+            if (g_weights) gw = __fadd_rn(gw, g_weights[i]);
+            const float w = weights[i];
+            g_rgb[i * 3] = __fmul_rn(w, gr);
+            g_rgb[i * 3 + 1] = __fmul_rn(w, gg);
+            g_rgb[i * 3 + 2] = __fmul_rn(w, gb);
+        }
+        const float gt = ok ? __fmul_rn(__fmul_rn(gw, al), T) : 0.f;
+        const float inc = __fadd_rn(carry, warp_incl_scan(gt, 0, lane));
+        float exc = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) exc = carry;
+        carry = __shfl_sync(0xffffffffu, inc, 31);
+        if (ok) g_sigma[i] = __fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn(gw, T), __fsub_rn(1.0f, al)), exc), __fsub_rn(a1, a0));
+    }
+}
+
+// ray samples -> query points: positions = o[r] + d[r] * (t0 + t1) / 2 and the direction of the ray, per sample
+// (examples/utils.py:250-262: the rgb_sigma_fn / sigma_fn closures of the training and test renderers)
+__global__ void __launch_bounds__(256)
+sample_points_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d, const int64_t *__restrict__ ray_idx,
+                     const float *__restrict__ t0, const float *__restrict__ t1, int64_t n, float *__restrict__ pos,
+                     float *__restrict__ dirs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t r = ray_idx[i];
+    const float h = __fadd_rn(t0[i], t1[i]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float d = rays_d[r * 3 + k];
+        pos[i * 3 + k] = __fadd_rn(rays_o[r * 3 + k], __fdiv_rn(__fmul_rn(d, h), 2.0f));
+        if (dirs) dirs[i * 3 + k] = d;
+    }
+}
+
+// keep[i] != 0 samples move to the front, order kept: out index = exclusive count of kept samples before i (`rank`, an
+// int64 inclusive prefix sum of keep computed by the caller, so rank[i] - 1 is the slot of a kept sample)
+__global__ void __launch_bounds__(256)
+compact_samples_kernel(const uint8_t *__restrict__ keep, const int64_t *__restrict__ rank, int64_t n, const float *__restrict__ t0,
+                       const float *__restrict__ t1, const int64_t *__restrict__ ray_idx, float *__restrict__ o0,
+                       float *__restrict__ o1, int64_t *__restrict__ oi, const int64_t *__restrict__ packed, int64_t n_rays,
+                       int64_t *__restrict__ packed_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (packed_out && i < n_rays) {   // (start, count) of the ray's kept samples: pack_info of the compacted ray_indices
+        const int64_t s = packed[i * 2], c = packed[i * 2 + 1];
+        const int64_t before = s > 0 ? rank[(s < n ? s : n) - 1] : 0;
+        packed_out[i * 2] = before;
+        packed_out[i * 2 + 1] = (c > 0 ? rank[s + c - 1] : before) - before;
+    }
+    if (i >= n || !keep[i]) return;
+    const int64_t k = rank[i] - 1;
+    o0[k] = t0[i];
+    o1[k] = t1[i];
+    oi[k] = ray_idx[i];
 }
 
 // volrend.py:211-266 + :314-364 + :485-549 in one pass per ray, one warp per ray (32 samples per pass)
@@ -542,6 +693,43 @@ int cnc_packed_scan(const float *in, const int64_t *packed_info, int64_t n_rays,
     if (!in || !packed_info || !out) { set_error("packed_scan: null pointer"); return CNC_EINVAL; }
     mr::packed_scan_kernel<<<div_up((uint64_t)n_rays * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(in, packed_info, n_rays, out, op, inclusive, reverse);
     return check_launch("packed_scan");
+}
+
+int cnc_render_bwd(const float *t_starts, const float *t_ends, const float *trans, const float *alphas, const float *weights,
+                   const float *rgbs, const int64_t *packed_info, int64_t n_rays, const float *g_colors, const float *g_opacities,
+                   const float *g_depths, const float *g_weights, float *g_sigmas, float *g_rgbs, cnc_stream_t stream) {
+    if (n_rays == 0) return CNC_OK;
+    if (!t_starts || !t_ends || !trans || !alphas || !weights || !rgbs || !packed_info || !g_sigmas || !g_rgbs) {
+        set_error("render_bwd: null pointer");
+        return CNC_EINVAL;
+    }
+    mr::render_bwd_kernel<<<div_up((uint64_t)n_rays * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        t_starts, t_ends, trans, alphas, weights, rgbs, packed_info, n_rays, g_colors, g_opacities, g_depths, g_weights, g_sigmas, g_rgbs);
+    return check_launch("render_bwd");
+}
+
+int cnc_sample_points(const float *rays_o, const float *rays_d, const int64_t *ray_indices, const float *t_starts, const float *t_ends,
+                      int64_t n, float *positions, float *dirs, cnc_stream_t stream) {
+    if (n == 0) return CNC_OK;
+    if (!rays_o || !rays_d || !ray_indices || !t_starts || !t_ends || !positions) { set_error("sample_points: null pointer"); return CNC_EINVAL; }
+    mr::sample_points_kernel<<<div_up((uint64_t)n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rays_o, rays_d, ray_indices, t_starts,
+                                                                                                  t_ends, n, positions, dirs);
+    return check_launch("sample_points");
+}
+
+int cnc_compact_samples(const uint8_t *keep, const int64_t *rank, int64_t n, const float *t_starts, const float *t_ends,
+                        const int64_t *ray_indices, float *out_t_starts, float *out_t_ends, int64_t *out_ray_indices,
+                        const int64_t *packed_info, int64_t n_rays, int64_t *out_packed_info, cnc_stream_t stream) {
+    if (n == 0) return CNC_OK;
+    if (!keep || !rank || !t_starts || !t_ends || !ray_indices || !out_t_starts || !out_t_ends || !out_ray_indices ||
+        (out_packed_info && !packed_info)) {
+        set_error("compact_samples: null pointer");
+        return CNC_EINVAL;
+    }
+    const uint64_t threads = (uint64_t)(out_packed_info && n_rays > n ? n_rays : n);
+    mr::compact_samples_kernel<<<div_up(threads, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        keep, rank, n, t_starts, t_ends, ray_indices, out_t_starts, out_t_ends, out_ray_indices, packed_info, n_rays, out_packed_info);
+    return check_launch("compact_samples");
 }
 
 int cnc_render_from_density(const float *t_starts, const float *t_ends, const float *sigmas, const float *rgbs,

@@ -175,6 +175,20 @@ def ray_aabb_intersect(rays_o: Tensor, rays_d: Tensor, aabbs: Tensor, near_plane
     return t_mins, t_maxs, hits.bool()
 
 
+_INDEX01 = {}
+
+
+def _index01(n: int, dev) -> Tensor:
+    """[[0, 1]] * n (int64): what torch.sort returns as indices for a single box"""
+    key = (str(dev), n)
+    t = _INDEX01.get(key)
+    if t is None:
+        if len(_INDEX01) > 16:
+            _INDEX01.clear()
+        t = _INDEX01[key] = torch.tensor([0, 1], dtype=torch.int64, device=dev).repeat(n, 1)
+    return t
+
+
 @torch.no_grad()
 def traverse_grids(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tensor, near_planes: Optional[Tensor] = None,
                    far_planes: Optional[Tensor] = None, step_size: Optional[float] = 1e-3, cone_angle: Optional[float] = 0.0,
@@ -198,7 +212,11 @@ def traverse_grids(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tens
         traverse_steps_limit = -1
     if t_sorted is None or t_indices is None or hits is None:
         t_mins, t_maxs, hits = ray_aabb_intersect(o, d, aabbs)
-        t_sorted, t_indices = torch.sort(torch.cat([t_mins, t_maxs], dim=-1), dim=-1)
+        if aabbs.shape[0] == 1:     # one box: entry before exit (a miss has both at the same value; the stable order is 0, 1)
+            t_sorted = torch.cat([t_mins, t_maxs], dim=-1)
+            t_indices = _index01(n, dev)
+        else:
+            t_sorted, t_indices = torch.sort(torch.cat([t_mins, t_maxs], dim=-1), dim=-1)
     G = aabbs.shape[0]
     bins = binaries.contiguous()
     bins_u8 = bins.view(torch.uint8) if bins.dtype == torch.bool else bins.to(torch.uint8)
@@ -232,12 +250,39 @@ def traverse_grids(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tens
     return intervals, samples, term
 
 
+def _compact(masks: Tensor, t_starts: Tensor, t_ends: Tensor, ray_indices: Tensor, packed_info: Tensor):
+    """(ray_indices[masks], t_starts[masks], t_ends[masks]) (occ_grid.py:192-197) as one prefix sum, one host read of the
+    count and one kernel; the (start, count) table of what is kept rides along on the returned `ray_indices`
+    (`_packed` below picks it up, so `rendering` does not rebuild it with an index_add over all samples)."""
+    n = masks.shape[0]
+    if n == 0:
+        return ray_indices, t_starts, t_ends
+    keep = masks.contiguous().view(torch.uint8) if masks.dtype == torch.bool else masks.contiguous().to(torch.uint8)
+    rank = keep.cumsum(0, dtype=torch.int64)
+    total = int(rank[-1])                          # the host sync `nonzero` / boolean indexing has as well
+    dev = masks.device
+    t0, t1 = torch.empty(total, device=dev), torch.empty(total, device=dev)
+    ri = torch.empty(total, dtype=torch.int64, device=dev)
+    R = packed_info.shape[0]
+    if total == 0:
+        ri._cnc_packed = torch.zeros(R, 2, dtype=torch.int64, device=dev)
+        return ri, t0, t1
+    pk = torch.empty(R, 2, dtype=torch.int64, device=dev)
+    check(lib().cnc_compact_samples(ptr(keep), ptr(rank), n, ptr(t_starts.contiguous()), ptr(t_ends.contiguous()),
+                                    ptr(ray_indices.contiguous()), ptr(t0), ptr(t1), ptr(ri), ptr(packed_info.contiguous()), R,
+                                    ptr(pk), stream()))
+    ri._cnc_packed = pk
+    return ri, t0, t1
+
+
 # ------------------------------------------------------------------------------------------ volume rendering
 def _packed(packed_info, ray_indices, n_rays, like):
     if packed_info is None:
         if ray_indices is None:
             raise ValueError("flattened samples need packed_info or ray_indices")
-        packed_info = pack_info(ray_indices, n_rays)
+        packed_info = getattr(ray_indices, "_cnc_packed", None)      # left by OccGridEstimator.sampling for exactly this tensor
+        if packed_info is None or packed_info.shape[0] != n_rays:
+            packed_info = pack_info(ray_indices, n_rays)
     return packed_info.contiguous().to(torch.int64)
 
 
@@ -293,16 +338,12 @@ class _RenderAll(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gw, gT, ga, gC, gO, gD):
         t0, t1, T, al, w, c, packed_info, ri = ctx.saved_tensors
-        mid = (t0 + t1) * 0.5
-        gw_tot = (gC[ri] * c).sum(-1) + gO[ri] + gD[ri] * mid
-        if gw is not None:
-            gw_tot = gw_tot + gw
-        g_rgb = w.unsqueeze(-1) * gC[ri]
-        g_alpha = (gw_tot * T) * (1 - al)
-        g_trans = (gw_tot * al) * T
-        out = torch.empty_like(T)
-        check(lib().cnc_packed_scan(ptr(g_trans.contiguous()), ptr(packed_info), packed_info.shape[0], ptr(out), 0, 0, 1, stream()))
-        return None, None, (g_alpha - out) * (t1 - t0), g_rgb, None, None
+        f = lambda g: None if g is None else g.contiguous().float()
+        gw, gC, gO, gD = f(gw), f(gC), f(gO), f(gD)
+        g_sigma, g_rgb = torch.empty_like(T), torch.empty_like(c)
+        check(lib().cnc_render_bwd(ptr(t0), ptr(t1), ptr(T), ptr(al), ptr(w), ptr(c), ptr(packed_info), packed_info.shape[0],
+                                   ptr(gC), ptr(gO), ptr(gD), ptr(gw), ptr(g_sigma), ptr(g_rgb), stream()))
+        return None, None, g_sigma, g_rgb, None, None
 
 
 def render_weight_from_density(t_starts, t_ends, sigmas, packed_info=None, ray_indices=None, n_rays=None, prefix_trans=None):
@@ -467,8 +508,7 @@ class OccGridEstimator(torch.nn.Module):
             assert sigmas.shape == t_starts.shape, "sigmas must have shape of (N,)! Got {}".format(sigmas.shape)
             masks = render_visibility_from_density(t_starts=t_starts, t_ends=t_ends, sigmas=sigmas, packed_info=packed_info,
                                                    early_stop_eps=early_stop_eps, alpha_thre=alpha_thre)
-            keep = masks.nonzero().squeeze(1)      # one compaction (and one host sync) instead of one per indexed tensor
-            ray_indices, t_starts, t_ends = ray_indices[keep], t_starts[keep], t_ends[keep]
+            ray_indices, t_starts, t_ends = _compact(masks, t_starts, t_ends, ray_indices, packed_info)
         return ray_indices, t_starts, t_ends
 
     @torch.no_grad()

@@ -27,6 +27,18 @@ def namedtuple_map(fn, tup):
     return type(tup)(*(None if x is None else fn(x) for x in tup))
 
 
+def sample_points(origins: torch.Tensor, viewdirs: torch.Tensor, ray_indices: torch.Tensor, t_starts: torch.Tensor,
+                  t_ends: torch.Tensor):
+    """(origins[ri] + viewdirs[ri] * (t_starts + t_ends)[:, None] / 2, viewdirs[ri]) -- the query points of
+    examples/utils.py:250-262 -- in one pass (csrc/march_render.cu, `cnc_sample_points`); no gradient"""
+    n = t_starts.shape[0]
+    pos = torch.empty(n, 3, device=origins.device)
+    dirs = torch.empty(n, 3, device=origins.device)
+    check(lib().cnc_sample_points(ptr(origins.contiguous()), ptr(viewdirs.contiguous()), ptr(ray_indices.contiguous()),
+                                  ptr(t_starts.contiguous()), ptr(t_ends.contiguous()), n, ptr(pos), ptr(dirs), stream()))
+    return pos, dirs
+
+
 def render_image_with_occgrid(radiance_field: torch.nn.Module, estimator: OccGridEstimator, rays: Rays, near_plane: float = 0.0,
                               far_plane: float = 1e10, render_step_size: float = 1e-3, render_bkgd: Optional[torch.Tensor] = None,
                               cone_angle: float = 0.0, alpha_thre: float = 0.0, test_chunk_size: int = 8192, timestamps=None,
@@ -42,8 +54,11 @@ def render_image_with_occgrid(radiance_field: torch.nn.Module, estimator: OccGri
         num_rays = rays_shape[0]
 
     def positions_of(chunk_rays, t_starts, t_ends, ray_indices):
-        t_dirs = chunk_rays.viewdirs[ray_indices]
-        return chunk_rays.origins[ray_indices] + t_dirs * (t_starts + t_ends)[:, None] / 2.0, t_dirs
+        o, d = chunk_rays.origins, chunk_rays.viewdirs
+        if o.is_cuda and o.dtype == torch.float32 and not (o.requires_grad or d.requires_grad or t_starts.requires_grad):
+            return sample_points(o, d, ray_indices, t_starts, t_ends)      # the two lines below as one kernel
+        t_dirs = d[ray_indices]
+        return o[ray_indices] + t_dirs * (t_starts + t_ends)[:, None] / 2.0, t_dirs
 
     results, extras = [], None
     chunk = torch.iinfo(torch.int32).max if radiance_field.training else test_chunk_size

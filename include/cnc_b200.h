@@ -477,6 +477,23 @@ int cnc_render_from_density(const float *t_starts, const float *t_ends, const fl
                             const float *rgbs, const int64_t *packed_info, int64_t n_rays,
                             const float *prefix_trans, float *weights, float *trans, float *alphas,
                             float *colors, float *opacities, float *depths, cnc_stream_t stream);
+/* backward of cnc_render_from_density (weights, colours, opacities, weighted depths) in one pass per ray: the analytic
+ * gradient nerfacc's autograd assembles from render_weight_from_density + accumulate_along_rays (volrend.py:14-160);
+ * g_colors [R,3] / g_opacities [R] / g_depths [R] / g_weights [n] nullable (= zero) */
+int cnc_render_bwd(const float *t_starts, const float *t_ends, const float *trans, const float *alphas, const float *weights,
+                   const float *rgbs, const int64_t *packed_info, int64_t n_rays, const float *g_colors, const float *g_opacities,
+                   const float *g_depths, const float *g_weights, float *g_sigmas, float *g_rgbs, cnc_stream_t stream);
+/* query points of ray samples: positions[i] = o[r] + d[r] * (t0 + t1) / 2, dirs[i] = d[r], r = ray_indices[i]
+ * (examples/utils.py:250-262, the sigma_fn / rgb_sigma_fn closures); dirs nullable */
+int cnc_sample_points(const float *rays_o, const float *rays_d, const int64_t *ray_indices, const float *t_starts, const float *t_ends,
+                      int64_t n, float *positions, float *dirs, cnc_stream_t stream);
+/* samples with keep[i] != 0 move to slot rank[i] - 1 (rank = inclusive int64 prefix sum of keep), order kept: the
+ * `t_starts[masks], t_ends[masks], ray_indices[masks]` of OccGridEstimator.sampling (occ_grid.py:192-197);
+ * out_packed_info [n_rays,2] (nullable) = (start, count) per ray of what is kept, from packed_info [n_rays,2] of the input
+ * (= pack_info(ray_indices[masks]), pack.py:9-37) */
+int cnc_compact_samples(const uint8_t *keep, const int64_t *rank, int64_t n, const float *t_starts, const float *t_ends,
+                        const int64_t *ray_indices, float *out_t_starts, float *out_t_ends, int64_t *out_ray_indices,
+                        const int64_t *packed_info, int64_t n_rays, int64_t *out_packed_info, cnc_stream_t stream);
 
 #ifdef __cplusplus
 }

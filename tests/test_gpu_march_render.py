@@ -272,3 +272,51 @@ def test_device_loop_equals_the_host_loop(cuda, cone, step, alpha_thre):
     assert float(a[1].mean()) > 0.3
     if cone == 0.0:
         assert float((a[1] > 1 - 1e-4).float().mean()) > 0.05   # rays did saturate
+
+
+def test_fused_render_backward_sample_points_and_compaction(cuda):
+    """the one-kernel pieces of the training step against the torch expressions they replace: the analytic backward of the
+    rendering tail (volrend.py:14-160 through autograd), the query points of a sample batch (examples/utils.py:250-262) and
+    the boolean-mask compaction of OccGridEstimator.sampling (occ_grid.py:192-197) with its pack_info"""
+    from cnc_b200 import nerfacc as N
+    from cnc_b200.render import sample_points
+
+    g = torch.Generator().manual_seed(3)
+    cnt = torch.randint(0, 90, (700,), generator=g)
+    cnt[5] = 0
+    cnt[-1] = 0
+    n, R = int(cnt.sum()), cnt.numel()
+    ri = torch.repeat_interleave(torch.arange(R), cnt).to(cuda)
+    t0 = (torch.rand(n, generator=g) * 3).to(cuda)
+    t1 = t0 + 5e-3
+    sig = (torch.rand(n, generator=g) * 30).to(cuda).requires_grad_(True)
+    rgb = torch.rand(n, 3, generator=g).to(cuda).requires_grad_(True)
+    pk = N.pack_info(ri, R)
+    # --- backward: the fused Function vs the op-by-op composition (scans + index_add), same upstream gradients
+    w, T_, al, col, op, dp = N._RenderAll.apply(t0, t1, sig, rgb, pk, ri)
+    gC, gO, gD, gW = (torch.randn(R, 3, generator=g).to(cuda), torch.randn(R, generator=g).to(cuda), torch.randn(R, generator=g).to(cuda),
+                      torch.randn(n, generator=g).to(cuda))
+    (col * gC).sum().add((op * gO).sum()).add((dp * gD).sum()).add((w * gW).sum()).backward()
+    gs1, gr1 = sig.grad.clone(), rgb.grad.clone()
+    sig.grad = rgb.grad = None
+    w2, _, _ = N.render_weight_from_density(t0, t1, sig, ray_indices=ri, n_rays=R)
+    col2 = N.accumulate_along_rays(w2, rgb, ri, R)
+    op2 = N.accumulate_along_rays(w2, None, ri, R).squeeze(-1)
+    dp2 = N.accumulate_along_rays(w2, ((t0 + t1) / 2)[:, None], ri, R).squeeze(-1)
+    (col2 * gC).sum().add((op2 * gO).sum()).add((dp2 * gD).sum()).add((w2 * gW).sum()).backward()
+    torch.testing.assert_close(gr1, rgb.grad, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(gs1, sig.grad, rtol=2e-4, atol=2e-5 * float(sig.grad.abs().max()))
+    # --- query points
+    o, d = torch.randn(R, 3, generator=g).to(cuda), torch.randn(R, 3, generator=g).to(cuda)
+    pos, dirs = sample_points(o, d, ri, t0, t1)
+    assert torch.equal(dirs, d[ri])
+    assert torch.equal(pos, o[ri] + d[ri] * (t0 + t1)[:, None] / 2.0)
+    # --- compaction
+    keep = (torch.rand(n, generator=g) < 0.4).to(cuda)
+    ri2, a0, a1 = N._compact(keep, t0, t1, ri, pk)
+    assert torch.equal(ri2, ri[keep]) and torch.equal(a0, t0[keep]) and torch.equal(a1, t1[keep])
+    assert torch.equal(ri2._cnc_packed, N.pack_info(ri[keep], R))
+    assert N._packed(None, ri2, R, None) is ri2._cnc_packed or torch.equal(N._packed(None, ri2, R, None), ri2._cnc_packed)
+    none = torch.zeros(n, dtype=torch.bool, device=cuda)
+    ri3, b0, b1 = N._compact(none, t0, t1, ri, pk)
+    assert ri3.numel() == 0 and torch.equal(ri3._cnc_packed, torch.zeros(R, 2, dtype=torch.int64, device=cuda))
