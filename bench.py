@@ -498,7 +498,9 @@ def train_bench(arm, rank, world, steps, field):
         from cnc_b200.trainer import TrainStep
 
         ts = TrainStep(field, est, lr=1e-4, exchange=os.environ.get("CNC_EXCHANGE", "auto"))
-        call = lambda t: t(rays, pixels, render_bkgd=bk, refresh_occupancy=False)
+        # the batch of the next step is known while this one runs (here: the same rays), so its occupancy march overlaps this
+        # step's forward / backward on a side stream (trainer.TrainStep `next_rays`); `no_lookahead_ms` below is without
+        call = lambda t, ahead=True: t(rays, pixels, render_bkgd=bk, refresh_occupancy=False, next_rays=(lambda n: rays) if ahead else None)
     else:
         ts = RefTrainStep(arm, field, est, lr=1e-4)
         call = lambda t: t(rays, pixels, refresh_occupancy=False)
@@ -531,6 +533,22 @@ def train_bench(arm, rank, world, steps, field):
            "steps": steps, "ms_per_step": ms / steps, "scaling": "weak",
            "samples_per_step_all_ranks": tot / steps, "samples_per_s": tot / (ms * 1e-3),
            "comm_bytes_per_step": ts.comm_bytes_per_step() if (ours and world > 1) else 0, "rays_per_rank": n_rays}
+    if ours:
+        for _ in range(2):
+            call(ts, False)
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        e0.record()
+        for _ in range(steps):
+            call(ts, False)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        out["no_lookahead_ms"] = float(t[0]) / steps
+        out["lookahead"] = "occupancy march of the next batch issued on a side stream during this step (same samples)"
     if ours and world > 1:
         out["comm"] = ts.comm_description()
         if ts.table_opt is not None and ts.table_opt.peer is not None:

@@ -728,9 +728,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                         hs[k] = h;
                         split_tf32(h, hi[k], lo[k]);
                     }
-                    // training forward: geo goes out as rows of 80 (column 0 = the slot of the density pre-activation, not
-                    // used by the consumer), one 32-byte store per block instead of 79 scalar stores per sample
-                    if (SAVE && a.geo != nullptr && live) st_global_v8(a.geo + (size_t)row * 80 + 8 * b, hs);
+                    // training forward: the head input goes out as rows of 96 in the kernel's own column order (SH0 | geo 0..78 |
+                    // SH1..15 | 0, see head_src_col) -- what the weight gradient of the first head layer contracts with -- one
+                    // 32-byte store per block of 8 columns
+                    if (SAVE && a.geo != nullptr && live) st_global_v8(a.geo + (size_t)row * 96 + 8 * b, hs);
                     if (!DENSITY_ONLY) {
                         tmem_st8(tl + 0u + 8 * b, hi);
                         tmem_st8(tl + 96u + 8 * b, lo);
@@ -744,11 +745,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_fwd_kernel(const FieldArgs 
                         d3[d] = __fsub_rn(__fmul_rn(d01, 2.f), 1.f);             // tcnn maps back to [-1,1]
                     }
                     sh16_eval_h(d3[0], d3[1], d3[2], sh);
+                    float vs[8];
 #pragma unroll
                     for (int k = 0; k < 8; k++) {
                         const float v = (b == 10) ? sh[1 + k] : (k < 7 ? sh[9 + k] : 0.f);
+                        vs[k] = v;
                         split_tf32(v, hi[k], lo[k]);
                     }
+                    if (SAVE && a.geo != nullptr && live) st_global_v8(a.geo + (size_t)row * 96 + 8 * b, vs);
                     tmem_st8(tl + 8u * b, hi);
                     tmem_st8(tl + 96u + 8u * b, lo);
                 }
@@ -1059,7 +1063,7 @@ int cnc_field_fwd_train(const float *pos, const float *dirs, const float *aabb6_
     if (!dirs || !geo || !x0 || !h1 || !h3 || !h4) { set_error("field_fwd_train: null pointer"); return CNC_EINVAL; }
     if ((reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(h1) | reinterpret_cast<uintptr_t>(h3) |
          reinterpret_cast<uintptr_t>(h4) | reinterpret_cast<uintptr_t>(geo)) & 31u) {
-        set_error("field_fwd_train: activation buffers must be 32-byte aligned (rows leave as 256-bit stores); geo is [N,80]");
+        set_error("field_fwd_train: activation buffers must be 32-byte aligned (rows leave as 256-bit stores); head_in is [N,96]");
         return CNC_EINVAL;
     }
     return field_fwd_impl(pos, dirs, aabb6_host, bits_xyz, bits_xy, bits_xz, bits_yz, offsets3, resolutions3, offsets2,

@@ -94,7 +94,7 @@ class _FusedFieldTrain(Function):
         bits = [e.sign_bits() for e in encs]
         sigma = torch.empty(n, device=dev)
         rgb = torch.empty(n, 3, device=dev)
-        geo = torch.empty(n, 80, device=dev)      # columns 1..79 (column 0 is scratch: rows leave the kernel as 256-bit stores)
+        geo = torch.empty(n, 96, device=dev)      # the head input, columns in the kernel's order (_HEAD_ROW_OF below)
         x0 = torch.empty(n, 256, device=dev)
         h1, h3, h4 = (torch.empty(n, 160, device=dev) for _ in range(3))
         check(lib().cnc_field_fwd_train(ptr(pos), ptr(dirs), ctypes.addressof(field._aabb_c()), *[ptr(b) for b in bits],
@@ -155,15 +155,26 @@ class _FusedFieldTrain(Function):
         gW5, gb5 = g5[:160, :3].t(), g5[160, :3]
         g4 = wgrad(h3, dz4, with_ones=True)                     # [161, 160]: rows = input features, last row = bias grad
         gW4, gb4 = g4[:160].t(), g4[160]
-        head_in = torch.cat([sh16((dirs + 1.0) / 2.0), geo[:, 1:], geo.new_zeros(n, 1)], dim=-1)   # ngp.py:540-542 (+ pad to 96)
-        g3 = wgrad(head_in, dz3, with_ones=True)
-        gW3, gb3 = g3[:95].t(), g3[96]
+        g3 = wgrad(geo, dz3, with_ones=True)                    # rows in the saved column order; [96] = bias
+        gW3, gb3 = g3[_head_rows(g3.device)].t(), g3[96]        # -> cat[SH16, geo79] order (ngp.py:540-542)
         g2 = wgrad(h1, dz2, with_ones=True)
         gW2, gb2 = g2[:160].t(), g2[160]
         g1 = wgrad(x0, dz1)                                     # x0 column 255 is the kernel's all-ones pad column
         gW1, gb1 = g1[:255].t(), g1[255]
         return (None, None, None, *grads, gW1, gb1, gW2, gb2, gW3, gb3, gW4, gb4, gW5, gb5)
 
+
+
+_HEAD_ROWS = {}
+
+
+def _head_rows(dev) -> torch.Tensor:
+    """row of the saved head input (SH0 | geo 0..78 | SH1..15 | 0, csrc/field_fused.cu head_src_col) that holds column c of
+    cat[SH16, geo79], c = 0..94"""
+    t = _HEAD_ROWS.get(str(dev))
+    if t is None:
+        t = _HEAD_ROWS[str(dev)] = torch.tensor([0] + list(range(80, 95)) + list(range(1, 80)), dtype=torch.int64, device=dev)
+    return t
 
 
 def sh16(d01: torch.Tensor, fp16_round: bool = True) -> torch.Tensor:

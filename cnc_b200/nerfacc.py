@@ -449,6 +449,119 @@ def _enlarge_aabb(aabb, factor: float) -> Tensor:
     return torch.cat([center - extent * factor, center + extent * factor])
 
 
+class Premarch:
+    """The occupancy march of a ray batch, issued before the batch is needed (not in nerfacc).
+
+    The march depends on the rays and on the occupancy grid only -- not on the field -- so a training loop that knows its
+    next batch can run it on a side stream while the current step's forward / backward occupy the device: count pass,
+    prefix sum, and the fill pass into a buffer kept from step to step (no size is needed on the host in between; a batch
+    that outgrows the buffer is filled again at its exact size when it is taken).  `take` hands the result to
+    `OccGridEstimator.sampling`; the samples are the ones the in-line march produces, bit for bit: same kernels, same random
+    jitter draw (the caller keeps the order of draws, see trainer.TrainStep)."""
+
+    def __init__(self, device, capacity: int = 1 << 20):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.capacity = capacity
+        self.sets = [None, None]          # two buffer sets: the consumer of one step may still hold views of the other
+        self.turn = 0
+        self.pending = None
+        self.taken = 0                    # marches handed to a step so far
+        self.total_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+
+    def _buffers(self, k):
+        b = self.sets[k]
+        if b is None or b[0].numel() < self.capacity:
+            b = self.sets[k] = (torch.empty(self.capacity, device=self.device), torch.empty(self.capacity, device=self.device),
+                                torch.empty(self.capacity, dtype=torch.int64, device=self.device))
+        return b
+
+    @torch.no_grad()
+    def issue(self, est: "OccGridEstimator", rays_o: Tensor, rays_d: Tensor, near_plane: float = 0.0, far_plane: float = 1e10,
+              t_min=None, t_max=None, render_step_size: float = 1e-3, stratified: bool = False, cone_angle: float = 0.0) -> None:
+        """start the march of (rays_o, rays_d) against the estimator's CURRENT grid; everything queued on the current
+        stream so far (e.g. an occupancy refresh) is ordered before it"""
+        entry = torch.cuda.Event()
+        entry.record()
+        o, d = rays_o.contiguous().float(), rays_d.contiguous().float()
+        n, dev = o.shape[0], o.device
+        k = self.turn
+        self.turn ^= 1
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(entry)
+            near_planes, far_planes = est._planes(o, near_plane, far_plane, t_min, t_max)
+            if stratified:
+                near_planes += torch.rand_like(near_planes) * render_step_size
+            t_mins, t_maxs, hits = ray_aabb_intersect(o, d, est.aabbs)
+            if est.aabbs.shape[0] == 1:
+                t_sorted, t_indices = torch.cat([t_mins, t_maxs], dim=-1), _index01(n, dev)
+            else:
+                t_sorted, t_indices = torch.sort(torch.cat([t_mins, t_maxs], dim=-1), dim=-1)
+            bins = est.binaries.contiguous()
+            args = dict(o=o, d=d, bins=bins, bins_u8=bins.view(torch.uint8) if bins.dtype == torch.bool else bins.to(torch.uint8),
+                        bb=est.aabbs.contiguous().float(), hits=hits.contiguous().to(torch.uint8), ts=t_sorted.contiguous().float(),
+                        ti=t_indices.contiguous(), near=near_planes.contiguous(), far=far_planes.contiguous(),
+                        step=float(render_step_size), cone=float(cone_angle))
+            cnt = torch.empty(n, dtype=torch.int64, device=dev)
+            _march_pass(args, None, None, None, None, None, cnt)
+            ends = cnt.cumsum(0)
+            starts = ends - cnt
+            self.total_host.copy_(ends[-1:], non_blocking=True)
+            counted = torch.cuda.Event()
+            counted.record()
+            t0, t1, ri = self._buffers(k)
+            fits = (ends <= t0.numel()).to(torch.uint8)          # rays that would run past the buffer are left out (see take)
+            _march_pass(args, fits, starts, t0, t1, ri, None)
+            filled = torch.cuda.Event()
+            filled.record()
+        self.pending = dict(key=(rays_o.data_ptr(), rays_d.data_ptr(), n, float(near_plane), float(far_plane), float(render_step_size),
+                                 bool(stratified), float(cone_angle), id(est.binaries)),
+                            args=args, starts=starts, cnt=cnt, bufs=(t0, t1, ri), counted=counted, filled=filled,
+                            keep=(rays_o, rays_d))
+
+    def matches(self, est, rays_o, rays_d, near_plane, far_plane, render_step_size, stratified, cone_angle) -> bool:
+        p = self.pending
+        return p is not None and p["key"] == (rays_o.data_ptr(), rays_d.data_ptr(), rays_o.shape[0], float(near_plane), float(far_plane),
+                                              float(render_step_size), bool(stratified), float(cone_angle), id(est.binaries))
+
+    def drop(self) -> None:
+        self.pending = None
+
+    @torch.no_grad()
+    def take(self, est, rays_o, rays_d, near_plane, far_plane, t_min, t_max, render_step_size, stratified, cone_angle):
+        """(t_starts, t_ends, ray_indices, packed_info) of the pending march; the current stream waits for it"""
+        if t_min is not None or t_max is not None or not self.matches(est, rays_o, rays_d, near_plane, far_plane, render_step_size,
+                                                                      stratified, cone_angle):
+            raise RuntimeError("Premarch.take: no march pending for these rays and this grid (check with matches() first)")
+        p, self.pending = self.pending, None
+        self.taken += 1
+        p["counted"].synchronize()
+        total = int(self.total_host[0])
+        cur = torch.cuda.current_stream()
+        cur.wait_event(p["filled"])
+        t0, t1, ri = p["bufs"]
+        if total > t0.numel():                # outgrown: fill at the exact size now, and start the next one larger
+            self.capacity = max(2 * self.capacity, int(total * 1.5))
+            t0, t1 = torch.empty(total, device=self.device), torch.empty(total, device=self.device)
+            ri = torch.empty(total, dtype=torch.int64, device=self.device)
+            for t in p["args"].values():
+                if isinstance(t, Tensor):
+                    t.record_stream(cur)
+            _march_pass(p["args"], None, p["starts"], t0, t1, ri, None)
+        for t in (t0, t1, ri, p["starts"], p["cnt"]):
+            t.record_stream(cur)
+        packed = torch.stack([p["starts"], p["cnt"]], dim=-1)
+        return t0[:total], t1[:total], ri[:total], packed
+
+
+def _march_pass(a, rays_mask, starts, t0, t1, ri, cnt) -> None:
+    G, bins = a["bb"].shape[0], a["bins"]
+    check(lib().cnc_traverse_grids(ptr(a["o"]), ptr(a["d"]), ptr(rays_mask), a["o"].shape[0], G, bins.shape[-3], bins.shape[-2],
+                                   bins.shape[-1], ptr(a["bins_u8"]), ptr(a["bb"]), ptr(a["hits"]), ptr(a["ts"]), ptr(a["ti"]),
+                                   ptr(a["near"]), ptr(a["far"]), a["step"], a["cone"], -1, ptr(starts), ptr(cnt), ptr(t0), ptr(t1),
+                                   ptr(ri), None, stream()))
+
+
 class OccGridEstimator(torch.nn.Module):
     """Occupancy-grid transmittance estimator.  nerfacc/estimators/occ_grid.py:19-424"""
 
@@ -485,20 +598,21 @@ class OccGridEstimator(torch.nn.Module):
     def sampling(self, rays_o: Tensor, rays_d: Tensor, sigma_fn: Optional[Callable] = None, alpha_fn: Optional[Callable] = None,
                  near_plane: float = 0.0, far_plane: float = 1e10, t_min: Optional[Tensor] = None, t_max: Optional[Tensor] = None,
                  render_step_size: float = 1e-3, early_stop_eps: float = 1e-4, alpha_thre: float = 0.0, stratified: bool = False,
-                 cone_angle: float = 0.0) -> Tuple[Tensor, Tensor, Tensor]:
-        """(ray_indices, t_starts, t_ends) of the samples that survive occupancy + visibility skipping.  :88-239"""
-        near_planes = torch.full_like(rays_o[..., 0], fill_value=near_plane)
-        far_planes = torch.full_like(rays_o[..., 0], fill_value=far_plane)
-        if t_min is not None:
-            near_planes = torch.clamp(near_planes, min=t_min)
-        if t_max is not None:
-            far_planes = torch.clamp(far_planes, max=t_max)
-        if stratified:
-            near_planes += torch.rand_like(near_planes) * render_step_size
-        intervals, samples, _ = traverse_grids(rays_o, rays_d, self.binaries, self.aabbs, near_planes=near_planes,
-                                               far_planes=far_planes, step_size=render_step_size, cone_angle=cone_angle)
-        t_starts, t_ends = intervals.t_starts, intervals.t_ends      # == vals[is_left], vals[is_right] (occ_grid.py:188-189)
-        ray_indices, packed_info = samples.ray_indices, samples.packed_info
+                 cone_angle: float = 0.0, premarched: Optional["Premarch"] = None) -> Tuple[Tensor, Tensor, Tensor]:
+        """(ray_indices, t_starts, t_ends) of the samples that survive occupancy + visibility skipping.  :88-239
+        `premarched` (not in nerfacc): the occupancy march of exactly these rays, issued ahead of time (`Premarch`)."""
+        if premarched is None:
+            near_planes, far_planes = self._planes(rays_o, near_plane, far_plane, t_min, t_max)
+        if premarched is not None:
+            t_starts, t_ends, ray_indices, packed_info = premarched.take(self, rays_o, rays_d, near_plane, far_plane, t_min, t_max,
+                                                                         render_step_size, stratified, cone_angle)
+        else:
+            if stratified:
+                near_planes += torch.rand_like(near_planes) * render_step_size
+            intervals, samples, _ = traverse_grids(rays_o, rays_d, self.binaries, self.aabbs, near_planes=near_planes,
+                                                   far_planes=far_planes, step_size=render_step_size, cone_angle=cone_angle)
+            t_starts, t_ends = intervals.t_starts, intervals.t_ends      # == vals[is_left], vals[is_right] (occ_grid.py:188-189)
+            ray_indices, packed_info = samples.ray_indices, samples.packed_info
         if (alpha_thre > 0.0 or early_stop_eps > 0.0) and (sigma_fn is not None or alpha_fn is not None):
             if alpha_thre > 0.0:   # (min(alpha_thre <= 0, mean) cannot make the test below true: no device read needed)
                 alpha_thre = min(alpha_thre, self.occs.mean().item())
@@ -510,6 +624,16 @@ class OccGridEstimator(torch.nn.Module):
                                                    early_stop_eps=early_stop_eps, alpha_thre=alpha_thre)
             ray_indices, t_starts, t_ends = _compact(masks, t_starts, t_ends, ray_indices, packed_info)
         return ray_indices, t_starts, t_ends
+
+    @staticmethod
+    def _planes(rays_o, near_plane, far_plane, t_min, t_max):
+        near_planes = torch.full_like(rays_o[..., 0], fill_value=near_plane)
+        far_planes = torch.full_like(rays_o[..., 0], fill_value=far_plane)
+        if t_min is not None:
+            near_planes = torch.clamp(near_planes, min=t_min)
+        if t_max is not None:
+            far_planes = torch.clamp(far_planes, max=t_max)
+        return near_planes, far_planes
 
     @torch.no_grad()
     def update_every_n_steps(self, step: int, occ_eval_fn: Callable, occ_thre: float = 1e-2, ema_decay: float = 0.95,

@@ -42,8 +42,9 @@ def sample_points(origins: torch.Tensor, viewdirs: torch.Tensor, ray_indices: to
 def render_image_with_occgrid(radiance_field: torch.nn.Module, estimator: OccGridEstimator, rays: Rays, near_plane: float = 0.0,
                               far_plane: float = 1e10, render_step_size: float = 1e-3, render_bkgd: Optional[torch.Tensor] = None,
                               cone_angle: float = 0.0, alpha_thre: float = 0.0, test_chunk_size: int = 8192, timestamps=None,
-                              return_extra=False, tmp=None):
-    """(colors, opacities, depths, n_rendering_samples[, extras])"""
+                              return_extra=False, tmp=None, premarch=None):
+    """(colors, opacities, depths, n_rendering_samples[, extras]); `premarch` (not in the reference): a nerfacc.Premarch that
+    may hold the occupancy march of exactly these rays, issued ahead of time"""
     if timestamps is not None:
         raise NotImplementedError("timestamps belong to the dynamic-scene fields, which the CNC scripts do not use")
     rays_shape = rays.origins.shape
@@ -74,11 +75,14 @@ def render_image_with_occgrid(radiance_field: torch.nn.Module, estimator: OccGri
             rgbs, sigmas = radiance_field(positions, t_dirs)
             return rgbs, sigmas.squeeze(-1), positions
 
+        ahead = premarch if (premarch is not None and premarch.matches(estimator, chunk_rays.origins, chunk_rays.viewdirs, near_plane,
+                                                                       far_plane, render_step_size, radiance_field.training,
+                                                                       cone_angle)) else None
         ray_indices, t_starts, t_ends = estimator.sampling(chunk_rays.origins, chunk_rays.viewdirs, sigma_fn=sigma_fn,
                                                            near_plane=near_plane, far_plane=far_plane,
                                                            render_step_size=render_step_size,
                                                            stratified=radiance_field.training, cone_angle=cone_angle,
-                                                           alpha_thre=alpha_thre)
+                                                           alpha_thre=alpha_thre, premarched=ahead)
         rgb, opacity, depth, extras = rendering(t_starts, t_ends, ray_indices, n_rays=chunk_rays.origins.shape[0],
                                                 rgb_sigma_fn=rgb_sigma_fn, render_bkgd=render_bkgd)
         results.append([rgb, opacity, depth, len(t_starts)])

@@ -49,6 +49,7 @@ class TrainStep:
         self.reducer = GradAllReducer(field_rest + ctx, bucket_bytes=bucket_bytes)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.step_id = 0
+        self._premarch = None
 
     # ---- what the exchange moves (for the bench line / DESIGN.md)
     def comm_bytes_per_step(self) -> int:
@@ -81,7 +82,9 @@ class TrainStep:
         if getattr(self, "_vote_stream", None) is None:
             self._vote_stream = torch.cuda.Stream(device)
             self._vote_host = torch.zeros(1, dtype=torch.int64).pin_memory()
-        flag = torch.tensor([n_samples], dtype=torch.int64).pin_memory().to(device, non_blocking=True)
+            self._vote_in = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self._vote_in[0] = n_samples            # (the copy of the previous step left this buffer long ago: its result was read)
+        flag = self._vote_in.to(device, non_blocking=True)
         self._vote_stream.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(self._vote_stream):
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
@@ -97,8 +100,32 @@ class TrainStep:
         vote.synchronize()
         return int(self._vote_host[0]) > 0
 
-    def __call__(self, rays: Rays, pixels: torch.Tensor, render_bkgd: Optional[torch.Tensor] = None, refresh_occupancy: bool = True):
-        """returns (loss value tensor, number of rendered samples on this rank)"""
+    def _march_ahead(self, next_rays, n_samples: int, refresh_occupancy: bool) -> None:
+        """issue the occupancy march of the NEXT batch on a side stream (nerfacc.Premarch): it depends on the rays and the
+        grid only, so it runs beside this step's forward / backward instead of in front of the next step.  Not before a step
+        that refreshes the grid, and not with a rate term (its random entry sample would be drawn after the next batch's
+        jitter instead of before): in both cases the next step marches in line, and the order of random draws -- hence every
+        sample -- stays what it is without the look-ahead."""
+        if next_rays is None or (self.cm is not None and self.lmbda > 0):
+            return
+        if refresh_occupancy and (self.step_id + 1) % self.occ_every == 0:
+            return
+        if callable(next_rays):
+            next_rays = next_rays(n_samples)
+        if next_rays is None or not next_rays.origins.is_cuda:
+            return
+        if self._premarch is None:
+            from .nerfacc import Premarch
+
+            self._premarch = Premarch(next_rays.origins.device)
+        o, d = next_rays.origins, next_rays.viewdirs
+        self._premarch.issue(self.estimator, o.reshape(-1, 3), d.reshape(-1, 3), render_step_size=self.render_step_size, stratified=True)
+
+    def __call__(self, rays: Rays, pixels: torch.Tensor, render_bkgd: Optional[torch.Tensor] = None, refresh_occupancy: bool = True,
+                 next_rays=None):
+        """returns (loss value tensor, number of rendered samples on this rank).  `next_rays` (optional): the batch of the
+        NEXT call, or a function `n_samples -> Rays` that draws it once this step's sample count is known (the reference sizes
+        the next batch from it, train...:340-344); its occupancy march then overlaps this step (see `_march_ahead`)."""
         self.field.train()
         self.estimator.train()
         if refresh_occupancy:   # train...:314-321
@@ -108,7 +135,10 @@ class TrainStep:
                 # each rank drew its own random cell samples: rank 0's grid is everybody's grid
                 broadcast_module_buffers(self.estimator, ["occs", "binaries"], src=0)
         rgb, acc, depth, n_samples = render_image_with_occgrid(self.field, self.estimator, rays, render_step_size=self.render_step_size,
-                                                               render_bkgd=render_bkgd)
+                                                               render_bkgd=render_bkgd, premarch=self._premarch)
+        if self._premarch is not None:
+            self._premarch.drop()                 # (a march issued for other rays / another grid is not kept)
+        self._march_ahead(next_rays, n_samples, refresh_occupancy)
         # train...:337-338: a batch without samples skips the step.  Under data parallelism all ranks decide together; the
         # vote travels while this rank goes on (a rank without samples contributes zero gradients to the collectives, which
         # every rank issues in the same order either way) and is read just before the update is applied.

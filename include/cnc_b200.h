@@ -363,13 +363,14 @@ int cnc_field_fwd_host(const float *pos_host, const float *dirs_host, const floa
                        cnc_stream_t s_compute, cnc_stream_t s_in, cnc_stream_t s_out);
 /* Training forward: the same kernel, additionally leaving what the backward pass of ngp.py:514-566 needs in HBM as
  * the values go by (no recomputation, no extra pass): x0 [N,256] = input of Linear(255,160) (192 grid features |
- * x, sin/cos | a constant 1 in the pad column), h1 / h3 / h4 [N,160] = the ReLU outputs, geo80 [N,80] = the 79 geo features
- * in columns 1..79 (column 0 is scratch); all 32-byte aligned (the rows leave as 256-bit stores), all required. */
+ * x, sin/cos | a constant 1 in the pad column), h1 / h3 / h4 [N,160] = the ReLU outputs, head_in [N,96] = the input of the
+ * first head layer in the kernel's column order (SH band 0 | 79 geo features | SH bands 1..15 | 0: the rows of that layer's
+ * weight gradient come out in the same order); all 32-byte aligned (the rows leave as 256-bit stores), all required. */
 int cnc_field_fwd_train(const float *pos, const float *dirs, const float *aabb6_host,
                         const uint8_t *bits_xyz, const uint8_t *bits_xy, const uint8_t *bits_xz,
                         const uint8_t *bits_yz, const int32_t *offsets3, const int32_t *resolutions3,
                         const int32_t *offsets2, const int32_t *resolutions2, const float *blob,
-                        float *sigma, float *rgb, float *geo80, float *x0, float *h1, float *h3, float *h4,
+                        float *sigma, float *rgb, float *head_in, float *x0, float *h1, float *h3, float *h4,
                         uint32_t N, cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -27,13 +27,14 @@ rays = Rays(o.to(dev), d.to(dev)); pixels = torch.rand(n_rays, 3, generator=g).t
 ts = TrainStep(field, est, lr=1e-4, exchange=os.environ.get("CNC_EXCHANGE", "auto"))
 if rank == 0:
     print("exchange:", ts.comm_description())
+AHEAD = (lambda n: rays) if os.environ.get("AHEAD", "1") == "1" else None
 for _ in range(3):
-    _, n_s = ts(rays, pixels, refresh_occupancy=False)
+    _, n_s = ts(rays, pixels, refresh_occupancy=False, next_rays=AHEAD)
 torch.cuda.synchronize()
 import time
 t = time.perf_counter()
 for _ in range(5):
-    ts(rays, pixels, refresh_occupancy=False)
+    ts(rays, pixels, refresh_occupancy=False, next_rays=AHEAD)
 torch.cuda.synchronize()
 if rank == 0:
     print(f"samples {n_s}; wall {1e3 * (time.perf_counter() - t) / 5:.2f} ms/step; world {world}")
@@ -43,7 +44,7 @@ if os.environ.get("PROFILE", "1") == "0":
     sys.exit(0)
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3):
-        ts(rays, pixels, refresh_occupancy=False)
+        ts(rays, pixels, refresh_occupancy=False, next_rays=AHEAD)
     torch.cuda.synchronize()
 if rank == 0 and os.environ.get("TRACE"):
     prof.export_chrome_trace(os.environ["TRACE"])

@@ -175,3 +175,47 @@ def test_train_step_with_rate_term(cuda):
         assert torch.isfinite(loss) and n > 0
     assert not torch.equal(cm.context_model_3D[0].weight.detach(), w0)      # the context model trains with the field
     assert all(torch.isfinite(p).all() for p in field.parameters())
+
+
+def test_march_ahead_gives_the_same_samples_and_the_same_training(cuda):
+    """nerfacc.Premarch (the occupancy march of the next batch on a side stream) hands `sampling` exactly what the in-line
+    march produces -- same jitter draw, same kernels -- also when the batch outgrows its buffer; TrainStep(next_rays=...)
+    uses it on every step that does not refresh the grid and trains like the plain loop."""
+    from cnc_b200.nerfacc import Premarch
+    from cnc_b200.trainer import TrainStep
+
+    field, est, rays, pixels = _scene(cuda, n_rays=500)
+    field.train()
+    sigma_fn = lambda t0, t1, ri: field.query_density(rays.origins[ri] + rays.viewdirs[ri] * ((t0 + t1) / 2)[:, None]).squeeze(-1)
+    for cap in (1 << 20, 1000):                      # the second one is outgrown at once
+        torch.manual_seed(11)
+        want = est.sampling(rays.origins, rays.viewdirs, sigma_fn=sigma_fn, render_step_size=5e-3, stratified=True)
+        torch.manual_seed(11)
+        pm = Premarch(cuda, capacity=cap)
+        pm.issue(est, rays.origins, rays.viewdirs, render_step_size=5e-3, stratified=True)
+        assert pm.matches(est, rays.origins, rays.viewdirs, 0.0, 1e10, 5e-3, True, 0.0)
+        assert not pm.matches(est, rays.origins, rays.viewdirs, 0.0, 1e10, 1e-2, True, 0.0)
+        got = est.sampling(rays.origins, rays.viewdirs, sigma_fn=sigma_fn, render_step_size=5e-3, stratified=True, premarched=pm)
+        assert want[0].numel() > 10000
+        for a, b in zip(want, got):
+            assert torch.equal(a, b)
+        assert pm.pending is None and pm.taken == 1
+    # the training loop with the look-ahead: used on the steps between grid refreshes, and the loss falls the same way
+    curves = []
+    for ahead in (False, True):
+        field, est, rays, pixels = _scene(cuda, n_rays=500)
+        torch.manual_seed(3)
+        ts = TrainStep(field, est, lr=2e-3, occ_refresh_every=4)
+        ts.step_id = 1024       # past the estimator's warm-up: a refresh touches a random quarter of the cells
+        losses = []
+        for _ in range(24):
+            loss, n = ts(rays, pixels, render_bkgd=torch.zeros(3, device=cuda), refresh_occupancy=True,
+                         next_rays=(lambda n_samples: rays) if ahead else None)
+            losses.append(float(loss))
+        if ahead:
+            assert ts._premarch.taken == 18      # every step but the first and the five that follow a refresh decision
+        curves.append(losses)
+    assert np.isfinite(curves[1]).all()
+    np.testing.assert_allclose(curves[1][0], curves[0][0], rtol=1e-4)            # same first step
+    assert np.mean(curves[1][-4:]) < 0.9 * curves[1][0]
+    np.testing.assert_allclose(np.mean(curves[1][-4:]), np.mean(curves[0][-4:]), rtol=0.2)
