@@ -333,6 +333,7 @@ class _RenderAll(torch.autograd.Function):
                                             ptr(colors), ptr(opac), ptr(depth), stream()))
         ctx.save_for_backward(t0, t1, T, al, w, c, packed_info, ray_indices)
         ctx.mark_non_differentiable(T, al)
+        ctx.set_materialize_grads(False)     # outputs nobody differentiates arrive as None, not as zero-filled tensors
         return w, T, al, colors, opac, depth
 
     @staticmethod
@@ -340,6 +341,8 @@ class _RenderAll(torch.autograd.Function):
         t0, t1, T, al, w, c, packed_info, ri = ctx.saved_tensors
         f = lambda g: None if g is None else g.contiguous().float()
         gw, gC, gO, gD = f(gw), f(gC), f(gO), f(gD)
+        if gw is None and gC is None and gO is None and gD is None:
+            return None, None, None, None, None, None
         g_sigma, g_rgb = torch.empty_like(T), torch.empty_like(c)
         check(lib().cnc_render_bwd(ptr(t0), ptr(t1), ptr(T), ptr(al), ptr(w), ptr(c), ptr(packed_info), packed_info.shape[0],
                                    ptr(gC), ptr(gO), ptr(gD), ptr(gw), ptr(g_sigma), ptr(g_rgb), stream()))
@@ -478,11 +481,15 @@ class Premarch:
 
     @torch.no_grad()
     def issue(self, est: "OccGridEstimator", rays_o: Tensor, rays_d: Tensor, near_plane: float = 0.0, far_plane: float = 1e10,
-              t_min=None, t_max=None, render_step_size: float = 1e-3, stratified: bool = False, cone_angle: float = 0.0) -> None:
-        """start the march of (rays_o, rays_d) against the estimator's CURRENT grid; everything queued on the current
-        stream so far (e.g. an occupancy refresh) is ordered before it"""
-        entry = torch.cuda.Event()
-        entry.record()
+              t_min=None, t_max=None, render_step_size: float = 1e-3, stratified: bool = False, cone_angle: float = 0.0,
+              after: Optional[torch.cuda.Event] = None) -> None:
+        """start the march of (rays_o, rays_d) against the estimator's CURRENT grid.  It is ordered behind `after` (an event
+        the caller recorded once the rays and the grid were final) or, without one, behind everything queued on the current
+        stream so far."""
+        entry = after
+        if entry is None:
+            entry = torch.cuda.Event()
+            entry.record()
         o, d = rays_o.contiguous().float(), rays_d.contiguous().float()
         n, dev = o.shape[0], o.device
         k = self.turn

@@ -100,26 +100,36 @@ class TrainStep:
         vote.synchronize()
         return int(self._vote_host[0]) > 0
 
-    def _march_ahead(self, next_rays, n_samples: int, refresh_occupancy: bool) -> None:
-        """issue the occupancy march of the NEXT batch on a side stream (nerfacc.Premarch): it depends on the rays and the
-        grid only, so it runs beside this step's forward / backward instead of in front of the next step.  Not before a step
-        that refreshes the grid, and not with a rate term (its random entry sample would be drawn after the next batch's
-        jitter instead of before): in both cases the next step marches in line, and the order of random draws -- hence every
-        sample -- stays what it is without the look-ahead."""
+    def _pick_next(self, next_rays, n_samples: int, refresh_occupancy: bool):
+        """the batch whose occupancy march may run ahead (nerfacc.Premarch), and the point of the stream from which it may.
+        Not before a step that refreshes the grid, and not with a rate term (its random entry sample would be drawn after
+        the next batch's jitter instead of before): in both cases the next step marches in line, and the order of random
+        draws -- hence every sample -- stays what it is without the look-ahead."""
         if next_rays is None or (self.cm is not None and self.lmbda > 0):
-            return
+            return None
         if refresh_occupancy and (self.step_id + 1) % self.occ_every == 0:
-            return
+            return None
         if callable(next_rays):
             next_rays = next_rays(n_samples)
         if next_rays is None or not next_rays.origins.is_cuda:
+            return None
+        ready = torch.cuda.Event()
+        ready.record()
+        return next_rays, ready
+
+    def _march_ahead(self, picked) -> None:
+        """issue the march of the next batch on the side stream.  Called once this step's backward and update are queued: the
+        host is then far ahead of the device, and the march (which depends on the rays and the grid only) runs beside the
+        weight-gradient and optimizer kernels instead of in front of the next step."""
+        if picked is None:
             return
+        next_rays, ready = picked
         if self._premarch is None:
             from .nerfacc import Premarch
 
             self._premarch = Premarch(next_rays.origins.device)
-        o, d = next_rays.origins, next_rays.viewdirs
-        self._premarch.issue(self.estimator, o.reshape(-1, 3), d.reshape(-1, 3), render_step_size=self.render_step_size, stratified=True)
+        self._premarch.issue(self.estimator, next_rays.origins.reshape(-1, 3), next_rays.viewdirs.reshape(-1, 3),
+                             render_step_size=self.render_step_size, stratified=True, after=ready)
 
     def __call__(self, rays: Rays, pixels: torch.Tensor, render_bkgd: Optional[torch.Tensor] = None, refresh_occupancy: bool = True,
                  next_rays=None):
@@ -138,12 +148,13 @@ class TrainStep:
                                                                render_bkgd=render_bkgd, premarch=self._premarch)
         if self._premarch is not None:
             self._premarch.drop()                 # (a march issued for other rays / another grid is not kept)
-        self._march_ahead(next_rays, n_samples, refresh_occupancy)
+        picked = self._pick_next(next_rays, n_samples, refresh_occupancy)
         # train...:337-338: a batch without samples skips the step.  Under data parallelism all ranks decide together; the
         # vote travels while this rank goes on (a rank without samples contributes zero gradients to the collectives, which
         # every rank issues in the same order either way) and is read just before the update is applied.
         vote = self._vote_async(n_samples, pixels.device)
         if self.world == 1 and n_samples == 0:
+            self._march_ahead(picked)
             self.step_id += 1
             return torch.zeros((), device=pixels.device), n_samples
         loss = F.mse_loss(rgb, pixels)   # train...:346
@@ -181,6 +192,7 @@ class TrainStep:
         elif exchanged is not None:
             for w in exchanged[0]:
                 w.wait()
+        self._march_ahead(picked)
         self.step_id += 1
         return loss.detach(), n_samples
 
