@@ -478,6 +478,9 @@ def codec_bench(arm, cpu_seconds=12.0, rank=0, world=1, dist=None):
     return res
 
 
+SAMPLES_PER_RANK = 380625     # what the 1100 rays of the single-GPU batch (seed 7) produce on the ball scene
+
+
 def train_bench(arm, rank, world, steps, field):
     """forward + backward + (N > 1: NCCL exchange of the gradients) + Adam on a synthetic ray batch per rank:
     rays from a radius-4 sphere towards the origin, ball occupancy, random target pixels.
@@ -485,14 +488,15 @@ def train_bench(arm, rank, world, steps, field):
     dev, ours = arm.dev, arm.impl == "ours"
     est = arm.estimator()
     g = torch.Generator(device="cpu").manual_seed(7 + rank)
-    n_rays = 1100
-    o = torch.randn(n_rays, 3, generator=g)
+    n_rays, pool = 1100, 1400
+    o = torch.randn(pool, 3, generator=g)
     o = o / o.norm(dim=-1, keepdim=True) * 4
-    tgt = (torch.rand(n_rays, 3, generator=g) - 0.5) * 1.2
+    tgt = (torch.rand(pool, 3, generator=g) - 0.5) * 1.2
     d = tgt - o
     d = d / d.norm(dim=-1, keepdim=True)
-    rays = arm.Rays(o.to(dev), d.to(dev))
-    pixels = torch.rand(n_rays, 3, generator=g).to(dev)
+    o_all, d_all, px_all = o.to(dev), d.to(dev), torch.rand(pool, 3, generator=g).to(dev)
+    rays = arm.Rays(o_all[:n_rays].contiguous(), d_all[:n_rays].contiguous())
+    pixels = px_all[:n_rays].contiguous()
     bk = torch.ones(3, device=dev)
     if ours:
         from cnc_b200.trainer import TrainStep
@@ -505,8 +509,14 @@ def train_bench(arm, rank, world, steps, field):
         ts = RefTrainStep(arm, field, est, lr=1e-4)
         call = lambda t: t(rays, pixels, refresh_occupancy=False)
     n_s = 0
-    for _ in range(3):
+    for i in range(4 if world > 1 else 3):
         _, n_s = call(ts)
+        if i == 0 and world > 1 and ours:
+            # every rank sizes its batch to the sample budget of the single-GPU run, as the training loop sizes each batch from
+            # the previous one's sample count (train...:340-344): ranks march different rays, equal work needs unequal ray counts
+            n_rays = max(64, min(pool, int(round(n_rays * SAMPLES_PER_RANK / max(int(n_s), 1)))))
+            rays = arm.Rays(o_all[:n_rays].contiguous(), d_all[:n_rays].contiguous())
+            pixels = px_all[:n_rays].contiguous()
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()

@@ -85,6 +85,7 @@ SIGNATURES = {
     "cnc_peer_import": [_vp, _vp],
     "cnc_peer_unmap": [_vp],
     "cnc_peer_barrier": [_vp, _i32, _i32, _i32, _u32, _u32, _vp],
+    "cnc_peer_min": [_vp, _i32, _i32, _i32, _u32, _u32, _vp, _u32, _vp],
     "cnc_peer_reduce": [_vp, _i32, _i64, _i64, _f32, _vp, _i32, _vp],
     "cnc_peer_push": [_vp, _i32, _i32, _vp, _vp, _i32, _vp],
 }

@@ -65,6 +65,38 @@ __global__ void barrier_kernel(Pads pads, int rank, int world, int slot, uint32_
     }
 }
 
+// every rank contributes one number and learns the minimum over the ranks (the skip vote of the training step: the sample
+// count of the rank's batch).  value words by epoch parity (a rank can be at most one vote ahead of another), epoch words
+// released after them.
+__global__ void min_kernel(Pads pads, int rank, int world, int slot, uint32_t epoch, uint32_t value, uint32_t *out,
+                           uint64_t timeout_ns) {
+    const int k = threadIdx.x;
+    uint32_t v = 0xFFFFFFFFu;
+    if (k < world) {
+        const int vslot = slot + 1 + (int)(epoch & 1u);
+        *reinterpret_cast<volatile uint32_t *>(pads.p[k] + vslot * MAX_WORLD + rank) = value;
+        __threadfence_system();
+        st_release_sys(pads.p[k] + slot * MAX_WORLD + rank, epoch);
+        const uint32_t *mine = pads.p[rank] + slot * MAX_WORLD + k;
+        const uint64_t t0 = globaltimer_ns();
+        while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+            __nanosleep(64);
+            if (globaltimer_ns() - t0 > timeout_ns) {
+                printf("cnc_peer_min: rank %d waited %llu ms for rank %d (epoch %u): giving up\n", rank,
+                       (unsigned long long)(timeout_ns / 1000000ull), k, epoch);
+                __trap();
+            }
+        }
+        v = *reinterpret_cast<volatile uint32_t *>(pads.p[rank] + vslot * MAX_WORLD + k);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, v, d);
+        v = o < v ? o : v;
+    }
+    if (k == 0) *out = v;
+}
+
 template <int W>
 __global__ void __launch_bounds__(512) reduce_kernel(Srcs src, int64_t lo, int64_t n4, float scale, float4 *__restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -162,6 +194,21 @@ int cnc_peer_barrier(void *const *pads, int32_t rank, int32_t world, int32_t slo
     }
     peer::barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(a, rank, world, slot, epoch, (uint64_t)timeout_ms * 1000000ull);
     return check_launch("peer_barrier");
+}
+
+int cnc_peer_min(void *const *pads, int32_t rank, int32_t world, int32_t slot, uint32_t epoch, uint32_t value, uint32_t *out,
+                 uint32_t timeout_ms, cnc_stream_t stream) {
+    if (!pads || !out || world < 1 || world > peer::MAX_WORLD || rank < 0 || rank >= world || slot < 0 || slot + 2 >= peer::PAD_SLOTS) {
+        set_error("peer_min: bad argument (uses slots slot .. slot + 2)");
+        return CNC_EINVAL;
+    }
+    peer::Pads a{};
+    for (int k = 0; k < world; k++) {
+        if (!pads[k]) { set_error("peer_min: null pad"); return CNC_EINVAL; }
+        a.p[k] = static_cast<uint32_t *>(pads[k]);
+    }
+    peer::min_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(a, rank, world, slot, epoch, value, out, (uint64_t)timeout_ms * 1000000ull);
+    return check_launch("peer_min");
 }
 
 int cnc_peer_reduce(const void *const *srcs, int32_t world, int64_t lo, int64_t count, float scale, float *out, int32_t blocks,

@@ -46,6 +46,7 @@ class GradAllReducer:
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20, group=None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
+        self.peer = None
         self.buckets: List[List[int]] = []
         cur, cur_bytes = [], 0
         for i, p in enumerate(self.params):
@@ -64,10 +65,56 @@ class GradAllReducer:
     def bytes_per_step(self) -> int:
         return sum(p.numel() * p.element_size() for p in self.params)
 
+    def use_peer_memory(self, signals, slot: int, control_group=None) -> None:
+        """average over NVLink peer memory instead of NCCL (csrc/peer.cu): the gradients are packed into a buffer every rank
+        maps, the ranks meet at `signals.barrier(slot)`, and each rank sums all N buffers itself (rank order: every rank gets
+        the same bits).  For the small parameters (MLPs, context models: < 1 MB) the cost of an all-reduce is its latency;
+        this one has no ring and no spinning NCCL kernel beside the weight-gradient GEMMs.  Collective call."""
+        from . import peer as P
+
+        n = sum(p.numel() for p in self.params)
+        n = (n + 3) // 4 * 4
+        dev = self.params[0].device
+        mem = P.PeerMemory(2 * 4 * n, group=self.group, device=dev, control_group=control_group)   # two copies: see reduce()
+        self.peer = {"P": P, "sig": signals, "slot": slot, "mem": mem, "n": n, "turn": 0,
+                     "mine": [mem.tensor(4 * n * k, n) for k in (0, 1)], "src": [mem.pointer_array(4 * n * k) for k in (0, 1)],
+                     "out": torch.empty(n, device=dev)}
+        off, views = 0, [[], []]
+        for p in self.params:
+            for k in (0, 1):
+                views[k].append(self.peer["mine"][k][off:off + p.numel()].view_as(p))
+            off += p.numel()
+        self.peer["views"] = views
+        self.peer["out_views"] = []
+        off = 0
+        for p in self.params:
+            self.peer["out_views"].append(self.peer["out"][off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    @torch.no_grad()
+    def _reduce_peer(self) -> None:
+        pr = self.peer
+        k = pr["turn"]
+        pr["turn"] ^= 1        # (a rank that skips its update may be a whole step ahead of the slowest reader of this buffer)
+        world = dist.get_world_size(self.group)
+        have = [p.grad is not None for p in self.params]
+        if not all(have):
+            pr["mine"][k].zero_()
+        if any(have):
+            torch._foreach_copy_([v for v, h in zip(pr["views"][k], have) if h], [p.grad for p, h in zip(self.params, have) if h])
+        pr["sig"].barrier(pr["slot"])
+        pr["P"].reduce_rows(pr["src"][k], world, 0, pr["n"], 1.0 / world, pr["out"])
+        for p, h in zip(self.params, have):
+            if not h:
+                p.grad = torch.empty_like(p)
+        torch._foreach_copy_([p.grad for p in self.params], pr["out_views"])
+
     @torch.no_grad()
     def reduce(self) -> None:
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return
+        if self.peer is not None:
+            return self._reduce_peer()
         world = dist.get_world_size(self.group)
         pending = []
         for b in self.buckets:

@@ -113,6 +113,15 @@ class PeerSignals:
         check(lib().cnc_peer_barrier(m.pointer_array(), m.rank, m.world, slot, e & 0xFFFFFFFF, self.timeout_ms, stream()))
 
 
+    def minimum(self, slot: int, value: int, out: torch.Tensor) -> None:
+        """out[0] (uint32 / int32 device word) = min over the ranks of `value` (0 <= value < 2^32); uses pad slots slot..slot+2"""
+        e = self.epochs.get(slot, 0) + 1
+        self.epochs[slot] = e
+        m = self.mem
+        check(lib().cnc_peer_min(m.pointer_array(), m.rank, m.world, slot, e & 0xFFFFFFFF, min(int(value), 0xFFFFFFFF), out.data_ptr(),
+                                 self.timeout_ms, stream()))
+
+
 def reduce_rows(srcs, world: int, lo: int, count: int, scale: float, out: torch.Tensor, blocks: int = 0) -> None:
     """out[:count] = scale * sum over the ranks of their buffer[lo : lo + count] (fp32, rank order); `srcs` = pointer array"""
     assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() >= count

@@ -50,6 +50,11 @@ class TrainStep:
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.step_id = 0
         self._premarch = None
+        # the tables' exchange runs over NVLink peer memory: so do the small gradients and the skip vote -- no NCCL kernel
+        # (a spinning all-reduce holds SM slots beside the persistent GEMM kernels of backward) is left in the step
+        self._peer_sig = self.table_opt.peer["sig"] if (self.table_opt is not None and self.table_opt.peer is not None) else None
+        if self._peer_sig is not None and self.reducer.params:
+            self.reducer.use_peer_memory(self._peer_sig, slot=4)
 
     # ---- what the exchange moves (for the bench line / DESIGN.md)
     def comm_bytes_per_step(self) -> int:
@@ -64,8 +69,9 @@ class TrainStep:
         if self.table_opt.peer is not None:
             return ("latent tables over NVLink peer memory: device-side barrier, every rank loads and averages its 1/N of the rows "
                     "from all N gradient buffers (cnc_peer_reduce), Adam on them, stores its words of the sign and STE-window bit "
-                    "planes into every peer (cnc_peer_push); MLP / context-model gradients: one bucketed NCCL all-reduce; sample "
-                    "count: 8-byte NCCL all-reduce")
+                    "planes into every peer (cnc_peer_push); MLP / context-model gradients: packed into a mapped buffer, summed by every "
+                    "rank from all N (cnc_peer_reduce); skip vote: minimum of the sample counts through the signal pads (cnc_peer_min); "
+                    "no NCCL kernel in the step")
         return ("latent tables: reduce-scatter(avg) of the gradient by rows, Adam on the owned 1/N, all-gather of the sign and "
                 "STE-window bit planes; MLP / context-model gradients: one bucketed all-reduce; sample count: 8-byte all-reduce")
 
@@ -83,6 +89,15 @@ class TrainStep:
             self._vote_stream = torch.cuda.Stream(device)
             self._vote_host = torch.zeros(1, dtype=torch.int64).pin_memory()
             self._vote_in = torch.zeros(1, dtype=torch.int64).pin_memory()
+            self._vote_dev = torch.zeros(2, dtype=torch.int32, device=device)       # (one int64 for the copy below)
+        if self._peer_sig is not None:
+            # one warp: the count goes into every rank's signal pad, the minimum comes out of the own one
+            with torch.cuda.stream(self._vote_stream):
+                self._peer_sig.minimum(10, n_samples, self._vote_dev)
+                self._vote_host.copy_(self._vote_dev.view(torch.int64), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._vote_stream)
+            return ev
         self._vote_in[0] = n_samples            # (the copy of the previous step left this buffer long ago: its result was read)
         flag = self._vote_in.to(device, non_blocking=True)
         self._vote_stream.wait_stream(torch.cuda.current_stream(device))

@@ -207,6 +207,8 @@ int cnc_adam_planes(float *params, const float *grad, float *exp_avg, float *exp
  *                                 (pads[k] = rank k's pad as mapped here, cnc_peer_pad_bytes() bytes, zero at start) and waits
  *                                 until its own pad holds >= epoch from everybody; epochs of a slot must increase.  A wait
  *                                 longer than timeout_ms traps the kernel (the next CUDA call reports it).
+ *   cnc_peer_min                : every rank contributes `value` and receives the minimum over the ranks in *out (device
+ *                                 word); same meeting discipline as the barrier, on pad slots slot .. slot + 2
  *   cnc_peer_reduce             : out[i] = scale * sum_{k < world} srcs[k][lo + i], i < count, summed in rank order (lo,
  *                                 count multiples of 4); `blocks` caps the grid (0 = one CTA per SM)
  *   cnc_peer_push               : words [off, off + words) of rank `rank`'s arena are stored at the same offsets of every
@@ -221,6 +223,8 @@ int cnc_peer_import(const uint8_t *handle, void **out);
 int cnc_peer_unmap(void *p);
 int cnc_peer_barrier(void *const *pads, int32_t rank, int32_t world, int32_t slot, uint32_t epoch, uint32_t timeout_ms,
                      cnc_stream_t stream);
+int cnc_peer_min(void *const *pads, int32_t rank, int32_t world, int32_t slot, uint32_t epoch, uint32_t value, uint32_t *out,
+                 uint32_t timeout_ms, cnc_stream_t stream);
 int cnc_peer_reduce(const void *const *srcs, int32_t world, int64_t lo, int64_t count, float scale, float *out, int32_t blocks,
                     cnc_stream_t stream);
 int cnc_peer_push(void *const *arenas, int32_t rank, int32_t world, const int64_t *seg_off_words, const int64_t *seg_words,

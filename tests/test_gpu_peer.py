@@ -67,11 +67,35 @@ def _primitives_worker(rank, world, port, q):
     sig.barrier(1)
     P.push_words(arena, [(rank * 100, 100), (5000 + 7 * rank, 7)])
     sig.barrier(1)
+    # minimum over the ranks of one number each (the skip vote), twice in a row (value words alternate by epoch parity)
+    mins = torch.zeros(2, dtype=torch.int32, device=dev)
+    got_min = []
+    for step, value in enumerate((100 + 7 * rank, 0 if rank == 1 else 5)):
+        sig.minimum(10, value, mins)
+        got_min.append(int(mins.view(torch.int64)[0]))
+    # bucketed gradient average through a mapped buffer (dp.GradAllReducer.use_peer_memory), twice, second time with a
+    # parameter that has no gradient on rank 1
+    from cnc_b200.dp import GradAllReducer
+
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(33, 7, device=dev)), torch.nn.Parameter(torch.zeros(5, device=dev)),
+              torch.nn.Parameter(torch.zeros(160, 160, device=dev))]
+    red = GradAllReducer(params)
+    red.use_peer_memory(sig, slot=4)
+    avg = []
+    for step in range(2):
+        for i, p in enumerate(params):
+            p.grad = torch.randn(p.shape, generator=torch.Generator().manual_seed(1000 * step + 10 * i + rank)).to(dev)
+        if step == 1 and rank == 1:
+            params[1].grad = None
+        red.reduce()
+        avg.append([p.grad.cpu().numpy().copy() for p in params])
     torch.cuda.synchronize()
-    q.put((rank, out.cpu().numpy().copy(), tail.cpu().numpy().copy(), words.cpu().numpy().copy()))
+    q.put((rank, out.cpu().numpy().copy(), tail.cpu().numpy().copy(), words.cpu().numpy().copy(), got_min, avg))
     dist.barrier()
     del mine, words
-    for m in (arena, mem, sig.mem):
+    del red, params
+    for m in (arena, mem):
         m.close()
     dist.destroy_process_group()
 
@@ -101,7 +125,14 @@ def test_peer_barrier_reduce_push_world2():
     n, S = 4096 * 8 + 64, 4096 * 4
     vals = [torch.randn(n, generator=torch.Generator().manual_seed(40 + r)) for r in range(world)]
     want = (vals[0] + vals[1]) * 0.5                 # rank order, then the scale: what the kernel does
-    for rank, got, tail, words in out:
+    for rank, got, tail, words, got_min, avg in out:
+        assert got_min == [100, 0]
+        for step in range(2):
+            for i, a in enumerate(avg[step]):
+                gs = [torch.randn(a.shape, generator=torch.Generator().manual_seed(1000 * step + 10 * i + r)) for r in range(world)]
+                if step == 1 and i == 1:
+                    gs[1] = torch.zeros_like(gs[1])
+                assert torch.equal(torch.from_numpy(a), (gs[0] + gs[1]) * 0.5)
         assert torch.equal(torch.from_numpy(got), want[rank * S:(rank + 1) * S])
         assert torch.equal(torch.from_numpy(tail), want[2 * S:2 * S + 64])
         w = torch.from_numpy(words)
