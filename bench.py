@@ -560,6 +560,24 @@ def train_bench(arm, rank, world, steps, field):
         out["no_lookahead_ms"] = float(t[0]) / steps
         out["lookahead"] = "occupancy march of the next batch issued on a side stream during this step (same samples)"
     if ours and world > 1:
+        # the same step without data parallelism (every rank its own replica, no exchange), same run, same rays: the
+        # scaling efficiency of the step that has the collective, from one launch
+        field1 = arm.field(seed=0)
+        ts1 = TrainStep(field1, arm.estimator(), lr=1e-4, data_parallel=False)
+        for _ in range(3):
+            call(ts1)
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        e0.record()
+        for _ in range(steps):
+            call(ts1)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        out["replicas_without_exchange_ms"] = float(t[0]) / steps
+        out["efficiency_vs_replicas"] = out["replicas_without_exchange_ms"] / out["ms_per_step"]
+        del ts1, field1
         out["comm"] = ts.comm_description()
         if ts.table_opt is not None and ts.table_opt.peer is not None:
             out["nvlink_bytes_per_step"] = ts.table_opt.link_bytes_per_step()
@@ -921,6 +939,11 @@ def main():
         line["fwd_bwd"] = fwd_bwd
     if train is not None:
         line["train_step"] = train
+        # the step that HAS an exchange, next to the collective-free forward that `value` is (configs[3] of BASELINE.json)
+        line["scaling_with_exchange"] = {"metric": "training-step ray-samples/s over all ranks", "value": train.get("samples_per_s"),
+                                         "ms_per_step": train.get("ms_per_step"), "scaling": "weak",
+                                         "efficiency_vs_replicas_same_run": train.get("efficiency_vs_replicas"),
+                                         "comm_bytes_per_step": train.get("comm_bytes_per_step")}
     if codec is not None:
         line["codec"] = codec
     print(json.dumps(line))

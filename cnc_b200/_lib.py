@@ -78,6 +78,7 @@ SIGNATURES = {
     "cnc_ctx_mlp_bwd": [_vp, _vp, _vp, _vp, _vp, _u32, _i64, _vp],
     "cnc_render_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "cnc_sample_points": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "cnc_pack_ray_chunks": [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp],
     "cnc_compact_samples": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "cnc_peer_alloc": [_u64, _vp],
     "cnc_peer_free": [_vp],

@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(128) traverse_kernel(const MarchArgs a) {
                                                 const int64_t at = start + j - 31 + lane;
                                                 a.t_starts[at] = k0;
                                                 a.t_ends[at] = k1;
-                                                a.ray_idx[at] = tid;
+                                                if (a.ray_idx) a.ray_idx[at] = tid;
                                             }
                                         }
                                     }, t_last);
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(128) traverse_kernel(const MarchArgs a) {
             const int64_t at = start + (n_samples & ~(int64_t)31) + lane;
             a.t_starts[at] = k0;
             a.t_ends[at] = k1;
-            a.ray_idx[at] = tid;
+            if (a.ray_idx) a.ray_idx[at] = tid;
         }
         if (lane) return;
     } else {
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(128) traverse_kernel(const MarchArgs a) {
                                   if (fill) {
                                       a.t_starts[start + j] = t0;
                                       a.t_ends[start + j] = t1;
-                                      a.ray_idx[start + j] = tid;
+                                      if (a.ray_idx) a.ray_idx[start + j] = tid;
                                   }
                               }, t_last);
     }
@@ -373,6 +373,22 @@ sample_points_kernel(const float *__restrict__ rays_o, const float *__restrict__
         const float d = rays_d[r * 3 + k];
         pos[i * 3 + k] = __fadd_rn(rays_o[r * 3 + k], __fdiv_rn(__fmul_rn(d, h), 2.0f));
         if (dirs) dirs[i * 3 + k] = d;
+    }
+}
+
+// one walk instead of two: the march wrote ray r's samples at scratch[r * cap ..] and its count; this moves them to their
+// packed place (start_r = exclusive prefix sum of the counts) and writes the ray index.  One warp per ray, coalesced.
+__global__ void __launch_bounds__(128)
+pack_ray_chunks_kernel(const float *__restrict__ s0, const float *__restrict__ s1, int64_t cap, const int64_t *__restrict__ packed,
+                       int64_t n_rays, float *__restrict__ o0, float *__restrict__ o1, int64_t *__restrict__ oi) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (r >= n_rays) return;
+    const int64_t start = packed[r * 2], c = packed[r * 2 + 1];
+    for (int64_t j = lane; j < c; j += 32) {
+        o0[start + j] = s0[r * cap + j];
+        o1[start + j] = s1[r * cap + j];
+        oi[start + j] = r;
     }
 }
 
@@ -631,8 +647,8 @@ int cnc_traverse_grids(const float *rays_o, const float *rays_d, const uint8_t *
         set_error("traverse_grids: null pointer");
         return CNC_EINVAL;
     }
-    if ((t_starts != nullptr) != (chunk_starts != nullptr) || (t_starts && (!t_ends || !ray_indices)) || (!t_starts && !cnt)) {
-        set_error("traverse_grids: count pass needs cnt, fill pass needs chunk_starts + t_starts + t_ends + ray_indices");
+    if ((t_starts != nullptr) != (chunk_starts != nullptr) || (t_starts && !t_ends) || (!t_starts && !cnt)) {
+        set_error("traverse_grids: count pass needs cnt, fill pass needs chunk_starts + t_starts + t_ends (+ ray_indices)");
         return CNC_EINVAL;
     }
     mr::MarchArgs a{rays_o, rays_d, rays_mask, n_rays, n_grids, rx, ry, rz, binaries, aabbs, hits, t_sorted, t_indices,
@@ -715,6 +731,18 @@ int cnc_sample_points(const float *rays_o, const float *rays_d, const int64_t *r
     mr::sample_points_kernel<<<div_up((uint64_t)n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rays_o, rays_d, ray_indices, t_starts,
                                                                                                   t_ends, n, positions, dirs);
     return check_launch("sample_points");
+}
+
+int cnc_pack_ray_chunks(const float *scratch_t_starts, const float *scratch_t_ends, int64_t cap, const int64_t *packed_info,
+                        int64_t n_rays, float *t_starts, float *t_ends, int64_t *ray_indices, cnc_stream_t stream) {
+    if (n_rays == 0) return CNC_OK;
+    if (!scratch_t_starts || !scratch_t_ends || !packed_info || !t_starts || !t_ends || !ray_indices || cap <= 0) {
+        set_error("pack_ray_chunks: bad argument");
+        return CNC_EINVAL;
+    }
+    mr::pack_ray_chunks_kernel<<<div_up((uint64_t)n_rays * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        scratch_t_starts, scratch_t_ends, cap, packed_info, n_rays, t_starts, t_ends, ray_indices);
+    return check_launch("pack_ray_chunks");
 }
 
 int cnc_compact_samples(const uint8_t *keep, const int64_t *rank, int64_t n, const float *t_starts, const float *t_ends,

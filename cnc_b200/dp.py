@@ -178,7 +178,7 @@ class ShardedTableAdam:
         self.encoders = list(encoders)
         self.lr, self.betas, self.eps, self.weight_decay, self.group = lr, betas, eps, weight_decay, group
         self.ste_window = ste_window    # the table gradients arrive without the STE window mask: apply it in the Adam pass
-        on = dist.is_initialized()
+        on = dist.is_initialized() and group is not False         # group=False: this process alone, whatever is initialised
         self.world = dist.get_world_size(group) if on else 1
         self.rank = dist.get_rank(group) if on else 0
         self.step_id = 0

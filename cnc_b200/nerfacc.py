@@ -176,6 +176,20 @@ def ray_aabb_intersect(rays_o: Tensor, rays_d: Tensor, aabbs: Tensor, near_plane
 
 
 _INDEX01 = {}
+_SCRATCH = {}
+_CAPS = {}
+
+
+def _ray_capacity(aabbs: Tensor, step_size: float) -> int:
+    """upper bound of the samples one ray can produce: the diagonal of the largest box in steps (+ slack per level)"""
+    key = (aabbs.data_ptr(), aabbs._version, step_size)
+    c = _CAPS.get(key)
+    if c is None:
+        if len(_CAPS) > 16:
+            _CAPS.clear()
+        diag = float((aabbs[:, 3:] - aabbs[:, :3]).norm(dim=-1).max())
+        c = _CAPS[key] = int(diag / step_size) + 2 * aabbs.shape[0] + 16
+    return c
 
 
 def _index01(n: int, dev) -> Tensor:
@@ -234,17 +248,49 @@ def traverse_grids(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tens
                                    float(step_size), float(cone_angle), int(traverse_steps_limit), ptr(starts), ptr(c),
                                    ptr(t0), ptr(t1), ptr(ri), ptr(tm), stream()))
 
-    run(None, None, None, None, cnt, None)
-    starts = cnt.cumsum(0) - cnt
-    total = int(cnt.sum())                       # the one host sync of the reference too (data_spec.hpp:91)
-    t0 = torch.empty(total, device=dev)
-    t1 = torch.empty(total, device=dev)
-    ri = torch.empty(total, dtype=torch.int64, device=dev)
-    if total:
-        run(starts, t0, t1, ri, None, term)
+    cap = _ray_capacity(bb, float(step_size)) if (traverse_steps_limit <= 0 and step_size and step_size > 0) else 0
+    one_walk = 0 < cap and 0 < n <= 148 * 64 * 2 and n * cap <= (1 << 26)
+    if one_walk:
+        # ONE walk: every ray writes its samples into its own slice of a scratch buffer (cap = an upper bound of the samples
+        # of a ray: box diagonal / step) and its count; a copy kernel packs them.  The walk is the cost (a serial chain per
+        # ray), so this is half of count pass + fill pass.  A ray that fills its slice (cannot happen within the bound) sends
+        # the call down the two-pass road.
+        key = (str(dev), n, cap, stream())       # (per stream: the slices are live until the pack kernel has run)
+        sc = _SCRATCH.get(key)
+        if sc is None:
+            if len(_SCRATCH) > 4:
+                _SCRATCH.clear()
+            sc = _SCRATCH[key] = (torch.empty(n * cap, device=dev), torch.empty(n * cap, device=dev),
+                                  torch.arange(n, dtype=torch.int64, device=dev) * cap)
+        check(L.cnc_traverse_grids(ptr(o), ptr(d), ptr(rays_mask_u8), n, G, bins.shape[-3], bins.shape[-2], bins.shape[-1],
+                                   ptr(bins_u8), ptr(bb), ptr(hits_u8), ptr(ts), ptr(ti), ptr(nearp), ptr(farp),
+                                   float(step_size), float(cone_angle), cap, ptr(sc[2]), ptr(cnt), ptr(sc[0]), ptr(sc[1]), None,
+                                   ptr(term), stream()))
+        ends = cnt.cumsum(0)
+        starts = ends - cnt
+        total, most = torch.stack([ends[-1], cnt.max()]).tolist()      # the one host sync of the reference too (data_spec.hpp:91)
+        one_walk = most < cap
+    if one_walk:
+        t0 = torch.empty(total, device=dev)
+        t1 = torch.empty(total, device=dev)
+        ri = torch.empty(total, dtype=torch.int64, device=dev)
+        packed = torch.stack([starts, cnt], dim=-1)
+        if total:
+            check(L.cnc_pack_ray_chunks(ptr(sc[0]), ptr(sc[1]), cap, ptr(packed), n, ptr(t0), ptr(t1), ptr(ri), stream()))
+        if rays_mask_u8 is not None:
+            term = torch.where(rays_mask_u8.bool(), term, nearp)     # (masked rays: the kernel leaves their plane untouched)
     else:
-        term.copy_(nearp)
-    packed = torch.stack([starts, cnt], dim=-1)
+        run(None, None, None, None, cnt, None)
+        starts = cnt.cumsum(0) - cnt
+        total = int(cnt.sum())                       # the one host sync of the reference too (data_spec.hpp:91)
+        t0 = torch.empty(total, device=dev)
+        t1 = torch.empty(total, device=dev)
+        ri = torch.empty(total, dtype=torch.int64, device=dev)
+        if total:
+            run(starts, t0, t1, ri, None, term)
+        else:
+            term.copy_(nearp)
+        packed = torch.stack([starts, cnt], dim=-1)
     intervals = RayIntervals(t_starts=t0, t_ends=t1, sample_packed_info=packed, sample_ray_indices=ri)
     samples = _LazySamples(t0, t1, packed, ri)
     return intervals, samples, term

@@ -28,7 +28,8 @@ from .render import Rays, render_image_with_occgrid
 class TrainStep:
     def __init__(self, radiance_field, estimator, context_model=None, lmbda: float = 0.0, lr: float = 6e-3,
                  render_step_size: float = 5e-3, target_sample_batch_size: int = 1 << 18, bucket_bytes: int = 32 << 20,
-                 weight_decay: float = 2e-6, occ_refresh_every: int = 16, shard_tables: bool = True, exchange: str = "auto"):
+                 weight_decay: float = 2e-6, occ_refresh_every: int = 16, shard_tables: bool = True, exchange: str = "auto",
+                 data_parallel: bool = True):
         self.field, self.estimator, self.cm, self.lmbda = radiance_field, estimator, context_model, lmbda
         self.render_step_size, self.target, self.occ_every = render_step_size, target_sample_batch_size, occ_refresh_every
         self.lr = lr
@@ -40,14 +41,16 @@ class TrainStep:
         ctx = [p for p in context_model.parameters() if p.requires_grad] if context_model is not None else []
         # the STE window of the render path's table gradient is applied inside the table optimizer's pass (idempotent for the
         # contributions of the rate term, which arrive already masked): four full-table elementwise kernels less per step
-        self.table_opt = ShardedTableAdam(encs, lr=lr, eps=1e-15, weight_decay=weight_decay, ste_window=True,
-                                          exchange=exchange) if self.sharded else None
+        # data_parallel=False: a single-process step even under torchrun (every rank trains its own replica; bench.py times it
+        # beside the data-parallel step to state the scaling efficiency from one run)
+        self.table_opt = ShardedTableAdam(encs, lr=lr, eps=1e-15, weight_decay=weight_decay, ste_window=True, exchange=exchange,
+                                          group=None if data_parallel else False) if self.sharded else None
         groups = [{"params": field_rest, "weight_decay": weight_decay}]
         if ctx:
             groups.append({"params": ctx, "weight_decay": 0.0})
         self.optimizer = torch.optim.Adam(groups, lr=lr, eps=1e-15, fused=field_rest[0].is_cuda)
         self.reducer = GradAllReducer(field_rest + ctx, bucket_bytes=bucket_bytes)
-        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.world = dist.get_world_size() if (dist.is_initialized() and data_parallel) else 1
         self.step_id = 0
         self._premarch = None
         # the tables' exchange runs over NVLink peer memory: so do the small gradients and the skip vote -- no NCCL kernel
@@ -199,7 +202,8 @@ class TrainStep:
         if self.table_opt is not None:
             self.table_opt.lr = self.lr
             exchanged = self.table_opt.exchange()   # tables: reduce-scatter of the rows (asynchronous)
-        self.reducer.reduce()                       # MLPs + context models: one small bucketed all-reduce
+        if self.world > 1:
+            self.reducer.reduce()                   # MLPs + context models: one small bucketed average over the ranks
         if self._vote_result(vote):
             if exchanged is not None:
                 self.table_opt.apply(exchanged)     # Adam on the owned rows -> bit planes all-gather -> stand-ins

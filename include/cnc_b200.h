@@ -492,6 +492,12 @@ int cnc_render_bwd(const float *t_starts, const float *t_ends, const float *tran
  * (examples/utils.py:250-262, the sigma_fn / rgb_sigma_fn closures); dirs nullable */
 int cnc_sample_points(const float *rays_o, const float *rays_d, const int64_t *ray_indices, const float *t_starts, const float *t_ends,
                       int64_t n, float *positions, float *dirs, cnc_stream_t stream);
+/* One-walk marching: cnc_traverse_grids called with chunk_starts[r] = r * cap, steps_limit = cap, cnt AND the fill outputs
+ * (ray_indices may be NULL) leaves ray r's samples at scratch[r * cap ..] and its count; this moves them to the packed layout
+ * of packed_info [n_rays,2] = (exclusive prefix sum of the counts, counts) and writes ray_indices.  The caller picks cap as
+ * an upper bound of the samples of one ray (box diagonal / step) and falls back to count + fill when a count reaches it. */
+int cnc_pack_ray_chunks(const float *scratch_t_starts, const float *scratch_t_ends, int64_t cap, const int64_t *packed_info,
+                        int64_t n_rays, float *t_starts, float *t_ends, int64_t *ray_indices, cnc_stream_t stream);
 /* samples with keep[i] != 0 move to slot rank[i] - 1 (rank = inclusive int64 prefix sum of keep), order kept: the
  * `t_starts[masks], t_ends[masks], ray_indices[masks]` of OccGridEstimator.sampling (occ_grid.py:192-197);
  * out_packed_info [n_rays,2] (nullable) = (start, count) per ray of what is kept, from packed_info [n_rays,2] of the input
