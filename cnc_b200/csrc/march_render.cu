@@ -90,10 +90,11 @@ struct MarchArgs {
 // and ALL 32 occupancy bytes are loaded at once (one memory latency per 32 cells instead of one per cell: the walk is a
 // latency chain, 390 cycles per cell when measured one load at a time); a ballot hands every lane the 32 bits, and the walk
 // proper replays the same cells with the same arithmetic in the same order -- sample placement stays bit for bit.
-template <bool WARP = false, class Emit>
+template <bool WARP = false, bool CDT = false, class Emit>
 __device__ __forceinline__ int64_t march_ray(const MarchArgs &a, int64_t tid, float near, float far, int32_t steps_limit, Emit emit,
                                              float &t_end) {
     const float eps = 1e-6f;
+    const float dtc = a.step_size, half = __fmul_rn(a.step_size, 0.5f);
     const float o[3] = {a.rays_o[tid * 3], a.rays_o[tid * 3 + 1], a.rays_o[tid * 3 + 2]};
     const float d[3] = {a.rays_d[tid * 3], a.rays_d[tid * 3 + 1], a.rays_d[tid * 3 + 2]};
     const float inv[3] = {__fdiv_rn(1.0f, d[0]), __fdiv_rn(1.0f, d[1]), __fdiv_rn(1.0f, d[2])};
@@ -114,13 +115,7 @@ __device__ __forceinline__ int64_t march_ray(const MarchArgs &a, int64_t tid, fl
         const float this_tmin = fmaxf(a.t_sorted[i], near);
         const float this_tmax = fminf(a.t_sorted[i + 1], far);
         if (this_tmin >= this_tmax) continue;
-        if (!continuous) {
-            if (a.step_size <= 0.0f) t_last = this_tmin;
-            else {
-                const float dt = calc_dt(t_last, a.cone_angle, a.step_size, 1e10f);
-                while (!(__fmaf_rn(dt, 0.5f, t_last) >= this_tmin)) t_last = __fadd_rn(t_last, dt);
-            }
-        }
+        const bool first_skip = !continuous;   // (the skip itself follows the traversal setup: it only touches t_last)
         const float *bb = a.aabbs + level * 6;
         // setup_traversal, utils_grid.cuh:59-118
         float tdist[3], delta[3];
@@ -142,81 +137,102 @@ __device__ __forceinline__ int64_t march_ray(const MarchArgs &a, int64_t tid, fl
             delta[k] = (d[k] == 0.0f) ? this_tmax : __fmul_rn(__fmul_rn(vox, inv[k]), sf);
             over[k] = fin + step[k];
         }
-        uint32_t occ_bits = 0;   // WARP: occupancy of the next cells of the DDA, bit 0 = the current one
-        int occ_left = 0;
-        const uint32_t lane = WARP ? (threadIdx.x & 31u) : 0u;
-        while (steps_limit <= 0 || n_samples < steps_limit) {
-            const float t_trav = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), this_tmax);
-            const int64_t cell = (int64_t)cur[0] * a.ry * a.rz + (int64_t)cur[1] * a.rz + cur[2] + level * (int64_t)a.rx * a.ry * a.rz;
-            bool occupied;
-            if (WARP) {
-                if (occ_left == 0) {
-                    // run the DDA ahead on a copy: lane j keeps the j-th cell from here
-                    float td[3] = {tdist[0], tdist[1], tdist[2]};
-                    int cu[3] = {cur[0], cur[1], cur[2]};
-                    int64_t mine = cell;
-                    int n_ahead = 0;
-                    for (int j = 0; j < 32; j++) {
-                        const int64_t cj = (int64_t)cu[0] * a.ry * a.rz + (int64_t)cu[1] * a.rz + cu[2] + level * (int64_t)a.rx * a.ry * a.rz;
-                        if (lane == (uint32_t)j) mine = cj;
-                        n_ahead = j + 1;
-                        const int axj = ((td[0] < td[1]) && (td[0] < td[2])) ? 0 : ((td[1] < td[2]) ? 1 : 2);
-                        bool fin = false;
-#pragma unroll
-                        for (int k = 0; k < 3; k++) {
-                            if (k == axj) {
-                                cu[k] += step[k];
-                                td[k] = __fadd_rn(td[k], delta[k]);
-                                fin = cu[k] == over[k];
-                            }
-                        }
-                        if (fin) break;
-                    }
-                    const bool o = lane < (uint32_t)n_ahead && a.binaries[mine] != 0;
-                    occ_bits = __ballot_sync(0xffffffffu, o);
-                    occ_left = n_ahead;
+        // the two ways t_last moves (grid.cu:225-290): through an empty cell / up to a segment start without samples, and
+        // through an occupied cell with one sample per step.  CDT (cone_angle == 0): dt is the step size, and
+        // fma(dt, 0.5, t) == t + dt/2 (the product is exact), so a step is two additions.
+        auto skip_to = [&](float target) {
+            if (a.step_size <= 0.0f) { t_last = target; return; }
+            if (CDT) {
+                for (;;) {   // four steps per round trip: the additions are the chain, the comparisons hang off it
+                    const float t1 = __fadd_rn(t_last, dtc), t2 = __fadd_rn(t1, dtc), t3 = __fadd_rn(t2, dtc), t4 = __fadd_rn(t3, dtc);
+                    if (__fadd_rn(t_last, half) >= target) break;
+                    if (__fadd_rn(t1, half) >= target) { t_last = t1; break; }
+                    if (__fadd_rn(t2, half) >= target) { t_last = t2; break; }
+                    if (__fadd_rn(t3, half) >= target) { t_last = t3; break; }
+                    t_last = t4;
                 }
-                occupied = occ_bits & 1u;
-                occ_bits >>= 1;
-                occ_left--;
             } else {
-                occupied = a.binaries[cell] != 0;
+                const float dt = calc_dt(t_last, a.cone_angle, a.step_size, 1e10f);
+                while (!(__fmaf_rn(dt, 0.5f, t_last) >= target)) t_last = __fadd_rn(t_last, dt);
             }
-            if (!occupied) {
-                if (a.step_size <= 0.0f) t_last = t_trav;
-                else {
+        };
+        auto sample_to = [&](float t_trav) {
+            while (steps_limit <= 0 || n_samples < steps_limit) {
+                float t_next;
+                if (a.step_size <= 0.0f) t_next = t_trav;
+                else if (CDT) {
+                    if (__fadd_rn(t_last, half) >= t_trav) break;
+                    t_next = __fadd_rn(t_last, dtc);
+                } else {
                     const float dt = calc_dt(t_last, a.cone_angle, a.step_size, 1e10f);
-                    while (!(__fmaf_rn(dt, 0.5f, t_last) >= t_trav)) t_last = __fadd_rn(t_last, dt);
+                    if (__fmaf_rn(dt, 0.5f, t_last) >= t_trav) break;
+                    t_next = __fadd_rn(t_last, dt);
                 }
-                continuous = false;
-            } else {
-                while (steps_limit <= 0 || n_samples < steps_limit) {
-                    float t_next;
-                    if (a.step_size <= 0.0f) t_next = t_trav;
-                    else {
-                        const float dt = calc_dt(t_last, a.cone_angle, a.step_size, 1e10f);
-                        if (__fmaf_rn(dt, 0.5f, t_last) >= t_trav) break;
-                        t_next = __fadd_rn(t_last, dt);
-                    }
-                    emit(n_samples, t_last, t_next);
-                    n_samples++;
-                    continuous = true;
-                    t_last = t_next;
-                    if (t_next >= t_trav) break;
-                }
+                emit(n_samples, t_last, t_next);
+                n_samples++;
+                continuous = true;
+                t_last = t_next;
+                if (t_next >= t_trav) break;
             }
-            // single_traversal, utils_grid.cuh:121-149
-            const int ax = ((tdist[0] < tdist[1]) && (tdist[0] < tdist[2])) ? 0 : ((tdist[1] < tdist[2]) ? 1 : 2);
-            bool done = false;
+        };
+        if (first_skip) skip_to(this_tmin);
+        if (WARP) {
+            // The DDA does not depend on the sampling state: the warp runs it 32 cells ahead (every lane the same arithmetic,
+            // lane j keeps cell j and the time the ray leaves it), loads the 32 occupancy bytes at once, and then walks the
+            // 32 cells against a ballot and shuffles -- same cells, same exit times, same order as one cell at a time.
+            const uint32_t lane = threadIdx.x & 31u;
+            const int64_t sx = (int64_t)a.ry * a.rz, sy = a.rz;
+            const int64_t cstep[3] = {step[0] * sx, step[1] * sy, (int64_t)step[2]};
+            int64_t cell = cur[0] * sx + cur[1] * sy + cur[2] + level * (int64_t)a.rx * sx;
+            bool seg_done = false, stop = false;
+            while (!seg_done && !stop) {
+                float my_tt = 0.f;
+                int64_t my_cell = cell;
+                int n_ahead = 0;
+                for (int j = 0; j < 32; j++) {
+                    const float tt = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), this_tmax);
+                    if (lane == (uint32_t)j) { my_tt = tt; my_cell = cell; }
+                    n_ahead = j + 1;
+                    const int ax = ((tdist[0] < tdist[1]) && (tdist[0] < tdist[2])) ? 0 : ((tdist[1] < tdist[2]) ? 1 : 2);
+                    bool fin = false;
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                if (k == ax) {
-                    cur[k] += step[k];
-                    tdist[k] = __fadd_rn(tdist[k], delta[k]);
-                    done = cur[k] == over[k];
+                    for (int k = 0; k < 3; k++) {
+                        if (k == ax) {
+                            cur[k] += step[k];
+                            tdist[k] = __fadd_rn(tdist[k], delta[k]);
+                            cell += cstep[k];
+                            fin = cur[k] == over[k];
+                        }
+                    }
+                    if (fin) { seg_done = true; break; }
+                }
+                const uint32_t occ = __ballot_sync(0xffffffffu, lane < (uint32_t)n_ahead && a.binaries[my_cell] != 0);
+                for (int j = 0; j < n_ahead; j++) {
+                    if (!(steps_limit <= 0 || n_samples < steps_limit)) { stop = true; break; }
+                    const float t_trav = __shfl_sync(0xffffffffu, my_tt, j);
+                    if ((occ >> j) & 1u) sample_to(t_trav);
+                    else { skip_to(t_trav); continuous = false; }
                 }
             }
-            if (done) break;
+        } else {
+            while (steps_limit <= 0 || n_samples < steps_limit) {
+                const float t_trav = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), this_tmax);
+                const int64_t cell = (int64_t)cur[0] * a.ry * a.rz + (int64_t)cur[1] * a.rz + cur[2] + level * (int64_t)a.rx * a.ry * a.rz;
+                if (a.binaries[cell]) sample_to(t_trav);
+                else { skip_to(t_trav); continuous = false; }
+                // single_traversal, utils_grid.cuh:121-149
+                const int ax = ((tdist[0] < tdist[1]) && (tdist[0] < tdist[2])) ? 0 : ((tdist[1] < tdist[2]) ? 1 : 2);
+                bool done = false;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    if (k == ax) {
+                        cur[k] += step[k];
+                        tdist[k] = __fadd_rn(tdist[k], delta[k]);
+                        done = cur[k] == over[k];
+                    }
+                }
+                if (done) break;
+            }
         }
     }
     t_end = t_last;
@@ -228,7 +244,7 @@ __device__ __forceinline__ int64_t march_ray(const MarchArgs &a, int64_t tid, fl
 // loops, and with 32 rays per warp the warp executes the UNION of 32 different loop nests (measured: 292 us for 1100
 // rays, ten times one ray's chain); a training batch has a few thousand rays, far fewer than the machine has warp slots.
 // Large batches (test-time wavefronts of 10^5..10^6 rays with a step limit) keep one thread per ray.
-template <bool RAY_PER_WARP>
+template <bool RAY_PER_WARP, bool CDT = false>
 __global__ void __launch_bounds__(128) traverse_kernel(const MarchArgs a) {
     int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u;
@@ -245,7 +261,7 @@ __global__ void __launch_bounds__(128) traverse_kernel(const MarchArgs a) {
     if (RAY_PER_WARP) {
         // every lane sees every sample; lane (j % 32) keeps sample j, and 32 of them leave as one coalesced store
         float k0 = 0.f, k1 = 0.f;
-        n_samples = march_ray<true>(a, tid, a.near_planes[tid], a.far_planes[tid], a.steps_limit,
+        n_samples = march_ray<true, CDT>(a, tid, a.near_planes[tid], a.far_planes[tid], a.steps_limit,
                                     [&](int64_t j, float t0, float t1) {
                                         if (fill) {
                                             if ((uint32_t)(j & 31) == lane) { k0 = t0; k1 = t1; }
@@ -654,9 +670,12 @@ int cnc_traverse_grids(const float *rays_o, const float *rays_d, const uint8_t *
     mr::MarchArgs a{rays_o, rays_d, rays_mask, n_rays, n_grids, rx, ry, rz, binaries, aabbs, hits, t_sorted, t_indices,
                     near_planes, far_planes, step_size, cone_angle, steps_limit, chunk_starts, cnt, t_starts, t_ends,
                     ray_indices, terminate_planes};
-    if (n_rays <= 148 * 64 * 2)   // at most two waves of one-ray warps
-        mr::traverse_kernel<true><<<div_up((uint64_t)n_rays * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
-    else
+    if (n_rays <= 148 * 64 * 2) {   // at most two waves of one-ray warps
+        if (cone_angle == 0.0f && step_size > 0.0f)
+            mr::traverse_kernel<true, true><<<div_up((uint64_t)n_rays * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+        else
+            mr::traverse_kernel<true, false><<<div_up((uint64_t)n_rays * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    } else
         mr::traverse_kernel<false><<<div_up((uint64_t)n_rays, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return check_launch("traverse_grids");
 }

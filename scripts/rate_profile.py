@@ -23,3 +23,5 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for i in range(3): step(i + 33)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by=os.environ.get("SORT", "cuda_time_total"), row_limit=40, max_name_column_width=60))
+if os.environ.get("TRACE"):
+    prof.export_chrome_trace(os.environ["TRACE"])
