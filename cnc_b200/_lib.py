@@ -145,7 +145,16 @@ def ptr(t):
 def stream():
     """The current torch CUDA stream handle (the reference launches on the legacy default
     stream, gridencoder.cu:635; we follow torch's current stream so DP ranks / side streams work)."""
-    return torch.cuda.current_stream().cuda_stream
+    # (torch.cuda.current_stream() builds a Stream object: ~15 us per call, once per kernel launch -- a millisecond per
+    #  training step on the host-bound paths; the raw handle is a C call)
+    return _raw_stream(_cur_device())
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_cur_device = getattr(torch._C, "_cuda_getDevice", None)
+if _raw_stream is None or _cur_device is None:      # other torch builds: the documented road
+    _raw_stream = lambda d: torch.cuda.current_stream(d).cuda_stream
+    _cur_device = torch.cuda.current_device
 
 
 def need_cuda(**tensors):

@@ -552,7 +552,8 @@ class CNC_context_models(nn.Module):
             del keys
             ent, cnt = torch.unique_consecutive(entry, return_counts=True)
             seg = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(cnt, 0)])
-            cache[1][n] = (pts, ent.to(torch.int64), seg, ent.cpu().numpy(), seg.cpu().numpy())
+            ent = ent.to(torch.int64)     # (also on the host: searchsorted with a python int would convert an int32 array per call)
+            cache[1][n] = (pts, ent, seg, ent.cpu().numpy(), seg.cpu().numpy())
         return cache[1][n]
 
     def _pruned_weights(self, n, vx, binary_vxl):
