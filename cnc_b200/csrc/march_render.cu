@@ -526,6 +526,7 @@ struct WaveArgs {
 
 // one thread per ray: count the samples of the round, reserve their slots (warp-aggregated atomic), march again writing
 // them.  The walk itself is march_ray, i.e. the sample placement of traverse_grids bit for bit.
+template <bool CDT>
 __global__ void __launch_bounds__(128) wf_march_kernel(const WaveArgs w) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31u;
@@ -534,10 +535,17 @@ __global__ void __launch_bounds__(128) wf_march_kernel(const WaveArgs w) {
     const bool live = tid < w.m.n_rays && w.ray_mask[tid];
     float near = 0.f, far = 0.f, t_end = 0.f;
     uint32_t cnt = 0;
+    // the round's samples of this ray (the schedule hands out at most 64 per ray and round): kept from the one walk, so that
+    // the slot assignment below does not have to be followed by a second walk
+    constexpr int KEEP = 64;
+    float k0[KEEP], k1[KEEP];
+    const bool keep = limit > 0 && limit <= KEEP;
     if (live) {
         near = w.near_planes[tid];
         far = w.m.far_planes[tid];
-        cnt = (uint32_t)march_ray(w.m, tid, near, far, limit, [](int64_t, float, float) {}, t_end);
+        cnt = (uint32_t)march_ray<false, CDT>(w.m, tid, near, far, limit, [&](int64_t j, float ta, float tb) {
+            if (keep) { k0[j] = ta; k1[j] = tb; }
+        }, t_end);
     }
     // slots: exclusive prefix inside the warp + one atomic per warp
     uint32_t incl = cnt;
@@ -557,8 +565,7 @@ __global__ void __launch_bounds__(128) wf_march_kernel(const WaveArgs w) {
     if (cnt == 0 || base + cnt > w.capacity) return;   // (capacity is sized for the schedule: n_live * n <= n_rays * min_samples)
     const float o[3] = {w.m.rays_o[tid * 3], w.m.rays_o[tid * 3 + 1], w.m.rays_o[tid * 3 + 2]};
     const float d[3] = {w.m.rays_d[tid * 3], w.m.rays_d[tid * 3 + 1], w.m.rays_d[tid * 3 + 2]};
-    float dummy;
-    march_ray(w.m, tid, near, far, limit, [&](int64_t j, float ta, float tb) {
+    auto put = [&](int64_t j, float ta, float tb) {
         const uint32_t k = base + (uint32_t)j;
         w.t0[k] = ta;
         w.t1[k] = tb;
@@ -569,7 +576,13 @@ __global__ void __launch_bounds__(128) wf_march_kernel(const WaveArgs w) {
             w.pos[k * 3 + c] = __fadd_rn(o[c], __fdiv_rn(__fmul_rn(d[c], ts), 2.0f));
             w.dir[k * 3 + c] = d[c];
         }
-    }, dummy);
+    };
+    if (keep) {
+        for (uint32_t j = 0; j < cnt; j++) put(j, k0[j], k1[j]);
+    } else {
+        float dummy;
+        march_ray<false, CDT>(w.m, tid, near, far, limit, put, dummy);
+    }
 }
 
 struct CompArgs {
@@ -702,7 +715,10 @@ int cnc_wavefront_march(const float *rays_o, const float *rays_d, int64_t n_rays
                         near_planes, far_planes, step_size, cone_angle, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     w.st = state; w.ray_mask = ray_mask; w.near_planes = near_planes; w.capacity = capacity;
     w.ray_base = ray_base; w.ray_cnt = ray_cnt; w.ray_term = ray_term; w.t0 = t0; w.t1 = t1; w.pos = pos; w.dir = dirs;
-    mr::wf_march_kernel<<<div_up((uint64_t)n_rays, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(w);
+    if (cone_angle == 0.0f && step_size > 0.0f)
+        mr::wf_march_kernel<true><<<div_up((uint64_t)n_rays, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(w);
+    else
+        mr::wf_march_kernel<false><<<div_up((uint64_t)n_rays, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(w);
     return check_launch("wavefront_march");
 }
 
