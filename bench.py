@@ -581,6 +581,27 @@ def train_bench(arm, rank, world, steps, field):
         out["comm"] = ts.comm_description()
         if ts.table_opt is not None and ts.table_opt.peer is not None:
             out["nvlink_bytes_per_step"] = ts.table_opt.link_bytes_per_step()
+    if world > 1 and ours:
+        # the lambda > 0 step under data parallelism: rays sharded as above, the rate term shared among the ranks
+        # (context_models.set_data_parallel: every rank samples 150 000 / N entries and evaluates its share of the plane terms)
+        cm = arm.context_model()
+        ts2 = TrainStep(field, est, context_model=cm, lmbda=1e-3, lr=1e-4, exchange=os.environ.get("CNC_EXCHANGE", "auto"))
+        for _ in range(2):
+            call(ts2)
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        e0.record()
+        for _ in range(steps):
+            call(ts2)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        out["with_rate_term"] = {"what": "lambda > 0 step, data parallel: rate term shared among the ranks (sampled entries and "
+                                         "plane terms split, gradients averaged)", "lambda": 1e-3, "ms_per_step": float(t[0]) / steps,
+                                 "sampled_entries_per_rank": int(cm._dp_snl[0].sum()) if getattr(cm, "_dp_snl", None) else None}
+        del cm, ts2
+        torch.cuda.empty_cache()
     if world == 1:
         # the same step with the rate term of the CNC loss (lambda > 0: context model on 150 000 sampled entries + planes)
         cm = arm.context_model()

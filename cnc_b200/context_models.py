@@ -918,6 +918,24 @@ class CNC_context_models(nn.Module):
         return mean / unique_cnt_2D.unsqueeze(-1), unique_value_2D, (points_n, indices_2D, unique_value_2D, unique_cnt_2D)
 
     # ------------------------------------------------------------------------------------------ loss
+    def set_data_parallel(self, rank: int = 0, world: int = 1) -> None:
+        """share the rate term among `world` data-parallel ranks whose gradients are AVERAGED afterwards:
+        * the sampled 3D entries: every rank takes sample_num / world of them, its random windows shifted by rank / world of
+          the level -- together the ranks still sample `sample_num` entries per step, and each rank's scaled estimate of the
+          level's bits is unbiased, so the average is;
+        * the plane terms (axis, level): exact sums, dealt round-robin; a rank multiplies its terms by `world`, so the average
+          over the ranks is the full sum;
+        * everything cheap and exact (the terms of uncoded levels) stays replicated.
+        rank 0 of world 1 (the default) is the reference's single-process loss."""
+        self.dp_rank, self.dp_world = int(rank), int(world)
+        if world <= 1:
+            self._dp_snl = None
+            return
+        snl = torch.round(self.hashparams_num_levels * ((self.sample_num / world) / self.hashparams_num_levels.sum())).to(torch.long)
+        snl = torch.minimum(torch.clamp(snl, min=1), self.hashparams_num_levels)
+        coded = [n for n in range(self.n_levels) if n not in self.skip_levels_3D and n < self.Pg_level]
+        self._dp_snl = (snl, int(sum(int(snl[n]) for n in coded)))
+
     def forward_binary_vxl_mixPg_3D2D(self, Encoding_xyz, Encoding_xy, Encoding_xz, Encoding_yz, binary_vxl=None,
                                       verbose=False, sample_num=None, step=0):
         """Rate term of the training loss: (bits per parameter, MB).  utils_bpp_acc.py:533-706"""
@@ -929,15 +947,21 @@ class CNC_context_models(nn.Module):
         if refresh:
             self.batched_inputs_list = {}
         ttl_bit_sum, ttl_num_sum = 0, 0
+        rank, world = getattr(self, "dp_rank", 0), getattr(self, "dp_world", 1)
+        coded_2D = [n for n in range(self.n_levels_2D) if not (n in self.skip_levels_2D or n >= self.Pg_level_2D)]
+        # (data parallel: the coded plane terms are dealt round-robin over the ranks, see set_data_parallel)
+        mine = {(a, n) for t, (a, n) in enumerate((a, n) for a in ("xy", "xz", "yz") for n in coded_2D) if t % world == rank}
         finest = pq["xyz"][self.offs[-2]:self.offs[-1]]
-        pns = self.get_pn_embed_frac3(finest, self.idx_coords2_tmp) if self.use_dimension_wise else {}
+        pns = self.get_pn_embed_frac3(finest, self.idx_coords2_tmp) if (self.use_dimension_wise and mine) else {}
         for axis, Enc in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz)):
             pn = pns.get(axis)
             Pgs_2D, bits_2D = self.level_entropies(pq[axis], self.offs_2D)
             means, rows_l = [], []
             for n in range(self.n_levels_2D):
                 Pg_n, bit_n = Pgs_2D[n], bits_2D[n]
-                if not (n in self.skip_levels_2D or n >= self.Pg_level_2D):
+                if n in coded_2D:
+                    if (axis, n) not in mine:
+                        continue
                     mean, rows, batch = self._probs_2D(Enc, None, planes[axis], n, pn, Pg_n,
                                                        self.batched_inputs_list.get((axis, n)), differentiable=True)
                     self.batched_inputs_list[(axis, n)] = batch
@@ -946,16 +970,22 @@ class CNC_context_models(nn.Module):
                 else:
                     ttl_bit_sum = ttl_bit_sum + bit_n
             if means:   # one gather of the coded rows of the plane (one index backward instead of one per level)
-                ttl_bit_sum = ttl_bit_sum + torch.sum(self.entropy_model(pq[axis][torch.cat(rows_l), :], torch.cat(means, 0)))
+                plane_bits = torch.sum(self.entropy_model(pq[axis][torch.cat(rows_l), :], torch.cat(means, 0)))
+                ttl_bit_sum = ttl_bit_sum + (plane_bits * world if world > 1 else plane_bits)
             ttl_num_sum += pq[axis].numel()
 
         if sample_num is not None:
             snl = torch.round(self.hashparams_num_levels * (sample_num / self.hashparams_num_levels.sum())).to(torch.long)
             snl = self.hashparams_num_levels if snl[-1] > self.hashparams_num_levels[-1] else snl
             n_valid = sum(int(snl[n]) for n in range(self.n_levels) if n not in self.skip_levels_3D and n < self.Pg_level)
+        elif world > 1 and getattr(self, "_dp_snl", None) is not None:
+            snl, n_valid = self._dp_snl
         else:
             snl, n_valid = self.sample_num_levels, self.ttl_sample_num_valid_levels
-        start = torch.round((self.hashparams_num_levels - snl) * torch.rand_like(self.utils_rand)).to(torch.long)
+        u = torch.rand_like(self.utils_rand)
+        if world > 1:      # this rank's windows: the same draw on every rank lands rank / world of the level further on
+            u = torch.remainder(u + rank / world, 1.0)
+        start = torch.round((self.hashparams_num_levels - snl) * u).to(torch.long)
         start, snl_h = torch.stack([start, snl.to(torch.long)]).tolist()   # one device->host read for both
         fast = (self.n_features == 8 and self.max_context_layer_num == 3 and Encoding_xyz.ste_binary
                 and getattr(self, "fused_gather_train", True) and min([n for n in range(self.n_levels) if n not in self.skip_levels_3D] + [99]) >= 3)

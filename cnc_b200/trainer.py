@@ -29,8 +29,18 @@ class TrainStep:
     def __init__(self, radiance_field, estimator, context_model=None, lmbda: float = 0.0, lr: float = 6e-3,
                  render_step_size: float = 5e-3, target_sample_batch_size: int = 1 << 18, bucket_bytes: int = 32 << 20,
                  weight_decay: float = 2e-6, occ_refresh_every: int = 16, shard_tables: bool = True, exchange: str = "auto",
-                 data_parallel: bool = True):
+                 data_parallel: bool = True, sync_initial_state: bool = True):
         self.field, self.estimator, self.cm, self.lmbda = radiance_field, estimator, context_model, lmbda
+        if dist.is_initialized() and data_parallel and dist.get_world_size() > 1 and sync_initial_state:
+            # replicas start from rank 0's parameters, occupancy and context models (whatever the ranks' RNG did before)
+            with torch.no_grad():
+                for m in (radiance_field, context_model):
+                    if m is not None:
+                        for p in m.parameters():
+                            dist.broadcast(p.data, src=0)
+            broadcast_module_buffers(estimator, ["occs", "binaries"], src=0)
+            if hasattr(radiance_field, "invalidate_caches"):
+                radiance_field.invalidate_caches()
         self.render_step_size, self.target, self.occ_every = render_step_size, target_sample_batch_size, occ_refresh_every
         self.lr = lr
         mb = radiance_field.mlp_base
@@ -53,6 +63,9 @@ class TrainStep:
         self.world = dist.get_world_size() if (dist.is_initialized() and data_parallel) else 1
         self.step_id = 0
         self._premarch = None
+        if context_model is not None and hasattr(context_model, "set_data_parallel"):
+            # the rate term is shared among the ranks: each samples 1/N of the entries and evaluates its share of the plane terms
+            context_model.set_data_parallel(dist.get_rank() if self.world > 1 else 0, self.world)
         # the tables' exchange runs over NVLink peer memory: so do the small gradients and the skip vote -- no NCCL kernel
         # (a spinning all-reduce holds SM slots beside the persistent GEMM kernels of backward) is left in the step
         self._peer_sig = self.table_opt.peer["sig"] if (self.table_opt is not None and self.table_opt.peer is not None) else None
@@ -74,7 +87,7 @@ class TrainStep:
                     "from all N gradient buffers (cnc_peer_reduce), Adam on them, stores its words of the sign and STE-window bit "
                     "planes into every peer (cnc_peer_push); MLP / context-model gradients: packed into a mapped buffer, summed by every "
                     "rank from all N (cnc_peer_reduce); skip vote: minimum of the sample counts through the signal pads (cnc_peer_min); "
-                    "no NCCL kernel in the step")
+                    "no NCCL kernel in the step" + ("; rate term: sampled entries and plane terms split over the ranks" if self.cm is not None else ""))
         return ("latent tables: reduce-scatter(avg) of the gradient by rows, Adam on the owned 1/N, all-gather of the sign and "
                 "STE-window bit planes; MLP / context-model gradients: one bucketed all-reduce; sample count: 8-byte all-reduce")
 

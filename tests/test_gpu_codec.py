@@ -467,3 +467,41 @@ def test_fused_plane_gather_equals_the_two_k1_flow(cuda):
     assert all(float(g.abs().max()) > 0 for g in out[True][1])
     assert list(streams[True]) == list(streams[False])
     assert all(streams[True][k] == streams[False][k] for k in streams[True])    # identical features -> identical bytes
+
+
+def test_rate_term_shared_among_data_parallel_ranks(cuda):
+    """CNC_context_models.set_data_parallel: the plane terms dealt over the ranks (times world), the sampled 3D entries split
+    among them -- the AVERAGE over the ranks of loss and gradients is the single-process rate term.  Checked with every entry
+    sampled (so that the 3D part is exact, too); and with the training sample size, that each rank samples its share and the
+    windows of different ranks differ."""
+    cm, encs, vxl = make(cuda, **SMALL)
+    params = [e.params for e in encs] + [p for p in cm.parameters() if p.requires_grad]
+
+    def run(rank, world, sample_num=None):
+        cm.set_data_parallel(rank, world)
+        for p in params:
+            p.grad = None
+        torch.manual_seed(0)
+        bpp, _ = cm.forward_binary_vxl_mixPg_3D2D(*encs, vxl, step=0, sample_num=sample_num)
+        bpp.backward()
+        return float(bpp), [torch.zeros_like(p) if p.grad is None else p.grad.clone() for p in params]
+
+    everything = 10 ** 9
+    full_bpp, full_g = run(0, 1, sample_num=everything)
+    cm.sample_num = everything * 3          # (a third of it is still every entry)
+    world = 3
+    parts = [run(r, world) for r in range(world)]
+    np.testing.assert_allclose(np.mean([b for b, _ in parts]), full_bpp, rtol=2e-5)
+    assert max(abs(b - full_bpp) for b, _ in parts) > 1e-3 * full_bpp          # no rank computes the whole thing
+    for k, g in enumerate(full_g):
+        avg = sum(p[1][k] for p in parts) / world
+        torch.testing.assert_close(avg, g, rtol=2e-4, atol=2e-6 * float(g.abs().max()) + 1e-12)
+    # training sample size: a rank's share, windows shifted by rank / world
+    cm.sample_num = 4000
+    cm.set_data_parallel(1, 4)
+    snl, n_valid = cm._dp_snl
+    assert abs(int(snl.sum()) - 1000) <= cm.n_levels and 0 < n_valid <= int(snl.sum())
+    b1, _ = run(1, 4)
+    b2, _ = run(2, 4)
+    assert np.isfinite([b1, b2]).all() and b1 != b2
+    cm.set_data_parallel(0, 1)
