@@ -105,27 +105,35 @@ class _cnt_np_embed3(Function):
     by its closed form in the occupancy grid, the atomics by per-cell / per-row ownership."""
 
     @staticmethod
-    def forward(ctx, embeddings, vx, pts_by_row, seg, resolution, hashmap_size):
+    def forward(ctx, embeddings, vx, pts_by_row, seg, resolution, hashmap_size, axes=(0, 1, 2)):
+        """-> one plane per entry of `axes` (0 = xy, 1 = xz, 2 = yz), in that order: a data-parallel rank builds (and
+        differentiates) only the planes its share of the plane terms reads"""
         embeddings = embeddings.contiguous()
         F = embeddings.shape[-1]
         bits = _backend.sign_pack(embeddings.detach())
         s = resolution - 2
-        outs = [torch.empty(s, s, F, 2, device=embeddings.device) for _ in range(3)]
+        outs = [torch.empty(s, s, F, 2, device=embeddings.device) if a in axes else None for a in range(3)]
         check(lib().cnc_vote3_fwd(ptr(vx), vx.shape[-1], ptr(bits), resolution, F, hashmap_size, *[ptr(o) for o in outs], stream()))
-        sums = [o.sum(dim=-1, keepdim=True) + 1e-6 for o in outs]
+        sums = [outs[a].sum(dim=-1, keepdim=True) + 1e-6 for a in axes]
         ctx.save_for_backward(bits, vx, pts_by_row, seg, *sums)
-        ctx.dims = [resolution, F, hashmap_size, tuple(embeddings.shape)]
-        return tuple(o / sm for o, sm in zip(outs, sums))
+        ctx.dims = [resolution, F, hashmap_size, tuple(embeddings.shape), tuple(axes)]
+        ctx.set_materialize_grads(False)
+        return tuple(outs[a] / sm for a, sm in zip(axes, sums))
 
     @staticmethod
-    def backward(ctx, g_xy, g_xz, g_yz):
-        bits, vx, pts_by_row, seg, s_xy, s_xz, s_yz = ctx.saved_tensors
-        resolution, F, hashmap_size, shape = ctx.dims
+    def backward(ctx, *grads):
+        bits, vx, pts_by_row, seg, *sums = ctx.saved_tensors
+        resolution, F, hashmap_size, shape, axes = ctx.dims
+        if all(g is None for g in grads):
+            return None, None, None, None, None, None, None
         g = torch.zeros(shape, device=bits.device)
-        gs = [(gg / sm).contiguous() for gg, sm in ((g_xy, s_xy), (g_xz, s_xz), (g_yz, s_yz))]   # 1 / sum folded in (:1012)
+        gs = [None, None, None]
+        for a, gg, sm in zip(axes, grads, sums):
+            if gg is not None:
+                gs[a] = (gg / sm).contiguous()     # 1 / sum folded in (:1012)
         check(lib().cnc_vote3_bwd(ptr(pts_by_row), ptr(seg), ptr(vx), vx.shape[-1], ptr(bits), resolution, F, hashmap_size,
                                   ptr(gs[0]), ptr(gs[1]), ptr(gs[2]), ptr(g), stream()))
-        return g, None, None, None, None, None
+        return g, None, None, None, None, None, None
 
 
 class align_and_pack(Function):
@@ -728,22 +736,25 @@ class CNC_context_models(nn.Module):
             cache = self._vote_table = (key, pts, seg.contiguous(), vx)   # (vx kept alive: the key stays sound)
         return cache[1], cache[2]
 
-    def get_pn_embed_frac3(self, embeddings_3D_q, binary_vxl):
+    def get_pn_embed_frac3(self, embeddings_3D_q, binary_vxl, axes=("xy", "xz", "yz")):
         """{"xy","xz","yz"} -> +1 vote fraction plane, zero padded to [res*res, F]: what `get_idx_coords2` followed by
-        three `get_pn_embed_frac` calls compute (utils_bpp_acc.py:498-530), without the voxel list."""
+        three `get_pn_embed_frac` calls compute (utils_bpp_acc.py:498-530), without the voxel list.  `axes`: the planes wanted."""
+        names = ("xy", "xz", "yz")
+        axes = tuple(a for a in names if a in axes)
         vx = binary_vxl.squeeze(0)
         vx = (vx if vx.dtype in (torch.bool, torch.uint8) else vx != 0).contiguous()
         if not (self._vote3_ready() and vx.shape[-1] == self.binary_vxl_len):
             idx = self.get_idx_coords2(binary_vxl)
-            return {a: self.get_pn_embed_frac(embeddings_3D_q, idx, axis=a) for a in ("xy", "xz", "yz")}
+            return {a: self.get_pn_embed_frac(embeddings_3D_q, idx, axis=a) for a in axes}
         res = self.res[-1]
         if torch.is_grad_enabled() and embeddings_3D_q.requires_grad:
             pts_by_row, seg = self._vote_member_table(vx)      # the backward's voxel list, pruned to the vote list itself
         else:
             pts_by_row, seg = None, None                       # (no backward: the forward reads the occupancy grid only)
-        fr = _cnt_np_embed3.apply(embeddings_3D_q, vx, pts_by_row, seg, res, self.offs[-1] - self.offs[-2])
+        fr = _cnt_np_embed3.apply(embeddings_3D_q, vx, pts_by_row, seg, res, self.offs[-1] - self.offs[-2],
+                                  tuple(names.index(a) for a in axes))
         out = {}
-        for a, f in zip(("xy", "xz", "yz"), fr):
+        for a, f in zip(axes, fr):
             f = nnf.pad(f[..., 0].permute(2, 0, 1).unsqueeze(0), pad=[1, 1, 1, 1]).squeeze(0).permute(1, 2, 0).contiguous()
             out[a] = f.view(-1, self.n_features)
         return out
@@ -952,7 +963,7 @@ class CNC_context_models(nn.Module):
         # (data parallel: the coded plane terms are dealt round-robin over the ranks, see set_data_parallel)
         mine = {(a, n) for t, (a, n) in enumerate((a, n) for a in ("xy", "xz", "yz") for n in coded_2D) if t % world == rank}
         finest = pq["xyz"][self.offs[-2]:self.offs[-1]]
-        pns = self.get_pn_embed_frac3(finest, self.idx_coords2_tmp) if (self.use_dimension_wise and mine) else {}
+        pns = self.get_pn_embed_frac3(finest, self.idx_coords2_tmp, axes={a for a, _ in mine}) if (self.use_dimension_wise and mine) else {}
         for axis, Enc in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz)):
             pn = pns.get(axis)
             Pgs_2D, bits_2D = self.level_entropies(pq[axis], self.offs_2D)

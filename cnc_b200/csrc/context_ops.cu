@@ -177,6 +177,7 @@ vote3_fwd_kernel(const uint8_t *__restrict__ vxl, uint32_t Rb, const uint8_t *__
     const uint32_t s = res - 2u, t = s / Rb, axis = blockIdx.z;
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x + 1u, u = blockIdx.y + 1u;   // plane cell, 1-based like the coords
     if (v > s) return;
+    if ((axis == 0 ? out_xy : (axis == 1 ? out_xz : out_yz)) == nullptr) return;   // plane not asked for
     // axis 0: (u, v, w) = (x, y, z); axis 1: (x, z, y); axis 2: (y, z, x)   (gridencoder.cu:902-906)
     const uint32_t du = axis == 2 ? 1u : 0u, dv = axis == 0 ? 1u : 2u, dw = 3u - du - dv;
     const uint32_t stride[3] = {Rb * Rb, Rb, 1u};
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(256) vote3_bwd_kernel(const Vote3BwdArgs a) {
         if (!member) continue;
 #pragma unroll
         for (int ax = 0; ax < 3; ax++) {
+            if (a.grad[ax] == nullptr) continue;   // (warp-uniform: a plane nobody differentiated)
             const uint32_t u = ax == 2 ? c[1] : c[0], v = ax == 0 ? c[1] : c[2];
             const size_t cell = (size_t)(u - 1u) * s + (v - 1u);
             // grad[ax] holds d loss / d fraction already divided by the cell's vote sum (1 / sum, :1012, folded by the caller:
@@ -351,7 +353,7 @@ int cnc_vote_planes_bwd(const int16_t *pts, const float *table, const float *out
 
 int cnc_vote3_fwd(const uint8_t *binary_vxl, uint32_t Rb, const uint8_t *sign_bits, uint32_t resolution, uint32_t F,
                   uint32_t hashmap_size, float *out_xy, float *out_xz, float *out_yz, cnc_stream_t stream) {
-    if (!binary_vxl || !sign_bits || !out_xy || !out_xz || !out_yz) { set_error("vote3_fwd: null pointer"); return CNC_EINVAL; }
+    if (!binary_vxl || !sign_bits || !(out_xy || out_xz || out_yz)) { set_error("vote3_fwd: null pointer"); return CNC_EINVAL; }
     if (F != 8 || Rb == 0 || Rb > 128 || resolution < 3 || (resolution - 2) % Rb != 0) {
         set_error("vote3_fwd: needs F == 8, Rb <= 128 and (resolution - 2) a multiple of Rb");
         return CNC_ENOTSUP;
@@ -365,7 +367,7 @@ int cnc_vote3_fwd(const uint8_t *binary_vxl, uint32_t Rb, const uint8_t *sign_bi
 int cnc_vote3_bwd(const int16_t *pts_by_row, const int64_t *seg, const uint8_t *binary_vxl, uint32_t Rb, const uint8_t *sign_bits,
                   uint32_t resolution, uint32_t F, uint32_t hashmap_size, const float *grad_xy, const float *grad_xz,
                   const float *grad_yz, float *grad_table, cnc_stream_t stream) {
-    if (!pts_by_row || !seg || !binary_vxl || !sign_bits || !grad_xy || !grad_xz || !grad_yz || !grad_table) {
+    if (!pts_by_row || !seg || !binary_vxl || !sign_bits || !(grad_xy || grad_xz || grad_yz) || !grad_table) {
         set_error("vote3_bwd: null pointer");
         return CNC_EINVAL;
     }

@@ -252,7 +252,9 @@ int cnc_vote_planes_bwd(const int16_t *pts, const float *table, const float *out
  * (gridencoder.cu:1047-1087 summed over the three planes): pts_by_row / seg = the level's inverse hash table (voxel
  * coords grouped by table row, [T+1] running counts); grad_* [(res-2),(res-2),8,2] = d loss / d fraction already
  * divided by the cell's vote sum (the 1/sum of :1012, folded by the caller); grad_table [T,8] is overwritten.
- * F == 8, Rb <= 128. */
+ * F == 8, Rb <= 128.  *   A NULL output plane (forward) / NULL gradient plane (backward) skips that axis: a data-parallel rank builds only the
+ *   planes its share of the plane terms reads.
+ */
 int cnc_vote3_fwd(const uint8_t *binary_vxl, uint32_t Rb, const uint8_t *sign_bits, uint32_t resolution,
                   uint32_t F, uint32_t hashmap_size, float *out_xy, float *out_xz, float *out_yz,
                   cnc_stream_t stream);
