@@ -94,11 +94,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const Args a) {
         constexpr uint32_t x4 = MI / 4, z4 = NO / 4;               // float4 per row
         constexpr uint32_t nx = KS * x4, nz = KS * z4;
         constexpr int JX = (nx + NSTAGER - 1) / NSTAGER, JZ = (nz + NSTAGER - 1) / NSTAGER;
-        for (uint32_t it = 0; it < my; it++) {
-            const uint32_t slab = blockIdx.x + it * gridDim.x, s = it % NSTAGE, use = it / NSTAGE;
-            const uint32_t row0 = slab * KS;
-            // all loads of the slab first (they do not depend on the ring), then wait for the stage
-            float4 vx[JX], vz[JZ];
+        // The loads of slab it + 1 are issued BEFORE slab it is converted and stored (a second register set): the global loads
+        // of a slab and the split / swizzled stores of the previous one overlap instead of alternating, which is what kept the
+        // kernel at 60 % of the HBM peak (and made it the most sensitive kernel of the step to anything else using memory).
+        auto load_slab = [&](uint32_t it, float4 (&vx)[JX], float4 (&vz)[JZ]) {
+            const uint32_t row0 = (blockIdx.x + it * gridDim.x) * KS;
 #pragma unroll
             for (int j = 0; j < JX; j++) {
                 const uint32_t i = threadIdx.x + j * NSTAGER, r = i / x4, c4 = i % x4, row = row0 + r;
@@ -108,6 +108,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const Args a) {
             for (int j = 0; j < JZ; j++) {
                 const uint32_t i = threadIdx.x + j * NSTAGER, r = i / z4, c4 = i % z4, row = row0 + r;
                 vz[j] = (i < nz && row < a.Ns) ? __ldg(reinterpret_cast<const float4 *>(a.Z + (size_t)row * a.ldz) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        constexpr bool AHEAD = MI <= 160;      // (the 256-wide layer holds 13 float4 per slab and thread: a second set costs more than it hides)
+        float4 vx[JX], vz[JZ];
+        if (AHEAD && my) load_slab(0, vx, vz);
+        for (uint32_t it = 0; it < my; it++) {
+            const uint32_t slab = blockIdx.x + it * gridDim.x, s = it % NSTAGE, use = it / NSTAGE;
+            const uint32_t row0 = slab * KS;
+            float4 wx[AHEAD ? JX : 1], wz[AHEAD ? JZ : 1];
+            if (AHEAD) {
+                if (it + 1 < my) load_slab(it + 1, reinterpret_cast<float4 (&)[JX]>(wx), reinterpret_cast<float4 (&)[JZ]>(wz));
+            } else {
+                load_slab(it, vx, vz);
             }
             if (use > 0) mbar_wait(empty(s), (use - 1) & 1u);
             uint8_t *st = smem + s * STAGE_BYTES;
@@ -141,6 +154,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const Args a) {
             fence_async_smem();
             __syncwarp();
             if ((threadIdx.x & 31) == 0) mbar_arrive(full(s));
+            if (AHEAD && it + 1 < my) {
+#pragma unroll
+                for (int j = 0; j < (AHEAD ? JX : 0); j++) vx[j] = wx[j];
+#pragma unroll
+                for (int j = 0; j < (AHEAD ? JZ : 0); j++) vz[j] = wz[j];
+            }
         }
         // =============================== epilogue: TMEM -> partial tile ===============================
         if (warp < 4) {
