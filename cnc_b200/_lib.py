@@ -41,6 +41,9 @@ SIGNATURES = {
     "cnc_level_row_hist": [_u32, _u32, _vp, _vp],
     "cnc_level_pruned_keys": [_u32, _u32, _vp, _i32, _vp, _vp, _vp, _i32, _vp],
     "cnc_keys_to_points": [_vp, _u64, _u32, _vp, _vp, _vp],
+    "cnc_bernoulli_bits_fwd": [_vp, _vp, _i64, _vp, _vp],
+    "cnc_bernoulli_bits_bwd": [_vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "cnc_level_popcount": [_vp, _vp, _i32, _vp, _vp],
     "cnc_ste_planes_pack": [_vp, _vp, _vp, _u64, _vp],
     "cnc_surrogate_fill": [_vp, _vp, _vp, _u64, _u64, _u64, _vp],
     "cnc_adam_planes": [_vp, _vp, _vp, _vp, _vp, _vp, _u64, _f32, _f32, _f32, _f32, _f32, _i64, _f32, _i32, _vp],
@@ -120,6 +123,8 @@ def lib():
         L.cnc_ctx_mlp_max_partials.argtypes = []
         L.cnc_lin8_rows_per_block.restype = C.c_int
         L.cnc_lin8_rows_per_block.argtypes = []
+        L.cnc_bernoulli_bits_blocks.restype = C.c_int
+        L.cnc_bernoulli_bits_blocks.argtypes = [_i64]
         for name in ("cnc_peer_handle_bytes", "cnc_peer_pad_bytes"):
             getattr(L, name).restype = C.c_int
             getattr(L, name).argtypes = []

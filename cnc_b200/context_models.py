@@ -326,13 +326,44 @@ def _level_const(offsets, F, device):
     return _LEVEL_CONST[key]
 
 
+class _RowsGather(Function):
+    """table[rows] for DISTINCT rows, differentiable in the table.  Autograd's own backward of an index is an accumulating
+    index_put: a radix sort of the indices and a dozen launches, every step, for indices that never repeat (the coded rows of
+    a level, a window of a level's entries); here it is a zero fill and one scatter."""
+
+    @staticmethod
+    def forward(ctx, table, rows):
+        ctx.save_for_backward(rows)
+        ctx.shape = tuple(table.shape)
+        return table.index_select(0, rows)
+
+    @staticmethod
+    def backward(ctx, g):
+        (rows,) = ctx.saved_tensors
+        out = torch.zeros(ctx.shape, device=g.device, dtype=g.dtype)
+        out.index_copy_(0, rows, g.contiguous())
+        return out, None
+
+
 class _LevelSums(Function):
     """sum of all entries of every level of a table [rows, F] -> [L]; the backward hands one full-size gradient tensor
     to autograd instead of one zero-padded tensor per level slice (what slicing under autograd does)."""
 
     @staticmethod
-    def forward(ctx, params_q, offsets):
+    def forward(ctx, params_q, offsets, binary=False):
         ctx.offsets, ctx.shape = tuple(int(o) for o in offsets), tuple(params_q.shape)
+        F = params_q.shape[-1]
+        if binary and params_q.is_cuda and all((o * F) % 8 == 0 for o in ctx.offsets):
+            # every entry is +1 or -1: sum = 2 * (#bits set in the sign plane) - (#entries), exact, one launch over 1 bit per
+            # entry instead of one fp32 reduction per level (whose result beyond 2^24 entries is rounded)
+            key = ("byte_offs",) + ctx.offsets + (F, str(params_q.device))
+            if key not in _LEVEL_CONST:
+                _LEVEL_CONST[key] = torch.tensor([o * F // 8 for o in ctx.offsets], dtype=torch.int64).to(params_q.device)
+            bits = _backend.sign_pack(params_q.detach().contiguous())
+            ones = torch.empty(len(ctx.offsets) - 1, dtype=torch.int64, device=params_q.device)
+            check(lib().cnc_level_popcount(ptr(bits), ptr(_LEVEL_CONST[key]), ones.numel(), ptr(ones), stream()))
+            _, ttl = _level_const(ctx.offsets, F, params_q.device)
+            return 2.0 * ones.to(torch.float32) - ttl
         return torch.stack([params_q[o0:o1].sum() for o0, o1 in zip(ctx.offsets[:-1], ctx.offsets[1:])])
 
     @staticmethod
@@ -344,7 +375,32 @@ class _LevelSums(Function):
         else:
             gr = torch.zeros(ctx.shape[0], device=g.device, dtype=g.dtype)
             gr[offs[0]:offs[-1]] = g[level]
-        return gr.unsqueeze(-1).expand(ctx.shape).contiguous(), None
+        return gr.unsqueeze(-1).expand(ctx.shape).contiguous(), None, None
+
+
+class _BernoulliBitsSum(Function):
+    """torch.sum(Bernoulli_entropy(x, p)) with its gradients in x and p as one kernel each way (`cnc_bernoulli_bits_fwd /
+    _bwd`): under autograd the same expression is ~12 elementwise launches forward and ~30 backward, four times per step."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        x, p = x.contiguous().float(), p.contiguous().float()
+        n = x.numel()
+        ctx.save_for_backward(x, p)
+        if n == 0:
+            return torch.zeros((), device=x.device)
+        parts = torch.empty(lib().cnc_bernoulli_bits_blocks(n), device=x.device)
+        check(lib().cnc_bernoulli_bits_fwd(ptr(x), ptr(p), n, ptr(parts), stream()))
+        return parts.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, p = ctx.saved_tensors
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gp = torch.empty_like(p) if ctx.needs_input_grad[1] else None
+        if x.numel() and (gx is not None or gp is not None):
+            check(lib().cnc_bernoulli_bits_bwd(ptr(x), ptr(p), ptr(g.contiguous().float()), x.numel(), ptr(gx), ptr(gp), stream()))
+        return gx, gp
 
 
 class Bernoulli_entropy(nn.Module):
@@ -663,12 +719,18 @@ class CNC_context_models(nn.Module):
         Pg = pos / ttl
         return Pg, pos * (-torch.log2(Pg)) + neg * (-torch.log2(1 - Pg)), ttl
 
+    def _bits_sum(self, x, p):
+        """torch.sum(self.entropy_model(x, p)) -- fused on CUDA (`fused_entropy = False`: the op-by-op expression)"""
+        if x.is_cuda and getattr(self, "fused_entropy", True) and x.shape == p.shape:
+            return _BernoulliBitsSum.apply(x, p)
+        return torch.sum(self.entropy_model(x, p))
+
     def level_entropies(self, params_q, offsets=None):
         """get_BiRF_wentropy_leveln for every level at once (same arithmetic, utils_bpp_acc.py:472-486): ([Pg_n], [bit_n])"""
         offsets = self.offs if offsets is None else offsets
         F = params_q.shape[-1]
         _, ttl = _level_const(offsets, F, params_q.device)
-        s = _LevelSums.apply(params_q, offsets)
+        s = _LevelSums.apply(params_q, offsets, bool(self.ste_binary))
         pos, neg = (ttl + s) / 2.0, (ttl - s) / 2.0
         Pg = pos / ttl
         bits = pos * (-torch.log2(Pg)) + neg * (-torch.log2(1 - Pg))
@@ -981,7 +1043,7 @@ class CNC_context_models(nn.Module):
                 else:
                     ttl_bit_sum = ttl_bit_sum + bit_n
             if means:   # one gather of the coded rows of the plane (one index backward instead of one per level)
-                plane_bits = torch.sum(self.entropy_model(pq[axis][torch.cat(rows_l), :], torch.cat(means, 0)))
+                plane_bits = self._bits_sum(_RowsGather.apply(pq[axis], torch.cat(rows_l)), torch.cat(means, 0))
                 ttl_bit_sum = ttl_bit_sum + (plane_bits * world if world > 1 else plane_bits)
             ttl_num_sum += pq[axis].numel()
 
@@ -1025,7 +1087,7 @@ class CNC_context_models(nn.Module):
                 val_l.append(self.unique_value_list[n][ent[a_:b_]] + self.offs[n])
             if pts_l and sum(p.shape[0] for p in pts_l):
                 pts, w, nl, cnt, rows3 = (torch.cat(t, 0) for t in (pts_l, w_l, n_l, cnt_l, val_l))
-                vals = pq["xyz"][rows3]
+                vals = _RowsGather.apply(pq["xyz"], rows3)      # (a window of distinct entries per level)
                 cs = torch.cat([torch.zeros(1, dtype=torch.int64, device=pts.device), torch.cumsum(cnt, 0)])
                 vbits, vbit_off = self._vertex_bits(Encoding_xyz, vx)
                 ctx_in = _Ctx3DGather.apply(Encoding_xyz.params, torch.stack(Pgs_3D), pts, nl, Encoding_xyz, vbits, vbit_off)
@@ -1035,7 +1097,7 @@ class CNC_context_models(nn.Module):
                 else:
                     mlp_out = m3(ctx_in)
                 mean = segment_sum.apply(mlp_out, cs, w, None)
-                bits = torch.sum(self.entropy_model(vals, mean))
+                bits = self._bits_sum(vals, mean)
                 ttl_bit_sum = ttl_bit_sum + bits / n_valid * self.ttl_hashparams_num_valid_levels
             ttl_num_sum += pq["xyz"].numel()
             return ttl_bit_sum / ttl_num_sum, float(ttl_bit_sum.detach()) / 8 / 1024 / 1024
@@ -1092,7 +1154,7 @@ class CNC_context_models(nn.Module):
             else:
                 mlp_out = self.context_model_3D(ctx_in)
             mean = segment_sum.apply(mlp_out, cs, w.contiguous(), None)
-            bits = torch.sum(self.entropy_model(vals, mean))
+            bits = self._bits_sum(vals, mean)
             ttl_bit_sum = ttl_bit_sum + bits / n_valid * self.ttl_hashparams_num_valid_levels
         ttl_num_sum += pq["xyz"].numel()
         return ttl_bit_sum / ttl_num_sum, float(ttl_bit_sum.detach()) / 8 / 1024 / 1024

@@ -109,6 +109,48 @@ static int run_bwd(const float *x, const float *W, const float *gy, float *gx, f
     return check_launch("lin8_bwd");
 }
 
+// Bernoulli_entropy (utils_bpp_acc.py:1002-1013) summed: bits = sum_i -log2(p_i) (1 + x_i)/2 - log2(1 - p_i) (1 - x_i)/2 with p
+// clamped to [1e-6, 1 - 1e-6]; block partials (summed by the caller in index order).  The backward writes d/dp (zero where the
+// clamp is active, like torch.clamp's) and d/dx = (log2(1 - p) - log2(p)) / 2, both times the upstream scalar.
+constexpr int EB = 256;
+__global__ void __launch_bounds__(EB) bern_fwd_kernel(const float *__restrict__ x, const float *__restrict__ p, int64_t n,
+                                                      float *__restrict__ parts) {
+    __shared__ float red[EB / 32];
+    float acc = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x; i < n; i += (int64_t)gridDim.x * EB) {
+        const float pc = fminf(fmaxf(__ldg(p + i), 1e-6f), 1.0f - 1e-6f), xv = __ldg(x + i);
+        const float a = __fmul_rn(-log2f(pc), __fdiv_rn(__fadd_rn(1.0f, xv), 2.0f));
+        const float b = __fmul_rn(-log2f(__fsub_rn(1.0f, pc)), __fdiv_rn(__fsub_rn(1.0f, xv), 2.0f));
+        acc = __fadd_rn(acc, __fadd_rn(a, b));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, d));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < EB / 32; w++) t = __fadd_rn(t, red[w]);
+        parts[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(EB) bern_bwd_kernel(const float *__restrict__ x, const float *__restrict__ p, const float *__restrict__ g,
+                                                      int64_t n, float *__restrict__ gx, float *__restrict__ gp) {
+    const float gs = __ldg(g);
+    for (int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x; i < n; i += (int64_t)gridDim.x * EB) {
+        const float pv = __ldg(p + i), xv = __ldg(x + i);
+        const float pc = fminf(fmaxf(pv, 1e-6f), 1.0f - 1e-6f), qc = __fsub_rn(1.0f, pc);
+        const float wa = __fdiv_rn(__fadd_rn(1.0f, xv), 2.0f), wb = __fdiv_rn(__fsub_rn(1.0f, xv), 2.0f);
+        if (gp) {
+            // d/dpc [-log2(pc) wa - log2(1 - pc) wb] = (-wa / pc + wb / (1 - pc)) / ln 2; clamp passes the gradient inside [lo, hi]
+            const bool inside = pv >= 1e-6f && pv <= 1.0f - 1e-6f;
+            const float d = __fmul_rn(__fadd_rn(__fdiv_rn(-wa, pc), __fdiv_rn(wb, qc)), 1.4426950408889634f);
+            gp[i] = inside ? __fmul_rn(gs, d) : 0.f;
+        }
+        if (gx) gx[i] = __fmul_rn(gs, __fmul_rn(0.5f, __fsub_rn(log2f(qc), log2f(pc))));
+    }
+}
+
 }  // namespace l8
 }  // namespace cnc
 
@@ -130,6 +172,24 @@ int cnc_lin8_fwd(const float *x, const float *W, const float *b, float *y, int64
         case 33: return l8::run_fwd<33>(x, W, b, y, N, s);
         default: set_error("lin8_fwd: K must be 9, 17, 25 or 33 (8 * context levels + 1)"); return CNC_ENOTSUP;
     }
+}
+
+int cnc_bernoulli_bits_blocks(int64_t n) {
+    const int64_t b = (n + l8::EB - 1) / l8::EB;
+    return (int)(b < 1 ? 1 : (b > 1184 ? 1184 : b));     // 148 SMs x 8 resident CTAs
+}
+
+int cnc_bernoulli_bits_fwd(const float *x, const float *p, int64_t n, float *parts, cnc_stream_t stream) {
+    if (!x || !p || !parts || n < 0) { set_error("bernoulli_bits_fwd: bad argument"); return CNC_EINVAL; }
+    l8::bern_fwd_kernel<<<cnc_bernoulli_bits_blocks(n), l8::EB, 0, static_cast<cudaStream_t>(stream)>>>(x, p, n, parts);
+    return check_launch("bernoulli_bits_fwd");
+}
+
+int cnc_bernoulli_bits_bwd(const float *x, const float *p, const float *g, int64_t n, float *gx, float *gp, cnc_stream_t stream) {
+    if (n == 0) return CNC_OK;
+    if (!x || !p || !g || !(gx || gp) || n < 0) { set_error("bernoulli_bits_bwd: bad argument"); return CNC_EINVAL; }
+    l8::bern_bwd_kernel<<<cnc_bernoulli_bits_blocks(n), l8::EB, 0, static_cast<cudaStream_t>(stream)>>>(x, p, g, n, gx, gp);
+    return check_launch("bernoulli_bits_bwd");
 }
 
 int cnc_lin8_bwd(const float *x, const float *W, const float *gy, float *gx, float *parts, int64_t N, int32_t K, cnc_stream_t stream) {

@@ -139,6 +139,21 @@ __global__ void adam_planes_kernel(float *__restrict__ p, const float *__restric
 static bool ok16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static bool ok4(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
 
+// set bits per level of a sign plane: block (c, l) covers a chunk of level l's bytes (levels are byte aligned: row counts are
+// multiples of 8).  The zeroth-order statistics of the rate term (+1 frequency per level, utils_bpp_acc.py:472-486) from
+// 5 MB of bits in one launch instead of one fp32 reduction over the level's slice per level.
+__global__ void __launch_bounds__(256) level_popcount_kernel(const uint8_t *__restrict__ bits, const int64_t *__restrict__ byte_offs,
+                                                             unsigned long long *__restrict__ out) {
+    const int l = blockIdx.y;
+    const int64_t b0 = byte_offs[l], b1 = byte_offs[l + 1];
+    unsigned long long acc = 0;
+    for (int64_t i = b0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < b1; i += (int64_t)gridDim.x * blockDim.x)
+        acc += (unsigned)__popc((unsigned)__ldg(bits + i));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out + l, acc);
+}
+
 }  // namespace cnc
 
 using namespace cnc;
@@ -168,6 +183,15 @@ int cnc_surrogate_fill(float *params, const uint8_t *sign_bits, const uint8_t *m
         params, reinterpret_cast<const uint32_t *>(sign_bits), reinterpret_cast<const uint32_t *>(mask_bits), n / 32, keep_lo / 32,
         keep_hi / 32);
     return check_launch("surrogate_fill");
+}
+
+int cnc_level_popcount(const uint8_t *sign_bits, const int64_t *byte_offsets, int32_t n_levels, int64_t *out, cnc_stream_t stream) {
+    if (n_levels <= 0) return CNC_OK;
+    if (!sign_bits || !byte_offsets || !out) { set_error("level_popcount: null pointer"); return CNC_EINVAL; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (cudaMemsetAsync(out, 0, sizeof(int64_t) * (size_t)n_levels, s) != cudaSuccess) { set_error("level_popcount: memset failed"); return CNC_ECUDA; }
+    level_popcount_kernel<<<dim3(64, (unsigned)n_levels), 256, 0, s>>>(sign_bits, byte_offsets, reinterpret_cast<unsigned long long *>(out));
+    return check_launch("level_popcount");
 }
 
 int cnc_adam_planes(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, uint8_t *sign_bits, uint8_t *mask_bits,

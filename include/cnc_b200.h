@@ -92,6 +92,12 @@ int cnc_sign_unpack(const uint8_t *bits, float *out, uint64_t n, cnc_stream_t st
  *   bwd: gx [N,K] (nullable) = gy W; parts [ceil(N / cnc_lin8_rows_per_block()), 8K + 8] = per-block partials of
  *   (dW [8,K] row-major | db [8]); the caller sums them over the blocks in index order.
  * ---------------------------------------------------------------------------------------- */
+/* sum of Bernoulli_entropy(x, p) (utils_bpp_acc.py:1002-1013) and its gradient, as the rate term of the loss uses it:
+ *   fwd: parts [cnc_bernoulli_bits_blocks(n)] = per-block partial sums of -log2(pc)(1+x)/2 - log2(1-pc)(1-x)/2, pc = clamp(p);
+ *   bwd: gx / gp (nullable) = *g (upstream scalar, device) times d/dx, d/dp (zero where the clamp is active). */
+int cnc_bernoulli_bits_blocks(int64_t n);
+int cnc_bernoulli_bits_fwd(const float *x, const float *p, int64_t n, float *parts, cnc_stream_t stream);
+int cnc_bernoulli_bits_bwd(const float *x, const float *p, const float *g, int64_t n, float *gx, float *gp, cnc_stream_t stream);
 int cnc_lin8_rows_per_block(void);
 int cnc_lin8_fwd(const float *x, const float *W, const float *b, float *y, int64_t N, int32_t K, cnc_stream_t stream);
 int cnc_lin8_bwd(const float *x, const float *W, const float *gy, float *gx, float *parts, int64_t N, int32_t K,
@@ -189,6 +195,9 @@ int cnc_keys_to_points(const uint64_t *keys, uint64_t n, uint32_t resolution, in
  *                         ste_window != 0: the gradient of a latent outside [-1, 1] is dropped first (the STE_binary
  *                         backward, ngp.py:33-39, for callers that hand over the unmasked table gradient).
  * ---------------------------------------------------------------------------------------- */
+/* set bits per level of a sign plane: out[l] = popcount of bytes [byte_offsets[l], byte_offsets[l+1]) -- the +1 count of a
+ * level of a binarised table (get_BiRF_wentropy_leveln, utils_bpp_acc.py:472-486) without an fp32 pass over the level */
+int cnc_level_popcount(const uint8_t *sign_bits, const int64_t *byte_offsets, int32_t n_levels, int64_t *out, cnc_stream_t stream);
 int cnc_ste_planes_pack(const float *params, uint8_t *sign_bits, uint8_t *mask_bits, uint64_t n, cnc_stream_t stream);
 int cnc_surrogate_fill(float *params, const uint8_t *sign_bits, const uint8_t *mask_bits, uint64_t n, uint64_t keep_lo,
                        uint64_t keep_hi, cnc_stream_t stream);

@@ -30,7 +30,8 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         if n not in ("cnc_version", "cnc_last_error", "cnc_field_blob_floats", "cnc_context3d_mlp_floats",
                      "cnc_wgrad_max_partials", "cnc_dgrad_blob_floats", "cnc_ctx_mlp_floats", "cnc_ctx_mlp_max_partials",
-                         "cnc_lin8_rows_per_block", "cnc_peer_handle_bytes", "cnc_peer_pad_bytes"):
+                         "cnc_lin8_rows_per_block", "cnc_peer_handle_bytes", "cnc_peer_pad_bytes",
+                         "cnc_bernoulli_bits_blocks"):
             assert n in _lib.SIGNATURES, n
     L.cnc_version.restype = ctypes.c_int
     assert L.cnc_version() >= 100

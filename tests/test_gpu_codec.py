@@ -505,3 +505,45 @@ def test_rate_term_shared_among_data_parallel_ranks(cuda):
     b2, _ = run(2, 4)
     assert np.isfinite([b1, b2]).all() and b1 != b2
     cm.set_data_parallel(0, 1)
+
+
+def test_rate_term_fused_pieces_match_the_op_by_op_expressions(cuda):
+    """the small-op chains of the rate term as single kernels: sum of Bernoulli_entropy (value and both gradients), gather of
+    distinct rows with a scatter backward, level sums of a +-1 table from its sign plane"""
+    from cnc_b200.context_models import Bernoulli_entropy, _BernoulliBitsSum, _LevelSums, _RowsGather
+
+    g = torch.Generator().manual_seed(2)
+    n = 70001
+    x = torch.where(torch.rand(n, 8, generator=g) < 0.5, -1.0, 1.0).to(cuda).requires_grad_(True)
+    p = torch.rand(n, 8, generator=g).to(cuda)
+    with torch.no_grad():
+        p[:50] = torch.tensor([0.0, 1.0, 1e-7, 1 - 1e-7, 1e-6, 1 - 1e-6, 0.5, 2.0], device=cuda)      # on and beyond the clamp
+    p.requires_grad_(True)
+    want = torch.sum(Bernoulli_entropy()(x, p)) * 0.37
+    want.backward()
+    gx, gp = x.grad.clone(), p.grad.clone()
+    x.grad = p.grad = None
+    got = _BernoulliBitsSum.apply(x, p) * 0.37
+    got.backward()
+    torch.testing.assert_close(got, want, rtol=2e-6, atol=0)
+    torch.testing.assert_close(x.grad, gx, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(p.grad, gp, rtol=1e-5, atol=1e-7)
+    # rows gather
+    table = torch.randn(5000, 8, generator=g).to(cuda).requires_grad_(True)
+    rows = torch.randperm(5000, generator=g)[:1234].to(cuda)
+    w = torch.randn(1234, 8, generator=g).to(cuda)
+    (table[rows] * w).sum().backward()
+    g0 = table.grad.clone()
+    table.grad = None
+    out = _RowsGather.apply(table, rows)
+    assert torch.equal(out, table[rows])
+    (out * w).sum().backward()
+    assert torch.equal(table.grad, g0)
+    # level sums
+    offs = [0, 8, 1000, 1008, 4000]
+    q = torch.where(torch.rand(4000, 8, generator=g) < 0.3, -1.0, 1.0).to(cuda).requires_grad_(True)
+    a = _LevelSums.apply(q, offs, True)
+    b = _LevelSums.apply(q, offs, False)
+    assert torch.equal(a, b)
+    (a * torch.arange(1, 5, device=cuda)).sum().backward()
+    assert torch.equal(q.grad[:8], torch.ones(8, 8, device=cuda)) and torch.equal(q.grad[1008:], torch.full((2992, 8), 4.0, device=cuda))
