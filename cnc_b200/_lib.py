@@ -50,7 +50,7 @@ SIGNATURES = {
     "cnc_vote_planes_fwd": [_vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _vp],
     "cnc_vote_planes_bwd": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _vp],
     "cnc_vote3_fwd": [_vp, _u32, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp],
-    "cnc_vote3_bwd": [_vp, _vp, _vp, _u32, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp],
+    "cnc_vote3_bwd": [_vp, _vp, _vp, _u32, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _i32, _vp],
     "cnc_query_mask": [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i64, _i32, _vp],
     "cnc_align_pack_fwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _vp],
     "cnc_align_pack_bwd": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp],

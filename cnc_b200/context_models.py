@@ -105,7 +105,7 @@ class _cnt_np_embed3(Function):
     by its closed form in the occupancy grid, the atomics by per-cell / per-row ownership."""
 
     @staticmethod
-    def forward(ctx, embeddings, vx, pts_by_row, seg, resolution, hashmap_size, axes=(0, 1, 2)):
+    def forward(ctx, embeddings, vx, pts_by_row, seg, resolution, hashmap_size, axes=(0, 1, 2), members_only=False):
         """-> one plane per entry of `axes` (0 = xy, 1 = xz, 2 = yz), in that order: a data-parallel rank builds (and
         differentiates) only the planes its share of the plane terms reads"""
         embeddings = embeddings.contiguous()
@@ -118,6 +118,7 @@ class _cnt_np_embed3(Function):
         ctx.save_for_backward(bits, vx, pts_by_row, seg, *sums)
         ctx.dims = [resolution, F, hashmap_size, tuple(embeddings.shape), tuple(axes)]
         ctx.set_materialize_grads(False)
+        ctx.members_only = members_only
         return tuple(outs[a] / sm for a, sm in zip(axes, sums))
 
     @staticmethod
@@ -125,15 +126,15 @@ class _cnt_np_embed3(Function):
         bits, vx, pts_by_row, seg, *sums = ctx.saved_tensors
         resolution, F, hashmap_size, shape, axes = ctx.dims
         if all(g is None for g in grads):
-            return None, None, None, None, None, None, None
+            return None, None, None, None, None, None, None, None
         g = torch.zeros(shape, device=bits.device)
         gs = [None, None, None]
         for a, gg, sm in zip(axes, grads, sums):
             if gg is not None:
                 gs[a] = (gg / sm).contiguous()     # 1 / sum folded in (:1012)
         check(lib().cnc_vote3_bwd(ptr(pts_by_row), ptr(seg), ptr(vx), vx.shape[-1], ptr(bits), resolution, F, hashmap_size,
-                                  ptr(gs[0]), ptr(gs[1]), ptr(gs[2]), ptr(g), stream()))
-        return g, None, None, None, None, None, None
+                                  ptr(gs[0]), ptr(gs[1]), ptr(gs[2]), ptr(g), int(ctx.members_only), stream()))
+        return g, None, None, None, None, None, None, None
 
 
 class align_and_pack(Function):
@@ -814,7 +815,7 @@ class CNC_context_models(nn.Module):
         else:
             pts_by_row, seg = None, None                       # (no backward: the forward reads the occupancy grid only)
         fr = _cnt_np_embed3.apply(embeddings_3D_q, vx, pts_by_row, seg, res, self.offs[-1] - self.offs[-2],
-                                  tuple(names.index(a) for a in axes))
+                                  tuple(names.index(a) for a in axes), pts_by_row is not None)
         out = {}
         for a, f in zip(axes, fr):
             f = nnf.pad(f[..., 0].permute(2, 0, 1).unsqueeze(0), pad=[1, 1, 1, 1]).squeeze(0).permute(1, 2, 0).contiguous()

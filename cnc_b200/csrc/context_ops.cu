@@ -222,6 +222,7 @@ struct Vote3BwdArgs {
     const float *grad[3];     // (d loss / d fraction) / vote sum, [s,s,8,2] per axis (xy, xz, yz)
     float *grad_table;        // [T,8]
     uint32_t Rb, res, T;
+    int32_t members_only;     // pts holds vote-list members only (built with the same predicate): no test per voxel
 };
 
 __global__ void __launch_bounds__(256) vote3_bwd_kernel(const Vote3BwdArgs a) {
@@ -235,19 +236,21 @@ __global__ void __launch_bounds__(256) vote3_bwd_kernel(const Vote3BwdArgs a) {
     for (int ch = 0; ch < 8; ch++) accp[ch] = accn[ch] = 0.f;
     for (int64_t i = v0 + lane; i < v1; i += 32) {
         const uint32_t c[3] = {(uint32_t)(int32_t)__ldg(a.pts + i * 3), (uint32_t)(int32_t)__ldg(a.pts + i * 3 + 1), (uint32_t)(int32_t)__ldg(a.pts + i * 3 + 2)};
-        bool ok = true;
-        uint32_t lo[3], hi[3];
+        if (!a.members_only) {
+            bool ok = true;
+            uint32_t lo[3], hi[3];
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-            ok = ok && c[d] != 0u && c[d] < a.res - 1u;   // gridencoder.cu:895-898
-            vote_cand(c[d], t, a.Rb, lo[d], hi[d]);
+            for (int d = 0; d < 3; d++) {
+                ok = ok && c[d] != 0u && c[d] < a.res - 1u;   // gridencoder.cu:895-898
+                vote_cand(c[d], t, a.Rb, lo[d], hi[d]);
+            }
+            if (!ok) continue;
+            bool member = false;
+            for (uint32_t o0 = lo[0]; o0 <= hi[0]; o0++)
+                for (uint32_t o1 = lo[1]; o1 <= hi[1]; o1++)
+                    for (uint32_t o2 = lo[2]; o2 <= hi[2]; o2++) member |= a.vxl[((size_t)o0 * a.Rb + o1) * a.Rb + o2] != 0;
+            if (!member) continue;
         }
-        if (!ok) continue;
-        bool member = false;
-        for (uint32_t o0 = lo[0]; o0 <= hi[0]; o0++)
-            for (uint32_t o1 = lo[1]; o1 <= hi[1]; o1++)
-                for (uint32_t o2 = lo[2]; o2 <= hi[2]; o2++) member |= a.vxl[((size_t)o0 * a.Rb + o1) * a.Rb + o2] != 0;
-        if (!member) continue;
 #pragma unroll
         for (int ax = 0; ax < 3; ax++) {
             if (a.grad[ax] == nullptr) continue;   // (warp-uniform: a plane nobody differentiated)
@@ -366,7 +369,7 @@ int cnc_vote3_fwd(const uint8_t *binary_vxl, uint32_t Rb, const uint8_t *sign_bi
 
 int cnc_vote3_bwd(const int16_t *pts_by_row, const int64_t *seg, const uint8_t *binary_vxl, uint32_t Rb, const uint8_t *sign_bits,
                   uint32_t resolution, uint32_t F, uint32_t hashmap_size, const float *grad_xy, const float *grad_xz,
-                  const float *grad_yz, float *grad_table, cnc_stream_t stream) {
+                  const float *grad_yz, float *grad_table, int32_t members_only, cnc_stream_t stream) {
     if (!pts_by_row || !seg || !binary_vxl || !sign_bits || !(grad_xy || grad_xz || grad_yz) || !grad_table) {
         set_error("vote3_bwd: null pointer");
         return CNC_EINVAL;
@@ -375,7 +378,7 @@ int cnc_vote3_bwd(const int16_t *pts_by_row, const int64_t *seg, const uint8_t *
         set_error("vote3_bwd: needs F == 8, Rb <= 128 and (resolution - 2) a multiple of Rb");
         return CNC_ENOTSUP;
     }
-    Vote3BwdArgs a{pts_by_row, seg, binary_vxl, sign_bits, {grad_xy, grad_xz, grad_yz}, grad_table, Rb, resolution, hashmap_size};
+    Vote3BwdArgs a{pts_by_row, seg, binary_vxl, sign_bits, {grad_xy, grad_xz, grad_yz}, grad_table, Rb, resolution, hashmap_size, members_only};
     vote3_bwd_kernel<<<div_up((uint64_t)hashmap_size * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return check_launch("vote3_bwd");
 }

@@ -263,6 +263,8 @@ int cnc_vote_planes_bwd(const int16_t *pts, const float *table, const float *out
  * divided by the cell's vote sum (the 1/sum of :1012, folded by the caller); grad_table [T,8] is overwritten.
  * F == 8, Rb <= 128.  *   A NULL output plane (forward) / NULL gradient plane (backward) skips that axis: a data-parallel rank builds only the
  *   planes its share of the plane terms reads.
+  *   members_only != 0: pts_by_row lists vote-list members only (cnc_level_pruned_keys mode 1): the per-voxel membership
+ *   test is skipped.
  */
 int cnc_vote3_fwd(const uint8_t *binary_vxl, uint32_t Rb, const uint8_t *sign_bits, uint32_t resolution,
                   uint32_t F, uint32_t hashmap_size, float *out_xy, float *out_xz, float *out_yz,
@@ -270,7 +272,7 @@ int cnc_vote3_fwd(const uint8_t *binary_vxl, uint32_t Rb, const uint8_t *sign_bi
 int cnc_vote3_bwd(const int16_t *pts_by_row, const int64_t *seg, const uint8_t *binary_vxl, uint32_t Rb,
                   const uint8_t *sign_bits, uint32_t resolution, uint32_t F, uint32_t hashmap_size,
                   const float *grad_xy, const float *grad_xz, const float *grad_yz, float *grad_table,
-                  cnc_stream_t stream);
+                  int32_t members_only, cnc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Occupancy query of voxels.
