@@ -731,7 +731,7 @@ class CNC_context_models(nn.Module):
         offsets = self.offs if offsets is None else offsets
         F = params_q.shape[-1]
         _, ttl = _level_const(offsets, F, params_q.device)
-        s = _LevelSums.apply(params_q, offsets, bool(self.ste_binary))
+        s = _LevelSums.apply(params_q, offsets, bool(getattr(self, "ste_binary", False)))
         pos, neg = (ttl + s) / 2.0, (ttl - s) / 2.0
         Pg = pos / ttl
         bits = pos * (-torch.log2(Pg)) + neg * (-torch.log2(1 - Pg))
