@@ -620,6 +620,17 @@ def train_bench(arm, rank, world, steps, field):
         out["with_rate_term"] = {"what": "same step + lambda * bits-per-parameter (forward_binary_vxl_mixPg_3D2D, 150 000 sampled "
                                          "entries, dimension-wise context) and its backward", "lambda": 1e-3,
                                  "ms_per_step": e0.elapsed_time(e1) / steps}
+        if ours:     # the same with the rate term on a side stream beside the render path (TrainStep.overlap_rate_term)
+            ts2.overlap_rate_term = True
+            call(ts2)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                call(ts2)
+            e1.record()
+            torch.cuda.synchronize()
+            out["with_rate_term"]["two_streams_ms"] = e0.elapsed_time(e1) / steps
+            ts2.overlap_rate_term = False
         # the rate term alone (forward + backward), the part of the step utils_bpp_acc.py:533-706 owns
         mb = field.mlp_base
         encs = (mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz)

@@ -1011,8 +1011,10 @@ class CNC_context_models(nn.Module):
         self._dp_snl = (snl, int(sum(int(snl[n]) for n in coded)))
 
     def forward_binary_vxl_mixPg_3D2D(self, Encoding_xyz, Encoding_xy, Encoding_xz, Encoding_yz, binary_vxl=None,
-                                      verbose=False, sample_num=None, step=0):
-        """Rate term of the training loss: (bits per parameter, MB).  utils_bpp_acc.py:533-706"""
+                                      verbose=False, sample_num=None, step=0, mb_as_tensor=False):
+        """Rate term of the training loss: (bits per parameter, MB).  utils_bpp_acc.py:533-706
+        `mb_as_tensor` (not in the reference): the MB figure stays a device tensor -- as a Python float it is a host read that
+        waits for the whole forward."""
         pq = {k: self.get_STE_params(E) for k, E in (("xy", Encoding_xy), ("xz", Encoding_xz), ("yz", Encoding_yz), ("xyz", Encoding_xyz))}
         refresh = step % self.step_update == 0 or self.idx_coords2_tmp is None
         if refresh:   # the reference caches the voxel list for step_update steps (:541-543): keep the occupancy it stands for
@@ -1101,7 +1103,8 @@ class CNC_context_models(nn.Module):
                 bits = self._bits_sum(vals, mean)
                 ttl_bit_sum = ttl_bit_sum + bits / n_valid * self.ttl_hashparams_num_valid_levels
             ttl_num_sum += pq["xyz"].numel()
-            return ttl_bit_sum / ttl_num_sum, float(ttl_bit_sum.detach()) / 8 / 1024 / 1024
+            mb = ttl_bit_sum.detach() / 8 / 1024 / 1024
+            return ttl_bit_sum / ttl_num_sum, (mb if mb_as_tensor else float(mb))
         self._ensure_full_tables()
         pts_l, ptsn_l, Pg_l, n_l, cnt_l, val_l = [], [], [], [], [], []
         for n in range(self.n_levels):
@@ -1158,7 +1161,8 @@ class CNC_context_models(nn.Module):
             bits = self._bits_sum(vals, mean)
             ttl_bit_sum = ttl_bit_sum + bits / n_valid * self.ttl_hashparams_num_valid_levels
         ttl_num_sum += pq["xyz"].numel()
-        return ttl_bit_sum / ttl_num_sum, float(ttl_bit_sum.detach()) / 8 / 1024 / 1024
+        mb = ttl_bit_sum.detach() / 8 / 1024 / 1024
+        return ttl_bit_sum / ttl_num_sum, (mb if mb_as_tensor else float(mb))
 
     # ------------------------------------------------------------------------------------------ encode
     @torch.no_grad()

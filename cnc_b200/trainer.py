@@ -29,7 +29,7 @@ class TrainStep:
     def __init__(self, radiance_field, estimator, context_model=None, lmbda: float = 0.0, lr: float = 6e-3,
                  render_step_size: float = 5e-3, target_sample_batch_size: int = 1 << 18, bucket_bytes: int = 32 << 20,
                  weight_decay: float = 2e-6, occ_refresh_every: int = 16, shard_tables: bool = True, exchange: str = "auto",
-                 data_parallel: bool = True, sync_initial_state: bool = True):
+                 data_parallel: bool = True, sync_initial_state: bool = True, overlap_rate_term: bool = False):
         self.field, self.estimator, self.cm, self.lmbda = radiance_field, estimator, context_model, lmbda
         if dist.is_initialized() and data_parallel and dist.get_world_size() > 1 and sync_initial_state:
             # replicas start from rank 0's parameters, occupancy and context models (whatever the ranks' RNG did before)
@@ -63,6 +63,8 @@ class TrainStep:
         self.world = dist.get_world_size() if (dist.is_initialized() and data_parallel) else 1
         self.step_id = 0
         self._premarch = None
+        self._rate_stream = None
+        self.overlap_rate_term = overlap_rate_term
         if context_model is not None and hasattr(context_model, "set_data_parallel"):
             # the rate term is shared among the ranks: each samples 1/N of the entries and evaluates its share of the plane terms
             context_model.set_data_parallel(dist.get_rank() if self.world > 1 else 0, self.world)
@@ -131,6 +133,12 @@ class TrainStep:
         vote.synchronize()
         return int(self._vote_host[0]) > 0
 
+    def _rate_term(self):
+        mb = self.field.mlp_base
+        bpp, _ = self.cm.forward_binary_vxl_mixPg_3D2D(mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz,
+                                                       self.estimator.binaries, step=self.step_id, mb_as_tensor=True)
+        return bpp
+
     def _pick_next(self, next_rays, n_samples: int, refresh_occupancy: bool):
         """the batch whose occupancy march may run ahead (nerfacc.Premarch), and the point of the stream from which it may.
         Not before a step that refreshes the grid, and not with a rate term (its random entry sample would be drawn after
@@ -175,6 +183,19 @@ class TrainStep:
             if self.world > 1 and self.step_id % self.occ_every == 0:
                 # each rank drew its own random cell samples: rank 0's grid is everybody's grid
                 broadcast_module_buffers(self.estimator, ["occs", "binaries"], src=0)
+        # overlap_rate_term (off by default): the rate term does not depend on the rays, so its forward can be issued first, on
+        # a side stream, and its small kernels (and, in backward, the nodes autograd runs on that same stream) share the device
+        # with the render path's few large ones.  Measured: 13.8 instead of 14.0 ms per step -- the step is bound by the rate
+        # term's own chain of kernels, not by the 3.7 ms beside it -- at the price of cross-stream gradient accumulation.
+        bpp = None
+        with_rate = self.cm is not None and self.lmbda > 0
+        if with_rate and self.overlap_rate_term and pixels.is_cuda:
+            cur = torch.cuda.current_stream(pixels.device)
+            if self._rate_stream is None:
+                self._rate_stream = torch.cuda.Stream(pixels.device)
+            self._rate_stream.wait_stream(cur)
+            with torch.cuda.stream(self._rate_stream):
+                bpp = self._rate_term()
         rgb, acc, depth, n_samples = render_image_with_occgrid(self.field, self.estimator, rays, render_step_size=self.render_step_size,
                                                                render_bkgd=render_bkgd, premarch=self._premarch)
         if self._premarch is not None:
@@ -184,15 +205,17 @@ class TrainStep:
         # vote travels while this rank goes on (a rank without samples contributes zero gradients to the collectives, which
         # every rank issues in the same order either way) and is read just before the update is applied.
         vote = self._vote_async(n_samples, pixels.device)
+        if bpp is not None:
+            torch.cuda.current_stream(pixels.device).wait_stream(self._rate_stream)
+            bpp.record_stream(torch.cuda.current_stream(pixels.device))
         if self.world == 1 and n_samples == 0:
             self._march_ahead(picked)
             self.step_id += 1
             return torch.zeros((), device=pixels.device), n_samples
         loss = F.mse_loss(rgb, pixels)   # train...:346
-        if self.cm is not None and self.lmbda > 0:
-            mb = self.field.mlp_base
-            bpp, _ = self.cm.forward_binary_vxl_mixPg_3D2D(mb.encoding_xyz, mb.encoding_xy, mb.encoding_xz, mb.encoding_yz,
-                                                           self.estimator.binaries, step=self.step_id)
+        if with_rate:
+            if bpp is None:
+                bpp = self._rate_term()
             loss = loss + self.lmbda * bpp
         self.optimizer.zero_grad(set_to_none=True)
         if self.table_opt is not None:
