@@ -192,19 +192,27 @@ vote3_fwd_kernel(const uint8_t *__restrict__ vxl, uint32_t Rb, const uint8_t *__
                 if (col[(size_t)ow * stride[dw]]) M[ow >> 5] |= 1u << (ow & 31u);
         }
     uint32_t pos[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, cnt = 0u;
-    if ((M[0] | M[1] | M[2] | M[3]) != 0u) {
-        for (uint32_t w = 1u; w <= s; w++) {
-            uint32_t wlo, whi;
-            vote_cand(w, t, Rb, wlo, whi);
-            bool member = false;
-            for (uint32_t ow = wlo; ow <= whi; ow++) member |= ((M[ow >> 5] >> (ow & 31u)) & 1u) != 0u;
-            if (!member) continue;
-            uint32_t c[3];
-            c[du] = u; c[dv] = v; c[dw] = w;
-            const uint32_t sb = __ldg(bits + grid_row<3>(c, T, res));
+    // members along w: an occupied column cell o covers w in [o t, o t + t + 1] (the inverse of vote_cand); walking the set
+    // bits of M visits exactly those w, in ascending order and once each, instead of testing all s positions
+    uint32_t w_done = 0u;
 #pragma unroll
-            for (int ch = 0; ch < 8; ch++) pos[ch] += (sb >> ch) & 1u;
-            cnt++;
+    for (int word = 0; word < 4; word++) {
+        uint32_t mbits = M[word];
+        while (mbits) {
+            const uint32_t o = (uint32_t)word * 32u + (uint32_t)__ffs((int)mbits) - 1u;
+            mbits &= mbits - 1u;
+            uint32_t w0 = o * t, w1 = o * t + t + 1u;
+            if (w0 <= w_done) w0 = w_done + 1u;
+            if (w1 > s) w1 = s;
+            for (uint32_t w = w0; w <= w1; w++) {
+                uint32_t c[3];
+                c[du] = u; c[dv] = v; c[dw] = w;
+                const uint32_t sb = __ldg(bits + grid_row<3>(c, T, res));
+#pragma unroll
+                for (int ch = 0; ch < 8; ch++) pos[ch] += (sb >> ch) & 1u;
+                cnt++;
+            }
+            if (w1 > w_done) w_done = w1;
         }
     }
     float *out = axis == 0 ? out_xy : (axis == 1 ? out_xz : out_yz);
