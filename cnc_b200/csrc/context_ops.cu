@@ -293,6 +293,40 @@ __global__ void __launch_bounds__(256) vote3_bwd_kernel(const Vote3BwdArgs a) {
     }
 }
 
+// The same reduction for a list that holds vote-list members only (no test per voxel): FOUR lanes per voxel, lane q loading the
+// q-th 16 bytes of the voxel's 64-byte cell record of each plane -- a warp instruction then touches 16 sectors instead of 32 (the
+// kernel is bound by L1 wavefronts, not by DRAM: the planes are L2 resident) -- and accumulating only the half (+1 votes or -1
+// votes) that the row's own sign selects, for its two channels.
+__global__ void __launch_bounds__(256) vote3_bwd_members_kernel(const Vote3BwdArgs a) {
+    const uint32_t lane = threadIdx.x & 31u, q = lane & 3u, sub = lane >> 2;
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= a.T) return;
+    const uint32_t s = a.res - 2u;
+    const int64_t v0 = __ldg(a.seg + row), v1 = __ldg(a.seg + row + 1);
+    const uint32_t sb = __ldg(a.bits + row);
+    const bool p0 = (sb >> (2u * q)) & 1u, p1 = (sb >> (2u * q + 1u)) & 1u;
+    float acc0 = 0.f, acc1 = 0.f;
+    for (int64_t i = v0 + sub; i < v1; i += 8) {
+        const uint32_t c[3] = {(uint32_t)(int32_t)__ldg(a.pts + i * 3), (uint32_t)(int32_t)__ldg(a.pts + i * 3 + 1), (uint32_t)(int32_t)__ldg(a.pts + i * 3 + 2)};
+#pragma unroll
+        for (int ax = 0; ax < 3; ax++) {
+            if (a.grad[ax] == nullptr) continue;
+            const uint32_t u = ax == 2 ? c[1] : c[0], v = ax == 0 ? c[1] : c[2];
+            const size_t cell = (size_t)(u - 1u) * s + (v - 1u);
+            const float4 g = __ldg(reinterpret_cast<const float4 *>(a.grad[ax] + cell * 16u) + q);   // (pos, neg) of channels 2q, 2q+1
+            acc0 = __fadd_rn(acc0, p0 ? g.x : g.y);
+            acc1 = __fadd_rn(acc1, p1 ? g.z : g.w);
+        }
+    }
+#pragma unroll
+    for (int sh = 4; sh < 32; sh <<= 1) {
+        acc0 = __fadd_rn(acc0, __shfl_xor_sync(0xFFFFFFFFu, acc0, sh));
+        acc1 = __fadd_rn(acc1, __shfl_xor_sync(0xFFFFFFFFu, acc1, sh));
+    }
+    if (sub == 0)   // d fraction / d vote carries the sign of the row's own value
+        *reinterpret_cast<float2 *>(a.grad_table + (size_t)row * 8u + 2u * q) = make_float2(p0 ? acc0 : -acc0, p1 ? acc1 : -acc1);
+}
+
 static inline uint32_t gs_blocks(int64_t total) {
     const int64_t b = (total + 255) / 256;
     const int64_t cap = 148ll * 32;
@@ -387,7 +421,10 @@ int cnc_vote3_bwd(const int16_t *pts_by_row, const int64_t *seg, const uint8_t *
         return CNC_ENOTSUP;
     }
     Vote3BwdArgs a{pts_by_row, seg, binary_vxl, sign_bits, {grad_xy, grad_xz, grad_yz}, grad_table, Rb, resolution, hashmap_size, members_only};
-    vote3_bwd_kernel<<<div_up((uint64_t)hashmap_size * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    if (members_only)
+        vote3_bwd_members_kernel<<<div_up((uint64_t)hashmap_size * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    else
+        vote3_bwd_kernel<<<div_up((uint64_t)hashmap_size * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return check_launch("vote3_bwd");
 }
 
