@@ -43,6 +43,8 @@ SIGNATURES = {
     "cnc_keys_to_points": [_vp, _u64, _u32, _vp, _vp, _vp],
     "cnc_bernoulli_bits_fwd": [_vp, _vp, _i64, _vp, _vp],
     "cnc_bernoulli_bits_bwd": [_vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "cnc_rows8_gather": [_vp, _vp, _i64, _vp, _vp],
+    "cnc_rows8_scatter": [_vp, _vp, _i64, _vp, _vp],
     "cnc_level_popcount": [_vp, _vp, _i32, _vp, _vp],
     "cnc_ste_planes_pack": [_vp, _vp, _vp, _u64, _vp],
     "cnc_surrogate_fill": [_vp, _vp, _vp, _u64, _u64, _u64, _vp],

@@ -336,13 +336,22 @@ class _RowsGather(Function):
     def forward(ctx, table, rows):
         ctx.save_for_backward(rows)
         ctx.shape = tuple(table.shape)
+        ctx.fast = table.is_cuda and table.dim() == 2 and table.shape[1] == 8 and table.dtype == torch.float32 and table.is_contiguous()
+        if ctx.fast:
+            rows = rows.contiguous()
+            out = torch.empty(rows.numel(), 8, device=table.device)
+            check(lib().cnc_rows8_gather(ptr(table), ptr(rows), rows.numel(), ptr(out), stream()))
+            return out
         return table.index_select(0, rows)
 
     @staticmethod
     def backward(ctx, g):
         (rows,) = ctx.saved_tensors
         out = torch.zeros(ctx.shape, device=g.device, dtype=g.dtype)
-        out.index_copy_(0, rows, g.contiguous())
+        if ctx.fast and g.dtype == torch.float32:
+            check(lib().cnc_rows8_scatter(ptr(g.contiguous()), ptr(rows.contiguous()), rows.numel(), ptr(out), stream()))
+        else:
+            out.index_copy_(0, rows, g.contiguous())
         return out, None
 
 

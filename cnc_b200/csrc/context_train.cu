@@ -157,73 +157,107 @@ __device__ __forceinline__ bool corners2_of(const Args2 &a, int64_t v, int slot,
     return make_corners<2>(xi, lc, (uint32_t)a.Rb, a.vxl2, cs);
 }
 
-__global__ void __launch_bounds__(256) ctx2d_gather_fwd_kernel(const Args2 a) {
-    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= a.N) return;
-    const int slot = blockIdx.y;
-    LevelConst lc;
-    Corners<2> cs;
-    float acc[8];
+// thread = vertex, all slots in turn; the block's [256, K] tile of x (K odd: conflict-free rows) goes through shared memory, so
+// that the global side is one contiguous, fully coalesced copy -- with a (vertex, slot) thread writing its 8 floats at a row
+// stride of K the stores touched 8 sectors per thread where 2 hold the data, and the kernel was bound by exactly that.
+__global__ void __launch_bounds__(256) ctx2d_gather_fwd_kernel(const Args2 a, int slots) {
+    extern __shared__ float tile[];
+    const int64_t row0 = (int64_t)blockIdx.x * blockDim.x, v = row0 + threadIdx.x;
+    float *mine = tile + (size_t)threadIdx.x * a.K;
+    for (int slot = 0; slot < slots; slot++) {
+        LevelConst lc;
+        Corners<2> cs;
+        float acc[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = 0.f;
-    if (corners2_of(a, v, slot, lc, cs)) {
-        if (slot < a.c) {
+        for (int k = 0; k < 8; k++) acc[k] = 0.f;
+        if (v < a.N && corners2_of(a, v, slot, lc, cs)) {
+            if (slot < a.c) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                if ((cs.valid >> i) & 1u) {
-                    const uint32_t sb = __ldg(a.sign_bits + (uint64_t)lc.base_row + cs.row[i]);
-                    const float ww = __fmul_rn(cs.w[i], cs.wn_re);
+                for (int i = 0; i < 4; i++) {
+                    if ((cs.valid >> i) & 1u) {
+                        const uint32_t sb = __ldg(a.sign_bits + (uint64_t)lc.base_row + cs.row[i]);
+                        const float ww = __fmul_rn(cs.w[i], cs.wn_re);
 #pragma unroll
-                    for (int k = 0; k < 8; k++) acc[k] = __fadd_rn(acc[k], ((sb >> k) & 1u) ? ww : -ww);
+                        for (int k = 0; k < 8; k++) acc[k] = __fadd_rn(acc[k], ((sb >> k) & 1u) ? ww : -ww);
+                    }
                 }
-            }
-        } else {
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                if ((cs.valid >> i) & 1u) {
-                    const float4 *r = reinterpret_cast<const float4 *>(a.frac + (size_t)cs.row[i] * 8);
-                    const float4 r0 = __ldg(r), r1 = __ldg(r + 1);
-                    const float t[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-                    const float ww = __fmul_rn(cs.w[i], cs.wn_re);
+                for (int i = 0; i < 4; i++) {
+                    if ((cs.valid >> i) & 1u) {
+                        const float4 *r = reinterpret_cast<const float4 *>(a.frac + (size_t)cs.row[i] * 8);
+                        const float4 r0 = __ldg(r), r1 = __ldg(r + 1);
+                        const float t[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                        const float ww = __fmul_rn(cs.w[i], cs.wn_re);
 #pragma unroll
-                    for (int k = 0; k < 8; k++) acc[k] = __fmaf_rn(ww, t[k], acc[k]);   // gridencoder.cu:301
+                        for (int k = 0; k < 8; k++) acc[k] = __fmaf_rn(ww, t[k], acc[k]);   // gridencoder.cu:301
+                    }
                 }
             }
         }
-    }
-    float *o = a.x + v * a.K + slot * 8;
 #pragma unroll
-    for (int k = 0; k < 8; k++) o[k] = acc[k];
-    if (slot == 0) a.x[v * a.K + a.K - 1] = __ldg(a.Pg);
+        for (int k = 0; k < 8; k++) mine[slot * 8 + k] = acc[k];
+    }
+    mine[a.K - 1] = __ldg(a.Pg);
+    __syncthreads();
+    const int64_t rows = a.N - row0 < (int64_t)blockDim.x ? a.N - row0 : (int64_t)blockDim.x;
+    float *dst = a.x + row0 * a.K;
+    for (int64_t e = threadIdx.x; e < rows * a.K; e += blockDim.x) dst[e] = tile[e];
 }
 
-__global__ void __launch_bounds__(256) ctx2d_gather_bwd_kernel(const Args2 a) {
-    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int slot = blockIdx.y;
-    if (slot == 0) {
-        float g = v < a.N ? __ldg(a.gx + v * a.K + a.K - 1) : 0.f;
+__global__ void __launch_bounds__(256) ctx2d_gather_bwd_kernel(const Args2 a, int slots) {
+    extern __shared__ float tile[];
+    const int64_t row0 = (int64_t)blockIdx.x * blockDim.x, v = row0 + threadIdx.x;
+    const int64_t rows = a.N - row0 < (int64_t)blockDim.x ? a.N - row0 : (int64_t)blockDim.x;
+    const float *src = a.gx + row0 * a.K;
+    for (int64_t e = threadIdx.x; e < rows * a.K; e += blockDim.x) tile[e] = __ldg(src + e);
+    __syncthreads();
+    const float *mine = tile + (size_t)threadIdx.x * a.K;
+    {
+        float g = v < a.N ? mine[a.K - 1] : 0.f;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) g = __fadd_rn(g, __shfl_xor_sync(0xffffffffu, g, d));
         if ((threadIdx.x & 31) == 0) atomicAdd(a.g_pg, g);
     }
     if (v >= a.N) return;
-    LevelConst lc;
-    Corners<2> cs;
-    if (!corners2_of(a, v, slot, lc, cs)) return;
-    float g[8];
-    const float *gi = a.gx + v * a.K + slot * 8;
+    for (int slot = 0; slot < slots; slot++) {
+        LevelConst lc;
+        Corners<2> cs;
+        if (!corners2_of(a, v, slot, lc, cs)) continue;
+        float g[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) g[k] = __ldg(gi + k);
-    float *gt = slot < a.c ? a.grad_table + (size_t)lc.base_row * 8 : a.grad_frac;
+        for (int k = 0; k < 8; k++) g[k] = mine[slot * 8 + k];
+        float *gt = slot < a.c ? a.grad_table + (size_t)lc.base_row * 8 : a.grad_frac;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        if ((cs.valid >> i) & 1u) {
-            const float ww = __fmul_rn(cs.w[i], cs.wn_re);
-            float4 *p = reinterpret_cast<float4 *>(gt + (size_t)cs.row[i] * 8);
-            atomicAdd(p, make_float4(__fmul_rn(ww, g[0]), __fmul_rn(ww, g[1]), __fmul_rn(ww, g[2]), __fmul_rn(ww, g[3])));
-            atomicAdd(p + 1, make_float4(__fmul_rn(ww, g[4]), __fmul_rn(ww, g[5]), __fmul_rn(ww, g[6]), __fmul_rn(ww, g[7])));
+        for (int i = 0; i < 4; i++) {
+            if ((cs.valid >> i) & 1u) {
+                const float ww = __fmul_rn(cs.w[i], cs.wn_re);
+                float4 *p = reinterpret_cast<float4 *>(gt + (size_t)cs.row[i] * 8);
+                atomicAdd(p, make_float4(__fmul_rn(ww, g[0]), __fmul_rn(ww, g[1]), __fmul_rn(ww, g[2]), __fmul_rn(ww, g[3])));
+                atomicAdd(p + 1, make_float4(__fmul_rn(ww, g[4]), __fmul_rn(ww, g[5]), __fmul_rn(ww, g[6]), __fmul_rn(ww, g[7])));
+            }
         }
     }
+}
+
+// table[rows[i]] -> out[i] and back (rows of 8 floats = one 32-byte sector; torch's index_select runs this at 160 GB/s)
+__global__ void __launch_bounds__(256) rows8_gather_kernel(const float *__restrict__ table, const int64_t *__restrict__ rows, int64_t M,
+                                                           float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const float4 *r = reinterpret_cast<const float4 *>(table + rows[i] * 8);
+    float4 *o = reinterpret_cast<float4 *>(out + i * 8);
+    o[0] = __ldg(r);
+    o[1] = __ldg(r + 1);
+}
+__global__ void __launch_bounds__(256) rows8_scatter_kernel(const float *__restrict__ g, const int64_t *__restrict__ rows, int64_t M,
+                                                            float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const float4 *r = reinterpret_cast<const float4 *>(g + i * 8);
+    float4 *o = reinterpret_cast<float4 *>(out + rows[i] * 8);
+    o[0] = __ldg(r);
+    o[1] = __ldg(r + 1);
 }
 
 }  // namespace ct
@@ -274,7 +308,7 @@ int cnc_ctx2d_gather_fwd(const float *pts, int64_t N, const uint8_t *sign_bits, 
     if (frac && (reinterpret_cast<uintptr_t>(frac) & 15u)) { set_error("ctx2d_gather_fwd: frac must be 16-byte aligned"); return CNC_EINVAL; }
     ct::Args2 a{pts, sign_bits, offsets, resolutions, binary_vxl_2D, frac, Pg, x, nullptr, nullptr, nullptr, nullptr, N, level, n_ctx_levels,
                 8 * slots + 1, Rb, res_frac};
-    ct::ctx2d_gather_fwd_kernel<<<dim3(div_up((uint64_t)N, 256), slots), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    ct::ctx2d_gather_fwd_kernel<<<div_up((uint64_t)N, 256), 256, 256 * a.K * sizeof(float), static_cast<cudaStream_t>(stream)>>>(a, slots);
     return check_launch("ctx2d_gather_fwd");
 }
 
@@ -293,8 +327,28 @@ int cnc_ctx2d_gather_bwd(const float *pts, int64_t N, const int32_t *offsets, co
     }
     ct::Args2 a{pts, nullptr, offsets, resolutions, binary_vxl_2D, nullptr, nullptr, nullptr, gx, grad_table, grad_frac, grad_pg, N, level,
                 n_ctx_levels, 8 * slots + 1, Rb, res_frac};
-    ct::ctx2d_gather_bwd_kernel<<<dim3(div_up((uint64_t)N, 256), slots), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    ct::ctx2d_gather_bwd_kernel<<<div_up((uint64_t)N, 256), 256, 256 * a.K * sizeof(float), static_cast<cudaStream_t>(stream)>>>(a, slots);
     return check_launch("ctx2d_gather_bwd");
+}
+
+int cnc_rows8_gather(const float *table, const int64_t *rows, int64_t M, float *out, cnc_stream_t stream) {
+    if (M == 0) return CNC_OK;
+    if (!table || !rows || !out || ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) & 15u)) {
+        set_error("rows8_gather: null or misaligned pointer");
+        return CNC_EINVAL;
+    }
+    ct::rows8_gather_kernel<<<div_up((uint64_t)M, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(table, rows, M, out);
+    return check_launch("rows8_gather");
+}
+
+int cnc_rows8_scatter(const float *grad, const int64_t *rows, int64_t M, float *out, cnc_stream_t stream) {
+    if (M == 0) return CNC_OK;
+    if (!grad || !rows || !out || ((reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(out)) & 15u)) {
+        set_error("rows8_scatter: null or misaligned pointer");
+        return CNC_EINVAL;
+    }
+    ct::rows8_scatter_kernel<<<div_up((uint64_t)M, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(grad, rows, M, out);
+    return check_launch("rows8_scatter");
 }
 
 }  // extern "C"

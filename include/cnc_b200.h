@@ -96,6 +96,10 @@ int cnc_sign_unpack(const uint8_t *bits, float *out, uint64_t n, cnc_stream_t st
  *   fwd: parts [cnc_bernoulli_bits_blocks(n)] = per-block partial sums of -log2(pc)(1+x)/2 - log2(1-pc)(1-x)/2, pc = clamp(p);
  *   bwd: gx / gp (nullable) = *g (upstream scalar, device) times d/dx, d/dp (zero where the clamp is active). */
 int cnc_bernoulli_bits_blocks(int64_t n);
+/* rows of 8 floats: out[i] = table[rows[i]] / out[rows[i]] = grad[i] (distinct rows; the caller zeroes `out` of the scatter):
+ * `params_q[unique_value_list + offset]` of utils_bpp_acc.py:560,690 and its backward */
+int cnc_rows8_gather(const float *table, const int64_t *rows, int64_t M, float *out, cnc_stream_t stream);
+int cnc_rows8_scatter(const float *grad, const int64_t *rows, int64_t M, float *out, cnc_stream_t stream);
 int cnc_bernoulli_bits_fwd(const float *x, const float *p, int64_t n, float *parts, cnc_stream_t stream);
 int cnc_bernoulli_bits_bwd(const float *x, const float *p, const float *g, int64_t n, float *gx, float *gp, cnc_stream_t stream);
 int cnc_lin8_rows_per_block(void);
