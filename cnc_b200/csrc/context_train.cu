@@ -219,22 +219,49 @@ __global__ void __launch_bounds__(256) ctx2d_gather_bwd_kernel(const Args2 a, in
         for (int d = 16; d > 0; d >>= 1) g = __fadd_rn(g, __shfl_xor_sync(0xffffffffu, g, d));
         if ((threadIdx.x & 31) == 0) atomicAdd(a.g_pg, g);
     }
-    if (v >= a.N) return;
+    const bool inside = v < a.N;
+    const uint32_t lane = threadIdx.x & 31u;
     for (int slot = 0; slot < slots; slot++) {
         LevelConst lc;
         Corners<2> cs;
-        if (!corners2_of(a, v, slot, lc, cs)) continue;
+        const bool ok = corners2_of(a, inside ? v : a.N - 1, slot, lc, cs) && inside;
         float g[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) g[k] = mine[slot * 8 + k];
+        for (int k = 0; k < 8; k++) g[k] = inside ? mine[slot * 8 + k] : 0.f;
         float *gt = slot < a.c ? a.grad_table + (size_t)lc.base_row * 8 : a.grad_frac;
+        // the coarser plane levels: neighbouring vertices of the fine level (= neighbouring lanes) share their corners, and a
+        // few thousand rows would take every atomic -- contributions are summed over runs of lanes with the same row first
+        // (the segmented shuffle reduction of K2, grid_encode.cu); the fraction plane has the fine level's own resolution
+        const bool agg = slot < a.c;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            if ((cs.valid >> i) & 1u) {
-                const float ww = __fmul_rn(cs.w[i], cs.wn_re);
+            const bool on = ok && ((cs.valid >> i) & 1u);
+            const float ww = on ? __fmul_rn(cs.w[i], cs.wn_re) : 0.f;
+            float w8[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) w8[k] = __fmul_rn(ww, g[k]);
+            bool head = on;
+            if (agg) {
+                const uint32_t key = on ? cs.row[i] : 0xFFFFFFFFu;
+                const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+                const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+                const uint32_t start = 31u - (uint32_t)__clz(heads & (0xffffffffu >> (31u - lane)));
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t ostart = __shfl_down_sync(0xffffffffu, start, d);
+                    const bool take = (lane + d < 32u) && ostart == start;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const float o = __shfl_down_sync(0xffffffffu, w8[k], d);
+                        if (take) w8[k] = __fadd_rn(w8[k], o);
+                    }
+                }
+                head = on && start == lane;
+            }
+            if (head) {
                 float4 *p = reinterpret_cast<float4 *>(gt + (size_t)cs.row[i] * 8);
-                atomicAdd(p, make_float4(__fmul_rn(ww, g[0]), __fmul_rn(ww, g[1]), __fmul_rn(ww, g[2]), __fmul_rn(ww, g[3])));
-                atomicAdd(p + 1, make_float4(__fmul_rn(ww, g[4]), __fmul_rn(ww, g[5]), __fmul_rn(ww, g[6]), __fmul_rn(ww, g[7])));
+                atomicAdd(p, make_float4(w8[0], w8[1], w8[2], w8[3]));
+                atomicAdd(p + 1, make_float4(w8[4], w8[5], w8[6], w8[7]));
             }
         }
     }
