@@ -141,10 +141,11 @@ class TrainStep:
 
     def _pick_next(self, next_rays, n_samples: int, refresh_occupancy: bool):
         """the batch whose occupancy march may run ahead (nerfacc.Premarch), and the point of the stream from which it may.
-        Not before a step that refreshes the grid, and not with a rate term (its random entry sample would be drawn after
-        the next batch's jitter instead of before): in both cases the next step marches in line, and the order of random
-        draws -- hence every sample -- stays what it is without the look-ahead."""
-        if next_rays is None or (self.cm is not None and self.lmbda > 0):
+        Not before a step that refreshes the grid: that step marches in line.  The march itself is issued at the END of the
+        step (`_march_ahead`), i.e. after the rate term has drawn its random windows, so the order of random draws -- jitter
+        of batch t, windows of step t, jitter of batch t + 1 -- and hence every sample stays what it is without the
+        look-ahead (with `overlap_rate_term` the rate term runs first and the order is its own)."""
+        if next_rays is None:
             return None
         if refresh_occupancy and (self.step_id + 1) % self.occ_every == 0:
             return None
