@@ -567,15 +567,20 @@ class Premarch:
             _march_pass(args, fits, starts, t0, t1, ri, None)
             filled = torch.cuda.Event()
             filled.record()
-        self.pending = dict(key=(rays_o.data_ptr(), rays_d.data_ptr(), n, float(near_plane), float(far_plane), float(render_step_size),
-                                 bool(stratified), float(cone_angle), id(est.binaries)),
+        self.pending = dict(key=self._key(est, rays_o, rays_d, near_plane, far_plane, render_step_size, stratified, cone_angle),
                             args=args, starts=starts, cnt=cnt, bufs=(t0, t1, ri), counted=counted, filled=filled,
                             keep=(rays_o, rays_d))
 
+    @staticmethod
+    def _key(est, rays_o, rays_d, near_plane, far_plane, render_step_size, stratified, cone_angle):
+        """what a pending march was issued for: the ray tensors (storage address AND version counter: a batch written in
+        place into the same buffer is a different batch), their number, the march parameters, the grid object"""
+        return (rays_o.data_ptr(), rays_o._version, rays_d.data_ptr(), rays_d._version, int(rays_o.shape[0]), float(near_plane),
+                float(far_plane), float(render_step_size), bool(stratified), float(cone_angle), id(est.binaries), est.binaries._version)
+
     def matches(self, est, rays_o, rays_d, near_plane, far_plane, render_step_size, stratified, cone_angle) -> bool:
         p = self.pending
-        return p is not None and p["key"] == (rays_o.data_ptr(), rays_d.data_ptr(), rays_o.shape[0], float(near_plane), float(far_plane),
-                                              float(render_step_size), bool(stratified), float(cone_angle), id(est.binaries))
+        return p is not None and p["key"] == self._key(est, rays_o, rays_d, near_plane, far_plane, render_step_size, stratified, cone_angle)
 
     def drop(self) -> None:
         self.pending = None
