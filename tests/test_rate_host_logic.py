@@ -69,3 +69,30 @@ def test_fused_context_mlp_with_no_voxels():
     assert grads[0].shape == (0, 25)
     for g, p_ in zip(grads[1:], ps):
         assert g.shape == p_.shape and not g.any()
+
+
+def test_rows_gather_and_bits_sum_host_paths():
+    """the torch branches of `_RowsGather` (distinct rows: scatter backward) and `CNC_context_models._bits_sum` (CPU tensors
+    take the op-by-op Bernoulli_entropy) -- the CUDA branches are checked against these expressions in tests/test_gpu_codec.py"""
+    from cnc_b200.context_models import Bernoulli_entropy, _RowsGather
+
+    torch.manual_seed(1)
+    table = torch.randn(50, 8, dtype=torch.float64, requires_grad=True)
+    rows = torch.randperm(50)[:17]
+    out = _RowsGather.apply(table, rows)
+    assert torch.equal(out, table[rows])
+    w = torch.randn(17, 8, dtype=torch.float64)
+    (ga,) = torch.autograd.grad((out * w).sum(), table)
+    (gb,) = torch.autograd.grad((table[rows] * w).sum(), table)
+    assert torch.equal(ga, gb)
+    stub = types.SimpleNamespace(entropy_model=Bernoulli_entropy())
+    x = torch.where(torch.rand(9, 8) < 0.5, -1.0, 1.0)
+    p = torch.rand(9, 8)
+    got = CNC_context_models._bits_sum(stub, x, p)
+    torch.testing.assert_close(got, torch.sum(Bernoulli_entropy()(x, p)))
+
+
+def test_level_sums_binary_flag_is_ignored_off_the_gpu():
+    offs = [0, 8, 24]
+    q = torch.where(torch.rand(24, 8) < 0.4, -1.0, 1.0)
+    assert torch.equal(_LevelSums.apply(q, offs, True), _LevelSums.apply(q, offs, False))
