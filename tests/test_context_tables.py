@@ -104,3 +104,31 @@ def test_layout_rebuilds_identical_tables_in_a_fresh_object():
             assert torch.equal(a, b)
         assert cm2.skip_levels_3D == (0, 1) and cm2.res == cm.res
     assert isinstance(_small(shuffle_seed=3).layout()["shuffle_seed"], int)
+
+
+def test_data_parallel_share_of_the_sampled_entries_cpu():
+    """CNC_context_models.set_data_parallel: every rank's share of the sampled 3D entries (sample_num / world spread over the
+    levels like the single-process sample, at least one entry and at most the whole level), and the single-process setting"""
+    from cnc_b200.context_models import CNC_context_models
+
+    torch.manual_seed(0)
+    cm = CNC_context_models(num_dim=3, resolutions_list=[6, 10, 18, 34], resolutions_list_2D=[18, 34], log2_hashmap_size=12,
+                            log2_hashmap_size_2D=10, n_features=8, sample_num=800, ste_binary=True, Rb=16,
+                            skip_levels_3D=(0, 1, 2), device="cpu")
+    full = cm.sample_num_levels.clone()
+    for world in (2, 4, 8):
+        cm.set_data_parallel(world - 1, world)
+        snl, n_valid = cm._dp_snl
+        assert cm.dp_rank == world - 1 and cm.dp_world == world
+        assert (snl >= 1).all() and (snl <= cm.hashparams_num_levels).all()
+        assert abs(int(snl.sum()) * world - int(full.sum())) <= world * cm.n_levels      # the ranks together: the whole sample
+        coded = [n for n in range(cm.n_levels) if n not in cm.skip_levels_3D and n < cm.Pg_level]
+        assert n_valid == sum(int(snl[n]) for n in coded)
+    cm.set_data_parallel(0, 1)
+    assert cm._dp_snl is None and cm.dp_world == 1
+    # the plane terms dealt round-robin cover every coded (axis, level) exactly once over the ranks
+    coded_2D = [n for n in range(cm.n_levels_2D) if not (n in cm.skip_levels_2D or n >= cm.Pg_level_2D)]
+    terms = [(a, n) for a in ("xy", "xz", "yz") for n in coded_2D]
+    for world in (1, 2, 3, 8):
+        dealt = [{t for i, t in enumerate(terms) if i % world == r} for r in range(world)]
+        assert set().union(*dealt) == set(terms) and sum(len(d) for d in dealt) == len(terms)
